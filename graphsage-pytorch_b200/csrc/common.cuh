@@ -1,0 +1,102 @@
+// Shared device/host helpers for the gsage_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gsage_b200.h"
+
+namespace gs {
+
+constexpr int kWarp = 32;
+constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
+
+extern int64_t g_launches;     // counted on the host at every kernel launch (gs_launch_count)
+
+inline int finish_launch(int n = 1) {
+  g_launches += n;
+  cudaError_t e = cudaPeekAtLastError();
+  return e == cudaSuccess ? GS_OK : static_cast<int>(e);
+}
+
+inline cudaStream_t as_stream(gs_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+__device__ __forceinline__ int live_rows(const int32_t* num_rows_dev, int max_rows) {
+  if (num_rows_dev == nullptr) return max_rows;
+  int n = __ldg(num_rows_dev);
+  return n < max_rows ? n : max_rows;
+}
+
+// 128-bit read-only load that does not allocate in L1: gathered feature rows are touched
+// once per kernel, L1 residency only evicts the index lists.
+__device__ __forceinline__ float4 ldg_stream_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Philox4x32-10 (Salmon et al., SC'11).  ctr = 128-bit counter, key = 64-bit key.
+__host__ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t (&k)[2]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#ifdef __CUDA_ARCH__
+  uint32_t hi0 = __umulhi(M0, c[0]), hi1 = __umulhi(M1, c[2]);
+#else
+  uint32_t hi0 = static_cast<uint32_t>((static_cast<uint64_t>(M0) * c[0]) >> 32);
+  uint32_t hi1 = static_cast<uint32_t>((static_cast<uint64_t>(M1) * c[2]) >> 32);
+#endif
+  uint32_t lo0 = M0 * c[0], lo1 = M1 * c[2];
+  uint32_t n0 = hi1 ^ c[1] ^ k[0], n1 = lo1, n2 = hi0 ^ c[3] ^ k[1], n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+  k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u;
+}
+
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                       uint64_t key, uint32_t (&out)[4]) {
+  uint32_t c[4] = {c0, c1, c2, c3};
+  uint32_t k[2] = {static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32)};
+#pragma unroll
+  for (int i = 0; i < 10; ++i) philox_round(c, k);
+  out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+}
+
+// Stream of 32-bit draws for one (row, purpose): block b of the stream is
+// philox(ctr = {row, b, offset_lo, offset_hi}, key = seed).
+struct PhiloxStream {
+  uint32_t row, blk, off_lo, off_hi;
+  uint64_t key;
+  uint32_t buf[4];
+  int have;
+  __device__ PhiloxStream(uint64_t seed, uint64_t offset, uint32_t row_)
+      : row(row_), blk(0), off_lo(static_cast<uint32_t>(offset)), off_hi(static_cast<uint32_t>(offset >> 32)),
+        key(seed), have(0) {}
+  __device__ __forceinline__ uint32_t next() {
+    if (have == 0) {
+      philox4x32_10(row, blk++, off_lo, off_hi, key, buf);
+      have = 4;
+    }
+    return buf[4 - have--];
+  }
+  // uniform integer in [0, n)  (n >= 1), multiply-shift
+  __device__ __forceinline__ uint32_t below(uint32_t n) { return __umulhi(next(), n); }
+};
+
+}  // namespace gs

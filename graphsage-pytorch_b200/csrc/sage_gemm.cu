@@ -1,0 +1,303 @@
+// K4 SageLayer GEMM, fp32 SIMT path (GS_PREC_FP32): the 1e-5 parity mode.
+//
+// Replaces SageLayer.forward, src/models.py:215-219:  out = relu(W . cat[self, agg]^T)^T.
+// The concat is never materialised: the K loop walks a *virtual* operand
+//   X[r, :] = [ self_table[self_idx[r], 0:Dp) | agg[r, 0:Dp) ]        Dp = round_up(D, 4)
+// (gcn: X = agg only), reading the self rows straight from the previous layer's table
+// through the index list (the `pre_hidden_embs[nb]` gather of :265) and the aggregate from
+// K3's output.  Feature tables are stored with rows padded to Dp floats (zero filled), so
+// every operand load is a 128-bit load; the weight keeps its native [H x 2D] layout and a
+// virtual column kv maps to weight column kv (self part) or kv - Dp + D (agg part).
+//
+// Three kernels: forward (X.W^T, ReLU epilogue), bwd_x (dZ.W), bwd_w (dZ^T.X, split over
+// row chunks, accumulated with fp32 atomics).  dZ = grad_out * (out > 0) is applied while
+// the tile is loaded, so the ReLU backward never touches HBM on its own.
+// The tcgen05 tensor-core path lives in sage_gemm_tc.cu.
+#include "common.cuh"
+
+namespace gs {
+
+constexpr int BM = 64, BN = 64, BK = 16, kGemmThreads = 256, kPad = 4;
+
+struct XOperand {
+  const float* self_table; int64_t ld_self; const int32_t* self_idx;
+  const float* agg; int64_t ld_agg;
+  int dim, dim_pad, gcn;
+  __device__ __forceinline__ int kv_total() const { return gcn ? dim_pad : 2 * dim_pad; }
+  // weight column of virtual column kv, or -1 for a padding column
+  __device__ __forceinline__ int wcol(int kv) const {
+    if (kv < dim) return kv;
+    if (gcn) return -1;
+    const int k2 = kv - dim_pad;
+    return (k2 >= 0 && k2 < dim) ? dim + k2 : -1;
+  }
+  __device__ __forceinline__ float4 load4(int r, int self_row, int kv) const {
+    if (gcn) return *reinterpret_cast<const float4*>(agg + static_cast<int64_t>(r) * ld_agg + kv);
+    if (kv < dim_pad) return *reinterpret_cast<const float4*>(self_table + static_cast<int64_t>(self_row) * ld_self + kv);
+    return *reinterpret_cast<const float4*>(agg + static_cast<int64_t>(r) * ld_agg + (kv - dim_pad));
+  }
+};
+
+__device__ __forceinline__ void fma_tile(float (&acc)[4][4], const float* __restrict__ a_col, const float* __restrict__ b_col) {
+  const float4 a = *reinterpret_cast<const float4*>(a_col);
+  const float4 b = *reinterpret_cast<const float4*>(b_col);
+  const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+}
+
+// ---------------------------------------------------------------------------------------
+// forward: out[r,h] = act( sum_kv X[r,kv] * W[h, wcol(kv)] )
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kGemmThreads)
+sage_fwd_kernel(XOperand x, const float* __restrict__ weight, int64_t ldw, int out_dim,
+                const int32_t* __restrict__ num_rows_dev, int max_rows, float* __restrict__ out, int64_t ld_out, int relu) {
+  __shared__ __align__(16) float Xs[BK][BM + kPad];
+  __shared__ __align__(16) float Ws[BK][BN + kPad];
+  const int rows = live_rows(num_rows_dev, max_rows);
+  const int row0 = blockIdx.x * BM, col0 = blockIdx.y * BN;
+  if (row0 >= rows) return;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  // loader roles: X tile = 64 rows x 4 float4; W tile = 64 cols(h) x 16 k scalars
+  const int lx_row = tid >> 2, lx_kq = (tid & 3) * 4;
+  const int xr = row0 + lx_row;
+  const bool xr_ok = xr < rows;
+  const int self_row = (xr_ok && !x.gcn) ? (x.self_idx ? x.self_idx[xr] : xr) : 0;
+  const int lw_h = tid >> 2, lw_kq = (tid & 3) * 4;
+  const int wh = col0 + lw_h;
+  float acc[4][4] = {};
+  const int kt = x.kv_total();
+  for (int k0 = 0; k0 < kt; k0 += BK) {
+    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (xr_ok && k0 + lx_kq < kt) xv = x.load4(xr, self_row, k0 + lx_kq);
+    float wv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int kv = k0 + lw_kq + i;
+      const int wc = kv < kt ? x.wcol(kv) : -1;
+      wv[i] = (wc >= 0 && wh < out_dim) ? __ldg(weight + static_cast<int64_t>(wh) * ldw + wc) : 0.f;
+    }
+    __syncthreads();
+    Xs[lx_kq + 0][lx_row] = xv.x; Xs[lx_kq + 1][lx_row] = xv.y; Xs[lx_kq + 2][lx_row] = xv.z; Xs[lx_kq + 3][lx_row] = xv.w;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) Ws[lw_kq + i][lw_h] = wv[i];
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) fma_tile(acc, &Xs[kk][ty * 4], &Ws[kk][tx * 4]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = row0 + ty * 4 + i;
+    if (r >= rows) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int h = col0 + tx * 4 + j;
+      if (h < out_dim) out[static_cast<int64_t>(r) * ld_out + h] = relu ? fmaxf(acc[i][j], 0.f) : acc[i][j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// bwd_x: dX[r, c] = sum_h dZ[r,h] W[h,c]   (c over the native 2D / D weight columns)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kGemmThreads)
+sage_bwd_x_kernel(const float* __restrict__ grad_out, int64_t ld_go, const float* __restrict__ out, int64_t ld_out,
+                  const float* __restrict__ weight, int64_t ldw, int dim, int out_dim, int gcn, int relu,
+                  const int32_t* __restrict__ num_rows_dev, int max_rows,
+                  float* __restrict__ grad_self, int64_t ld_gs, float* __restrict__ grad_agg, int64_t ld_ga) {
+  __shared__ __align__(16) float As[BK][BM + kPad];   // dZ^T tile: [h][row]
+  __shared__ __align__(16) float Bs[BK][BN + kPad];   // W tile:    [h][col]
+  const int rows = live_rows(num_rows_dev, max_rows);
+  const int row0 = blockIdx.x * BM, col0 = blockIdx.y * BN;
+  if (row0 >= rows) return;
+  const int ncols = gcn ? dim : 2 * dim;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int la_row = tid >> 2, la_hq = (tid & 3) * 4;          // dZ: 64 rows x 16 h
+  const int lb_h = tid >> 4, lb_c = (tid & 15) * 4;            // W : 16 h x 64 cols
+  const int ar = row0 + la_row;
+  float acc[4][4] = {};
+  for (int h0 = 0; h0 < out_dim; h0 += BK) {
+    float av[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int h = h0 + la_hq + i;
+      float g = 0.f;
+      if (ar < rows && h < out_dim) {
+        g = grad_out[static_cast<int64_t>(ar) * ld_go + h];
+        if (relu && !(out[static_cast<int64_t>(ar) * ld_out + h] > 0.f)) g = 0.f;
+      }
+      av[i] = g;
+    }
+    float bv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int h = h0 + lb_h, c = col0 + lb_c + j;
+      bv[j] = (h < out_dim && c < ncols) ? __ldg(weight + static_cast<int64_t>(h) * ldw + c) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) As[la_hq + i][la_row] = av[i];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Bs[lb_h][lb_c + j] = bv[j];
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) fma_tile(acc, &As[kk][ty * 4], &Bs[kk][tx * 4]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = row0 + ty * 4 + i;
+    if (r >= rows) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = col0 + tx * 4 + j;
+      if (c >= ncols) continue;
+      if (gcn) grad_agg[static_cast<int64_t>(r) * ld_ga + c] = acc[i][j];
+      else if (c < dim) grad_self[static_cast<int64_t>(r) * ld_gs + c] = acc[i][j];
+      else grad_agg[static_cast<int64_t>(r) * ld_ga + (c - dim)] = acc[i][j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// bwd_w: dW[h, wcol(kv)] += sum_{r in chunk} dZ[r,h] X[r,kv]
+// grid = (kv tiles, h tiles, row chunks); each CTA reduces `rows_per_chunk` rows.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kGemmThreads)
+sage_bwd_w_kernel(XOperand x, const float* __restrict__ grad_out, int64_t ld_go, const float* __restrict__ out,
+                  int64_t ld_out, int out_dim, int relu, const int32_t* __restrict__ num_rows_dev, int max_rows,
+                  int rows_per_chunk, float* __restrict__ grad_w, int64_t ldw) {
+  __shared__ __align__(16) float As[BK][BM + kPad];   // dZ tile: [row][h]
+  __shared__ __align__(16) float Bs[BK][BN + kPad];   // X tile : [row][kv]
+  const int rows = live_rows(num_rows_dev, max_rows);
+  const int kv0 = blockIdx.x * BN, h0 = blockIdx.y * BM;
+  const int r_begin = blockIdx.z * rows_per_chunk;
+  const int r_end = min(rows, r_begin + rows_per_chunk);
+  if (r_begin >= r_end) return;
+  const int kt = x.kv_total();
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int l_row = tid >> 4, l_q = (tid & 15) * 4;            // 16 rows x 16 float4
+  float acc[4][4] = {};
+  for (int r0 = r_begin; r0 < r_end; r0 += BK) {
+    const int r = r0 + l_row;
+    float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = av;
+    if (r < r_end) {
+      float g[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int h = h0 + l_q + i;
+        g[i] = 0.f;
+        if (h < out_dim) {
+          g[i] = grad_out[static_cast<int64_t>(r) * ld_go + h];
+          if (relu && !(out[static_cast<int64_t>(r) * ld_out + h] > 0.f)) g[i] = 0.f;
+        }
+      }
+      av = make_float4(g[0], g[1], g[2], g[3]);
+      const int kv = kv0 + l_q;
+      if (kv < kt) {
+        const int self_row = x.gcn ? 0 : (x.self_idx ? x.self_idx[r] : r);
+        bv = x.load4(r, self_row, kv);
+      }
+    }
+    __syncthreads();
+    *reinterpret_cast<float4*>(&As[l_row][l_q]) = av;
+    *reinterpret_cast<float4*>(&Bs[l_row][l_q]) = bv;
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) fma_tile(acc, &As[kk][ty * 4], &Bs[kk][tx * 4]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int h = h0 + ty * 4 + i;
+    if (h >= out_dim) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int kv = kv0 + tx * 4 + j;
+      const int wc = kv < kt ? x.wcol(kv) : -1;
+      if (wc >= 0) atomicAdd(grad_w + static_cast<int64_t>(h) * ldw + wc, acc[i][j]);
+    }
+  }
+}
+
+static int check_x(const float* self_table, int64_t ld_self, const float* agg, int64_t ld_agg, int dim, int gcn) {
+  if (!agg || dim < 1) return GS_ERR_BAD_ARG;
+  const int dp = (dim + 3) & ~3;
+  if ((ld_agg & 3) || ld_agg < dp || !aligned16(agg)) return GS_ERR_ALIGNMENT;
+  if (!gcn) {
+    if (!self_table) return GS_ERR_BAD_ARG;
+    if ((ld_self & 3) || ld_self < dp || !aligned16(self_table)) return GS_ERR_ALIGNMENT;
+  }
+  return GS_OK;
+}
+
+}  // namespace gs
+
+using namespace gs;
+
+int gs_sage_gemm_fwd_tc(const float*, int64_t, const int32_t*, const float*, int64_t, int32_t, const float*, int64_t,
+                        int32_t, int32_t, const int32_t*, int32_t, float*, int64_t, int32_t, int32_t, gs_stream_t);
+
+extern "C" int gs_sage_gemm_fwd(const float* self_table, int64_t ld_self, const int32_t* self_idx,
+                                const float* agg, int64_t ld_agg, int32_t dim,
+                                const float* weight, int64_t ldw, int32_t out_dim, int32_t gcn,
+                                const int32_t* num_rows_dev, int32_t max_rows,
+                                float* out, int64_t ld_out, int32_t relu, int32_t precision, gs_stream_t stream) {
+  if (!weight || !out || out_dim < 1 || max_rows < 0) return GS_ERR_BAD_ARG;
+  if (int e = check_x(self_table, ld_self, agg, ld_agg, dim, gcn)) return e;
+  if (ldw < (gcn ? dim : 2 * dim) || ld_out < out_dim) return GS_ERR_BAD_ARG;
+  if (max_rows == 0) return GS_OK;
+  if (precision != GS_PREC_FP32)
+    return gs_sage_gemm_fwd_tc(self_table, ld_self, self_idx, agg, ld_agg, dim, weight, ldw, out_dim, gcn,
+                               num_rows_dev, max_rows, out, ld_out, relu, precision, stream);
+  XOperand x{self_table, ld_self, self_idx, agg, ld_agg, dim, (dim + 3) & ~3, gcn};
+  dim3 grid((max_rows + BM - 1) / BM, (out_dim + BN - 1) / BN);
+  sage_fwd_kernel<<<grid, kGemmThreads, 0, as_stream(stream)>>>(x, weight, ldw, out_dim, num_rows_dev, max_rows, out,
+                                                                ld_out, relu);
+  return finish_launch();
+}
+
+extern "C" int gs_sage_gemm_bwd_x(const float* grad_out, int64_t ld_go, const float* out, int64_t ld_out,
+                                  const float* weight, int64_t ldw, int32_t dim, int32_t out_dim, int32_t gcn,
+                                  int32_t relu, const int32_t* num_rows_dev, int32_t max_rows,
+                                  float* grad_self, int64_t ld_gs, float* grad_agg, int64_t ld_ga, gs_stream_t stream) {
+  if (!grad_out || !weight || !grad_agg || dim < 1 || out_dim < 1 || max_rows < 0) return GS_ERR_BAD_ARG;
+  if (relu && !out) return GS_ERR_BAD_ARG;
+  if (!gcn && !grad_self) return GS_ERR_BAD_ARG;
+  if (ld_ga < dim || (!gcn && ld_gs < dim) || ldw < (gcn ? dim : 2 * dim)) return GS_ERR_BAD_ARG;
+  if (max_rows == 0) return GS_OK;
+  const int ncols = gcn ? dim : 2 * dim;
+  dim3 grid((max_rows + BM - 1) / BM, (ncols + BN - 1) / BN);
+  sage_bwd_x_kernel<<<grid, kGemmThreads, 0, as_stream(stream)>>>(grad_out, ld_go, out, ld_out, weight, ldw, dim,
+                                                                  out_dim, gcn, relu, num_rows_dev, max_rows,
+                                                                  grad_self, ld_gs, grad_agg, ld_ga);
+  return finish_launch();
+}
+
+extern "C" int gs_sage_gemm_bwd_w(const float* self_table, int64_t ld_self, const int32_t* self_idx,
+                                  const float* agg, int64_t ld_agg, int32_t dim,
+                                  const float* grad_out, int64_t ld_go, const float* out, int64_t ld_out,
+                                  int32_t out_dim, int32_t gcn, int32_t relu,
+                                  const int32_t* num_rows_dev, int32_t max_rows,
+                                  float* grad_w, int64_t ldw, gs_stream_t stream) {
+  if (!grad_out || !grad_w || out_dim < 1 || max_rows < 0) return GS_ERR_BAD_ARG;
+  if (relu && !out) return GS_ERR_BAD_ARG;
+  if (int e = check_x(self_table, ld_self, agg, ld_agg, dim, gcn)) return e;
+  if (ldw < (gcn ? dim : 2 * dim)) return GS_ERR_BAD_ARG;
+  if (max_rows == 0) return GS_OK;
+  XOperand x{self_table, ld_self, self_idx, agg, ld_agg, dim, (dim + 3) & ~3, gcn};
+  const int kt = gcn ? x.dim_pad : 2 * x.dim_pad;
+  const int tiles = ((kt + BN - 1) / BN) * ((out_dim + BM - 1) / BM);
+  // enough row chunks to fill the machine (~2 CTAs per SM), at least 64 rows per chunk
+  int chunks = (2 * kNumSMs + tiles - 1) / tiles;
+  const int max_chunks = (max_rows + 63) / 64;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  int rows_per_chunk = (max_rows + chunks - 1) / chunks;
+  rows_per_chunk = ((rows_per_chunk + BK - 1) / BK) * BK;
+  chunks = (max_rows + rows_per_chunk - 1) / rows_per_chunk;
+  dim3 grid((kt + BN - 1) / BN, (out_dim + BM - 1) / BM, chunks);
+  sage_bwd_w_kernel<<<grid, kGemmThreads, 0, as_stream(stream)>>>(x, grad_out, ld_go, out, ld_out, out_dim, relu,
+                                                                  num_rows_dev, max_rows, rows_per_chunk, grad_w, ldw);
+  return finish_launch();
+}

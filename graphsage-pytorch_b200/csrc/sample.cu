@@ -1,0 +1,286 @@
+// K1 neighbour sampler, K5 random-walk positives and negative sampler.
+// Integer / index work, HBM-latency bound; no tensor cores by design.
+#include "common.cuh"
+
+namespace gs {
+
+// ---------------------------------------------------------------------------------------
+// K1: one thread per destination row.  Replaces src/models.py:279-285.
+//   deg <  k : every neighbour                       (:282 else-branch)
+//   deg >= k : k distinct uniform positions, Floyd's subset sampling: for j in deg-k..deg-1
+//              draw t in [0,j]; take t unless already taken, else take j.  Every k-subset
+//              is equally likely, which is what random.sample gives.
+// The row is then sorted ascending and the node's own id is dropped / inserted once
+// according to self_mode (the `| {self}` of :285 and the `- {self}` of :298).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+sample_neighbors_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t num_nodes,
+                        const int32_t* __restrict__ nodes, const int32_t* __restrict__ num_rows_dev, int max_rows,
+                        int k, int stride, int self_mode, uint64_t seed, uint64_t offset,
+                        const int64_t* __restrict__ offset_dev,
+                        int32_t* __restrict__ out_nbr, int32_t* __restrict__ out_cnt) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int rows = live_rows(num_rows_dev, max_rows);
+  if (r >= max_rows) return;
+  int32_t* dst = out_nbr + static_cast<int64_t>(r) * stride;
+  if (r >= rows) {           // keep the padding region well defined for the consumers
+    for (int j = 0; j < stride; ++j) dst[j] = -1;
+    out_cnt[r] = 0;
+    return;
+  }
+  const int32_t me = nodes[r];
+  int32_t sel[GS_MAX_FANOUT + 1];
+  int m = 0;
+  if (me >= 0 && me < num_nodes) {
+    const int64_t beg = rowptr[me];
+    const int64_t deg64 = rowptr[me + 1] - beg;
+    const uint32_t deg = static_cast<uint32_t>(deg64);
+    if (deg < static_cast<uint32_t>(k)) {
+      for (uint32_t j = 0; j < deg; ++j) sel[m++] = col[beg + j];
+    } else {
+      if (offset_dev != nullptr) offset += static_cast<uint64_t>(__ldg(offset_dev)) << 8;
+      PhiloxStream rng(seed, offset, static_cast<uint32_t>(r));
+      uint32_t pos[GS_MAX_FANOUT];
+      for (uint32_t j = deg - k; j < deg; ++j) {
+        uint32_t t = rng.below(j + 1);
+        bool taken = false;
+        for (int q = 0; q < m; ++q) taken |= (pos[q] == t);
+        pos[m++] = taken ? j : t;
+      }
+      for (int q = 0; q < m; ++q) sel[q] = col[beg + pos[q]];
+    }
+  }
+  // insertion sort (m <= 32) ascending by node id
+  for (int a = 1; a < m; ++a) {
+    int32_t v = sel[a];
+    int b = a - 1;
+    while (b >= 0 && sel[b] > v) { sel[b + 1] = sel[b]; --b; }
+    sel[b + 1] = v;
+  }
+  if (self_mode != GS_SELF_KEEP) {
+    int w = 0;
+    for (int q = 0; q < m; ++q) if (sel[q] != me) sel[w++] = sel[q];
+    m = w;
+    if (self_mode == GS_SELF_ONCE) {
+      int b = m - 1;
+      while (b >= 0 && sel[b] > me) { sel[b + 1] = sel[b]; --b; }
+      sel[b + 1] = me;
+      ++m;
+    }
+  }
+  for (int j = 0; j < stride; ++j) dst[j] = j < m ? sel[j] : -1;
+  out_cnt[r] = m;
+}
+
+// ---------------------------------------------------------------------------------------
+// K5a: positives.  src/models.py:169-186.  One thread per (seed, walk).
+// ---------------------------------------------------------------------------------------
+__global__ void random_walk_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                   int64_t num_nodes, const int32_t* __restrict__ seeds, int num_seeds, int n_walks,
+                                   int walk_len, const uint8_t* __restrict__ is_train, uint64_t seed, uint64_t offset,
+                                   int32_t* __restrict__ pos) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= num_seeds * n_walks) return;
+  const int s = t / n_walks;
+  const int32_t start = seeds[s];
+  int32_t* dst = pos + static_cast<int64_t>(t) * walk_len;
+  PhiloxStream rng(seed, offset, static_cast<uint32_t>(t));
+  int32_t cur = start;
+  bool dead = !(start >= 0 && start < num_nodes) || (rowptr[start + 1] == rowptr[start]);   // :171-172
+  for (int step = 0; step < walk_len; ++step) {
+    int32_t out = -1;
+    if (!dead) {
+      const int64_t beg = rowptr[cur];
+      const uint32_t deg = static_cast<uint32_t>(rowptr[cur + 1] - beg);
+      if (deg == 0) {
+        dead = true;
+      } else {
+        const int32_t nxt = col[beg + rng.below(deg)];                                     // :178
+        if (nxt != start && is_train[nxt]) out = nxt;                                      // :180
+        cur = nxt;
+      }
+    }
+    dst[step] = out;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K5b: negatives.  src/models.py:153-167.  One CTA per seed.
+//   1. level-synchronous BFS for `hops` levels over the full adjacency, visited set kept as
+//      a bitmap of num_nodes bits, frontiers as two id queues (all in `workspace`).
+//   2. far = train nodes whose bit is clear; |far| counted by the CTA.
+//   3. num_neg distinct ranks in [0,|far|) by Floyd's algorithm (thread 0), then the CTA
+//      walks the train list again and emits the nodes holding those ranks.
+// ---------------------------------------------------------------------------------------
+constexpr int kNegThreads = 256;
+
+__global__ void __launch_bounds__(kNegThreads)
+negative_sample_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t num_nodes,
+                       const int32_t* __restrict__ seeds, int hops, int num_neg,
+                       const int32_t* __restrict__ train_nodes, int num_train, uint64_t seed, uint64_t offset,
+                       int32_t* __restrict__ neg, int32_t* __restrict__ neg_cnt, uint32_t* __restrict__ workspace) {
+  const int s = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kNegThreads / 32;
+  const int64_t words = (num_nodes + 31) / 32;
+  const int64_t per_seed = words + 2 * num_nodes;
+  uint32_t* bitmap = workspace + s * per_seed;
+  int32_t* queue_a = reinterpret_cast<int32_t*>(bitmap + words);
+  int32_t* queue_b = queue_a + num_nodes;
+  __shared__ int s_cur, s_next, s_far;
+  __shared__ uint32_t s_rank[GS_MAX_FANOUT * 4];
+  __shared__ int s_scan[kNegThreads];
+
+  for (int64_t w = tid; w < words; w += kNegThreads) bitmap[w] = 0u;
+  const int32_t me = seeds[s];
+  if (tid == 0) { s_cur = 0; s_next = 0; }
+  __syncthreads();
+  if (tid == 0 && me >= 0 && me < num_nodes) {
+    bitmap[me >> 5] |= 1u << (me & 31);
+    queue_a[0] = me;
+    s_cur = 1;
+  }
+  __syncthreads();
+  int32_t* cur_q = queue_a;
+  int32_t* next_q = queue_b;
+  for (int hop = 0; hop < hops; ++hop) {
+    const int n_cur = s_cur;
+    if (n_cur == 0) break;
+    for (int i = warp; i < n_cur; i += nwarps) {
+      const int32_t v = cur_q[i];
+      const int64_t beg = rowptr[v], end = rowptr[v + 1];
+      for (int64_t e = beg + lane; e < end; e += 32) {
+        const int32_t u = col[e];
+        const uint32_t bit = 1u << (u & 31);
+        const uint32_t old = atomicOr(&bitmap[u >> 5], bit);
+        if (!(old & bit)) next_q[atomicAdd(&s_next, 1)] = u;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) { s_cur = s_next; s_next = 0; }
+    int32_t* t = cur_q; cur_q = next_q; next_q = t;
+    __syncthreads();
+  }
+  __threadfence_block();
+  // count far train nodes
+  int mine = 0;
+  for (int i = tid; i < num_train; i += kNegThreads) {
+    const int32_t v = train_nodes[i];
+    mine += !((bitmap[v >> 5] >> (v & 31)) & 1u);
+  }
+  if (tid == 0) s_far = 0;
+  __syncthreads();
+  mine = __reduce_add_sync(0xffffffffu, mine);
+  if (lane == 0) atomicAdd(&s_far, mine);
+  __syncthreads();
+  const int far = s_far;
+  const int take = far < num_neg ? far : num_neg;     // :164  (all of them when too few)
+  if (tid == 0) {
+    if (far > num_neg) {
+      PhiloxStream rng(seed, offset, static_cast<uint32_t>(s));
+      int m = 0;
+      for (uint32_t j = far - num_neg; j < static_cast<uint32_t>(far); ++j) {
+        uint32_t t = rng.below(j + 1);
+        bool taken = false;
+        for (int q = 0; q < m; ++q) taken |= (s_rank[q] == t);
+        s_rank[m++] = taken ? j : t;
+      }
+      // ascending ranks so the output order is deterministic
+      for (int a = 1; a < m; ++a) {
+        uint32_t v = s_rank[a];
+        int b = a - 1;
+        while (b >= 0 && s_rank[b] > v) { s_rank[b + 1] = s_rank[b]; --b; }
+        s_rank[b + 1] = v;
+      }
+    }
+    neg_cnt[s] = take;
+  }
+  __syncthreads();
+  // second walk over the train list in chunks of kNegThreads with a block scan of the
+  // "is far" flags to recover each far node's rank.
+  int32_t* dst = neg + static_cast<int64_t>(s) * num_neg;
+  for (int i = tid; i < num_neg; i += kNegThreads) dst[i] = -1;
+  __syncthreads();
+  int base = 0;
+  for (int chunk = 0; chunk < num_train; chunk += kNegThreads) {
+    const int i = chunk + tid;
+    int32_t v = -1;
+    int flag = 0;
+    if (i < num_train) {
+      v = train_nodes[i];
+      flag = !((bitmap[v >> 5] >> (v & 31)) & 1u);
+    }
+    s_scan[tid] = flag;
+    __syncthreads();
+    for (int o = 1; o < kNegThreads; o <<= 1) {          // Hillis-Steele inclusive scan
+      int add = tid >= o ? s_scan[tid - o] : 0;
+      __syncthreads();
+      s_scan[tid] += add;
+      __syncthreads();
+    }
+    const int rank = base + s_scan[tid] - flag;
+    if (flag) {
+      if (far <= num_neg) {
+        dst[rank] = v;
+      } else {
+        int lo = 0, hi = num_neg;                        // binary search in the sorted rank list
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (s_rank[mid] < static_cast<uint32_t>(rank)) lo = mid + 1; else hi = mid; }
+        if (lo < num_neg && s_rank[lo] == static_cast<uint32_t>(rank)) dst[lo] = v;
+      }
+    }
+    base += s_scan[kNegThreads - 1];
+    __syncthreads();
+  }
+}
+
+}  // namespace gs
+
+using namespace gs;
+
+extern "C" int gs_sample_neighbors(const int64_t* rowptr, const int32_t* col, int64_t num_nodes,
+                                   const int32_t* nodes, const int32_t* num_rows_dev, int32_t max_rows,
+                                   int32_t k, int32_t stride, int32_t self_mode, uint64_t seed, uint64_t offset,
+                                   const int64_t* offset_dev, int32_t* out_nbr, int32_t* out_cnt, gs_stream_t stream) {
+  if (!rowptr || !col || !nodes || !out_nbr || !out_cnt) return GS_ERR_BAD_ARG;
+  if (k < 1 || k > GS_MAX_FANOUT || max_rows < 0) return GS_ERR_BAD_ARG;
+  if (stride < k + (self_mode == GS_SELF_ONCE ? 1 : 0)) return GS_ERR_BAD_ARG;
+  if (self_mode < GS_SELF_KEEP || self_mode > GS_SELF_ONCE) return GS_ERR_BAD_ARG;
+  if (max_rows == 0) return GS_OK;
+  const int threads = 128;
+  sample_neighbors_kernel<<<(max_rows + threads - 1) / threads, threads, 0, as_stream(stream)>>>(
+      rowptr, col, num_nodes, nodes, num_rows_dev, max_rows, k, stride, self_mode, seed, offset, offset_dev, out_nbr,
+      out_cnt);
+  return finish_launch();
+}
+
+extern "C" int gs_random_walk_pos(const int64_t* rowptr, const int32_t* col, int64_t num_nodes,
+                                  const int32_t* seeds, int32_t num_seeds, int32_t n_walks, int32_t walk_len,
+                                  const uint8_t* is_train, uint64_t seed, uint64_t offset, int32_t* pos,
+                                  gs_stream_t stream) {
+  if (!rowptr || !col || !seeds || !is_train || !pos) return GS_ERR_BAD_ARG;
+  if (num_seeds < 0 || n_walks < 1 || walk_len < 1) return GS_ERR_BAD_ARG;
+  if (num_seeds == 0) return GS_OK;
+  const int total = num_seeds * n_walks, threads = 128;
+  random_walk_kernel<<<(total + threads - 1) / threads, threads, 0, as_stream(stream)>>>(
+      rowptr, col, num_nodes, seeds, num_seeds, n_walks, walk_len, is_train, seed, offset, pos);
+  return finish_launch();
+}
+
+extern "C" size_t gs_negative_workspace_bytes(int64_t num_nodes, int32_t num_seeds) {
+  const int64_t words = (num_nodes + 31) / 32;
+  return static_cast<size_t>(num_seeds) * static_cast<size_t>(words + 2 * num_nodes) * sizeof(uint32_t);
+}
+
+extern "C" int gs_negative_sample(const int64_t* rowptr, const int32_t* col, int64_t num_nodes,
+                                  const int32_t* seeds, int32_t num_seeds, int32_t hops, int32_t num_neg,
+                                  const int32_t* train_nodes, int32_t num_train, uint64_t seed, uint64_t offset,
+                                  int32_t* neg, int32_t* neg_cnt, void* workspace, size_t workspace_bytes,
+                                  gs_stream_t stream) {
+  if (!rowptr || !col || !seeds || !train_nodes || !neg || !neg_cnt || !workspace) return GS_ERR_BAD_ARG;
+  if (num_neg < 1 || num_neg > GS_MAX_FANOUT * 4 || hops < 0 || num_seeds < 0 || num_train < 0) return GS_ERR_BAD_ARG;
+  if (workspace_bytes < gs_negative_workspace_bytes(num_nodes, num_seeds)) return GS_ERR_WORKSPACE;
+  if (num_seeds == 0) return GS_OK;
+  negative_sample_kernel<<<num_seeds, kNegThreads, 0, as_stream(stream)>>>(
+      rowptr, col, num_nodes, seeds, hops, num_neg, train_nodes, num_train, seed, offset, neg, neg_cnt,
+      static_cast<uint32_t*>(workspace));
+  return finish_launch();
+}

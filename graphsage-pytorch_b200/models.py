@@ -1,0 +1,571 @@
+"""Drop-in for the reference's `src/models.py`: GraphSage, SageLayer, Classification,
+UnsupervisedLoss with the same constructor / forward signatures, attribute names and
+state_dict keys (`sage_layer{i}.weight`, `layer.0.weight`, `layer.0.bias`), so the
+reference's own training loop (`src/utils.py`) runs against these classes unchanged.
+
+Everything numerical happens in hand-written sm_100a kernels behind the C ABI of
+include/gsage_b200.h (see ops.py / native.py).  There is no CPU path: a model whose
+tensors are not on a CUDA device raises.  Reference lines are cited per method.
+"""
+from __future__ import annotations
+
+import weakref
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import native, ops
+from .graph import AdjCSR, DeviceCSR, adj_to_csr
+
+_PRECISIONS = {"fp32": native.PREC_FP32, "tf32": native.PREC_TF32, "tf32x3": native.PREC_TF32X3}
+
+# One device CSR per adjacency object (GraphSage and UnsupervisedLoss receive the same dict,
+# src/main.py:54,61): id(adj) -> (weakref-or-strong ref, DeviceCSR)
+_CSR_CACHE: Dict[tuple, tuple] = {}
+
+
+def _device_csr(adj_lists, num_nodes: Optional[int], device) -> DeviceCSR:
+    key = (id(adj_lists), str(device))
+    hit = _CSR_CACHE.get(key)
+    if hit is not None and hit[0] is adj_lists and (num_nodes is None or hit[1].num_nodes == num_nodes):
+        return hit[1]
+    if num_nodes is None:
+        if isinstance(adj_lists, AdjCSR):
+            num_nodes = adj_lists.num_nodes
+        else:
+            hi = -1
+            for node, nbrs in adj_lists.items():
+                hi = max(hi, int(node), max(nbrs) if nbrs else -1)
+            num_nodes = int(hi) + 1
+    csr = DeviceCSR.from_adj(adj_lists, num_nodes, device)
+    _CSR_CACHE[key] = (adj_lists, csr)
+    if len(_CSR_CACHE) > 8:
+        _CSR_CACHE.pop(next(iter(_CSR_CACHE)))
+    return csr
+
+
+def _as_device_ids(nodes, device) -> torch.Tensor:
+    """numpy int64 array (src/utils.py:149), python list (src/utils.py:67) or tensor -> int32 on device."""
+    if isinstance(nodes, torch.Tensor):
+        return nodes.to(device=device, dtype=torch.int32, non_blocking=True).contiguous()
+    arr = np.ascontiguousarray(np.asarray(nodes), dtype=np.int32)
+    return torch.from_numpy(arr).to(device, non_blocking=True)
+
+
+def _padded_table(x: torch.Tensor) -> torch.Tensor:
+    """fp32, contiguous, rows padded with zeros to a multiple of 4 floats (128-bit loads)."""
+    x = x.detach()
+    if x.dtype != torch.float32:
+        x = x.float()
+    f = x.shape[1]
+    if f % 4:
+        x = F.pad(x, (0, 4 - f % 4))
+    return x.contiguous()
+
+
+# ================================================================================================
+# Classification                                                       src/models.py:8-27
+# ================================================================================================
+class _ClassifyFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, embeds, weight, bias):
+        emb = _padded_table(embeds) if (embeds.shape[1] % 4 or not embeds.is_contiguous()
+                                        or embeds.dtype != torch.float32) else embeds.detach()
+        w = weight.detach().contiguous()
+        b = bias.detach().contiguous() if bias is not None else None
+        logp = ops.cls_fwd(emb, embeds.shape[1], w, b, w.shape[0])
+        ctx.save_for_backward(emb, w, logp)
+        ctx.has_bias = bias is not None
+        ctx.dim = embeds.shape[1]
+        return logp
+
+    @staticmethod
+    def backward(ctx, grad_logp):
+        emb, w, logp = ctx.saved_tensors
+        need_e, need_w, need_b = ctx.needs_input_grad
+        dim = ctx.dim
+        grad_emb = torch.empty_like(emb) if need_e else None
+        grad_w = torch.zeros_like(w) if need_w else None
+        grad_b = torch.zeros((w.shape[0],), dtype=torch.float32, device=w.device) if (need_b and ctx.has_bias) else None
+        ops.cls_bwd(grad_logp.contiguous(), logp, emb, dim, w, w.shape[0], grad_emb, grad_w, grad_b)
+        if grad_emb is not None and grad_emb.shape[1] != dim:
+            grad_emb = grad_emb[:, :dim]
+        return grad_emb, grad_w, grad_b
+
+
+class Classification(nn.Module):
+    """log_softmax(Linear(emb_size -> num_classes)); src/models.py:8-27."""
+
+    def __init__(self, emb_size, num_classes):
+        super().__init__()
+        self.layer = nn.Sequential(nn.Linear(emb_size, num_classes))        # :14-17
+        self.init_params()
+
+    def init_params(self):                                                   # :20-23
+        for param in self.parameters():
+            if len(param.size()) == 2:
+                nn.init.xavier_uniform_(param)
+
+    def forward(self, embeds):                                               # :25-27
+        lin = self.layer[0]
+        native.require_cuda(lin.weight, "Classification parameters")
+        return _ClassifyFn.apply(embeds, lin.weight, lin.bias)
+
+
+# ================================================================================================
+# SageLayer                                                            src/models.py:189-220
+# ================================================================================================
+class _SageLayerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, self_feats, agg_feats, weight, gcn, precision):
+        dim = agg_feats.shape[1]
+        agg = _padded_table(agg_feats)
+        selff = None if gcn else _padded_table(self_feats)
+        w = weight.detach().contiguous()
+        rows, out_dim = agg.shape[0], w.shape[0]
+        out = ops.sage_gemm_fwd(selff, None, agg, dim, w, out_dim, gcn, None, rows, True, precision)
+        ctx.save_for_backward(selff, agg, w, out)
+        ctx.gcn, ctx.dim = gcn, dim
+        return out[:, :out_dim] if out.shape[1] != out_dim else out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        selff, agg, w, out = ctx.saved_tensors
+        gcn, dim = ctx.gcn, ctx.dim
+        rows, out_dim = agg.shape[0], w.shape[0]
+        g = _padded_table(grad_out)
+        need_s, need_a, need_w = ctx.needs_input_grad[:3]
+        grad_w = None
+        if need_w:
+            grad_w = torch.zeros_like(w)
+            ops.sage_gemm_bwd_w(selff, None, agg, dim, g, out, out_dim, gcn, True, None, rows, grad_w)
+        gs = ga = None
+        if need_a or (need_s and not gcn):
+            gs, ga = ops.sage_gemm_bwd_x(g, out, w, dim, out_dim, gcn, True, None, rows)
+            ga = ga[:, :dim]
+            gs = gs[:, :dim] if gs is not None else None
+        return gs, ga, grad_w, None, None
+
+
+class SageLayer(nn.Module):
+    """relu(W . cat[self, agg]^T)^T ; src/models.py:189-220 (no bias, ReLU on every layer)."""
+
+    def __init__(self, input_size, out_size, gcn=False, precision: str = "fp32"):
+        super().__init__()
+        self.input_size = input_size
+        self.out_size = out_size
+        self.gcn = gcn
+        self.precision = precision
+        self.weight = nn.Parameter(torch.empty(out_size, self.input_size if self.gcn else 2 * self.input_size))   # :201
+        self.init_params()
+
+    def init_params(self):                                                   # :205-207
+        for param in self.parameters():
+            nn.init.xavier_uniform_(param)
+
+    def forward(self, self_feats, aggregate_feats, neighs=None):             # :209-220
+        native.require_cuda(self.weight, "SageLayer.weight")
+        return _SageLayerFn.apply(self_feats, aggregate_feats, self.weight, self.gcn, _PRECISIONS[self.precision])
+
+
+# ================================================================================================
+# GraphSage                                                            src/models.py:222-330
+# ================================================================================================
+class _Frontier:
+    """Per-layer device state of one forward pass (rows = destination nodes of that layer)."""
+    __slots__ = ("nodes", "num_rows", "rows_max", "stride", "nbr", "cnt", "nbr_idx", "self_idx", "agg", "argmax", "h",
+                 "table_in", "dim_in")
+
+
+class _GraphSageFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, nodes_dev, injected, *weights):
+        layers = model._run_forward(nodes_dev, [w.detach() for w in weights], injected)
+        ctx.model, ctx.layers = model, layers
+        ctx.save_for_backward(*weights)
+        h = layers[-1].h
+        model._last_layers = layers
+        return h[:, :model.out_size] if h.shape[1] != model.out_size else h
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        weights = [w.detach() for w in ctx.saved_tensors]
+        grads = ctx.model._run_backward(ctx.layers, grad_out, weights, ctx.needs_input_grad[3:])
+        return (None, None, None, *grads)
+
+
+class GraphSage(nn.Module):
+    """Same constructor and forward as src/models.py:224,241.  Extra keyword arguments
+    (`num_sample`, `precision`, `seed`) default to the reference's behaviour."""
+
+    def __init__(self, num_layers, input_size, out_size, raw_features, adj_lists, device, gcn=False, agg_func='MEAN',
+                 *, num_sample: int = 10, precision: str = "fp32", seed: Optional[int] = None):
+        super().__init__()
+        if agg_func not in ('MEAN', 'MAX'):
+            raise ValueError("agg_func must be 'MEAN' or 'MAX' (src/models.py:311,316)")
+        if precision not in _PRECISIONS:
+            raise ValueError(f"precision must be one of {list(_PRECISIONS)}")
+        if not 1 <= num_sample <= native.MAX_FANOUT:
+            raise ValueError(f"num_sample must be in 1..{native.MAX_FANOUT}")
+        self.input_size = input_size
+        self.out_size = out_size
+        self.num_layers = num_layers
+        self.gcn = gcn
+        self.device = device
+        self.agg_func = agg_func
+        self.num_sample = num_sample          # src/models.py:277 default argument
+        self.precision = precision
+        self.raw_features = raw_features      # :234
+        self.adj_lists = adj_lists            # :235
+        self.seed = int(torch.initial_seed() if seed is None else seed) & 0x7FFFFFFFFFFFFFFF
+        self._calls = 0
+        self._native_state = None
+        self._injected = None
+        self._last_layers = None
+        for index in range(1, num_layers + 1):                                # :237-239
+            layer_size = out_size if index != 1 else input_size
+            setattr(self, 'sage_layer' + str(index), SageLayer(layer_size, out_size, gcn=self.gcn, precision=precision))
+
+    # ---- pickling (src/utils.py:52 saves the live modules): native handles are rebuilt lazily
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state['_native_state'] = None
+        state['_last_layers'] = None
+        state['_injected'] = None
+        return state
+
+    # ---- lazily built device state: CSR + padded feature table ---------------------------------
+    def _state(self):
+        if self._native_state is None:
+            dev = self.sage_layer1.weight.device
+            if dev.type != 'cuda':
+                dev = torch.device(self.device) if self.device is not None else dev
+            if torch.device(dev).type != 'cuda':
+                raise RuntimeError("GraphSage (gsage_b200) runs only on a CUDA device; there is no CPU fallback. "
+                                   "Construct it with device=torch.device('cuda') and call .to(device).")
+            native.load()
+            feats = self.raw_features
+            if not isinstance(feats, torch.Tensor):
+                feats = torch.as_tensor(np.asarray(feats), dtype=torch.float32)
+            table = _padded_table(feats.to(dev))
+            csr = _device_csr(self.adj_lists, table.shape[0], dev)
+            self._native_state = (csr, table, torch.device(dev))
+        return self._native_state
+
+    def inject_samples(self, calls):
+        """Injected-sample mode: `calls` is the per-call list of (nodes, samp_neighs) recorded
+        at the `_get_unique_neighs_list` seam of a reference run (src/models.py:250); the next
+        forward consumes them instead of drawing its own.  Pass None to clear."""
+        self._injected = calls
+
+    # ---- forward -------------------------------------------------------------------------------
+    def forward(self, nodes_batch):                                           # :241-269
+        csr, table, dev = self._state()
+        nodes_dev = _as_device_ids(nodes_batch, dev)
+        weights = [getattr(self, 'sage_layer' + str(i)).weight for i in range(1, self.num_layers + 1)]
+        for w in weights:
+            native.require_cuda(w, "GraphSage weights")
+        injected, self._injected = self._injected, None
+        return _GraphSageFn.apply(self, nodes_dev, injected, *weights)
+
+    def _list_stride(self) -> int:
+        return self.num_sample + (1 if self.gcn else 0)
+
+    def _injected_lists(self, nodes_host: np.ndarray, call, positional: bool):
+        """Recorded python sets -> fixed-stride id lists in the canonical form the sampler
+        writes (ascending, own id dropped for gcn=False / present once for gcn=True)."""
+        rec_nodes, rec_samp = call[0], call[1]
+        by_node = None if positional else {int(n): s for n, s in zip(rec_nodes, rec_samp)}
+        rows = []
+        for i, n in enumerate(nodes_host.tolist()):
+            s = rec_samp[i] if positional else by_node[n]
+            ids = sorted(int(x) for x in s if int(x) != n)
+            if self.gcn:
+                ids = sorted(ids + [n])
+            rows.append(ids)
+        stride = max(self._list_stride(), max((len(r) for r in rows), default=1))
+        nbr = np.full((len(rows), stride), -1, dtype=np.int32)
+        cnt = np.zeros(len(rows), dtype=np.int32)
+        for i, ids in enumerate(rows):
+            nbr[i, :len(ids)] = ids
+            cnt[i] = len(ids)
+        return nbr, cnt, stride
+
+    def _run_forward(self, nodes_dev: torch.Tensor, weights: Sequence[torch.Tensor], injected=None,
+                     offset_dev: Optional[torch.Tensor] = None) -> List[_Frontier]:
+        csr, table, dev = self._state()
+        L, k = self.num_layers, self.num_sample
+        self_mode = native.SELF_ONCE if self.gcn else native.SELF_DROP
+        mode = native.AGG_MEAN if self.agg_func == 'MEAN' else native.AGG_MAX
+        prec = _PRECISIONS[self.precision]
+        self._calls += 1
+        layers: List[Optional[_Frontier]] = [None] * (L + 1)
+        nodes, num_rows, rows_max = nodes_dev, None, int(nodes_dev.shape[0])
+        # ---- sampling phase, batch outward (src/models.py:249-251) ----
+        for l in range(L, 0, -1):
+            fr = _Frontier()
+            fr.nodes, fr.num_rows, fr.rows_max = nodes, num_rows, rows_max
+            if injected is not None:
+                live = rows_max if num_rows is None else int(num_rows.item())
+                host_nodes = nodes[:live].cpu().numpy()
+                nbr_h, cnt_h, stride = self._injected_lists(host_nodes, injected[L - l], positional=(l == L))
+                fr.stride = stride
+                fr.nbr = torch.full((rows_max, stride), -1, dtype=torch.int32, device=dev)
+                fr.cnt = torch.zeros((rows_max,), dtype=torch.int32, device=dev)
+                fr.nbr[:live] = torch.from_numpy(nbr_h).to(dev)
+                fr.cnt[:live] = torch.from_numpy(cnt_h).to(dev)
+            else:
+                fr.stride = self._list_stride()
+                offset = (self._calls << 8) | l
+                fr.nbr, fr.cnt = ops.sample_neighbors(csr.rowptr, csr.col, csr.num_nodes, nodes, num_rows, rows_max, k,
+                                                      fr.stride, self_mode, self.seed, offset, offset_dev=offset_dev)
+            if l > 1:   # unique + remap (src/models.py:286-288); the next frontier is U, ascending
+                uniq, num_uniq, fr.nbr_idx, fr.self_idx = ops.unique_remap(nodes, num_rows, rows_max, fr.nbr, fr.stride,
+                                                                           csr.id_bits)
+                nodes, num_rows = uniq, num_uniq
+                rows_max = min(rows_max * (fr.stride + 1), max(csr.num_nodes, 1))
+            else:       # layer 1 gathers straight from the feature table by node id: no U0, no remap
+                fr.nbr_idx, fr.self_idx = fr.nbr, nodes
+            layers[l] = fr
+        # ---- compute phase (src/models.py:255-267) ----
+        tbl, dim = table, self.input_size
+        for l in range(1, L + 1):
+            fr = layers[l]
+            fr.table_in, fr.dim_in = tbl, dim
+            fr.agg, fr.argmax = ops.agg_fwd(tbl, dim, fr.nbr_idx, fr.stride, fr.cnt, fr.num_rows, fr.rows_max, mode)
+            fr.h = ops.sage_gemm_fwd(None if self.gcn else tbl, fr.self_idx, fr.agg, dim, weights[l - 1], self.out_size,
+                                     self.gcn, fr.num_rows, fr.rows_max, True, prec)
+            tbl, dim = fr.h, self.out_size
+        return layers[1:]
+
+    def _run_backward(self, layers: List[_Frontier], grad_out: torch.Tensor, weights, needs,
+                      grad_bufs=None) -> List[Optional[torch.Tensor]]:
+        """Weight gradients of all layers.  `grad_bufs` (optional, pre-zeroed) receive them in
+        place (static buffers of the captured train step); otherwise fresh tensors are returned."""
+        L, H = self.num_layers, self.out_size
+        mode = native.AGG_MEAN if self.agg_func == 'MEAN' else native.AGG_MAX
+        g = _padded_table(grad_out)
+        grads: List[Optional[torch.Tensor]] = [None] * L
+        lowest = min((i for i in range(L) if needs[i]), default=None)
+        if lowest is None:
+            return grads
+        for l in range(L, 0, -1):
+            fr = layers[l - 1]
+            w = weights[l - 1]
+            if needs[l - 1]:
+                gw = torch.zeros_like(w) if grad_bufs is None else grad_bufs[l - 1]
+                ops.sage_gemm_bwd_w(None if self.gcn else fr.table_in, fr.self_idx, fr.agg, fr.dim_in, g, fr.h, H,
+                                    self.gcn, True, fr.num_rows, fr.rows_max, gw)
+                grads[l - 1] = gw
+            if l - 1 <= lowest:          # nothing below needs a gradient (raw features never do)
+                break
+            gs, ga = ops.sage_gemm_bwd_x(g, fr.h, w, fr.dim_in, H, self.gcn, True, fr.num_rows, fr.rows_max)
+            prev = layers[l - 2]
+            g_prev = torch.zeros((prev.rows_max, ops.pad4(H)), dtype=torch.float32, device=g.device)
+            ops.agg_bwd(ga, gs, fr.dim_in, fr.nbr_idx, fr.stride, fr.cnt, fr.self_idx, fr.argmax, fr.num_rows,
+                        fr.rows_max, mode, g_prev)
+            g = g_prev
+        return grads
+
+    # ---- compatibility methods of the reference (slow paths, host round trips) ------------------
+    def _get_unique_neighs_list(self, nodes, num_sample=10):                  # :277-289
+        """Same return triple as the reference: (list of python sets incl. the node itself,
+        {node: index}, unique list).  Unique order is ascending id (the reference's is CPython
+        set order; as sets they are equal)."""
+        csr, _, dev = self._state()
+        nodes_dev = _as_device_ids(nodes, dev)
+        n = int(nodes_dev.shape[0])
+        self._calls += 1
+        if num_sample is None:
+            raise NotImplementedError("num_sample=None (full neighbourhood) is not used by the reference forward")
+        nbr, cnt = ops.sample_neighbors(csr.rowptr, csr.col, csr.num_nodes, nodes_dev, None, n, int(num_sample),
+                                        int(num_sample) + 1, native.SELF_ONCE, self.seed, (self._calls << 8) | 0xFF)
+        uniq, num_uniq, _, _ = ops.unique_remap(nodes_dev, None, n, nbr, int(num_sample) + 1, csr.id_bits,
+                                                want_nbr_idx=False, want_self_idx=False)
+        nbr_h, cnt_h = nbr.cpu().numpy(), cnt.cpu().numpy()
+        uniq_list = uniq[:int(num_uniq.item())].cpu().tolist()
+        samp = [set(nbr_h[i, :cnt_h[i]].tolist()) for i in range(n)]
+        return samp, dict(zip(uniq_list, range(len(uniq_list)))), uniq_list
+
+    def _nodes_map(self, nodes, hidden_embs, neighs):                         # :271-275
+        layer_nodes, samp_neighs, layer_nodes_dict = neighs
+        assert len(samp_neighs) == len(nodes)
+        return [layer_nodes_dict[x] for x in nodes]
+
+    def aggregate(self, nodes, pre_hidden_embs, pre_neighs, num_sample=10):   # :291-330
+        """Reference signature; runs the K3 kernel on lists built from the given python sets."""
+        unique_nodes_list, samp_neighs, unique_nodes = pre_neighs
+        assert len(nodes) == len(samp_neighs)
+        _, _, dev = self._state()
+        rows = []
+        for i, s in enumerate(samp_neighs):
+            me = nodes[i]
+            assert me in s                                                    # :295-296
+            rows.append(sorted(unique_nodes[x] for x in s if self.gcn or x != me))
+        stride = max(1, max(len(r) for r in rows))
+        nbr = np.full((len(rows), stride), -1, dtype=np.int32)
+        cnt = np.asarray([len(r) for r in rows], dtype=np.int32)
+        for i, r in enumerate(rows):
+            nbr[i, :len(r)] = r
+        embed = pre_hidden_embs if len(pre_hidden_embs) == len(unique_nodes) \
+            else pre_hidden_embs[torch.as_tensor(unique_nodes_list, device=pre_hidden_embs.device)]   # :300-303
+        table = _padded_table(embed.to(dev))
+        mode = native.AGG_MEAN if self.agg_func == 'MEAN' else native.AGG_MAX
+        out, _ = ops.agg_fwd(table, embed.shape[1], torch.from_numpy(nbr).to(dev), stride, torch.from_numpy(cnt).to(dev),
+                             None, len(rows), mode)
+        return out[:, :embed.shape[1]]
+
+
+# ================================================================================================
+# UnsupervisedLoss                                                     src/models.py:45-186
+# ================================================================================================
+class _PairLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, embeddings, owner, mode):
+        emb = _padded_table(embeddings)
+        dim = embeddings.shape[1]
+        p = owner._pairs
+        loss, coef_pos, coef_neg, num_active = ops.pair_loss_fwd(emb, dim, p['seed_idx'], p['pos_ptr'], p['pos_idx'],
+                                                                 p['neg_ptr'], p['neg_idx'], mode, float(owner.Q),
+                                                                 float(owner.MARGIN))
+        ctx.save_for_backward(emb, coef_pos, coef_neg, num_active)
+        ctx.pairs, ctx.dim = p, dim
+        return loss.reshape(()) if mode == 0 else loss        # get_loss_sage: 0-d, get_loss_margin: [1]  (:96, :128)
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        emb, coef_pos, coef_neg, num_active = ctx.saved_tensors
+        p = ctx.pairs
+        grad_emb = torch.zeros_like(emb)
+        ops.pair_loss_bwd(emb, ctx.dim, p['seed_idx'], p['pos_ptr'], p['pos_idx'], p['neg_ptr'], p['neg_idx'],
+                          coef_pos, coef_neg, num_active, grad_loss.reshape(1).contiguous().float(), grad_emb)
+        return (grad_emb[:, :ctx.dim] if grad_emb.shape[1] != ctx.dim else grad_emb), None, None
+
+
+class UnsupervisedLoss(object):
+    """Same surface as src/models.py:45-186.  Sampling (random-walk positives, far negatives,
+    batch union) and both losses run on the device; the python pair stores
+    (`positive_pairs`, `node_positive_pairs`, ...) are materialised lazily on attribute access."""
+
+    def __init__(self, adj_lists, train_nodes, device, *, seed: Optional[int] = None):
+        self.Q = 10                      # :49
+        self.N_WALKS = 6                 # :50
+        self.WALK_LEN = 1                # :51
+        self.N_WALK_LEN = 5              # :52
+        self.MARGIN = 3                  # :53
+        self.adj_lists = adj_lists
+        self.train_nodes = train_nodes
+        self.device = device
+        self.target_nodes = None
+        self.unique_nodes_batch = []
+        self.seed = int(torch.initial_seed() if seed is None else seed) & 0x7FFFFFFFFFFFFFFF
+        self._calls = 0
+        self._dev = None
+        self._pairs = None
+        self._host_pairs = None
+
+    def _state(self):
+        if self._dev is None:
+            dev = torch.device(self.device)
+            if dev.type != 'cuda':
+                raise RuntimeError("UnsupervisedLoss (gsage_b200) runs only on a CUDA device; there is no CPU fallback")
+            native.load()
+            csr = _device_csr(self.adj_lists, None, dev)
+            train = torch.from_numpy(np.ascontiguousarray(np.asarray(self.train_nodes), dtype=np.int32)).to(dev)
+            is_train = torch.zeros((csr.num_nodes,), dtype=torch.uint8, device=dev)
+            is_train[train.long()] = 1
+            self._dev = (csr, train, is_train, dev)
+        return self._dev
+
+    # ---- A8: batch extension (src/models.py:135-148) -------------------------------------------
+    def extend_nodes(self, nodes, num_neg=6):
+        csr, train, is_train, dev = self._state()
+        self._calls += 1
+        self.target_nodes = nodes
+        seeds = _as_device_ids(nodes, dev)
+        s = int(seeds.shape[0])
+        n_pos = self.N_WALKS * self.WALK_LEN
+        pos = ops.random_walk_pos(csr.rowptr, csr.col, csr.num_nodes, seeds, self.N_WALKS, self.WALK_LEN, is_train,
+                                  self.seed, (self._calls << 8) | 1)                            # :169-186
+        neg, _ = ops.negative_sample(csr.rowptr, csr.col, csr.num_nodes, seeds, self.N_WALK_LEN, int(num_neg), train,
+                                     self.seed, (self._calls << 8) | 2)                         # :153-167
+        lists = torch.cat([pos, neg], dim=1).contiguous()
+        stride = n_pos + int(num_neg)
+        uniq, num_uniq, idx, seed_idx = ops.unique_remap(seeds, None, s, lists, stride, csr.id_bits)    # :146
+        n = int(num_uniq.item())
+        batch = uniq[:n]
+        self._pairs = dict(seed_idx=seed_idx, pos_idx=idx[:, :n_pos].contiguous().view(-1),
+                           neg_idx=idx[:, n_pos:].contiguous().view(-1),
+                           pos_ptr=torch.arange(0, (s + 1) * n_pos, n_pos, dtype=torch.int32, device=dev),
+                           neg_ptr=torch.arange(0, (s + 1) * int(num_neg), int(num_neg), dtype=torch.int32, device=dev),
+                           seeds=seeds, pos=pos, neg=neg, batch=batch)
+        self._host_pairs = None
+        self.unique_nodes_batch = batch.cpu().tolist()
+        return self.unique_nodes_batch
+
+    def set_pairs(self, unique_nodes_batch, seeds, node_positive_pairs, node_negtive_pairs):
+        """Injected-pair mode: install pair stores recorded from a reference run (same
+        attribute semantics as src/models.py:59-63) instead of drawing them on the device."""
+        _, _, _, dev = self._state()
+        index = {int(n): i for i, n in enumerate(unique_nodes_batch)}
+        seeds = [int(s) for s in seeds]
+        pos_rows = [[index[int(b)] for _, b in node_positive_pairs.get(s, [])] for s in seeds]
+        neg_rows = [[index[int(b)] for _, b in node_negtive_pairs.get(s, [])] for s in seeds]
+
+        def csr(rows):
+            ptr = np.zeros(len(rows) + 1, dtype=np.int32)
+            ptr[1:] = np.cumsum([len(r) for r in rows])
+            flat = np.asarray([x for r in rows for x in r] or [0], dtype=np.int32)
+            return torch.from_numpy(ptr).to(dev), torch.from_numpy(flat).to(dev)
+
+        pos_ptr, pos_idx = csr(pos_rows)
+        neg_ptr, neg_idx = csr(neg_rows)
+        seed_idx = torch.tensor([index[s] for s in seeds], dtype=torch.int32, device=dev)
+        self._pairs = dict(seed_idx=seed_idx, pos_idx=pos_idx, neg_idx=neg_idx, pos_ptr=pos_ptr, neg_ptr=neg_ptr)
+        self._host_pairs = dict(pos=[t for s in seeds for t in node_positive_pairs.get(s, [])],
+                                neg=[t for s in seeds for t in node_negtive_pairs.get(s, [])],
+                                npos=node_positive_pairs, nneg=node_negtive_pairs)
+        self.target_nodes = seeds
+        self.unique_nodes_batch = [int(n) for n in unique_nodes_batch]
+
+    def get_positive_nodes(self, nodes):                                      # :150-151
+        raise NotImplementedError("call extend_nodes(); positives are drawn on the device (gs_random_walk_pos)")
+
+    def get_negtive_nodes(self, nodes, num_neg):                              # :153
+        raise NotImplementedError("call extend_nodes(); negatives are drawn on the device (gs_negative_sample)")
+
+    # ---- lazily materialised python pair stores (reference attribute names, :59-62) -----------
+    def _host(self):
+        if self._host_pairs is None:
+            p = self._pairs
+            if p is None:
+                return dict(pos=[], neg=[], npos={}, nneg={})
+            seeds = p['seeds'].cpu().tolist()
+            pos, neg = p['pos'].cpu().tolist(), p['neg'].cpu().tolist()
+            npos = {s: [(s, v) for v in row if v >= 0] for s, row in zip(seeds, pos)}
+            nneg = {s: [(s, v) for v in row if v >= 0] for s, row in zip(seeds, neg)}
+            self._host_pairs = dict(pos=[t for s in seeds for t in npos[s]], neg=[t for s in seeds for t in nneg[s]],
+                                    npos=npos, nneg=nneg)
+        return self._host_pairs
+
+    positive_pairs = property(lambda self: self._host()['pos'])
+    negtive_pairs = property(lambda self: self._host()['neg'])
+    node_positive_pairs = property(lambda self: self._host()['npos'])
+    node_negtive_pairs = property(lambda self: self._host()['nneg'])
+
+    def _check(self, embeddings, nodes):
+        assert len(embeddings) == len(self.unique_nodes_batch)                                  # :66 / :101
+        assert np.array_equal(np.asarray(nodes), np.asarray(self.unique_nodes_batch))           # :67 / :102
+        native.require_cuda(embeddings, "embeddings")
+
+    # ---- A9 / A10 -------------------------------------------------------------------------------
+    def get_loss_sage(self, embeddings, nodes):                               # :65-98
+        self._check(embeddings, nodes)
+        return _PairLossFn.apply(embeddings, self, 0)
+
+    def get_loss_margin(self, embeddings, nodes):                             # :100-132
+        self._check(embeddings, nodes)
+        return _PairLossFn.apply(embeddings, self, 1)

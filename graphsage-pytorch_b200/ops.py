@@ -1,0 +1,252 @@
+"""Operator-level Python wrappers over the C ABI (one function per entry point of
+include/gsage_b200.h).  They allocate outputs with torch (device memory is plumbing), pass
+raw pointers and torch's current stream, and raise on any non-zero return code.  No wrapper
+has a CPU or eager-PyTorch fallback."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import native
+from .native import check, ptr, stream
+
+I32 = torch.int32
+F32 = torch.float32
+
+
+def pad4(n: int) -> int:
+    return (int(n) + 3) & ~3
+
+
+def _lib():
+    return native.load()
+
+
+# ----------------------------------------------------------------------------------------------
+# K1
+# ----------------------------------------------------------------------------------------------
+def sample_neighbors(rowptr, col, num_nodes: int, nodes, num_rows, max_rows: int, k: int, stride: int,
+                     self_mode: int, seed: int, offset: int, out_nbr=None, out_cnt=None, offset_dev=None):
+    """src/models.py:279-285 on the device CSR -> (nbr [max_rows, stride] int32, cnt [max_rows] int32)."""
+    native.require_cuda(nodes, "nodes")
+    dev = nodes.device
+    if out_nbr is None:
+        out_nbr = torch.empty((max_rows, stride), dtype=I32, device=dev)
+    if out_cnt is None:
+        out_cnt = torch.empty((max_rows,), dtype=I32, device=dev)
+    check(_lib().gs_sample_neighbors(ptr(rowptr), ptr(col), num_nodes, ptr(nodes), ptr(num_rows), max_rows, k, stride,
+                                     self_mode, seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF,
+                                     ptr(offset_dev), ptr(out_nbr), ptr(out_cnt), stream()), "gs_sample_neighbors")
+    return out_nbr, out_cnt
+
+
+# ----------------------------------------------------------------------------------------------
+# K2
+# ----------------------------------------------------------------------------------------------
+def unique_workspace(max_rows: int, stride: int, device) -> torch.Tensor:
+    n = int(_lib().gs_unique_workspace_bytes(max_rows, stride))
+    return torch.empty((max(n, 16),), dtype=torch.uint8, device=device)
+
+
+def unique_remap(nodes, num_rows, max_rows: int, nbr, stride: int, id_bits: int, *, uniq=None, num_uniq=None,
+                 nbr_idx=None, self_idx=None, workspace=None, want_nbr_idx=True, want_self_idx=True):
+    """src/models.py:286-288 (+ the lookups of :306 / :274) -> (uniq, num_uniq, nbr_idx, self_idx)."""
+    native.require_cuda(nodes, "nodes")
+    dev = nodes.device
+    cap = max_rows * (stride + 1)
+    if uniq is None:
+        uniq = torch.empty((max(cap, 1),), dtype=I32, device=dev)
+    if num_uniq is None:
+        num_uniq = torch.empty((1,), dtype=I32, device=dev)
+    if nbr_idx is None and want_nbr_idx and stride > 0:
+        nbr_idx = torch.empty((max_rows, stride), dtype=I32, device=dev)
+    if self_idx is None and want_self_idx:
+        self_idx = torch.empty((max_rows,), dtype=I32, device=dev)
+    if workspace is None:
+        workspace = unique_workspace(max_rows, stride, dev)
+    check(_lib().gs_unique_remap(ptr(nodes), ptr(num_rows), max_rows, ptr(nbr), stride, id_bits, ptr(uniq),
+                                 ptr(num_uniq), ptr(nbr_idx), ptr(self_idx), ptr(workspace), workspace.numel(),
+                                 stream()), "gs_unique_remap")
+    return uniq, num_uniq, nbr_idx, self_idx
+
+
+# ----------------------------------------------------------------------------------------------
+# K3
+# ----------------------------------------------------------------------------------------------
+def agg_fwd(table, dim: int, nbr, stride: int, cnt, num_rows, max_rows: int, mode: int, out=None, argmax=None):
+    """src/models.py:300-326 -> out [max_rows, pad4(dim)] (and argmax for MAX)."""
+    native.require_cuda(table, "table")
+    ld_out = pad4(dim)
+    if out is None:
+        out = torch.empty((max_rows, ld_out), dtype=F32, device=table.device)
+    if mode == native.AGG_MAX and argmax is None:
+        argmax = torch.empty((max_rows, ld_out), dtype=I32, device=table.device)
+    check(_lib().gs_agg_fwd(ptr(table), table.stride(0), dim, ptr(nbr), stride, ptr(cnt), ptr(num_rows), max_rows, mode,
+                            ptr(out), out.stride(0), ptr(argmax), argmax.stride(0) if argmax is not None else 0,
+                            stream()), "gs_agg_fwd")
+    return out, argmax
+
+
+def agg_bwd(grad_agg, grad_self, dim: int, nbr, stride: int, cnt, self_idx, argmax, num_rows, max_rows: int,
+            mode: int, grad_table):
+    check(_lib().gs_agg_bwd(ptr(grad_agg), grad_agg.stride(0) if grad_agg is not None else 0,
+                            ptr(grad_self), grad_self.stride(0) if grad_self is not None else 0, dim,
+                            ptr(nbr), stride, ptr(cnt), ptr(self_idx), ptr(argmax),
+                            argmax.stride(0) if argmax is not None else 0, ptr(num_rows), max_rows, mode,
+                            ptr(grad_table), grad_table.stride(0), stream()), "gs_agg_bwd")
+    return grad_table
+
+
+# ----------------------------------------------------------------------------------------------
+# K4
+# ----------------------------------------------------------------------------------------------
+def sage_gemm_fwd(self_table, self_idx, agg, dim: int, weight, out_dim: int, gcn: bool, num_rows, max_rows: int,
+                  relu: bool = True, precision: int = native.PREC_FP32, out=None):
+    """src/models.py:215-219 -> out [max_rows, pad4(out_dim)]."""
+    native.require_cuda(agg, "agg")
+    if out is None:
+        ld = pad4(out_dim)
+        alloc = torch.empty if ld == out_dim else torch.zeros
+        out = alloc((max_rows, ld), dtype=F32, device=agg.device)
+    check(_lib().gs_sage_gemm_fwd(ptr(self_table), self_table.stride(0) if self_table is not None else 0, ptr(self_idx),
+                                  ptr(agg), agg.stride(0), dim, ptr(weight), weight.stride(0), out_dim, int(gcn),
+                                  ptr(num_rows), max_rows, ptr(out), out.stride(0), int(relu), precision, stream()),
+          "gs_sage_gemm_fwd")
+    return out
+
+
+def sage_gemm_bwd_w(self_table, self_idx, agg, dim: int, grad_out, out, out_dim: int, gcn: bool, relu: bool, num_rows,
+                    max_rows: int, grad_w):
+    check(_lib().gs_sage_gemm_bwd_w(ptr(self_table), self_table.stride(0) if self_table is not None else 0,
+                                    ptr(self_idx), ptr(agg), agg.stride(0), dim, ptr(grad_out), grad_out.stride(0),
+                                    ptr(out), out.stride(0) if out is not None else 0, out_dim, int(gcn), int(relu),
+                                    ptr(num_rows), max_rows, ptr(grad_w), grad_w.stride(0), stream()),
+          "gs_sage_gemm_bwd_w")
+    return grad_w
+
+
+def sage_gemm_bwd_x(grad_out, out, weight, dim: int, out_dim: int, gcn: bool, relu: bool, num_rows, max_rows: int,
+                    grad_self=None, grad_agg=None):
+    dev = grad_out.device
+    ld = pad4(dim)
+    alloc = torch.empty if ld == dim else torch.zeros
+    if grad_agg is None:
+        grad_agg = alloc((max_rows, ld), dtype=F32, device=dev)
+    if not gcn and grad_self is None:
+        grad_self = alloc((max_rows, ld), dtype=F32, device=dev)
+    check(_lib().gs_sage_gemm_bwd_x(ptr(grad_out), grad_out.stride(0), ptr(out), out.stride(0) if out is not None else 0,
+                                    ptr(weight), weight.stride(0), dim, out_dim, int(gcn), int(relu), ptr(num_rows),
+                                    max_rows, ptr(grad_self), grad_self.stride(0) if grad_self is not None else 0,
+                                    ptr(grad_agg), grad_agg.stride(0), stream()), "gs_sage_gemm_bwd_x")
+    return grad_self, grad_agg
+
+
+# ----------------------------------------------------------------------------------------------
+# classifier / loss / update
+# ----------------------------------------------------------------------------------------------
+def cls_fwd(emb, dim: int, weight, bias, num_classes: int, logp=None):
+    native.require_cuda(emb, "embeds")
+    rows = emb.shape[0]
+    if logp is None:
+        logp = torch.empty((rows, num_classes), dtype=F32, device=emb.device)
+    check(_lib().gs_cls_fwd(ptr(emb), emb.stride(0), rows, dim, ptr(weight), ptr(bias), num_classes, ptr(logp),
+                            stream()), "gs_cls_fwd")
+    return logp
+
+
+def cls_bwd(grad_logp, logp, emb, dim: int, weight, num_classes: int, grad_emb, grad_w, grad_b, scratch=None):
+    rows = emb.shape[0]
+    if scratch is None:
+        scratch = torch.empty((rows, num_classes), dtype=F32, device=emb.device)
+    check(_lib().gs_cls_bwd(ptr(grad_logp), ptr(logp), ptr(emb), emb.stride(0), rows, dim, ptr(weight), num_classes,
+                            ptr(grad_emb), grad_emb.stride(0) if grad_emb is not None else 0, ptr(grad_w), ptr(grad_b),
+                            ptr(scratch), stream()), "gs_cls_bwd")
+
+
+def nll_fwd_bwd(logp, labels, loss=None, grad_logp=None, want_grad=True, label_index=None):
+    rows, classes = logp.shape
+    if loss is None:
+        loss = torch.empty((1,), dtype=F32, device=logp.device)
+    if grad_logp is None and want_grad:
+        grad_logp = torch.empty_like(logp)
+    check(_lib().gs_nll_fwd_bwd(ptr(logp), ptr(labels), ptr(label_index), rows, classes, ptr(loss), ptr(grad_logp),
+                                stream()),
+          "gs_nll_fwd_bwd")
+    return loss, grad_logp
+
+
+class TensorList:
+    """Device-side (param, grad, numel) table of one model for gs_clip_sgd."""
+
+    def __init__(self, params, grads):
+        dev = params[0].device
+        self.params, self.grads = list(params), list(grads)
+        self.p = torch.tensor([p.data_ptr() for p in params], dtype=torch.int64, device=dev)
+        self.g = torch.tensor([g.data_ptr() for g in grads], dtype=torch.int64, device=dev)
+        self.n = torch.tensor([p.numel() for p in params], dtype=torch.int64, device=dev)
+        self.max_numel = max(p.numel() for p in params)
+        self.scratch = torch.zeros((1,), dtype=F32, device=dev)
+
+
+def clip_sgd(tl: TensorList, max_norm: float, lr: float, grad_div: float = 1.0, zero_grads: bool = False):
+    check(_lib().gs_clip_sgd(ptr(tl.p), ptr(tl.g), ptr(tl.n), len(tl.params), tl.max_numel, float(max_norm), float(lr),
+                             float(grad_div), int(zero_grads), ptr(tl.scratch), stream()), "gs_clip_sgd")
+
+
+# ----------------------------------------------------------------------------------------------
+# K5 / K6
+# ----------------------------------------------------------------------------------------------
+def random_walk_pos(rowptr, col, num_nodes: int, seeds, n_walks: int, walk_len: int, is_train, seed: int, offset: int,
+                    out=None):
+    n = seeds.shape[0]
+    if out is None:
+        out = torch.empty((n, n_walks * walk_len), dtype=I32, device=seeds.device)
+    check(_lib().gs_random_walk_pos(ptr(rowptr), ptr(col), num_nodes, ptr(seeds), n, n_walks, walk_len, ptr(is_train),
+                                    seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF, ptr(out), stream()),
+          "gs_random_walk_pos")
+    return out
+
+
+def negative_workspace_bytes(num_nodes: int, num_seeds: int) -> int:
+    return int(_lib().gs_negative_workspace_bytes(num_nodes, num_seeds))
+
+
+def negative_sample(rowptr, col, num_nodes: int, seeds, hops: int, num_neg: int, train_nodes, seed: int, offset: int,
+                    workspace=None, out=None, out_cnt=None):
+    n = seeds.shape[0]
+    dev = seeds.device
+    if workspace is None:
+        workspace = torch.empty((negative_workspace_bytes(num_nodes, n),), dtype=torch.uint8, device=dev)
+    if out is None:
+        out = torch.empty((n, num_neg), dtype=I32, device=dev)
+    if out_cnt is None:
+        out_cnt = torch.empty((n,), dtype=I32, device=dev)
+    check(_lib().gs_negative_sample(ptr(rowptr), ptr(col), num_nodes, ptr(seeds), n, hops, num_neg, ptr(train_nodes),
+                                    train_nodes.shape[0], seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF,
+                                    ptr(out), ptr(out_cnt), ptr(workspace), workspace.numel(), stream()),
+          "gs_negative_sample")
+    return out, out_cnt
+
+
+def pair_loss_fwd(emb, dim: int, seed_idx, pos_ptr, pos_idx, neg_ptr, neg_idx, mode: int, q: float, margin: float):
+    dev = emb.device
+    loss = torch.empty((1,), dtype=F32, device=dev)
+    coef_pos = torch.empty((pos_idx.numel(),), dtype=F32, device=dev)
+    coef_neg = torch.empty((neg_idx.numel(),), dtype=F32, device=dev)
+    scratch = torch.empty((1,), dtype=F32, device=dev)
+    num_active = torch.empty((1,), dtype=I32, device=dev)
+    check(_lib().gs_pair_loss_fwd(ptr(emb), emb.stride(0), dim, ptr(seed_idx), seed_idx.shape[0], ptr(pos_ptr),
+                                  ptr(pos_idx), ptr(neg_ptr), ptr(neg_idx), mode, float(q), float(margin), ptr(loss),
+                                  ptr(coef_pos), ptr(coef_neg), ptr(scratch), ptr(num_active), stream()),
+          "gs_pair_loss_fwd")
+    return loss, coef_pos, coef_neg, num_active
+
+
+def pair_loss_bwd(emb, dim: int, seed_idx, pos_ptr, pos_idx, neg_ptr, neg_idx, coef_pos, coef_neg, num_active,
+                  grad_loss, grad_emb):
+    check(_lib().gs_pair_loss_bwd(ptr(emb), emb.stride(0), dim, ptr(seed_idx), seed_idx.shape[0], ptr(pos_ptr),
+                                  ptr(pos_idx), ptr(neg_ptr), ptr(neg_idx), ptr(coef_pos), ptr(coef_neg),
+                                  ptr(num_active), ptr(grad_loss), ptr(grad_emb), grad_emb.stride(0), stream()),
+          "gs_pair_loss_bwd")
+    return grad_emb

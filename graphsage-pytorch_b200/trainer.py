@@ -1,0 +1,137 @@
+"""Device-resident supervised train step: the body of the reference's `apply_model`
+(src/utils.py:141-191, learn_method='sup') as one CUDA-graph replay.
+
+    seeds -> sample -> unique/remap -> sample -> agg1 -> layer1 -> agg2 -> layer2 -> classifier ->
+    NLL -> backward (classifier, layer2, scatter, layer1) -> [NCCL allreduce] -> clip + SGD
+
+The eager drop-in classes (models.py) pay Python + autograd + launch overhead per kernel; at
+b_sz=1024 the kernels themselves are ~100 us, so the step is captured once (all shapes are
+static: frontier sizes that are only known on the device are passed as device counters, see
+include/gsage_b200.h) and replayed.  The Philox offset is a device counter bumped inside the
+graph so every replay draws fresh neighbours.  With world_size > 1 the gradients live in one
+flat buffer that is all-reduced (sum) between backward and the update, and the update
+divides by world_size (data-parallel mean).
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import native, ops
+from .models import Classification, GraphSage
+
+
+class SupervisedTrainer:
+    def __init__(self, model: GraphSage, classifier: Classification, labels, b_sz: int, *, lr: float = 0.7,
+                 max_norm: float = 5.0, use_graph: bool = True, process_group=None, world_size: int = 1):
+        csr, table, dev = model._state()
+        self.model, self.classifier, self.dev, self.b_sz = model, classifier, dev, int(b_sz)
+        self.lr, self.max_norm, self.world_size, self.pg = lr, max_norm, world_size, process_group
+        self.labels = labels if isinstance(labels, torch.Tensor) else torch.from_numpy(np.asarray(labels, dtype=np.int64))
+        self.labels = self.labels.to(dev)
+        self.weights: List[torch.Tensor] = [getattr(model, f'sage_layer{i}').weight for i in range(1, model.num_layers + 1)]
+        lin = classifier.layer[0]
+        self.cls_w, self.cls_b = lin.weight, lin.bias
+        for p in self.weights + [self.cls_w, self.cls_b]:
+            native.require_cuda(p, "parameters")
+        # one flat gradient buffer (single allreduce), views per tensor
+        params = self.weights + [self.cls_w, self.cls_b]
+        sizes = [p.numel() for p in params]
+        offs = np.concatenate([[0], np.cumsum([(s + 3) & ~3 for s in sizes])])      # keep every view 16-byte aligned
+        self.flat_grad = torch.zeros((int(offs[-1]),), dtype=torch.float32, device=dev)
+        self.grads = [self.flat_grad[int(o):int(o) + s].view_as(p) for o, s, p in zip(offs[:-1], sizes, params)]
+        n_sage = len(self.weights)
+        # clip is per model (src/utils.py:185-186): graphSage parameters, then classification parameters
+        self.tl_sage = ops.TensorList([p.data for p in self.weights], self.grads[:n_sage])
+        self.tl_cls = ops.TensorList([self.cls_w.data, self.cls_b.data], self.grads[n_sage:])
+        self.seeds = torch.zeros((self.b_sz,), dtype=torch.int32, device=dev)
+        self.seeds_pinned = torch.zeros((self.b_sz,), dtype=torch.int32).pin_memory()
+        self.loss = torch.zeros((1,), dtype=torch.float32, device=dev)
+        self.step_counter = torch.zeros((1,), dtype=torch.int64, device=dev)
+        self.use_graph = use_graph
+        self._graph_fb: Optional[torch.cuda.CUDAGraph] = None
+        self._graph_up: Optional[torch.cuda.CUDAGraph] = None
+        self.launches_per_step = 0
+        self.last_layers = None
+
+    # ---- the step, expressed once; runs eagerly or under capture -------------------------------
+    def _forward_backward(self):
+        m, c = self.model, self.classifier
+        weights = [w.detach() for w in self.weights]
+        layers = m._run_forward(self.seeds, weights, None, offset_dev=self.step_counter)
+        self.last_layers = layers
+        emb = layers[-1].h
+        classes = self.cls_w.shape[0]
+        logp = ops.cls_fwd(emb, m.out_size, self.cls_w.detach(), self.cls_b.detach(), classes)
+        _, glogp = ops.nll_fwd_bwd(logp, self.labels, loss=self.loss, label_index=self.seeds)        # utils.py:153,162-163
+        gemb = torch.empty_like(emb)
+        n_sage = len(self.weights)
+        ops.cls_bwd(glogp, logp, emb, m.out_size, self.cls_w.detach(), classes, gemb, self.grads[n_sage],
+                    self.grads[n_sage + 1])
+        m._run_backward(layers, gemb, weights, [True] * n_sage, grad_bufs=self.grads[:n_sage])
+        self.step_counter.add_(1)
+
+    def _update(self):
+        div = float(self.world_size)
+        ops.clip_sgd(self.tl_sage, self.max_norm, self.lr, div, zero_grads=True)                       # utils.py:185-191
+        ops.clip_sgd(self.tl_cls, self.max_norm, self.lr, div, zero_grads=True)
+
+    def _allreduce(self):
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.pg)
+
+    def _capture(self):
+        # warm-up on a side stream (allocator + lazy module loads), then capture
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._forward_backward()
+                self.flat_grad.zero_()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        before = native.launch_count()
+        self._graph_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph_fb):
+            self._forward_backward()
+        mid = native.launch_count()
+        self._graph_up = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph_up):
+            self._update()
+        self.launches_per_step = native.launch_count() - before
+        self._fb_launches, self._up_launches = mid - before, native.launch_count() - mid
+        self.flat_grad.zero_()
+
+    def step_device(self, seeds_dev: torch.Tensor) -> torch.Tensor:
+        """One step with the batch already in HBM (int32 [b_sz]).  Returns the device loss."""
+        self.seeds.copy_(seeds_dev, non_blocking=True)
+        return self._run()
+
+    def step(self, nodes_batch) -> torch.Tensor:
+        """One step from a HOST batch (numpy int64 as the reference's loop provides,
+        src/utils.py:145): pinned staging copy -> H2D -> step.  Call .item() on the result for
+        the loss (the reference does, src/utils.py:183)."""
+        arr = np.asarray(nodes_batch)
+        if arr.shape[0] != self.b_sz:
+            raise ValueError(f"trainer was built for b_sz={self.b_sz}, got {arr.shape[0]}")
+        self.seeds_pinned.numpy()[:] = arr
+        self.seeds.copy_(self.seeds_pinned, non_blocking=True)
+        return self._run()
+
+    def _run(self) -> torch.Tensor:
+        if self.use_graph:
+            if self._graph_fb is None:
+                self._capture()
+            self._graph_fb.replay()
+            self._allreduce()
+            self._graph_up.replay()
+        else:
+            before = native.launch_count()
+            self._forward_backward()
+            self._allreduce()
+            self._update()
+            self.launches_per_step = native.launch_count() - before
+        return self.loss

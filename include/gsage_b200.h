@@ -1,0 +1,207 @@
+/*
+ * gsage_b200.h -- C ABI of the B200-native GraphSAGE minibatch hot path.
+ *
+ * The reference (Lolash/graphSAGE-pytorch) has no FFI layer: its boundary is the Python
+ * class surface of src/models.py.  This header is what a maintainer would bind from those
+ * classes (ctypes stub in INTEGRATION.md); every entry point names the reference lines it
+ * replaces.  Conventions:
+ *   - extern "C", plain pointers and sizes; no torch / C++ types.
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`.
+ *   - the caller owns every buffer (inputs, outputs, scratch); nothing is allocated,
+ *     nothing synchronises with the host, every launch goes to `stream` (a cudaStream_t
+ *     passed as void*), so a sequence of calls can be captured into a CUDA graph.
+ *   - row counts that are only known on the device (|U| after unique) are passed as
+ *     `const int32_t* num_rows_dev` (nullable => `max_rows` rows are live); kernels are
+ *     launched for `max_rows` and rows >= *num_rows_dev exit.
+ *   - node ids and row indices are int32 (N < 2^31), CSR offsets int64, -1 pads lists.
+ *   - return value: 0 on success, a negative GS_ERR_* for bad arguments, or a positive
+ *     cudaError_t from the launch.  gs_error_string() decodes both.
+ */
+#ifndef GSAGE_B200_H_
+#define GSAGE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GS_ABI_VERSION 4
+
+#define GS_OK 0
+#define GS_ERR_BAD_ARG (-1)
+#define GS_ERR_UNSUPPORTED (-2)
+#define GS_ERR_WORKSPACE (-3)
+#define GS_ERR_ALIGNMENT (-4)
+
+#define GS_AGG_MEAN 0 /* src/models.py:311-314 */
+#define GS_AGG_MAX 1  /* src/models.py:316-326 */
+
+#define GS_SELF_KEEP 0 /* leave sampled rows as drawn                                    */
+#define GS_SELF_DROP 1 /* gcn=False: remove the row's own id (src/models.py:298)         */
+#define GS_SELF_ONCE 2 /* gcn=True : own id present exactly once (src/models.py:285)     */
+
+#define GS_PREC_FP32 0      /* SIMT FFMA, fp32 accumulate: the 1e-5 parity mode          */
+#define GS_PREC_TF32 1      /* tcgen05 kind::tf32, one pass                              */
+#define GS_PREC_TF32X3 2    /* tcgen05 kind::tf32, 3-term split (fp32-faithful)          */
+
+#define GS_MAX_FANOUT 32
+
+typedef void* gs_stream_t; /* cudaStream_t */
+
+int gs_version(void);
+const char* gs_error_string(int code);
+/* number of kernels this library has launched since load / since the last reset (bench.py's gpu_launches) */
+int64_t gs_launch_count(void);
+void gs_launch_count_reset(void);
+
+/* ------------------------------------------------------------------------------------
+ * K1  neighbour sampler.  Replaces GraphSage._get_unique_neighs_list's sampling half,
+ * src/models.py:279-285: rows with degree < k keep every neighbour, others draw k distinct
+ * uniform ones (Floyd's subset algorithm on Philox4x32-10 keyed by (seed, offset, row)).
+ * Rows are written sorted ascending, -1 padded to `stride` (>= k+1 when self_mode is ONCE).
+ * offset_dev (nullable): a device counter added to `offset`, so a captured CUDA graph draws
+ * fresh samples on every replay (the host bumps / a kernel increments the counter).
+ * ------------------------------------------------------------------------------------ */
+int gs_sample_neighbors(const int64_t* rowptr, const int32_t* col, int64_t num_nodes,
+                        const int32_t* nodes, const int32_t* num_rows_dev, int32_t max_rows,
+                        int32_t k, int32_t stride, int32_t self_mode,
+                        uint64_t seed, uint64_t offset, const int64_t* offset_dev,
+                        int32_t* out_nbr, int32_t* out_cnt, gs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * K2  unique + remap.  Replaces src/models.py:286-288 (set.union / dict(zip)) and the
+ * index lookups of :306 and :274 (_nodes_map).  Input ids = nodes[r] and nbr[r][j] (>= 0).
+ * Output: uniq ascending, *num_uniq_dev, nbr_idx[r][j] = position of nbr[r][j] in uniq
+ * (-1 stays -1), self_idx[r] = position of nodes[r].  LSD radix sort (8-bit digits over
+ * `id_bits` bits) + run-length heads + binary-search remap; one CTA when it fits in
+ * shared memory, multi-CTA otherwise.  Either of nbr_idx / self_idx may be NULL.
+ * ------------------------------------------------------------------------------------ */
+size_t gs_unique_workspace_bytes(int32_t max_rows, int32_t stride);
+int gs_unique_remap(const int32_t* nodes, const int32_t* num_rows_dev, int32_t max_rows,
+                    const int32_t* nbr, int32_t stride, int32_t id_bits,
+                    int32_t* uniq, int32_t* num_uniq_dev, int32_t* nbr_idx, int32_t* self_idx,
+                    void* workspace, size_t workspace_bytes, gs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * K3  gather-segment-reduce.  Replaces GraphSage.aggregate, src/models.py:300-326 (the
+ * embed_matrix gather, the dense mask, its normalisation and mask.mm / the MAX loop).
+ * out[r,:] = mean or max over j < cnt[r] of table[nbr[r*stride+j], :].  cnt==0 gives NaN
+ * for MEAN (0/0 as in the reference) and NaN for MAX (the reference raises).
+ * `table` rows are `ld` floats apart; ld % 4 == 0 and 16-byte aligned bases required.
+ * argmax (MAX only, nullable) receives the winning table row per element, first on ties.
+ * ------------------------------------------------------------------------------------ */
+int gs_agg_fwd(const float* table, int64_t ld, int32_t dim,
+               const int32_t* nbr, int32_t stride, const int32_t* cnt,
+               const int32_t* num_rows_dev, int32_t max_rows, int32_t mode,
+               float* out, int64_t ld_out, int32_t* argmax, int64_t ld_arg, gs_stream_t stream);
+
+/* Autograd of K3 plus the self-row gather of src/models.py:265: scatter-adds
+ *   grad_table[nbr[r][j], :] += grad_agg[r, :] / cnt[r]          (MEAN)
+ *   grad_table[argmax[r][c], c] += grad_agg[r, c]                (MAX)
+ *   grad_table[self_idx[r], :] += grad_self[r, :]                (when grad_self != NULL)
+ * grad_table must be zeroed by the caller. */
+int gs_agg_bwd(const float* grad_agg, int64_t ld_ga, const float* grad_self, int64_t ld_gs, int32_t dim,
+               const int32_t* nbr, int32_t stride, const int32_t* cnt, const int32_t* self_idx,
+               const int32_t* argmax, int64_t ld_arg, const int32_t* num_rows_dev, int32_t max_rows, int32_t mode,
+               float* grad_table, int64_t ld_gt, gs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * K4  SageLayer.  Replaces src/models.py:215-219: out = relu(W . [self | agg]^T)^T with the
+ * concat never materialised: X[r,:] = [ self_table[self_idx[r], :dim] | agg[r, :dim] ]
+ * (gcn: X = agg only, W is [out_dim x dim]).  self_idx NULL => identity.
+ * ------------------------------------------------------------------------------------ */
+int gs_sage_gemm_fwd(const float* self_table, int64_t ld_self, const int32_t* self_idx,
+                     const float* agg, int64_t ld_agg, int32_t dim,
+                     const float* weight, int64_t ldw, int32_t out_dim, int32_t gcn,
+                     const int32_t* num_rows_dev, int32_t max_rows,
+                     float* out, int64_t ld_out, int32_t relu, int32_t precision, gs_stream_t stream);
+
+/* dW[h,k] += sum_r dZ[r,h] X[r,k],  dZ = grad_out * (out > 0) when relu.  grad_w must be
+ * zeroed by the caller (partials are accumulated with atomics). */
+int gs_sage_gemm_bwd_w(const float* self_table, int64_t ld_self, const int32_t* self_idx,
+                       const float* agg, int64_t ld_agg, int32_t dim,
+                       const float* grad_out, int64_t ld_go, const float* out, int64_t ld_out,
+                       int32_t out_dim, int32_t gcn, int32_t relu,
+                       const int32_t* num_rows_dev, int32_t max_rows,
+                       float* grad_w, int64_t ldw, gs_stream_t stream);
+
+/* dX[r,k] = sum_h dZ[r,h] W[h,k]  -> grad_self[r,:dim] (non-gcn) and grad_agg[r,:dim]. */
+int gs_sage_gemm_bwd_x(const float* grad_out, int64_t ld_go, const float* out, int64_t ld_out,
+                       const float* weight, int64_t ldw, int32_t dim, int32_t out_dim, int32_t gcn, int32_t relu,
+                       const int32_t* num_rows_dev, int32_t max_rows,
+                       float* grad_self, int64_t ld_gs, float* grad_agg, int64_t ld_ga, gs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Classification, src/models.py:25-27: logp = log_softmax(emb . W^T + b).
+ * ------------------------------------------------------------------------------------ */
+int gs_cls_fwd(const float* emb, int64_t ld_emb, int32_t rows, int32_t dim,
+               const float* weight, const float* bias, int32_t num_classes,
+               float* logp, gs_stream_t stream);
+/* backward through log_softmax + Linear; grad_w / grad_b accumulate (zero them first);
+ * grad_emb (nullable) is overwritten.  scratch: rows*num_classes floats (grad of the logits). */
+int gs_cls_bwd(const float* grad_logp, const float* logp, const float* emb, int64_t ld_emb,
+               int32_t rows, int32_t dim, const float* weight, int32_t num_classes,
+               float* grad_emb, int64_t ld_ge, float* grad_w, float* grad_b, float* scratch, gs_stream_t stream);
+/* Supervised loss of src/utils.py:153,162-163 fused with its gradient:
+ * y_r = labels[label_index ? label_index[r] : r]   (label_index = the batch's node ids, :153)
+ * loss[0] = -mean_r logp[r, y_r];  grad_logp[r,c] = -(c==y_r) / rows  (nullable). */
+int gs_nll_fwd_bwd(const float* logp, const int64_t* labels, const int32_t* label_index, int32_t rows,
+                   int32_t num_classes, float* loss, float* grad_logp, gs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Update step of src/utils.py:185-187: per-model clip_grad_norm_(max_norm) then SGD.
+ * params / grads / numels are DEVICE arrays describing the `num_tensors` tensors of ONE
+ * model (max_numel = the largest numel, sizes the grid); grads are divided by `grad_div`
+ * first (data-parallel mean of summed gradients); max_norm <= 0 disables clipping;
+ * zero_grads != 0 also clears the gradients (src/utils.py:189-191).  norm_scratch: 1 float.
+ * ------------------------------------------------------------------------------------ */
+int gs_clip_sgd(float* const* params, float* const* grads, const int64_t* numels, int32_t num_tensors,
+                int64_t max_numel, float max_norm, float lr, float grad_div, int32_t zero_grads,
+                float* norm_scratch, gs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * K5  UnsupervisedLoss sampling, src/models.py:153-186.
+ * gs_random_walk_pos: n_walks walks of walk_len steps per seed (6 x 1 in the reference,
+ *   :50-51); a step yields a pair when next != seed and is_train[next] (:180).
+ *   pos[(s*n_walks+w)*walk_len+t] = next or -1.  Zero-degree seeds produce no pairs (:171-172).
+ * gs_negative_sample: `num_neg` distinct train nodes outside the `hops`-hop ball of each
+ *   seed (:155-164).  The ball is marked in a per-seed bitmap of `num_nodes` bits held in
+ *   `workspace`; when fewer than num_neg far train nodes exist all of them are returned.
+ * ------------------------------------------------------------------------------------ */
+int gs_random_walk_pos(const int64_t* rowptr, const int32_t* col, int64_t num_nodes,
+                       const int32_t* seeds, int32_t num_seeds, int32_t n_walks, int32_t walk_len,
+                       const uint8_t* is_train, uint64_t seed, uint64_t offset,
+                       int32_t* pos, gs_stream_t stream);
+size_t gs_negative_workspace_bytes(int64_t num_nodes, int32_t num_seeds);
+int gs_negative_sample(const int64_t* rowptr, const int32_t* col, int64_t num_nodes,
+                       const int32_t* seeds, int32_t num_seeds, int32_t hops, int32_t num_neg,
+                       const int32_t* train_nodes, int32_t num_train, uint64_t seed, uint64_t offset,
+                       int32_t* neg, int32_t* neg_cnt, void* workspace, size_t workspace_bytes, gs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * K6  pair losses, src/models.py:65-132.  Pairs are grouped per seed: seed s owns
+ * pos_idx[pos_ptr[s]..pos_ptr[s+1]) and neg_idx[neg_ptr[s]..), all row indices into `emb`
+ * (seed_idx[s] is the seed's own row).  Seeds with no positive or no negative pair are
+ * skipped (:75-76, :110-111).  mode 0 = "normal" (get_loss_sage, Q), 1 = margin.
+ * fwd writes loss[0] and per-pair coefficients into `coef` (len = total pairs) for bwd.
+ * ------------------------------------------------------------------------------------ */
+int gs_pair_loss_fwd(const float* emb, int64_t ld, int32_t dim,
+                     const int32_t* seed_idx, int32_t num_seeds,
+                     const int32_t* pos_ptr, const int32_t* pos_idx,
+                     const int32_t* neg_ptr, const int32_t* neg_idx,
+                     int32_t mode, float q, float margin,
+                     float* loss, float* coef_pos, float* coef_neg, float* loss_sum_scratch, int32_t* num_active,
+                     gs_stream_t stream);
+int gs_pair_loss_bwd(const float* emb, int64_t ld, int32_t dim,
+                     const int32_t* seed_idx, int32_t num_seeds,
+                     const int32_t* pos_ptr, const int32_t* pos_idx,
+                     const int32_t* neg_ptr, const int32_t* neg_idx,
+                     const float* coef_pos, const float* coef_neg, const int32_t* num_active,
+                     const float* grad_loss, float* grad_emb, int64_t ld_ge, gs_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSAGE_B200_H_ */

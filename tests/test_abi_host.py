@@ -1,0 +1,116 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/gsage_b200.h declares
+(no compute calls without a GPU); host-side logic (adjacency conversion, synthetic graphs,
+loud failure without CUDA); the product never imports the oracle."""
+import os
+import re
+from collections import defaultdict
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, 'include', 'gsage_b200.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(gs_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import graphsage_b200  # noqa: F401
+    from graphsage_b200 import native
+    lib = native.load()
+    names = header_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f'{n} declared in include/gsage_b200.h but not exported'
+    assert sorted(native.exported_symbols()) == names          # ctypes table mirrors the header one to one
+    assert lib.gs_version() == native.ABI_VERSION
+    assert b'bad argument' in lib.gs_error_string(-1)
+    assert os.path.dirname(native.lib_path()) == os.path.join(ROOT, 'graphsage-pytorch_b200')   # in-tree .so
+
+
+def test_bad_arguments_are_rejected_before_any_launch():
+    from graphsage_b200 import native
+    lib = native.load()
+    assert lib.gs_sample_neighbors(None, None, 0, None, None, 4, 10, 10, 0, 1, 1, None, None, None, None) == -1
+    assert lib.gs_agg_fwd(None, 0, 0, None, 0, None, None, 0, 0, None, 0, None, 0, None) == -1
+    assert lib.gs_unique_workspace_bytes(1024, 11) == 16                      # single-CTA path needs no scratch
+    assert lib.gs_unique_workspace_bytes(90112, 11) > 8 * 90112 * 12
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'graphsage-pytorch_b200')
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(base, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle', text, flags=re.M), f
+
+
+def test_adjacency_conversion_and_mapping_semantics():
+    from graphsage_b200.graph import AdjCSR, adj_to_csr
+    adj = defaultdict(set)
+    edges = [(0, 3), (3, 1), (1, 1), (4, 0), (2, 4)]
+    for a, b in edges:
+        adj[a].add(b)
+        adj[b].add(a)
+    rowptr, col = adj_to_csr(adj, 6)                 # node 5 has no key: empty row (defaultdict semantics)
+    assert rowptr.tolist() == [0, 2, 4, 5, 7, 9, 9]
+    assert col.tolist() == [3, 4, 1, 3, 4, 0, 1, 0, 2]
+    view = AdjCSR(rowptr, col)
+    for v in range(6):
+        assert view[v] == adj.get(v, set())
+    assert view[17] == set() and len(view) == 6
+    with pytest.raises(ValueError):
+        adj_to_csr({0: {9}}, 3)
+
+
+def test_synthetic_graph_is_a_valid_dict_of_sets_image():
+    from graphsage_b200 import synth
+    rowptr, col = synth.powerlaw_graph(5000, 60000, seed=0)
+    n = len(rowptr) - 1
+    row = np.repeat(np.arange(n), np.diff(rowptr))
+    assert np.all(np.diff(rowptr) >= 2) and not np.any(row == col)
+    key = row.astype(np.int64) * n + col
+    assert np.all(np.diff(key) > 0)                                   # sorted rows, no duplicates
+    rev = col.astype(np.int64) * n + row
+    assert np.array_equal(np.sort(rev), key)                          # both directions present
+    deg = np.diff(rowptr)
+    assert deg.max() > 20 * np.median(deg)                            # heavy tail
+
+
+def test_cpu_tensors_fail_loudly():
+    from graphsage_b200 import models
+    from graphsage_b200.graph import AdjCSR
+    adj = AdjCSR(np.array([0, 1, 2]), np.array([1, 0]))
+    m = models.GraphSage(2, 8, 4, torch.zeros(2, 8), adj, torch.device('cpu'))
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        m([0, 1])
+    layer = models.SageLayer(8, 4)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        layer(torch.zeros(2, 8), torch.zeros(2, 8))
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        models.Classification(4, 3)(torch.zeros(2, 4))
+    assert list(m.state_dict()) == ['sage_layer1.weight', 'sage_layer2.weight']
+    assert m.sage_layer1.weight.shape == (4, 16) and m.sage_layer2.weight.shape == (4, 8)
+
+
+def test_philox_host_matches_known_answer():
+    """Philox4x32-10 known-answer vectors (Random123 kat_vectors): the sampler's generator."""
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+
+    def philox(ctr, key):
+        c, k = list(ctr), list(key)
+        for _ in range(10):
+            p0, p1 = M0 * c[0], M1 * c[2]
+            c = [(p1 >> 32) ^ c[1] ^ k[0], p1 & 0xFFFFFFFF, (p0 >> 32) ^ c[3] ^ k[1], p0 & 0xFFFFFFFF]
+            k = [(k[0] + W0) & 0xFFFFFFFF, (k[1] + W1) & 0xFFFFFFFF]
+        return c
+
+    assert philox([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert philox([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert philox([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]

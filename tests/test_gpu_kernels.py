@@ -1,0 +1,309 @@
+"""GPU: each kernel through the C ABI (ops.py -> libgsage_b200.so) against an independent CPU
+statement of the same operation.  Integer outputs are compared bit-exactly; fp32 outputs with
+the norm-relative 1e-5 bound of SURVEY.md §8(c)."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import sage_oracle as so
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def rel(a, b):
+    a = np.asarray(a.detach().cpu() if isinstance(a, torch.Tensor) else a, dtype=np.float64)
+    b = np.asarray(b.detach().cpu() if isinstance(b, torch.Tensor) else b, dtype=np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+@pytest.fixture(scope='module')
+def g():
+    import graphsage_b200  # noqa: F401
+    from graphsage_b200 import native, ops
+    native.load()
+    return ops
+
+
+@pytest.fixture(scope='module')
+def dev():
+    return torch.device('cuda:0')
+
+
+# ------------------------------------------------------------------------------------------------
+# K1 sampler
+# ------------------------------------------------------------------------------------------------
+def _csr_dev(rowptr, col, dev):
+    return torch.from_numpy(rowptr).to(dev), torch.from_numpy(col).to(dev)
+
+
+@pytest.mark.parametrize('self_mode', [0, 1, 2])
+def test_sampler_exact_semantics(g, dev, self_mode):
+    rowptr, col = cases.load_topology('pubmed')          # has 3 self-loops and deg in 1..171
+    n = len(rowptr) - 1
+    rp, cl = _csr_dev(rowptr, col, dev)
+    nodes = np.arange(n, dtype=np.int32)
+    k, stride = 10, 11
+    nbr, cnt = g.sample_neighbors(rp, cl, n, torch.from_numpy(nodes).to(dev), None, n, k, stride, self_mode, 824, 5)
+    nbr, cnt = nbr.cpu().numpy(), cnt.cpu().numpy()
+    deg = np.diff(rowptr)
+    for v in range(0, n, 3):
+        row = nbr[v, :cnt[v]]
+        adj = set(col[rowptr[v]:rowptr[v + 1]].tolist())
+        assert np.all(nbr[v, cnt[v]:] == -1)
+        assert np.all(np.diff(row) > 0)                                        # ascending, distinct
+        drawn = set(row.tolist())
+        if self_mode == 0:
+            assert drawn <= adj and len(drawn) == min(deg[v], k)               # src/models.py:282
+        elif self_mode == 1:
+            assert v not in drawn and drawn <= adj
+            assert len(drawn) >= min(deg[v], k) - 1
+            if v not in adj:
+                assert len(drawn) == min(deg[v], k)
+        else:
+            assert v in drawn and (drawn - {v}) <= adj
+    # determinism under a fixed (seed, offset) and sensitivity to the offset
+    nbr2, _ = g.sample_neighbors(rp, cl, n, torch.from_numpy(nodes).to(dev), None, n, k, stride, self_mode, 824, 5)
+    nbr3, _ = g.sample_neighbors(rp, cl, n, torch.from_numpy(nodes).to(dev), None, n, k, stride, self_mode, 824, 6)
+    assert np.array_equal(nbr2.cpu().numpy(), nbr)
+    assert not np.array_equal(nbr3.cpu().numpy(), nbr)
+
+
+def test_sampler_distribution(g, dev):
+    """Inclusion frequency of every neighbour -> k/deg (chi-square), pair inclusion ->
+    k(k-1)/(deg(deg-1)); the native sampler cannot match random.sample's stream."""
+    deg, k, trials = 37, 10, 20000
+    rowptr = np.array([0, deg], dtype=np.int64)
+    col = np.arange(1, deg + 1, dtype=np.int32)
+    rp, cl = _csr_dev(rowptr, col, dev)
+    nodes = torch.zeros((trials,), dtype=torch.int32, device=dev)
+    nbr, cnt = g.sample_neighbors(rp, cl, deg + 1, nodes, None, trials, k, k, 0, 12345, 1)
+    nbr = nbr.cpu().numpy()
+    assert np.all(cnt.cpu().numpy() == k)
+    counts = np.bincount(nbr.ravel(), minlength=deg + 1)[1:]
+    expect = trials * k / deg
+    chi2 = ((counts - expect) ** 2 / (expect * (1 - k / deg))).sum()
+    assert chi2 < 80, chi2                                  # dof 36: mean 36, p(>80) ~ 3e-5
+    pair = np.zeros((deg + 1, deg + 1))
+    for a in range(k):
+        for b in range(a + 1, k):
+            np.add.at(pair, (nbr[:, a], nbr[:, b]), 1)
+    pair = (pair + pair.T)[1:, 1:][np.triu_indices(deg, 1)]
+    p2 = k * (k - 1) / (deg * (deg - 1))
+    z = (pair - trials * p2) / np.sqrt(trials * p2 * (1 - p2))
+    assert np.abs(z).max() < 5.5 and abs(z.mean()) < 0.3
+    # rows are independent: consecutive rows share about k*k/deg members
+    inter = np.mean([len(set(nbr[i]) & set(nbr[i + 1])) for i in range(0, 4000, 2)])
+    assert abs(inter - k * k / deg) < 0.2
+
+
+def test_sampler_device_row_count(g, dev):
+    rowptr, col = cases.load_topology('cora')
+    n = len(rowptr) - 1
+    rp, cl = _csr_dev(rowptr, col, dev)
+    nodes = torch.arange(100, dtype=torch.int32, device=dev)
+    live = torch.tensor([37], dtype=torch.int32, device=dev)
+    nbr, cnt = g.sample_neighbors(rp, cl, n, nodes, live, 100, 10, 10, 1, 1, 1)
+    assert np.all(nbr[37:].cpu().numpy() == -1) and np.all(cnt[37:].cpu().numpy() == 0)
+    assert np.all(cnt[:37].cpu().numpy() > 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# K2 unique / remap: bit-exact
+# ------------------------------------------------------------------------------------------------
+def _check_unique(g, dev, nodes, nbr, id_bits, live=None):
+    rows, stride = nbr.shape
+    nodes_t, nbr_t = torch.from_numpy(nodes).to(dev), torch.from_numpy(nbr).to(dev)
+    live_t = None if live is None else torch.tensor([live], dtype=torch.int32, device=dev)
+    uniq, num, nbr_idx, self_idx = g.unique_remap(nodes_t, live_t, rows, nbr_t, stride, id_bits)
+    m = rows if live is None else live
+    ids = np.concatenate([nodes[:m], nbr[:m].ravel()])
+    want = np.unique(ids[ids >= 0])
+    n = int(num.item())
+    assert n == len(want)
+    got = uniq[:n].cpu().numpy()
+    assert np.array_equal(got, want)
+    ni, si = nbr_idx.cpu().numpy(), self_idx.cpu().numpy()
+    ref_idx = np.where(nbr[:m] >= 0, np.searchsorted(want, np.maximum(nbr[:m], 0)), -1)
+    assert np.array_equal(ni[:m], ref_idx)
+    assert np.all(ni[m:] == -1)
+    assert np.array_equal(si[:m], np.searchsorted(want, nodes[:m]))
+
+
+@pytest.mark.parametrize('rows,stride,n_ids,bits', [(1, 11, 50, 6), (1024, 11, 2_449_029, 22), (2047, 11, 100_000_000, 27),
+                                                    (2048, 11, 5000, 13), (37, 3, 1 << 31, 32)])
+def test_unique_single_cta(g, dev, rows, stride, n_ids, bits):
+    rng = np.random.default_rng(rows + stride)
+    nodes = rng.integers(0, n_ids, size=rows).astype(np.int32)
+    nbr = rng.integers(0, n_ids, size=(rows, stride)).astype(np.int32)
+    nbr[rng.random((rows, stride)) < 0.2] = -1
+    _check_unique(g, dev, nodes, nbr, bits)
+    _check_unique(g, dev, nodes, nbr, bits, live=max(1, rows // 3))
+
+
+@pytest.mark.parametrize('rows,stride,n_ids,bits', [(11264, 11, 2_449_029, 22), (90112, 11, 100_000_000, 27),
+                                                    (3000, 106, 19717, 15)])
+def test_unique_multi_cta(g, dev, rows, stride, n_ids, bits):
+    rng = np.random.default_rng(rows)
+    nodes = rng.integers(0, n_ids, size=rows).astype(np.int32)
+    nbr = rng.integers(0, n_ids, size=(rows, stride)).astype(np.int32)
+    nbr[rng.random((rows, stride)) < 0.1] = -1
+    _check_unique(g, dev, nodes, nbr, bits)
+    _check_unique(g, dev, nodes, nbr, bits, live=rows // 2 + 1)
+
+
+@pytest.mark.parametrize('name', ['cora_mean_sup', 'pubmed_selfloop_gcn', 'cora_3layer_gcn_max'])
+def test_unique_remap_matches_reference_calls(g, dev, name):
+    """Injected-sample contract: on the reference's own recorded samples,
+    U_dev == U_ref as sets and every remapped slot points at the recorded neighbour."""
+    inp, fx = cases.load_fixture(name)
+    gcn = inp['spec']['gcn']
+    bits = int(len(inp['rowptr']) - 1).bit_length()
+    for nodes, samp, uniq_ref in fx['calls']:
+        U, self_idx, cols, cnt = so.canonical_unique_remap(nodes, samp, drop_self=not gcn)
+        width = cols.shape[1]
+        nbr = np.where(cols >= 0, U[np.maximum(cols, 0)], -1).astype(np.int32)     # canonical id lists
+        nodes_np = np.asarray(nodes, dtype=np.int32)
+        uniq, num, nbr_idx, sidx = g.unique_remap(torch.from_numpy(nodes_np).to(dev), None, len(nodes),
+                                                  torch.from_numpy(nbr).to(dev), width, bits)
+        n = int(num.item())
+        assert set(uniq[:n].cpu().tolist()) == set(uniq_ref) and n == len(uniq_ref)
+        assert np.array_equal(uniq[:n].cpu().numpy(), U.astype(np.int32))
+        assert np.array_equal(nbr_idx.cpu().numpy(), cols)
+        assert np.array_equal(sidx.cpu().numpy(), self_idx.astype(np.int32))
+
+
+# ------------------------------------------------------------------------------------------------
+# K3 aggregation
+# ------------------------------------------------------------------------------------------------
+def _agg_ref(table, nbr, cnt, mode):
+    rows = []
+    for r in range(nbr.shape[0]):
+        ids = nbr[r, :cnt[r]]
+        if len(ids) == 0:
+            rows.append(torch.full((table.shape[1],), float('nan')))
+        elif mode == 0:
+            rows.append(table[ids].sum(0) / len(ids))
+        else:
+            rows.append(table[ids].max(0)[0])
+    return torch.stack(rows)
+
+
+@pytest.mark.parametrize('dim', [100, 128, 1433, 500, 7])
+@pytest.mark.parametrize('mode', [0, 1])
+def test_agg_fwd_bwd(g, dev, dim, mode):
+    rng = np.random.default_rng(dim + mode)
+    n_table, rows, stride = 3000, 777, 11
+    ld = (dim + 3) & ~3
+    table = torch.zeros((n_table, ld))
+    table[:, :dim] = torch.from_numpy(rng.standard_normal((n_table, dim)).astype(np.float32))
+    cnt = rng.integers(0, stride + 1, size=rows).astype(np.int32)
+    cnt[:5] = [0, 1, stride, 2, 10]
+    nbr = np.full((rows, stride), -1, dtype=np.int32)
+    for r in range(rows):
+        nbr[r, :cnt[r]] = np.sort(rng.choice(n_table, size=cnt[r], replace=False))
+    t_dev = table.to(dev)
+    nbr_d, cnt_d = torch.from_numpy(nbr).to(dev), torch.from_numpy(cnt).to(dev)
+    out, argmax = g.agg_fwd(t_dev, dim, nbr_d, stride, cnt_d, None, rows, mode)
+    want = _agg_ref(table[:, :dim], nbr, cnt, mode)
+    got = out[:, :dim].cpu()
+    empty = cnt == 0
+    assert torch.isnan(got[empty]).all()                      # 0/0 as the reference (MEAN); MAX raises there
+    assert rel(got[~empty], want[~empty]) <= TOL
+    if ld != dim:
+        assert torch.all(out[~torch.from_numpy(empty).to(dev)][:, dim:] == 0)
+    # backward against autograd on the same expression (rows with cnt == 0 contribute nothing)
+    tbl = table[:, :dim].clone().requires_grad_(True)
+    keep = np.where(~empty)[0]
+    ref = _agg_ref(tbl, nbr[keep], cnt[keep], mode)
+    gout = torch.from_numpy(rng.standard_normal((rows, ld)).astype(np.float32))
+    gout[:, dim:] = 0
+    (ref * gout[keep, :dim]).sum().backward()
+    gself = torch.from_numpy(rng.standard_normal((rows, ld)).astype(np.float32))
+    gself[:, dim:] = 0
+    self_idx = rng.integers(0, n_table, size=rows).astype(np.int32)
+    want_g = tbl.grad.clone()
+    want_g.index_add_(0, torch.from_numpy(self_idx).long(), gself[:, :dim])
+    gt = torch.zeros((n_table, ld), device=dev)
+    g.agg_bwd(gout.to(dev), gself.to(dev), dim, nbr_d, stride, cnt_d, torch.from_numpy(self_idx).to(dev), argmax, None,
+              rows, mode, gt)
+    assert rel(gt[:, :dim], want_g) <= TOL
+
+
+# ------------------------------------------------------------------------------------------------
+# K4 SageLayer GEMM (fp32 path) and Classification
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('dim,out_dim,gcn', [(100, 128, False), (128, 128, False), (1433, 128, False), (602, 128, True),
+                                             (64, 32, False), (7, 5, False)])
+def test_sage_gemm_fwd_bwd(g, dev, dim, out_dim, gcn):
+    rng = np.random.default_rng(dim * 3 + out_dim)
+    n_table, rows = 1500, 1027
+    ld = (dim + 3) & ~3
+    table = torch.zeros((n_table, ld))
+    table[:, :dim] = torch.from_numpy(rng.standard_normal((n_table, dim)).astype(np.float32))
+    agg = torch.zeros((rows, ld))
+    agg[:, :dim] = torch.from_numpy(rng.standard_normal((rows, dim)).astype(np.float32))
+    self_idx = rng.integers(0, n_table, size=rows)
+    w = torch.from_numpy(rng.uniform(-0.2, 0.2, size=(out_dim, dim if gcn else 2 * dim)).astype(np.float32))
+    live = 1000
+    live_t = torch.tensor([live], dtype=torch.int32, device=dev)
+    sidx_d = torch.from_numpy(self_idx.astype(np.int32)).to(dev)
+    out = g.sage_gemm_fwd(None if gcn else table.to(dev), sidx_d, agg.to(dev), dim, w.to(dev), out_dim, gcn, live_t, rows)
+    # torch fp32 reference of src/models.py:215-219
+    w_ref = w.clone().requires_grad_(True)
+    tbl = table[:, :dim].clone().requires_grad_(True)
+    agg_ref = agg[:live, :dim].clone().requires_grad_(True)
+    comb = agg_ref if gcn else torch.cat([tbl[self_idx[:live]], agg_ref], 1)
+    want = torch.relu(w_ref.mm(comb.t())).t()
+    assert rel(out[:live, :out_dim], want) <= TOL
+    gout = torch.from_numpy(rng.standard_normal((rows, (out_dim + 3) & ~3)).astype(np.float32))
+    (want * gout[:live, :out_dim]).sum().backward()
+    gw = torch.zeros_like(w, device=dev)
+    g.sage_gemm_bwd_w(None if gcn else table.to(dev), sidx_d, agg.to(dev), dim, gout.to(dev), out, out_dim, gcn, True,
+                      live_t, rows, gw)
+    assert rel(gw, w_ref.grad) <= TOL
+    gs, ga = g.sage_gemm_bwd_x(gout.to(dev), out, w.to(dev), dim, out_dim, gcn, True, live_t, rows)
+    assert rel(ga[:live, :dim], agg_ref.grad) <= TOL
+    if not gcn:
+        want_gs = torch.zeros((n_table, dim)).index_add_(0, torch.from_numpy(self_idx[:live]), gs[:live, :dim].cpu())
+        assert rel(want_gs, tbl.grad) <= TOL
+
+
+@pytest.mark.parametrize('rows,dim,classes', [(1024, 128, 47), (150, 32, 7), (33, 128, 3)])
+def test_classifier_and_nll(g, dev, rows, dim, classes):
+    rng = np.random.default_rng(classes)
+    emb = torch.from_numpy(rng.standard_normal((rows, dim)).astype(np.float32))
+    w = torch.from_numpy(rng.uniform(-0.3, 0.3, size=(classes, dim)).astype(np.float32))
+    b = torch.from_numpy(rng.uniform(-0.1, 0.1, size=(classes,)).astype(np.float32))
+    labels = torch.from_numpy(rng.integers(0, classes, size=rows))
+    e_ref, w_ref, b_ref = emb.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    logp_ref = so.classification(w_ref, b_ref, e_ref)
+    loss_ref = so.supervised_loss(logp_ref, labels.numpy())
+    loss_ref.backward()
+    logp = g.cls_fwd(emb.to(dev), dim, w.to(dev), b.to(dev), classes)
+    assert rel(logp, logp_ref) <= TOL
+    loss, glogp = g.nll_fwd_bwd(logp, labels.to(dev))
+    assert rel(loss, loss_ref.reshape(1)) <= TOL
+    ge, gw, gb = torch.empty((rows, dim), device=dev), torch.zeros((classes, dim), device=dev), torch.zeros((classes,), device=dev)
+    g.cls_bwd(glogp, logp, emb.to(dev), dim, w.to(dev), classes, ge, gw, gb)
+    assert rel(ge, e_ref.grad) <= TOL and rel(gw, w_ref.grad) <= TOL and rel(gb, b_ref.grad) <= TOL
+
+
+def test_clip_sgd_matches_torch(g, dev):
+    rng = np.random.default_rng(3)
+    shapes = [(128, 200), (128, 256), (47, 128), (47,)]
+    for scale in (0.01, 10.0):                                  # below and above the clip threshold
+        ps = [torch.from_numpy(rng.standard_normal(s).astype(np.float32)) for s in shapes]
+        gs_ = [torch.from_numpy((scale * rng.standard_normal(s)).astype(np.float32)) for s in shapes]
+        ref = [p.clone().requires_grad_(True) for p in ps]
+        for p, gr in zip(ref, gs_):
+            p.grad = gr.clone()
+        torch.nn.utils.clip_grad_norm_(ref, 5)                  # src/utils.py:186
+        torch.optim.SGD(ref, lr=0.7).step()                     # src/utils.py:136,187
+        pd, gd = [p.to(dev) for p in ps], [x.to(dev) for x in gs_]
+        tl = g.TensorList(pd, gd)
+        g.clip_sgd(tl, 5.0, 0.7, 1.0, zero_grads=True)
+        for a, b in zip(pd, ref):
+            assert rel(a, b) <= 1e-6
+        assert all(float(x.abs().max()) == 0.0 for x in gd)

@@ -1,0 +1,273 @@
+"""GPU: the drop-in classes (graphsage_b200.models) against the golden fixtures (outputs of the
+reference itself) in injected-sample mode, and against the oracle when the native sampler
+draws.  Tolerance: 1e-5 norm-relative fp32."""
+import io
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import sage_oracle as so
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def rel(a, b):
+    a = np.asarray(a.detach().cpu() if isinstance(a, torch.Tensor) else a, dtype=np.float64)
+    b = np.asarray(b.detach().cpu() if isinstance(b, torch.Tensor) else b, dtype=np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+@pytest.fixture(scope='module')
+def M():
+    import graphsage_b200
+    from graphsage_b200 import models
+    return models
+
+
+def build_models(M, inp, dev, adj=None, seed=1):
+    spec = inp['spec']
+    feats = torch.from_numpy(inp['feats']).to(dev)
+    if adj is None:
+        from graphsage_b200.graph import AdjCSR
+        adj = AdjCSR(inp['rowptr'], inp['col'])
+    model = M.GraphSage(spec['num_layers'], feats.shape[1], spec['hidden'], feats, adj, dev, gcn=spec['gcn'],
+                        agg_func=spec['agg'], seed=seed).to(dev)
+    cls = M.Classification(spec['hidden'], spec['classes']).to(dev)
+    with torch.no_grad():
+        for i, w in enumerate(inp['weights']):
+            getattr(model, f'sage_layer{i + 1}').weight.copy_(torch.from_numpy(w))
+        cls.layer[0].weight.copy_(torch.from_numpy(inp['cls_w']))
+        cls.layer[0].bias.copy_(torch.from_numpy(inp['cls_b']))
+    return model, cls, adj
+
+
+def pairs_from_fixture(fx):
+    npos = {int(n): [] for n in fx['pos_nodes']}
+    nneg = {int(n): [] for n in fx['neg_nodes']}
+    for a, b in fx['pos_pairs']:
+        npos[int(a)].append((int(a), int(b)))
+    for a, b in fx['neg_pairs']:
+        nneg[int(a)].append((int(a), int(b)))
+    return npos, nneg
+
+
+@pytest.mark.parametrize('name', list(cases.CASES))
+def test_injected_sample_parity_with_reference(M, name):
+    dev = torch.device('cuda:0')
+    inp, fx = cases.load_fixture(name)
+    spec = inp['spec']
+    model, cls, adj = build_models(M, inp, dev)
+    batch = fx['batch']
+    model.inject_samples([(c[0], c[1]) for c in fx['calls']])
+    embs = model(batch)                                                     # src/utils.py:157
+    assert embs.shape == (len(batch), spec['hidden'])
+    assert rel(embs, fx['ref_embs']) <= TOL
+    logp = cls(embs)
+    assert rel(logp, fx['ref_logp']) <= TOL
+    labels = inp['labels'][batch]
+    loss_sup = -torch.sum(logp[range(logp.size(0)), labels], 0) / len(batch)      # src/utils.py:162-163
+    assert rel(loss_sup.reshape(1), fx['ref_loss_sup']) <= TOL
+    loss = loss_sup
+    if spec['learn'] != 'sup':
+        unsup = M.UnsupervisedLoss(adj, inp['train'], dev)
+        npos, nneg = pairs_from_fixture(fx)
+        unsup.set_pairs(batch.tolist(), inp['seeds'].tolist(), npos, nneg)
+        net = unsup.get_loss_margin(embs, batch) if spec['unsup_loss'] == 'margin' else unsup.get_loss_sage(embs, batch)
+        assert net.shape == (torch.Size([1]) if spec['unsup_loss'] == 'margin' else torch.Size([]))   # models.py:96,128
+        assert rel(net.reshape(1), fx['ref_loss_net']) <= TOL
+        loss = net if spec['learn'] == 'unsup' else loss_sup + net
+    assert rel(loss.reshape(1), fx['ref_loss']) <= TOL
+    loss.backward()                                                         # src/utils.py:184
+    for layer in range(spec['num_layers']):
+        gw = getattr(model, f'sage_layer{layer + 1}').weight.grad
+        assert rel(gw, fx[f'ref_grad_w{layer + 1}']) <= TOL, f'grad_w{layer + 1}'
+    if spec['learn'] != 'unsup':
+        assert rel(cls.layer[0].weight.grad, fx['ref_grad_cls_w']) <= TOL
+        assert rel(cls.layer[0].bias.grad, fx['ref_grad_cls_b']) <= TOL
+
+
+def _recorded_calls(model):
+    """(nodes, samp_neighs incl. self, unique_list) per call from the model's last forward."""
+    layers = model._last_layers
+    calls = []
+    for fr in reversed(layers):                       # batch-level call first
+        live = fr.rows_max if fr.num_rows is None else int(fr.num_rows.item())
+        nodes = fr.nodes[:live].cpu().tolist()
+        nbr, cnt = fr.nbr[:live].cpu().numpy(), fr.cnt[:live].cpu().numpy()
+        samp = [set(nbr[i, :cnt[i]].tolist()) | {nodes[i]} for i in range(live)]
+        calls.append((nodes, samp, sorted(set.union(*samp))))
+    return calls
+
+
+@pytest.mark.parametrize('gcn,agg', [(False, 'MEAN'), (True, 'MEAN'), (False, 'MAX')])
+def test_native_sampler_forward_backward_vs_oracle(M, gcn, agg):
+    """The device sampler draws; the oracle replays exactly those draws (injection seam), so
+    embeddings / loss / gradients must agree although the RNG streams differ."""
+    dev = torch.device('cuda:0')
+    inp = cases.build_inputs('cora_max_plus')
+    inp['spec'].update(gcn=gcn, agg=agg)
+    wrng = np.random.default_rng(5)
+    f, h = inp['feats'].shape[1], inp['spec']['hidden']
+    from graphsage_b200 import synth
+    inp['weights'] = [synth.xavier_uniform_np(wrng, h, f if gcn else 2 * f), synth.xavier_uniform_np(wrng, h, h if gcn else 2 * h)]
+    model, cls, _ = build_models(M, inp, dev, seed=99)
+    batch = inp['train'][:300]
+    embs = model(batch)
+    logp = cls(embs)
+    labels = inp['labels'][batch]
+    loss = -torch.sum(logp[range(logp.size(0)), labels], 0) / len(batch)
+    loss.backward()
+    calls = _recorded_calls(model)
+    # sampler invariants on the recorded draws
+    deg = np.diff(inp['rowptr'])
+    for nodes, samp, _ in calls:
+        for n, s in zip(nodes, samp):
+            nb = set(inp['col'][inp['rowptr'][n]:inp['rowptr'][n + 1]].tolist())
+            assert (s - {n}) <= nb and len(s - {n}) >= min(deg[n], 10) - (1 if n in nb else 0)
+    w = [torch.from_numpy(x.copy()).requires_grad_(True) for x in inp['weights']]
+    cw = torch.from_numpy(inp['cls_w'].copy()).requires_grad_(True)
+    cb = torch.from_numpy(inp['cls_b'].copy()).requires_grad_(True)
+    adj = so.LazySetAdjacency(inp['rowptr'], inp['col'])
+    o_embs = so.graphsage_forward(w, torch.from_numpy(inp['feats']), adj, batch, gcn, agg,
+                                  injected=[(c[1], c[2]) for c in calls])
+    o_loss = so.supervised_loss(so.classification(cw, cb, o_embs), labels)
+    o_loss.backward()
+    assert rel(embs, o_embs) <= TOL
+    assert rel(loss.reshape(1), o_loss.reshape(1)) <= TOL
+    assert rel(model.sage_layer1.weight.grad, w[0].grad) <= TOL
+    assert rel(model.sage_layer2.weight.grad, w[1].grad) <= TOL
+    assert rel(cls.layer[0].weight.grad, cw.grad) <= TOL
+    # same (seed, call counter) => same draw; next call => different draw
+    model2, _, _ = build_models(M, inp, dev, seed=99)
+    e2 = model2(batch)
+    assert torch.equal(e2, embs)
+    e3 = model2(batch)
+    assert not torch.equal(e3, embs)
+
+
+def test_unsupervised_sampling_semantics_and_loss(M):
+    """Device random walks / far negatives obey src/models.py:153-186; the loss on the device
+    pairs equals the oracle's loss on the same pairs."""
+    dev = torch.device('cuda:0')
+    inp = cases.build_inputs('cora_max_plus')
+    model, cls, adj = build_models(M, inp, dev)
+    train = inp['train']
+    train_set = set(train.tolist())
+    oadj = so.LazySetAdjacency(inp['rowptr'], inp['col'])
+    for num_neg, which in ((6, 'margin'), (100, 'normal')):
+        unsup = M.UnsupervisedLoss(adj, train, dev, seed=7)
+        seeds = train[:20]
+        batch = unsup.extend_nodes(seeds, num_neg=num_neg)
+        assert set(seeds.tolist()) <= set(batch) and len(set(batch)) == len(batch)
+        npos, nneg = unsup.node_positive_pairs, unsup.node_negtive_pairs
+        assert set(i for p in unsup.positive_pairs for i in p) | set(i for p in unsup.negtive_pairs for i in p) \
+            | set(seeds.tolist()) == set(batch)
+        for s in seeds.tolist():
+            assert len(npos[s]) <= 6
+            for a, b in npos[s]:
+                assert a == s and b != s and b in oadj[s] and b in train_set          # :178-180
+            ball, frontier = {s}, {s}
+            for _ in range(5):                                                        # :157-162
+                cur = set()
+                for v in frontier:
+                    cur |= oadj[v]
+                frontier = cur - ball
+                ball |= cur
+            far = train_set - ball
+            got = [b for _, b in nneg[s]]
+            assert len(set(got)) == len(got) == min(num_neg, len(far)) and set(got) <= far   # :163-164
+        batch_np = np.asarray(batch)
+        embs = model(batch_np)
+        loss = unsup.get_loss_margin(embs, batch_np) if which == 'margin' else unsup.get_loss_sage(embs, batch_np)
+        loss.backward()
+        # oracle on the same pairs and the same embeddings
+        ps = so.PairSampler(oadj, train)
+        ps.unique_nodes_batch = list(batch)
+        ps.node_positive_pairs, ps.node_negtive_pairs = npos, nneg
+        e_ref = embs.detach().cpu().clone().requires_grad_(True)
+        o = so.loss_margin(ps, e_ref, batch_np) if which == 'margin' else so.loss_sage(ps, e_ref, batch_np)
+        assert rel(loss.reshape(1), o.reshape(1)) <= TOL
+
+
+def test_pair_loss_gradient_vs_oracle(M):
+    dev = torch.device('cuda:0')
+    inp, fx = cases.load_fixture('cora_max_plus')
+    from graphsage_b200.graph import AdjCSR
+    adj = AdjCSR(inp['rowptr'], inp['col'])
+    npos, nneg = pairs_from_fixture(fx)
+    batch = fx['batch']
+    rng = np.random.default_rng(0)
+    emb = torch.from_numpy(np.maximum(rng.standard_normal((len(batch), 32)), 0).astype(np.float32))
+    for which in ('margin', 'normal'):
+        unsup = M.UnsupervisedLoss(adj, inp['train'], dev)
+        unsup.set_pairs(batch.tolist(), inp['seeds'].tolist(), npos, nneg)
+        e_dev = emb.to(dev).requires_grad_(True)
+        loss = unsup.get_loss_margin(e_dev, batch) if which == 'margin' else unsup.get_loss_sage(e_dev, batch)
+        loss.backward(torch.ones_like(loss) * 1.5)
+        ps = so.PairSampler(so.LazySetAdjacency(inp['rowptr'], inp['col']), inp['train'])
+        ps.unique_nodes_batch = batch.tolist()
+        ps.node_positive_pairs, ps.node_negtive_pairs = npos, nneg
+        e_ref = emb.clone().requires_grad_(True)
+        o = so.loss_margin(ps, e_ref, batch) if which == 'margin' else so.loss_sage(ps, e_ref, batch)
+        o.backward(torch.ones_like(o) * 1.5)
+        assert rel(loss.reshape(1), o.reshape(1)) <= TOL
+        assert rel(e_dev.grad, e_ref.grad) <= TOL
+
+
+def test_dropin_surface(M):
+    """state_dict keys, pickling of live modules (src/utils.py:52), frozen-parameter forward
+    (src/utils.py:20-27), list input (src/utils.py:67), compat methods, loud CPU failure."""
+    dev = torch.device('cuda:0')
+    inp = cases.build_inputs('pubmed_selfloop_mean')
+    model, cls, adj = build_models(M, inp, dev)
+    assert list(model.state_dict()) == ['sage_layer1.weight', 'sage_layer2.weight']
+    assert list(cls.state_dict()) == ['layer.0.weight', 'layer.0.bias']
+    assert model.sage_layer1.weight.shape == (32, 96) and model.out_size == 32
+    for p in list(model.parameters()) + list(cls.parameters()):
+        p.requires_grad = False
+    out = cls(model(list(range(50))))
+    assert out.shape == (50, 3) and not out.requires_grad and torch.isfinite(out).all()
+    buf = io.BytesIO()
+    torch.save([model, cls], buf)
+    buf.seek(0)
+    m2, c2 = torch.load(buf, weights_only=False)
+    assert m2(np.arange(5)).shape == (5, 32)
+    samp, index_of, uniq = model._get_unique_neighs_list(list(range(30)))
+    assert len(samp) == 30 and all(i in s for i, s in enumerate(samp)) and sorted(index_of) == sorted(uniq)
+    assert set(uniq) == set.union(*samp)
+    cpu_model = M.GraphSage(2, 48, 32, torch.from_numpy(inp['feats']), adj, torch.device('cpu'))
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        cpu_model(np.arange(4))
+
+
+def test_training_loop_runs_like_apply_model(M):
+    """The body of src/utils.py:141-191 (extend, forward, loss, backward, clip, SGD) with the
+    drop-in classes: loss must be finite and fall over a few steps."""
+    dev = torch.device('cuda:0')
+    torch.manual_seed(824)
+    inp = cases.build_inputs('cora_max_plus')
+    model, cls, adj = build_models(M, inp, dev, seed=824)
+    unsup = M.UnsupervisedLoss(adj, inp['train'], dev, seed=824)
+    params = list(model.parameters()) + list(cls.parameters())
+    opt = torch.optim.SGD(params, lr=0.7)
+    labels = inp['labels']
+    losses = []
+    for step in range(12):
+        seeds = inp['train'][step * 20:(step + 1) * 20]
+        batch = np.asarray(list(unsup.extend_nodes(seeds, num_neg=6)))
+        embs = model(batch)
+        logp = cls(embs)
+        loss = -torch.sum(logp[range(logp.size(0)), labels[batch]], 0) / len(batch)
+        loss = loss + unsup.get_loss_margin(embs, batch)
+        losses.append(float(loss.item()))
+        loss.backward()
+        for m in (model, cls):
+            torch.nn.utils.clip_grad_norm_(m.parameters(), 5)
+        opt.step()
+        opt.zero_grad()
+    assert all(np.isfinite(losses))
+    assert np.mean(losses[-3:]) < np.mean(losses[:3])
