@@ -69,21 +69,26 @@ sage_fwd_kernel(XOperand x, const float* __restrict__ weight, int64_t ldw, int o
   const int wh = col0 + lw_h;
   float acc[4][4] = {};
   const int kt = x.kv_total();
-  for (int k0 = 0; k0 < kt; k0 += BK) {
-    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 xv;
+  float wv[4];
+  auto fetch = [&](int k0) {                       // global -> registers for the tile starting at k0
+    xv = make_float4(0.f, 0.f, 0.f, 0.f);
     if (xr_ok && k0 + lx_kq < kt) xv = x.load4(xr, self_row, k0 + lx_kq);
-    float wv[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int kv = k0 + lw_kq + i;
       const int wc = kv < kt ? x.wcol(kv) : -1;
       wv[i] = (wc >= 0 && wh < out_dim) ? __ldg(weight + static_cast<int64_t>(wh) * ldw + wc) : 0.f;
     }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < kt; k0 += BK) {
     __syncthreads();
     Xs[lx_kq + 0][lx_row] = xv.x; Xs[lx_kq + 1][lx_row] = xv.y; Xs[lx_kq + 2][lx_row] = xv.z; Xs[lx_kq + 3][lx_row] = xv.w;
 #pragma unroll
     for (int i = 0; i < 4; ++i) Ws[lw_kq + i][lw_h] = wv[i];
     __syncthreads();
+    if (k0 + BK < kt) fetch(k0 + BK);              // next tile's loads fly while this one is multiplied
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) fma_tile(acc, &Xs[kk][ty * 4], &Ws[kk][tx * 4]);
   }
@@ -118,8 +123,8 @@ sage_bwd_x_kernel(const float* __restrict__ grad_out, int64_t ld_go, const float
   const int lb_h = tid >> 4, lb_c = (tid & 15) * 4;            // W : 16 h x 64 cols
   const int ar = row0 + la_row;
   float acc[4][4] = {};
-  for (int h0 = 0; h0 < out_dim; h0 += BK) {
-    float av[4];
+  float av[4], bv[4];
+  auto fetch = [&](int h0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int h = h0 + la_hq + i;
@@ -130,18 +135,21 @@ sage_bwd_x_kernel(const float* __restrict__ grad_out, int64_t ld_go, const float
       }
       av[i] = g;
     }
-    float bv[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int h = h0 + lb_h, c = col0 + lb_c + j;
       bv[j] = (h < out_dim && c < ncols) ? __ldg(weight + static_cast<int64_t>(h) * ldw + c) : 0.f;
     }
+  };
+  fetch(0);
+  for (int h0 = 0; h0 < out_dim; h0 += BK) {
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 4; ++i) As[la_hq + i][la_row] = av[i];
 #pragma unroll
     for (int j = 0; j < 4; ++j) Bs[lb_h][lb_c + j] = bv[j];
     __syncthreads();
+    if (h0 + BK < out_dim) fetch(h0 + BK);
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) fma_tile(acc, &As[kk][ty * 4], &Bs[kk][tx * 4]);
   }
@@ -179,9 +187,11 @@ sage_bwd_w_kernel(XOperand x, const float* __restrict__ grad_out, int64_t ld_go,
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int l_row = tid >> 4, l_q = (tid & 15) * 4;            // 16 rows x 16 float4
   float acc[4][4] = {};
-  for (int r0 = r_begin; r0 < r_end; r0 += BK) {
+  float4 av, bv;
+  auto fetch = [&](int r0) {
     const int r = r0 + l_row;
-    float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = av;
+    av = make_float4(0.f, 0.f, 0.f, 0.f);
+    bv = av;
     if (r < r_end) {
       float g[4];
 #pragma unroll
@@ -200,10 +210,14 @@ sage_bwd_w_kernel(XOperand x, const float* __restrict__ grad_out, int64_t ld_go,
         bv = x.load4(r, self_row, kv);
       }
     }
+  };
+  fetch(r_begin);
+  for (int r0 = r_begin; r0 < r_end; r0 += BK) {
     __syncthreads();
     *reinterpret_cast<float4*>(&As[l_row][l_q]) = av;
     *reinterpret_cast<float4*>(&Bs[l_row][l_q]) = bv;
     __syncthreads();
+    if (r0 + BK < r_end) fetch(r0 + BK);
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) fma_tile(acc, &As[kk][ty * 4], &Bs[kk][tx * 4]);
   }
@@ -237,6 +251,11 @@ using namespace gs;
 
 int gs_sage_gemm_fwd_tc(const float*, int64_t, const int32_t*, const float*, int64_t, int32_t, const float*, int64_t,
                         int32_t, int32_t, const int32_t*, int32_t, float*, int64_t, int32_t, int32_t, gs_stream_t);
+int gs_sage_gemm_bwd_x_tc(const float*, int64_t, const float*, int64_t, const float*, int64_t, int32_t, int32_t, int32_t,
+                          int32_t, const int32_t*, int32_t, float*, int64_t, float*, int64_t, int32_t, gs_stream_t);
+int gs_sage_gemm_bwd_w_tc(const float*, int64_t, const int32_t*, const float*, int64_t, int32_t, const float*, int64_t,
+                          const float*, int64_t, int32_t, int32_t, int32_t, const int32_t*, int32_t, float*, int64_t,
+                          int32_t, gs_stream_t);
 
 extern "C" int gs_sage_gemm_fwd(const float* self_table, int64_t ld_self, const int32_t* self_idx,
                                 const float* agg, int64_t ld_agg, int32_t dim,
@@ -247,6 +266,11 @@ extern "C" int gs_sage_gemm_fwd(const float* self_table, int64_t ld_self, const 
   if (int e = check_x(self_table, ld_self, agg, ld_agg, dim, gcn)) return e;
   if (ldw < (gcn ? dim : 2 * dim) || ld_out < out_dim) return GS_ERR_BAD_ARG;
   if (max_rows == 0) return GS_OK;
+  // The tensor core accumulates its fp32 partial sums with truncation, an error that grows
+  // linearly with the number of K steps (measured 2.8e-6 at K=256, 2.3e-5 at K=2866); the
+  // fp32-faithful mode therefore keeps contractions longer than 1024 on the FFMA path.
+  const int k_total = gcn ? ((dim + 3) & ~3) : 2 * ((dim + 3) & ~3);
+  if (precision == GS_PREC_TF32X3 && k_total > 1024) precision = GS_PREC_FP32;
   if (precision != GS_PREC_FP32)
     return gs_sage_gemm_fwd_tc(self_table, ld_self, self_idx, agg, ld_agg, dim, weight, ldw, out_dim, gcn,
                                num_rows_dev, max_rows, out, ld_out, relu, precision, stream);
@@ -260,12 +284,16 @@ extern "C" int gs_sage_gemm_fwd(const float* self_table, int64_t ld_self, const 
 extern "C" int gs_sage_gemm_bwd_x(const float* grad_out, int64_t ld_go, const float* out, int64_t ld_out,
                                   const float* weight, int64_t ldw, int32_t dim, int32_t out_dim, int32_t gcn,
                                   int32_t relu, const int32_t* num_rows_dev, int32_t max_rows,
-                                  float* grad_self, int64_t ld_gs, float* grad_agg, int64_t ld_ga, gs_stream_t stream) {
+                                  float* grad_self, int64_t ld_gs, float* grad_agg, int64_t ld_ga, int32_t precision,
+                                  gs_stream_t stream) {
   if (!grad_out || !weight || !grad_agg || dim < 1 || out_dim < 1 || max_rows < 0) return GS_ERR_BAD_ARG;
   if (relu && !out) return GS_ERR_BAD_ARG;
   if (!gcn && !grad_self) return GS_ERR_BAD_ARG;
   if (ld_ga < dim || (!gcn && ld_gs < dim) || ldw < (gcn ? dim : 2 * dim)) return GS_ERR_BAD_ARG;
   if (max_rows == 0) return GS_OK;
+  if (precision != GS_PREC_FP32)
+    return gs_sage_gemm_bwd_x_tc(grad_out, ld_go, out, ld_out, weight, ldw, dim, out_dim, gcn, relu, num_rows_dev,
+                                 max_rows, grad_self, ld_gs, grad_agg, ld_ga, precision, stream);
   const int ncols = gcn ? dim : 2 * dim;
   dim3 grid((max_rows + BM - 1) / BM, (ncols + BN - 1) / BN);
   sage_bwd_x_kernel<<<grid, kGemmThreads, 0, as_stream(stream)>>>(grad_out, ld_go, out, ld_out, weight, ldw, dim,
@@ -279,12 +307,15 @@ extern "C" int gs_sage_gemm_bwd_w(const float* self_table, int64_t ld_self, cons
                                   const float* grad_out, int64_t ld_go, const float* out, int64_t ld_out,
                                   int32_t out_dim, int32_t gcn, int32_t relu,
                                   const int32_t* num_rows_dev, int32_t max_rows,
-                                  float* grad_w, int64_t ldw, gs_stream_t stream) {
+                                  float* grad_w, int64_t ldw, int32_t precision, gs_stream_t stream) {
   if (!grad_out || !grad_w || out_dim < 1 || max_rows < 0) return GS_ERR_BAD_ARG;
   if (relu && !out) return GS_ERR_BAD_ARG;
   if (int e = check_x(self_table, ld_self, agg, ld_agg, dim, gcn)) return e;
   if (ldw < (gcn ? dim : 2 * dim)) return GS_ERR_BAD_ARG;
   if (max_rows == 0) return GS_OK;
+  if (precision != GS_PREC_FP32)
+    return gs_sage_gemm_bwd_w_tc(self_table, ld_self, self_idx, agg, ld_agg, dim, grad_out, ld_go, out, ld_out, out_dim,
+                                 gcn, relu, num_rows_dev, max_rows, grad_w, ldw, precision, stream);
   XOperand x{self_table, ld_self, self_idx, agg, ld_agg, dim, (dim + 3) & ~3, gcn};
   const int kt = gcn ? x.dim_pad : 2 * x.dim_pad;
   const int tiles = ((kt + BN - 1) / BN) * ((out_dim + BM - 1) / BM);
@@ -299,5 +330,45 @@ extern "C" int gs_sage_gemm_bwd_w(const float* self_table, int64_t ld_self, cons
   dim3 grid((kt + BN - 1) / BN, (out_dim + BM - 1) / BM, chunks);
   sage_bwd_w_kernel<<<grid, kGemmThreads, 0, as_stream(stream)>>>(x, grad_out, ld_go, out, ld_out, out_dim, relu,
                                                                   num_rows_dev, max_rows, rows_per_chunk, grad_w, ldw);
+  return finish_launch();
+}
+
+// ---------------------------------------------------------------------------------------
+// ReLU backward in place: grad[r, c] = 0 where out[r, c] <= 0.  The tensor-core backward
+// kernels stream dZ with cp.async (no registers in between), so the mask is applied once
+// here instead of inside both of them.
+// ---------------------------------------------------------------------------------------
+namespace gs {
+__global__ void __launch_bounds__(256)
+relu_bwd_kernel(float* __restrict__ grad, int64_t ld_g, const float* __restrict__ out, int64_t ld_out, int dim4,
+                const int32_t* __restrict__ num_rows_dev, int max_rows) {
+  const int rows = live_rows(num_rows_dev, max_rows);
+  const int64_t total = static_cast<int64_t>(rows) * dim4;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / dim4;
+    const int c = static_cast<int>(i - r * dim4) * 4;
+    float4 g = *reinterpret_cast<const float4*>(grad + r * ld_g + c);
+    const float4 o = *reinterpret_cast<const float4*>(out + r * ld_out + c);
+    g.x = o.x > 0.f ? g.x : 0.f;
+    g.y = o.y > 0.f ? g.y : 0.f;
+    g.z = o.z > 0.f ? g.z : 0.f;
+    g.w = o.w > 0.f ? g.w : 0.f;
+    *reinterpret_cast<float4*>(grad + r * ld_g + c) = g;
+  }
+}
+}  // namespace gs
+
+extern "C" int gs_relu_bwd_inplace(float* grad, int64_t ld_g, const float* out, int64_t ld_out, int32_t dim,
+                                   const int32_t* num_rows_dev, int32_t max_rows, gs_stream_t stream) {
+  if (!grad || !out || dim < 1 || max_rows < 0) return GS_ERR_BAD_ARG;
+  const int dim4 = (dim + 3) / 4;
+  if ((ld_g & 3) || (ld_out & 3) || ld_g < 4 * dim4 || ld_out < 4 * dim4 || !aligned16(grad) || !aligned16(out))
+    return GS_ERR_ALIGNMENT;
+  if (max_rows == 0) return GS_OK;
+  const int64_t total = static_cast<int64_t>(max_rows) * dim4;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+  relu_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(grad, ld_g, out, ld_out, dim4, num_rows_dev, max_rows);
   return finish_launch();
 }

@@ -5,71 +5,73 @@
 namespace gs {
 
 // ---------------------------------------------------------------------------------------
-// K1: one thread per destination row.  Replaces src/models.py:279-285.
-//   deg <  k : every neighbour                       (:282 else-branch)
-//   deg >= k : k distinct uniform positions, Floyd's subset sampling: for j in deg-k..deg-1
-//              draw t in [0,j]; take t unless already taken, else take j.  Every k-subset
-//              is equally likely, which is what random.sample gives.
-// The row is then sorted ascending and the node's own id is dropped / inserted once
-// according to self_mode (the `| {self}` of :285 and the `- {self}` of :298).
+// K1: one WARP per destination row, everything in registers.  Replaces src/models.py:279-285.
+//   deg <  k : every neighbour (lane j reads col[beg+j])             (:282 else-branch)
+//   deg >= k : k distinct uniform positions by Floyd's subset sampling: for i in 0..k-1,
+//              j = deg-k+i, draw t in [0,j]; take t unless some earlier pick equals t, else
+//              take j.  Every k-subset is equally likely, which is what random.sample gives.
+//              Lane i owns pick i; the "already taken" test is one warp vote.
+// The k (<= 32) ids are then ranked across lanes (rank = number of smaller valid ids), which
+// sorts the row ascending without a scratch array, and the node's own id is dropped /
+// inserted once according to self_mode (the `| {self}` of :285 and the `- {self}` of :298).
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+constexpr int kSampleWarps = 8;
+
+__global__ void __launch_bounds__(kSampleWarps * 32)
 sample_neighbors_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t num_nodes,
                         const int32_t* __restrict__ nodes, const int32_t* __restrict__ num_rows_dev, int max_rows,
                         int k, int stride, int self_mode, uint64_t seed, uint64_t offset,
                         const int64_t* __restrict__ offset_dev,
                         int32_t* __restrict__ out_nbr, int32_t* __restrict__ out_cnt) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  const int rows = live_rows(num_rows_dev, max_rows);
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * kSampleWarps + (threadIdx.x >> 5);
   if (r >= max_rows) return;
+  const int rows = live_rows(num_rows_dev, max_rows);
   int32_t* dst = out_nbr + static_cast<int64_t>(r) * stride;
   if (r >= rows) {           // keep the padding region well defined for the consumers
-    for (int j = 0; j < stride; ++j) dst[j] = -1;
-    out_cnt[r] = 0;
+    for (int j = lane; j < stride; j += 32) dst[j] = -1;
+    if (lane == 0) out_cnt[r] = 0;
     return;
   }
-  const int32_t me = nodes[r];
-  int32_t sel[GS_MAX_FANOUT + 1];
-  int m = 0;
+  const int32_t me = __ldg(nodes + r);
+  constexpr int32_t kNone = 0x7fffffff;
+  int32_t val = kNone;
   if (me >= 0 && me < num_nodes) {
-    const int64_t beg = rowptr[me];
-    const int64_t deg64 = rowptr[me + 1] - beg;
-    const uint32_t deg = static_cast<uint32_t>(deg64);
+    const int64_t beg = __ldg(rowptr + me);
+    const uint32_t deg = static_cast<uint32_t>(__ldg(rowptr + me + 1) - beg);
     if (deg < static_cast<uint32_t>(k)) {
-      for (uint32_t j = 0; j < deg; ++j) sel[m++] = col[beg + j];
+      if (static_cast<uint32_t>(lane) < deg) val = __ldg(col + beg + lane);
     } else {
       if (offset_dev != nullptr) offset += static_cast<uint64_t>(__ldg(offset_dev)) << 8;
-      PhiloxStream rng(seed, offset, static_cast<uint32_t>(r));
-      uint32_t pos[GS_MAX_FANOUT];
-      for (uint32_t j = deg - k; j < deg; ++j) {
-        uint32_t t = rng.below(j + 1);
-        bool taken = false;
-        for (int q = 0; q < m; ++q) taken |= (pos[q] == t);
-        pos[m++] = taken ? j : t;
+      uint32_t mypos = 0xffffffffu;
+      uint32_t draw[4];
+      for (int i = 0; i < k; ++i) {              // warp-uniform loop: every lane runs the same stream
+        if ((i & 3) == 0)
+          philox4x32_10(static_cast<uint32_t>(r), static_cast<uint32_t>(i >> 2), static_cast<uint32_t>(offset),
+                        static_cast<uint32_t>(offset >> 32), seed, draw);
+        const uint32_t x = (i & 3) == 0 ? draw[0] : (i & 3) == 1 ? draw[1] : (i & 3) == 2 ? draw[2] : draw[3];
+        const uint32_t j = deg - k + i;
+        const uint32_t t = __umulhi(x, j + 1);   // uniform in [0, j]
+        const bool taken = __any_sync(0xffffffffu, mypos == t);
+        if (lane == i) mypos = taken ? j : t;
       }
-      for (int q = 0; q < m; ++q) sel[q] = col[beg + pos[q]];
+      if (lane < k) val = __ldg(col + beg + mypos);
     }
   }
-  // insertion sort (m <= 32) ascending by node id
-  for (int a = 1; a < m; ++a) {
-    int32_t v = sel[a];
-    int b = a - 1;
-    while (b >= 0 && sel[b] > v) { sel[b + 1] = sel[b]; --b; }
-    sel[b + 1] = v;
+  bool valid = val != kNone;
+  if (self_mode != GS_SELF_KEEP && val == me) valid = false;
+  if (self_mode == GS_SELF_ONCE && lane == 31) { val = me; valid = true; }     // k <= 31 in this mode
+  int rank = 0;
+  const int scan = (self_mode == GS_SELF_ONCE) ? 32 : k;
+  for (int o = 0; o < scan; ++o) {
+    const int32_t v = __shfl_sync(0xffffffffu, val, o);
+    const bool ok = __shfl_sync(0xffffffffu, static_cast<int>(valid), o) != 0;
+    rank += (ok && v < val) ? 1 : 0;
   }
-  if (self_mode != GS_SELF_KEEP) {
-    int w = 0;
-    for (int q = 0; q < m; ++q) if (sel[q] != me) sel[w++] = sel[q];
-    m = w;
-    if (self_mode == GS_SELF_ONCE) {
-      int b = m - 1;
-      while (b >= 0 && sel[b] > me) { sel[b + 1] = sel[b]; --b; }
-      sel[b + 1] = me;
-      ++m;
-    }
-  }
-  for (int j = 0; j < stride; ++j) dst[j] = j < m ? sel[j] : -1;
-  out_cnt[r] = m;
+  const int m = __popc(__ballot_sync(0xffffffffu, valid));
+  if (valid) dst[rank] = val;
+  for (int j = m + lane; j < stride; j += 32) dst[j] = -1;
+  if (lane == 0) out_cnt[r] = m;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -242,11 +244,11 @@ extern "C" int gs_sample_neighbors(const int64_t* rowptr, const int32_t* col, in
                                    const int64_t* offset_dev, int32_t* out_nbr, int32_t* out_cnt, gs_stream_t stream) {
   if (!rowptr || !col || !nodes || !out_nbr || !out_cnt) return GS_ERR_BAD_ARG;
   if (k < 1 || k > GS_MAX_FANOUT || max_rows < 0) return GS_ERR_BAD_ARG;
+  if (self_mode == GS_SELF_ONCE && k > GS_MAX_FANOUT - 1) return GS_ERR_UNSUPPORTED;
   if (stride < k + (self_mode == GS_SELF_ONCE ? 1 : 0)) return GS_ERR_BAD_ARG;
   if (self_mode < GS_SELF_KEEP || self_mode > GS_SELF_ONCE) return GS_ERR_BAD_ARG;
   if (max_rows == 0) return GS_OK;
-  const int threads = 128;
-  sample_neighbors_kernel<<<(max_rows + threads - 1) / threads, threads, 0, as_stream(stream)>>>(
+  sample_neighbors_kernel<<<(max_rows + kSampleWarps - 1) / kSampleWarps, kSampleWarps * 32, 0, as_stream(stream)>>>(
       rowptr, col, num_nodes, nodes, num_rows_dev, max_rows, k, stride, self_mode, seed, offset, offset_dev, out_nbr,
       out_cnt);
   return finish_launch();

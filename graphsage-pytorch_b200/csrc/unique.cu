@@ -328,6 +328,140 @@ __global__ void remap_kernel(const int32_t* __restrict__ nodes, const int32_t* _
   }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// bitmap path: unique + remap in O(M + N/32) memory-parallel work, no sort.
+//   mark  : bitmap[id>>5] |= 1<<(id&31) for every input id            (M atomics, spread)
+//   scan  : per-word exclusive popcount prefix (4096-word blocks + one block of block sums)
+//   emit  : every set bit writes its id at its rank  -> uniq ascending
+//   remap : rank(id) = prefix[word] + popc(bits below id)
+//   clear : the touched words are zeroed again, so the bitmap is all-zero between calls
+// Output is identical to the radix path (ascending unique ids), bit for bit.
+// ---------------------------------------------------------------------------------------
+constexpr int kBmBlockWords = 4096;   // words per scan block: 1024 threads x uint4
+
+__device__ __forceinline__ int32_t combined_id(const int32_t* __restrict__ nodes, const int32_t* __restrict__ nbr,
+                                               int rows, int stride, int64_t i) {
+  if (i < rows) return nodes[i];
+  return nbr[i - rows];
+}
+
+__global__ void __launch_bounds__(256)
+bitmap_mark_kernel(const int32_t* __restrict__ nodes, const int32_t* __restrict__ num_rows_dev, int max_rows,
+                   const int32_t* __restrict__ nbr, int stride, int64_t num_nodes, uint32_t* __restrict__ bitmap,
+                   int clear) {
+  const int rows = live_rows(num_rows_dev, max_rows);
+  const int64_t m = static_cast<int64_t>(rows) * (stride + 1);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < m;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int32_t id = combined_id(nodes, nbr, rows, stride, i);
+    if (id < 0 || id >= num_nodes) continue;
+    if (clear) bitmap[id >> 5] = 0u;
+    else atomicOr(&bitmap[id >> 5], 1u << (id & 31));
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+bitmap_scan_kernel(const uint32_t* __restrict__ bitmap, int32_t* __restrict__ wprefix, uint32_t* __restrict__ block_sum) {
+  __shared__ int s_warp[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t w0 = static_cast<int64_t>(blockIdx.x) * kBmBlockWords + 4 * tid;
+  const uint4 b = *reinterpret_cast<const uint4*>(bitmap + w0);
+  const int c0 = __popc(b.x), c1 = __popc(b.y), c2 = __popc(b.z), c3 = __popc(b.w);
+  const int mine = c0 + c1 + c2 + c3;
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int v = s_warp[lane], wi = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    s_warp[lane] = wi - v;
+    if (lane == 31) block_sum[blockIdx.x] = static_cast<uint32_t>(wi);
+  }
+  __syncthreads();
+  const int base = s_warp[warp] + incl - mine;
+  *reinterpret_cast<int4*>(wprefix + w0) = make_int4(base, base + c0, base + c0 + c1, base + c0 + c1 + c2);
+}
+
+__global__ void __launch_bounds__(256)
+bitmap_emit_remap_kernel(const int32_t* __restrict__ nodes, const int32_t* __restrict__ num_rows_dev, int max_rows,
+                         const int32_t* __restrict__ nbr, int stride, int64_t num_nodes, int64_t words,
+                         int emit_blocks, const uint32_t* __restrict__ bitmap, const int32_t* __restrict__ wprefix,
+                         const uint32_t* __restrict__ block_sum, int32_t* __restrict__ uniq,
+                         int32_t* __restrict__ nbr_idx, int32_t* __restrict__ self_idx) {
+  if (static_cast<int>(blockIdx.x) < emit_blocks) {            // ---- emit: one thread per bitmap word
+    const int64_t w = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (w >= words) return;
+    uint32_t bits = bitmap[w];
+    if (bits == 0u) return;
+    int at = static_cast<int>(block_sum[w / kBmBlockWords]) + wprefix[w];
+    while (bits) {
+      const int b = __ffs(bits) - 1;
+      uniq[at++] = static_cast<int32_t>(w * 32 + b);
+      bits &= bits - 1;
+    }
+    return;
+  }
+  // ---- remap: one thread per input slot
+  const int rows = live_rows(num_rows_dev, max_rows);
+  const int64_t live = static_cast<int64_t>(rows) * stride, all = static_cast<int64_t>(max_rows) * stride;
+  const int64_t t0 = static_cast<int64_t>(blockIdx.x - emit_blocks) * blockDim.x + threadIdx.x;
+  const int64_t step = static_cast<int64_t>(gridDim.x - emit_blocks) * blockDim.x;
+  auto rank_of = [&](int32_t id) -> int32_t {
+    const int64_t w = id >> 5;
+    return static_cast<int32_t>(block_sum[w / kBmBlockWords]) + wprefix[w] +
+           __popc(bitmap[w] & ((1u << (id & 31)) - 1u));
+  };
+  if (nbr_idx != nullptr) {
+    for (int64_t i = t0; i < all; i += step) {
+      int32_t idx = -1;
+      if (i < live) {
+        const int32_t id = nbr[i];
+        if (id >= 0 && id < num_nodes) idx = rank_of(id);
+      }
+      nbr_idx[i] = idx;
+    }
+  }
+  if (self_idx != nullptr) {
+    for (int64_t i = t0; i < max_rows; i += step) {
+      int32_t idx = -1;
+      if (i < rows) {
+        const int32_t id = nodes[i];
+        if (id >= 0 && id < num_nodes) idx = rank_of(id);
+      }
+      self_idx[i] = idx;
+    }
+  }
+}
+
+struct BitmapPlan {
+  int64_t words, words_pad;
+  int nblk;
+  size_t off_prefix, off_bsum, total;
+};
+
+static BitmapPlan make_bitmap_plan(int64_t num_nodes) {
+  BitmapPlan p{};
+  p.words = (num_nodes + 31) / 32;
+  p.nblk = static_cast<int>((p.words + kBmBlockWords - 1) / kBmBlockWords);
+  if (p.nblk < 1) p.nblk = 1;
+  p.words_pad = static_cast<int64_t>(p.nblk) * kBmBlockWords;
+  size_t off = static_cast<size_t>(p.words_pad) * 4;
+  p.off_prefix = off; off += static_cast<size_t>(p.words_pad) * 4;
+  p.off_bsum = off;   off += static_cast<size_t>(p.nblk + 1) * 4;
+  p.total = (off + 15) & ~static_cast<size_t>(15);
+  return p;
+}
+
 struct UniquePlan {
   bool small;
   int cap_keys;       // padded key capacity
@@ -423,4 +557,42 @@ extern "C" int gs_unique_remap(const int32_t* nodes, const int32_t* num_rows_dev
     ++launches;
   }
   return finish_launch(launches);
+}
+
+extern "C" size_t gs_unique_bitmap_workspace_bytes(int64_t num_nodes) {
+  if (num_nodes < 1) return 0;
+  return make_bitmap_plan(num_nodes).total;
+}
+
+extern "C" int gs_unique_remap_bitmap(const int32_t* nodes, const int32_t* num_rows_dev, int32_t max_rows,
+                                      const int32_t* nbr, int32_t stride, int64_t num_nodes,
+                                      int32_t* uniq, int32_t* num_uniq_dev, int32_t* nbr_idx, int32_t* self_idx,
+                                      void* workspace, size_t workspace_bytes, gs_stream_t stream) {
+  if (!nodes || !uniq || !num_uniq_dev || max_rows < 0 || stride < 0 || num_nodes < 1) return GS_ERR_BAD_ARG;
+  if (stride > 0 && !nbr) return GS_ERR_BAD_ARG;
+  if (num_nodes > (1ll << 31)) return GS_ERR_UNSUPPORTED;
+  const BitmapPlan p = make_bitmap_plan(num_nodes);
+  if (!workspace || workspace_bytes < p.total || !aligned16(workspace)) return GS_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  if (max_rows == 0) {
+    cudaError_t e = cudaMemsetAsync(num_uniq_dev, 0, sizeof(int32_t), st);
+    return e == cudaSuccess ? GS_OK : static_cast<int>(e);
+  }
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  uint32_t* bitmap = reinterpret_cast<uint32_t*>(ws);
+  int32_t* wprefix = reinterpret_cast<int32_t*>(ws + p.off_prefix);
+  uint32_t* bsum = reinterpret_cast<uint32_t*>(ws + p.off_bsum);
+  const int64_t m = static_cast<int64_t>(max_rows) * (stride + 1);
+  const int id_blocks = static_cast<int>(std::min<int64_t>((m + 255) / 256, 148 * 8));
+  bitmap_mark_kernel<<<id_blocks, 256, 0, st>>>(nodes, num_rows_dev, max_rows, nbr, stride, num_nodes, bitmap, 0);
+  bitmap_scan_kernel<<<p.nblk, 1024, 0, st>>>(bitmap, wprefix, bsum);
+  exclusive_scan_kernel<<<1, 1024, 0, st>>>(bsum, p.nblk, num_uniq_dev);
+  const int emit_blocks = static_cast<int>((p.words + 255) / 256);
+  const int64_t slots = static_cast<int64_t>(max_rows) * (stride > 0 ? stride : 1);
+  const int remap_blocks = static_cast<int>(std::min<int64_t>((slots + 255) / 256, 148 * 8));
+  bitmap_emit_remap_kernel<<<emit_blocks + remap_blocks, 256, 0, st>>>(nodes, num_rows_dev, max_rows, nbr, stride,
+                                                                      num_nodes, p.words, emit_blocks, bitmap, wprefix,
+                                                                      bsum, uniq, nbr_idx, self_idx);
+  bitmap_mark_kernel<<<id_blocks, 256, 0, st>>>(nodes, num_rows_dev, max_rows, nbr, stride, num_nodes, bitmap, 1);
+  return finish_launch(5);
 }

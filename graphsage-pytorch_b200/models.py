@@ -153,7 +153,7 @@ class _SageLayerFn(torch.autograd.Function):
 class SageLayer(nn.Module):
     """relu(W . cat[self, agg]^T)^T ; src/models.py:189-220 (no bias, ReLU on every layer)."""
 
-    def __init__(self, input_size, out_size, gcn=False, precision: str = "fp32"):
+    def __init__(self, input_size, out_size, gcn=False, precision: str = "tf32x3"):
         super().__init__()
         self.input_size = input_size
         self.out_size = out_size
@@ -202,7 +202,8 @@ class GraphSage(nn.Module):
     (`num_sample`, `precision`, `seed`) default to the reference's behaviour."""
 
     def __init__(self, num_layers, input_size, out_size, raw_features, adj_lists, device, gcn=False, agg_func='MEAN',
-                 *, num_sample: int = 10, precision: str = "fp32", seed: Optional[int] = None):
+                 *, num_sample: int = 10, precision: str = "tf32x3", seed: Optional[int] = None,
+                 unique_algo: str = "auto"):
         super().__init__()
         if agg_func not in ('MEAN', 'MAX'):
             raise ValueError("agg_func must be 'MEAN' or 'MAX' (src/models.py:311,316)")
@@ -217,12 +218,16 @@ class GraphSage(nn.Module):
         self.device = device
         self.agg_func = agg_func
         self.num_sample = num_sample          # src/models.py:277 default argument
+        if unique_algo not in ("auto", "bitmap", "radix"):
+            raise ValueError("unique_algo must be 'auto', 'bitmap' or 'radix'")
+        self.unique_algo = unique_algo        # K2 path: bitmap/rank (default when N <= 2^28) or radix sort
         self.precision = precision
         self.raw_features = raw_features      # :234
         self.adj_lists = adj_lists            # :235
         self.seed = int(torch.initial_seed() if seed is None else seed) & 0x7FFFFFFFFFFFFFFF
         self._calls = 0
         self._native_state = None
+        self._bitmap_ws = None
         self._injected = None
         self._last_layers = None
         for index in range(1, num_layers + 1):                                # :237-239
@@ -233,6 +238,7 @@ class GraphSage(nn.Module):
     def __getstate__(self):
         state = self.__dict__.copy()
         state['_native_state'] = None
+        state['_bitmap_ws'] = None
         state['_last_layers'] = None
         state['_injected'] = None
         return state
@@ -253,6 +259,8 @@ class GraphSage(nn.Module):
             table = _padded_table(feats.to(dev))
             csr = _device_csr(self.adj_lists, table.shape[0], dev)
             self._native_state = (csr, table, torch.device(dev))
+            use_bitmap = self.unique_algo == "bitmap" or (self.unique_algo == "auto" and csr.num_nodes <= (1 << 28))
+            self._bitmap_ws = ops.unique_bitmap_workspace(csr.num_nodes, dev) if use_bitmap else None
         return self._native_state
 
     def inject_samples(self, calls):
@@ -323,8 +331,12 @@ class GraphSage(nn.Module):
                 fr.nbr, fr.cnt = ops.sample_neighbors(csr.rowptr, csr.col, csr.num_nodes, nodes, num_rows, rows_max, k,
                                                       fr.stride, self_mode, self.seed, offset, offset_dev=offset_dev)
             if l > 1:   # unique + remap (src/models.py:286-288); the next frontier is U, ascending
-                uniq, num_uniq, fr.nbr_idx, fr.self_idx = ops.unique_remap(nodes, num_rows, rows_max, fr.nbr, fr.stride,
-                                                                           csr.id_bits)
+                if self._bitmap_ws is not None:
+                    uniq, num_uniq, fr.nbr_idx, fr.self_idx = ops.unique_remap_bitmap(
+                        nodes, num_rows, rows_max, fr.nbr, fr.stride, csr.num_nodes, self._bitmap_ws)
+                else:
+                    uniq, num_uniq, fr.nbr_idx, fr.self_idx = ops.unique_remap(nodes, num_rows, rows_max, fr.nbr,
+                                                                               fr.stride, csr.id_bits)
                 nodes, num_rows = uniq, num_uniq
                 rows_max = min(rows_max * (fr.stride + 1), max(csr.num_nodes, 1))
             else:       # layer 1 gathers straight from the feature table by node id: no U0, no remap
@@ -342,12 +354,19 @@ class GraphSage(nn.Module):
         return layers[1:]
 
     def _run_backward(self, layers: List[_Frontier], grad_out: torch.Tensor, weights, needs,
-                      grad_bufs=None) -> List[Optional[torch.Tensor]]:
+                      grad_bufs=None, own_grad: bool = False) -> List[Optional[torch.Tensor]]:
         """Weight gradients of all layers.  `grad_bufs` (optional, pre-zeroed) receive them in
-        place (static buffers of the captured train step); otherwise fresh tensors are returned."""
+        place (static buffers of the captured train step); otherwise fresh tensors are returned.
+        `own_grad`: grad_out is a scratch buffer of the caller and may be overwritten."""
         L, H = self.num_layers, self.out_size
         mode = native.AGG_MEAN if self.agg_func == 'MEAN' else native.AGG_MAX
+        prec = _PRECISIONS[self.precision]
+        # tensor-core path: dZ = grad * (h > 0) is formed once, in place, and the GEMMs run with
+        # relu=False (they stream dZ with cp.async); the FFMA path masks while loading its tiles.
+        premask = prec != native.PREC_FP32
         g = _padded_table(grad_out)
+        if premask and not own_grad and g.data_ptr() == grad_out.data_ptr():
+            g = g.clone()                # never overwrite a gradient tensor autograd handed us
         grads: List[Optional[torch.Tensor]] = [None] * L
         lowest = min((i for i in range(L) if needs[i]), default=None)
         if lowest is None:
@@ -355,14 +374,17 @@ class GraphSage(nn.Module):
         for l in range(L, 0, -1):
             fr = layers[l - 1]
             w = weights[l - 1]
+            if premask:
+                ops.relu_bwd_inplace(g, fr.h, H, fr.num_rows, fr.rows_max)
             if needs[l - 1]:
                 gw = torch.zeros_like(w) if grad_bufs is None else grad_bufs[l - 1]
                 ops.sage_gemm_bwd_w(None if self.gcn else fr.table_in, fr.self_idx, fr.agg, fr.dim_in, g, fr.h, H,
-                                    self.gcn, True, fr.num_rows, fr.rows_max, gw)
+                                    self.gcn, not premask, fr.num_rows, fr.rows_max, gw, precision=prec)
                 grads[l - 1] = gw
             if l - 1 <= lowest:          # nothing below needs a gradient (raw features never do)
                 break
-            gs, ga = ops.sage_gemm_bwd_x(g, fr.h, w, fr.dim_in, H, self.gcn, True, fr.num_rows, fr.rows_max)
+            gs, ga = ops.sage_gemm_bwd_x(g, fr.h, w, fr.dim_in, H, self.gcn, not premask, fr.num_rows, fr.rows_max,
+                                         precision=prec)
             prev = layers[l - 2]
             g_prev = torch.zeros((prev.rows_max, ops.pad4(H)), dtype=torch.float32, device=g.device)
             ops.agg_bwd(ga, gs, fr.dim_in, fr.nbr_idx, fr.stride, fr.cnt, fr.self_idx, fr.argmax, fr.num_rows,

@@ -71,6 +71,33 @@ def unique_remap(nodes, num_rows, max_rows: int, nbr, stride: int, id_bits: int,
     return uniq, num_uniq, nbr_idx, self_idx
 
 
+def unique_bitmap_workspace(num_nodes: int, device) -> torch.Tensor:
+    """Zero-initialised scratch of the bitmap path; allocate once per graph and reuse (every
+    call leaves the bitmap part zeroed again)."""
+    n = int(_lib().gs_unique_bitmap_workspace_bytes(num_nodes))
+    return torch.zeros((max(n, 16),), dtype=torch.uint8, device=device)
+
+
+def unique_remap_bitmap(nodes, num_rows, max_rows: int, nbr, stride: int, num_nodes: int, workspace, *, uniq=None,
+                        num_uniq=None, nbr_idx=None, self_idx=None, want_nbr_idx=True, want_self_idx=True):
+    """Same contract and outputs as unique_remap, via the bitmap/rank path (gs_unique_remap_bitmap)."""
+    native.require_cuda(nodes, "nodes")
+    dev = nodes.device
+    cap = min(max_rows * (stride + 1), max(num_nodes, 1))
+    if uniq is None:
+        uniq = torch.empty((max(cap, 1),), dtype=I32, device=dev)
+    if num_uniq is None:
+        num_uniq = torch.empty((1,), dtype=I32, device=dev)
+    if nbr_idx is None and want_nbr_idx and stride > 0:
+        nbr_idx = torch.empty((max_rows, stride), dtype=I32, device=dev)
+    if self_idx is None and want_self_idx:
+        self_idx = torch.empty((max_rows,), dtype=I32, device=dev)
+    check(_lib().gs_unique_remap_bitmap(ptr(nodes), ptr(num_rows), max_rows, ptr(nbr), stride, num_nodes, ptr(uniq),
+                                        ptr(num_uniq), ptr(nbr_idx), ptr(self_idx), ptr(workspace), workspace.numel(),
+                                        stream()), "gs_unique_remap_bitmap")
+    return uniq, num_uniq, nbr_idx, self_idx
+
+
 # ----------------------------------------------------------------------------------------------
 # K3
 # ----------------------------------------------------------------------------------------------
@@ -117,17 +144,17 @@ def sage_gemm_fwd(self_table, self_idx, agg, dim: int, weight, out_dim: int, gcn
 
 
 def sage_gemm_bwd_w(self_table, self_idx, agg, dim: int, grad_out, out, out_dim: int, gcn: bool, relu: bool, num_rows,
-                    max_rows: int, grad_w):
+                    max_rows: int, grad_w, precision: int = native.PREC_FP32):
     check(_lib().gs_sage_gemm_bwd_w(ptr(self_table), self_table.stride(0) if self_table is not None else 0,
                                     ptr(self_idx), ptr(agg), agg.stride(0), dim, ptr(grad_out), grad_out.stride(0),
                                     ptr(out), out.stride(0) if out is not None else 0, out_dim, int(gcn), int(relu),
-                                    ptr(num_rows), max_rows, ptr(grad_w), grad_w.stride(0), stream()),
+                                    ptr(num_rows), max_rows, ptr(grad_w), grad_w.stride(0), precision, stream()),
           "gs_sage_gemm_bwd_w")
     return grad_w
 
 
 def sage_gemm_bwd_x(grad_out, out, weight, dim: int, out_dim: int, gcn: bool, relu: bool, num_rows, max_rows: int,
-                    grad_self=None, grad_agg=None):
+                    grad_self=None, grad_agg=None, precision: int = native.PREC_FP32):
     dev = grad_out.device
     ld = pad4(dim)
     alloc = torch.empty if ld == dim else torch.zeros
@@ -138,30 +165,38 @@ def sage_gemm_bwd_x(grad_out, out, weight, dim: int, out_dim: int, gcn: bool, re
     check(_lib().gs_sage_gemm_bwd_x(ptr(grad_out), grad_out.stride(0), ptr(out), out.stride(0) if out is not None else 0,
                                     ptr(weight), weight.stride(0), dim, out_dim, int(gcn), int(relu), ptr(num_rows),
                                     max_rows, ptr(grad_self), grad_self.stride(0) if grad_self is not None else 0,
-                                    ptr(grad_agg), grad_agg.stride(0), stream()), "gs_sage_gemm_bwd_x")
+                                    ptr(grad_agg), grad_agg.stride(0), precision, stream()), "gs_sage_gemm_bwd_x")
     return grad_self, grad_agg
+
+
+def relu_bwd_inplace(grad, out, dim: int, num_rows, max_rows: int):
+    """grad[r, c] = 0 where out[r, c] <= 0 (in place)."""
+    check(_lib().gs_relu_bwd_inplace(ptr(grad), grad.stride(0), ptr(out), out.stride(0), dim, ptr(num_rows), max_rows,
+                                     stream()), "gs_relu_bwd_inplace")
+    return grad
 
 
 # ----------------------------------------------------------------------------------------------
 # classifier / loss / update
 # ----------------------------------------------------------------------------------------------
-def cls_fwd(emb, dim: int, weight, bias, num_classes: int, logp=None):
+def cls_fwd(emb, dim: int, weight, bias, num_classes: int, logp=None, precision: int = native.PREC_TF32X3):
     native.require_cuda(emb, "embeds")
     rows = emb.shape[0]
     if logp is None:
         logp = torch.empty((rows, num_classes), dtype=F32, device=emb.device)
     check(_lib().gs_cls_fwd(ptr(emb), emb.stride(0), rows, dim, ptr(weight), ptr(bias), num_classes, ptr(logp),
-                            stream()), "gs_cls_fwd")
+                            precision, stream()), "gs_cls_fwd")
     return logp
 
 
-def cls_bwd(grad_logp, logp, emb, dim: int, weight, num_classes: int, grad_emb, grad_w, grad_b, scratch=None):
+def cls_bwd(grad_logp, logp, emb, dim: int, weight, num_classes: int, grad_emb, grad_w, grad_b, scratch=None,
+            precision: int = native.PREC_TF32X3):
     rows = emb.shape[0]
     if scratch is None:
         scratch = torch.empty((rows, num_classes), dtype=F32, device=emb.device)
     check(_lib().gs_cls_bwd(ptr(grad_logp), ptr(logp), ptr(emb), emb.stride(0), rows, dim, ptr(weight), num_classes,
                             ptr(grad_emb), grad_emb.stride(0) if grad_emb is not None else 0, ptr(grad_w), ptr(grad_b),
-                            ptr(scratch), stream()), "gs_cls_bwd")
+                            ptr(scratch), precision, stream()), "gs_cls_bwd")
 
 
 def nll_fwd_bwd(logp, labels, loss=None, grad_logp=None, want_grad=True, label_index=None):
@@ -174,6 +209,21 @@ def nll_fwd_bwd(logp, labels, loss=None, grad_logp=None, want_grad=True, label_i
                                 stream()),
           "gs_nll_fwd_bwd")
     return loss, grad_logp
+
+
+def cls_nll_fwd_bwd(emb, dim: int, weight, bias, num_classes: int, labels, label_index, loss, grad_emb, grad_w, grad_b,
+                    logp=None, scratch=None, precision: int = native.PREC_TF32X3):
+    """Classifier + NLL(mean) forward and backward in one call (src/models.py:25-27, src/utils.py:153,162-163)."""
+    rows = emb.shape[0]
+    if logp is None:
+        logp = torch.empty((rows, num_classes), dtype=F32, device=emb.device)
+    if scratch is None:
+        scratch = torch.empty((rows, num_classes), dtype=F32, device=emb.device)
+    check(_lib().gs_cls_nll_fwd_bwd(ptr(emb), emb.stride(0), rows, dim, ptr(weight), ptr(bias), num_classes, ptr(labels),
+                                    ptr(label_index), ptr(logp), ptr(loss), ptr(grad_emb),
+                                    grad_emb.stride(0) if grad_emb is not None else 0, ptr(grad_w), ptr(grad_b),
+                                    ptr(scratch), precision, stream()), "gs_cls_nll_fwd_bwd")
+    return logp
 
 
 class TensorList:

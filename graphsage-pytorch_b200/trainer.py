@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import native, ops
-from .models import Classification, GraphSage
+from .models import _PRECISIONS, Classification, GraphSage
 
 
 class SupervisedTrainer:
@@ -64,13 +64,12 @@ class SupervisedTrainer:
         self.last_layers = layers
         emb = layers[-1].h
         classes = self.cls_w.shape[0]
-        logp = ops.cls_fwd(emb, m.out_size, self.cls_w.detach(), self.cls_b.detach(), classes)
-        _, glogp = ops.nll_fwd_bwd(logp, self.labels, loss=self.loss, label_index=self.seeds)        # utils.py:153,162-163
         gemb = torch.empty_like(emb)
         n_sage = len(self.weights)
-        ops.cls_bwd(glogp, logp, emb, m.out_size, self.cls_w.detach(), classes, gemb, self.grads[n_sage],
-                    self.grads[n_sage + 1])
-        m._run_backward(layers, gemb, weights, [True] * n_sage, grad_bufs=self.grads[:n_sage])
+        ops.cls_nll_fwd_bwd(emb, m.out_size, self.cls_w.detach(), self.cls_b.detach(), classes, self.labels, self.seeds,
+                            self.loss, gemb, self.grads[n_sage], self.grads[n_sage + 1],
+                            precision=_PRECISIONS[m.precision])                                # utils.py:153,161-163
+        m._run_backward(layers, gemb, weights, [True] * n_sage, grad_bufs=self.grads[:n_sage], own_grad=True)
         self.step_counter.add_(1)
 
     def _update(self):

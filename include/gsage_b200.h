@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 4
+#define GS_ABI_VERSION 6
 
 #define GS_OK 0
 #define GS_ERR_BAD_ARG (-1)
@@ -84,6 +84,17 @@ int gs_unique_remap(const int32_t* nodes, const int32_t* num_rows_dev, int32_t m
                     int32_t* uniq, int32_t* num_uniq_dev, int32_t* nbr_idx, int32_t* self_idx,
                     void* workspace, size_t workspace_bytes, gs_stream_t stream);
 
+/* K2, bitmap path: same outputs as gs_unique_remap (ascending unique ids, bit for bit) in
+ * O(M + N/32) memory-parallel work: mark ids in a num_nodes-bit map, popcount-scan it, emit
+ * set bits at their rank, remap by rank lookup, clear the touched words.  The first
+ * ceil(num_nodes/32) words (rounded up to 4096) of `workspace` are the bitmap: the caller
+ * zeroes the workspace ONCE; every call leaves the bitmap zeroed again. */
+size_t gs_unique_bitmap_workspace_bytes(int64_t num_nodes);
+int gs_unique_remap_bitmap(const int32_t* nodes, const int32_t* num_rows_dev, int32_t max_rows,
+                           const int32_t* nbr, int32_t stride, int64_t num_nodes,
+                           int32_t* uniq, int32_t* num_uniq_dev, int32_t* nbr_idx, int32_t* self_idx,
+                           void* workspace, size_t workspace_bytes, gs_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * K3  gather-segment-reduce.  Replaces GraphSage.aggregate, src/models.py:300-326 (the
  * embed_matrix gather, the dense mask, its normalisation and mask.mm / the MAX loop).
@@ -125,30 +136,47 @@ int gs_sage_gemm_bwd_w(const float* self_table, int64_t ld_self, const int32_t* 
                        const float* grad_out, int64_t ld_go, const float* out, int64_t ld_out,
                        int32_t out_dim, int32_t gcn, int32_t relu,
                        const int32_t* num_rows_dev, int32_t max_rows,
-                       float* grad_w, int64_t ldw, gs_stream_t stream);
+                       float* grad_w, int64_t ldw, int32_t precision, gs_stream_t stream);
 
 /* dX[r,k] = sum_h dZ[r,h] W[h,k]  -> grad_self[r,:dim] (non-gcn) and grad_agg[r,:dim]. */
 int gs_sage_gemm_bwd_x(const float* grad_out, int64_t ld_go, const float* out, int64_t ld_out,
                        const float* weight, int64_t ldw, int32_t dim, int32_t out_dim, int32_t gcn, int32_t relu,
                        const int32_t* num_rows_dev, int32_t max_rows,
-                       float* grad_self, int64_t ld_gs, float* grad_agg, int64_t ld_ga, gs_stream_t stream);
+                       float* grad_self, int64_t ld_gs, float* grad_agg, int64_t ld_ga, int32_t precision,
+                       gs_stream_t stream);
+
+/* ReLU backward in place: grad[r,c] = 0 where out[r,c] <= 0.  Used before the tensor-core
+ * backward kernels (called with relu = 0), which stream dZ with cp.async. */
+int gs_relu_bwd_inplace(float* grad, int64_t ld_g, const float* out, int64_t ld_out, int32_t dim,
+                        const int32_t* num_rows_dev, int32_t max_rows, gs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Classification, src/models.py:25-27: logp = log_softmax(emb . W^T + b).
  * ------------------------------------------------------------------------------------ */
 int gs_cls_fwd(const float* emb, int64_t ld_emb, int32_t rows, int32_t dim,
                const float* weight, const float* bias, int32_t num_classes,
-               float* logp, gs_stream_t stream);
+               float* logp, int32_t precision, gs_stream_t stream);
 /* backward through log_softmax + Linear; grad_w / grad_b accumulate (zero them first);
  * grad_emb (nullable) is overwritten.  scratch: rows*num_classes floats (grad of the logits). */
 int gs_cls_bwd(const float* grad_logp, const float* logp, const float* emb, int64_t ld_emb,
                int32_t rows, int32_t dim, const float* weight, int32_t num_classes,
-               float* grad_emb, int64_t ld_ge, float* grad_w, float* grad_b, float* scratch, gs_stream_t stream);
+               float* grad_emb, int64_t ld_ge, float* grad_w, float* grad_b, float* scratch, int32_t precision,
+               gs_stream_t stream);
 /* Supervised loss of src/utils.py:153,162-163 fused with its gradient:
  * y_r = labels[label_index ? label_index[r] : r]   (label_index = the batch's node ids, :153)
  * loss[0] = -mean_r logp[r, y_r];  grad_logp[r,c] = -(c==y_r) / rows  (nullable). */
 int gs_nll_fwd_bwd(const float* logp, const int64_t* labels, const int32_t* label_index, int32_t rows,
                    int32_t num_classes, float* loss, float* grad_logp, gs_stream_t stream);
+
+/* The supervised tail in one call (classifier forward, NLL mean of src/utils.py:153,162-163,
+ * and their backward): logits GEMM -> fused bias + log_softmax + NLL + d logits + grad_b ->
+ * grad_w GEMM -> grad_emb GEMM.  loss[0] is overwritten; grad_w / grad_b accumulate (zero
+ * them first); grad_emb (nullable) is overwritten; scratch: rows*num_classes floats. */
+int gs_cls_nll_fwd_bwd(const float* emb, int64_t ld_emb, int32_t rows, int32_t dim,
+                       const float* weight, const float* bias, int32_t num_classes,
+                       const int64_t* labels, const int32_t* label_index,
+                       float* logp, float* loss, float* grad_emb, int64_t ld_ge,
+                       float* grad_w, float* grad_b, float* scratch, int32_t precision, gs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Update step of src/utils.py:185-187: per-model clip_grad_norm_(max_norm) then SGD.

@@ -153,6 +153,33 @@ def test_unique_multi_cta(g, dev, rows, stride, n_ids, bits):
     _check_unique(g, dev, nodes, nbr, bits, live=rows // 2 + 1)
 
 
+@pytest.mark.parametrize('rows,stride,n_ids', [(1, 11, 50), (1024, 11, 2_449_029), (11264, 11, 2_449_029),
+                                               (8192, 11, 100_000_000), (3000, 106, 19717), (500, 4, 4096 * 32 + 1)])
+def test_unique_bitmap_path(g, dev, rows, stride, n_ids):
+    """Bitmap/rank path: identical outputs to the radix path (np.unique oracle), bitmap left clean."""
+    rng = np.random.default_rng(rows * 7 + stride)
+    ws = g.unique_bitmap_workspace(n_ids, dev)
+    words = (n_ids + 31) // 32
+    for rep, live in enumerate((None, max(1, rows // 3), None)):
+        nodes = rng.integers(0, n_ids, size=rows).astype(np.int32)
+        nbr = rng.integers(0, n_ids, size=(rows, stride)).astype(np.int32)
+        nbr[rng.random((rows, stride)) < 0.15] = -1
+        if rep == 2:
+            nodes[:], nbr[:] = n_ids - 1, n_ids - 1            # everything collides on the last id
+        nodes_t, nbr_t = torch.from_numpy(nodes).to(dev), torch.from_numpy(nbr).to(dev)
+        live_t = None if live is None else torch.tensor([live], dtype=torch.int32, device=dev)
+        uniq, num, nbr_idx, self_idx = g.unique_remap_bitmap(nodes_t, live_t, rows, nbr_t, stride, n_ids, ws)
+        m = rows if live is None else live
+        ids = np.concatenate([nodes[:m], nbr[:m].ravel()])
+        want = np.unique(ids[ids >= 0])
+        n = int(num.item())
+        assert n == len(want) and np.array_equal(uniq[:n].cpu().numpy(), want)
+        ni, si = nbr_idx.cpu().numpy(), self_idx.cpu().numpy()
+        assert np.array_equal(ni[:m], np.where(nbr[:m] >= 0, np.searchsorted(want, np.maximum(nbr[:m], 0)), -1))
+        assert np.all(ni[m:] == -1) and np.array_equal(si[:m], np.searchsorted(want, nodes[:m]))
+        assert int(ws[:words * 4].view(torch.int32).abs().max().item()) == 0       # bitmap cleared for the next call
+
+
 @pytest.mark.parametrize('name', ['cora_mean_sup', 'pubmed_selfloop_gcn', 'cora_3layer_gcn_max'])
 def test_unique_remap_matches_reference_calls(g, dev, name):
     """Injected-sample contract: on the reference's own recorded samples,
@@ -268,6 +295,66 @@ def test_sage_gemm_fwd_bwd(g, dev, dim, out_dim, gcn):
     if not gcn:
         want_gs = torch.zeros((n_table, dim)).index_add_(0, torch.from_numpy(self_idx[:live]), gs[:live, :dim].cpu())
         assert rel(want_gs, tbl.grad) <= TOL
+
+
+TC_TOL = {1: 2e-3, 2: 1e-5}      # GS_PREC_TF32 (10-bit mantissa operands) / GS_PREC_TF32X3 (fp32-faithful split)
+
+
+@pytest.mark.parametrize('precision', [2, 1])
+@pytest.mark.parametrize('dim,out_dim,gcn,rows,live', [(100, 128, False, 11264, 10900), (128, 128, False, 1024, 1024),
+                                                       (1433, 128, False, 300, 257), (602, 128, True, 1000, 999),
+                                                       (64, 32, False, 200, 130), (50, 256, False, 400, 400),
+                                                       (7, 5, False, 64, 33)])
+def test_sage_gemm_tensor_core_path(g, dev, precision, dim, out_dim, gcn, rows, live):
+    """tcgen05 kind::tf32 path of K4 (forward, bwd_x, bwd_w) against a float64 evaluation of
+    src/models.py:215-219 and its autograd."""
+    rng = np.random.default_rng(dim * 5 + out_dim + precision)
+    n_table = 3000
+    ld = (dim + 3) & ~3
+    table = torch.zeros((n_table, ld))
+    table[:, :dim] = torch.from_numpy(rng.standard_normal((n_table, dim)).astype(np.float32))
+    agg = torch.zeros((rows, ld))
+    agg[:, :dim] = torch.from_numpy(rng.standard_normal((rows, dim)).astype(np.float32))
+    self_idx = rng.integers(0, n_table, size=rows)
+    w = torch.from_numpy(rng.uniform(-0.2, 0.2, size=(out_dim, dim if gcn else 2 * dim)).astype(np.float32))
+    live_t = torch.tensor([live], dtype=torch.int32, device=dev)
+    sidx_d = torch.from_numpy(self_idx.astype(np.int32)).to(dev)
+    t_d, a_d, w_d = table.to(dev), agg.to(dev), w.to(dev)
+    out = g.sage_gemm_fwd(None if gcn else t_d, sidx_d, a_d, dim, w_d, out_dim, gcn, live_t, rows, True, precision)
+    w_ref = w.double().requires_grad_(True)
+    tbl = table[:, :dim].double().requires_grad_(True)
+    agg_ref = agg[:live, :dim].double().requires_grad_(True)
+    comb = agg_ref if gcn else torch.cat([tbl[self_idx[:live]], agg_ref], 1)
+    want = torch.relu(w_ref.mm(comb.t())).t()
+    tol = TC_TOL[precision]
+    assert rel(out[:live, :out_dim], want) <= tol
+    # backward uses the fp32-path forward output for the ReLU mask so both sides mask identically
+    out32 = g.sage_gemm_fwd(None if gcn else t_d, sidx_d, a_d, dim, w_d, out_dim, gcn, live_t, rows, True, 0)
+    gout = torch.from_numpy(rng.standard_normal((rows, (out_dim + 3) & ~3)).astype(np.float32))
+    mask = (out32[:live, :out_dim] > 0).cpu().double()
+    pre = w_ref.mm(comb.t()).t()
+    (pre * mask * gout[:live, :out_dim].double()).sum().backward()
+    gw = torch.zeros_like(w, device=dev)
+    g.sage_gemm_bwd_w(None if gcn else t_d, sidx_d, a_d, dim, gout.to(dev), out32, out_dim, gcn, True, live_t, rows, gw,
+                      precision=precision)
+    assert rel(gw, w_ref.grad) <= tol
+    gs, ga = g.sage_gemm_bwd_x(gout.to(dev), out32, w_d, dim, out_dim, gcn, True, live_t, rows, precision=precision)
+    assert rel(ga[:live, :dim], agg_ref.grad) <= tol
+    if not gcn:
+        want_gs = torch.zeros((n_table, dim), dtype=torch.float64).index_add_(
+            0, torch.from_numpy(self_idx[:live]), gs[:live, :dim].cpu().double())
+        assert rel(want_gs, tbl.grad) <= tol
+    # pre-masked gradient + relu=False: the cp.async-staged variants of the same kernels
+    gm = gout.to(dev).clone()
+    g.relu_bwd_inplace(gm, out32, out_dim, live_t, rows)
+    gw2 = torch.zeros_like(w, device=dev)
+    g.sage_gemm_bwd_w(None if gcn else t_d, sidx_d, a_d, dim, gm, out32, out_dim, gcn, False, live_t, rows, gw2,
+                      precision=precision)
+    assert rel(gw2, w_ref.grad) <= tol
+    gs2, ga2 = g.sage_gemm_bwd_x(gm, out32, w_d, dim, out_dim, gcn, False, live_t, rows, precision=precision)
+    assert rel(ga2[:live, :dim], agg_ref.grad) <= tol
+    if not gcn:
+        assert rel(gs2[:live, :dim], gs[:live, :dim]) <= tol
 
 
 @pytest.mark.parametrize('rows,dim,classes', [(1024, 128, 47), (150, 32, 7), (33, 128, 3)])
