@@ -124,6 +124,171 @@ agg_bwd_kernel(const float* __restrict__ grad_agg, int64_t ld_ga, const float* _
   }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// K3 forward, asynchronous-copy pipeline (the default for sampled lists, stride <= 16).
+//
+// The register-staged kernel above keeps <= 16 warps per SM resident (92 registers) and each
+// warp spends most of its life in the dependent chain cnt -> ids -> rows, so only ~1/3 of the
+// HBM latency x bandwidth product is ever in flight (measured 1.6 TB/s, ncu r1).  Here every
+// warp owns a ring of STAGES shared-memory slots; a slot receives the <= stride gathered rows of
+// one destination row by cp.async (LDGSTS, 16 bytes per lane, lane = float4 column, so a warp
+// instruction moves one whole 400-512 B row piece, coalesced).  Copies are issued STAGES rows
+// ahead of the row being reduced and hold no registers while in flight: 8 warps x 4 slots x
+// ~4 KB keep > 100 KB per SM outstanding.  Every lane reduces exactly the bytes it copied, so
+// cp.async.wait_group is the only synchronisation.  A persistent grid (one CTA per SM) walks
+// the rows round-robin; wide tables are processed in column chunks of 128 floats.
+//
+// (A first version used one cp.async.bulk (TMA, UBLKCP) per gathered row: 2.2 TB/s.  With 400 B
+// copies the per-SM TMA unit, not HBM, was the limit -- ~45 cycles per copy -- so the LSU path
+// is used; ncu numbers in profiles/.)
+// ---------------------------------------------------------------------------------------
+constexpr int kPipeWarps = 16;          // 4 per scheduler: enough to cover each other's instruction latencies
+constexpr int kPipeMaxStride = 16;
+constexpr int kPipeChunkF4 = 32;            // float4 per column chunk = 512 B per copied row piece
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// cursor over a warp's work items (row, column chunk) without any division
+struct ItemCursor {
+  int row, chunk;
+  __device__ __forceinline__ void advance(int n_chunks, int row_step) {
+    if (++chunk == n_chunks) { chunk = 0; row += row_step; }
+  }
+};
+
+template <int MODE, int STAGES>
+__global__ void __launch_bounds__(kPipeWarps * 32, 1)
+agg_fwd_pipe_kernel(const float* __restrict__ table, int64_t ld, int dim4, const int32_t* __restrict__ nbr, int stride,
+                    const int32_t* __restrict__ cnt, const int32_t* __restrict__ num_rows_dev, int max_rows,
+                    float* __restrict__ out, int64_t ld_out, int32_t* __restrict__ argmax, int64_t ld_arg,
+                    int slot_bytes) {
+  extern __shared__ __align__(128) unsigned char pipe_smem[];
+  __shared__ int32_t s_ids[kPipeWarps][STAGES][kPipeMaxStride];
+  __shared__ int32_t s_n[kPipeWarps][STAGES];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows = live_rows(num_rows_dev, max_rows);
+  const int total_warps = gridDim.x * kPipeWarps;
+  const int gw = blockIdx.x * kPipeWarps + warp;
+  const int n_chunks = (dim4 + kPipeChunkF4 - 1) / kPipeChunkF4;
+  unsigned char* ring = pipe_smem + static_cast<size_t>(warp) * STAGES * slot_bytes;
+  const int piece_stride = slot_bytes / stride;                 // bytes between neighbour pieces inside a slot
+  const float qnan = __int_as_float(0x7fc00000);
+  const uint32_t lane_dst = smem_addr(ring) + lane * 16;
+  const float* lane_src = table + lane * 4;
+
+  // index fetch for the item under cursor c (this lane's neighbour id, -1 beyond the row's count);
+  // issued two items ahead of its use so the dependent chain cnt/ids -> row addresses never sits
+  // on the critical path
+  auto fetch = [&](const ItemCursor& c) -> int {
+    int mine = -1;
+    if (c.row < rows) {
+      const int n = __ldg(cnt + c.row);              // the two loads are independent: one latency, not two
+      const int v = lane < stride ? __ldg(nbr + static_cast<int64_t>(c.row) * stride + lane) : -1;
+      mine = lane < n ? v : -1;
+    }
+    return mine;
+  };
+  auto issue = [&](const ItemCursor& c, int s, int mine) {       // always commits one group (possibly empty)
+    if (c.row < rows) {                              // warp-uniform
+      const int f4 = min(kPipeChunkF4, dim4 - c.chunk * kPipeChunkF4);
+      const int n = __popc(__ballot_sync(0xffffffffu, mine >= 0));   // ids occupy slots [0, n)
+      if (lane < kPipeMaxStride) s_ids[warp][s][lane] = mine;
+      if (lane == 0) s_n[warp][s] = n;
+      __syncwarp();
+      if (lane < f4) {
+        const uint32_t dst = lane_dst + s * slot_bytes;
+        const float* src0 = lane_src + c.chunk * (kPipeChunkF4 * 4);
+        const int32_t* ids = s_ids[warp][s];
+#pragma unroll 4
+        for (int j = 0; j < n; ++j)                  // n is warp-uniform: no divergence, ids by LDS broadcast
+          cp_async_16(dst + j * piece_stride, src0 + static_cast<int64_t>(ids[j]) * ld);
+      }
+    }
+    cp_async_commit();
+  };
+
+  ItemCursor ci{gw, 0}, cc{gw, 0}, cf{gw, 0};        // issue, consume and index-fetch cursors
+  int pre[STAGES + 2];
+#pragma unroll
+  for (int i = 0; i < STAGES + 2; ++i) {             // all index loads of the pipeline fill fly together
+    pre[i] = fetch(cf);
+    cf.advance(n_chunks, total_warps);
+  }
+#pragma unroll
+  for (int t = 0; t < STAGES; ++t) {
+    issue(ci, t, pre[t]);
+    ci.advance(n_chunks, total_warps);
+  }
+  int ma = pre[STAGES], mb = pre[STAGES + 1];
+  int s = 0;
+  while (cc.row < rows) {
+    const int f4 = min(kPipeChunkF4, dim4 - cc.chunk * kPipeChunkF4);
+    cp_async_wait<STAGES - 1>();                    // the oldest outstanding group (this item) has landed
+    __syncwarp();                                   // s_ids written by other lanes
+    const unsigned char* slot = ring + s * slot_bytes + lane * 16;
+    if (lane < f4) {
+      float4 acc = (MODE == GS_AGG_MEAN) ? make_float4(0.f, 0.f, 0.f, 0.f)
+                                         : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      int4 arg = make_int4(-1, -1, -1, -1);
+      const int n = s_n[warp][s];
+      const int32_t* ids = s_ids[warp][s];
+#pragma unroll 4
+      for (int j = 0; j < n; ++j) {
+        const float4 v = *reinterpret_cast<const float4*>(slot + j * piece_stride);
+        if (MODE == GS_AGG_MEAN) {
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        } else {
+          const int id = ids[j];
+          if (v.x > acc.x) { acc.x = v.x; arg.x = id; }
+          if (v.y > acc.y) { acc.y = v.y; arg.y = id; }
+          if (v.z > acc.z) { acc.z = v.z; arg.z = id; }
+          if (v.w > acc.w) { acc.w = v.w; arg.w = id; }
+        }
+      }
+      if (MODE == GS_AGG_MEAN) {
+        const float inv = 1.0f / static_cast<float>(n);        // n == 0: 0 * inf = NaN, the reference's 0/0
+        acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+      } else if (n == 0) {
+        acc = make_float4(qnan, qnan, qnan, qnan);
+      }
+      const int c4 = cc.chunk * kPipeChunkF4 + lane;
+      *reinterpret_cast<float4*>(out + static_cast<int64_t>(cc.row) * ld_out + 4 * c4) = acc;
+      if (MODE == GS_AGG_MAX && argmax != nullptr)
+        *reinterpret_cast<int4*>(argmax + static_cast<int64_t>(cc.row) * ld_arg + 4 * c4) = arg;
+    }
+    __syncwarp();                                   // every lane is done with the slot before it is refilled
+    issue(ci, s, ma);
+    ci.advance(n_chunks, total_warps);
+    ma = mb;
+    mb = fetch(cf);
+    cf.advance(n_chunks, total_warps);
+    cc.advance(n_chunks, total_warps);
+    s = (s + 1 == STAGES) ? 0 : s + 1;
+  }
+  cp_async_wait<0>();
+}
+
+template <int MODE, int STAGES>
+static int launch_pipe(const float* table, int64_t ld, int dim4, const int32_t* nbr, int stride, const int32_t* cnt,
+                       const int32_t* num_rows_dev, int max_rows, float* out, int64_t ld_out, int32_t* argmax,
+                       int64_t ld_arg, int slot_bytes, cudaStream_t st) {
+  const int smem = kPipeWarps * STAGES * slot_bytes;
+  cudaError_t e = cudaFuncSetAttribute(agg_fwd_pipe_kernel<MODE, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  int grid = (max_rows + kPipeWarps - 1) / kPipeWarps;
+  if (grid > kNumSMs) grid = kNumSMs;
+  agg_fwd_pipe_kernel<MODE, STAGES><<<grid, kPipeWarps * 32, smem, st>>>(table, ld, dim4, nbr, stride, cnt, num_rows_dev,
+                                                                        max_rows, out, ld_out, argmax, ld_arg, slot_bytes);
+  return finish_launch();
+}
+
 }  // namespace gs
 
 using namespace gs;
@@ -138,12 +303,27 @@ extern "C" int gs_agg_fwd(const float* table, int64_t ld, int32_t dim, const int
   if (!aligned16(table) || !aligned16(out)) return GS_ERR_ALIGNMENT;
   if (argmax && ((ld_arg & 3) || ld_arg < 4 * dim4 || !aligned16(argmax))) return GS_ERR_ALIGNMENT;
   if (max_rows == 0) return GS_OK;
+  cudaStream_t st = as_stream(stream);
+  if (stride <= kPipeMaxStride) {
+    // asynchronous-copy pipeline: slot = `stride` pieces of one column chunk
+    const int f4 = dim4 < kPipeChunkF4 ? dim4 : kPipeChunkF4;
+    const int slot_bytes = stride * f4 * 16;
+    const int budget = 216 * 1024 / kPipeWarps;
+    int32_t* am = (mode == GS_AGG_MAX) ? argmax : nullptr;
+    const int64_t la = (mode == GS_AGG_MAX) ? ld_arg : 0;
+#define GS_PIPE(MODE_, STAGES_) \
+    return launch_pipe<MODE_, STAGES_>(table, ld, dim4, nbr, stride, cnt, num_rows_dev, max_rows, out, ld_out, am, la, slot_bytes, st)
+    if (3 * slot_bytes <= budget) { if (mode == GS_AGG_MEAN) GS_PIPE(GS_AGG_MEAN, 3); else GS_PIPE(GS_AGG_MAX, 3); }
+    if (2 * slot_bytes <= budget) { if (mode == GS_AGG_MEAN) GS_PIPE(GS_AGG_MEAN, 2); else GS_PIPE(GS_AGG_MAX, 2); }
+    if (slot_bytes <= budget) { if (mode == GS_AGG_MEAN) GS_PIPE(GS_AGG_MEAN, 1); else GS_PIPE(GS_AGG_MAX, 1); }
+#undef GS_PIPE
+  }
   const int blocks = (max_rows + kAggWarps - 1) / kAggWarps;
   if (mode == GS_AGG_MEAN)
-    agg_fwd_kernel<GS_AGG_MEAN><<<blocks, kAggWarps * 32, 0, as_stream(stream)>>>(
+    agg_fwd_kernel<GS_AGG_MEAN><<<blocks, kAggWarps * 32, 0, st>>>(
         table, ld, dim4, nbr, stride, cnt, num_rows_dev, max_rows, out, ld_out, nullptr, 0);
   else
-    agg_fwd_kernel<GS_AGG_MAX><<<blocks, kAggWarps * 32, 0, as_stream(stream)>>>(
+    agg_fwd_kernel<GS_AGG_MAX><<<blocks, kAggWarps * 32, 0, st>>>(
         table, ld, dim4, nbr, stride, cnt, num_rows_dev, max_rows, out, ld_out, argmax, ld_arg);
   return finish_launch();
 }
