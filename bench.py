@@ -60,13 +60,8 @@ def build_workload(scale: float):
 
 def batches_for(train: np.ndarray, b_sz: int, steps: int, rank: int, world: int, seed: int = SEED):
     """Disjoint b_sz slices of the shuffled train ids per (step, rank) (src/utils.py:127,145 per rank)."""
-    rng = np.random.default_rng(seed)
-    perm = rng.permutation(train)
-    need = b_sz * steps * world
-    if need > len(perm):
-        perm = np.concatenate([perm] * (need // len(perm) + 1))
-    out = perm[:need].reshape(steps, world, b_sz)[:, rank, :]
-    return np.ascontiguousarray(out)
+    from graphsage_b200.trainer import shard_batches
+    return shard_batches(train, b_sz, steps, rank, world, seed)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -23,6 +23,36 @@ from . import native, ops
 from .models import _PRECISIONS, Classification, GraphSage
 
 
+def flat_layout(shapes):
+    """Offsets of every parameter's gradient inside the single flat buffer that is all-reduced
+    (one collective per step).  Each view starts on a 16-byte boundary so the
+    kernels' 128-bit accesses stay aligned.  Returns (offsets, total_elements)."""
+    sizes = [int(np.prod(s)) if len(s) else 1 for s in shapes]
+    offs = np.concatenate([[0], np.cumsum([(n + 3) & ~3 for n in sizes])]).astype(np.int64)
+    return [int(o) for o in offs[:-1]], int(offs[-1])
+
+
+def dp_allreduce_(flat_grad: torch.Tensor, world_size: int, group=None) -> torch.Tensor:
+    """The one exchange step of the data-parallel path: sum the flat gradient over ranks.  The
+    division by world_size happens inside the update (gs_clip_sgd's grad_div), after which every
+    rank clips and steps identically, so replicas stay bit-identical."""
+    if world_size > 1:
+        import torch.distributed as dist
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+    return flat_grad
+
+
+def shard_batches(train: np.ndarray, b_sz: int, steps: int, rank: int, world: int, seed: int) -> np.ndarray:
+    """Disjoint b_sz slices of the shuffled train ids per (step, rank): rank r takes slice r of
+    every global batch of world*b_sz seeds (src/utils.py:127,145 applied per rank)."""
+    rng = np.random.default_rng(seed)
+    perm = rng.permutation(train)
+    need = b_sz * steps * world
+    if need > len(perm):
+        perm = np.concatenate([perm] * (need // len(perm) + 1))
+    return np.ascontiguousarray(perm[:need].reshape(steps, world, b_sz)[:, rank, :])
+
+
 class SupervisedTrainer:
     def __init__(self, model: GraphSage, classifier: Classification, labels, b_sz: int, *, lr: float = 0.7,
                  max_norm: float = 5.0, use_graph: bool = True, process_group=None, world_size: int = 1):
@@ -38,10 +68,9 @@ class SupervisedTrainer:
             native.require_cuda(p, "parameters")
         # one flat gradient buffer (single allreduce), views per tensor
         params = self.weights + [self.cls_w, self.cls_b]
-        sizes = [p.numel() for p in params]
-        offs = np.concatenate([[0], np.cumsum([(s + 3) & ~3 for s in sizes])])      # keep every view 16-byte aligned
-        self.flat_grad = torch.zeros((int(offs[-1]),), dtype=torch.float32, device=dev)
-        self.grads = [self.flat_grad[int(o):int(o) + s].view_as(p) for o, s, p in zip(offs[:-1], sizes, params)]
+        offs, total = flat_layout([tuple(p.shape) for p in params])
+        self.flat_grad = torch.zeros((total,), dtype=torch.float32, device=dev)
+        self.grads = [self.flat_grad[o:o + p.numel()].view_as(p) for o, p in zip(offs, params)]
         n_sage = len(self.weights)
         # clip is per model (src/utils.py:185-186): graphSage parameters, then classification parameters
         self.tl_sage = ops.TensorList([p.data for p in self.weights], self.grads[:n_sage])
@@ -78,9 +107,7 @@ class SupervisedTrainer:
         ops.clip_sgd(self.tl_cls, self.max_norm, self.lr, div, zero_grads=True)
 
     def _allreduce(self):
-        if self.world_size > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.pg)
+        dp_allreduce_(self.flat_grad, self.world_size, self.pg)
 
     def _capture(self):
         # warm-up on a side stream (allocator + lazy module loads), then capture
