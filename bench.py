@@ -191,7 +191,9 @@ def workload_config(args, cfg, rowptr, col, b_sz):
             "nodes": int(len(rowptr) - 1), "csr_entries": int(len(col)), "feats": cfg["feats"], "hidden": cfg["hidden"],
             "classes": cfg["classes"], "layers": 2, "fanout": 10, "agg": "MEAN", "gcn": False, "learn_method": "sup",
             "b_sz_per_gpu": b_sz, "global_batch": b_sz * args.gpus, "parallelism": f"dp{args.gpus}",
-            "batch_extension": False, "l2_policy": "feature table 980 MB >> 126 MB L2; fresh seeds every step",
+            "batch_extension": False, "exchange": ("fused NVLink peer-memory all-reduce+clip+SGD kernel" if args.exchange == "peer"
+                                                   else "NCCL all-reduce + separate clip/SGD kernels"),
+            "l2_policy": "feature table 980 MB >> 126 MB L2; fresh seeds every step",
             "update": "clip_grad_norm 5 per model + SGD lr 0.7 inside the step"}
 
 
@@ -241,7 +243,7 @@ def run_ours(args):
         cls.layer[0].weight.copy_(torch.from_numpy(synth.xavier_uniform_np(wrng, cfg["classes"], cfg["hidden"])))
         cls.layer[0].bias.zero_()
     trainer = SupervisedTrainer(model, cls, labels, b_sz, lr=0.7, max_norm=5.0, use_graph=not args.no_graph,
-                                world_size=world)
+                                world_size=world, rank=rank, exchange=args.exchange)
     host_batches = batches_for(train, b_sz, K + W, rank, world)
     dev_batches = torch.from_numpy(host_batches.astype(np.int32)).to(dev)
 
@@ -291,6 +293,8 @@ def run_ours(args):
     e3.record()
     sync_all()
     ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+    if trainer.dp is not None:
+        trainer.dp.status()                                                    # raises if a peer wait ever timed out
     clk = clocks.stop(t_begin, time.time()) if rank == 0 else None
 
     # ---- roofline of the dominant kernel: layer-1 aggregation, events around its launch ----
@@ -421,6 +425,9 @@ def main():
     ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "tf32x3"],
                     help="K4 GEMM mode: fp32 = FFMA; tf32x3 = tcgen05 3-term tf32 split (fp32-faithful, 1e-5 parity); "
                          "tf32 = single tf32 product (2e-3)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="gradient exchange + update: peer = one fused kernel over NVLink peer memory (default); "
+                         "nccl = library all-reduce followed by the separate norm/update kernels (comparison)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--ref-budget-s", type=float, default=150.0)

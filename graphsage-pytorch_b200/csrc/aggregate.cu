@@ -289,6 +289,110 @@ static int launch_pipe(const float* table, int64_t ld, int dim4, const int32_t* 
   return finish_launch();
 }
 
+// ---------------------------------------------------------------------------------------
+// K3 forward over a ROW-PARTITIONED bf16 feature table (BASELINE.json configs[4]: 100M nodes,
+// 128 bf16 features, 8 shards).  Shard s holds the rows of nodes [s*rows_per_shard,
+// (s+1)*rows_per_shard); its base pointer is either local HBM or a CUDA-IPC mapping of a
+// peer GPU's HBM, so a gathered row is read directly over NVLink by the 16-byte loads below
+// -- no collective, no staging copy.  A 128-feature row is 256 B = 16 lanes
+// x 16 B, so a warp fetches TWO neighbour rows per load instruction (one per half-warp) and
+// keeps up to kShardBatch of them in flight per lane before reducing in fp32; the peer
+// latency (~2-3 us) is covered by 16+ warps/SM x 6 x 512 B outstanding.  The same launch
+// converts the destination node's own row to fp32 (`out_self`), because the SageLayer GEMM
+// consumes fp32 operands and its gather index cannot cross shards.
+// ---------------------------------------------------------------------------------------
+constexpr int kMaxShards = 8;
+constexpr int kShardBatch = 8;
+struct ShardTable {
+  const uint16_t* base[kMaxShards];
+  int num_shards;
+  long long rows_per_shard;
+};
+
+__device__ __forceinline__ uint4 ldg_stream_u4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void bf16x8_add(float (&acc)[8], const uint4& v) {
+  acc[0] += __uint_as_float(v.x << 16); acc[1] += __uint_as_float(v.x & 0xffff0000u);
+  acc[2] += __uint_as_float(v.y << 16); acc[3] += __uint_as_float(v.y & 0xffff0000u);
+  acc[4] += __uint_as_float(v.z << 16); acc[5] += __uint_as_float(v.z & 0xffff0000u);
+  acc[6] += __uint_as_float(v.w << 16); acc[7] += __uint_as_float(v.w & 0xffff0000u);
+}
+
+// LPR = lanes per gathered row (16: two rows per warp instruction, dim <= 128; 32: one row, column loop)
+template <int LPR>
+__global__ void __launch_bounds__(kAggWarps * 32)
+agg_fwd_bf16_sharded_kernel(const ShardTable tab_arg, int64_t ld, int dim8, const int32_t* __restrict__ nbr, int stride,
+                            const int32_t* __restrict__ cnt, const int32_t* __restrict__ self_nodes,
+                            const int32_t* __restrict__ num_rows_dev, int max_rows, float* __restrict__ out_agg,
+                            int64_t ld_agg, float* __restrict__ out_self, int64_t ld_self) {
+  __shared__ const uint16_t* s_base[kMaxShards];
+  if (threadIdx.x < kMaxShards) s_base[threadIdx.x] = threadIdx.x < tab_arg.num_shards ? tab_arg.base[threadIdx.x] : nullptr;
+  __syncthreads();
+  constexpr int SUB = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane / LPR, sl = lane % LPR;
+  const int r = blockIdx.x * kAggWarps + (threadIdx.x >> 5);
+  if (r >= live_rows(num_rows_dev, max_rows)) return;
+  const int n = min(__ldg(cnt + r), stride);
+  const int mine = lane < n ? __ldg(nbr + static_cast<int64_t>(r) * stride + lane) : -1;      // stride <= 32
+  const int me = (out_self != nullptr) ? __ldg(self_nodes + r) : -1;
+  const int rps = static_cast<int>(tab_arg.rows_per_shard);   // node ids are int32, so is the shard height
+  const float inv = 1.0f / static_cast<float>(n);             // n == 0: 0 * inf = NaN, the reference's 0/0
+  auto row_ptr = [&](int id) -> const uint16_t* {
+    const int sh = id / rps;
+    return s_base[sh] + static_cast<long long>(id - sh * rps) * ld;
+  };
+  for (int cbase = 0; cbase < dim8; cbase += LPR) {
+    const int c8 = cbase + sl;
+    const bool active = c8 < dim8;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    uint4 sv = make_uint4(0u, 0u, 0u, 0u);
+    const bool self_here = active && me >= 0 && sub == 0;
+    if (self_here) sv = ldg_stream_u4(row_ptr(me) + 8 * c8);
+    for (int j0 = 0; j0 < n; j0 += SUB * kShardBatch) {
+      uint4 v[kShardBatch];
+      bool ok[kShardBatch];
+#pragma unroll
+      for (int u = 0; u < kShardBatch; ++u) {
+        const int j = j0 + u * SUB + sub;
+        const int id = __shfl_sync(0xffffffffu, mine, j & 31);
+        ok[u] = active && j < n && id >= 0;
+        if (ok[u]) v[u] = ldg_stream_u4(row_ptr(id) + 8 * c8);
+      }
+#pragma unroll
+      for (int u = 0; u < kShardBatch; ++u)
+        if (ok[u]) bf16x8_add(acc, v[u]);
+    }
+    if (SUB == 2) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 16);
+    }
+    if (active) {
+      // 8 fp32 outputs per column piece: with two half-warps each writes one float4 of them
+      float* dst = out_agg + static_cast<int64_t>(r) * ld_agg + 8 * c8;
+      const float4 lo = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
+      const float4 hi = make_float4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);
+      if (SUB == 1 || sub == 0) *reinterpret_cast<float4*>(dst) = lo;
+      if (SUB == 1 || sub == 1) *reinterpret_cast<float4*>(dst + 4) = hi;
+      if (self_here) {
+        float s8[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s8[k] = 0.f;
+        bf16x8_add(s8, sv);
+        float* sd = out_self + static_cast<int64_t>(r) * ld_self + 8 * c8;
+        *reinterpret_cast<float4*>(sd) = make_float4(s8[0], s8[1], s8[2], s8[3]);
+        *reinterpret_cast<float4*>(sd + 4) = make_float4(s8[4], s8[5], s8[6], s8[7]);
+      }
+    }
+  }
+}
+
 }  // namespace gs
 
 using namespace gs;
@@ -353,5 +457,36 @@ extern "C" int gs_agg_bwd(const float* grad_agg, int64_t ld_ga, const float* gra
     agg_bwd_kernel<GS_AGG_MAX><<<blocks, kAggWarps * 32, 0, as_stream(stream)>>>(
         grad_agg, ld_ga, grad_self, ld_gs, dim4, nbr, stride, cnt, self_idx, argmax, ld_arg, num_rows_dev, max_rows,
         grad_table, ld_gt);
+  return finish_launch();
+}
+
+extern "C" int gs_agg_fwd_bf16_sharded(const void* const* shard_bases_host, int32_t num_shards, int64_t rows_per_shard,
+                                       int64_t ld, int32_t dim, const int32_t* nbr, int32_t stride, const int32_t* cnt,
+                                       const int32_t* self_nodes, const int32_t* num_rows_dev, int32_t max_rows,
+                                       float* out_agg, int64_t ld_agg, float* out_self, int64_t ld_self,
+                                       gs_stream_t stream) {
+  if (!shard_bases_host || num_shards < 1 || num_shards > kMaxShards || rows_per_shard < 1 || rows_per_shard > 0x7fffffffLL)
+    return GS_ERR_BAD_ARG;
+  if (!nbr || !cnt || !out_agg || dim < 1 || stride < 1 || stride > 32 || max_rows < 0) return GS_ERR_BAD_ARG;
+  if (out_self && !self_nodes) return GS_ERR_BAD_ARG;
+  const int dim8 = (dim + 7) / 8;
+  if ((ld & 7) || ld < 8 * dim8) return GS_ERR_ALIGNMENT;                 // bf16 rows in 16-byte pieces
+  if ((ld_agg & 3) || ld_agg < 8 * dim8 || !aligned16(out_agg)) return GS_ERR_ALIGNMENT;
+  if (out_self && ((ld_self & 3) || ld_self < 8 * dim8 || !aligned16(out_self))) return GS_ERR_ALIGNMENT;
+  ShardTable tab{};
+  tab.num_shards = num_shards;
+  tab.rows_per_shard = rows_per_shard;
+  for (int s = 0; s < num_shards; ++s) {
+    if (!shard_bases_host[s] || !aligned16(shard_bases_host[s])) return GS_ERR_ALIGNMENT;
+    tab.base[s] = static_cast<const uint16_t*>(shard_bases_host[s]);
+  }
+  if (max_rows == 0) return GS_OK;
+  const int blocks = (max_rows + kAggWarps - 1) / kAggWarps;
+  if (dim8 <= 16)
+    agg_fwd_bf16_sharded_kernel<16><<<blocks, kAggWarps * 32, 0, as_stream(stream)>>>(
+        tab, ld, dim8, nbr, stride, cnt, self_nodes, num_rows_dev, max_rows, out_agg, ld_agg, out_self, ld_self);
+  else
+    agg_fwd_bf16_sharded_kernel<32><<<blocks, kAggWarps * 32, 0, as_stream(stream)>>>(
+        tab, ld, dim8, nbr, stride, cnt, self_nodes, num_rows_dev, max_rows, out_agg, ld_agg, out_self, ld_self);
   return finish_launch();
 }

@@ -19,6 +19,7 @@ import torch.nn.functional as F
 
 from . import native, ops
 from .graph import AdjCSR, DeviceCSR, adj_to_csr
+from .peer import ShardedTable
 
 _PRECISIONS = {"fp32": native.PREC_FP32, "tf32": native.PREC_TF32, "tf32x3": native.PREC_TF32X3}
 
@@ -254,9 +255,14 @@ class GraphSage(nn.Module):
                                    "Construct it with device=torch.device('cuda') and call .to(device).")
             native.load()
             feats = self.raw_features
-            if not isinstance(feats, torch.Tensor):
-                feats = torch.as_tensor(np.asarray(feats), dtype=torch.float32)
-            table = _padded_table(feats.to(dev))
+            if isinstance(feats, ShardedTable):        # row-partitioned bf16 table, peer shards read over NVLink
+                if self.agg_func != 'MEAN':
+                    raise NotImplementedError("a ShardedTable supports agg_func='MEAN' (BASELINE configs[4])")
+                table = feats
+            else:
+                if not isinstance(feats, torch.Tensor):
+                    feats = torch.as_tensor(np.asarray(feats), dtype=torch.float32)
+                table = _padded_table(feats.to(dev))
             csr = _device_csr(self.adj_lists, table.shape[0], dev)
             self._native_state = (csr, table, torch.device(dev))
             use_bitmap = self.unique_algo == "bitmap" or (self.unique_algo == "auto" and csr.num_nodes <= (1 << 28))
@@ -347,7 +353,15 @@ class GraphSage(nn.Module):
         for l in range(1, L + 1):
             fr = layers[l]
             fr.table_in, fr.dim_in = tbl, dim
-            fr.agg, fr.argmax = ops.agg_fwd(tbl, dim, fr.nbr_idx, fr.stride, fr.cnt, fr.num_rows, fr.rows_max, mode)
+            if isinstance(tbl, ShardedTable):
+                # layer 1 over a row-partitioned table: K3 also emits the fp32 self rows (:265), which
+                # become K4's self operand with the identity index (forward and backward)
+                fr.agg, self_rows = ops.agg_fwd_sharded(tbl, fr.nbr_idx, fr.stride, fr.cnt, fr.nodes, fr.num_rows,
+                                                        fr.rows_max, want_self=not self.gcn)
+                fr.argmax, fr.table_in, fr.self_idx = None, self_rows, None
+                tbl = self_rows
+            else:
+                fr.agg, fr.argmax = ops.agg_fwd(tbl, dim, fr.nbr_idx, fr.stride, fr.cnt, fr.num_rows, fr.rows_max, mode)
             fr.h = ops.sage_gemm_fwd(None if self.gcn else tbl, fr.self_idx, fr.agg, dim, weights[l - 1], self.out_size,
                                      self.gcn, fr.num_rows, fr.rows_max, True, prec)
             tbl, dim = fr.h, self.out_size

@@ -115,6 +115,28 @@ def agg_fwd(table, dim: int, nbr, stride: int, cnt, num_rows, max_rows: int, mod
     return out, argmax
 
 
+def pad8(n: int) -> int:
+    return (int(n) + 7) & ~7
+
+
+def agg_fwd_sharded(table, nbr, stride: int, cnt, self_nodes, num_rows, max_rows: int, want_self: bool = True,
+                    out=None, out_self=None):
+    """MEAN over a row-partitioned bf16 table (peer.ShardedTable), global node ids in `nbr`
+    -> (agg fp32 [max_rows, pad8(dim)], self rows fp32 or None).  Remote shards are read over NVLink."""
+    native.require_cuda(nbr, "nbr")
+    ld = pad8(table.dim)
+    if out is None:
+        out = torch.empty((max_rows, ld), dtype=F32, device=nbr.device)
+    if want_self and out_self is None:
+        out_self = torch.empty((max_rows, ld), dtype=F32, device=nbr.device)
+    check(_lib().gs_agg_fwd_bf16_sharded(table.bases, table.num_shards, table.rows_per_shard, table.ld, table.dim,
+                                         ptr(nbr), stride, ptr(cnt), ptr(self_nodes) if want_self else None,
+                                         ptr(num_rows), max_rows, ptr(out), out.stride(0),
+                                         ptr(out_self) if want_self else None,
+                                         out_self.stride(0) if want_self else 0, stream()), "gs_agg_fwd_bf16_sharded")
+    return out, (out_self if want_self else None)
+
+
 def agg_bwd(grad_agg, grad_self, dim: int, nbr, stride: int, cnt, self_idx, argmax, num_rows, max_rows: int,
             mode: int, grad_table):
     check(_lib().gs_agg_bwd(ptr(grad_agg), grad_agg.stride(0) if grad_agg is not None else 0,

@@ -2,15 +2,18 @@
 (src/utils.py:141-191, learn_method='sup') as one CUDA-graph replay.
 
     seeds -> sample -> unique/remap -> sample -> agg1 -> layer1 -> agg2 -> layer2 -> classifier ->
-    NLL -> backward (classifier, layer2, scatter, layer1) -> [NCCL allreduce] -> clip + SGD
+    NLL -> backward (classifier, layer2, scatter, layer1) -> all-reduce + clip + SGD (one kernel)
 
 The eager drop-in classes (models.py) pay Python + autograd + launch overhead per kernel; at
 b_sz=1024 the kernels themselves are ~100 us, so the step is captured once (all shapes are
 static: frontier sizes that are only known on the device are passed as device counters, see
 include/gsage_b200.h) and replayed.  The Philox offset is a device counter bumped inside the
-graph so every replay draws fresh neighbours.  With world_size > 1 the gradients live in one
-flat buffer that is all-reduced (sum) between backward and the update, and the update
-divides by world_size (data-parallel mean).
+graph so every replay draws fresh neighbours.  The gradients live in one flat buffer; the
+exchange step of the data-parallel path and the update are ONE kernel
+(gs_dp_allreduce_clip_sgd: push over NVLink peer memory, rank-ordered sum, per-model clip, SGD,
+zero), captured in the same graph as forward/backward -- a step is a single graph replay at any
+world size.  `exchange='nccl'` keeps the library all-reduce + separate update kernels as the
+comparison baseline.
 """
 from __future__ import annotations
 
@@ -21,6 +24,7 @@ import torch
 
 from . import native, ops
 from .models import _PRECISIONS, Classification, GraphSage
+from .peer import DpExchange
 
 
 def flat_layout(shapes):
@@ -55,7 +59,8 @@ def shard_batches(train: np.ndarray, b_sz: int, steps: int, rank: int, world: in
 
 class SupervisedTrainer:
     def __init__(self, model: GraphSage, classifier: Classification, labels, b_sz: int, *, lr: float = 0.7,
-                 max_norm: float = 5.0, use_graph: bool = True, process_group=None, world_size: int = 1):
+                 max_norm: float = 5.0, use_graph: bool = True, process_group=None, world_size: int = 1,
+                 rank: int = 0, exchange: str = "peer"):
         csr, table, dev = model._state()
         self.model, self.classifier, self.dev, self.b_sz = model, classifier, dev, int(b_sz)
         self.lr, self.max_norm, self.world_size, self.pg = lr, max_norm, world_size, process_group
@@ -75,6 +80,14 @@ class SupervisedTrainer:
         # clip is per model (src/utils.py:185-186): graphSage parameters, then classification parameters
         self.tl_sage = ops.TensorList([p.data for p in self.weights], self.grads[:n_sage])
         self.tl_cls = ops.TensorList([self.cls_w.data, self.cls_b.data], self.grads[n_sage:])
+        if exchange not in ("peer", "nccl"):
+            raise ValueError("exchange must be 'peer' (fused NVLink kernel) or 'nccl'")
+        self.exchange = exchange
+        self.dp: Optional[DpExchange] = None
+        if exchange == "peer":
+            # clip groups follow src/utils.py:185-186: model 0 = graphSage, model 1 = classification
+            self.dp = DpExchange(self.flat_grad, [p.data for p in params], offs, [0] * n_sage + [1, 1],
+                                 world=world_size, rank=rank, group=process_group)
         self.seeds = torch.zeros((self.b_sz,), dtype=torch.int32, device=dev)
         self.seeds_pinned = torch.zeros((self.b_sz,), dtype=torch.int32).pin_memory()
         self.loss = torch.zeros((1,), dtype=torch.float32, device=dev)
@@ -102,12 +115,16 @@ class SupervisedTrainer:
         self.step_counter.add_(1)
 
     def _update(self):
+        if self.dp is not None:
+            self.dp.update(self.max_norm, self.lr)                                                     # utils.py:184-191
+            return
         div = float(self.world_size)
         ops.clip_sgd(self.tl_sage, self.max_norm, self.lr, div, zero_grads=True)                       # utils.py:185-191
         ops.clip_sgd(self.tl_cls, self.max_norm, self.lr, div, zero_grads=True)
 
     def _allreduce(self):
-        dp_allreduce_(self.flat_grad, self.world_size, self.pg)
+        if self.dp is None:
+            dp_allreduce_(self.flat_grad, self.world_size, self.pg)
 
     def _capture(self):
         # warm-up on a side stream (allocator + lazy module loads), then capture
@@ -123,10 +140,13 @@ class SupervisedTrainer:
         self._graph_fb = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph_fb):
             self._forward_backward()
+            if self.dp is not None:
+                self._update()               # the exchange is a kernel of ours: the whole step is one graph
         mid = native.launch_count()
-        self._graph_up = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph_up):
-            self._update()
+        if self.dp is None:
+            self._graph_up = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph_up):
+                self._update()
         self.launches_per_step = native.launch_count() - before
         self._fb_launches, self._up_launches = mid - before, native.launch_count() - mid
         self.flat_grad.zero_()
@@ -152,8 +172,9 @@ class SupervisedTrainer:
             if self._graph_fb is None:
                 self._capture()
             self._graph_fb.replay()
-            self._allreduce()
-            self._graph_up.replay()
+            if self.dp is None:
+                self._allreduce()
+                self._graph_up.replay()
         else:
             before = native.launch_count()
             self._forward_backward()

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 6
+#define GS_ABI_VERSION 7
 
 #define GS_OK 0
 #define GS_ERR_BAD_ARG (-1)
@@ -118,6 +118,19 @@ int gs_agg_bwd(const float* grad_agg, int64_t ld_ga, const float* grad_self, int
                const int32_t* argmax, int64_t ld_arg, const int32_t* num_rows_dev, int32_t max_rows, int32_t mode,
                float* grad_table, int64_t ld_gt, gs_stream_t stream);
 
+/* K3 forward over a ROW-PARTITIONED bf16 feature table (BASELINE.json configs[4]: features
+ * split by contiguous node-id blocks across the GPUs of one box).  shard_bases_host is a HOST
+ * array of `num_shards` (<= 8) device pointers: shard s holds rows [s*rows_per_shard,
+ * (s+1)*rows_per_shard) as bf16, `ld` elements apart (ld % 8 == 0); a base may be local HBM or
+ * a peer mapping obtained with gs_peer_open -- gathered rows are then read straight over
+ * NVLink, no collective.  nbr holds GLOBAL node ids (MEAN of src/models.py:311-314, fp32
+ * accumulate).  out_self (nullable) receives the fp32 copy of row self_nodes[r]: the
+ * self_feats gather of src/models.py:265 for layer 1, which K4 then reads with self_idx = NULL. */
+int gs_agg_fwd_bf16_sharded(const void* const* shard_bases_host, int32_t num_shards, int64_t rows_per_shard,
+                            int64_t ld, int32_t dim, const int32_t* nbr, int32_t stride, const int32_t* cnt,
+                            const int32_t* self_nodes, const int32_t* num_rows_dev, int32_t max_rows,
+                            float* out_agg, int64_t ld_agg, float* out_self, int64_t ld_self, gs_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * K4  SageLayer.  Replaces src/models.py:215-219: out = relu(W . [self | agg]^T)^T with the
  * concat never materialised: X[r,:] = [ self_table[self_idx[r], :dim] | agg[r, :dim] ]
@@ -188,6 +201,42 @@ int gs_cls_nll_fwd_bwd(const float* emb, int64_t ld_emb, int32_t rows, int32_t d
 int gs_clip_sgd(float* const* params, float* const* grads, const int64_t* numels, int32_t num_tensors,
                 int64_t max_numel, float max_norm, float lr, float grad_div, int32_t zero_grads,
                 float* norm_scratch, gs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Data-parallel exchange + update in ONE kernel (src/utils.py:184-191 on the
+ * mean gradient of all ranks): all-reduce of the flat gradient buffer over NVLink peer memory
+ * (push into every peer's receive slot, per-slice flags, rank-ordered sum => bit-identical
+ * replicas), per-model clip_grad_norm_(max_norm), SGD(lr), gradients zeroed.
+ *   flat_grad      this rank's flat fp32 gradient (n_total % 4 == 0), summed in place
+ *   peer_regions_host  HOST array of `world` device pointers: rank r's exchange region of
+ *                  gs_dp_region_bytes(n_total, world) bytes (zeroed; own entry = local
+ *                  pointer, others = gs_peer_open mappings).  NULL when world == 1.
+ *   seg_*_host     HOST arrays describing the `num_segs` (<= 16) parameter tensors: device
+ *                  pointer, offset of its gradient inside flat_grad (multiple of 4), numel,
+ *                  clip group (0..3; the reference clips each model separately, :185-186)
+ *   state          gs_dp_state_bytes() of zeroed device memory, private to this (flat_grad,
+ *                  n_total); carries the epoch between calls
+ *   timeout_ns     a peer that does not arrive within this time sets status != 0 (see
+ *                  gs_dp_status) instead of hanging the GPU; 0 => 2 s
+ * ------------------------------------------------------------------------------------ */
+size_t gs_dp_state_bytes(void);
+size_t gs_dp_region_bytes(int64_t n_total, int32_t world);
+size_t gs_dp_region_recv_offset(void);
+int gs_dp_allreduce_clip_sgd(float* flat_grad, int64_t n_total, void* const* peer_regions_host, int32_t rank,
+                             int32_t world, float* const* seg_params_host, const int64_t* seg_offsets_host,
+                             const int64_t* seg_numels_host, const int32_t* seg_groups_host, int32_t num_segs,
+                             float max_norm, float lr, void* state, uint64_t timeout_ns, gs_stream_t stream);
+/* synchronises `stream`, then reports the epoch counter, the status word (0 ok, 1 peer
+ * wait timed out, 2 grid barrier timed out) and the last step's 4 per-group gradient norms */
+int gs_dp_status(const void* state, uint32_t* epoch_host, uint32_t* status_host, float* norms_host, gs_stream_t stream);
+
+/* Peer memory for the two uses above: plain cudaMalloc'ed, zero-filled regions exported with
+ * CUDA IPC (one process per GPU; handles are 64 bytes and travel over any host channel). */
+int gs_peer_alloc(size_t bytes, void** out_ptr_host);
+int gs_peer_free(void* ptr);
+int gs_peer_export(void* ptr, unsigned char* handle64_host);
+int gs_peer_open(const unsigned char* handle64_host, void** out_ptr_host);
+int gs_peer_close(void* ptr);
 
 /* ------------------------------------------------------------------------------------
  * K5  UnsupervisedLoss sampling, src/models.py:153-186.

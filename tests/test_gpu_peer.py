@@ -1,0 +1,210 @@
+"""GPU: the multi-GPU pieces of the path exercised on ONE device, plus a
+2-rank run over real CUDA-IPC peer memory when the box has two GPUs.
+
+  * gs_dp_allreduce_clip_sgd at world 1 against torch's clip_grad_norm_ + SGD (src/utils.py:185-187);
+  * the same kernel as rank 0 of a world of 2, with the peer emulated by pre-filling this rank's
+    receive slot and flags (so nothing waits), checking the sum order, the pushed copy and the
+    published flags;
+  * gs_agg_fwd_bf16_sharded against the dense fp32 kernel on the bf16-rounded table;
+  * GraphSage over a ShardedTable against GraphSage over the equivalent dense table.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def rel(a, b):
+    a = np.asarray(a.detach().cpu() if isinstance(a, torch.Tensor) else a, dtype=np.float64)
+    b = np.asarray(b.detach().cpu() if isinstance(b, torch.Tensor) else b, dtype=np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+@pytest.fixture(scope='module')
+def P():
+    import graphsage_b200  # noqa: F401
+    from graphsage_b200 import native, peer
+    native.load()
+    return peer
+
+
+@pytest.fixture(scope='module')
+def dev():
+    return torch.device('cuda:0')
+
+
+def _flat_problem(dev, shapes, seed, scale=1.0):
+    from graphsage_b200.trainer import flat_layout
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    params = [torch.randn(s, generator=g).to(dev) for s in shapes]
+    offs, total = flat_layout([tuple(s) for s in shapes])
+    flat = torch.zeros((total,), dtype=torch.float32, device=dev)
+    grads = [flat[o:o + p.numel()].view_as(p) for o, p in zip(offs, params)]
+    for gr in grads:
+        gr.copy_((torch.randn(gr.shape, generator=g) * scale).to(dev))
+    return params, offs, flat, grads
+
+
+def _torch_update(params, grads, groups, max_norm, lr):
+    """src/utils.py:185-187 with torch ops: clip each model separately, then SGD."""
+    ps = [torch.nn.Parameter(p.detach().cpu().clone()) for p in params]
+    for p, g in zip(ps, grads):
+        p.grad = g.detach().cpu().clone()
+    norms = []
+    for grp in sorted(set(groups)):
+        norms.append(float(torch.nn.utils.clip_grad_norm_([p for p, q in zip(ps, groups) if q == grp], max_norm)))
+    torch.optim.SGD(ps, lr=lr).step()
+    return [p.detach() for p in ps], norms
+
+
+@pytest.mark.parametrize('scale', [0.01, 3.0])          # below and above the clip threshold
+def test_dp_update_world1_matches_torch_clip_sgd(P, dev, scale):
+    shapes = [(128, 200), (128, 256), (47, 128), (47,)]
+    groups = [0, 0, 1, 1]
+    params, offs, flat, grads = _flat_problem(dev, shapes, 5, scale)
+    want, norms = _torch_update(params, grads, groups, 5.0, 0.7)
+    dp = P.DpExchange(flat, params, offs, groups, world=1, rank=0)
+    dp.update(5.0, 0.7)
+    epoch, status, got_norms = dp.status()
+    assert (epoch, status) == (1, 0)
+    for p, w in zip(params, want):
+        assert rel(p, w) <= 1e-6
+    assert abs(got_norms[0] - norms[0]) <= 1e-5 * norms[0] and abs(got_norms[1] - norms[1]) <= 1e-5 * norms[1]
+    assert float(flat.abs().max()) == 0.0                              # zero_grad, src/utils.py:189-191
+    # a second step on fresh gradients reuses the state (epoch 2)
+    for gr in grads:
+        gr.normal_()
+    want2, _ = _torch_update(params, grads, groups, 5.0, 0.7)
+    dp.update(5.0, 0.7)
+    assert dp.status()[0] == 2
+    for p, w in zip(params, want2):
+        assert rel(p, w) <= 1e-6
+
+
+def test_dp_update_rank0_of_2_with_emulated_peer(P, dev):
+    from graphsage_b200 import native
+    lib = native.load()
+    shapes = [(64, 130), (10, 64), (10,)]            # 130: a tensor whose numel is not a multiple of 4 columns wide
+    groups = [0, 1, 1]
+    params, offs, flat, grads = _flat_problem(dev, shapes, 11, 2.0)
+    n_total = flat.numel()
+    nbytes = int(lib.gs_dp_region_bytes(n_total, 2))
+    recv_off = int(lib.gs_dp_region_recv_offset())
+    mine = torch.zeros((nbytes,), dtype=torch.uint8, device=dev)
+    theirs = torch.zeros((nbytes,), dtype=torch.uint8, device=dev)
+    dp = P.DpExchange(flat, params, offs, groups, world=2, rank=0, region_ptrs=[mine.data_ptr(), theirs.data_ptr()])
+    max_ctas = recv_off // 4 // 8
+    my_flags = mine[:recv_off].view(torch.int32).view(8, max_ctas)
+    their_flags = theirs[:recv_off].view(torch.int32).view(8, max_ctas)
+    my_recv = mine[recv_off:].view(torch.float32).view(2, 2, n_total)          # [parity][source rank][n]
+    their_recv = theirs[recv_off:].view(torch.float32).view(2, 2, n_total)
+    gen = torch.Generator(device='cpu').manual_seed(3)
+    for epoch in (1, 2, 3):
+        par = epoch & 1
+        local = (torch.randn((n_total,), generator=gen) * 2.0).to(dev)
+        for gr, o in zip(grads, offs):
+            gr.copy_(local[o:o + gr.numel()].view_as(gr))
+        local = flat.clone()
+        remote = torch.zeros_like(flat)
+        for gr, o in zip(grads, offs):
+            remote[o:o + gr.numel()] = (torch.randn((gr.numel(),), generator=gen) * 2.0).to(dev)
+        my_recv[par, 1].copy_(remote)              # what rank 1 would have pushed ...
+        my_flags[1].fill_(epoch)                   # ... and published
+        mean = [((local[o:o + p.numel()] + remote[o:o + p.numel()]) * 0.5).view_as(p) for o, p in zip(offs, params)]
+        want, _ = _torch_update(params, mean, groups, 5.0, 0.7)
+        torch.cuda.synchronize()
+        dp.update(5.0, 0.7)
+        assert dp.status()[:2] == (epoch, 0)
+        for p, w in zip(params, want):
+            assert rel(p, w) <= 1e-6
+        assert torch.equal(their_recv[par, 0], local)                           # my gradient landed in the peer's slot
+        grid = int(their_flags[0].ne(0).sum().item())
+        assert grid >= 1 and torch.all(their_flags[0, :grid] == epoch) and torch.all(their_flags[0, grid:] == 0)
+        assert float(flat.abs().max()) == 0.0
+
+
+def test_dp_update_times_out_instead_of_hanging(P, dev):
+    shapes = [(32, 32)]
+    params, offs, flat, grads = _flat_problem(dev, shapes, 1)
+    from graphsage_b200 import native
+    lib = native.load()
+    nbytes = int(lib.gs_dp_region_bytes(flat.numel(), 2))
+    mine = torch.zeros((nbytes,), dtype=torch.uint8, device=dev)
+    theirs = torch.zeros((nbytes,), dtype=torch.uint8, device=dev)
+    dp = P.DpExchange(flat, params, offs, [0], world=2, rank=0, timeout_s=0.05,
+                      region_ptrs=[mine.data_ptr(), theirs.data_ptr()])
+    dp.update(5.0, 0.7)                                # the peer never publishes
+    with pytest.raises(RuntimeError, match='timed out'):
+        dp.status()
+
+
+@pytest.mark.parametrize('dim,shards', [(128, 8), (128, 1), (100, 3), (264, 2)])
+def test_agg_fwd_sharded_matches_dense_kernel(P, dev, dim, shards):
+    from graphsage_b200 import native, ops
+    rng = np.random.default_rng(dim + shards)
+    n, rows, stride = 5000, 777, 11
+    feats = torch.from_numpy(rng.standard_normal((n, dim)).astype(np.float32)).to(dev)
+    table = P.ShardedTable.from_full(feats, shards)
+    dense = table.to_dense_fp32()
+    assert torch.equal(dense, feats.to(torch.bfloat16).float())
+    cnt = rng.integers(0, stride + 1, size=rows).astype(np.int32)
+    cnt[:3] = [0, 1, stride]
+    nbr = np.full((rows, stride), -1, dtype=np.int32)
+    for r in range(rows):
+        nbr[r, :cnt[r]] = np.sort(rng.choice(n, size=cnt[r], replace=False))
+    nodes = rng.integers(0, n, size=rows).astype(np.int32)
+    nodes[0], nodes[1] = 0, n - 1
+    nbr_d, cnt_d, nodes_d = (torch.from_numpy(x).to(dev) for x in (nbr, cnt, nodes))
+    live = torch.tensor([rows - 5], dtype=torch.int32, device=dev)
+    agg, selfr = ops.agg_fwd_sharded(table, nbr_d, stride, cnt_d, nodes_d, live, rows)
+    pad = torch.nn.functional.pad(dense, (0, (-dim) % 4)).contiguous()
+    want, _ = ops.agg_fwd(pad, dim, nbr_d, stride, cnt_d, live, rows, native.AGG_MEAN)
+    torch.cuda.synchronize()
+    ok = cnt[:rows - 5] > 0
+    got, ref = agg[:rows - 5, :dim].cpu().numpy(), want[:rows - 5, :dim].cpu().numpy()
+    assert rel(got[ok], ref[ok]) <= 1e-6
+    assert np.all(np.isnan(got[~ok]))                                   # 0/0 as in the reference (src/models.py:312-313)
+    assert torch.equal(selfr[:rows - 5, :dim], dense[nodes_d[:rows - 5].long()])
+
+
+@pytest.mark.parametrize('gcn', [False, True])
+def test_graphsage_over_sharded_table_matches_dense_table(P, dev, gcn):
+    from graphsage_b200 import models
+    from graphsage_b200.graph import AdjCSR
+    rowptr, col = cases.load_topology('cora')
+    n = len(rowptr) - 1
+    rng = np.random.default_rng(4)
+    feats = torch.from_numpy(rng.standard_normal((n, 128)).astype(np.float32)).to(dev)
+    table = P.ShardedTable.from_full(feats, 4)
+    adj = AdjCSR(rowptr, col)
+    torch.manual_seed(0)
+    a = models.GraphSage(2, 128, 64, table, adj, dev, gcn=gcn, agg_func='MEAN', seed=9, precision='fp32').to(dev)
+    b = models.GraphSage(2, 128, 64, table.to_dense_fp32(), adj, dev, gcn=gcn, agg_func='MEAN', seed=9, precision='fp32').to(dev)
+    b.load_state_dict(a.state_dict())
+    batch = np.arange(0, n, 9)
+    ea, eb = a(batch), b(batch)                       # same Philox seed and call count => same samples
+    assert rel(ea, eb) <= 1e-5
+    ea.square().sum().backward()
+    eb.square().sum().backward()
+    for l in (1, 2):
+        ga, gb = getattr(a, f'sage_layer{l}').weight.grad, getattr(b, f'sage_layer{l}').weight.grad
+        assert rel(ga, gb) <= 1e-5
+
+
+@pytest.mark.skipif(torch.cuda.is_available() and torch.cuda.device_count() < 2, reason='needs two GPUs')
+def test_two_ranks_over_cuda_ipc():
+    """Real peers: tests/mp_peer_check.py under torchrun on 2 GPUs (fused all-reduce/update against
+    NCCL + torch, bit-identical replicas, remote-shard gather)."""
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2', '--master-addr', '127.0.0.1',
+           '--master-port', '29517', os.path.join(ROOT, 'tests', 'mp_peer_check.py')]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert 'MP_PEER_CHECK_OK' in out.stdout
