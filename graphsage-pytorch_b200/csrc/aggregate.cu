@@ -8,6 +8,8 @@
 // independent 16-byte loads per lane are put in flight before any is consumed.  The kernel
 // is HBM-bound: algorithmic bytes per row = cnt*dim*4 (gathered rows) + dim*4 (output)
 // + cnt*4 (ids) + 4 (count)   [SURVEY.md §8(d)].
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gs {
@@ -15,50 +17,58 @@ namespace gs {
 constexpr int kAggWarps = 8;          // warps (= rows) per CTA
 constexpr int kBatch = 12;            // loads in flight per lane; covers fanout 10 + self in one go
 
+// Register-staged forward.  One warp per destination row, lane = float4 column.  The row's count,
+// its id list and the live-row counter are three INDEPENDENT loads (one latency), then up to
+// kBatch 16-byte row pieces per lane are in flight before the first is consumed.  <= 80 registers
+// keep 24 warps (= 24 rows, ~100 KB of gathers) resident per SM; a non-persistent grid lets the
+// hardware scheduler overlap the index latency of one wave with the gathers of the previous one.
 template <int MODE>
-__global__ void __launch_bounds__(kAggWarps * 32)
-agg_fwd_kernel(const float* __restrict__ table, int64_t ld, int dim4,
+__global__ void __launch_bounds__(kAggWarps * 32, MODE == GS_AGG_MEAN ? 3 : 2)
+agg_fwd_kernel(const float* __restrict__ table, uint32_t ld_bytes, int dim4,
                const int32_t* __restrict__ nbr, int stride, const int32_t* __restrict__ cnt,
                const int32_t* __restrict__ num_rows_dev, int max_rows,
                float* __restrict__ out, int64_t ld_out, int32_t* __restrict__ argmax, int64_t ld_arg) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * kAggWarps + (threadIdx.x >> 5);
-  if (r >= live_rows(num_rows_dev, max_rows)) return;
-  const int n = min(cnt[r], stride);
+  if (r >= max_rows) return;
   const int32_t* row_ids = nbr + static_cast<int64_t>(r) * stride;
+  const int n_raw = __ldg(cnt + r);
+  const int mine_raw = lane < stride ? __ldg(row_ids + lane) : -1;
+  if (r >= live_rows(num_rows_dev, max_rows)) return;
+  const int n = min(n_raw, stride);
   const float inv = 1.0f / static_cast<float>(n);         // n == 0 -> inf; 0 * inf = NaN as in the reference (0/0)
   const float qnan = __int_as_float(0x7fc00000);
+  const char* tbase = reinterpret_cast<const char*>(table);
 
   for (int cbase = 0; cbase < dim4; cbase += 32) {
     const int c4 = cbase + lane;
     const bool active = c4 < dim4;
+    const char* col = tbase + 16 * c4;
     float4 acc = (MODE == GS_AGG_MEAN) ? make_float4(0.f, 0.f, 0.f, 0.f)
                                        : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
     int4 arg = make_int4(-1, -1, -1, -1);
-    for (int jc = 0; jc < n; jc += 32) {
-      const int mine = (jc + lane < n) ? __ldg(row_ids + jc + lane) : -1;
+    for (int jc = 0; jc < n; jc += 32) {                  // lists longer than a warp: compatibility callers only
+      const int mine = jc == 0 ? (lane < n ? mine_raw : -1) : (jc + lane < n ? __ldg(row_ids + jc + lane) : -1);
       const int here = min(32, n - jc);
-      for (int j0 = 0; j0 < here; j0 += kBatch) {
+      for (int j0 = 0; j0 < here; j0 += kBatch) {         // a single pass for fan-out 10 (+ self)
         float4 v[kBatch];
         int id[kBatch];
 #pragma unroll
         for (int u = 0; u < kBatch; ++u) {
-          id[u] = __shfl_sync(0xffffffffu, mine, (j0 + u) & 31);
-          const bool ok = active && (j0 + u < here) && id[u] >= 0;
-          if (!ok) id[u] = -1;
-          if (ok) v[u] = ldg_stream_f4(table + static_cast<int64_t>(id[u]) * ld + 4 * c4);
+          const int got = __shfl_sync(0xffffffffu, mine, (j0 + u) & 31);
+          id[u] = (active && j0 + u < here) ? got : -1;
+          const char* src = col + static_cast<size_t>(static_cast<uint32_t>(id[u])) * ld_bytes;
+          v[u] = ldg_stream_f4_if<(MODE == GS_AGG_MEAN) ? 0u : 0xff800000u>(src, id[u] >= 0);   // 0 / -inf when off
         }
 #pragma unroll
         for (int u = 0; u < kBatch; ++u) {
-          if (id[u] >= 0) {
-            if (MODE == GS_AGG_MEAN) {
-              acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
-            } else {
-              if (v[u].x > acc.x) { acc.x = v[u].x; arg.x = id[u]; }
-              if (v[u].y > acc.y) { acc.y = v[u].y; arg.y = id[u]; }
-              if (v[u].z > acc.z) { acc.z = v[u].z; arg.z = id[u]; }
-              if (v[u].w > acc.w) { acc.w = v[u].w; arg.w = id[u]; }
-            }
+          if (MODE == GS_AGG_MEAN) {
+            acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+          } else {
+            if (v[u].x > acc.x) { acc.x = v[u].x; arg.x = id[u]; }
+            if (v[u].y > acc.y) { acc.y = v[u].y; arg.y = id[u]; }
+            if (v[u].z > acc.z) { acc.z = v[u].z; arg.z = id[u]; }
+            if (v[u].w > acc.w) { acc.w = v[u].w; arg.w = id[u]; }
           }
         }
       }
@@ -275,6 +285,16 @@ agg_fwd_pipe_kernel(const float* __restrict__ table, int64_t ld, int dim4, const
   cp_async_wait<0>();
 }
 
+// GS_AGG_IMPL=pipe selects the cp.async ring kernel (kept for A/B measurements); default: register kernel
+static int agg_impl() {
+  static int impl = -1;
+  if (impl < 0) {
+    const char* e = getenv("GS_AGG_IMPL");
+    impl = (e && e[0] == 'p') ? 1 : 0;
+  }
+  return impl;
+}
+
 template <int MODE, int STAGES>
 static int launch_pipe(const float* table, int64_t ld, int dim4, const int32_t* nbr, int stride, const int32_t* cnt,
                        const int32_t* num_rows_dev, int max_rows, float* out, int64_t ld_out, int32_t* argmax,
@@ -408,7 +428,7 @@ extern "C" int gs_agg_fwd(const float* table, int64_t ld, int32_t dim, const int
   if (argmax && ((ld_arg & 3) || ld_arg < 4 * dim4 || !aligned16(argmax))) return GS_ERR_ALIGNMENT;
   if (max_rows == 0) return GS_OK;
   cudaStream_t st = as_stream(stream);
-  if (stride <= kPipeMaxStride) {
+  if (agg_impl() == 1 && stride <= kPipeMaxStride) {
     // asynchronous-copy pipeline: slot = `stride` pieces of one column chunk
     const int f4 = dim4 < kPipeChunkF4 ? dim4 : kPipeChunkF4;
     const int slot_bytes = stride * f4 * 16;
@@ -422,13 +442,15 @@ extern "C" int gs_agg_fwd(const float* table, int64_t ld, int32_t dim, const int
     if (slot_bytes <= budget) { if (mode == GS_AGG_MEAN) GS_PIPE(GS_AGG_MEAN, 1); else GS_PIPE(GS_AGG_MAX, 1); }
 #undef GS_PIPE
   }
+  if (ld * 4 > 0xffffffffLL) return GS_ERR_UNSUPPORTED;
   const int blocks = (max_rows + kAggWarps - 1) / kAggWarps;
+  const uint32_t ld_bytes = static_cast<uint32_t>(ld * 4);
   if (mode == GS_AGG_MEAN)
     agg_fwd_kernel<GS_AGG_MEAN><<<blocks, kAggWarps * 32, 0, st>>>(
-        table, ld, dim4, nbr, stride, cnt, num_rows_dev, max_rows, out, ld_out, nullptr, 0);
+        table, ld_bytes, dim4, nbr, stride, cnt, num_rows_dev, max_rows, out, ld_out, nullptr, 0);
   else
     agg_fwd_kernel<GS_AGG_MAX><<<blocks, kAggWarps * 32, 0, st>>>(
-        table, ld, dim4, nbr, stride, cnt, num_rows_dev, max_rows, out, ld_out, argmax, ld_arg);
+        table, ld_bytes, dim4, nbr, stride, cnt, num_rows_dev, max_rows, out, ld_out, argmax, ld_arg);
   return finish_launch();
 }
 

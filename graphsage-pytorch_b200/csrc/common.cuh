@@ -38,6 +38,27 @@ __device__ __forceinline__ float4 ldg_stream_f4(const float* p) {
   return v;
 }
 
+// The same load under a predicate, yielding `fill` (a 32-bit pattern) in all four lanes when it is
+// off.  Written as one asm block so the compiler sees no select between the load and its use: a
+// batch of these issues back to back, which is the whole point of register staging.
+template <uint32_t FILL>
+__device__ __forceinline__ float4 ldg_stream_f4_if(const void* p, bool on) {
+  float4 v;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "mov.b32 %0, %6;\n\t"
+      "mov.b32 %1, %6;\n\t"
+      "mov.b32 %2, %6;\n\t"
+      "mov.b32 %3, %6;\n\t"
+      "@q ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];\n\t"
+      "}"
+      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+      : "l"(p), "r"(static_cast<int>(on)), "n"(FILL));
+  return v;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -9,11 +9,14 @@
 //
 // Why the operands are staged by threads and not by TMA: the A rows of the self half are a
 // gather through an index list and every operand needs an element-wise transform on the way
-// (ReLU mask for dZ, hi/lo split for the fp32-faithful mode), so 8 producer warps load 16-byte
-// pieces (coalesced per row), transform them in registers and store them into the 128-byte
-// swizzled layout the UMMA shared-memory descriptors expect; a proxy fence + mbarrier hands the
-// stage to the single MMA-issuing thread; tcgen05.commit hands it back.  The accumulator
-// (128 lanes x N fp32 columns) lives in TMEM and is read once by the epilogue (tcgen05.ld).
+// (hi/lo split for the fp32-faithful mode), so the 8 producer warps cp.async 16-byte pieces
+// (coalesced per row) straight into the 128-byte swizzled layout the UMMA shared-memory
+// descriptors expect, num_stages-1 k-stages ahead.  Every thread owns the same pieces in every
+// stage, so cp.async.wait_group is the only wait before it splits ITS pieces in place
+// (hi = trunc_tf32(x), lo = x - hi); a proxy fence + mbarrier hands the stage to the single
+// MMA-issuing thread and tcgen05.commit hands it back.  The accumulator (128 lanes x N fp32
+// columns) lives in TMEM, is read once (tcgen05.ld), transposed through the then idle operand
+// ring in shared memory and leaves the SM as full coalesced rows (float4 stores / vector REDs).
 //
 // Precision modes:
 //   GS_PREC_TF32   one tf32 product  (10-bit mantissa operands, fp32 accumulate)
@@ -29,11 +32,17 @@ constexpr int kTileM = 128;
 constexpr int kBK = 32;                                  // tf32 elements per k-stage: 128 bytes, one swizzle row
 constexpr int kProducerWarps = 8;
 constexpr int kProducerThreads = kProducerWarps * 32;
-constexpr int kLoaderWarps = 8;                          // cp.async issuers of the asynchronous path (4 for A, 4 for B)
-constexpr int kThreads = kProducerThreads + 32 + kLoaderWarps * 32;   // converters/epilogue + MMA/TMEM warp + loaders
+constexpr int kThreads = kProducerThreads + 32;          // producers/epilogue + MMA/TMEM warp
 constexpr int kMaxStages = 4;
 constexpr int kSmemBudget = 196 * 1024;
-constexpr int kMaxChunkRows = 512;                       // bwd_w: rows reduced per CTA (index cache size)
+constexpr int kMaxChunkRows = 512;
+// kind::tf32 reads the top 19 bits of each 32-bit operand element (the low 13 mantissa bits are
+// ignored), so the "hi" operand of the 3-term split is the raw fp32 value and only lo = x - trunc(x)
+// has to be written.  Checked by the 1e-5 parity tests: a rounding tensor core would miss them by 1e-4.
+#ifndef GS_TC_IMPLICIT_TRUNC
+#define GS_TC_IMPLICIT_TRUNC 1
+#endif
+constexpr bool kImplicitTrunc = GS_TC_IMPLICIT_TRUNC != 0;                       // bwd_w: rows reduced per CTA (index cache size)
 
 // ---------------------------------------------------------------------------------------------
 // optional pipeline trace (build with -DGS_TC_TRACE): CTA 0 records SM clock at pipeline events
@@ -73,10 +82,6 @@ __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, u
   // no "memory" clobber on purpose: the compiler may hoist the (independent) index loads of the
   // next pieces above this copy; ordering against the mbarrier operations is kept by `volatile`.
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes));
-}
-// the mbarrier receives one arrival from this thread once all its earlier cp.async have landed
-__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -228,21 +233,6 @@ struct XView {            // virtual concat operand, see sage_gemm.cu
 
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
-// One operand row as the loader warps see it: elements [0, split) come from p0, [split, limit)
-// from p1 (stored pre-offset by -split so that p1 + x is the address), anything else is zero.
-struct RowDesc {
-  const float* p0; const float* p1; int split, limit;
-  __device__ __forceinline__ const float* at(int x) const {
-    return x < split ? p0 + x : (x < limit ? p1 + x : nullptr);
-  }
-};
-__device__ __forceinline__ RowDesc empty_row() { return RowDesc{nullptr, nullptr, 0, 0}; }
-__device__ __forceinline__ RowDesc xview_row(const XView& x, int r) {
-  if (x.gcn) return RowDesc{x.agg + static_cast<int64_t>(r) * x.ld_agg, nullptr, x.dim_pad, x.dim_pad};
-  return RowDesc{x.self_table + static_cast<int64_t>(x.self_row(r)) * x.ld_self,
-                 x.agg + static_cast<int64_t>(r) * x.ld_agg - x.dim_pad, x.dim_pad, 2 * x.dim_pad};
-}
-
 struct LoadX_K {           // forward A: X rows, K-major
   XView x; int row0, rows;
   __device__ __forceinline__ float4 operator()(int e, int k, int ks) const {
@@ -255,8 +245,20 @@ struct LoadX_K {           // forward A: X rows, K-major
     if (r >= rows || kv >= x.kv_total()) return nullptr;
     return x.ptr4(r, kv);
   }
-  __device__ __forceinline__ RowDesc row(int e, int) const { return row0 + e < rows ? xview_row(x, row0 + e) : empty_row(); }
-  __device__ __forceinline__ int origin() const { return 0; }
+  // per-piece state computed once: the piece's source is affine in the k-stage
+  struct Prep { const float* s; const float* a; int k; };
+  __device__ __forceinline__ Prep prep(int e, int k) const {
+    const int r = row0 + e;
+    if (r >= rows) return Prep{nullptr, nullptr, 1 << 30};
+    const float* a = x.agg + static_cast<int64_t>(r) * x.ld_agg + k - (x.gcn ? 0 : x.dim_pad);
+    const float* sp = x.gcn ? a : x.self_table + static_cast<int64_t>(x.self_row(r)) * x.ld_self + k;
+    return Prep{sp, a, k};
+  }
+  __device__ __forceinline__ const float* ptr(const Prep& p, int ks) const {
+    const int kv = ks * kBK + p.k;
+    if (kv >= x.kv_total()) return nullptr;                  // also rows beyond the tile (k = 2^30)
+    return (kv < x.dim_pad ? p.s : p.a) + ks * kBK;
+  }
 };
 struct LoadW_K {           // forward B: W[h, wcol(kv)], K-major
   XView x; const float* w; int64_t ldw; int h0, out_dim; bool vec_ok;
@@ -275,11 +277,15 @@ struct LoadW_K {           // forward B: W[h, wcol(kv)], K-major
     if (h >= out_dim || kv >= x.kv_total()) return nullptr;
     return w + static_cast<int64_t>(h) * ldw + kv;
   }
-  __device__ __forceinline__ RowDesc row(int e, int) const {
-    const int kt = x.kv_total();
-    return h0 + e < out_dim ? RowDesc{w + static_cast<int64_t>(h0 + e) * ldw, nullptr, kt, kt} : empty_row();
+  struct Prep { const float* p; int k; };
+  __device__ __forceinline__ Prep prep(int e, int k) const {
+    const int h = h0 + e;
+    if (h >= out_dim) return Prep{nullptr, 1 << 30};
+    return Prep{w + static_cast<int64_t>(h) * ldw + k, k};
   }
-  __device__ __forceinline__ int origin() const { return 0; }
+  __device__ __forceinline__ const float* ptr(const Prep& p, int ks) const {
+    return ks * kBK + p.k < x.kv_total() ? p.p + ks * kBK : nullptr;
+  }
 };
 struct LoadDZ_K {          // bwd_x A: dZ rows (ReLU mask), K-major over h
   const float* go; int64_t ld_go; const float* out; int64_t ld_out; int row0, rows, out_dim, relu;
@@ -302,10 +308,15 @@ struct LoadDZ_K {          // bwd_x A: dZ rows (ReLU mask), K-major over h
     if (r >= rows || h >= out_dim) return nullptr;
     return go + static_cast<int64_t>(r) * ld_go + h;
   }
-  __device__ __forceinline__ RowDesc row(int e, int) const {
-    return row0 + e < rows ? RowDesc{go + static_cast<int64_t>(row0 + e) * ld_go, nullptr, out_dim, out_dim} : empty_row();
+  struct Prep { const float* p; int k; };
+  __device__ __forceinline__ Prep prep(int e, int k) const {
+    const int r = row0 + e;
+    if (r >= rows) return Prep{nullptr, 1 << 30};
+    return Prep{go + static_cast<int64_t>(r) * ld_go + k, k};
   }
-  __device__ __forceinline__ int origin() const { return 0; }
+  __device__ __forceinline__ const float* ptr(const Prep& p, int ks) const {
+    return ks * kBK + p.k < out_dim ? p.p + ks * kBK : nullptr;
+  }
 };
 struct LoadW_MN {          // bwd_x B: W[h = k, c = n..n+3], MN-major (c contiguous)
   const float* w; int64_t ldw; int c0, ncols, out_dim; bool vec_ok;
@@ -324,11 +335,15 @@ struct LoadW_MN {          // bwd_x B: W[h = k, c = n..n+3], MN-major (c contigu
     if (h >= out_dim || c >= ncols) return nullptr;
     return w + static_cast<int64_t>(h) * ldw + c;
   }
-  __device__ __forceinline__ RowDesc row(int k, int ks) const {
-    const int h = ks * kBK + k;
-    return h < out_dim ? RowDesc{w + static_cast<int64_t>(h) * ldw, nullptr, ncols, ncols} : empty_row();
+  struct Prep { const float* p; int k; };
+  __device__ __forceinline__ Prep prep(int e, int k) const {
+    const int c = c0 + e;
+    if (c >= ncols) return Prep{nullptr, 1 << 30};
+    return Prep{w + static_cast<int64_t>(k) * ldw + c, k};
   }
-  __device__ __forceinline__ int origin() const { return c0; }
+  __device__ __forceinline__ const float* ptr(const Prep& p, int ks) const {
+    return ks * kBK + p.k < out_dim ? p.p + static_cast<int64_t>(ks * kBK) * ldw : nullptr;
+  }
 };
 struct LoadDZ_MN {         // bwd_w A: dZ[r = k, h = m..m+3], MN-major (h contiguous)
   const float* go; int64_t ld_go; const float* out; int64_t ld_out; int r_begin, r_end, h0, out_dim, relu;
@@ -351,11 +366,15 @@ struct LoadDZ_MN {         // bwd_w A: dZ[r = k, h = m..m+3], MN-major (h contig
     if (r >= r_end || h >= out_dim) return nullptr;
     return go + static_cast<int64_t>(r) * ld_go + h;
   }
-  __device__ __forceinline__ RowDesc row(int k, int ks) const {
-    const int r = r_begin + ks * kBK + k;
-    return r < r_end ? RowDesc{go + static_cast<int64_t>(r) * ld_go, nullptr, out_dim, out_dim} : empty_row();
+  struct Prep { const float* p; int r; };
+  __device__ __forceinline__ Prep prep(int e, int k) const {
+    const int h = h0 + e;
+    if (h >= out_dim) return Prep{nullptr, 1 << 30};
+    return Prep{go + static_cast<int64_t>(r_begin + k) * ld_go + h, r_begin + k};
   }
-  __device__ __forceinline__ int origin() const { return h0; }
+  __device__ __forceinline__ const float* ptr(const Prep& p, int ks) const {
+    return p.r + ks * kBK < r_end ? p.p + static_cast<int64_t>(ks * kBK) * ld_go : nullptr;
+  }
 };
 struct LoadX_MN {          // bwd_w B: X[r = k, kv = n..n+3], MN-major (kv contiguous)
   XView x; int r_begin, r_end, kv0;
@@ -369,64 +388,86 @@ struct LoadX_MN {          // bwd_w B: X[r = k, kv = n..n+3], MN-major (kv conti
     if (r >= r_end || kv >= x.kv_total()) return nullptr;
     return x.ptr4(r, kv);
   }
-  __device__ __forceinline__ RowDesc row(int k, int ks) const {
-    const int r = r_begin + ks * kBK + k;
-    return r < r_end ? xview_row(x, r) : empty_row();
+  // agg half: affine in the k-stage; self half: one index lookup (shared-memory cache) per stage
+  struct Prep { const float* a; int r; int kv; };
+  __device__ __forceinline__ Prep prep(int e, int k) const {
+    const int kv = kv0 + e;
+    if (kv >= x.kv_total()) return Prep{nullptr, 1 << 30, 0};
+    const bool self_half = !x.gcn && kv < x.dim_pad;
+    const float* a = self_half ? nullptr
+                               : x.agg + static_cast<int64_t>(r_begin + k) * x.ld_agg + kv - (x.gcn ? 0 : x.dim_pad);
+    return Prep{a, r_begin + k, kv};
   }
-  __device__ __forceinline__ int origin() const { return kv0; }
+  __device__ __forceinline__ const float* ptr(const Prep& p, int ks) const {
+    const int r = p.r + ks * kBK;
+    if (r >= r_end) return nullptr;
+    if (p.a) return p.a + static_cast<int64_t>(ks * kBK) * x.ld_agg;
+    return x.self_table + static_cast<int64_t>(x.self_row(r)) * x.ld_self + p.kv;
+  }
 };
 
 // ---------------------------------------------------------------------------------------------
-// epilogues: called per thread with row m (tile-local, = TMEM lane) and 32 accumulator columns
+// epilogues: called with tile-local row m (= TMEM lane), tile-local column n (n % 4 == 0) and 4
+// consecutive accumulator columns; the lanes of a warp hold consecutive n of ONE row, so global
+// accesses are coalesced
 // ---------------------------------------------------------------------------------------------
 struct StoreOut {          // forward: out[r, h] = relu(acc)
   float* out; int64_t ld_out; int row0, rows, h0, out_dim, relu;
-  __device__ __forceinline__ void operator()(int m, int n_base, const uint32_t (&v)[32]) const {
-    const int r = row0 + m;
-    if (r >= rows) return;
-    float* dst = out + static_cast<int64_t>(r) * ld_out + h0 + n_base;
-    const int lim = out_dim - h0 - n_base;
-    if (lim >= 32 && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-        *reinterpret_cast<float4*>(dst + j) = o;
-      }
+  __device__ __forceinline__ void operator()(int m, int n, float4 v) const {
+    const int r = row0 + m, h = h0 + n;
+    if (r >= rows || h >= out_dim) return;
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    float* dst = out + static_cast<int64_t>(r) * ld_out + h;
+    if (h + 3 < out_dim && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+      *reinterpret_cast<float4*>(dst) = v;
     } else {
+      const float o[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < lim) { const float o = __uint_as_float(v[j]); dst[j] = relu ? fmaxf(o, 0.f) : o; }
+      for (int j = 0; j < 4; ++j) if (h + j < out_dim) dst[j] = o[j];
     }
   }
 };
 struct StoreDX {           // bwd_x: dX[r, c] -> grad_self (c < dim) / grad_agg (c >= dim)
   float* gs; int64_t ld_gs; float* ga; int64_t ld_ga; int row0, rows, c0, dim, ncols, gcn;
-  __device__ __forceinline__ void operator()(int m, int n_base, const uint32_t (&v)[32]) const {
-    const int r = row0 + m;
-    if (r >= rows) return;
+  __device__ __forceinline__ void operator()(int m, int n, float4 v) const {
+    const int r = row0 + m, c = c0 + n;
+    if (r >= rows || c >= ncols) return;
+    const bool to_self = !gcn && c < dim;
+    float* dst = to_self ? gs + static_cast<int64_t>(r) * ld_gs + c
+                         : ga + static_cast<int64_t>(r) * ld_ga + (gcn ? c : c - dim);
+    const int lim = to_self ? dim : ncols;                    // a 4-group never straddles the seam when dim % 4 == 0
+    if (c + 3 < lim && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+      *reinterpret_cast<float4*>(dst) = v;
+    } else {
+      const float o[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int c = c0 + n_base + j;
-      if (c >= ncols) continue;
-      const float o = __uint_as_float(v[j]);
-      if (gcn) ga[static_cast<int64_t>(r) * ld_ga + c] = o;
-      else if (c < dim) gs[static_cast<int64_t>(r) * ld_gs + c] = o;
-      else ga[static_cast<int64_t>(r) * ld_ga + (c - dim)] = o;
+      for (int j = 0; j < 4; ++j) {
+        const int cj = c + j;
+        if (cj >= ncols) continue;
+        if (gcn) ga[static_cast<int64_t>(r) * ld_ga + cj] = o[j];
+        else if (cj < dim) gs[static_cast<int64_t>(r) * ld_gs + cj] = o[j];
+        else ga[static_cast<int64_t>(r) * ld_ga + (cj - dim)] = o[j];
+      }
     }
   }
 };
-struct AddDW {             // bwd_w: grad_w[h, wcol(kv)] += acc   (row chunks reduced with fp32 atomics)
+struct AddDW {             // bwd_w: grad_w[h, wcol(kv)] += acc   (row chunks reduced with fp32 REDs)
   XView x; float* gw; int64_t ldw; int h0, out_dim, kv0;
-  __device__ __forceinline__ void operator()(int m, int n_base, const uint32_t (&v)[32]) const {
-    const int h = h0 + m;
-    if (h >= out_dim) return;
+  __device__ __forceinline__ void operator()(int m, int n, float4 v) const {
+    const int h = h0 + m, kv = kv0 + n;
     const int kt = x.kv_total();
+    if (h >= out_dim || kv >= kt) return;
+    float* row = gw + static_cast<int64_t>(h) * ldw;
+    const int c = x.wcol(kv);
+    if ((x.dim & 3) == 0 && c >= 0 && ((reinterpret_cast<uintptr_t>(row + c) & 15u) == 0)) {
+      atomicAdd(reinterpret_cast<float4*>(row + c), v);       // dim % 4 == 0: the 4 columns are consecutive in W
+    } else {
+      const float o[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int kv = kv0 + n_base + j;
-      const int c = kv < kt ? x.wcol(kv) : -1;
-      if (c >= 0) atomicAdd(gw + static_cast<int64_t>(h) * ldw + c, __uint_as_float(v[j]));
+      for (int j = 0; j < 4; ++j) {
+        const int cj = kv + j < kt ? x.wcol(kv + j) : -1;
+        if (cj >= 0) atomicAdd(row + cj, o[j]);
+      }
     }
   }
 };
@@ -434,6 +475,17 @@ struct AddDW {             // bwd_w: grad_w[h, wcol(kv)] += acc   (row chunks re
 // ---------------------------------------------------------------------------------------------
 // the core: one CTA computes a [128 x n_tile] accumulator over `k_stages` stages of 32.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_pending(int n) {      // at most n groups still in flight
+  switch (n) {
+    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+  }
+}
+__device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory"); }
+
 template <bool A_MN, bool B_MN, bool SPLIT3, bool ASYNC, class LoadA, class LoadB, class Epi>
 __device__ __forceinline__ void gemm_core(const LoadA& load_a, const LoadB& load_b, const Epi& epi, int n_tile,
                                           int k_stages, int num_stages, unsigned char* smem, const void* gdummy) {
@@ -445,10 +497,8 @@ __device__ __forceinline__ void gemm_core(const LoadA& load_a, const LoadB& load
   const int stage_bytes = (SPLIT3 ? 2 : 1) * (a_bytes + b_bytes);
   __shared__ __align__(8) uint64_t s_full[kMaxStages];
   __shared__ __align__(8) uint64_t s_empty[kMaxStages];
-  __shared__ __align__(8) uint64_t s_landed[kMaxStages];
   __shared__ __align__(8) uint64_t s_acc;
   __shared__ uint32_t s_tmem;
-  __shared__ RowDesc s_rowdesc[kLoaderWarps][32];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t tmem_cols = n_tile <= 32 ? 32u : n_tile <= 64 ? 64u : n_tile <= 128 ? 128u : 256u;
@@ -457,7 +507,6 @@ __device__ __forceinline__ void gemm_core(const LoadA& load_a, const LoadB& load
     for (int s = 0; s < num_stages; ++s) {
       mbar_init(smem_u32(&s_full[s]), kProducerThreads);
       mbar_init(smem_u32(&s_empty[s]), 1);
-      mbar_init(smem_u32(&s_landed[s]), kLoaderWarps * 32);
     }
     mbar_init(smem_u32(&s_acc), 1);
     fence_barrier_init();
@@ -475,50 +524,89 @@ __device__ __forceinline__ void gemm_core(const LoadA& load_a, const LoadB& load
     const int b_chunks = chunks_in_tile(n_tile, B_MN);
     constexpr int kMaxA = 4, kMaxB = 8;           // 1024 / 256 and 2048 / 256 pieces per thread
     if (ASYNC) {
-      // ================= converters, asynchronous path =================
-      // The two loader warps (below) cp.async every 16-byte piece straight into its swizzled
-      // slot of the *hi* buffer, as many stages ahead as the ring allows and without holding
-      // registers, so the gather latency of several stages overlaps.  When a stage has landed
-      // these 8 warps rewrite hi = trunc_tf32(x) and derive lo = x - hi in shared memory
-      // (3xTF32 only), then hand the stage to the tensor core.
+      // ================= producers, asynchronous path: cp.async ring, num_stages - 1 stages ahead =================
+      const int ahead = num_stages - 1;            // 0 only if a single stage fits (then load and compute alternate)
+      typename LoadA::Prep pa[kMaxA];
+      typename LoadB::Prep pb[kMaxB];
+      int oa[kMaxA], ob[kMaxB];                    // byte offset of my pieces inside an operand tile (-1: none)
+#pragma unroll
+      for (int i = 0; i < kMaxA; ++i) {
+        const int q = tid + i * kProducerThreads;
+        int e = 0, k = 0;
+        oa[i] = -1;
+        if (q < a_chunks) chunk_coords(q, kTileM, A_MN, e, k, oa[i]);
+        pa[i] = load_a.prep(e, k);
+      }
+#pragma unroll
+      for (int i = 0; i < kMaxB; ++i) {
+        const int q = tid + i * kProducerThreads;
+        int e = 0, k = 0;
+        ob[i] = -1;
+        if (q < b_chunks) chunk_coords(q, n_tile, B_MN, e, k, ob[i]);
+        pb[i] = load_b.prep(e, k);
+      }
+      int issued = 0;
+      auto issue_next = [&]() {                    // always commits exactly one group (empty past the last stage)
+        if (issued < k_stages) {
+          const int stage = issued % num_stages;
+          if (issued >= num_stages) mbar_wait(smem_u32(&s_empty[stage]), static_cast<uint32_t>(issued / num_stages - 1) & 1u);
+          const uint32_t a_hi = smem_base + stage * stage_bytes;
+          const uint32_t b_hi = a_hi + (SPLIT3 ? 2 : 1) * a_bytes;
+#pragma unroll
+          for (int i = 0; i < kMaxA; ++i) {
+            if (oa[i] >= 0) {
+              const float* src = load_a.ptr(pa[i], issued);
+              cp_async16(a_hi + oa[i], src ? static_cast<const void*>(src) : gdummy, src ? 16u : 0u);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < kMaxB; ++i) {
+            if (ob[i] >= 0) {
+              const float* src = load_b.ptr(pb[i], issued);
+              cp_async16(b_hi + ob[i], src ? static_cast<const void*>(src) : gdummy, src ? 16u : 0u);
+            }
+          }
+        }
+        cp_async_commit_group();
+        if (warp == 0 && issued < k_stages) GS_TRACE(19 + 4 * issued);
+        ++issued;
+      };
+      for (int i = 0; i < ahead; ++i) issue_next();
       for (int ks = 0; ks < k_stages; ++ks) {
         const int stage = ks % num_stages;
-        mbar_wait(smem_u32(&s_landed[stage]), static_cast<uint32_t>(ks / num_stages) & 1u);
+        if (ahead == 0) issue_next();
+        cp_async_wait_pending(ahead == 0 ? 0 : ahead - 1);       // my pieces of stage ks have landed
         if (warp == 0) GS_TRACE(16 + 4 * ks);
-        if (SPLIT3) {
+        if (SPLIT3) {                                            // split MY pieces in place: hi = trunc_tf32(x), lo = x - hi
           unsigned char* a_hi = smem_al + stage * stage_bytes;
           unsigned char* a_lo = a_hi + a_bytes;
           unsigned char* b_hi = a_hi + 2 * a_bytes;
           unsigned char* b_lo = b_hi + b_bytes;
 #pragma unroll
           for (int i = 0; i < kMaxA; ++i) {
-            const int q = tid + i * kProducerThreads;
-            if (q < a_chunks) {
-              int e, k, off;
-              chunk_coords(q, kTileM, A_MN, e, k, off);
-              const float4 v = *reinterpret_cast<const float4*>(a_hi + off);
+            if (oa[i] >= 0) {
+              const float4 v = *reinterpret_cast<const float4*>(a_hi + oa[i]);
               const float4 h = tf32_hi(v);
-              *reinterpret_cast<float4*>(a_hi + off) = h;
-              *reinterpret_cast<float4*>(a_lo + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+              if (!kImplicitTrunc) *reinterpret_cast<float4*>(a_hi + oa[i]) = h;
+              *reinterpret_cast<float4*>(a_lo + oa[i]) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
             }
           }
 #pragma unroll
           for (int i = 0; i < kMaxB; ++i) {
-            const int q = tid + i * kProducerThreads;
-            if (q < b_chunks) {
-              int e, k, off;
-              chunk_coords(q, n_tile, B_MN, e, k, off);
-              const float4 v = *reinterpret_cast<const float4*>(b_hi + off);
+            if (ob[i] >= 0) {
+              const float4 v = *reinterpret_cast<const float4*>(b_hi + ob[i]);
               const float4 h = tf32_hi(v);
-              *reinterpret_cast<float4*>(b_hi + off) = h;
-              *reinterpret_cast<float4*>(b_lo + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+              if (!kImplicitTrunc) *reinterpret_cast<float4*>(b_hi + ob[i]) = h;
+              *reinterpret_cast<float4*>(b_lo + ob[i]) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
             }
           }
         }
-        fence_proxy_async();
+        fence_proxy_async();                       // generic-proxy writes -> visible to the tensor-core (async) proxy
         mbar_arrive(smem_u32(&s_full[stage]));
         if (warp == 0) GS_TRACE(17 + 4 * ks);
+        if (ahead > 0) issue_next();               // refill the stage the MMA of k-stage ks-1 is about to release
       }
+      cp_async_wait_pending(0);
     } else {
     // ================= producers, register-staged path: global -> registers -> swizzled smem =================
     // (operands whose rows are not 16-byte aligned, or that need the ReLU mask applied on the fly)
@@ -578,20 +666,45 @@ __device__ __forceinline__ void gemm_core(const LoadA& load_a, const LoadB& load
       mbar_arrive(smem_u32(&s_full[stage]));
     }
     }
-    // =========================== epilogue: TMEM -> registers -> global ===========================
-    mbar_wait(smem_u32(&s_acc), 0);
+    // =========================== epilogue: TMEM -> registers -> smem (transpose) -> global ===========================
+    mbar_wait(smem_u32(&s_acc), 0);                // every MMA has completed: the operand ring is idle
     tc_fence_after();
     if (warp == 0) GS_TRACE(2);
     const int quad = warp & 3;                     // a warp may only touch TMEM lanes 32*(warp%4) .. +31
     const int m = quad * 32 + lane;
     const int n_chunks = (n_tile + 31) / 32;
+    const int ldst = n_tile + 4;                   // floats per staged row (+4: rows land on different banks)
+    float* stg = reinterpret_cast<float*>(smem_al);
     for (int c = warp >> 2; c < n_chunks; c += 2) {
       uint32_t v[32];
       tmem_ld32(tmem_acc + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(c * 32), v);
-      epi(m, c * 32, v);
+      float* dst = stg + m * ldst + c * 32;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        if (c * 32 + j < n_tile)
+          *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                            __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+    }
+    tc_fence_before();
+    if (warp == 0) GS_TRACE(4);
+    producers_sync();
+    if (warp == 0) GS_TRACE(5);
+    const int n4 = n_tile >> 2;
+    const uint32_t stg_s = smem_base;               // explicit shared-space loads: LDS, and no aliasing with the global stores
+    for (int q = lane; q < n4; q += 32) {
+#pragma unroll 1
+      for (int m0 = warp; m0 < kTileM; m0 += 4 * kProducerWarps) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t a = stg_s + static_cast<uint32_t>(((m0 + u * kProducerWarps) * ldst + 4 * q) * 4);
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "r"(a));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) epi(m0 + u * kProducerWarps, 4 * q, v[u]);
+      }
     }
     if (warp == 0) GS_TRACE(3);
-    tc_fence_before();
   } else if (warp == kProducerWarps) {
     // =========================== MMA issuer (one elected thread) ===========================
     const uint32_t idesc = make_idesc(kTileM, n_tile, A_MN, B_MN);
@@ -627,62 +740,6 @@ __device__ __forceinline__ void gemm_core(const LoadA& load_a, const LoadB& load
       __syncwarp();
     }
     tc_fence_before();
-  }
-  else if (ASYNC) {
-    // =========================== loader warps: 4 stream A, 4 stream B ===========================
-    // A lone warp retires roughly one dependent instruction per 4-6 cycles, so the per-piece
-    // address arithmetic is what bounds a cp.async stream (measured: ~400 cycles per piece with
-    // generic per-piece addressing).  Each warp therefore first builds, lane-per-row, a small
-    // table of row descriptors in shared memory (base pointers, the self|agg seam, the valid
-    // length) and then walks the pieces lane-per-piece (coalesced) with ~8 instructions each.
-    const int lw = warp - (kProducerWarps + 1);                  // 0..7
-    const bool is_a = lw < 4;
-    const int part = lw & 3;                                     // which quarter of the operand
-    RowDesc* desc = s_rowdesc[lw];
-    for (int ks = 0; ks < k_stages; ++ks) {
-      const int stage = ks % num_stages;
-      if (ks >= num_stages) mbar_wait(smem_u32(&s_empty[stage]), static_cast<uint32_t>(ks / num_stages - 1) & 1u);
-      const uint32_t a_hi = smem_base + stage * stage_bytes;
-      const uint32_t dst = is_a ? a_hi : a_hi + (SPLIT3 ? 2 : 1) * a_bytes;
-      const bool mn = is_a ? A_MN : B_MN;
-      const int extent = is_a ? kTileM : n_tile;
-      if (!mn) {
-        // K-major: tile rows e, 8 pieces (128 B) per row.  This warp owns rows part*32 + 128*j.
-        const int k0 = ks * kBK;
-        for (int e0 = part * 32; e0 < extent; e0 += 128) {
-          __syncwarp();
-          desc[lane] = is_a ? load_a.row(e0 + lane, ks) : load_b.row(e0 + lane, ks);
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int el = 4 * i + (lane >> 3), c = lane & 7, e = e0 + el;
-            if (e < extent) {
-              const float* src = desc[el].at(k0 + 4 * c);
-              cp_async16(dst + e * 128 + ((c ^ (e & 7)) << 4), src ? static_cast<const void*>(src) : gdummy, src ? 16u : 0u);
-            }
-          }
-        }
-      } else {
-        // MN-major: tile rows k (32 per stage), G*8 pieces per row.  This warp owns k = part*8 .. +7.
-        const int groups = (extent + 31) / 32, per_k = groups * 8;
-        const int origin = is_a ? load_a.origin() : load_b.origin();
-        __syncwarp();
-        if (lane < 8) desc[lane] = is_a ? load_a.row(part * 8 + lane, ks) : load_b.row(part * 8 + lane, ks);
-        __syncwarp();
-        for (int kl = 0; kl < 8; ++kl) {
-          const int k = part * 8 + kl;
-          const uint32_t row_dst = dst + (k >> 2) * groups * 512 + (k & 3) * 128;
-          for (int cc = lane; cc < per_k; cc += 32) {
-            const int g = cc >> 3, c = cc & 7;
-            const float* src = desc[kl].at(origin + g * 32 + 4 * c);
-            cp_async16(row_dst + g * 512 + ((((c >> 1) ^ (k & 3)) << 5) | ((c & 1) << 4)),
-                       src ? static_cast<const void*>(src) : gdummy, src ? 16u : 0u);
-          }
-        }
-      }
-      cp_async_mbar_arrive_noinc(smem_u32(&s_landed[stage]));
-      if (lw == 0) GS_TRACE(19 + 4 * ks);
-    }
   }
   __syncthreads();
   if (warp == kProducerWarps) {
@@ -750,17 +807,23 @@ sage_bwd_w_tc_kernel(XView x, const float* __restrict__ grad_out, int64_t ld_go,
 
 struct Plan { int n_tile, num_stages, smem; };
 
-static Plan make_plan(int n_total, bool a_mn, bool b_mn, bool split3) {
+// n_total output columns, `m_tiles` CTAs along M.  n_tile is capped so that at least 3 stages of the
+// (split) operand ring fit, and halved while the grid would leave most SMs idle (the extra CTAs
+// re-read the A tile from L2, which is cheap next to an idle SM).
+static Plan make_plan(int n_total, bool a_mn, bool b_mn, bool split3, int m_tiles) {
   Plan p{};
   int n_tile = (n_total + 15) & ~15;
-  if (n_tile > 256) n_tile = 256;
+  const int cap = split3 ? 128 : 256;
+  if (n_tile > cap) n_tile = cap;
+  while (n_tile > 32 && m_tiles * ((n_total + n_tile - 1) / n_tile) < kNumSMs / 2) n_tile = ((n_tile / 2) + 15) & ~15;
   p.n_tile = n_tile;
   const int stage = (split3 ? 2 : 1) * (tile_bytes(kTileM, a_mn) + tile_bytes(n_tile, b_mn));
   int stages = kSmemBudget / stage;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 1) stages = 1;
   p.num_stages = stages;
-  p.smem = stages * stage + 1024;
+  const int staging = kTileM * (n_tile + 4) * 4;              // epilogue transpose buffer reuses the ring
+  p.smem = (stages * stage > staging ? stages * stage : staging) + 1024;
   return p;
 }
 
@@ -798,7 +861,7 @@ int gs_sage_gemm_fwd_tc(const float* self_table, int64_t ld_self, const int32_t*
   if (precision != GS_PREC_TF32 && !split3) return GS_ERR_BAD_ARG;
   XView x{self_table, ld_self, self_idx, agg, ld_agg, dim, (dim + 3) & ~3, gcn, nullptr, 0, 0};
   const int kt = gcn ? x.dim_pad : 2 * x.dim_pad;
-  const Plan p = make_plan(out_dim, false, false, split3);
+  const Plan p = make_plan(out_dim, false, false, split3, (max_rows + kTileM - 1) / kTileM);
   const int k_stages = (kt + kBK - 1) / kBK;
   const bool vec_ok = (dim % 4 == 0) && (ldw % 4 == 0) && aligned16(weight);
   const bool async = vec_ok;                       // X rows are always 16-byte aligned (padded tables)
@@ -815,7 +878,7 @@ int gs_sage_gemm_bwd_x_tc(const float* grad_out, int64_t ld_go, const float* out
   const bool split3 = precision == GS_PREC_TF32X3;
   if (precision != GS_PREC_TF32 && !split3) return GS_ERR_BAD_ARG;
   const int ncols = gcn ? dim : 2 * dim;
-  const Plan p = make_plan(ncols, false, true, split3);
+  const Plan p = make_plan(ncols, false, true, split3, (max_rows + kTileM - 1) / kTileM);
   const int k_stages = (out_dim + kBK - 1) / kBK;
   const bool vec_ok = (ldw % 4 == 0) && aligned16(weight);
   const bool async = vec_ok && !relu && (ncols % 4 == 0) && (out_dim % 4 == 0) && (ld_go % 4 == 0) && aligned16(grad_out);
@@ -834,7 +897,7 @@ int gs_sage_gemm_bwd_w_tc(const float* self_table, int64_t ld_self, const int32_
   if (precision != GS_PREC_TF32 && !split3) return GS_ERR_BAD_ARG;
   XView x{self_table, ld_self, self_idx, agg, ld_agg, dim, (dim + 3) & ~3, gcn, nullptr, 0, 0};
   const int kt = gcn ? x.dim_pad : 2 * x.dim_pad;
-  const Plan p = make_plan(kt, true, true, split3);
+  const Plan p = make_plan(kt, true, true, split3, kNumSMs);   // row chunks fill the machine
   const int tiles = ((kt + p.n_tile - 1) / p.n_tile) * ((out_dim + kTileM - 1) / kTileM);
   int chunks = (kNumSMs + tiles - 1) / tiles;                 // about one CTA per SM
   const int max_chunks = (max_rows + 4 * kBK - 1) / (4 * kBK);   // at least 4 k-stages per CTA

@@ -1,5 +1,5 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: one training step
-(the launches between two consecutive clip_sgd pairs) and per-kernel totals."""
+(the launches between two consecutive update kernels) and per-kernel totals."""
 import collections
 import csv
 import sys
@@ -10,8 +10,10 @@ def main(path, step_index=-2):
     hdr = rows[0]
     ki, vi, ii = hdr.index('Kernel Name'), hdr.index('Metric Value'), hdr.index('ID')
     data = [(int(r[ii]), r[ki], float(r[vi].replace(',', '')) / 1000.0) for r in rows[1:]]
-    ends = [i for i, d in enumerate(data) if 'clip_sgd_kernel' in d[1]]
-    ends = [e for j, e in enumerate(ends) if j % 2 == 1]          # second clip_sgd of each step
+    ends = [i for i, d in enumerate(data) if 'dp_update_kernel' in d[1]]       # fused exchange+update ends a step
+    if not ends:
+        ends = [i for i, d in enumerate(data) if 'clip_sgd_kernel' in d[1]]
+        ends = [e for j, e in enumerate(ends) if j % 2 == 1]      # second clip_sgd of each step
     lo, hi = ends[step_index - 1] + 1, ends[step_index] + 1
     step = data[lo:hi]
     total = sum(d[2] for d in step)

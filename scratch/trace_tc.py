@@ -17,7 +17,7 @@ def trace(label, fn, k_stages):
     lib.gs_debug_trace_read(buf.ctypes.data, 512)
     t0 = buf[0]
     rel = lambda i: int(buf[i] - t0)
-    print(f"== {label}: setup_done {rel(1)}  acc_ready {rel(2)}  epi_done {rel(3)}")
+    print(f"== {label}: setup_done {rel(1)}  acc_ready {rel(2)}  tmem2smem {rel(4)}  synced {rel(5)}  epi_done {rel(3)}")
     for ks in range(k_stages):
         print(f"   ks{ks}: loader_issued {rel(19+4*ks):7d}  landed {rel(16+4*ks):7d}  converted {rel(17+4*ks):7d}  mma_start {rel(18+4*ks):7d}")
 rng = np.random.default_rng(0)
@@ -30,6 +30,11 @@ def mk(rows, dim, out_dim):
     gout = torch.from_numpy(rng.standard_normal((rows, out_dim)).astype(np.float32)).to(dev)
     return table, agg, sidx, w, gout
 for prec in (2, 1):
+    table, agg, sidx, w, gout = mk(11264, 100, 128)
+    out = g.sage_gemm_fwd(table, sidx, agg, 100, w, 128, False, None, 11264, True, 0)
+    trace(f"fwd L1 prec={prec}", lambda: g.sage_gemm_fwd(table, sidx, agg, 100, w, 128, False, None, 11264, True, prec), 7)
+    gw = torch.zeros_like(w)
+    trace(f"bwd_w L1 prec={prec}", lambda: g.sage_gemm_bwd_w(table, sidx, agg, 100, gout, out, 128, False, False, None, 11264, gw, precision=prec), 5)
     table, agg, sidx, w, gout = mk(1024, 128, 128)
     out = g.sage_gemm_fwd(table, sidx, agg, 128, w, 128, False, None, 1024, True, 0)
     trace(f"fwd L2 prec={prec}", lambda: g.sage_gemm_fwd(table, sidx, agg, 128, w, 128, False, None, 1024, True, prec), 8)
