@@ -83,7 +83,8 @@ __device__ __forceinline__ int seg_of(const DpSegs& s, long long elem) {
 
 __global__ void __launch_bounds__(kDpThreads)
 dp_update_kernel(float* __restrict__ flat, long long n_total, const DpPeers peers_arg, const DpSegs segs_arg,
-                 DpState* __restrict__ st, float max_norm, float lr, unsigned long long timeout_ns) {
+                 DpState* __restrict__ st, float max_norm, float lr, unsigned long long timeout_ns,
+                 long long* __restrict__ step_counter) {
   // the tables are indexed dynamically: keep them in shared memory, not in a local-memory copy of the parameters
   __shared__ DpPeers peers;
   __shared__ DpSegs segs;
@@ -198,7 +199,10 @@ dp_update_kernel(float* __restrict__ flat, long long n_total, const DpPeers peer
     }
     flat4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  if (c == 0 && tid == 0) st->epoch = e;
+  if (c == 0 && tid == 0) {
+    st->epoch = e;
+    if (step_counter) *step_counter += 1;          // Philox offset of the next step's sampler (trainer.py)
+  }
 }
 
 }  // namespace gs
@@ -220,7 +224,8 @@ extern "C" size_t gs_dp_region_recv_offset(void) {
 extern "C" int gs_dp_allreduce_clip_sgd(float* flat_grad, int64_t n_total, void* const* peer_regions_host, int32_t rank,
                                         int32_t world, float* const* seg_params_host, const int64_t* seg_offsets_host,
                                         const int64_t* seg_numels_host, const int32_t* seg_groups_host, int32_t num_segs,
-                                        float max_norm, float lr, void* state, uint64_t timeout_ns, gs_stream_t stream) {
+                                        float max_norm, float lr, void* state, uint64_t timeout_ns,
+                                        int64_t* step_counter, gs_stream_t stream) {
   if (!flat_grad || !state || n_total < 4 || (n_total & 3) || !aligned16(flat_grad)) return GS_ERR_BAD_ARG;
   if (world < 1 || world > kDpMaxWorld || rank < 0 || rank >= world) return GS_ERR_BAD_ARG;
   if (num_segs < 1 || num_segs > kDpMaxSegs || !seg_params_host || !seg_offsets_host || !seg_numels_host) return GS_ERR_BAD_ARG;
@@ -255,7 +260,8 @@ extern "C" int gs_dp_allreduce_clip_sgd(float* flat_grad, int64_t n_total, void*
   if (grid < 1) grid = 1;
   dp_update_kernel<<<grid, kDpThreads, 0, as_stream(stream)>>>(flat_grad, n_total, peers, segs,
                                                               static_cast<DpState*>(state), max_norm, lr,
-                                                              timeout_ns ? timeout_ns : 2000000000ULL);
+                                                              timeout_ns ? timeout_ns : 2000000000ULL,
+                                                              reinterpret_cast<long long*>(step_counter));
   return finish_launch();
 }
 

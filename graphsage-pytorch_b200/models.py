@@ -368,10 +368,15 @@ class GraphSage(nn.Module):
         return layers[1:]
 
     def _run_backward(self, layers: List[_Frontier], grad_out: torch.Tensor, weights, needs,
-                      grad_bufs=None, own_grad: bool = False) -> List[Optional[torch.Tensor]]:
+                      grad_bufs=None, own_grad: bool = False, top_masked: bool = False,
+                      side_stream: Optional[torch.cuda.Stream] = None) -> List[Optional[torch.Tensor]]:
         """Weight gradients of all layers.  `grad_bufs` (optional, pre-zeroed) receive them in
         place (static buffers of the captured train step); otherwise fresh tensors are returned.
-        `own_grad`: grad_out is a scratch buffer of the caller and may be overwritten."""
+        `own_grad`: grad_out is a scratch buffer of the caller and may be overwritten.
+        `top_masked`: grad_out already carries the last layer's ReLU mask (gs_cls_nll_fwd_bwd).
+        `side_stream`: the weight-gradient GEMM of every layer but the first is a leaf of the
+        dependency graph (nothing downstream reads dW); with a side stream it runs beside the
+        dX -> scatter chain instead of in front of it (a fork/join when captured into a CUDA graph)."""
         L, H = self.num_layers, self.out_size
         mode = native.AGG_MEAN if self.agg_func == 'MEAN' else native.AGG_MAX
         prec = _PRECISIONS[self.precision]
@@ -382,18 +387,29 @@ class GraphSage(nn.Module):
         if premask and not own_grad and g.data_ptr() == grad_out.data_ptr():
             g = g.clone()                # never overwrite a gradient tensor autograd handed us
         grads: List[Optional[torch.Tensor]] = [None] * L
+        keep, forked = [], False         # tensors read on the side stream stay referenced until the join
         lowest = min((i for i in range(L) if needs[i]), default=None)
         if lowest is None:
             return grads
         for l in range(L, 0, -1):
             fr = layers[l - 1]
             w = weights[l - 1]
-            if premask:
+            if premask and not (top_masked and l == L):
                 ops.relu_bwd_inplace(g, fr.h, H, fr.num_rows, fr.rows_max)
             if needs[l - 1]:
                 gw = torch.zeros_like(w) if grad_bufs is None else grad_bufs[l - 1]
-                ops.sage_gemm_bwd_w(None if self.gcn else fr.table_in, fr.self_idx, fr.agg, fr.dim_in, g, fr.h, H,
-                                    self.gcn, not premask, fr.num_rows, fr.rows_max, gw, precision=prec)
+                fork = side_stream is not None and l - 1 > lowest and grad_bufs is not None
+                if fork:
+                    main = torch.cuda.current_stream()
+                    side_stream.wait_stream(main)
+                    keep.append(g)
+                    with torch.cuda.stream(side_stream):
+                        ops.sage_gemm_bwd_w(None if self.gcn else fr.table_in, fr.self_idx, fr.agg, fr.dim_in, g, fr.h, H,
+                                            self.gcn, not premask, fr.num_rows, fr.rows_max, gw, precision=prec)
+                    forked = True
+                else:
+                    ops.sage_gemm_bwd_w(None if self.gcn else fr.table_in, fr.self_idx, fr.agg, fr.dim_in, g, fr.h, H,
+                                        self.gcn, not premask, fr.num_rows, fr.rows_max, gw, precision=prec)
                 grads[l - 1] = gw
             if l - 1 <= lowest:          # nothing below needs a gradient (raw features never do)
                 break
@@ -404,6 +420,8 @@ class GraphSage(nn.Module):
             ops.agg_bwd(ga, gs, fr.dim_in, fr.nbr_idx, fr.stride, fr.cnt, fr.self_idx, fr.argmax, fr.num_rows,
                         fr.rows_max, mode, g_prev)
             g = g_prev
+        if forked:
+            torch.cuda.current_stream().wait_stream(side_stream)
         return grads
 
     # ---- compatibility methods of the reference (slow paths, host round trips) ------------------

@@ -127,11 +127,14 @@ class DpExchange:
             self.region = PeerRegion(nbytes, flat_grad.device, group=group, world=self.world, rank=self.rank)
             self._regions = (ctypes.c_void_p * self.world)(*self.region.ptrs)
 
-    def update(self, max_norm: float, lr: float):
-        """all-reduce(mean) -> clip per group -> SGD -> zero gradients; one launch on the current stream."""
+    def update(self, max_norm: float, lr: float, step_counter: Optional[torch.Tensor] = None):
+        """all-reduce(mean) -> clip per group -> SGD -> zero gradients (-> step_counter += 1); one launch
+        on the current stream."""
         check(self.lib.gs_dp_allreduce_clip_sgd(self.flat.data_ptr(), self.n_total, self._regions, self.rank, self.world,
                                                 self._p, self._o, self._n, self._g, self.num_segs, float(max_norm),
-                                                float(lr), self.state.data_ptr(), self.timeout_ns, native.stream()),
+                                                float(lr), self.state.data_ptr(), self.timeout_ns,
+                                                step_counter.data_ptr() if step_counter is not None else None,
+                                                native.stream()),
               "gs_dp_allreduce_clip_sgd")
 
     def status(self):

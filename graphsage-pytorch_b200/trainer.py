@@ -97,6 +97,7 @@ class SupervisedTrainer:
         self._graph_up: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_step = 0
         self.last_layers = None
+        self._side = torch.cuda.Stream(device=dev)      # dW GEMMs run beside the dX/scatter chain
 
     # ---- the step, expressed once; runs eagerly or under capture -------------------------------
     def _forward_backward(self):
@@ -110,13 +111,15 @@ class SupervisedTrainer:
         n_sage = len(self.weights)
         ops.cls_nll_fwd_bwd(emb, m.out_size, self.cls_w.detach(), self.cls_b.detach(), classes, self.labels, self.seeds,
                             self.loss, gemb, self.grads[n_sage], self.grads[n_sage + 1],
-                            precision=_PRECISIONS[m.precision])                                # utils.py:153,161-163
-        m._run_backward(layers, gemb, weights, [True] * n_sage, grad_bufs=self.grads[:n_sage], own_grad=True)
-        self.step_counter.add_(1)
+                            precision=_PRECISIONS[m.precision], mask_relu_input=True)          # utils.py:153,161-163
+        m._run_backward(layers, gemb, weights, [True] * n_sage, grad_bufs=self.grads[:n_sage], own_grad=True,
+                        top_masked=True, side_stream=self._side)
+        if self.dp is None:
+            self.step_counter.add_(1)        # the fused update kernel bumps it otherwise
 
     def _update(self):
         if self.dp is not None:
-            self.dp.update(self.max_norm, self.lr)                                                     # utils.py:184-191
+            self.dp.update(self.max_norm, self.lr, self.step_counter)                                  # utils.py:184-191
             return
         div = float(self.world_size)
         ops.clip_sgd(self.tl_sage, self.max_norm, self.lr, div, zero_grads=True)                       # utils.py:185-191

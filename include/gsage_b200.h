@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 7
+#define GS_ABI_VERSION 8
 
 #define GS_OK 0
 #define GS_ERR_BAD_ARG (-1)
@@ -182,14 +182,18 @@ int gs_nll_fwd_bwd(const float* logp, const int64_t* labels, const int32_t* labe
                    int32_t num_classes, float* loss, float* grad_logp, gs_stream_t stream);
 
 /* The supervised tail in one call (classifier forward, NLL mean of src/utils.py:153,162-163,
- * and their backward): logits GEMM -> fused bias + log_softmax + NLL + d logits + grad_b ->
- * grad_w GEMM -> grad_emb GEMM.  loss[0] is overwritten; grad_w / grad_b accumulate (zero
- * them first); grad_emb (nullable) is overwritten; scratch: rows*num_classes floats. */
+ * and their backward).  Heads with <= 64 classes and dim <= 256 (every configuration of the
+ * reference) run as ONE kernel; larger ones as logits GEMM -> fused bias + log_softmax + NLL +
+ * d logits + grad_b -> grad_w GEMM -> grad_emb GEMM.  loss[0] is overwritten; grad_w / grad_b
+ * accumulate (zero them first); grad_emb (nullable) is overwritten; scratch: rows*num_classes
+ * floats.  mask_relu_input != 0: emb is the ReLU output of the last SageLayer
+ * (src/models.py:219) and grad_emb is returned already multiplied by (emb > 0). */
 int gs_cls_nll_fwd_bwd(const float* emb, int64_t ld_emb, int32_t rows, int32_t dim,
                        const float* weight, const float* bias, int32_t num_classes,
                        const int64_t* labels, const int32_t* label_index,
                        float* logp, float* loss, float* grad_emb, int64_t ld_ge,
-                       float* grad_w, float* grad_b, float* scratch, int32_t precision, gs_stream_t stream);
+                       float* grad_w, float* grad_b, float* scratch, int32_t mask_relu_input, int32_t precision,
+                       gs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Update step of src/utils.py:185-187: per-model clip_grad_norm_(max_norm) then SGD.
@@ -218,6 +222,8 @@ int gs_clip_sgd(float* const* params, float* const* grads, const int64_t* numels
  *                  n_total); carries the epoch between calls
  *   timeout_ns     a peer that does not arrive within this time sets status != 0 (see
  *                  gs_dp_status) instead of hanging the GPU; 0 => 2 s
+ *   step_counter   nullable device int64, incremented by one (the sampler's Philox offset_dev,
+ *                  so a captured step draws fresh neighbours on every replay)
  * ------------------------------------------------------------------------------------ */
 size_t gs_dp_state_bytes(void);
 size_t gs_dp_region_bytes(int64_t n_total, int32_t world);
@@ -225,7 +231,8 @@ size_t gs_dp_region_recv_offset(void);
 int gs_dp_allreduce_clip_sgd(float* flat_grad, int64_t n_total, void* const* peer_regions_host, int32_t rank,
                              int32_t world, float* const* seg_params_host, const int64_t* seg_offsets_host,
                              const int64_t* seg_numels_host, const int32_t* seg_groups_host, int32_t num_segs,
-                             float max_norm, float lr, void* state, uint64_t timeout_ns, gs_stream_t stream);
+                             float max_norm, float lr, void* state, uint64_t timeout_ns, int64_t* step_counter,
+                             gs_stream_t stream);
 /* synchronises `stream`, then reports the epoch counter, the status word (0 ok, 1 peer
  * wait timed out, 2 grid barrier timed out) and the last step's 4 per-group gradient norms */
 int gs_dp_status(const void* state, uint32_t* epoch_host, uint32_t* status_host, float* norms_host, gs_stream_t stream);

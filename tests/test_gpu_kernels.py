@@ -394,3 +394,39 @@ def test_clip_sgd_matches_torch(g, dev):
         for a, b in zip(pd, ref):
             assert rel(a, b) <= 1e-6
         assert all(float(x.abs().max()) == 0.0 for x in gd)
+
+
+# ------------------------------------------------------------------------------------------------
+# supervised tail in one launch (classifier + log_softmax + NLL + backward), src/models.py:25-27, src/utils.py:153,162-163
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('rows,dim,classes,mask', [(1024, 128, 47, True), (1000, 128, 7, False), (37, 64, 3, True),
+                                                    (513, 256, 64, False), (200, 128, 41, True), (64, 128, 100, True)])
+def test_cls_nll_fwd_bwd_matches_torch(g, dev, rows, dim, classes, mask):
+    from graphsage_b200 import native
+    rng = np.random.default_rng(rows + classes)
+    emb = np.maximum(rng.standard_normal((rows, dim)), 0).astype(np.float32)       # a ReLU output, as in the model
+    w = rng.uniform(-0.3, 0.3, (classes, dim)).astype(np.float32)
+    b = rng.uniform(-0.1, 0.1, (classes,)).astype(np.float32)
+    n_nodes = 5000
+    labels = rng.integers(0, classes, n_nodes).astype(np.int64)
+    idx = rng.integers(0, n_nodes, rows).astype(np.int32)
+    te = torch.from_numpy(emb).requires_grad_(True)
+    tw = torch.from_numpy(w).requires_grad_(True)
+    tb = torch.from_numpy(b).requires_grad_(True)
+    logp = torch.log_softmax(te @ tw.t() + tb, dim=1)
+    y = torch.from_numpy(labels[idx])
+    loss = -torch.sum(logp[range(rows), y], 0) / rows                              # src/utils.py:162-163
+    loss.backward()
+    want_ge = te.grad * (te.detach() > 0) if mask else te.grad
+    d = lambda a: torch.from_numpy(a).to(dev)
+    e_d, w_d, b_d = d(emb), d(w), d(b)
+    loss_d = torch.full((1,), 7.0, device=dev)
+    ge = torch.full((rows, dim), 9.0, device=dev)
+    gw, gb = torch.zeros((classes, dim), device=dev), torch.zeros((classes,), device=dev)
+    lp = g.cls_nll_fwd_bwd(e_d, dim, w_d, b_d, classes, d(labels), d(idx), loss_d, ge, gw, gb,
+                           precision=native.PREC_FP32, mask_relu_input=mask)
+    assert rel(lp, logp) <= TOL
+    assert abs(float(loss_d.item()) - float(loss)) <= TOL * abs(float(loss))
+    assert rel(ge, want_ge) <= TOL
+    assert rel(gw, tw.grad) <= TOL
+    assert rel(gb, tb.grad) <= TOL
