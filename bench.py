@@ -407,8 +407,19 @@ def measure_agg_roofline(torch, ops, native, model, trainer, dev_batches, W, K, 
     except Exception as exc:      # the headline roofline above does not depend on this extra point
         big = {"error": repr(exc)[:200]}
     achieved = float(np.mean(bytes_) / np.mean(times) / 1e9)
-    return {"bound": "hbm", "kernel": "agg_fwd_pipe_kernel<MEAN> (layer 1, gs_agg_fwd)", "achieved": achieved, "peak": peak,
-            "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full` capture
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "agg_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            t = json.load(open(tpath))
+            traffic, traffic_src = float(t["dram_bytes_per_launch"]), t.get("source")
+        except Exception:
+            pass
+    kname = "agg_fwd_pipe_kernel<MEAN>" if os.environ.get("GS_AGG_IMPL", "").startswith("p") else "agg_fwd_kernel<MEAN>"
+    return {"bound": "hbm", "kernel": f"{kname} (layer 1, gs_agg_fwd)", "achieved": achieved, "peak": peak,
+            "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+            "peak_source": peak_src,
             "bytes_per_launch": float(np.mean(bytes_)), "us_per_launch": float(np.mean(times) * 1e6),
             "saturating_size": big, "launches_timed": n_iter, "us_per_launch_single_event_pair": float(np.mean(singles) * 1e6),
             "note": "achieved = algorithmic bytes / (CUDA-event time of n back-to-back launches on distinct frontiers / n)"}
@@ -422,9 +433,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--b_sz", type=int, default=1024)
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the graph for debugging (1.0 = the named config)")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "tf32x3"],
-                    help="K4 GEMM mode: fp32 = FFMA; tf32x3 = tcgen05 3-term tf32 split (fp32-faithful, 1e-5 parity); "
-                         "tf32 = single tf32 product (2e-3)")
+    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32", "tf32x3"],
+                    help="K4 GEMM mode: tf32x3 = tcgen05 3-term tf32 split (fp32-faithful, 1e-5 parity; default); "
+                         "fp32 = FFMA; tf32 = single tf32 product (2e-3, reduced precision: not a headline number)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="gradient exchange + update: peer = one fused kernel over NVLink peer memory (default); "
                          "nccl = library all-reduce followed by the separate norm/update kernels (comparison)")

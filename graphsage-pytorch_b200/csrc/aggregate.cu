@@ -28,6 +28,7 @@ agg_fwd_kernel(const float* __restrict__ table, uint32_t ld_bytes, int dim4,
                const int32_t* __restrict__ nbr, int stride, const int32_t* __restrict__ cnt,
                const int32_t* __restrict__ num_rows_dev, int max_rows,
                float* __restrict__ out, int64_t ld_out, int32_t* __restrict__ argmax, int64_t ld_arg) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * kAggWarps + (threadIdx.x >> 5);
   if (r >= max_rows) return;
@@ -95,6 +96,7 @@ agg_bwd_kernel(const float* __restrict__ grad_agg, int64_t ld_ga, const float* _
                int dim4, const int32_t* __restrict__ nbr, int stride, const int32_t* __restrict__ cnt,
                const int32_t* __restrict__ self_idx, const int32_t* __restrict__ argmax, int64_t ld_arg,
                const int32_t* __restrict__ num_rows_dev, int max_rows, float* __restrict__ grad_table, int64_t ld_gt) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * kAggWarps + (threadIdx.x >> 5);
   if (r >= live_rows(num_rows_dev, max_rows)) return;
@@ -179,6 +181,7 @@ agg_fwd_pipe_kernel(const float* __restrict__ table, int64_t ld, int dim4, const
                     const int32_t* __restrict__ cnt, const int32_t* __restrict__ num_rows_dev, int max_rows,
                     float* __restrict__ out, int64_t ld_out, int32_t* __restrict__ argmax, int64_t ld_arg,
                     int slot_bytes) {
+  pdl_sync();
   extern __shared__ __align__(128) unsigned char pipe_smem[];
   __shared__ int32_t s_ids[kPipeWarps][STAGES][kPipeMaxStride];
   __shared__ int32_t s_n[kPipeWarps][STAGES];
@@ -304,7 +307,7 @@ static int launch_pipe(const float* table, int64_t ld, int dim4, const int32_t* 
   if (e != cudaSuccess) return static_cast<int>(e);
   int grid = (max_rows + kPipeWarps - 1) / kPipeWarps;
   if (grid > kNumSMs) grid = kNumSMs;
-  agg_fwd_pipe_kernel<MODE, STAGES><<<grid, kPipeWarps * 32, smem, st>>>(table, ld, dim4, nbr, stride, cnt, num_rows_dev,
+  launch(agg_fwd_pipe_kernel<MODE, STAGES>, grid, kPipeWarps * 32, smem, st, table, ld, dim4, nbr, stride, cnt, num_rows_dev,
                                                                         max_rows, out, ld_out, argmax, ld_arg, slot_bytes);
   return finish_launch();
 }
@@ -350,6 +353,7 @@ agg_fwd_bf16_sharded_kernel(const ShardTable tab_arg, int64_t ld, int dim8, cons
                             const int32_t* __restrict__ cnt, const int32_t* __restrict__ self_nodes,
                             const int32_t* __restrict__ num_rows_dev, int max_rows, float* __restrict__ out_agg,
                             int64_t ld_agg, float* __restrict__ out_self, int64_t ld_self) {
+  pdl_sync();
   __shared__ const uint16_t* s_base[kMaxShards];
   if (threadIdx.x < kMaxShards) s_base[threadIdx.x] = threadIdx.x < tab_arg.num_shards ? tab_arg.base[threadIdx.x] : nullptr;
   __syncthreads();
@@ -446,10 +450,10 @@ extern "C" int gs_agg_fwd(const float* table, int64_t ld, int32_t dim, const int
   const int blocks = (max_rows + kAggWarps - 1) / kAggWarps;
   const uint32_t ld_bytes = static_cast<uint32_t>(ld * 4);
   if (mode == GS_AGG_MEAN)
-    agg_fwd_kernel<GS_AGG_MEAN><<<blocks, kAggWarps * 32, 0, st>>>(
+    launch(agg_fwd_kernel<GS_AGG_MEAN>, blocks, kAggWarps * 32, 0, st, 
         table, ld_bytes, dim4, nbr, stride, cnt, num_rows_dev, max_rows, out, ld_out, nullptr, 0);
   else
-    agg_fwd_kernel<GS_AGG_MAX><<<blocks, kAggWarps * 32, 0, st>>>(
+    launch(agg_fwd_kernel<GS_AGG_MAX>, blocks, kAggWarps * 32, 0, st, 
         table, ld_bytes, dim4, nbr, stride, cnt, num_rows_dev, max_rows, out, ld_out, argmax, ld_arg);
   return finish_launch();
 }
@@ -472,11 +476,11 @@ extern "C" int gs_agg_bwd(const float* grad_agg, int64_t ld_ga, const float* gra
   // a dummy index list keeps the kernel's pointer arithmetic valid when only grad_self is scattered
   const int blocks = (max_rows + kAggWarps - 1) / kAggWarps;
   if (mode == GS_AGG_MEAN)
-    agg_bwd_kernel<GS_AGG_MEAN><<<blocks, kAggWarps * 32, 0, as_stream(stream)>>>(
+    launch(agg_bwd_kernel<GS_AGG_MEAN>, blocks, kAggWarps * 32, 0, as_stream(stream), 
         grad_agg, ld_ga, grad_self, ld_gs, dim4, nbr, stride, cnt, self_idx, argmax, ld_arg, num_rows_dev, max_rows,
         grad_table, ld_gt);
   else
-    agg_bwd_kernel<GS_AGG_MAX><<<blocks, kAggWarps * 32, 0, as_stream(stream)>>>(
+    launch(agg_bwd_kernel<GS_AGG_MAX>, blocks, kAggWarps * 32, 0, as_stream(stream), 
         grad_agg, ld_ga, grad_self, ld_gs, dim4, nbr, stride, cnt, self_idx, argmax, ld_arg, num_rows_dev, max_rows,
         grad_table, ld_gt);
   return finish_launch();
@@ -505,10 +509,10 @@ extern "C" int gs_agg_fwd_bf16_sharded(const void* const* shard_bases_host, int3
   if (max_rows == 0) return GS_OK;
   const int blocks = (max_rows + kAggWarps - 1) / kAggWarps;
   if (dim8 <= 16)
-    agg_fwd_bf16_sharded_kernel<16><<<blocks, kAggWarps * 32, 0, as_stream(stream)>>>(
+    launch(agg_fwd_bf16_sharded_kernel<16>, blocks, kAggWarps * 32, 0, as_stream(stream), 
         tab, ld, dim8, nbr, stride, cnt, self_nodes, num_rows_dev, max_rows, out_agg, ld_agg, out_self, ld_self);
   else
-    agg_fwd_bf16_sharded_kernel<32><<<blocks, kAggWarps * 32, 0, as_stream(stream)>>>(
+    launch(agg_fwd_bf16_sharded_kernel<32>, blocks, kAggWarps * 32, 0, as_stream(stream), 
         tab, ld, dim8, nbr, stride, cnt, self_nodes, num_rows_dev, max_rows, out_agg, ld_agg, out_self, ld_self);
   return finish_launch();
 }

@@ -1,8 +1,18 @@
 // Library-level entry points: version, error strings, launch counter.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace gs {
 int64_t g_launches = 0;
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("GS_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
 }
 
 extern "C" int gs_version(void) { return GS_ABI_VERSION; }

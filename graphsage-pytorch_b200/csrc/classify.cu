@@ -12,6 +12,7 @@ constexpr int kRowWarps = 8;
 
 __global__ void __launch_bounds__(kRowWarps * 32)
 bias_logsoftmax_kernel(float* __restrict__ logp, const float* __restrict__ bias, int rows, int classes, int64_t ld) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * kRowWarps + (threadIdx.x >> 5);
   if (r >= rows) return;
@@ -34,6 +35,7 @@ bias_logsoftmax_kernel(float* __restrict__ logp, const float* __restrict__ bias,
 __global__ void __launch_bounds__(kRowWarps * 32)
 logsoftmax_bwd_kernel(const float* __restrict__ grad_logp, const float* __restrict__ logp, int rows, int classes,
                       int64_t ld, float* __restrict__ grad_logits, int64_t ld_gl, float* __restrict__ grad_b) {
+  pdl_sync();
   extern __shared__ float s_db[];
   for (int c = threadIdx.x; c < classes; c += blockDim.x) s_db[c] = 0.f;
   __syncthreads();
@@ -59,6 +61,7 @@ logsoftmax_bwd_kernel(const float* __restrict__ grad_logp, const float* __restri
 __global__ void __launch_bounds__(256)
 nll_kernel(const float* __restrict__ logp, const int64_t* __restrict__ labels, const int32_t* __restrict__ label_index,
            int rows, int classes, float* __restrict__ loss, float* __restrict__ grad_logp) {
+  pdl_sync();
   const float inv = 1.0f / static_cast<float>(rows);
   float part = 0.f;
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
@@ -79,6 +82,7 @@ __global__ void __launch_bounds__(kRowWarps * 32)
 softmax_nll_kernel(float* __restrict__ logp, const float* __restrict__ bias, const int64_t* __restrict__ labels,
                    const int32_t* __restrict__ label_index, int rows, int classes, float* __restrict__ loss,
                    float* __restrict__ dlogits, float* __restrict__ grad_b) {
+  pdl_sync();
   extern __shared__ float s_db[];            // [classes] + 1 (loss partial)
   for (int c = threadIdx.x; c <= classes; c += blockDim.x) s_db[c] = 0.f;
   __syncthreads();
@@ -134,6 +138,7 @@ cls_fused_kernel(const float* __restrict__ emb, int64_t ld_emb, int rows, int di
                  const int32_t* __restrict__ label_index, float* __restrict__ logp, float* __restrict__ loss,
                  float* __restrict__ grad_emb, int64_t ld_ge, float* __restrict__ grad_w, float* __restrict__ grad_b,
                  int mask_relu) {
+  pdl_sync();
   extern __shared__ __align__(16) float cls_smem[];
   const int cp = kClsMaxC + 1;                               // W^T row stride: lanes read consecutive classes
   float* w_s = cls_smem;                                     // [classes][dim]
@@ -268,7 +273,7 @@ extern "C" int gs_cls_nll_fwd_bwd(const float* emb, int64_t ld_emb, int32_t rows
     const size_t smem = cls_fused_smem(dim, num_classes);
     ce = cudaFuncSetAttribute(cls_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (ce != cudaSuccess) return static_cast<int>(ce);
-    cls_fused_kernel<<<(rows + kClsRows - 1) / kClsRows, kClsRows * 32, smem, st>>>(
+    launch(cls_fused_kernel, (rows + kClsRows - 1) / kClsRows, kClsRows * 32, smem, st, 
         emb, ld_emb, rows, dim, weight, bias, num_classes, labels, label_index, logp, loss, grad_emb, ld_ge, grad_w,
         grad_b, mask_relu_input);
     return finish_launch();
@@ -276,7 +281,7 @@ extern "C" int gs_cls_nll_fwd_bwd(const float* emb, int64_t ld_emb, int32_t rows
   int e = gs_sage_gemm_fwd(nullptr, 0, nullptr, emb, ld_emb, dim, weight, dim, num_classes, /*gcn=*/1, nullptr, rows,
                            logp, num_classes, /*relu=*/0, precision, stream);
   if (e) return e;
-  softmax_nll_kernel<<<(rows + kRowWarps - 1) / kRowWarps, kRowWarps * 32, (num_classes + 1) * sizeof(float), st>>>(
+  launch(softmax_nll_kernel, (rows + kRowWarps - 1) / kRowWarps, kRowWarps * 32, (num_classes + 1) * sizeof(float), st, 
       logp, bias, labels, label_index, rows, num_classes, loss, scratch, grad_b);
   e = finish_launch();
   if (e) return e;
@@ -305,7 +310,7 @@ extern "C" int gs_cls_fwd(const float* emb, int64_t ld_emb, int32_t rows, int32_
   int e = gs_sage_gemm_fwd(nullptr, 0, nullptr, emb, ld_emb, dim, weight, dim, num_classes, /*gcn=*/1, nullptr, rows,
                            logp, num_classes, /*relu=*/0, precision, stream);
   if (e) return e;
-  bias_logsoftmax_kernel<<<(rows + kRowWarps - 1) / kRowWarps, kRowWarps * 32, 0, as_stream(stream)>>>(
+  launch(bias_logsoftmax_kernel, (rows + kRowWarps - 1) / kRowWarps, kRowWarps * 32, 0, as_stream(stream), 
       logp, bias, rows, num_classes, num_classes);
   return finish_launch();
 }
@@ -316,8 +321,8 @@ extern "C" int gs_cls_bwd(const float* grad_logp, const float* logp, const float
                           int32_t precision, gs_stream_t stream) {
   if (!grad_logp || !logp || !emb || !weight || !scratch || rows < 0 || dim < 1 || num_classes < 1) return GS_ERR_BAD_ARG;
   if (rows == 0) return GS_OK;
-  logsoftmax_bwd_kernel<<<(rows + kRowWarps - 1) / kRowWarps, kRowWarps * 32, num_classes * sizeof(float),
-                          as_stream(stream)>>>(grad_logp, logp, rows, num_classes, num_classes, scratch, num_classes,
+  launch(logsoftmax_bwd_kernel, (rows + kRowWarps - 1) / kRowWarps, kRowWarps * 32, num_classes * sizeof(float),
+                          as_stream(stream), grad_logp, logp, rows, num_classes, num_classes, scratch, num_classes,
                                                grad_b);
   int e = finish_launch();
   if (e) return e;
@@ -340,6 +345,6 @@ extern "C" int gs_nll_fwd_bwd(const float* logp, const int64_t* labels, const in
   cudaError_t ce = cudaMemsetAsync(loss, 0, sizeof(float), as_stream(stream));
   if (ce != cudaSuccess) return static_cast<int>(ce);
   const int blocks = std::min((rows + 255) / 256, kNumSMs);
-  nll_kernel<<<blocks, 256, 0, as_stream(stream)>>>(logp, labels, label_index, rows, num_classes, loss, grad_logp);
+  launch(nll_kernel, blocks, 256, 0, as_stream(stream), logp, labels, label_index, rows, num_classes, loss, grad_logp);
   return finish_launch();
 }

@@ -20,6 +20,33 @@ inline int finish_launch(int n = 1) {
 
 inline cudaStream_t as_stream(gs_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Programmatic dependent launch.  A step is ~20 short kernels in a dependency chain, so the
+// launch latency + CTA ramp-up between two kernels is comparable to the kernels themselves.
+// Every kernel starts with pdl_sync(): it lets the NEXT kernel of the stream be scheduled as
+// soon as all CTAs of this one are resident (launch_dependents) and then waits until the
+// PREVIOUS kernel has completed and flushed its writes (wait) before touching global memory.
+// Both are no-ops for a launch without the attribute.  GS_PDL=0 disables the attribute.
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);     // errors surface through finish_launch()
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 __device__ __forceinline__ int live_rows(const int32_t* num_rows_dev, int max_rows) {

@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(kDpThreads)
 dp_update_kernel(float* __restrict__ flat, long long n_total, const DpPeers peers_arg, const DpSegs segs_arg,
                  DpState* __restrict__ st, float max_norm, float lr, unsigned long long timeout_ns,
                  long long* __restrict__ step_counter) {
+  pdl_sync();
   // the tables are indexed dynamically: keep them in shared memory, not in a local-memory copy of the parameters
   __shared__ DpPeers peers;
   __shared__ DpSegs segs;
@@ -258,7 +259,7 @@ extern "C" int gs_dp_allreduce_clip_sgd(float* flat_grad, int64_t n_total, void*
   int grid = static_cast<int>((n4 + 4 * kDpThreads - 1) / (4 * kDpThreads));
   if (grid > kDpMaxCtas) grid = kDpMaxCtas;
   if (grid < 1) grid = 1;
-  dp_update_kernel<<<grid, kDpThreads, 0, as_stream(stream)>>>(flat_grad, n_total, peers, segs,
+  launch(dp_update_kernel, grid, kDpThreads, 0, as_stream(stream), flat_grad, n_total, peers, segs,
                                                               static_cast<DpState*>(state), max_norm, lr,
                                                               timeout_ns ? timeout_ns : 2000000000ULL,
                                                               reinterpret_cast<long long*>(step_counter));

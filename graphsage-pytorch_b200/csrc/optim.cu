@@ -9,6 +9,7 @@ namespace gs {
 __global__ void __launch_bounds__(256)
 grad_sqnorm_kernel(float* const* __restrict__ grads, const int64_t* __restrict__ numels, float grad_div,
                    float* __restrict__ sqnorm) {
+  pdl_sync();
   const float* g = grads[blockIdx.y];
   const int64_t n = numels[blockIdx.y];
   const float inv = 1.0f / grad_div;
@@ -33,6 +34,7 @@ __global__ void __launch_bounds__(256)
 clip_sgd_kernel(float* const* __restrict__ params, float* const* __restrict__ grads,
                 const int64_t* __restrict__ numels, float max_norm, float lr, float grad_div,
                 const float* __restrict__ sqnorm, int zero_grads) {
+  pdl_sync();
   float* p = params[blockIdx.y];
   float* g = grads[blockIdx.y];
   const int64_t n = numels[blockIdx.y];
@@ -67,10 +69,10 @@ extern "C" int gs_clip_sgd(float* const* params, float* const* grads, const int6
   if (max_norm > 0.f) {
     cudaError_t ce = cudaMemsetAsync(norm_scratch, 0, sizeof(float), st);
     if (ce != cudaSuccess) return static_cast<int>(ce);
-    grad_sqnorm_kernel<<<grid, 256, 0, st>>>(grads, numels, grad_div, norm_scratch);
+    launch(grad_sqnorm_kernel, grid, 256, 0, st, grads, numels, grad_div, norm_scratch);
     ++launches;
   }
-  clip_sgd_kernel<<<grid, 256, 0, st>>>(params, grads, numels, max_norm, lr, grad_div, norm_scratch, zero_grads);
+  launch(clip_sgd_kernel, grid, 256, 0, st, params, grads, numels, max_norm, lr, grad_div, norm_scratch, zero_grads);
   ++launches;
   return finish_launch(launches);
 }

@@ -52,6 +52,7 @@ pair_loss_fwd_kernel(const float* __restrict__ emb, int64_t ld, int dim4, const 
                      const int32_t* __restrict__ neg_ptr, const int32_t* __restrict__ neg_idx, int mode, float q,
                      float margin, float* __restrict__ loss_sum, float* __restrict__ coef_pos,
                      float* __restrict__ coef_neg, int32_t* __restrict__ num_active) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int s = blockIdx.x * kPairWarps + (threadIdx.x >> 5);
   if (s >= num_seeds) return;
@@ -128,6 +129,7 @@ pair_loss_fwd_kernel(const float* __restrict__ emb, int64_t ld, int dim4, const 
 
 __global__ void pair_loss_finalize_kernel(float* __restrict__ loss, const float* __restrict__ loss_sum,
                                           const int32_t* __restrict__ num_active) {
+  pdl_sync();
   loss[0] = loss_sum[0] / static_cast<float>(num_active[0]);   // 0/0 = NaN when every seed was skipped (reference raises)
 }
 
@@ -139,6 +141,7 @@ pair_loss_bwd_kernel(const float* __restrict__ emb, int64_t ld, int dim4, const 
                      const float* __restrict__ coef_pos, const float* __restrict__ coef_neg,
                      const int32_t* __restrict__ num_active, const float* __restrict__ grad_loss,
                      float* __restrict__ grad_emb, int64_t ld_ge) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int s = blockIdx.x * kPairWarps + (threadIdx.x >> 5);
   if (s >= num_seeds) return;
@@ -225,12 +228,12 @@ extern "C" int gs_pair_loss_fwd(const float* emb, int64_t ld, int32_t dim, const
   if (ce != cudaSuccess) return static_cast<int>(ce);
   const int blocks = (num_seeds + kPairWarps - 1) / kPairWarps;
 #define CALL(S)                                                                                                    \
-  pair_loss_fwd_kernel<S><<<blocks, kPairWarps * 32, 0, st>>>(emb, ld, dim4, seed_idx, num_seeds, pos_ptr, pos_idx, \
+  launch(pair_loss_fwd_kernel<S>, blocks, kPairWarps * 32, 0, st, emb, ld, dim4, seed_idx, num_seeds, pos_ptr, pos_idx, \
                                                               neg_ptr, neg_idx, mode, q, margin, loss_sum_scratch, \
                                                               coef_pos, coef_neg, num_active)
   GS_DISPATCH_SLABS(dim4, CALL);
 #undef CALL
-  pair_loss_finalize_kernel<<<1, 1, 0, st>>>(loss, loss_sum_scratch, num_active);
+  launch(pair_loss_finalize_kernel, 1, 1, 0, st, loss, loss_sum_scratch, num_active);
   return finish_launch(2);
 }
 
@@ -249,7 +252,7 @@ extern "C" int gs_pair_loss_bwd(const float* emb, int64_t ld, int32_t dim, const
   cudaStream_t st = as_stream(stream);
   const int blocks = (num_seeds + kPairWarps - 1) / kPairWarps;
 #define CALL(S)                                                                                                    \
-  pair_loss_bwd_kernel<S><<<blocks, kPairWarps * 32, 0, st>>>(emb, ld, dim4, seed_idx, num_seeds, pos_ptr, pos_idx, \
+  launch(pair_loss_bwd_kernel<S>, blocks, kPairWarps * 32, 0, st, emb, ld, dim4, seed_idx, num_seeds, pos_ptr, pos_idx, \
                                                               neg_ptr, neg_idx, coef_pos, coef_neg, num_active,    \
                                                               grad_loss, grad_emb, ld_ge)
   GS_DISPATCH_SLABS(dim4, CALL);

@@ -54,6 +54,7 @@ __device__ __forceinline__ void fma_tile(float (&acc)[4][4], const float* __rest
 __global__ void __launch_bounds__(kGemmThreads)
 sage_fwd_kernel(XOperand x, const float* __restrict__ weight, int64_t ldw, int out_dim,
                 const int32_t* __restrict__ num_rows_dev, int max_rows, float* __restrict__ out, int64_t ld_out, int relu) {
+  pdl_sync();
   __shared__ __align__(16) float Xs[BK][BM + kPad];
   __shared__ __align__(16) float Ws[BK][BN + kPad];
   const int rows = live_rows(num_rows_dev, max_rows);
@@ -112,6 +113,7 @@ sage_bwd_x_kernel(const float* __restrict__ grad_out, int64_t ld_go, const float
                   const float* __restrict__ weight, int64_t ldw, int dim, int out_dim, int gcn, int relu,
                   const int32_t* __restrict__ num_rows_dev, int max_rows,
                   float* __restrict__ grad_self, int64_t ld_gs, float* __restrict__ grad_agg, int64_t ld_ga) {
+  pdl_sync();
   __shared__ __align__(16) float As[BK][BM + kPad];   // dZ^T tile: [h][row]
   __shared__ __align__(16) float Bs[BK][BN + kPad];   // W tile:    [h][col]
   const int rows = live_rows(num_rows_dev, max_rows);
@@ -176,6 +178,7 @@ __global__ void __launch_bounds__(kGemmThreads)
 sage_bwd_w_kernel(XOperand x, const float* __restrict__ grad_out, int64_t ld_go, const float* __restrict__ out,
                   int64_t ld_out, int out_dim, int relu, const int32_t* __restrict__ num_rows_dev, int max_rows,
                   int rows_per_chunk, float* __restrict__ grad_w, int64_t ldw) {
+  pdl_sync();
   __shared__ __align__(16) float As[BK][BM + kPad];   // dZ tile: [row][h]
   __shared__ __align__(16) float Bs[BK][BN + kPad];   // X tile : [row][kv]
   const int rows = live_rows(num_rows_dev, max_rows);
@@ -276,7 +279,7 @@ extern "C" int gs_sage_gemm_fwd(const float* self_table, int64_t ld_self, const 
                                num_rows_dev, max_rows, out, ld_out, relu, precision, stream);
   XOperand x{self_table, ld_self, self_idx, agg, ld_agg, dim, (dim + 3) & ~3, gcn};
   dim3 grid((max_rows + BM - 1) / BM, (out_dim + BN - 1) / BN);
-  sage_fwd_kernel<<<grid, kGemmThreads, 0, as_stream(stream)>>>(x, weight, ldw, out_dim, num_rows_dev, max_rows, out,
+  launch(sage_fwd_kernel, grid, kGemmThreads, 0, as_stream(stream), x, weight, ldw, out_dim, num_rows_dev, max_rows, out,
                                                                 ld_out, relu);
   return finish_launch();
 }
@@ -296,7 +299,7 @@ extern "C" int gs_sage_gemm_bwd_x(const float* grad_out, int64_t ld_go, const fl
                                  max_rows, grad_self, ld_gs, grad_agg, ld_ga, precision, stream);
   const int ncols = gcn ? dim : 2 * dim;
   dim3 grid((max_rows + BM - 1) / BM, (ncols + BN - 1) / BN);
-  sage_bwd_x_kernel<<<grid, kGemmThreads, 0, as_stream(stream)>>>(grad_out, ld_go, out, ld_out, weight, ldw, dim,
+  launch(sage_bwd_x_kernel, grid, kGemmThreads, 0, as_stream(stream), grad_out, ld_go, out, ld_out, weight, ldw, dim,
                                                                   out_dim, gcn, relu, num_rows_dev, max_rows,
                                                                   grad_self, ld_gs, grad_agg, ld_ga);
   return finish_launch();
@@ -328,7 +331,7 @@ extern "C" int gs_sage_gemm_bwd_w(const float* self_table, int64_t ld_self, cons
   rows_per_chunk = ((rows_per_chunk + BK - 1) / BK) * BK;
   chunks = (max_rows + rows_per_chunk - 1) / rows_per_chunk;
   dim3 grid((kt + BN - 1) / BN, (out_dim + BM - 1) / BM, chunks);
-  sage_bwd_w_kernel<<<grid, kGemmThreads, 0, as_stream(stream)>>>(x, grad_out, ld_go, out, ld_out, out_dim, relu,
+  launch(sage_bwd_w_kernel, grid, kGemmThreads, 0, as_stream(stream), x, grad_out, ld_go, out, ld_out, out_dim, relu,
                                                                   num_rows_dev, max_rows, rows_per_chunk, grad_w, ldw);
   return finish_launch();
 }
@@ -342,6 +345,7 @@ namespace gs {
 __global__ void __launch_bounds__(256)
 relu_bwd_kernel(float* __restrict__ grad, int64_t ld_g, const float* __restrict__ out, int64_t ld_out, int dim4,
                 const int32_t* __restrict__ num_rows_dev, int max_rows) {
+  pdl_sync();
   const int rows = live_rows(num_rows_dev, max_rows);
   const int64_t total = static_cast<int64_t>(rows) * dim4;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -369,6 +373,6 @@ extern "C" int gs_relu_bwd_inplace(float* grad, int64_t ld_g, const float* out, 
   const int64_t total = static_cast<int64_t>(max_rows) * dim4;
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
-  relu_bwd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(grad, ld_g, out, ld_out, dim4, num_rows_dev, max_rows);
+  launch(relu_bwd_kernel, blocks, 256, 0, as_stream(stream), grad, ld_g, out, ld_out, dim4, num_rows_dev, max_rows);
   return finish_launch();
 }

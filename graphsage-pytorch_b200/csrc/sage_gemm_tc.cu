@@ -753,6 +753,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 sage_fwd_tc_kernel(XView x, const float* __restrict__ weight, int64_t ldw, int out_dim, bool vec_ok,
                    const int32_t* __restrict__ num_rows_dev, int max_rows, float* __restrict__ out, int64_t ld_out,
                    int relu, int n_tile, int k_stages, int num_stages) {
+  pdl_sync();
   extern __shared__ unsigned char smem_dyn[];
   const int rows = live_rows(num_rows_dev, max_rows);
   const int row0 = blockIdx.x * kTileM, h0 = blockIdx.y * n_tile;
@@ -772,6 +773,7 @@ sage_bwd_x_tc_kernel(const float* __restrict__ grad_out, int64_t ld_go, const fl
                      const float* __restrict__ weight, int64_t ldw, int dim, int out_dim, int gcn, int relu, bool vec_ok,
                      const int32_t* __restrict__ num_rows_dev, int max_rows, float* __restrict__ grad_self, int64_t ld_gs,
                      float* __restrict__ grad_agg, int64_t ld_ga, int n_tile, int k_stages, int num_stages) {
+  pdl_sync();
   extern __shared__ unsigned char smem_dyn[];
   const int rows = live_rows(num_rows_dev, max_rows);
   const int row0 = blockIdx.x * kTileM, c0 = blockIdx.y * n_tile;
@@ -789,6 +791,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 sage_bwd_w_tc_kernel(XView x, const float* __restrict__ grad_out, int64_t ld_go, const float* __restrict__ out,
                      int64_t ld_out, int out_dim, int relu, const int32_t* __restrict__ num_rows_dev, int max_rows,
                      int rows_per_chunk, float* __restrict__ grad_w, int64_t ldw, int n_tile, int num_stages) {
+  pdl_sync();
   extern __shared__ unsigned char smem_dyn[];
   const int rows = live_rows(num_rows_dev, max_rows);
   const int kv0 = blockIdx.x * n_tile, h0 = blockIdx.y * kTileM;
@@ -844,13 +847,13 @@ using namespace gs::tc;
   do {                                                                                                      \
     int e_ = 0;                                                                                             \
     if (split3 && async) { if ((e_ = set_smem(KERNEL<true, true>, SMEM))) return e_;                        \
-      KERNEL<true, true><<<GRID, kThreads, SMEM, STREAM>>>(__VA_ARGS__); }                                  \
+      launch(KERNEL<true, true>, GRID, kThreads, SMEM, STREAM, __VA_ARGS__); }                                  \
     else if (split3) { if ((e_ = set_smem(KERNEL<true, false>, SMEM))) return e_;                           \
-      KERNEL<true, false><<<GRID, kThreads, SMEM, STREAM>>>(__VA_ARGS__); }                                 \
+      launch(KERNEL<true, false>, GRID, kThreads, SMEM, STREAM, __VA_ARGS__); }                                 \
     else if (async) { if ((e_ = set_smem(KERNEL<false, true>, SMEM))) return e_;                            \
-      KERNEL<false, true><<<GRID, kThreads, SMEM, STREAM>>>(__VA_ARGS__); }                                 \
+      launch(KERNEL<false, true>, GRID, kThreads, SMEM, STREAM, __VA_ARGS__); }                                 \
     else { if ((e_ = set_smem(KERNEL<false, false>, SMEM))) return e_;                                      \
-      KERNEL<false, false><<<GRID, kThreads, SMEM, STREAM>>>(__VA_ARGS__); }                                \
+      launch(KERNEL<false, false>, GRID, kThreads, SMEM, STREAM, __VA_ARGS__); }                                \
   } while (0)
 
 int gs_sage_gemm_fwd_tc(const float* self_table, int64_t ld_self, const int32_t* self_idx, const float* agg,

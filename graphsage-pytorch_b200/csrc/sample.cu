@@ -23,6 +23,7 @@ sample_neighbors_kernel(const int64_t* __restrict__ rowptr, const int32_t* __res
                         int k, int stride, int self_mode, uint64_t seed, uint64_t offset,
                         const int64_t* __restrict__ offset_dev,
                         int32_t* __restrict__ out_nbr, int32_t* __restrict__ out_cnt) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * kSampleWarps + (threadIdx.x >> 5);
   if (r >= max_rows) return;
@@ -81,6 +82,7 @@ __global__ void random_walk_kernel(const int64_t* __restrict__ rowptr, const int
                                    int64_t num_nodes, const int32_t* __restrict__ seeds, int num_seeds, int n_walks,
                                    int walk_len, const uint8_t* __restrict__ is_train, uint64_t seed, uint64_t offset,
                                    int32_t* __restrict__ pos) {
+  pdl_sync();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= num_seeds * n_walks) return;
   const int s = t / n_walks;
@@ -121,6 +123,7 @@ negative_sample_kernel(const int64_t* __restrict__ rowptr, const int32_t* __rest
                        const int32_t* __restrict__ seeds, int hops, int num_neg,
                        const int32_t* __restrict__ train_nodes, int num_train, uint64_t seed, uint64_t offset,
                        int32_t* __restrict__ neg, int32_t* __restrict__ neg_cnt, uint32_t* __restrict__ workspace) {
+  pdl_sync();
   const int s = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kNegThreads / 32;
   const int64_t words = (num_nodes + 31) / 32;
@@ -248,7 +251,7 @@ extern "C" int gs_sample_neighbors(const int64_t* rowptr, const int32_t* col, in
   if (stride < k + (self_mode == GS_SELF_ONCE ? 1 : 0)) return GS_ERR_BAD_ARG;
   if (self_mode < GS_SELF_KEEP || self_mode > GS_SELF_ONCE) return GS_ERR_BAD_ARG;
   if (max_rows == 0) return GS_OK;
-  sample_neighbors_kernel<<<(max_rows + kSampleWarps - 1) / kSampleWarps, kSampleWarps * 32, 0, as_stream(stream)>>>(
+  launch(sample_neighbors_kernel, (max_rows + kSampleWarps - 1) / kSampleWarps, kSampleWarps * 32, 0, as_stream(stream), 
       rowptr, col, num_nodes, nodes, num_rows_dev, max_rows, k, stride, self_mode, seed, offset, offset_dev, out_nbr,
       out_cnt);
   return finish_launch();
@@ -262,7 +265,7 @@ extern "C" int gs_random_walk_pos(const int64_t* rowptr, const int32_t* col, int
   if (num_seeds < 0 || n_walks < 1 || walk_len < 1) return GS_ERR_BAD_ARG;
   if (num_seeds == 0) return GS_OK;
   const int total = num_seeds * n_walks, threads = 128;
-  random_walk_kernel<<<(total + threads - 1) / threads, threads, 0, as_stream(stream)>>>(
+  launch(random_walk_kernel, (total + threads - 1) / threads, threads, 0, as_stream(stream), 
       rowptr, col, num_nodes, seeds, num_seeds, n_walks, walk_len, is_train, seed, offset, pos);
   return finish_launch();
 }
@@ -281,7 +284,7 @@ extern "C" int gs_negative_sample(const int64_t* rowptr, const int32_t* col, int
   if (num_neg < 1 || num_neg > GS_MAX_FANOUT * 4 || hops < 0 || num_seeds < 0 || num_train < 0) return GS_ERR_BAD_ARG;
   if (workspace_bytes < gs_negative_workspace_bytes(num_nodes, num_seeds)) return GS_ERR_WORKSPACE;
   if (num_seeds == 0) return GS_OK;
-  negative_sample_kernel<<<num_seeds, kNegThreads, 0, as_stream(stream)>>>(
+  launch(negative_sample_kernel, num_seeds, kNegThreads, 0, as_stream(stream), 
       rowptr, col, num_nodes, seeds, hops, num_neg, train_nodes, num_train, seed, offset, neg, neg_cnt,
       static_cast<uint32_t*>(workspace));
   return finish_launch();

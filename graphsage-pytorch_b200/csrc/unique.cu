@@ -81,6 +81,7 @@ unique_small_kernel(const int32_t* __restrict__ nodes, const int32_t* __restrict
                     const int32_t* __restrict__ nbr, int stride, int passes, int cap_keys,
                     int32_t* __restrict__ uniq, int32_t* __restrict__ num_uniq_dev,
                     int32_t* __restrict__ nbr_idx, int32_t* __restrict__ self_idx) {
+  pdl_sync();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* buf_a = reinterpret_cast<uint32_t*>(smem_raw);
   uint32_t* buf_b = buf_a + cap_keys;
@@ -198,6 +199,7 @@ unique_small_kernel(const int32_t* __restrict__ nodes, const int32_t* __restrict
 __global__ void gather_keys_kernel(const int32_t* __restrict__ nodes, const int32_t* __restrict__ num_rows_dev,
                                    int max_rows, const int32_t* __restrict__ nbr, int stride, int cap_keys,
                                    uint32_t* __restrict__ keys) {
+  pdl_sync();
   const int rows = live_rows(num_rows_dev, max_rows);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cap_keys; i += gridDim.x * blockDim.x)
     keys[i] = combined_key(nodes, nbr, rows, stride, i);
@@ -205,6 +207,7 @@ __global__ void gather_keys_kernel(const int32_t* __restrict__ nodes, const int3
 
 __global__ void __launch_bounds__(kTileThreads)
 radix_hist_kernel(const uint32_t* __restrict__ keys, int shift, int nblk, uint32_t* __restrict__ ghist) {
+  pdl_sync();
   __shared__ uint32_t hist[256];
   hist[threadIdx.x] = 0;
   __syncthreads();
@@ -216,6 +219,7 @@ radix_hist_kernel(const uint32_t* __restrict__ keys, int shift, int nblk, uint32
 
 // in-place exclusive scan of n uint32 by one CTA; total (optional) to *total_out
 __global__ void __launch_bounds__(1024) exclusive_scan_kernel(uint32_t* __restrict__ data, int n, int32_t* total_out) {
+  pdl_sync();
   __shared__ uint32_t s_part[1024];
   const int tid = threadIdx.x;
   const int per = (n + 1023) / 1024;
@@ -238,6 +242,7 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(uint32_t* __restri
 __global__ void __launch_bounds__(kTileThreads)
 radix_scatter_kernel(const uint32_t* __restrict__ keys, int shift, int nblk, const uint32_t* __restrict__ ghist,
                      uint32_t* __restrict__ out) {
+  pdl_sync();
   __shared__ uint32_t s_tile[kTileKeys];
   __shared__ uint32_t wcnt[kTileWarps * 256];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -269,6 +274,7 @@ __device__ __forceinline__ bool is_head(const uint32_t* __restrict__ keys, int64
 
 __global__ void __launch_bounds__(kTileThreads)
 rle_count_kernel(const uint32_t* __restrict__ keys, uint32_t* __restrict__ bcount) {
+  pdl_sync();
   __shared__ int s_cnt;
   if (threadIdx.x == 0) s_cnt = 0;
   __syncthreads();
@@ -283,6 +289,7 @@ rle_count_kernel(const uint32_t* __restrict__ keys, uint32_t* __restrict__ bcoun
 
 __global__ void __launch_bounds__(kTileThreads)
 rle_write_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ boffset, int32_t* __restrict__ uniq) {
+  pdl_sync();
   __shared__ int s_scan[kTileThreads];
   const int tid = threadIdx.x;
   constexpr int per = kTileKeys / kTileThreads;
@@ -306,6 +313,7 @@ __global__ void remap_kernel(const int32_t* __restrict__ nodes, const int32_t* _
                              const int32_t* __restrict__ nbr, int stride, const int32_t* __restrict__ uniq,
                              const int32_t* __restrict__ num_uniq_dev, int32_t* __restrict__ nbr_idx,
                              int32_t* __restrict__ self_idx) {
+  pdl_sync();
   const int rows = live_rows(num_rows_dev, max_rows);
   const int n_uniq = *num_uniq_dev;
   const uint32_t* u = reinterpret_cast<const uint32_t*>(uniq);
@@ -350,6 +358,7 @@ __global__ void __launch_bounds__(256)
 bitmap_mark_kernel(const int32_t* __restrict__ nodes, const int32_t* __restrict__ num_rows_dev, int max_rows,
                    const int32_t* __restrict__ nbr, int stride, int64_t num_nodes, uint32_t* __restrict__ bitmap,
                    int clear) {
+  pdl_sync();
   const int rows = live_rows(num_rows_dev, max_rows);
   const int64_t m = static_cast<int64_t>(rows) * (stride + 1);
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < m;
@@ -363,6 +372,7 @@ bitmap_mark_kernel(const int32_t* __restrict__ nodes, const int32_t* __restrict_
 
 __global__ void __launch_bounds__(1024)
 bitmap_scan_kernel(const uint32_t* __restrict__ bitmap, int32_t* __restrict__ wprefix, uint32_t* __restrict__ block_sum) {
+  pdl_sync();
   __shared__ int s_warp[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t w0 = static_cast<int64_t>(blockIdx.x) * kBmBlockWords + 4 * tid;
@@ -398,6 +408,7 @@ bitmap_emit_remap_kernel(const int32_t* __restrict__ nodes, const int32_t* __res
                          int emit_blocks, const uint32_t* __restrict__ bitmap, const int32_t* __restrict__ wprefix,
                          const uint32_t* __restrict__ block_sum, int32_t* __restrict__ uniq,
                          int32_t* __restrict__ nbr_idx, int32_t* __restrict__ self_idx) {
+  pdl_sync();
   if (static_cast<int>(blockIdx.x) < emit_blocks) {            // ---- emit: one thread per bitmap word
     const int64_t w = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (w >= words) return;
@@ -522,7 +533,7 @@ extern "C" int gs_unique_remap(const int32_t* nodes, const int32_t* num_rows_dev
       if (e != cudaSuccess) return static_cast<int>(e);
       attr_set = true;
     }
-    unique_small_kernel<<<1, kSmallThreads, smem, st>>>(nodes, num_rows_dev, max_rows, nbr, stride, passes,
+    launch(unique_small_kernel, 1, kSmallThreads, smem, st, nodes, num_rows_dev, max_rows, nbr, stride, passes,
                                                         p.cap_keys, uniq, num_uniq_dev, nbr_idx, self_idx);
     return finish_launch();
   }
@@ -533,26 +544,26 @@ extern "C" int gs_unique_remap(const int32_t* nodes, const int32_t* num_rows_dev
   uint32_t* ghist = reinterpret_cast<uint32_t*>(ws + p.off_hist);
   uint32_t* bcount = reinterpret_cast<uint32_t*>(ws + p.off_bcount);
   int launches = 0;
-  gather_keys_kernel<<<std::min(p.nblk * (kTileKeys / 256), 148 * 8), 256, 0, st>>>(nodes, num_rows_dev, max_rows, nbr,
+  launch(gather_keys_kernel, std::min(p.nblk * (kTileKeys / 256), 148 * 8), 256, 0, st, nodes, num_rows_dev, max_rows, nbr,
                                                                                 stride, p.cap_keys, keys_a);
   ++launches;
   uint32_t* in = keys_a;
   uint32_t* out = keys_b;
   for (int pass = 0; pass < passes; ++pass) {
-    radix_hist_kernel<<<p.nblk, kTileThreads, 0, st>>>(in, 8 * pass, p.nblk, ghist);
-    exclusive_scan_kernel<<<1, 1024, 0, st>>>(ghist, 256 * p.nblk, nullptr);
-    radix_scatter_kernel<<<p.nblk, kTileThreads, 0, st>>>(in, 8 * pass, p.nblk, ghist, out);
+    launch(radix_hist_kernel, p.nblk, kTileThreads, 0, st, in, 8 * pass, p.nblk, ghist);
+    launch(exclusive_scan_kernel, 1, 1024, 0, st, ghist, 256 * p.nblk, nullptr);
+    launch(radix_scatter_kernel, p.nblk, kTileThreads, 0, st, in, 8 * pass, p.nblk, ghist, out);
     launches += 3;
     uint32_t* t = in; in = out; out = t;
   }
-  rle_count_kernel<<<p.nblk, kTileThreads, 0, st>>>(in, bcount);
-  exclusive_scan_kernel<<<1, 1024, 0, st>>>(bcount, p.nblk, num_uniq_dev);
-  rle_write_kernel<<<p.nblk, kTileThreads, 0, st>>>(in, bcount, uniq);
+  launch(rle_count_kernel, p.nblk, kTileThreads, 0, st, in, bcount);
+  launch(exclusive_scan_kernel, 1, 1024, 0, st, bcount, p.nblk, num_uniq_dev);
+  launch(rle_write_kernel, p.nblk, kTileThreads, 0, st, in, bcount, uniq);
   launches += 3;
   if (nbr_idx || self_idx) {
     const int64_t work = static_cast<int64_t>(max_rows) * (stride > 0 ? stride : 1);
     const int blocks = static_cast<int>(std::min<int64_t>((work + 255) / 256, 148 * 16));
-    remap_kernel<<<blocks, 256, 0, st>>>(nodes, num_rows_dev, max_rows, nbr, stride, uniq, num_uniq_dev, nbr_idx,
+    launch(remap_kernel, blocks, 256, 0, st, nodes, num_rows_dev, max_rows, nbr, stride, uniq, num_uniq_dev, nbr_idx,
                                          self_idx);
     ++launches;
   }
@@ -584,15 +595,15 @@ extern "C" int gs_unique_remap_bitmap(const int32_t* nodes, const int32_t* num_r
   uint32_t* bsum = reinterpret_cast<uint32_t*>(ws + p.off_bsum);
   const int64_t m = static_cast<int64_t>(max_rows) * (stride + 1);
   const int id_blocks = static_cast<int>(std::min<int64_t>((m + 255) / 256, 148 * 8));
-  bitmap_mark_kernel<<<id_blocks, 256, 0, st>>>(nodes, num_rows_dev, max_rows, nbr, stride, num_nodes, bitmap, 0);
-  bitmap_scan_kernel<<<p.nblk, 1024, 0, st>>>(bitmap, wprefix, bsum);
-  exclusive_scan_kernel<<<1, 1024, 0, st>>>(bsum, p.nblk, num_uniq_dev);
+  launch(bitmap_mark_kernel, id_blocks, 256, 0, st, nodes, num_rows_dev, max_rows, nbr, stride, num_nodes, bitmap, 0);
+  launch(bitmap_scan_kernel, p.nblk, 1024, 0, st, bitmap, wprefix, bsum);
+  launch(exclusive_scan_kernel, 1, 1024, 0, st, bsum, p.nblk, num_uniq_dev);
   const int emit_blocks = static_cast<int>((p.words + 255) / 256);
   const int64_t slots = static_cast<int64_t>(max_rows) * (stride > 0 ? stride : 1);
   const int remap_blocks = static_cast<int>(std::min<int64_t>((slots + 255) / 256, 148 * 8));
-  bitmap_emit_remap_kernel<<<emit_blocks + remap_blocks, 256, 0, st>>>(nodes, num_rows_dev, max_rows, nbr, stride,
+  launch(bitmap_emit_remap_kernel, emit_blocks + remap_blocks, 256, 0, st, nodes, num_rows_dev, max_rows, nbr, stride,
                                                                       num_nodes, p.words, emit_blocks, bitmap, wprefix,
                                                                       bsum, uniq, nbr_idx, self_idx);
-  bitmap_mark_kernel<<<id_blocks, 256, 0, st>>>(nodes, num_rows_dev, max_rows, nbr, stride, num_nodes, bitmap, 1);
+  launch(bitmap_mark_kernel, id_blocks, 256, 0, st, nodes, num_rows_dev, max_rows, nbr, stride, num_nodes, bitmap, 1);
   return finish_launch(5);
 }
