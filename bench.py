@@ -332,6 +332,165 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs[4]: 100M-node / 1.6B-entry graph, 128 bf16 features ROW-PARTITIONED across
+# the GPUs, layer-1 gather straight from peer HBM over NVLink (python bench.py --workload cfg5)
+# ------------------------------------------------------------------------------------------------
+def run_cfg5(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    args.gpus = world
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the gsage_b200 hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import graphsage_b200  # noqa: F401
+    from graphsage_b200 import models, native, ops
+    from graphsage_b200.graph import DeviceCSR
+    from graphsage_b200.peer import ShardedTable
+    from graphsage_b200.trainer import SupervisedTrainer
+    import graphsage_b200.synth as synth
+    native.load()
+    n_per, dim, hidden, classes = int(args.cfg5_nodes_per_gpu), 128, 128, 47
+    n = n_per * world
+    b_sz = args.b_sz if args.b_sz != 1024 else 8192
+    K, W = args.steps, args.warmup
+    t0 = time.time()
+    rowptr, col = synth.device_powerlaw_csr(n, 16.0, dev, seed=0)          # replicated: same seed on every rank
+    csr = DeviceCSR.from_device(rowptr, col)
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    shard = torch.empty((n_per, dim), dtype=torch.bfloat16, device=dev)
+    for lo in range(0, n_per, 1 << 22):
+        hi = min(n_per, lo + (1 << 22))
+        shard[lo:hi] = torch.randn((hi - lo, dim), generator=gen, device=dev).to(torch.bfloat16)
+    table = ShardedTable.distributed(shard, n)
+    del shard
+    labels = torch.randint(0, classes, (n,), generator=torch.Generator(device=dev).manual_seed(2), device=dev)
+    log(f"[bench] cfg5 rank {rank}: n={n} nnz={csr.nnz} shard={n_per}x{dim} bf16 built in {time.time() - t0:.1f}s")
+    torch.manual_seed(SEED)
+    model = models.GraphSage(2, dim, hidden, table, csr, dev, gcn=False, agg_func="MEAN", seed=SEED + rank,
+                             precision=args.precision).to(dev)
+    cls = models.Classification(hidden, classes).to(dev)
+    trainer = SupervisedTrainer(model, cls, labels, b_sz, lr=0.7, max_norm=5.0, use_graph=not args.no_graph,
+                                world_size=world, rank=rank, exchange=args.exchange)
+    dev_batches = torch.randint(0, n, (K + W, b_sz), generator=torch.Generator(device=dev).manual_seed(77 + rank),
+                                device=dev, dtype=torch.int32)
+    host_batches = dev_batches.cpu().numpy().astype(np.int64)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for i in range(W):
+        trainer.step_device(dev_batches[i])
+    sync_all()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.25)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    t_begin = time.time()
+    e0.record()
+    for i in range(K):
+        trainer.step_device(dev_batches[W + i])
+    e1.record()
+    sync_all()
+    ms_dev = max_over_ranks(e0.elapsed_time(e1))
+    loss_dev = float(trainer.loss.item())
+    for i in range(min(W, 3)):
+        trainer.step(host_batches[i]).item()
+    sync_all()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    last = 0.0
+    for i in range(K):
+        last = trainer.step(host_batches[W + i]).item()
+    e3.record()
+    sync_all()
+    ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+    clk = clocks.stop(t_begin, time.time()) if rank == 0 else None
+    if trainer.dp is not None:
+        trainer.dp.status()
+
+    # ---- the sharded gather kernel alone: events around back-to-back launches on distinct frontiers ----
+    weights = [w.detach() for w in trainer.weights]
+    fronts, bytes_, remote_ = [], [], []
+    for i in range(min(8, K + W)):
+        fr = model._run_forward(dev_batches[i], weights, None)[0]
+        rows = int(fr.num_rows.item())
+        ids = fr.nbr[:rows]
+        nnz = int((ids >= 0).sum().item())
+        rem = int(((ids >= 0) & (torch.div(ids, n_per, rounding_mode="floor") != rank)).sum().item())
+        bytes_.append(nnz * dim * 2 + rows * dim * 2 + 2 * rows * dim * 4 + nnz * 4 + (rows + 1) * 4)
+        remote_.append(rem * dim * 2 + (rows * dim * 2) * (world - 1) / world)
+        fronts.append((fr, torch.empty_like(fr.agg), torch.empty_like(fr.agg)))
+
+    def launch(fr, out, outs):
+        ops.agg_fwd_sharded(table, fr.nbr, fr.stride, fr.cnt, fr.nodes, fr.num_rows, fr.rows_max, out=out, out_self=outs)
+
+    for f in fronts[:2]:
+        launch(*f)
+    sync_all()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for f in fronts:
+        launch(*f)
+    b.record()
+    sync_all()
+    t_launch = max_over_ranks(a.elapsed_time(b)) * 1e-3 / len(fronts)
+    peak = 6650.0
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    ach = float(np.mean(bytes_)) / t_launch / 1e9
+    nv_in = float(np.mean(remote_)) / t_launch / 1e9
+    roof = {"bound": "hbm", "kernel": "agg_fwd_bf16_sharded_kernel (layer 1, gs_agg_fwd_bf16_sharded)", "achieved": ach,
+            "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "bytes_per_launch": float(np.mean(bytes_)),
+            "us_per_launch": t_launch * 1e6, "remote_bytes_per_launch": float(np.mean(remote_)),
+            "nvlink_in_GBps": nv_in, "nvlink_peak_GBps": 770.0, "nvlink_frac": nv_in / 770.0 if world > 1 else None,
+            "note": "per GPU; rows owned by another rank are read from its HBM over NVLink by the same loads "
+                    "(nvlink_* = those bytes / launch time against the measured 770 GB/s peer-copy figure)"}
+    if rank == 0:
+        seeds_total = b_sz * world * K
+        line = {
+            "metric": "seed_nodes_per_sec_fwd_bwd", "value": seeds_total / (ms_dev * 1e-3), "unit": "seed nodes/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "f32 (tcgen05 3xTF32 split, fp32-faithful); features bf16",
+                                           "tf32": "tf32"}[args.precision],
+            "data": "synthetic",
+            "config": {"workload": "cfg5_sharded_features", "nodes": n, "nodes_per_gpu": n_per, "csr_entries": int(csr.nnz),
+                       "feats": dim, "feature_dtype": "bf16, row-partitioned, one shard per GPU (CUDA IPC peer mappings)",
+                       "hidden": hidden, "classes": classes, "layers": 2, "fanout": 10, "agg": "MEAN", "gcn": False,
+                       "learn_method": "sup", "b_sz_per_gpu": b_sz, "global_batch": b_sz * world, "parallelism": f"dp{world}",
+                       "l2_policy": f"feature shard {n_per * dim * 2 / 1e9:.1f} GB per GPU >> 126 MB L2; fresh seeds every step"},
+            "e2e": {"value": seeds_total / (ms_e2e * 1e-3), "unit": "seed nodes/s", "ms_per_step": ms_e2e / K,
+                    "h2d_bytes_per_step": int(b_sz * 4), "d2h_bytes_per_step": 4},
+            "gpu_launches": int(trainer.launches_per_step * K), "launches_per_step": int(trainer.launches_per_step),
+            "cuda_graph": bool(trainer.use_graph), "loss": loss_dev, "loss_e2e": last, "roofline": roof,
+            "cpu_baseline": None, "cpu_baseline_note": "the reference cannot hold this graph (>100 GB of Python sets, SURVEY.md 8d)",
+            "clocks": clk,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def measure_agg_roofline(torch, ops, native, model, trainer, dev_batches, W, K, dev):
     """Instrumented pass: run the step's sampling phase for fresh batches, then time ONLY the
     layer-1 gs_agg_fwd launch with CUDA events on its stream.  Algorithmic bytes per launch =
@@ -439,6 +598,11 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="gradient exchange + update: peer = one fused kernel over NVLink peer memory (default); "
                          "nccl = library all-reduce followed by the separate norm/update kernels (comparison)")
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg5"],
+                    help="cfg3 = ogbn-products-shaped (the headline, BASELINE configs[2]); cfg5 = row-partitioned bf16 "
+                         "features with P2P NVLink gather (configs[4]; b_sz 8192 per GPU unless --b_sz is given)")
+    ap.add_argument("--cfg5-nodes-per-gpu", type=int, default=12_500_000,
+                    help="cfg5: nodes (= feature rows) owned by each GPU; 12.5M x 8 GPUs = the named 100M-node graph")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--ref-budget-s", type=float, default=150.0)
@@ -448,6 +612,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "cfg5":
+        run_cfg5(args)
     else:
         run_ours(args)
 

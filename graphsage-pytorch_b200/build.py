@@ -41,7 +41,7 @@ def _digest() -> str:
     files = _sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + \
         [os.path.join(os.path.dirname(HERE), "include", "gsage_b200.h"), os.path.abspath(__file__)]
     for f in files:
-        h.update(f.encode())
+        h.update(os.path.basename(f).encode())      # NOT the absolute path: the snapshot on the GPU box lives elsewhere
         with open(f, "rb") as fp:
             h.update(fp.read())
     return h.hexdigest()
@@ -57,16 +57,25 @@ def is_current() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and is_current():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + _sources()
-    if verbose:
-        print(" ".join(cmd))
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or proc.returncode != 0:
-        sys.stderr.write(proc.stdout + proc.stderr)
-    if proc.returncode != 0:
-        raise RuntimeError("nvcc failed building libgsage_b200.so")
-    with open(STAMP, "w") as fp:
-        fp.write(_digest())
+    import fcntl
+    with open(LIB + ".lock", "w") as lock:          # ranks of one job may all find the library stale: one builds
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and is_current():
+            return LIB
+        tmp = f"{LIB}.{os.getpid()}.tmp"
+        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + _sources()
+        if verbose:
+            print(" ".join(cmd))
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or proc.returncode != 0:
+            sys.stderr.write(proc.stdout + proc.stderr)
+        if proc.returncode != 0:
+            if os.path.exists(tmp):
+                os.remove(tmp)
+            raise RuntimeError("nvcc failed building libgsage_b200.so")
+        os.replace(tmp, LIB)                        # atomic: a concurrent dlopen never sees a partial file
+        with open(STAMP, "w") as fp:
+            fp.write(_digest())
     return LIB
 
 

@@ -62,8 +62,20 @@ sample_neighbors_kernel(const int64_t* __restrict__ rowptr, const int32_t* __res
   bool valid = val != kNone;
   if (self_mode != GS_SELF_KEEP && val == me) valid = false;
   if (self_mode == GS_SELF_ONCE && lane == 31) { val = me; valid = true; }     // k <= 31 in this mode
-  int rank = 0;
   const int scan = (self_mode == GS_SELF_ONCE) ? 32 : k;
+  // The reference's rows are sets (src/dataCenter.py:33).  A CSR row that repeats an id (graphs
+  // generated on the device) must behave the same way: the draw is a set, so a repeated id keeps
+  // only its first lane -- otherwise two lanes would share a rank and leave a slot unwritten.
+  {
+    bool dup = false;
+    for (int o = 0; o < scan; ++o) {
+      const int32_t v = __shfl_sync(0xffffffffu, val, o);
+      const bool ok = __shfl_sync(0xffffffffu, static_cast<int>(valid), o) != 0;
+      dup |= ok && o < lane && v == val;
+    }
+    valid = valid && !dup;
+  }
+  int rank = 0;
   for (int o = 0; o < scan; ++o) {
     const int32_t v = __shfl_sync(0xffffffffu, val, o);
     const bool ok = __shfl_sync(0xffffffffu, static_cast<int>(valid), o) != 0;

@@ -87,6 +87,20 @@ class DeviceCSR:
         self.device = self.rowptr.device
 
     @classmethod
+    def from_device(cls, rowptr: torch.Tensor, col: torch.Tensor) -> "DeviceCSR":
+        """Wrap a CSR that already lives in HBM (graphs generated or loaded on the device: 1.6B
+        entries never pass through a host dict-of-sets).  Pass the result as `adj_lists`."""
+        if rowptr.dtype != torch.int64 or col.dtype != torch.int32 or not rowptr.is_cuda or col.device != rowptr.device:
+            raise ValueError("rowptr int64 / col int32 on the same CUDA device")
+        self = cls.__new__(cls)
+        self.num_nodes = int(rowptr.shape[0]) - 1
+        self.nnz = int(col.shape[0])
+        self.rowptr, self.col = rowptr.contiguous(), col.contiguous()
+        self.id_bits = max(1, int(self.num_nodes).bit_length())
+        self.device = rowptr.device
+        return self
+
+    @classmethod
     def from_adj(cls, adj_lists, num_nodes: int, device) -> "DeviceCSR":
         rowptr, col = adj_to_csr(adj_lists, num_nodes)
         return cls(rowptr, col, device)

@@ -29,6 +29,10 @@ _CSR_CACHE: Dict[tuple, tuple] = {}
 
 
 def _device_csr(adj_lists, num_nodes: Optional[int], device) -> DeviceCSR:
+    if isinstance(adj_lists, DeviceCSR):            # already resident (device-generated graphs)
+        if num_nodes is not None and adj_lists.num_nodes != num_nodes:
+            raise ValueError(f"adjacency has {adj_lists.num_nodes} rows, feature table {num_nodes}")
+        return adj_lists
     key = (id(adj_lists), str(device))
     hit = _CSR_CACHE.get(key)
     if hit is not None and hit[0] is adj_lists and (num_nodes is None or hit[1].num_nodes == num_nodes):

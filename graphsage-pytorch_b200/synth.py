@@ -144,3 +144,28 @@ CONFIGS = {
     "cfg4_reddit": dict(n=232_965, edges=57_307_946, feats=602, classes=41, hidden=128, agg="MEAN", gcn=True, learn="plus_unsup", unsup_loss="margin", b_sz=1024),
     "cfg5_100m": dict(n=100_000_000, edges=800_000_000, feats=128, classes=47, hidden=128, agg="MEAN", gcn=False, learn="sup", b_sz=8192),
 }
+
+
+def device_powerlaw_csr(n: int, mean_degree: float, device, seed: int = 0, max_degree: int = 10000):
+    """Adjacency of BASELINE.json configs[4] generated directly in HBM (1.6B entries at 100M
+    nodes never exist on the host): Pareto(alpha=2.5) out-degrees with the requested mean,
+    uniform random targets.  torch's Philox generator makes the result identical on every rank
+    that uses the same seed, so the replicas of a data-parallel job hold the same graph.
+    Returns (rowptr int64 [n+1], col int32 [nnz]) on `device`."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    alpha = 2.5
+    d_min = mean_degree * (alpha - 1.0) / alpha
+    u = torch.rand((n,), generator=g, device=device).clamp_min_(1e-9)
+    deg = torch.floor(d_min * u.pow_(-1.0 / alpha)).clamp_(1, max_degree).to(torch.int64)
+    del u
+    rowptr = torch.zeros((n + 1,), dtype=torch.int64, device=device)
+    torch.cumsum(deg, 0, out=rowptr[1:])
+    del deg
+    nnz = int(rowptr[-1].item())
+    col = torch.empty((nnz,), dtype=torch.int32, device=device)
+    step = 1 << 28
+    for lo in range(0, nnz, step):                 # bounded temporaries
+        hi = min(nnz, lo + step)
+        col[lo:hi] = torch.randint(0, n, (hi - lo,), generator=g, device=device, dtype=torch.int32)
+    return rowptr, col

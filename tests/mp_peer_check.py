@@ -54,10 +54,17 @@ def main():
     offs, total = flat_layout(shapes)
     flat = torch.zeros((total,), dtype=torch.float32, device=dev)
     views = [flat[o:o + p.numel()].view_as(p) for o, p in zip(offs, params)]
+    backends = ['symm', 'ipc']                                 # VMM symmetric memory (default) and legacy CUDA IPC regions
+    os.environ['GS_PEER_BACKEND'] = backends[0]
     dp = peer.DpExchange(flat, params, offs, groups, world=world, rank=rank)
     gr = torch.Generator().manual_seed(100 + rank)             # different gradients per rank
-    for step in range(5):
-        scale = [0.01, 5.0, 1.0, 0.1, 3.0][step]
+    for step in range(10):
+        if step == 5:                                          # second half: the same exchange over gs_peer_* IPC regions
+            dp.close()
+            os.environ['GS_PEER_BACKEND'] = backends[1]
+            dp = peer.DpExchange(flat, params, offs, groups, world=world, rank=rank)
+
+        scale = [0.01, 5.0, 1.0, 0.1, 3.0][step % 5]
         for v in views:
             v.copy_((torch.randn(v.shape, generator=gr) * scale).to(dev))
         mean = flat.clone()
@@ -65,7 +72,7 @@ def main():
         mean /= world
         dp.update(5.0, 0.7)
         epoch, status, _ = dp.status()
-        assert (epoch, status) == (step + 1, 0), (epoch, status)
+        assert (epoch, status) == (step % 5 + 1, 0), (epoch, status)
         # torch statement of src/utils.py:185-187 on the mean gradient
         ps = [torch.nn.Parameter(r.clone()) for r in ref]
         for p, o in zip(ps, offs):
@@ -78,6 +85,7 @@ def main():
             assert rel(p, r) <= 1e-6, (step, rel(p, r))
             assert all_equal_across_ranks(p, world), f'replicas diverged at step {step}'
         assert float(flat.abs().max()) == 0.0
+    os.environ['GS_PEER_BACKEND'] = 'symm'
     dist.barrier()
 
     # ---- 2. remote-shard gather ------------------------------------------------------------------

@@ -430,3 +430,31 @@ def test_cls_nll_fwd_bwd_matches_torch(g, dev, rows, dim, classes, mask):
     assert rel(ge, want_ge) <= TOL
     assert rel(gw, tw.grad) <= TOL
     assert rel(gb, tb.grad) <= TOL
+
+
+def test_sampler_treats_repeated_ids_in_a_row_as_a_set(g, dev):
+    """Device-generated graphs may repeat a neighbour inside a CSR row; the reference's rows are sets
+    (src/dataCenter.py:33), so the drawn list must be distinct, ascending and fully written."""
+    rng = np.random.default_rng(0)
+    n, k, stride = 64, 10, 11
+    rows = [rng.integers(0, 8, size=rng.integers(1, 40)).astype(np.int32) for _ in range(n)]     # ids 0..7: many repeats
+    rowptr = np.zeros(n + 1, dtype=np.int64)
+    rowptr[1:] = np.cumsum([len(r) for r in rows])
+    col = np.concatenate(rows)
+    rp, cl = _csr_dev(rowptr, col, dev)
+    nodes = torch.arange(n, dtype=torch.int32, device=dev)
+    for self_mode in (0, 1, 2):
+        for off in range(20):
+            out = torch.full((n, stride), 12345, dtype=torch.int32, device=dev)               # poison: every slot must be written
+            cnt = torch.full((n,), -7, dtype=torch.int32, device=dev)
+            g.sample_neighbors(rp, cl, n, nodes, None, n, k, stride, self_mode, 7, off, out_nbr=out, out_cnt=cnt)
+            o, c = out.cpu().numpy(), cnt.cpu().numpy()
+            for v in range(n):
+                row = o[v, :c[v]]
+                assert np.all(o[v, c[v]:] == -1) and np.all(np.diff(row) > 0)
+                allowed = set(rows[v].tolist()) | ({v} if self_mode == 2 else set())
+                assert set(row.tolist()) <= allowed
+                if self_mode == 1:
+                    assert v not in row
+                if self_mode == 2:
+                    assert v in row
