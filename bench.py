@@ -194,7 +194,9 @@ def workload_config(args, cfg, rowptr, col, b_sz):
             "batch_extension": False, "exchange": ("fused NVLink peer-memory all-reduce+clip+SGD kernel" if args.exchange == "peer"
                                                    else "NCCL all-reduce + separate clip/SGD kernels"),
             "l2_policy": "feature table 980 MB >> 126 MB L2; fresh seeds every step",
-            "update": "clip_grad_norm 5 per model + SGD lr 0.7 inside the step"}
+            "update": "clip_grad_norm 5 per model + SGD lr 0.7 inside the step",
+            "pipeline": ("2-stage: sampling/unique/layer-1 aggregation of batch n+1 in a graph branch beside the "
+                         "GEMMs/backward/update of batch n" if (args.pipeline and args.exchange == "peer") else "none")}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -218,7 +220,7 @@ def run_ours(args):
     import graphsage_b200  # noqa: F401
     from graphsage_b200 import models, native, ops
     from graphsage_b200.graph import AdjCSR
-    from graphsage_b200.trainer import SupervisedTrainer
+    from graphsage_b200.trainer import PipelinedTrainer, SupervisedTrainer
     import graphsage_b200.synth as synth
     native.load()
 
@@ -242,9 +244,15 @@ def run_ours(args):
         model.sage_layer2.weight.copy_(torch.from_numpy(synth.xavier_uniform_np(wrng, cfg["hidden"], 2 * cfg["hidden"])))
         cls.layer[0].weight.copy_(torch.from_numpy(synth.xavier_uniform_np(wrng, cfg["classes"], cfg["hidden"])))
         cls.layer[0].bias.zero_()
-    trainer = SupervisedTrainer(model, cls, labels, b_sz, lr=0.7, max_norm=5.0, use_graph=not args.no_graph,
-                                world_size=world, rank=rank, exchange=args.exchange)
-    host_batches = batches_for(train, b_sz, K + W, rank, world)
+    pipelined = args.pipeline and args.exchange == "peer"
+    trainer = (PipelinedTrainer if pipelined else SupervisedTrainer)(
+        model, cls, labels, b_sz, lr=0.7, max_norm=5.0, use_graph=not args.no_graph, world_size=world, rank=rank,
+        exchange=args.exchange)
+    # pipelined: submit(batch n+1) trains on batch n while batch n+1 is sampled/aggregated in a second graph
+    # branch -- every timed call still does one full sampling+aggregation and one full fwd/bwd/update
+    step_dev = trainer.submit_device if pipelined else trainer.step_device
+    step_host = trainer.submit if pipelined else trainer.step
+    host_batches = batches_for(train, b_sz, K + W + 1, rank, world)
     dev_batches = torch.from_numpy(host_batches.astype(np.int32)).to(dev)
 
     def sync_all():
@@ -260,8 +268,8 @@ def run_ours(args):
         return float(t.item())
 
     # ---- device-resident arm ("value") ----
-    for i in range(W):
-        trainer.step_device(dev_batches[i])
+    for i in range(W + 1):
+        step_dev(dev_batches[i])
     sync_all()
     clocks = ClockSampler(local)
     if rank == 0:
@@ -273,7 +281,7 @@ def run_ours(args):
     t_begin = time.time()
     e0.record()
     for i in range(K):
-        trainer.step_device(dev_batches[W + i])
+        step_dev(dev_batches[W + 1 + i])
     e1.record()
     sync_all()
     t_end = time.time()
@@ -282,17 +290,19 @@ def run_ours(args):
     launches_timed = trainer.launches_per_step * K if trainer.use_graph else native.launch_count()
 
     # ---- end-to-end arm ("e2e"): host numpy batch -> H2D -> step -> loss.item() ----
-    for i in range(min(W, 3)):
-        trainer.step(host_batches[i]).item()
+    for i in range(min(W, 3) + 1):
+        step_host(host_batches[i]).item()
     sync_all()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     last = 0.0
     for i in range(K):
-        last = trainer.step(host_batches[W + i]).item()                        # D2H of the loss every step
+        last = step_host(host_batches[W + 1 + i]).item()                       # H2D of a batch, D2H of a loss every step
     e3.record()
     sync_all()
     ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+    if pipelined:
+        trainer.flush()
     if trainer.dp is not None:
         trainer.dp.status()                                                    # raises if a peer wait ever timed out
     clk = clocks.stop(t_begin, time.time()) if rank == 0 else None
@@ -604,6 +614,8 @@ def main():
                          "features with P2P NVLink gather (configs[4]; b_sz 8192 per GPU unless --b_sz is given)")
     ap.add_argument("--cfg5-nodes-per-gpu", type=int, default=12_500_000,
                     help="cfg5: nodes (= feature rows) owned by each GPU; 12.5M x 8 GPUs = the named 100M-node graph")
+    ap.add_argument("--pipeline", type=int, default=1,
+                    help="1 (default): software-pipelined trainer (prepare batch n+1 beside training on batch n); 0: one batch at a time")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--ref-budget-s", type=float, default=150.0)

@@ -5,15 +5,18 @@
 
 namespace gs {
 int64_t g_launches = 0;
+static int g_pdl_override = -1;          // gs_set_pdl: -1 = follow GS_PDL (default on), 0 = off, 1 = on
 bool pdl_enabled() {
   static int on = -1;
   if (on < 0) {
     const char* e = getenv("GS_PDL");
     on = (e && e[0] == '0') ? 0 : 1;
   }
-  return on == 1;
+  return g_pdl_override < 0 ? on == 1 : g_pdl_override == 1;
 }
 }
+
+extern "C" void gs_set_pdl(int32_t mode) { gs::g_pdl_override = mode < 0 ? -1 : (mode ? 1 : 0); }
 
 extern "C" int gs_version(void) { return GS_ABI_VERSION; }
 

@@ -314,16 +314,24 @@ class GraphSage(nn.Module):
 
     def _run_forward(self, nodes_dev: torch.Tensor, weights: Sequence[torch.Tensor], injected=None,
                      offset_dev: Optional[torch.Tensor] = None) -> List[_Frontier]:
+        return self._run_compute(self._run_prep(nodes_dev, injected, offset_dev), weights)
+
+    def _run_prep(self, nodes_dev: torch.Tensor, injected=None, offset_dev: Optional[torch.Tensor] = None,
+                  reuse: Optional[List[_Frontier]] = None) -> List[_Frontier]:
+        """The weight-independent half of a forward pass: sampling + unique/remap of every layer
+        (src/models.py:249-251) and the layer-1 aggregation of the raw features (:260, index 1).
+        `reuse`: the frontiers of an earlier call whose buffers are overwritten in place (static
+        addresses: the pipelined trainer prepares step n+1 in a graph branch beside step n)."""
         csr, table, dev = self._state()
         L, k = self.num_layers, self.num_sample
         self_mode = native.SELF_ONCE if self.gcn else native.SELF_DROP
         mode = native.AGG_MEAN if self.agg_func == 'MEAN' else native.AGG_MAX
-        prec = _PRECISIONS[self.precision]
         self._calls += 1
         layers: List[Optional[_Frontier]] = [None] * (L + 1)
         nodes, num_rows, rows_max = nodes_dev, None, int(nodes_dev.shape[0])
         # ---- sampling phase, batch outward (src/models.py:249-251) ----
         for l in range(L, 0, -1):
+            old = reuse[l - 1] if reuse is not None else None
             fr = _Frontier()
             fr.nodes, fr.num_rows, fr.rows_max = nodes, num_rows, rows_max
             if injected is not None:
@@ -339,37 +347,55 @@ class GraphSage(nn.Module):
                 fr.stride = self._list_stride()
                 offset = (self._calls << 8) | l
                 fr.nbr, fr.cnt = ops.sample_neighbors(csr.rowptr, csr.col, csr.num_nodes, nodes, num_rows, rows_max, k,
-                                                      fr.stride, self_mode, self.seed, offset, offset_dev=offset_dev)
+                                                      fr.stride, self_mode, self.seed, offset, offset_dev=offset_dev,
+                                                      out_nbr=old.nbr if old else None, out_cnt=old.cnt if old else None)
             if l > 1:   # unique + remap (src/models.py:286-288); the next frontier is U, ascending
+                prev = reuse[l - 2] if reuse is not None else None
+                outs = dict(uniq=prev.nodes, num_uniq=prev.num_rows, nbr_idx=old.nbr_idx, self_idx=old.self_idx) if old else {}
                 if self._bitmap_ws is not None:
                     uniq, num_uniq, fr.nbr_idx, fr.self_idx = ops.unique_remap_bitmap(
-                        nodes, num_rows, rows_max, fr.nbr, fr.stride, csr.num_nodes, self._bitmap_ws)
+                        nodes, num_rows, rows_max, fr.nbr, fr.stride, csr.num_nodes, self._bitmap_ws, **outs)
                 else:
                     uniq, num_uniq, fr.nbr_idx, fr.self_idx = ops.unique_remap(nodes, num_rows, rows_max, fr.nbr,
-                                                                               fr.stride, csr.id_bits)
+                                                                               fr.stride, csr.id_bits, **outs)
                 nodes, num_rows = uniq, num_uniq
                 rows_max = min(rows_max * (fr.stride + 1), max(csr.num_nodes, 1))
             else:       # layer 1 gathers straight from the feature table by node id: no U0, no remap
                 fr.nbr_idx, fr.self_idx = fr.nbr, nodes
             layers[l] = fr
-        # ---- compute phase (src/models.py:255-267) ----
-        tbl, dim = table, self.input_size
-        for l in range(1, L + 1):
-            fr = layers[l]
-            fr.table_in, fr.dim_in = tbl, dim
-            if isinstance(tbl, ShardedTable):
-                # layer 1 over a row-partitioned table: K3 also emits the fp32 self rows (:265), which
-                # become K4's self operand with the identity index (forward and backward)
-                fr.agg, self_rows = ops.agg_fwd_sharded(tbl, fr.nbr_idx, fr.stride, fr.cnt, fr.nodes, fr.num_rows,
-                                                        fr.rows_max, want_self=not self.gcn)
-                fr.argmax, fr.table_in, fr.self_idx = None, self_rows, None
-                tbl = self_rows
-            else:
-                fr.agg, fr.argmax = ops.agg_fwd(tbl, dim, fr.nbr_idx, fr.stride, fr.cnt, fr.num_rows, fr.rows_max, mode)
-            fr.h = ops.sage_gemm_fwd(None if self.gcn else tbl, fr.self_idx, fr.agg, dim, weights[l - 1], self.out_size,
-                                     self.gcn, fr.num_rows, fr.rows_max, True, prec)
-            tbl, dim = fr.h, self.out_size
+        # ---- layer-1 aggregation: reads only the raw feature table ----
+        fr, old = layers[1], (reuse[0] if reuse is not None else None)
+        fr.table_in, fr.dim_in = table, self.input_size
+        if isinstance(table, ShardedTable):
+            # row-partitioned table: K3 also emits the fp32 self rows (:265), which become K4's self
+            # operand with the identity index (forward and backward)
+            fr.agg, self_rows = ops.agg_fwd_sharded(table, fr.nbr_idx, fr.stride, fr.cnt, fr.nodes, fr.num_rows,
+                                                    fr.rows_max, want_self=not self.gcn,
+                                                    out=old.agg if old else None,
+                                                    out_self=old.table_in if (old and not self.gcn) else None)
+            fr.argmax, fr.table_in, fr.self_idx = None, self_rows, None
+        else:
+            fr.agg, fr.argmax = ops.agg_fwd(table, self.input_size, fr.nbr_idx, fr.stride, fr.cnt, fr.num_rows,
+                                            fr.rows_max, mode, out=old.agg if old else None,
+                                            argmax=old.argmax if old else None)
         return layers[1:]
+
+    def _run_compute(self, layers: List[_Frontier], weights: Sequence[torch.Tensor]) -> List[_Frontier]:
+        """The weight-dependent half (src/models.py:255-267): SageLayer GEMM of every layer and the
+        aggregations above layer 1."""
+        L = self.num_layers
+        mode = native.AGG_MEAN if self.agg_func == 'MEAN' else native.AGG_MAX
+        prec = _PRECISIONS[self.precision]
+        for l in range(1, L + 1):
+            fr = layers[l - 1]
+            if l > 1:
+                prev = layers[l - 2]
+                fr.table_in, fr.dim_in = prev.h, self.out_size
+                fr.agg, fr.argmax = ops.agg_fwd(prev.h, self.out_size, fr.nbr_idx, fr.stride, fr.cnt, fr.num_rows,
+                                                fr.rows_max, mode)
+            fr.h = ops.sage_gemm_fwd(None if self.gcn else fr.table_in, fr.self_idx, fr.agg, fr.dim_in, weights[l - 1],
+                                     self.out_size, self.gcn, fr.num_rows, fr.rows_max, True, prec)
+        return layers
 
     def _run_backward(self, layers: List[_Frontier], grad_out: torch.Tensor, weights, needs,
                       grad_bufs=None, own_grad: bool = False, top_masked: bool = False,

@@ -20,7 +20,7 @@ AGG_MEAN, AGG_MAX = 0, 1
 SELF_KEEP, SELF_DROP, SELF_ONCE = 0, 1, 2
 PREC_FP32, PREC_TF32, PREC_TF32X3 = 0, 1, 2
 MAX_FANOUT = 32
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 _P, _I, _L, _F, _U64, _SZ = c_void_p, c_int32, c_int64, c_float, c_uint64, c_size_t
 
@@ -30,6 +30,7 @@ _SIGNATURES = {
     "gs_error_string": (ctypes.c_char_p, [_I]),
     "gs_launch_count": (_L, []),
     "gs_launch_count_reset": (None, []),
+    "gs_set_pdl": (None, [_I]),
     "gs_sample_neighbors": (_I, [_P, _P, _L, _P, _P, _I, _I, _I, _I, _U64, _U64, _P, _P, _P, _P]),
     "gs_unique_workspace_bytes": (_SZ, [_I, _I]),
     "gs_unique_remap": (_I, [_P, _P, _I, _P, _I, _I, _P, _P, _P, _P, _P, _SZ, _P]),
@@ -128,3 +129,8 @@ def launch_count() -> int:
 
 def launch_count_reset() -> None:
     load().gs_launch_count_reset()
+
+
+def set_pdl(mode: int) -> None:
+    """1 = programmatic dependent launch on, 0 = off, -1 = follow GS_PDL (see include/gsage_b200.h)."""
+    load().gs_set_pdl(int(mode))

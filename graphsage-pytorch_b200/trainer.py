@@ -185,3 +185,142 @@ class SupervisedTrainer:
             self._update()
             self.launches_per_step = native.launch_count() - before
         return self.loss
+
+
+class PipelinedTrainer(SupervisedTrainer):
+    """Software-pipelined supervised step.  Sampling, unique/remap and the layer-1 aggregation of
+    the raw features do not depend on the weights (`GraphSage._run_prep`), so the graph of step n
+    has TWO branches: the GEMMs / loss / backward / exchange+update of batch n, and beside it the
+    preparation of batch n+1 into the other of two static frontier slots.  The HBM-bound gathers
+    overlap the tensor-core and latency-bound half; every batch still gets exactly the same work
+    and the same arithmetic as in `SupervisedTrainer` (identical results when the sampler has no
+    choice to make, see tests/test_gpu_model.py::test_pipelined_trainer_matches_plain_trainer).
+
+        tr.submit(batch_0)            # primes the pipeline: prepares batch 0, returns None
+        loss_0 = tr.submit(batch_1)   # trains on batch 0 while preparing batch 1
+        ...
+        loss_k = tr.flush()           # trains on the last submitted batch
+
+    The reference's loop knows all batches of an epoch up front (src/utils.py:127,141-145), so
+    looking one batch ahead changes nothing in its semantics."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        if self.dp is None:
+            raise ValueError("PipelinedTrainer needs exchange='peer' (the whole step must be one graph)")
+        dev = self.dev
+        self.slot_seeds = [torch.zeros((self.b_sz,), dtype=torch.int32, device=dev) for _ in range(2)]
+        self.slot_layers = [None, None]
+        self.sample_counter = torch.zeros((1,), dtype=torch.int64, device=dev)
+        self._prep_stream = torch.cuda.Stream(device=dev)
+        self._graphs = [None, None]
+        self._cur: Optional[int] = None          # slot holding the prepared, not yet trained batch
+
+    # ---- the two halves ---------------------------------------------------------------------------
+    def _prep(self, slot: int):
+        self.slot_layers[slot] = self.model._run_prep(self.slot_seeds[slot], None, offset_dev=self.sample_counter,
+                                                      reuse=self.slot_layers[slot])
+        self.sample_counter.add_(1)
+
+    def _compute(self, slot: int, update: bool = True):
+        m = self.model
+        weights = [w.detach() for w in self.weights]
+        layers = m._run_compute(self.slot_layers[slot], weights)
+        self.last_layers = layers
+        emb = layers[-1].h
+        gemb = torch.empty_like(emb)
+        n_sage = len(self.weights)
+        ops.cls_nll_fwd_bwd(emb, m.out_size, self.cls_w.detach(), self.cls_b.detach(), self.cls_w.shape[0], self.labels,
+                            self.slot_seeds[slot], self.loss, gemb, self.grads[n_sage], self.grads[n_sage + 1],
+                            precision=_PRECISIONS[m.precision], mask_relu_input=True)
+        m._run_backward(layers, gemb, weights, [True] * n_sage, grad_bufs=self.grads[:n_sage], own_grad=True,
+                        top_masked=True, side_stream=self._side)
+        if update:
+            self.dp.update(self.max_norm, self.lr, None)
+
+    def _both(self, slot: int, update: bool = True):
+        """train on `slot` | prepare the other slot -- a fork/join, eagerly or under capture"""
+        main = torch.cuda.current_stream()
+        self._prep_stream.wait_stream(main)
+        try:
+            with torch.cuda.stream(self._prep_stream):
+                # programmatic dependent launch stays on for the (critical) training chain only: early-resident
+                # dependents of the preparation chain would hold SM slots the GEMMs need.  Measured per replay:
+                # both on 127 us, both off 110 us, training chain only 106 us (sequential step: 138 us).
+                native.set_pdl(0)
+                self._prep(1 - slot)
+            native.set_pdl(-1)
+            self._compute(slot, update)
+        finally:
+            native.set_pdl(-1)
+        main.wait_stream(self._prep_stream)
+
+    def _capture_pipeline(self):
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):            # warm-up: allocates both slots, loads modules; no update, counters restored
+            counter = self.sample_counter.clone()
+            self._prep(0)
+            self._prep(1)
+            for slot in (0, 1):
+                self._both(slot, update=False)
+                self.flat_grad.zero_()
+            self.sample_counter.copy_(counter)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        for slot in (0, 1):
+            before = native.launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._both(slot)
+            self._graphs[slot] = g
+            self.launches_per_step = native.launch_count() - before
+        self.flat_grad.zero_()
+
+    # ---- public ------------------------------------------------------------------------------------
+    def submit_device(self, seeds_dev: torch.Tensor) -> Optional[torch.Tensor]:
+        """Hand over the NEXT batch (int32 [b_sz] in HBM).  Trains on the previously submitted batch
+        (returns its device loss) while this one is prepared; the first call only prepares."""
+        if self.use_graph and self._graphs[0] is None:
+            self._capture_pipeline()
+        if self._cur is None:
+            self.slot_seeds[0].copy_(seeds_dev, non_blocking=True)
+            self._prep(0)
+            self._cur = 0
+            return None
+        nxt = 1 - self._cur
+        self.slot_seeds[nxt].copy_(seeds_dev, non_blocking=True)
+        if self.use_graph:
+            self._graphs[self._cur].replay()
+        else:
+            before = native.launch_count()
+            self._both(self._cur)
+            self.launches_per_step = native.launch_count() - before
+        self._cur = nxt
+        return self.loss
+
+    def submit(self, nodes_batch) -> Optional[torch.Tensor]:
+        """`submit_device` from a HOST batch (pinned staging copy + H2D inside the call)."""
+        arr = np.asarray(nodes_batch)
+        if arr.shape[0] != self.b_sz:
+            raise ValueError(f"trainer was built for b_sz={self.b_sz}, got {arr.shape[0]}")
+        self.seeds_pinned.numpy()[:] = arr
+        self.seeds.copy_(self.seeds_pinned, non_blocking=True)
+        return self.submit_device(self.seeds)
+
+    def flush(self) -> Optional[torch.Tensor]:
+        """Train on the last submitted batch (nothing left to prepare)."""
+        if self._cur is None:
+            return None
+        self._compute(self._cur)
+        self._cur = None
+        return self.loss
+
+    # the one-batch-at-a-time entry points of the base class keep their meaning
+    def step_device(self, seeds_dev: torch.Tensor) -> torch.Tensor:
+        self.submit_device(seeds_dev)
+        return self.flush()
+
+    def step(self, nodes_batch) -> torch.Tensor:
+        self.submit(nodes_batch)
+        return self.flush()

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 8
+#define GS_ABI_VERSION 9
 
 #define GS_OK 0
 #define GS_ERR_BAD_ARG (-1)
@@ -55,6 +55,13 @@ const char* gs_error_string(int code);
 /* number of kernels this library has launched since load / since the last reset (bench.py's gpu_launches) */
 int64_t gs_launch_count(void);
 void gs_launch_count_reset(void);
+/* Programmatic dependent launch (every kernel of the library starts with griddepcontrol.launch_dependents
+ * + griddepcontrol.wait and is launched with the programmatic-stream-serialization attribute, so the next
+ * kernel of a chain is scheduled while the current one drains).  mode: 1 = on, 0 = off, -1 = follow the
+ * GS_PDL environment variable (default on).  The attribute is fixed when a launch is captured into a graph;
+ * a caller running two chains side by side switches it off for one of them (early-resident dependents of
+ * one chain would otherwise hold SM slots the other chain needs). */
+void gs_set_pdl(int32_t mode);
 
 /* ------------------------------------------------------------------------------------
  * K1  neighbour sampler.  Replaces GraphSage._get_unique_neighs_list's sampling half,
