@@ -248,10 +248,8 @@ def run_ours(args):
     trainer = (PipelinedTrainer if pipelined else SupervisedTrainer)(
         model, cls, labels, b_sz, lr=0.7, max_norm=5.0, use_graph=not args.no_graph, world_size=world, rank=rank,
         exchange=args.exchange)
-    # pipelined: submit(batch n+1) trains on batch n while batch n+1 is sampled/aggregated in a second graph
-    # branch -- every timed call still does one full sampling+aggregation and one full fwd/bwd/update
-    step_dev = trainer.submit_device if pipelined else trainer.step_device
-    step_host = trainer.submit if pipelined else trainer.step
+    # pipelined: step i trains on batch i while batch i+1 is sampled/aggregated in a second graph branch --
+    # every timed step still does one full sampling+aggregation and one full fwd/bwd/update
     host_batches = batches_for(train, b_sz, K + W + 1, rank, world)
     dev_batches = torch.from_numpy(host_batches.astype(np.int32)).to(dev)
 
@@ -268,8 +266,13 @@ def run_ours(args):
         return float(t.item())
 
     # ---- device-resident arm ("value") ----
-    for i in range(W + 1):
-        step_dev(dev_batches[i])
+    if pipelined:
+        trainer.set_queue(dev_batches)                                         # the epoch's batches, resident in HBM
+        trainer.prime()
+        trainer.run(W)
+    else:
+        for i in range(W):
+            trainer.step_device(dev_batches[i])
     sync_all()
     clocks = ClockSampler(local)
     if rank == 0:
@@ -280,8 +283,11 @@ def run_ours(args):
     sync_all()
     t_begin = time.time()
     e0.record()
-    for i in range(K):
-        step_dev(dev_batches[W + 1 + i])
+    if pipelined:
+        trainer.run(K)                                                         # K steps: train batch i | prepare batch i+1
+    else:
+        for i in range(K):
+            trainer.step_device(dev_batches[W + i])
     e1.record()
     sync_all()
     t_end = time.time()
@@ -289,20 +295,47 @@ def run_ours(args):
     loss_dev = float(trainer.loss.item())
     launches_timed = trainer.launches_per_step * K if trainer.use_graph else native.launch_count()
 
-    # ---- end-to-end arm ("e2e"): host numpy batch -> H2D -> step -> loss.item() ----
-    for i in range(min(W, 3) + 1):
-        step_host(host_batches[i]).item()
-    sync_all()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    last = 0.0
-    for i in range(K):
-        last = step_host(host_batches[W + 1 + i]).item()                       # H2D of a batch, D2H of a loss every step
-    e3.record()
-    sync_all()
-    ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+    # ---- end-to-end arm ("e2e"): host numpy batch -> pinned H2D -> step -> loss back on the host, every step ----
     if pipelined:
+        # the loss of step i is copied D2H (pinned) right behind the step and read by the host one step later,
+        # while step i+1 runs: one H2D of a batch and one D2H + host read of a loss per step, no bubble
+        loss_pin = [torch.zeros((1,), dtype=torch.float32).pin_memory() for _ in range(2)]
+        loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
         trainer.flush()
+        trainer.feed(host_batches[0])
+        trainer.prime()
+        for i in range(min(W, 3)):
+            trainer.feed(host_batches[1 + i])
+            trainer.run(1)
+        sync_all()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        last = 0.0
+        for i in range(K):
+            trainer.feed(host_batches[W + 1 + i])
+            dev_loss = trainer.run(1)
+            loss_pin[i & 1].copy_(dev_loss, non_blocking=True)
+            loss_ev[i & 1].record()
+            if i > 0:
+                loss_ev[(i - 1) & 1].synchronize()
+                last = float(loss_pin[(i - 1) & 1][0])
+        loss_ev[(K - 1) & 1].synchronize()
+        last = float(loss_pin[(K - 1) & 1][0])
+        e3.record()
+        sync_all()
+        trainer.flush()
+    else:
+        for i in range(min(W, 3)):
+            trainer.step(host_batches[i]).item()
+        sync_all()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        last = 0.0
+        for i in range(K):
+            last = trainer.step(host_batches[W + i]).item()                    # D2H of the loss every step
+        e3.record()
+        sync_all()
+    ms_e2e = max_over_ranks(e2.elapsed_time(e3))
     if trainer.dp is not None:
         trainer.dp.status()                                                    # raises if a peer wait ever timed out
     clk = clocks.stop(t_begin, time.time()) if rank == 0 else None
@@ -333,6 +366,8 @@ def run_ours(args):
             "e2e": {"value": seeds_total / (ms_e2e * 1e-3), "unit": "seed nodes/s", "ms_per_step": ms_e2e / K,
                     "h2d_bytes_per_step": int(b_sz * 4), "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches_timed), "launches_per_step": int(trainer.launches_per_step),
+            "e2e_loss_read": ("async D2H into pinned memory behind every step, read by the host one step later"
+                              if pipelined else "loss.item() after every step"),
             "cuda_graph": bool(trainer.use_graph), "loss": loss_dev, "loss_e2e": last,
             "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
         }

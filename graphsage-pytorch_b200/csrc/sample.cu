@@ -249,9 +249,31 @@ negative_sample_kernel(const int64_t* __restrict__ rowptr, const int32_t* __rest
   }
 }
 
+// Batch queue of the device-resident train loop (src/utils.py:141-145: the batches of an epoch are
+// slices of one shuffled id array, all known up front).  desc = {address of an int32 [rows x b_sz]
+// array, rows, next}: copies row `next % rows` into dst and advances `next`, inside the step's
+// graph, so consecutive graph replays need no host-side copy between them.
+__global__ void __launch_bounds__(256)
+fetch_batch_kernel(long long* __restrict__ desc, int b_sz, int32_t* __restrict__ dst) {
+  pdl_sync();
+  const int32_t* base = reinterpret_cast<const int32_t*>(desc[0]);
+  const long long rows = desc[1], next = desc[2];
+  if (base == nullptr || rows <= 0) return;
+  const int32_t* src = base + (next % rows) * b_sz;
+  for (int i = threadIdx.x; i < b_sz; i += blockDim.x) dst[i] = src[i];
+  __syncthreads();
+  if (threadIdx.x == 0) desc[2] = next + 1;
+}
+
 }  // namespace gs
 
 using namespace gs;
+
+extern "C" int gs_fetch_batch(int64_t* queue_desc, int32_t b_sz, int32_t* dst, gs_stream_t stream) {
+  if (!queue_desc || !dst || b_sz < 1) return GS_ERR_BAD_ARG;
+  launch(fetch_batch_kernel, 1, 256, 0, as_stream(stream), reinterpret_cast<long long*>(queue_desc), b_sz, dst);
+  return finish_launch();
+}
 
 extern "C" int gs_sample_neighbors(const int64_t* rowptr, const int32_t* col, int64_t num_nodes,
                                    const int32_t* nodes, const int32_t* num_rows_dev, int32_t max_rows,

@@ -20,7 +20,7 @@ AGG_MEAN, AGG_MAX = 0, 1
 SELF_KEEP, SELF_DROP, SELF_ONCE = 0, 1, 2
 PREC_FP32, PREC_TF32, PREC_TF32X3 = 0, 1, 2
 MAX_FANOUT = 32
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 _P, _I, _L, _F, _U64, _SZ = c_void_p, c_int32, c_int64, c_float, c_uint64, c_size_t
 
@@ -32,6 +32,7 @@ _SIGNATURES = {
     "gs_launch_count_reset": (None, []),
     "gs_set_pdl": (None, [_I]),
     "gs_sample_neighbors": (_I, [_P, _P, _L, _P, _P, _I, _I, _I, _I, _U64, _U64, _P, _P, _P, _P]),
+    "gs_fetch_batch": (_I, [_P, _I, _P, _P]),
     "gs_unique_workspace_bytes": (_SZ, [_I, _I]),
     "gs_unique_remap": (_I, [_P, _P, _I, _P, _I, _I, _P, _P, _P, _P, _P, _SZ, _P]),
     "gs_unique_bitmap_workspace_bytes": (_SZ, [_L]),

@@ -41,6 +41,12 @@ def sample_neighbors(rowptr, col, num_nodes: int, nodes, num_rows, max_rows: int
     return out_nbr, out_cnt
 
 
+def fetch_batch(queue_desc, b_sz: int, dst):
+    """dst <- row (next % rows) of the queued batch array; next += 1 (device-resident train loop)."""
+    check(_lib().gs_fetch_batch(ptr(queue_desc), b_sz, ptr(dst), stream()), "gs_fetch_batch")
+    return dst
+
+
 # ----------------------------------------------------------------------------------------------
 # K2
 # ----------------------------------------------------------------------------------------------

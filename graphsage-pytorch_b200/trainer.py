@@ -188,21 +188,28 @@ class SupervisedTrainer:
 
 
 class PipelinedTrainer(SupervisedTrainer):
-    """Software-pipelined supervised step.  Sampling, unique/remap and the layer-1 aggregation of
-    the raw features do not depend on the weights (`GraphSage._run_prep`), so the graph of step n
-    has TWO branches: the GEMMs / loss / backward / exchange+update of batch n, and beside it the
-    preparation of batch n+1 into the other of two static frontier slots.  The HBM-bound gathers
-    overlap the tensor-core and latency-bound half; every batch still gets exactly the same work
-    and the same arithmetic as in `SupervisedTrainer` (identical results when the sampler has no
-    choice to make, see tests/test_gpu_model.py::test_pipelined_trainer_matches_plain_trainer).
+    """Software-pipelined, device-resident supervised loop (src/utils.py:141-191).
 
-        tr.submit(batch_0)            # primes the pipeline: prepares batch 0, returns None
-        loss_0 = tr.submit(batch_1)   # trains on batch 0 while preparing batch 1
-        ...
-        loss_k = tr.flush()           # trains on the last submitted batch
+    Sampling, unique/remap and the layer-1 aggregation of the raw features do not depend on the
+    weights (`GraphSage._run_prep`), so the graph of step n has TWO branches: the GEMMs / loss /
+    backward / exchange+update of batch n, and beside it the preparation of batch n+1 into the
+    other of two static frontier slots.  The HBM-bound gathers overlap the tensor-core and
+    latency-bound half; every batch still gets exactly the same work and arithmetic as in
+    `SupervisedTrainer` (identical results when the sampler has no choice to make, see
+    tests/test_gpu_model.py::test_pipelined_trainer_matches_plain_trainer).
 
-    The reference's loop knows all batches of an epoch up front (src/utils.py:127,141-145), so
-    looking one batch ahead changes nothing in its semantics."""
+    Batches come from a device-side QUEUE (the reference slices every batch of an epoch from one
+    shuffled array, src/utils.py:127,145): the preparation branch starts with gs_fetch_batch,
+    which copies the next row of the queued [rows x b_sz] array into its slot and advances the
+    cursor, so consecutive replays need no host work in between and two steps share one graph.
+
+        tr.set_queue(batches_int32_dev)        # or tr.feed(host_batch) per step (pinned H2D on a copy stream)
+        tr.prime()                             # prepares batch 0
+        loss = tr.run(n)                       # n steps: trains batch i while preparing batch i+1
+        loss = tr.flush()                      # trains on the last prepared batch
+    `submit` / `submit_device` / `step` keep the one-call-per-batch form on top of the same machinery."""
+
+    RING = 4          # rows of the internal staging ring used by feed()/submit()
 
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
@@ -212,12 +219,62 @@ class PipelinedTrainer(SupervisedTrainer):
         self.slot_seeds = [torch.zeros((self.b_sz,), dtype=torch.int32, device=dev) for _ in range(2)]
         self.slot_layers = [None, None]
         self.sample_counter = torch.zeros((1,), dtype=torch.int64, device=dev)
+        self.queue_desc = torch.zeros((3,), dtype=torch.int64, device=dev)        # {address, rows, next}
+        self._queue = None
+        self._ring = torch.zeros((self.RING, self.b_sz), dtype=torch.int32, device=dev)
+        self._ring_pinned = torch.zeros((self.RING, self.b_sz), dtype=torch.int32).pin_memory()
+        self._ring_events = [None] * self.RING
+        self._fed = 0                          # batches written into the ring so far
+        self._copy_stream = torch.cuda.Stream(device=dev)
         self._prep_stream = torch.cuda.Stream(device=dev)
-        self._graphs = [None, None]
-        self._cur: Optional[int] = None          # slot holding the prepared, not yet trained batch
+        self._graphs = [None, None]            # one step from slot 0 / slot 1
+        self._graph_pair = None                # two steps (slot 0 then slot 1) in one launch
+        self._cur: Optional[int] = None        # slot holding the prepared, not yet trained batch
+
+    # ---- batch queue --------------------------------------------------------------------------------
+    def set_queue(self, batches_dev: torch.Tensor):
+        """Queue an int32 [rows, b_sz] array resident in HBM; steps consume its rows in order (and wrap)."""
+        native.require_cuda(batches_dev, "batch queue")
+        if batches_dev.dtype != torch.int32 or batches_dev.dim() != 2 or batches_dev.shape[1] != self.b_sz \
+                or not batches_dev.is_contiguous():
+            raise ValueError(f"batch queue must be a contiguous int32 [rows, {self.b_sz}] tensor")
+        self._queue = batches_dev
+        desc = torch.tensor([batches_dev.data_ptr(), batches_dev.shape[0], 0], dtype=torch.int64)
+        self.queue_desc.copy_(desc.to(self.dev), non_blocking=False)
+
+    def feed(self, nodes_batch):
+        """Stage one HOST batch (numpy/list) for a later step: pinned copy + H2D on the copy stream
+        into the internal ring; the step that consumes it waits for the copy's event only."""
+        arr = np.asarray(nodes_batch)
+        if arr.shape[0] != self.b_sz:
+            raise ValueError(f"trainer was built for b_sz={self.b_sz}, got {arr.shape[0]}")
+        if self._queue is not self._ring:
+            torch.cuda.current_stream().synchronize()
+            self.set_queue(self._ring)
+            self._fed = 0
+        r = self._fed % self.RING
+        if self._ring_events[r] is not None:
+            self._ring_events[r].synchronize()            # the pinned row is free again
+        self._ring_pinned[r].numpy()[:] = arr
+        with torch.cuda.stream(self._copy_stream):
+            self._ring[r].copy_(self._ring_pinned[r], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        self._ring_events[r] = ev
+        torch.cuda.current_stream().wait_event(ev)
+        self._fed += 1
+
+    def feed_device(self, seeds_dev: torch.Tensor):
+        if self._queue is not self._ring:
+            torch.cuda.current_stream().synchronize()
+            self.set_queue(self._ring)
+            self._fed = 0
+        self._ring[self._fed % self.RING].copy_(seeds_dev, non_blocking=True)
+        self._fed += 1
 
     # ---- the two halves ---------------------------------------------------------------------------
     def _prep(self, slot: int):
+        ops.fetch_batch(self.queue_desc, self.b_sz, self.slot_seeds[slot])
         self.slot_layers[slot] = self.model._run_prep(self.slot_seeds[slot], None, offset_dev=self.sample_counter,
                                                       reuse=self.slot_layers[slot])
         self.sample_counter.add_(1)
@@ -258,14 +315,15 @@ class PipelinedTrainer(SupervisedTrainer):
     def _capture_pipeline(self):
         side = torch.cuda.Stream(device=self.dev)
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):            # warm-up: allocates both slots, loads modules; no update, counters restored
-            counter = self.sample_counter.clone()
+        with torch.cuda.stream(side):            # warm-up: allocates both slots, loads modules; no update, cursors restored
+            saved = (self.sample_counter.clone(), self.queue_desc.clone())
             self._prep(0)
             self._prep(1)
             for slot in (0, 1):
                 self._both(slot, update=False)
                 self.flat_grad.zero_()
-            self.sample_counter.copy_(counter)
+            self.sample_counter.copy_(saved[0])
+            self.queue_desc.copy_(saved[1])
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(self.dev)
         for slot in (0, 1):
@@ -275,48 +333,69 @@ class PipelinedTrainer(SupervisedTrainer):
                 self._both(slot)
             self._graphs[slot] = g
             self.launches_per_step = native.launch_count() - before
+        self._graph_pair = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph_pair):
+            self._both(0)
+            self._both(1)
         self.flat_grad.zero_()
 
     # ---- public ------------------------------------------------------------------------------------
-    def submit_device(self, seeds_dev: torch.Tensor) -> Optional[torch.Tensor]:
-        """Hand over the NEXT batch (int32 [b_sz] in HBM).  Trains on the previously submitted batch
-        (returns its device loss) while this one is prepared; the first call only prepares."""
+    def prime(self):
+        """Prepare the first queued batch (nothing to train on yet)."""
+        if self._queue is None:
+            raise RuntimeError("set_queue() or feed() a batch first")
         if self.use_graph and self._graphs[0] is None:
             self._capture_pipeline()
         if self._cur is None:
-            self.slot_seeds[0].copy_(seeds_dev, non_blocking=True)
             self._prep(0)
             self._cur = 0
-            return None
-        nxt = 1 - self._cur
-        self.slot_seeds[nxt].copy_(seeds_dev, non_blocking=True)
-        if self.use_graph:
-            self._graphs[self._cur].replay()
-        else:
-            before = native.launch_count()
-            self._both(self._cur)
-            self.launches_per_step = native.launch_count() - before
-        self._cur = nxt
+
+    def run(self, n: int = 1) -> torch.Tensor:
+        """n pipelined steps: step i trains on the prepared batch and prepares the next queued one.
+        Returns the device loss of the last trained batch."""
+        if self._cur is None:
+            raise RuntimeError("prime() the pipeline first")
+        while n > 0:
+            if self.use_graph and self._cur == 0 and n >= 2:
+                self._graph_pair.replay()
+                n -= 2
+                continue
+            if self.use_graph:
+                self._graphs[self._cur].replay()
+            else:
+                before = native.launch_count()
+                self._both(self._cur)
+                self.launches_per_step = native.launch_count() - before
+            self._cur = 1 - self._cur
+            n -= 1
         return self.loss
 
-    def submit(self, nodes_batch) -> Optional[torch.Tensor]:
-        """`submit_device` from a HOST batch (pinned staging copy + H2D inside the call)."""
-        arr = np.asarray(nodes_batch)
-        if arr.shape[0] != self.b_sz:
-            raise ValueError(f"trainer was built for b_sz={self.b_sz}, got {arr.shape[0]}")
-        self.seeds_pinned.numpy()[:] = arr
-        self.seeds.copy_(self.seeds_pinned, non_blocking=True)
-        return self.submit_device(self.seeds)
-
     def flush(self) -> Optional[torch.Tensor]:
-        """Train on the last submitted batch (nothing left to prepare)."""
+        """Train on the last prepared batch (nothing left to prepare)."""
         if self._cur is None:
             return None
         self._compute(self._cur)
         self._cur = None
         return self.loss
 
-    # the one-batch-at-a-time entry points of the base class keep their meaning
+    # one call per batch, on top of the queue: the batch handed over is the NEXT one
+    def submit_device(self, seeds_dev: torch.Tensor) -> Optional[torch.Tensor]:
+        """Hand over the next batch (int32 [b_sz] in HBM).  Trains on the previously submitted batch
+        (returns its device loss) while this one is prepared; the first call only prepares."""
+        self.feed_device(seeds_dev)
+        if self._cur is None:
+            self.prime()
+            return None
+        return self.run(1)
+
+    def submit(self, nodes_batch) -> Optional[torch.Tensor]:
+        """`submit_device` from a HOST batch (pinned staging + H2D on the copy stream)."""
+        self.feed(nodes_batch)
+        if self._cur is None:
+            self.prime()
+            return None
+        return self.run(1)
+
     def step_device(self, seeds_dev: torch.Tensor) -> torch.Tensor:
         self.submit_device(seeds_dev)
         return self.flush()

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 9
+#define GS_ABI_VERSION 10
 
 #define GS_OK 0
 #define GS_ERR_BAD_ARG (-1)
@@ -76,6 +76,12 @@ int gs_sample_neighbors(const int64_t* rowptr, const int32_t* col, int64_t num_n
                         int32_t k, int32_t stride, int32_t self_mode,
                         uint64_t seed, uint64_t offset, const int64_t* offset_dev,
                         int32_t* out_nbr, int32_t* out_cnt, gs_stream_t stream);
+
+/* Batch queue of the device-resident train loop (src/utils.py:141-145: every batch of an epoch
+ * is a slice of one shuffled id array).  queue_desc is 3 DEVICE int64: {address of an int32
+ * [rows x b_sz] array, rows, next}; copies row next % rows into dst and increments next -- a
+ * kernel of the step's graph, so back-to-back replays need no host-side copy between them. */
+int gs_fetch_batch(int64_t* queue_desc, int32_t b_sz, int32_t* dst, gs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * K2  unique + remap.  Replaces src/models.py:286-288 (set.union / dict(zip)) and the

@@ -40,3 +40,21 @@ def timeit(g, n=300):
 for name, g in (("prep", gP), ("compute", gC), ("both", gPC)):
     print(name, "us/replay", round(timeit(g), 1), flush=True)
 tr.dp.status()
+# ---- where do the 15 us between the probe (106) and the bench loop (121) go? ----
+g0, g1 = tr._graphs[0], tr._graphs[1]
+def loop(fn, n=400):
+    for _ in range(10): fn(0)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(n): fn(i)
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / n * 1e3
+print("same graph, no copy     ", round(loop(lambda i: g0.replay()), 1))
+print("alternating, no copy    ", round(loop(lambda i: (g0 if i & 1 else g1).replay()), 1))
+def with_copy(i):
+    tr.slot_seeds[i & 1].copy_(seeds[i % 64], non_blocking=True)
+    (g0 if i & 1 else g1).replay()
+print("alternating + seeds copy", round(loop(with_copy), 1))
+print("submit_device           ", round(loop(lambda i: tr.submit_device(seeds[i % 64])), 1))
+tr.dp.status()

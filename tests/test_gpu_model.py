@@ -314,12 +314,20 @@ def test_pipelined_trainer_matches_plain_trainer(M):
     labels = rng.integers(0, 5, size=n)
     batches = [rng.permutation(n)[:128] for _ in range(7)]
 
-    def run(kind, use_graph):
+    def run(kind, use_graph, queue=False):
         torch.manual_seed(3)
         model = M.GraphSage(2, 64, 32, feats, adj, dev, gcn=False, agg_func='MEAN', seed=11, precision='fp32').to(dev)
         cls = M.Classification(32, 5).to(dev)
         tr = kind(model, cls, labels, 128, use_graph=use_graph)
         losses = []
+        if queue:                                # device-resident queue: prime, 2+1+3 steps (pair graph and single graphs), flush
+            tr.set_queue(torch.from_numpy(np.stack(batches).astype(np.int32)).to(dev))
+            tr.prime()
+            for n_steps in (2, 1, 3):
+                tr.run(n_steps)
+            tr.flush()
+            tr.dp.status()
+            return None, [p.detach().clone() for p in list(model.parameters()) + list(cls.parameters())]
         if kind is PipelinedTrainer:
             for b in batches:
                 out = tr.submit(b)
@@ -333,8 +341,11 @@ def test_pipelined_trainer_matches_plain_trainer(M):
 
     base_l, base_p = run(SupervisedTrainer, True)
     assert base_l[-1] < base_l[0]
-    for kind, use_graph in ((PipelinedTrainer, True), (PipelinedTrainer, False), (SupervisedTrainer, False)):
-        l, p = run(kind, use_graph)
-        assert np.allclose(l, base_l, rtol=1e-5, atol=1e-6), (kind.__name__, use_graph, l, base_l)
+    for kind, use_graph, queue in ((PipelinedTrainer, True, False), (PipelinedTrainer, False, False),
+                                   (SupervisedTrainer, False, False), (PipelinedTrainer, True, True),
+                                   (PipelinedTrainer, False, True)):
+        l, p = run(kind, use_graph, queue)
+        if l is not None:
+            assert np.allclose(l, base_l, rtol=1e-5, atol=1e-6), (kind.__name__, use_graph, l, base_l)
         for a, b in zip(p, base_p):
-            assert rel(a, b) <= 1e-5, (kind.__name__, use_graph)
+            assert rel(a, b) <= 1e-5, (kind.__name__, use_graph, queue)
