@@ -202,70 +202,10 @@ def workload_config(args, cfg, rowptr, col, b_sz):
 # ------------------------------------------------------------------------------------------------
 # this repo
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        log(f"[bench] --gpus {args.gpus} but WORLD_SIZE {world}: using WORLD_SIZE")
-        args.gpus = world
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device: the gsage_b200 hot path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    import graphsage_b200  # noqa: F401
-    from graphsage_b200 import models, native, ops
-    from graphsage_b200.graph import AdjCSR
-    from graphsage_b200.trainer import PipelinedTrainer, SupervisedTrainer
-    import graphsage_b200.synth as synth
-    native.load()
-
-    if rank == 0:
-        cfg, rowptr, col, feats, labels, train = build_workload(args.scale)
-    if world > 1:
-        dist.barrier()
-    if rank != 0:
-        cfg, rowptr, col, feats, labels, train = build_workload(args.scale)      # from the cache rank 0 wrote
-    b_sz, K, W = args.b_sz, args.steps, args.warmup
-
-    torch.manual_seed(SEED)
-    feats_dev = torch.from_numpy(feats).to(dev)
-    adj = AdjCSR(rowptr, col)
-    model = models.GraphSage(2, cfg["feats"], cfg["hidden"], feats_dev, adj, dev, gcn=False, agg_func="MEAN",
-                             seed=SEED + rank, precision=args.precision).to(dev)
-    cls = models.Classification(cfg["hidden"], cfg["classes"]).to(dev)
-    wrng = np.random.default_rng(7)                                            # identical replicas on every rank
-    with torch.no_grad():
-        model.sage_layer1.weight.copy_(torch.from_numpy(synth.xavier_uniform_np(wrng, cfg["hidden"], 2 * cfg["feats"])))
-        model.sage_layer2.weight.copy_(torch.from_numpy(synth.xavier_uniform_np(wrng, cfg["hidden"], 2 * cfg["hidden"])))
-        cls.layer[0].weight.copy_(torch.from_numpy(synth.xavier_uniform_np(wrng, cfg["classes"], cfg["hidden"])))
-        cls.layer[0].bias.zero_()
-    pipelined = args.pipeline and args.exchange == "peer"
-    trainer = (PipelinedTrainer if pipelined else SupervisedTrainer)(
-        model, cls, labels, b_sz, lr=0.7, max_norm=5.0, use_graph=not args.no_graph, world_size=world, rank=rank,
-        exchange=args.exchange)
-    # pipelined: step i trains on batch i while batch i+1 is sampled/aggregated in a second graph branch --
-    # every timed step still does one full sampling+aggregation and one full fwd/bwd/update
-    host_batches = batches_for(train, b_sz, K + W + 1, rank, world)
-    dev_batches = torch.from_numpy(host_batches.astype(np.int32)).to(dev)
-
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def max_over_ranks(ms: float) -> float:
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---- device-resident arm ("value") ----
+def timed_arms(torch, native, trainer, pipelined, dev_batches, host_batches, K, W, rank, local, sync_all, max_over_ranks):
+    """The two timed regions shared by every workload.  Returns (ms_dev, loss_dev, launches, ms_e2e, last_loss, clocks).
+    dev arm ("value"): K steps with every batch already in HBM.  e2e arm: K steps from HOST numpy batches, with the
+    pinned H2D copy of each batch and the D2H read of each loss inside the timed region."""
     if pipelined:
         trainer.set_queue(dev_batches)                                         # the epoch's batches, resident in HBM
         trainer.prime()
@@ -339,6 +279,75 @@ def run_ours(args):
     if trainer.dp is not None:
         trainer.dp.status()                                                    # raises if a peer wait ever timed out
     clk = clocks.stop(t_begin, time.time()) if rank == 0 else None
+    return ms_dev, loss_dev, launches_timed, ms_e2e, last, clk
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        log(f"[bench] --gpus {args.gpus} but WORLD_SIZE {world}: using WORLD_SIZE")
+        args.gpus = world
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the gsage_b200 hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import graphsage_b200  # noqa: F401
+    from graphsage_b200 import models, native, ops
+    from graphsage_b200.graph import AdjCSR
+    from graphsage_b200.trainer import PipelinedTrainer, SupervisedTrainer
+    import graphsage_b200.synth as synth
+    native.load()
+
+    if rank == 0:
+        cfg, rowptr, col, feats, labels, train = build_workload(args.scale)
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        cfg, rowptr, col, feats, labels, train = build_workload(args.scale)      # from the cache rank 0 wrote
+    b_sz, K, W = args.b_sz, args.steps, args.warmup
+
+    torch.manual_seed(SEED)
+    feats_dev = torch.from_numpy(feats).to(dev)
+    adj = AdjCSR(rowptr, col)
+    model = models.GraphSage(2, cfg["feats"], cfg["hidden"], feats_dev, adj, dev, gcn=False, agg_func="MEAN",
+                             seed=SEED + rank, precision=args.precision).to(dev)
+    cls = models.Classification(cfg["hidden"], cfg["classes"]).to(dev)
+    wrng = np.random.default_rng(7)                                            # identical replicas on every rank
+    with torch.no_grad():
+        model.sage_layer1.weight.copy_(torch.from_numpy(synth.xavier_uniform_np(wrng, cfg["hidden"], 2 * cfg["feats"])))
+        model.sage_layer2.weight.copy_(torch.from_numpy(synth.xavier_uniform_np(wrng, cfg["hidden"], 2 * cfg["hidden"])))
+        cls.layer[0].weight.copy_(torch.from_numpy(synth.xavier_uniform_np(wrng, cfg["classes"], cfg["hidden"])))
+        cls.layer[0].bias.zero_()
+    pipelined = args.pipeline and args.exchange == "peer"
+    trainer = (PipelinedTrainer if pipelined else SupervisedTrainer)(
+        model, cls, labels, b_sz, lr=0.7, max_norm=5.0, use_graph=not args.no_graph, world_size=world, rank=rank,
+        exchange=args.exchange)
+    # pipelined: step i trains on batch i while batch i+1 is sampled/aggregated in a second graph branch --
+    # every timed step still does one full sampling+aggregation and one full fwd/bwd/update
+    host_batches = batches_for(train, b_sz, K + W + 1, rank, world)
+    dev_batches = torch.from_numpy(host_batches.astype(np.int32)).to(dev)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident arm ("value") ----
+    ms_dev, loss_dev, launches_timed, ms_e2e, last, clk = timed_arms(
+        torch, native, trainer, pipelined, dev_batches, host_batches, K, W, rank, local, sync_all, max_over_ranks)
 
     # ---- roofline of the dominant kernel: layer-1 aggregation, events around its launch ----
     roof = None
@@ -398,7 +407,7 @@ def run_cfg5(args):
     from graphsage_b200 import models, native, ops
     from graphsage_b200.graph import DeviceCSR
     from graphsage_b200.peer import ShardedTable
-    from graphsage_b200.trainer import SupervisedTrainer
+    from graphsage_b200.trainer import PipelinedTrainer, SupervisedTrainer
     import graphsage_b200.synth as synth
     native.load()
     n_per, dim, hidden, classes = int(args.cfg5_nodes_per_gpu), 128, 128, 47
@@ -421,9 +430,11 @@ def run_cfg5(args):
     model = models.GraphSage(2, dim, hidden, table, csr, dev, gcn=False, agg_func="MEAN", seed=SEED + rank,
                              precision=args.precision).to(dev)
     cls = models.Classification(hidden, classes).to(dev)
-    trainer = SupervisedTrainer(model, cls, labels, b_sz, lr=0.7, max_norm=5.0, use_graph=not args.no_graph,
-                                world_size=world, rank=rank, exchange=args.exchange)
-    dev_batches = torch.randint(0, n, (K + W, b_sz), generator=torch.Generator(device=dev).manual_seed(77 + rank),
+    pipelined = args.pipeline and args.exchange == "peer"
+    trainer = (PipelinedTrainer if pipelined else SupervisedTrainer)(
+        model, cls, labels, b_sz, lr=0.7, max_norm=5.0, use_graph=not args.no_graph, world_size=world, rank=rank,
+        exchange=args.exchange)
+    dev_batches = torch.randint(0, n, (K + W + 1, b_sz), generator=torch.Generator(device=dev).manual_seed(77 + rank),
                                 device=dev, dtype=torch.int32)
     host_batches = dev_batches.cpu().numpy().astype(np.int64)
 
@@ -439,43 +450,14 @@ def run_cfg5(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    for i in range(W):
-        trainer.step_device(dev_batches[i])
-    sync_all()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
-        time.sleep(0.25)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync_all()
-    t_begin = time.time()
-    e0.record()
-    for i in range(K):
-        trainer.step_device(dev_batches[W + i])
-    e1.record()
-    sync_all()
-    ms_dev = max_over_ranks(e0.elapsed_time(e1))
-    loss_dev = float(trainer.loss.item())
-    for i in range(min(W, 3)):
-        trainer.step(host_batches[i]).item()
-    sync_all()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    last = 0.0
-    for i in range(K):
-        last = trainer.step(host_batches[W + i]).item()
-    e3.record()
-    sync_all()
-    ms_e2e = max_over_ranks(e2.elapsed_time(e3))
-    clk = clocks.stop(t_begin, time.time()) if rank == 0 else None
-    if trainer.dp is not None:
-        trainer.dp.status()
+    ms_dev, loss_dev, _, ms_e2e, last, clk = timed_arms(
+        torch, native, trainer, pipelined, dev_batches, host_batches, K, W, rank, local, sync_all, max_over_ranks)
 
     # ---- the sharded gather kernel alone: events around back-to-back launches on distinct frontiers ----
     weights = [w.detach() for w in trainer.weights]
     fronts, bytes_, remote_ = [], [], []
     for i in range(min(8, K + W)):
-        fr = model._run_forward(dev_batches[i], weights, None)[0]
+        fr = model._run_forward(dev_batches[i].contiguous(), weights, None)[0]
         rows = int(fr.num_rows.item())
         ids = fr.nbr[:rows]
         nnz = int((ids >= 0).sum().item())

@@ -170,11 +170,21 @@ cls_fused_kernel(const float* __restrict__ emb, int64_t ld_emb, int rows, int di
   // ---- logits of my row: lane owns classes `lane` and `lane + 32` ----
   const float* e = e_s + warp * dim;
   float a0 = 0.f, a1 = 0.f;
-#pragma unroll 4
-  for (int k = 0; k < dim; ++k) {
-    const float x = e[k];
-    a0 = fmaf(x, wt_s[k * cp + lane], a0);
-    a1 = fmaf(x, wt_s[k * cp + lane + 32], a1);
+  {
+    // dim % 4 == 0: four independent partial sums per class shorten the FMA dependency chain; they are
+    // combined pairwise, so the result differs from a serial dot product only by fp32 rounding order
+    float p0[4] = {0.f, 0.f, 0.f, 0.f}, p1[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < dim; k += 4) {
+      const float4 x = *reinterpret_cast<const float4*>(e + k);
+      const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        p0[j] = fmaf(xs[j], wt_s[(k + j) * cp + lane], p0[j]);
+        p1[j] = fmaf(xs[j], wt_s[(k + j) * cp + lane + 32], p1[j]);
+      }
+    }
+    a0 = (p0[0] + p0[1]) + (p0[2] + p0[3]);
+    a1 = (p1[0] + p1[1]) + (p1[2] + p1[3]);
   }
   const bool v0 = lane < classes, v1 = lane + 32 < classes;
   if (bias) { if (v0) a0 += bias[lane]; if (v1) a1 += bias[lane + 32]; }

@@ -114,10 +114,14 @@ dp_update_kernel(float* __restrict__ flat, long long n_total, const DpPeers peer
       st_release_sys(peers.flags[tid] + me * kDpMaxCtas + c, e);
       // ---- wait for peer `tid`'s copy of slice c ----
       const uint32_t* f = peers.flags[me] + tid * kDpMaxCtas + c;
-      const unsigned long long t0 = global_ns();
-      while (static_cast<int>(ld_acquire_sys(f) - e) < 0) {
-        if (global_ns() - t0 > timeout_ns) { atomicExch(&st->status, 1u); break; }
-        __nanosleep(64);
+      unsigned long long t0 = 0;
+      for (unsigned spins = 0; static_cast<int>(ld_acquire_sys(f) - e) < 0; ++spins) {
+        if ((spins & 63u) == 63u) {                        // the timer is only consulted once the wait is long
+          const unsigned long long now = global_ns();
+          if (t0 == 0) t0 = now;
+          if (now - t0 > timeout_ns) { atomicExch(&st->status, 1u); break; }
+          __nanosleep(64);
+        }
       }
     }
     __syncthreads();
@@ -164,9 +168,13 @@ dp_update_kernel(float* __restrict__ flat, long long n_total, const DpPeers peer
   if (tid == 0) {
     atomicAdd(&st->arrive, 1ULL);
     const unsigned long long target = static_cast<unsigned long long>(e) * static_cast<unsigned long long>(G);
-    const unsigned long long t0 = global_ns();
-    while (ld_acquire_gpu_u64(&st->arrive) < target) {
-      if (global_ns() - t0 > timeout_ns) { atomicExch(&st->status, 2u); break; }
+    unsigned long long t0 = 0;
+    for (unsigned spins = 0; ld_acquire_gpu_u64(&st->arrive) < target; ++spins) {
+      if ((spins & 255u) == 255u) {
+        const unsigned long long now = global_ns();
+        if (t0 == 0) t0 = now;
+        if (now - t0 > timeout_ns) { atomicExch(&st->status, 2u); break; }
+      }
     }
   }
   __syncthreads();
