@@ -568,7 +568,26 @@ def measure_agg_roofline(torch, ops, native, model, trainer, dev_batches, W, K, 
         b.record()
         torch.cuda.synchronize(dev)
         singles.append(a.elapsed_time(b) * 1e-3)
-    times = [t_batch]
+    # (1b) the same chain replayed from a CUDA graph -- how the product launches it (the step is one graph)
+    t_graph = None
+    if trainer.use_graph:
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for fr, out in fronts:
+                    launch(fr, out)
+            g.replay()
+            torch.cuda.synchronize(dev)
+            reps = 5
+            a.record()
+            for _ in range(reps):
+                g.replay()
+            b.record()
+            torch.cuda.synchronize(dev)
+            t_graph = a.elapsed_time(b) * 1e-3 / (reps * n_iter)
+        except Exception as exc:
+            log(f"[bench] graph-replayed roofline chain failed: {exc!r}")
+    times = [t_graph if t_graph is not None else t_batch]
     # (3) the same kernel at a saturating size: frontier of 8 x b_sz seeds (~85K rows, ~390 MB gathered)
     big = None
     try:
@@ -602,13 +621,16 @@ def measure_agg_roofline(torch, ops, native, model, trainer, dev_batches, W, K, 
             traffic, traffic_src = float(t["dram_bytes_per_launch"]), t.get("source")
         except Exception:
             pass
-    kname = "agg_fwd_pipe_kernel<MEAN>" if os.environ.get("GS_AGG_IMPL", "").startswith("p") else "agg_fwd_kernel<MEAN>"
+    kname = "agg_fwd_kernel<MEAN>"
     return {"bound": "hbm", "kernel": f"{kname} (layer 1, gs_agg_fwd)", "achieved": achieved, "peak": peak,
             "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": peak_src,
             "bytes_per_launch": float(np.mean(bytes_)), "us_per_launch": float(np.mean(times) * 1e6),
             "saturating_size": big, "launches_timed": n_iter, "us_per_launch_single_event_pair": float(np.mean(singles) * 1e6),
-            "note": "achieved = algorithmic bytes / (CUDA-event time of n back-to-back launches on distinct frontiers / n)"}
+            "us_per_launch_eager_chain": float(t_batch * 1e6),
+            "us_per_launch_graph_chain": None if t_graph is None else float(t_graph * 1e6),
+            "note": "achieved = algorithmic bytes / (CUDA-event time of a chain of n back-to-back launches on distinct "
+                    "frontiers / n); the chain is replayed from a CUDA graph like the product's step (eager chain beside it)"}
 
 
 def main():
