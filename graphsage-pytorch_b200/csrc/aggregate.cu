@@ -106,12 +106,26 @@ agg_fwd_kernel(const float* __restrict__ table, uint32_t ld_bytes, int dim4,
 // Backward.  MEAN: every gathered row receives grad/cnt (vector red.add, 16 B per lane);
 // MAX: only the winning row per element.  The self-row gather of src/models.py:265 is the
 // same scatter with weight 1, folded in here so layer l's input gradient is one launch.
+// mask_table (nullable) = the ReLU output h the scattered-into rows came from (src/models.py:219):
+// a contribution to element (u, c) is dropped when h[u, c] <= 0.  The mask depends only on the
+// destination element, so masking every contribution equals masking the sum -- the separate
+// d(relu) pass over grad_table (one launch on the critical path of the step) disappears.
+__device__ __forceinline__ void scatter_add4(float* __restrict__ grad_table, int64_t ld_gt, const float* __restrict__ mask_table,
+                                             int64_t ld_mask, int row, int c4, float4 g) {
+  if (mask_table != nullptr) {
+    const float4 h = __ldg(reinterpret_cast<const float4*>(mask_table + static_cast<int64_t>(row) * ld_mask + 4 * c4));
+    g.x = h.x > 0.f ? g.x : 0.f; g.y = h.y > 0.f ? g.y : 0.f; g.z = h.z > 0.f ? g.z : 0.f; g.w = h.w > 0.f ? g.w : 0.f;
+  }
+  atomicAdd(reinterpret_cast<float4*>(grad_table + static_cast<int64_t>(row) * ld_gt + 4 * c4), g);
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kAggWarps * 32)
 agg_bwd_kernel(const float* __restrict__ grad_agg, int64_t ld_ga, const float* __restrict__ grad_self, int64_t ld_gs,
                int dim4, const int32_t* __restrict__ nbr, int stride, const int32_t* __restrict__ cnt,
                const int32_t* __restrict__ self_idx, const int32_t* __restrict__ argmax, int64_t ld_arg,
-               const int32_t* __restrict__ num_rows_dev, int max_rows, float* __restrict__ grad_table, int64_t ld_gt) {
+               const int32_t* __restrict__ num_rows_dev, int max_rows, float* __restrict__ grad_table, int64_t ld_gt,
+               const float* __restrict__ mask_table, int64_t ld_mask) {
   pdl_sync();
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * kAggWarps + (threadIdx.x >> 5);
@@ -126,7 +140,7 @@ agg_bwd_kernel(const float* __restrict__ grad_agg, int64_t ld_ga, const float* _
     const bool active = c4 < dim4;
     if (me >= 0 && active) {
       const float4 g = *reinterpret_cast<const float4*>(grad_self + static_cast<int64_t>(r) * ld_gs + 4 * c4);
-      atomicAdd(reinterpret_cast<float4*>(grad_table + static_cast<int64_t>(me) * ld_gt + 4 * c4), g);
+      scatter_add4(grad_table, ld_gt, mask_table, ld_mask, me, c4, g);
     }
     if (grad_agg == nullptr) continue;
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -138,16 +152,18 @@ agg_bwd_kernel(const float* __restrict__ grad_agg, int64_t ld_ga, const float* _
         const int here = min(32, n - jc);
         for (int j = 0; j < here; ++j) {
           const int id = __shfl_sync(0xffffffffu, mine, j);
-          if (active && id >= 0)
-            atomicAdd(reinterpret_cast<float4*>(grad_table + static_cast<int64_t>(id) * ld_gt + 4 * c4), g);
+          if (active && id >= 0) scatter_add4(grad_table, ld_gt, mask_table, ld_mask, id, c4, g);
         }
       }
     } else if (active) {
       const int4 a = *reinterpret_cast<const int4*>(argmax + static_cast<int64_t>(r) * ld_arg + 4 * c4);
-      if (a.x >= 0) atomicAdd(grad_table + static_cast<int64_t>(a.x) * ld_gt + 4 * c4 + 0, g.x);
-      if (a.y >= 0) atomicAdd(grad_table + static_cast<int64_t>(a.y) * ld_gt + 4 * c4 + 1, g.y);
-      if (a.z >= 0) atomicAdd(grad_table + static_cast<int64_t>(a.z) * ld_gt + 4 * c4 + 2, g.z);
-      if (a.w >= 0) atomicAdd(grad_table + static_cast<int64_t>(a.w) * ld_gt + 4 * c4 + 3, g.w);
+      auto on = [&](int row, int j) -> bool {      // the winning row's ReLU output decides (MAX: one row per element)
+        return row >= 0 && (mask_table == nullptr || __ldg(mask_table + static_cast<int64_t>(row) * ld_mask + 4 * c4 + j) > 0.f);
+      };
+      if (on(a.x, 0)) atomicAdd(grad_table + static_cast<int64_t>(a.x) * ld_gt + 4 * c4 + 0, g.x);
+      if (on(a.y, 1)) atomicAdd(grad_table + static_cast<int64_t>(a.y) * ld_gt + 4 * c4 + 1, g.y);
+      if (on(a.z, 2)) atomicAdd(grad_table + static_cast<int64_t>(a.z) * ld_gt + 4 * c4 + 2, g.z);
+      if (on(a.w, 3)) atomicAdd(grad_table + static_cast<int64_t>(a.w) * ld_gt + 4 * c4 + 3, g.w);
     }
   }
 }
@@ -300,7 +316,8 @@ extern "C" int gs_agg_fwd(const float* table, int64_t ld, int32_t dim, const int
 extern "C" int gs_agg_bwd(const float* grad_agg, int64_t ld_ga, const float* grad_self, int64_t ld_gs, int32_t dim,
                           const int32_t* nbr, int32_t stride, const int32_t* cnt, const int32_t* self_idx,
                           const int32_t* argmax, int64_t ld_arg, const int32_t* num_rows_dev, int32_t max_rows,
-                          int32_t mode, float* grad_table, int64_t ld_gt, gs_stream_t stream) {
+                          int32_t mode, float* grad_table, int64_t ld_gt, const float* mask_table, int64_t ld_mask,
+                          gs_stream_t stream) {
   if (!grad_table || dim < 1 || max_rows < 0) return GS_ERR_BAD_ARG;
   if (!grad_agg && !grad_self) return GS_ERR_BAD_ARG;
   if (grad_agg && (!nbr || !cnt || stride < 1)) return GS_ERR_BAD_ARG;
@@ -311,17 +328,18 @@ extern "C" int gs_agg_bwd(const float* grad_agg, int64_t ld_ga, const float* gra
   if (grad_agg && ((ld_ga & 3) || ld_ga < 4 * dim4 || !aligned16(grad_agg))) return GS_ERR_ALIGNMENT;
   if (grad_self && ((ld_gs & 3) || ld_gs < 4 * dim4 || !aligned16(grad_self))) return GS_ERR_ALIGNMENT;
   if (grad_agg && mode == GS_AGG_MAX && ((ld_arg & 3) || ld_arg < 4 * dim4 || !aligned16(argmax))) return GS_ERR_ALIGNMENT;
+  if (mask_table && ((ld_mask & 3) || ld_mask < 4 * dim4 || !aligned16(mask_table))) return GS_ERR_ALIGNMENT;
   if (max_rows == 0) return GS_OK;
   // a dummy index list keeps the kernel's pointer arithmetic valid when only grad_self is scattered
   const int blocks = (max_rows + kAggWarps - 1) / kAggWarps;
   if (mode == GS_AGG_MEAN)
     launch(agg_bwd_kernel<GS_AGG_MEAN>, blocks, kAggWarps * 32, 0, as_stream(stream), 
         grad_agg, ld_ga, grad_self, ld_gs, dim4, nbr, stride, cnt, self_idx, argmax, ld_arg, num_rows_dev, max_rows,
-        grad_table, ld_gt);
+        grad_table, ld_gt, mask_table, ld_mask);
   else
     launch(agg_bwd_kernel<GS_AGG_MAX>, blocks, kAggWarps * 32, 0, as_stream(stream), 
         grad_agg, ld_ga, grad_self, ld_gs, dim4, nbr, stride, cnt, self_idx, argmax, ld_arg, num_rows_dev, max_rows,
-        grad_table, ld_gt);
+        grad_table, ld_gt, mask_table, ld_mask);
   return finish_launch();
 }
 

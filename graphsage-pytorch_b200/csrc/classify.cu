@@ -269,11 +269,12 @@ extern "C" int gs_cls_nll_fwd_bwd(const float* emb, int64_t ld_emb, int32_t rows
                                   const int64_t* labels, const int32_t* label_index,
                                   float* logp, float* loss, float* grad_emb, int64_t ld_ge,
                                   float* grad_w, float* grad_b, float* scratch, int32_t mask_relu_input,
-                                  int32_t precision, gs_stream_t stream) {
+                                  int32_t zero_loss, int32_t precision, gs_stream_t stream) {
   if (!emb || !weight || !labels || !logp || !loss || !scratch || rows < 1 || dim < 1 || num_classes < 1)
     return GS_ERR_BAD_ARG;
   cudaStream_t st = as_stream(stream);
-  cudaError_t ce = cudaMemsetAsync(loss, 0, sizeof(float), st);
+  cudaError_t ce = cudaSuccess;
+  if (zero_loss) ce = cudaMemsetAsync(loss, 0, sizeof(float), st);     // 0: the caller zeroed it off the critical path
   if (ce != cudaSuccess) return static_cast<int>(ce);
   // small heads (every configuration of the reference: 3..47 classes, 128 features): one fused launch
   const bool fused_ok = num_classes <= kClsMaxC && dim <= kClsMaxD && (dim & 3) == 0 && (ld_emb & 3) == 0 &&

@@ -30,7 +30,10 @@ namespace tc {
 
 constexpr int kTileM = 128;
 constexpr int kBK = 32;                                  // tf32 elements per k-stage: 128 bytes, one swizzle row
-constexpr int kProducerWarps = 8;
+#ifndef GS_TC_PRODUCER_WARPS
+#define GS_TC_PRODUCER_WARPS 16
+#endif
+constexpr int kProducerWarps = GS_TC_PRODUCER_WARPS;     // multiple of 4 (TMEM lane quadrants), divides 32
 constexpr int kProducerThreads = kProducerWarps * 32;
 constexpr int kThreads = kProducerThreads + 32;          // producers/epilogue + MMA/TMEM warp
 constexpr int kMaxStages = 4;
@@ -522,7 +525,7 @@ __device__ __forceinline__ void gemm_core(const LoadA& load_a, const LoadB& load
   if (warp < kProducerWarps) {
     const int a_chunks = chunks_in_tile(kTileM, A_MN);
     const int b_chunks = chunks_in_tile(n_tile, B_MN);
-    constexpr int kMaxA = 4, kMaxB = 8;           // 1024 / 256 and 2048 / 256 pieces per thread
+    constexpr int kMaxA = 1024 / kProducerThreads, kMaxB = 2048 / kProducerThreads;   // 16-byte pieces per thread
     if (ASYNC) {
       // ================= producers, asynchronous path: cp.async ring, num_stages - 1 stages ahead =================
       const int ahead = num_stages - 1;            // 0 only if a single stage fits (then load and compute alternate)
@@ -675,7 +678,7 @@ __device__ __forceinline__ void gemm_core(const LoadA& load_a, const LoadB& load
     const int n_chunks = (n_tile + 31) / 32;
     const int ldst = n_tile + 4;                   // floats per staged row (+4: rows land on different banks)
     float* stg = reinterpret_cast<float*>(smem_al);
-    for (int c = warp >> 2; c < n_chunks; c += 2) {
+    for (int c = warp >> 2; c < n_chunks; c += kProducerWarps / 4) {
       uint32_t v[32];
       tmem_ld32(tmem_acc + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(c * 32), v);
       float* dst = stg + m * ldst + c * 32;

@@ -399,14 +399,17 @@ class GraphSage(nn.Module):
 
     def _run_backward(self, layers: List[_Frontier], grad_out: torch.Tensor, weights, needs,
                       grad_bufs=None, own_grad: bool = False, top_masked: bool = False,
-                      side_stream: Optional[torch.cuda.Stream] = None) -> List[Optional[torch.Tensor]]:
+                      side_stream: Optional[torch.cuda.Stream] = None,
+                      scatter_bufs: Optional[Sequence[Optional[torch.Tensor]]] = None) -> List[Optional[torch.Tensor]]:
         """Weight gradients of all layers.  `grad_bufs` (optional, pre-zeroed) receive them in
         place (static buffers of the captured train step); otherwise fresh tensors are returned.
         `own_grad`: grad_out is a scratch buffer of the caller and may be overwritten.
         `top_masked`: grad_out already carries the last layer's ReLU mask (gs_cls_nll_fwd_bwd).
         `side_stream`: the weight-gradient GEMM of every layer but the first is a leaf of the
         dependency graph (nothing downstream reads dW); with a side stream it runs beside the
-        dX -> scatter chain instead of in front of it (a fork/join when captured into a CUDA graph)."""
+        dX -> scatter chain instead of in front of it (a fork/join when captured into a CUDA graph).
+        `scatter_bufs[i]` (optional): ZEROED [layers[i].rows_max x pad4(H)] buffer that receives the gradient
+        w.r.t. layer i+1's output (see `zeroed_scatter_bufs`); without it the fill runs in line."""
         L, H = self.num_layers, self.out_size
         mode = native.AGG_MEAN if self.agg_func == 'MEAN' else native.AGG_MAX
         prec = _PRECISIONS[self.precision]
@@ -421,10 +424,11 @@ class GraphSage(nn.Module):
         lowest = min((i for i in range(L) if needs[i]), default=None)
         if lowest is None:
             return grads
+        masked = top_masked              # g already carries the ReLU mask of the layer it belongs to
         for l in range(L, 0, -1):
             fr = layers[l - 1]
             w = weights[l - 1]
-            if premask and not (top_masked and l == L):
+            if premask and not masked:
                 ops.relu_bwd_inplace(g, fr.h, H, fr.num_rows, fr.rows_max)
             if needs[l - 1]:
                 gw = torch.zeros_like(w) if grad_bufs is None else grad_bufs[l - 1]
@@ -446,13 +450,26 @@ class GraphSage(nn.Module):
             gs, ga = ops.sage_gemm_bwd_x(g, fr.h, w, fr.dim_in, H, self.gcn, not premask, fr.num_rows, fr.rows_max,
                                          precision=prec)
             prev = layers[l - 2]
-            g_prev = torch.zeros((prev.rows_max, ops.pad4(H)), dtype=torch.float32, device=g.device)
+            if scatter_bufs is not None and scatter_bufs[l - 2] is not None:
+                g_prev = scatter_bufs[l - 2]         # zero-filled by the caller, off the critical path
+            else:
+                g_prev = torch.zeros((prev.rows_max, ops.pad4(H)), dtype=torch.float32, device=g.device)
+            # tensor-core path: the scatter applies layer l-1's ReLU mask itself (mask_table = its output)
             ops.agg_bwd(ga, gs, fr.dim_in, fr.nbr_idx, fr.stride, fr.cnt, fr.self_idx, fr.argmax, fr.num_rows,
-                        fr.rows_max, mode, g_prev)
+                        fr.rows_max, mode, g_prev, mask_table=prev.h if premask else None)
+            masked = premask
             g = g_prev
         if forked:
             torch.cuda.current_stream().wait_stream(side_stream)
         return grads
+
+    def zeroed_scatter_bufs(self, layers: List[_Frontier]) -> List[Optional[torch.Tensor]]:
+        """Zero-filled targets of the backward scatters (one per layer below the top), allocated on the
+        current stream: a trainer calls this on a side stream at the start of the step so the fills run
+        beside the forward GEMMs instead of between bwd_x and the scatter."""
+        H = self.out_size
+        return [torch.zeros((fr.rows_max, ops.pad4(H)), dtype=torch.float32, device=fr.nodes.device)
+                for fr in layers[:-1]] + [None]
 
     # ---- compatibility methods of the reference (slow paths, host round trips) ------------------
     def _get_unique_neighs_list(self, nodes, num_sample=10):                  # :277-289

@@ -144,12 +144,15 @@ def agg_fwd_sharded(table, nbr, stride: int, cnt, self_nodes, num_rows, max_rows
 
 
 def agg_bwd(grad_agg, grad_self, dim: int, nbr, stride: int, cnt, self_idx, argmax, num_rows, max_rows: int,
-            mode: int, grad_table):
+            mode: int, grad_table, mask_table=None):
+    """Scatter backward of K3 (+ self rows).  `mask_table`: ReLU output of the rows scattered into;
+    with it grad_table receives d(pre-activation) and no separate relu_bwd pass is needed."""
     check(_lib().gs_agg_bwd(ptr(grad_agg), grad_agg.stride(0) if grad_agg is not None else 0,
                             ptr(grad_self), grad_self.stride(0) if grad_self is not None else 0, dim,
                             ptr(nbr), stride, ptr(cnt), ptr(self_idx), ptr(argmax),
                             argmax.stride(0) if argmax is not None else 0, ptr(num_rows), max_rows, mode,
-                            ptr(grad_table), grad_table.stride(0), stream()), "gs_agg_bwd")
+                            ptr(grad_table), grad_table.stride(0), ptr(mask_table),
+                            mask_table.stride(0) if mask_table is not None else 0, stream()), "gs_agg_bwd")
     return grad_table
 
 
@@ -240,8 +243,10 @@ def nll_fwd_bwd(logp, labels, loss=None, grad_logp=None, want_grad=True, label_i
 
 
 def cls_nll_fwd_bwd(emb, dim: int, weight, bias, num_classes: int, labels, label_index, loss, grad_emb, grad_w, grad_b,
-                    logp=None, scratch=None, precision: int = native.PREC_TF32X3, mask_relu_input: bool = False):
-    """Classifier + NLL(mean) forward and backward in one call (src/models.py:25-27, src/utils.py:153,162-163)."""
+                    logp=None, scratch=None, precision: int = native.PREC_TF32X3, mask_relu_input: bool = False,
+                    zero_loss: bool = True):
+    """Classifier + NLL(mean) forward and backward in one call (src/models.py:25-27, src/utils.py:153,162-163).
+    `zero_loss=False`: the caller zeroed `loss` already (a trainer does it beside the forward GEMMs)."""
     rows = emb.shape[0]
     if logp is None:
         logp = torch.empty((rows, num_classes), dtype=F32, device=emb.device)
@@ -250,7 +255,8 @@ def cls_nll_fwd_bwd(emb, dim: int, weight, bias, num_classes: int, labels, label
     check(_lib().gs_cls_nll_fwd_bwd(ptr(emb), emb.stride(0), rows, dim, ptr(weight), ptr(bias), num_classes, ptr(labels),
                                     ptr(label_index), ptr(logp), ptr(loss), ptr(grad_emb),
                                     grad_emb.stride(0) if grad_emb is not None else 0, ptr(grad_w), ptr(grad_b),
-                                    ptr(scratch), int(mask_relu_input), precision, stream()), "gs_cls_nll_fwd_bwd")
+                                    ptr(scratch), int(mask_relu_input), int(zero_loss), precision, stream()),
+          "gs_cls_nll_fwd_bwd")
     return logp
 
 

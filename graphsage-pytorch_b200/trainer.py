@@ -57,6 +57,22 @@ def shard_batches(train: np.ndarray, b_sz: int, steps: int, rank: int, world: in
     return np.ascontiguousarray(perm[:need].reshape(steps, world, b_sz)[:, rank, :])
 
 
+def _zero_beside(side: torch.cuda.Stream, loss: torch.Tensor, model: GraphSage, layers):
+    """Fork: zero the loss accumulator and the backward's scatter targets on `side` while the forward
+    GEMMs run on the current stream.  Returns (scatter_bufs, event to wait on before the loss kernel)."""
+    main = torch.cuda.current_stream()
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        loss.zero_()
+        bufs = model.zeroed_scatter_bufs(layers)
+        ev = torch.cuda.Event()
+        ev.record(side)
+    for b in bufs:
+        if b is not None:
+            b.record_stream(main)
+    return bufs, ev
+
+
 class SupervisedTrainer:
     def __init__(self, model: GraphSage, classifier: Classification, labels, b_sz: int, *, lr: float = 0.7,
                  max_norm: float = 5.0, use_graph: bool = True, process_group=None, world_size: int = 1,
@@ -103,17 +119,20 @@ class SupervisedTrainer:
     def _forward_backward(self):
         m, c = self.model, self.classifier
         weights = [w.detach() for w in self.weights]
-        layers = m._run_forward(self.seeds, weights, None, offset_dev=self.step_counter)
+        layers = m._run_prep(self.seeds, None, offset_dev=self.step_counter)
+        scatter_bufs, zeroed = _zero_beside(self._side, self.loss, m, layers)
+        layers = m._run_compute(layers, weights)
         self.last_layers = layers
         emb = layers[-1].h
         classes = self.cls_w.shape[0]
         gemb = torch.empty_like(emb)
         n_sage = len(self.weights)
+        torch.cuda.current_stream().wait_event(zeroed)
         ops.cls_nll_fwd_bwd(emb, m.out_size, self.cls_w.detach(), self.cls_b.detach(), classes, self.labels, self.seeds,
                             self.loss, gemb, self.grads[n_sage], self.grads[n_sage + 1],
-                            precision=_PRECISIONS[m.precision], mask_relu_input=True)          # utils.py:153,161-163
+                            precision=_PRECISIONS[m.precision], mask_relu_input=True, zero_loss=False)   # utils.py:153,161-163
         m._run_backward(layers, gemb, weights, [True] * n_sage, grad_bufs=self.grads[:n_sage], own_grad=True,
-                        top_masked=True, side_stream=self._side)
+                        top_masked=True, side_stream=self._side, scatter_bufs=scatter_bufs)
         if self.dp is None:
             self.step_counter.add_(1)        # the fused update kernel bumps it otherwise
 
@@ -282,16 +301,18 @@ class PipelinedTrainer(SupervisedTrainer):
     def _compute(self, slot: int, update: bool = True):
         m = self.model
         weights = [w.detach() for w in self.weights]
+        scatter_bufs, zeroed = _zero_beside(self._side, self.loss, m, self.slot_layers[slot])
         layers = m._run_compute(self.slot_layers[slot], weights)
         self.last_layers = layers
         emb = layers[-1].h
         gemb = torch.empty_like(emb)
         n_sage = len(self.weights)
+        torch.cuda.current_stream().wait_event(zeroed)
         ops.cls_nll_fwd_bwd(emb, m.out_size, self.cls_w.detach(), self.cls_b.detach(), self.cls_w.shape[0], self.labels,
                             self.slot_seeds[slot], self.loss, gemb, self.grads[n_sage], self.grads[n_sage + 1],
-                            precision=_PRECISIONS[m.precision], mask_relu_input=True)
+                            precision=_PRECISIONS[m.precision], mask_relu_input=True, zero_loss=False)
         m._run_backward(layers, gemb, weights, [True] * n_sage, grad_bufs=self.grads[:n_sage], own_grad=True,
-                        top_masked=True, side_stream=self._side)
+                        top_masked=True, side_stream=self._side, scatter_bufs=scatter_bufs)
         if update:
             self.dp.update(self.max_norm, self.lr, None)
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 10
+#define GS_ABI_VERSION 11
 
 #define GS_OK 0
 #define GS_ERR_BAD_ARG (-1)
@@ -125,11 +125,13 @@ int gs_agg_fwd(const float* table, int64_t ld, int32_t dim,
  *   grad_table[nbr[r][j], :] += grad_agg[r, :] / cnt[r]          (MEAN)
  *   grad_table[argmax[r][c], c] += grad_agg[r, c]                (MAX)
  *   grad_table[self_idx[r], :] += grad_self[r, :]                (when grad_self != NULL)
- * grad_table must be zeroed by the caller. */
+ * grad_table must be zeroed by the caller.  mask_table (nullable, [table rows x ld_mask]) is the
+ * ReLU output the table rows were produced with (src/models.py:219): contributions to elements
+ * whose output was <= 0 are dropped, i.e. grad_table receives d(pre-activation) directly. */
 int gs_agg_bwd(const float* grad_agg, int64_t ld_ga, const float* grad_self, int64_t ld_gs, int32_t dim,
                const int32_t* nbr, int32_t stride, const int32_t* cnt, const int32_t* self_idx,
                const int32_t* argmax, int64_t ld_arg, const int32_t* num_rows_dev, int32_t max_rows, int32_t mode,
-               float* grad_table, int64_t ld_gt, gs_stream_t stream);
+               float* grad_table, int64_t ld_gt, const float* mask_table, int64_t ld_mask, gs_stream_t stream);
 
 /* K3 forward over a ROW-PARTITIONED bf16 feature table (BASELINE.json configs[4]: features
  * split by contiguous node-id blocks across the GPUs of one box).  shard_bases_host is a HOST
@@ -200,13 +202,15 @@ int gs_nll_fwd_bwd(const float* logp, const int64_t* labels, const int32_t* labe
  * d logits + grad_b -> grad_w GEMM -> grad_emb GEMM.  loss[0] is overwritten; grad_w / grad_b
  * accumulate (zero them first); grad_emb (nullable) is overwritten; scratch: rows*num_classes
  * floats.  mask_relu_input != 0: emb is the ReLU output of the last SageLayer
- * (src/models.py:219) and grad_emb is returned already multiplied by (emb > 0). */
+ * (src/models.py:219) and grad_emb is returned already multiplied by (emb > 0).
+ * zero_loss == 0: loss[0] was zeroed by the caller (off the critical path of a captured step)
+ * and is accumulated into; != 0: it is zeroed here first. */
 int gs_cls_nll_fwd_bwd(const float* emb, int64_t ld_emb, int32_t rows, int32_t dim,
                        const float* weight, const float* bias, int32_t num_classes,
                        const int64_t* labels, const int32_t* label_index,
                        float* logp, float* loss, float* grad_emb, int64_t ld_ge,
-                       float* grad_w, float* grad_b, float* scratch, int32_t mask_relu_input, int32_t precision,
-                       gs_stream_t stream);
+                       float* grad_w, float* grad_b, float* scratch, int32_t mask_relu_input, int32_t zero_loss,
+                       int32_t precision, gs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Update step of src/utils.py:185-187: per-model clip_grad_norm_(max_norm) then SGD.

@@ -462,6 +462,13 @@ int main(int argc, char** argv) {
   const int ld = (argc > 1) ? atoi(argv[1]) : 100;       // floats per table row (100 = shipped layout)
   const int dim4 = dim / 4;
   const uint32_t ld_bytes = ld * 4;
+  if (argc > 2) {
+    size_t g = 0;
+    cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, atoi(argv[2]));
+    cudaDeviceGetLimit(&g, cudaLimitMaxL2FetchGranularity);
+    printf("L2 fetch granularity: requested %s -> %zu (%s)\n", argv[2], g, cudaGetErrorString(e));
+  }
+  const int only_top = argc > 3;
   const int n_front = 16, max_rows = 11264, rows = 10900;
   const int big_rows = 87874;
   float* table;
@@ -513,6 +520,7 @@ int main(int argc, char** argv) {
   printf("ld=%d floats  rows=%d  bytes/launch=%.1f MB  big: rows=%d bytes=%.1f MB\n", ld, rows, bytes / 1e6, big_rows, big.bytes / 1e6);
   for (size_t vi = 0; vi < vs.size(); ++vi) {
     auto& v = vs[vi];
+    if (only_top && vi > 3 && vi != 21 && vi != 23) continue;
     for (int i = 0; i < 3; ++i) v.run(table, ld_bytes, dim4, fr[i], stride, dim, st, v.knob);
     CK(cudaStreamSynchronize(st));
     float best = 1e9f, sum = 0;

@@ -256,6 +256,15 @@ def test_agg_fwd_bwd(g, dev, dim, mode):
     g.agg_bwd(gout.to(dev), gself.to(dev), dim, nbr_d, stride, cnt_d, torch.from_numpy(self_idx).to(dev), argmax, None,
               rows, mode, gt)
     assert rel(gt[:, :dim], want_g) <= TOL
+    # mask_table = the ReLU output the table rows came from: the scatter yields d(pre-activation),
+    # i.e. the unmasked result multiplied by (h > 0) -- what scatter + relu_bwd_inplace produced before
+    h = torch.zeros((n_table, ld))
+    h[:, :dim] = torch.from_numpy(rng.standard_normal((n_table, dim)).astype(np.float32)).clamp_(min=0)
+    gm = torch.zeros((n_table, ld), device=dev)
+    g.agg_bwd(gout.to(dev), gself.to(dev), dim, nbr_d, stride, cnt_d, torch.from_numpy(self_idx).to(dev), argmax, None,
+              rows, mode, gm, mask_table=h.to(dev))
+    assert rel(gm[:, :dim], want_g * (h[:, :dim] > 0)) <= TOL
+    assert torch.all(gm[:, :dim].cpu()[h[:, :dim] <= 0] == 0)
 
 
 # ------------------------------------------------------------------------------------------------
