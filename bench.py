@@ -349,6 +349,9 @@ def run_ours(args):
     ms_dev, loss_dev, launches_timed, ms_e2e, last, clk = timed_arms(
         torch, native, trainer, pipelined, dev_batches, host_batches, K, W, rank, local, sync_all, max_over_ranks)
 
+    if args.timeline and rank == 0 and pipelined:
+        dump_timeline(torch, native, PipelinedTrainer, model, cls, labels, b_sz, dev_batches, args.timeline)
+
     # ---- roofline of the dominant kernel: layer-1 aggregation, events around its launch ----
     roof = None
     if rank == 0:
@@ -518,6 +521,37 @@ def run_cfg5(args):
         dist.destroy_process_group()
 
 
+def dump_timeline(torch, native, PipelinedTrainer, model, cls, labels, b_sz, dev_batches, path):
+    """Diagnostics (not a bench number): capture the pipelined step with a %globaltimer marker behind every
+    launch, replay it, and write per-branch completion times of the last two-step replay to `path`."""
+    native.timeline_begin(dev_batches.device, 1024)
+    tr = PipelinedTrainer(model, cls, labels, b_sz, lr=0.0, max_norm=5.0, use_graph=True)
+    tr.set_queue(dev_batches[:64].contiguous())
+    tr.prime()
+    tr.run(8)
+    torch.cuda.synchronize()
+    stamps = native.timeline_read()
+    t_end = max(t for _, _, t in stamps)
+    live = [(lab, sid, t) for lab, sid, t in stamps if t > t_end - 400_000]      # the last replay (two steps)
+    t0 = min(t for _, _, t in live)
+    by_stream = {}
+    for lab, sid, t in live:
+        by_stream.setdefault(sid, []).append((t - t0, lab))
+    with open(path, "w") as fp:
+        fp.write("# completion time (us, relative) of every launch of the last two-step graph replay, per capture stream;\n"
+                 "# delta = since the previous marker on the same stream.  Markers serialise launches (no PDL overlap)\n"
+                 f"# and cost ~1-2 us each, so the replay is slower than the timed one: span {(t_end - t0) / 1e3:.1f} us\n")
+        for sid, items in sorted(by_stream.items(), key=lambda kv: min(x[0] for x in kv[1])):
+            items.sort()
+            fp.write(f"stream {sid:#x}\n")
+            prev = None
+            for t, lab in items:
+                d = "" if prev is None else f"{(t - prev) / 1e3:7.2f}"
+                fp.write(f"  {t / 1e3:8.2f}  {d:>7}  {lab}\n")
+                prev = t
+    log(f"[bench] timeline written to {path}")
+
+
 def measure_agg_roofline(torch, ops, native, model, trainer, dev_batches, W, K, dev):
     """Instrumented pass: run the step's sampling phase for fresh batches, then time ONLY the
     layer-1 gs_agg_fwd launch with CUDA events on its stream.  Algorithmic bytes per launch =
@@ -657,6 +691,7 @@ def main():
                     help="1 (default): software-pipelined trainer (prepare batch n+1 beside training on batch n); 0: one batch at a time")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--timeline", default="", help="diagnostics: write a per-launch completion timeline of the step to this file")
     ap.add_argument("--ref-budget-s", type=float, default=150.0)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -274,6 +274,12 @@ agg_fwd_bf16_sharded_kernel(const ShardTable tab_arg, int64_t ld, int dim8, cons
   }
 }
 
+// CTAs per SM of the persistent forward grid (gs_set_agg_ctas; 0 = as many as fit).  A trainer that runs
+// the aggregation in a branch BESIDE its critical chain lowers it: at full occupancy the persistent CTAs
+// hold every register of every SM until the kernel ends, and the (larger) GEMM / classifier CTAs of the
+// other branch wait for the whole kernel (measured: 30 us of stall per step, profiles/r1_timeline_*).
+static int g_agg_ctas = 0;
+
 // GS_AGG_GRID=rows launches one warp per row (kept for A/B measurements); default: persistent grid
 static bool agg_grid_persistent() {
   static int v = -1;
@@ -288,6 +294,8 @@ static bool agg_grid_persistent() {
 
 using namespace gs;
 
+extern "C" void gs_set_agg_ctas(int32_t ctas_per_sm) { g_agg_ctas = ctas_per_sm > 0 ? ctas_per_sm : 0; }
+
 extern "C" int gs_agg_fwd(const float* table, int64_t ld, int32_t dim, const int32_t* nbr, int32_t stride,
                           const int32_t* cnt, const int32_t* num_rows_dev, int32_t max_rows, int32_t mode,
                           float* out, int64_t ld_out, int32_t* argmax, int64_t ld_arg, gs_stream_t stream) {
@@ -301,7 +309,9 @@ extern "C" int gs_agg_fwd(const float* table, int64_t ld, int32_t dim, const int
   cudaStream_t st = as_stream(stream);
   if (ld * 4 > 0xffffffffLL) return GS_ERR_UNSUPPORTED;
   int blocks = (max_rows + kAggWarps - 1) / kAggWarps;
-  const int persistent = kNumSMs * (mode == GS_AGG_MEAN ? kAggCtasPerSM : 3);
+  int per_sm = mode == GS_AGG_MEAN ? kAggCtasPerSM : 3;
+  if (g_agg_ctas > 0 && g_agg_ctas < per_sm) per_sm = g_agg_ctas;
+  const int persistent = kNumSMs * per_sm;
   if (agg_grid_persistent() && blocks > persistent) blocks = persistent;
   const uint32_t ld_bytes = static_cast<uint32_t>(ld * 4);
   if (mode == GS_AGG_MEAN)

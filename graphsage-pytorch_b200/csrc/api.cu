@@ -3,6 +3,8 @@
 
 #include <stdlib.h>
 
+#include <mutex>
+
 namespace gs {
 int64_t g_launches = 0;
 static int g_pdl_override = -1;          // gs_set_pdl: -1 = follow GS_PDL (default on), 0 = off, 1 = on
@@ -16,7 +18,44 @@ bool pdl_enabled() {
 }
 }
 
+namespace gs {
+void prefer_max_smem(const void* kernel) {
+  static std::mutex mu;
+  static const void* seen[256];
+  static int n_seen = 0;
+  static int enabled = -1;
+  std::lock_guard<std::mutex> lock(mu);
+  if (enabled < 0) {
+    const char* e = getenv("GS_MAX_SMEM_CARVEOUT");       // 0: leave the driver's default split (A/B measurements)
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!enabled) return;
+  for (int i = 0; i < n_seen; ++i)
+    if (seen[i] == kernel) return;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (n_seen < 256) seen[n_seen++] = kernel;
+}
+}
+
 extern "C" void gs_set_pdl(int32_t mode) { gs::g_pdl_override = mode < 0 ? -1 : (mode ? 1 : 0); }
+
+// Timeline markers (diagnostics): one thread writes the GPU's global nanosecond timer.  A trainer built
+// with native.timeline_begin() puts one behind every launch of a step; read back they give per-kernel
+// completion times on each branch of the step graph (profiles/*timeline*), which ncu's serialised
+// replay cannot.  Markers are ordinary stream work: they cost ~1-2 us each and disable PDL overlap.
+namespace gs {
+__global__ void stamp_kernel(unsigned long long* slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  *slot = t;
+}
+}
+extern "C" int gs_debug_stamp(uint64_t* slot, gs_stream_t stream) {
+  if (!slot) return GS_ERR_BAD_ARG;
+  gs::stamp_kernel<<<1, 1, 0, gs::as_stream(stream)>>>(reinterpret_cast<unsigned long long*>(slot));
+  cudaError_t e = cudaPeekAtLastError();
+  return e == cudaSuccess ? GS_OK : static_cast<int>(e);
+}
 
 extern "C" int gs_version(void) { return GS_ABI_VERSION; }
 

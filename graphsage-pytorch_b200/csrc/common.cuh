@@ -32,8 +32,17 @@ __device__ __forceinline__ void pdl_sync() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
+// Every kernel of the library asks for the maximum shared-memory carveout, whether it uses shared memory
+// or not.  An SM can only hold CTAs that agree on its L1/shared split: a CTA that needs a different split
+// waits until the SM has drained.  In the pipelined step the gathers of the preparation branch (no shared
+// memory, default split) kept the classifier and GEMM CTAs of the training chain (100-200 KB) off every SM
+// for the whole aggregation kernel -- 20-30 us per step (profiles/r1_timeline_*.txt).  The streaming kernels
+// load with L1::no_allocate, so they lose nothing.
+void prefer_max_smem(const void* kernel);      // api.cu; once per kernel function
+
 template <typename... KArgs, typename... Args>
 inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  prefer_max_smem(reinterpret_cast<const void*>(kernel));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;

@@ -23,6 +23,10 @@
 //   GS_PREC_TF32X3 x = hi + lo with hi = x truncated to tf32, lo = x - hi (exact in fp32);
 //                  D = Alo.Bhi + Ahi.Blo + Ahi.Bhi.  Dropped term and the truncation of lo are
 //                  O(2^-22) relative: fp32-faithful, meets the 1e-5 parity bound.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>          // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint)
+
 #include "common.cuh"
 
 namespace gs {
@@ -37,6 +41,9 @@ constexpr int kProducerWarps = GS_TC_PRODUCER_WARPS;     // multiple of 4 (TMEM 
 constexpr int kProducerThreads = kProducerWarps * 32;
 constexpr int kThreads = kProducerThreads + 32;          // producers/epilogue + MMA/TMEM warp
 constexpr int kMaxStages = 4;
+// 544 threads x 72 registers = 39K of the SM's 64K: a GEMM CTA fits beside two 8-warp aggregation CTAs of
+// the preparation branch (2 x 12K), so neither branch of the pipelined step waits for the other's kernel to end
+constexpr int kMaxRegs = 72;
 constexpr int kSmemBudget = 196 * 1024;
 constexpr int kMaxChunkRows = 512;
 // kind::tf32 reads the top 19 bits of each 32-bit operand element (the low 13 mantissa bits are
@@ -85,6 +92,16 @@ __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, u
   // no "memory" clobber on purpose: the compiler may hoist the (independent) index loads of the
   // next pieces above this copy; ordering against the mbarrier operations is kept by `volatile`.
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes));
+}
+// TMA: one thread arms the stage's mbarrier with the byte count of the box and issues the tiled copy; the
+// TMA unit writes the box in the 128-byte swizzled layout the UMMA descriptors read and completes the barrier.
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
+               : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -491,7 +508,10 @@ __device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 1, %0;
 
 template <bool A_MN, bool B_MN, bool SPLIT3, bool ASYNC, class LoadA, class LoadB, class Epi>
 __device__ __forceinline__ void gemm_core(const LoadA& load_a, const LoadB& load_b, const Epi& epi, int n_tile,
-                                          int k_stages, int num_stages, unsigned char* smem, const void* gdummy) {
+                                          int k_stages, int num_stages, unsigned char* smem, const void* gdummy,
+                                          const CUtensorMap* tmap_b = nullptr, int tma_b_row = 0, int tma_b_box_rows = 0) {
+  // tmap_b != nullptr (K-major B only): the B tile of k-stage ks is the TMA box {32 k from 32*ks, tma_b_box_rows
+  // rows from tma_b_row}; the producers only split it (hi/lo) once it has landed
   // ---- carve shared memory: [stages][A_hi, (A_lo), B_hi, (B_lo)], 1024-byte aligned ----
   const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
   unsigned char* smem_al = smem + (smem_base - smem_u32(smem));
@@ -501,6 +521,7 @@ __device__ __forceinline__ void gemm_core(const LoadA& load_a, const LoadB& load
   __shared__ __align__(8) uint64_t s_full[kMaxStages];
   __shared__ __align__(8) uint64_t s_empty[kMaxStages];
   __shared__ __align__(8) uint64_t s_acc;
+  __shared__ __align__(8) uint64_t s_tma[kMaxStages];      // B tile landed (TMA transaction barrier)
   __shared__ uint32_t s_tmem;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -508,8 +529,9 @@ __device__ __forceinline__ void gemm_core(const LoadA& load_a, const LoadB& load
 
   if (tid == 0) {
     for (int s = 0; s < num_stages; ++s) {
-      mbar_init(smem_u32(&s_full[s]), kProducerThreads);
+      mbar_init(smem_u32(&s_full[s]), kProducerWarps);      // one arrival per producer warp (512 serialised arrivals cost ~1 us per stage)
       mbar_init(smem_u32(&s_empty[s]), 1);
+      mbar_init(smem_u32(&s_tma[s]), 1);
     }
     mbar_init(smem_u32(&s_acc), 1);
     fence_barrier_init();
@@ -562,12 +584,18 @@ __device__ __forceinline__ void gemm_core(const LoadA& load_a, const LoadB& load
               cp_async16(a_hi + oa[i], src ? static_cast<const void*>(src) : gdummy, src ? 16u : 0u);
             }
           }
+          if (tmap_b == nullptr) {
 #pragma unroll
-          for (int i = 0; i < kMaxB; ++i) {
-            if (ob[i] >= 0) {
-              const float* src = load_b.ptr(pb[i], issued);
-              cp_async16(b_hi + ob[i], src ? static_cast<const void*>(src) : gdummy, src ? 16u : 0u);
+            for (int i = 0; i < kMaxB; ++i) {
+              if (ob[i] >= 0) {
+                const float* src = load_b.ptr(pb[i], issued);
+                cp_async16(b_hi + ob[i], src ? static_cast<const void*>(src) : gdummy, src ? 16u : 0u);
+              }
             }
+          } else if (tid == 0) {
+            const uint32_t bar = smem_u32(&s_tma[stage]);
+            mbar_expect_tx(bar, static_cast<uint32_t>(tma_b_box_rows) * 128u);
+            tma_load_2d(b_hi, tmap_b, issued * kBK, tma_b_row, bar);
           }
         }
         cp_async_commit_group();
@@ -579,6 +607,7 @@ __device__ __forceinline__ void gemm_core(const LoadA& load_a, const LoadB& load
         const int stage = ks % num_stages;
         if (ahead == 0) issue_next();
         cp_async_wait_pending(ahead == 0 ? 0 : ahead - 1);       // my pieces of stage ks have landed
+        if (tmap_b != nullptr) mbar_wait(smem_u32(&s_tma[stage]), static_cast<uint32_t>(ks / num_stages) & 1u);
         if (warp == 0) GS_TRACE(16 + 4 * ks);
         if (SPLIT3) {                                            // split MY pieces in place: hi = trunc_tf32(x), lo = x - hi
           unsigned char* a_hi = smem_al + stage * stage_bytes;
@@ -605,7 +634,8 @@ __device__ __forceinline__ void gemm_core(const LoadA& load_a, const LoadB& load
           }
         }
         fence_proxy_async();                       // generic-proxy writes -> visible to the tensor-core (async) proxy
-        mbar_arrive(smem_u32(&s_full[stage]));
+        __syncwarp();                              // every lane's writes and fence are ordered before lane 0's arrival
+        if (lane == 0) mbar_arrive(smem_u32(&s_full[stage]));
         if (warp == 0) GS_TRACE(17 + 4 * ks);
         if (ahead > 0) issue_next();               // refill the stage the MMA of k-stage ks-1 is about to release
       }
@@ -666,7 +696,8 @@ __device__ __forceinline__ void gemm_core(const LoadA& load_a, const LoadB& load
         }
       }
       fence_proxy_async();                         // generic-proxy stores -> visible to the tensor-core (async) proxy
-      mbar_arrive(smem_u32(&s_full[stage]));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&s_full[stage]));
     }
     }
     // =========================== epilogue: TMEM -> registers -> smem (transpose) -> global ===========================
@@ -752,10 +783,11 @@ __device__ __forceinline__ void gemm_core(const LoadA& load_a, const LoadB& load
 }
 
 template <bool SPLIT3, bool ASYNC>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __maxnreg__(kMaxRegs)
 sage_fwd_tc_kernel(XView x, const float* __restrict__ weight, int64_t ldw, int out_dim, bool vec_ok,
                    const int32_t* __restrict__ num_rows_dev, int max_rows, float* __restrict__ out, int64_t ld_out,
-                   int relu, int n_tile, int k_stages, int num_stages) {
+                   int relu, int n_tile, int k_stages, int num_stages, const __grid_constant__ CUtensorMap tmap_w,
+                   int use_tma_w) {
   pdl_sync();
   extern __shared__ unsigned char smem_dyn[];
   const int rows = live_rows(num_rows_dev, max_rows);
@@ -767,11 +799,12 @@ sage_fwd_tc_kernel(XView x, const float* __restrict__ weight, int64_t ldw, int o
   LoadX_K la{x, row0, rows};
   LoadW_K lb{x, weight, ldw, h0, out_dim, vec_ok};
   StoreOut epi{out, ld_out, row0, rows, h0, out_dim, relu};
-  gemm_core<false, false, SPLIT3, ASYNC>(la, lb, epi, nt, k_stages, num_stages, smem_dyn, weight);
+  gemm_core<false, false, SPLIT3, ASYNC>(la, lb, epi, nt, k_stages, num_stages, smem_dyn, weight,
+                                         (ASYNC && use_tma_w) ? &tmap_w : nullptr, h0, n_tile);
 }
 
 template <bool SPLIT3, bool ASYNC>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __maxnreg__(kMaxRegs)
 sage_bwd_x_tc_kernel(const float* __restrict__ grad_out, int64_t ld_go, const float* __restrict__ out, int64_t ld_out,
                      const float* __restrict__ weight, int64_t ldw, int dim, int out_dim, int gcn, int relu, bool vec_ok,
                      const int32_t* __restrict__ num_rows_dev, int max_rows, float* __restrict__ grad_self, int64_t ld_gs,
@@ -790,7 +823,7 @@ sage_bwd_x_tc_kernel(const float* __restrict__ grad_out, int64_t ld_go, const fl
 }
 
 template <bool SPLIT3, bool ASYNC>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __maxnreg__(kMaxRegs)
 sage_bwd_w_tc_kernel(XView x, const float* __restrict__ grad_out, int64_t ld_go, const float* __restrict__ out,
                      int64_t ld_out, int out_dim, int relu, const int32_t* __restrict__ num_rows_dev, int max_rows,
                      int rows_per_chunk, float* __restrict__ grad_w, int64_t ldw, int n_tile, int num_stages) {
@@ -833,6 +866,38 @@ static Plan make_plan(int n_total, bool a_mn, bool b_mn, bool split3, int m_tile
   return p;
 }
 
+// 2-D fp32 tensor map over a row-major [rows x cols] matrix (leading dimension ld floats): box = 32 columns
+// (one 128-byte swizzle row) x box_rows rows, SWIZZLE_128B, out-of-range elements read as zero.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    const char* e = getenv("GS_TC_TMA");
+    if (e && e[0] == '0') fn = nullptr;                      // GS_TC_TMA=0: cp.async for every operand (A/B measurements)
+  }
+  return fn;
+}
+static bool make_tmap_2d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn || box_rows < 1 || box_rows > 256 || (ld & 3) || !aligned16(base)) return false;
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 4u};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estr[2] = {1u, 1u};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <class K>
 static int set_smem(K kernel, int bytes) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -872,8 +937,12 @@ int gs_sage_gemm_fwd_tc(const float* self_table, int64_t ld_self, const int32_t*
   const bool vec_ok = (dim % 4 == 0) && (ldw % 4 == 0) && aligned16(weight);
   const bool async = vec_ok;                       // X rows are always 16-byte aligned (padded tables)
   dim3 grid((max_rows + kTileM - 1) / kTileM, (out_dim + p.n_tile - 1) / p.n_tile);
+  // W through TMA when every column tile is a full box (the box may not spill over the next operand tile)
+  CUtensorMap tmap_w;
+  memset(&tmap_w, 0, sizeof(tmap_w));
+  const int use_tma_w = (async && out_dim % p.n_tile == 0 && make_tmap_2d(&tmap_w, weight, out_dim, kt, ldw, p.n_tile)) ? 1 : 0;
   GS_TC_LAUNCH(sage_fwd_tc_kernel, grid, p.smem, as_stream(stream), x, weight, ldw, out_dim, vec_ok, num_rows_dev,
-               max_rows, out, ld_out, relu, p.n_tile, k_stages, p.num_stages);
+               max_rows, out, ld_out, relu, p.n_tile, k_stages, p.num_stages, tmap_w, use_tma_w);
   return finish_launch();
 }
 

@@ -38,6 +38,8 @@ _SIGNATURES = {
     "gs_unique_bitmap_workspace_bytes": (_SZ, [_L]),
     "gs_unique_remap_bitmap": (_I, [_P, _P, _I, _P, _I, _L, _P, _P, _P, _P, _P, _SZ, _P]),
     "gs_agg_fwd": (_I, [_P, _L, _I, _P, _I, _P, _P, _I, _I, _P, _L, _P, _L, _P]),
+    "gs_debug_stamp": (_I, [_P, _P]),
+    "gs_set_agg_ctas": (None, [_I]),
     "gs_agg_bwd": (_I, [_P, _L, _P, _L, _I, _P, _I, _P, _P, _P, _L, _P, _I, _I, _P, _L, _P, _L, _P]),
     "gs_sage_gemm_fwd": (_I, [_P, _L, _P, _P, _L, _I, _P, _L, _I, _I, _P, _I, _P, _L, _I, _I, _P]),
     "gs_sage_gemm_bwd_w": (_I, [_P, _L, _P, _P, _L, _I, _P, _L, _P, _L, _I, _I, _I, _P, _I, _P, _L, _I, _P]),
@@ -103,10 +105,50 @@ def exported_symbols():
     return list(_SIGNATURES)
 
 
+_timeline = None      # (device int64 buffer, [(label, stream id)]) while timeline markers are being recorded
+
+
+def timeline_begin(device, capacity: int = 512) -> None:
+    """Diagnostics: from now on every checked launch is followed by a gs_debug_stamp marker on its stream.
+    Capture/replay a step, then timeline_read()."""
+    global _timeline
+    _timeline = (torch.zeros((capacity,), dtype=torch.int64, device=device), [])
+
+
+def timeline_mark(label: str) -> None:
+    if _timeline is None:
+        return
+    buf, labels = _timeline
+    if len(labels) >= buf.numel():
+        return
+    st = torch.cuda.current_stream()
+    load().gs_debug_stamp(buf.data_ptr() + 8 * len(labels), st.cuda_stream)
+    labels.append((label, st.cuda_stream))
+
+
+def timeline_read():
+    """[(label, stream id, ns)] in launch order; stops recording."""
+    global _timeline
+    if _timeline is None:
+        return []
+    buf, labels = _timeline
+    _timeline = None
+    torch.cuda.synchronize()
+    t = buf.cpu().tolist()
+    return [(lab, sid, t[i]) for i, (lab, sid) in enumerate(labels)]
+
+
+def set_agg_ctas(ctas_per_sm: int) -> None:
+    """Occupancy cap of the K3 forward grid for subsequent launches (0 = full); see gs_set_agg_ctas."""
+    load().gs_set_agg_ctas(int(ctas_per_sm))
+
+
 def check(code: int, what: str) -> None:
     if code != 0:
         msg = load().gs_error_string(code)
         raise RuntimeError(f"{what} failed ({code}): {msg.decode() if msg else '?'}")
+    if _timeline is not None:
+        timeline_mark(what)
 
 
 def ptr(t: Optional[torch.Tensor]) -> Optional[int]:

@@ -17,6 +17,7 @@ comparison baseline.
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional
 
 import numpy as np
@@ -246,6 +247,10 @@ class PipelinedTrainer(SupervisedTrainer):
         self._fed = 0                          # batches written into the ring so far
         self._copy_stream = torch.cuda.Stream(device=dev)
         self._prep_stream = torch.cuda.Stream(device=dev)
+        # occupancy cap (CTAs/SM) of the layer-1 aggregation while it runs beside the training chain, 0 = none
+        # (gs_set_agg_ctas).  Measured on B200 with every kernel on the max-shared carveout: 5/SM (no cap)
+        # 10.97M seed nodes/s, 3/SM 10.56M, 2/SM 10.33M, 1/SM 9.5M -- the gathers finish sooner than they hurt.
+        self.bg_agg_ctas = int(os.environ.get("GS_BG_AGG_CTAS", "0"))
         self._graphs = [None, None]            # one step from slot 0 / slot 1
         self._graph_pair = None                # two steps (slot 0 then slot 1) in one launch
         self._cur: Optional[int] = None        # slot holding the prepared, not yet trained batch
@@ -326,11 +331,14 @@ class PipelinedTrainer(SupervisedTrainer):
                 # dependents of the preparation chain would hold SM slots the GEMMs need.  Measured per replay:
                 # both on 127 us, both off 110 us, training chain only 106 us (sequential step: 138 us).
                 native.set_pdl(0)
+                native.set_agg_ctas(self.bg_agg_ctas)
                 self._prep(1 - slot)
             native.set_pdl(-1)
+            native.set_agg_ctas(0)
             self._compute(slot, update)
         finally:
             native.set_pdl(-1)
+            native.set_agg_ctas(0)
         main.wait_stream(self._prep_stream)
 
     def _capture_pipeline(self):

@@ -55,6 +55,10 @@ const char* gs_error_string(int code);
 /* number of kernels this library has launched since load / since the last reset (bench.py's gpu_launches) */
 int64_t gs_launch_count(void);
 void gs_launch_count_reset(void);
+/* Diagnostics: enqueue a one-thread kernel that writes the GPU's %globaltimer (ns) to *slot (device memory).
+ * Markers placed behind the launches of a step give per-kernel completion times on every branch of the
+ * step graph (native.timeline_begin / timeline_read); not counted by gs_launch_count. */
+int gs_debug_stamp(uint64_t* slot, gs_stream_t stream);
 /* Programmatic dependent launch (every kernel of the library starts with griddepcontrol.launch_dependents
  * + griddepcontrol.wait and is launched with the programmatic-stream-serialization attribute, so the next
  * kernel of a chain is scheduled while the current one drains).  mode: 1 = on, 0 = off, -1 = follow the
@@ -116,6 +120,10 @@ int gs_unique_remap_bitmap(const int32_t* nodes, const int32_t* num_rows_dev, in
  * `table` rows are `ld` floats apart; ld % 4 == 0 and 16-byte aligned bases required.
  * argmax (MAX only, nullable) receives the winning table row per element, first on ties.
  * ------------------------------------------------------------------------------------ */
+/* Occupancy of the K3 forward grid for subsequent launches (process-wide, like gs_set_pdl): at most
+ * `ctas_per_sm` persistent CTAs of 8 warps per SM; 0 = full occupancy (default).  Lower it for launches
+ * that run beside a critical chain of larger CTAs (trainer.PipelinedTrainer), restore it afterwards. */
+void gs_set_agg_ctas(int32_t ctas_per_sm);
 int gs_agg_fwd(const float* table, int64_t ld, int32_t dim,
                const int32_t* nbr, int32_t stride, const int32_t* cnt,
                const int32_t* num_rows_dev, int32_t max_rows, int32_t mode,
