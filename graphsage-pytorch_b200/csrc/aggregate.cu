@@ -314,6 +314,9 @@ extern "C" int gs_agg_fwd(const float* table, int64_t ld, int32_t dim, const int
   const int persistent = kNumSMs * per_sm;
   if (agg_grid_persistent() && blocks > persistent) blocks = persistent;
   const uint32_t ld_bytes = static_cast<uint32_t>(ld * 4);
+  set_kernel_carveout(mode == GS_AGG_MEAN ? reinterpret_cast<const void*>(agg_fwd_kernel<GS_AGG_MEAN>)
+                                          : reinterpret_cast<const void*>(agg_fwd_kernel<GS_AGG_MAX>),
+                      background_launches());
   if (mode == GS_AGG_MEAN)
     launch(agg_fwd_kernel<GS_AGG_MEAN>, blocks, kAggWarps * 32, 0, st, 
         table, ld_bytes, dim4, nbr, stride, cnt, num_rows_dev, max_rows, out, ld_out, nullptr, 0);
@@ -375,6 +378,9 @@ extern "C" int gs_agg_fwd_bf16_sharded(const void* const* shard_bases_host, int3
   }
   if (max_rows == 0) return GS_OK;
   const int blocks = (max_rows + kAggWarps - 1) / kAggWarps;
+  set_kernel_carveout(dim8 <= 16 ? reinterpret_cast<const void*>(agg_fwd_bf16_sharded_kernel<16>)
+                                 : reinterpret_cast<const void*>(agg_fwd_bf16_sharded_kernel<32>),
+                      background_launches());
   if (dim8 <= 16)
     launch(agg_fwd_bf16_sharded_kernel<16>, blocks, kAggWarps * 32, 0, as_stream(stream), 
         tab, ld, dim8, nbr, stride, cnt, self_nodes, num_rows_dev, max_rows, out_agg, ld_agg, out_self, ld_self);

@@ -19,23 +19,41 @@ bool pdl_enabled() {
 }
 
 namespace gs {
-void prefer_max_smem(const void* kernel) {
-  static std::mutex mu;
-  static const void* seen[256];
-  static int n_seen = 0;
+static std::mutex g_carve_mu;
+static const void* g_carve_seen[256];
+static int g_carve_n = 0;
+static int g_background = 0;            // gs_set_background
+
+static bool carveout_enabled() {
   static int enabled = -1;
-  std::lock_guard<std::mutex> lock(mu);
   if (enabled < 0) {
     const char* e = getenv("GS_MAX_SMEM_CARVEOUT");       // 0: leave the driver's default split (A/B measurements)
     enabled = (e && e[0] == '0') ? 0 : 1;
   }
-  if (!enabled) return;
-  for (int i = 0; i < n_seen; ++i)
-    if (seen[i] == kernel) return;
+  return enabled == 1;
+}
+static bool carve_seen_or_add(const void* kernel) {       // caller holds g_carve_mu
+  for (int i = 0; i < g_carve_n; ++i)
+    if (g_carve_seen[i] == kernel) return true;
+  if (g_carve_n < 256) g_carve_seen[g_carve_n++] = kernel;
+  return false;
+}
+void prefer_max_smem(const void* kernel) {
+  std::lock_guard<std::mutex> lock(g_carve_mu);
+  if (!carveout_enabled() || carve_seen_or_add(kernel)) return;
   cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  if (n_seen < 256) seen[n_seen++] = kernel;
 }
+void set_kernel_carveout(const void* kernel, bool max_shared) {
+  std::lock_guard<std::mutex> lock(g_carve_mu);
+  if (!carveout_enabled()) return;
+  carve_seen_or_add(kernel);             // launch() leaves this kernel's split alone from now on
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                       max_shared ? cudaSharedmemCarveoutMaxShared : cudaSharedmemCarveoutDefault);
 }
+bool background_launches() { return g_background != 0; }
+}
+
+extern "C" void gs_set_background(int32_t on) { gs::g_background = on ? 1 : 0; }
 
 extern "C" void gs_set_pdl(int32_t mode) { gs::g_pdl_override = mode < 0 ? -1 : (mode ? 1 : 0); }
 

@@ -149,8 +149,12 @@ cls_fused_kernel(const float* __restrict__ emb, int64_t ld_emb, int rows, int di
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int r0 = blockIdx.x * kClsRows;
 
-  for (int i = tid; i < dim * cp; i += blockDim.x) wt_s[i] = 0.f;
-  __syncthreads();
+  // the label sits behind two dependent global loads (index, then label): start them before the staging
+  const int r = r0 + warp;
+  const bool live = r < rows;
+  int y = -1;
+  if (live) y = static_cast<int>(labels[label_index ? label_index[r] : r]);
+  // W^T columns >= classes are never initialised: the lanes that read them are masked by selects below
   const int d4 = dim >> 2;
   for (int i = tid; i < classes * d4; i += blockDim.x) {
     const int c = i / d4, k = (i - c * d4) * 4;
@@ -158,8 +162,6 @@ cls_fused_kernel(const float* __restrict__ emb, int64_t ld_emb, int rows, int di
     *reinterpret_cast<float4*>(w_s + c * dim + k) = v;
     wt_s[(k + 0) * cp + c] = v.x; wt_s[(k + 1) * cp + c] = v.y; wt_s[(k + 2) * cp + c] = v.z; wt_s[(k + 3) * cp + c] = v.w;
   }
-  const int r = r0 + warp;
-  const bool live = r < rows;
   for (int k = lane * 4; k < dim; k += 128) {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (live) v = *reinterpret_cast<const float4*>(emb + static_cast<int64_t>(r) * ld_emb + k);
@@ -194,7 +196,6 @@ cls_fused_kernel(const float* __restrict__ emb, int64_t ld_emb, int rows, int di
   const float lp0 = a0 - lse, lp1 = a1 - lse;
   float dl0 = 0.f, dl1 = 0.f, lpart = 0.f;
   if (live) {
-    const int y = static_cast<int>(labels[label_index ? label_index[r] : r]);
     const float inv = 1.0f / static_cast<float>(rows);
     if (v0) { dl0 = (expf(lp0) - (lane == y ? 1.f : 0.f)) * inv; if (lane == y) lpart = -lp0 * inv; }
     if (v1) { dl1 = (expf(lp1) - (lane + 32 == y ? 1.f : 0.f)) * inv; if (lane + 32 == y) lpart = -lp1 * inv; }

@@ -39,6 +39,11 @@ __device__ __forceinline__ void pdl_sync() {
 // for the whole aggregation kernel -- 20-30 us per step (profiles/r1_timeline_*.txt).  The streaming kernels
 // load with L1::no_allocate, so they lose nothing.
 void prefer_max_smem(const void* kernel);      // api.cu; once per kernel function
+// Exception: the HBM-bound gather kernels.  The L1 the max-shared split takes away is where their loads in
+// flight land (measured: layer-1 aggregation 0.59 -> 0.52 of the HBM copy peak, 0.82 -> 0.69 at 88K rows), so
+// they ask for it only when launched as background work of a two-branch step (gs_set_background).
+void set_kernel_carveout(const void* kernel, bool max_shared);
+bool background_launches();
 
 template <typename... KArgs, typename... Args>
 inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

@@ -40,6 +40,7 @@ _SIGNATURES = {
     "gs_agg_fwd": (_I, [_P, _L, _I, _P, _I, _P, _P, _I, _I, _P, _L, _P, _L, _P]),
     "gs_debug_stamp": (_I, [_P, _P]),
     "gs_set_agg_ctas": (None, [_I]),
+    "gs_set_background": (None, [_I]),
     "gs_agg_bwd": (_I, [_P, _L, _P, _L, _I, _P, _I, _P, _P, _P, _L, _P, _I, _I, _P, _L, _P, _L, _P]),
     "gs_sage_gemm_fwd": (_I, [_P, _L, _P, _P, _L, _I, _P, _L, _I, _I, _P, _I, _P, _L, _I, _I, _P]),
     "gs_sage_gemm_bwd_w": (_I, [_P, _L, _P, _P, _L, _I, _P, _L, _P, _L, _I, _I, _I, _P, _I, _P, _L, _I, _P]),
@@ -141,6 +142,11 @@ def timeline_read():
 def set_agg_ctas(ctas_per_sm: int) -> None:
     """Occupancy cap of the K3 forward grid for subsequent launches (0 = full); see gs_set_agg_ctas."""
     load().gs_set_agg_ctas(int(ctas_per_sm))
+
+
+def set_background(on: bool) -> None:
+    """Mark subsequent launches as background work of a two-branch step (see gs_set_background)."""
+    load().gs_set_background(int(bool(on)))
 
 
 def check(code: int, what: str) -> None:

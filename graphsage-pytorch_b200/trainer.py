@@ -332,13 +332,16 @@ class PipelinedTrainer(SupervisedTrainer):
                 # both on 127 us, both off 110 us, training chain only 106 us (sequential step: 138 us).
                 native.set_pdl(0)
                 native.set_agg_ctas(self.bg_agg_ctas)
+                native.set_background(True)
                 self._prep(1 - slot)
             native.set_pdl(-1)
             native.set_agg_ctas(0)
+            native.set_background(False)
             self._compute(slot, update)
         finally:
             native.set_pdl(-1)
             native.set_agg_ctas(0)
+            native.set_background(False)
         main.wait_stream(self._prep_stream)
 
     def _capture_pipeline(self):

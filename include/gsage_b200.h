@@ -124,6 +124,11 @@ int gs_unique_remap_bitmap(const int32_t* nodes, const int32_t* num_rows_dev, in
  * `ctas_per_sm` persistent CTAs of 8 warps per SM; 0 = full occupancy (default).  Lower it for launches
  * that run beside a critical chain of larger CTAs (trainer.PipelinedTrainer), restore it afterwards. */
 void gs_set_agg_ctas(int32_t ctas_per_sm);
+/* Process-wide switch like gs_set_pdl: launches issued while it is on are background work of a two-branch
+ * step (trainer.PipelinedTrainer's preparation branch).  Every kernel of the library prefers the maximum
+ * shared-memory carveout so that CTAs of both branches can share an SM; the K3 forward kernel, whose HBM
+ * throughput needs the L1 that carveout removes, does so only while this switch is on. */
+void gs_set_background(int32_t on);
 int gs_agg_fwd(const float* table, int64_t ld, int32_t dim,
                const int32_t* nbr, int32_t stride, const int32_t* cnt,
                const int32_t* num_rows_dev, int32_t max_rows, int32_t mode,
