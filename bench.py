@@ -521,6 +521,57 @@ def run_cfg5(args):
         dist.destroy_process_group()
 
 
+def run_infer(args):
+    """`--workload infer` (not the headline): forward-only embeddings of the cfg-3 graph through
+    inference.get_gnn_embeddings, the reference's src/utils.py:59-78 loop, at --b_sz nodes per forward."""
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the gsage_b200 hot path has no CPU fallback")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    import graphsage_b200  # noqa: F401
+    from graphsage_b200 import inference, models, native
+    from graphsage_b200.graph import AdjCSR
+    import graphsage_b200.synth as synth
+    native.load()
+    cfg, rowptr, col, feats, labels, train = build_workload(args.scale)
+    n_nodes = int(len(rowptr) - 1)
+    b_sz = args.b_sz if args.b_sz != 1024 else 8192
+    torch.manual_seed(SEED)
+    model = models.GraphSage(2, cfg["feats"], cfg["hidden"], torch.from_numpy(feats).to(dev), AdjCSR(rowptr, col), dev,
+                             gcn=False, agg_func="MEAN", seed=SEED, precision=args.precision).to(dev)
+    wrng = np.random.default_rng(7)
+    with torch.no_grad():
+        model.sage_layer1.weight.copy_(torch.from_numpy(synth.xavier_uniform_np(wrng, cfg["hidden"], 2 * cfg["feats"])))
+        model.sage_layer2.weight.copy_(torch.from_numpy(synth.xavier_uniform_np(wrng, cfg["hidden"], 2 * cfg["hidden"])))
+    n_batches = max(4, min(args.steps, 64))
+    rng = np.random.default_rng(SEED)
+    nodes = torch.from_numpy(rng.permutation(n_nodes)[:n_batches * b_sz].astype(np.int32)).to(dev)
+    out = torch.empty((nodes.shape[0], cfg["hidden"]), dtype=torch.float32, device=dev)
+    inference.get_gnn_embeddings(model, nodes[:max(3, args.warmup) * b_sz], b_sz=b_sz)
+    torch.cuda.synchronize(dev)
+    native.launch_count_reset()
+    sampler = ClockSampler(0)
+    sampler.start()
+    t0 = time.time()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    inference.get_gnn_embeddings(model, nodes, b_sz=b_sz, out=out)
+    b.record()
+    torch.cuda.synchronize(dev)
+    t1 = time.time()
+    clk = sampler.stop(t0, t1)
+    ms = a.elapsed_time(b)
+    line = {"metric": "nodes_per_sec_inference", "value": nodes.shape[0] / (ms * 1e-3), "unit": "nodes/s", "n_gpus": 1,
+            "steps": n_batches, "warmup": max(3, args.warmup), "ms_per_step": ms / n_batches, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (tcgen05 3xTF32 split, fp32-faithful)", "data": "synthetic",
+            "config": {"workload": "cfg3_products forward-only embeddings (src/utils.py:59-78)", "nodes": n_nodes,
+                       "b_sz": b_sz, "fanout": 10, "layers": 2, "agg": "MEAN",
+                       "l2_policy": "feature table 980 MB >> 126 MB L2; distinct nodes every batch"},
+            "gpu_launches": int(native.launch_count()), "clocks": clk}
+    print(json.dumps(line), flush=True)
+
+
 def dump_timeline(torch, native, PipelinedTrainer, model, cls, labels, b_sz, dev_batches, path):
     """Diagnostics (not a bench number): capture the pipelined step with a %globaltimer marker behind every
     launch, replay it, and write per-branch completion times of the last two-step replay to `path`."""
@@ -709,7 +760,7 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="gradient exchange + update: peer = one fused kernel over NVLink peer memory (default); "
                          "nccl = library all-reduce followed by the separate norm/update kernels (comparison)")
-    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg5"],
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg5", "infer"],
                     help="cfg3 = ogbn-products-shaped (the headline, BASELINE configs[2]); cfg5 = row-partitioned bf16 "
                          "features with P2P NVLink gather (configs[4]; b_sz 8192 per GPU unless --b_sz is given)")
     ap.add_argument("--cfg5-nodes-per-gpu", type=int, default=12_500_000,
@@ -728,6 +779,8 @@ def main():
         run_reference(args)
     elif args.workload == "cfg5":
         run_cfg5(args)
+    elif args.workload == "infer":
+        run_infer(args)
     else:
         run_ours(args)
 

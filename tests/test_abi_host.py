@@ -114,3 +114,19 @@ def test_philox_host_matches_known_answer():
     assert philox([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
     assert philox([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_micro_f1_is_sklearn_micro_f1_for_single_label_predictions():
+    """inference.micro_f1 restates f1_score(average='micro') (src/utils.py:32,45) without leaving the device."""
+    import numpy as np
+    import torch
+    from sklearn.metrics import f1_score
+    from graphsage_b200 import inference
+    rng = np.random.default_rng(3)
+    for classes, n in ((7, 500), (3, 41), (47, 2000)):
+        y = rng.integers(0, classes, size=n)
+        p = np.where(rng.random(n) < 0.6, y, rng.integers(0, classes, size=n))
+        assert abs(inference.micro_f1(torch.from_numpy(y), torch.from_numpy(p)) - f1_score(y, p, average='micro')) < 1e-12
+    import pytest
+    with pytest.raises(ValueError):
+        inference.micro_f1(torch.zeros(3, dtype=torch.int64), torch.zeros(4, dtype=torch.int64))

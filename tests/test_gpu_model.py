@@ -349,3 +349,72 @@ def test_pipelined_trainer_matches_plain_trainer(M):
             assert np.allclose(l, base_l, rtol=1e-5, atol=1e-6), (kind.__name__, use_graph, l, base_l)
         for a, b in zip(p, base_p):
             assert rel(a, b) <= 1e-5, (kind.__name__, use_graph, queue)
+
+
+# ------------------------------------------------------------------------------------------------
+# N2: forward-only embeddings / evaluation, src/utils.py:13-78
+# ------------------------------------------------------------------------------------------------
+def _small_degree_graph(n, max_deg, rng):
+    """Undirected graph whose degrees stay below the fan-out: the reference then takes every neighbour
+    (src/models.py:282), so embeddings do not depend on any random stream."""
+    nbrs = [set() for _ in range(n)]
+    for v in range(n):
+        for u in rng.integers(0, n, size=rng.integers(1, 3)):
+            u = int(u)
+            if u != v and len(nbrs[v]) < max_deg and len(nbrs[u]) < max_deg:
+                nbrs[v].add(u)
+                nbrs[u].add(v)
+    for v in range(n):                      # no isolated node (0/0 rows are a separate test)
+        if not nbrs[v]:
+            u = (v + 1) % n
+            nbrs[v].add(u)
+            nbrs[u].add(v)
+    return {v: s for v, s in enumerate(nbrs)}
+
+
+@pytest.mark.parametrize('gcn,agg', [(False, 'MEAN'), (True, 'MEAN'), (False, 'MAX')])
+def test_get_gnn_embeddings_and_evaluate_match_the_oracle(M, gcn, agg):
+    from graphsage_b200 import inference
+    from sklearn.metrics import f1_score
+    dev = torch.device('cuda:0')
+    rng = np.random.default_rng(11)
+    n, f, h, c = 700, 20, 32, 5
+    adj = _small_degree_graph(n, 9, rng)
+    assert max(len(s) for s in adj.values()) < 10
+    feats = rng.standard_normal((n, f)).astype(np.float32)
+    w1 = so.xavier_uniform(rng, h, f if gcn else 2 * f)
+    w2 = so.xavier_uniform(rng, h, h if gcn else 2 * h)
+    cw, cb = so.xavier_uniform(rng, c, h), torch.from_numpy(rng.standard_normal(c).astype(np.float32) * 0.1)
+    labels = rng.integers(0, c, size=n)
+    model = M.GraphSage(2, f, h, torch.from_numpy(feats).to(dev), adj, dev, gcn=gcn, agg_func=agg, seed=5).to(dev)
+    cls = M.Classification(h, c).to(dev)
+    with torch.no_grad():
+        model.sage_layer1.weight.copy_(w1)
+        model.sage_layer2.weight.copy_(w2)
+        cls.layer[0].weight.copy_(cw)
+        cls.layer[0].bias.copy_(cb)
+    # oracle: the reference algorithm, all nodes 100 at a time (utils.py:63-71 uses 500; any split gives the same rows)
+    ref = torch.cat([so.graphsage_forward([w1, w2], torch.from_numpy(feats), adj, list(range(lo, min(lo + 100, n))),
+                                          gcn=gcn, agg_func=agg) for lo in range(0, n, 100)], 0)
+    for b_sz in (123, 500, 4096):
+        got = inference.get_gnn_embeddings(model, None, b_sz=b_sz)
+        assert got.shape == (n, h) and not got.requires_grad
+        assert rel(got, ref) <= TOL
+    some = rng.permutation(n)[:257]
+    assert rel(inference.get_gnn_embeddings(model, some.tolist()), ref[some]) <= TOL       # python list, like utils.py:67
+    assert rel(inference.get_gnn_embeddings(model, some), ref[some]) <= TOL                # numpy int64, like utils.py:149
+    # evaluation: arg-max of the classifier, micro-F1 as sklearn computes it (utils.py:26-32)
+    val, test = np.arange(0, 300), np.arange(300, 700)
+    ref_pred = torch.argmax(so.classification(cw, cb, ref), 1).numpy()
+    logits = so.classification(cw, cb, ref)
+    top2 = torch.topk(logits, 2, dim=1).values
+    safe = ((top2[:, 0] - top2[:, 1]) > 1e-4).numpy()            # rows whose arg-max is not a round-off coin toss
+    pred = inference.predict(model, cls, np.arange(n)).cpu().numpy()
+    assert (pred[safe] == ref_pred[safe]).all() and safe.mean() > 0.95
+    vali, tst, best = inference.evaluate(val, test, labels, model, cls, max_vali_f1=0.0)
+    assert abs(vali - f1_score(labels[val], pred[val], average='micro')) < 1e-12 or not safe[val].all()
+    assert tst is not None and best == vali
+    assert abs(tst - f1_score(labels[test], pred[test], average='micro')) < 1e-12 or not safe[test].all()
+    vali2, tst2, best2 = inference.evaluate(val, test, labels, model, cls, max_vali_f1=2.0)
+    assert tst2 is None and best2 == 2.0                         # no improvement: the test split is not scored (utils.py:35)
+    assert all(p.requires_grad for p in list(model.parameters()) + list(cls.parameters()))   # utils.py:54-55
