@@ -469,6 +469,13 @@ int main(int argc, char** argv) {
     printf("L2 fetch granularity: requested %s -> %zu (%s)\n", argv[2], g, cudaGetErrorString(e));
   }
   const int only_top = argc > 3;
+  const int carve = argc > 4 ? atoi(argv[4]) : -1;
+  if (carve >= -1) {
+    cudaFuncSetAttribute(agg_d<6, 5, 0, 0, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    cudaFuncSetAttribute(agg_base<3>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    cudaFuncSetAttribute(agg_persist<2, 0, 5, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    printf("carveout %d\n", carve);
+  }
   const int n_front = 16, max_rows = 11264, rows = 10900;
   const int big_rows = 87874;
   float* table;
@@ -520,7 +527,7 @@ int main(int argc, char** argv) {
   printf("ld=%d floats  rows=%d  bytes/launch=%.1f MB  big: rows=%d bytes=%.1f MB\n", ld, rows, bytes / 1e6, big_rows, big.bytes / 1e6);
   for (size_t vi = 0; vi < vs.size(); ++vi) {
     auto& v = vs[vi];
-    if (only_top && vi > 3 && vi != 21 && vi != 23) continue;
+    if (only_top && vi > 2) continue;
     for (int i = 0; i < 3; ++i) v.run(table, ld_bytes, dim4, fr[i], stride, dim, st, v.knob);
     CK(cudaStreamSynchronize(st));
     float best = 1e9f, sum = 0;
