@@ -178,13 +178,26 @@ dp_update_kernel(float* __restrict__ flat, long long n_total, const DpPeers peer
     }
   }
   __syncthreads();
-  if (tid < kDpMaxGroups) {
-    float tot = 0.f;
-    for (int cc = 0; cc < G; ++cc) tot += __ldcg(&st->partial[cc][tid]);       // CTA order: identical on every CTA and rank
-    const float norm = sqrtf(tot);
-    // torch.nn.utils.clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), clamped to <= 1
-    s_coef[tid] = max_norm > 0.f ? fminf(max_norm / (norm + 1e-6f), 1.0f) : 1.0f;
-    if (c == 0) st->norm[tid] = norm;
+  if (tid < 32) {
+    // all G x groups partials in flight at once (lane = CTA, G <= 64), then a shuffle tree: the order of the
+    // additions is fixed by the lane numbers, hence identical on every CTA and every rank
+    float v[kDpMaxGroups];
+#pragma unroll
+    for (int g = 0; g < kDpMaxGroups; ++g) {
+      const float a = tid < G ? __ldcg(&st->partial[tid][g]) : 0.f;
+      const float b = tid + 32 < G ? __ldcg(&st->partial[tid + 32][g]) : 0.f;
+      v[g] = a + b;
+    }
+#pragma unroll
+    for (int g = 0; g < kDpMaxGroups; ++g) {
+      const float tot = warp_sum(v[g]);
+      if (tid == g) {
+        const float norm = sqrtf(tot);
+        // torch.nn.utils.clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), clamped to <= 1
+        s_coef[g] = max_norm > 0.f ? fminf(max_norm / (norm + 1e-6f), 1.0f) : 1.0f;
+        if (c == 0) st->norm[g] = norm;
+      }
+    }
   }
   __syncthreads();
 
