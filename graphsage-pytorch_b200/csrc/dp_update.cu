@@ -108,7 +108,8 @@ dp_update_kernel(float* __restrict__ flat, long long n_total, const DpPeers peer
       float4* dst = reinterpret_cast<float4*>(peers.recv[p]) + static_cast<long long>(par * W + me) * n4;
       for (long long i = b4 + tid; i < e4; i += kDpThreads) dst[i] = flat4[i];
     }
-    __threadfence_system();
+    // No per-thread system fence here: the CTA barrier orders every thread's remote stores before the flag
+    // writers, and their release at system scope is cumulative -- one fence round trip over NVLink, not two.
     __syncthreads();
     if (tid < W && tid != me) {
       st_release_sys(peers.flags[tid] + me * kDpMaxCtas + c, e);
