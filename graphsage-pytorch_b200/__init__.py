@@ -7,7 +7,7 @@ __version__ = "0.1.0"
 from . import synth  # noqa: F401  (numpy only)
 
 _LAZY_CLASSES = ("GraphSage", "SageLayer", "Classification", "UnsupervisedLoss")
-_LAZY_MODULES = ("models", "native", "ops", "graph", "trainer", "build", "inference", "peer")
+_LAZY_MODULES = ("models", "native", "ops", "graph", "trainer", "build", "inference", "peer", "datacache")
 
 
 def __getattr__(name):
