@@ -10,6 +10,11 @@ leaves the device; the per-batch work is the same kernels as a training forward:
 unique/remap -> aggregation -> SageLayer GEMM.  At b_sz 8192 on the cfg-3 graph the layer-1 aggregation
 launch gathers ~390 MB and runs at 0.8 of the HBM copy peak (bench.py --workload infer).
 
+`train_classification` (row N4, src/utils.py:80-111) trains the classifier on frozen embeddings: 800 epochs of
+[50 x 128] . [128 x C] steps, a pure launch-latency workload.  One epoch (every batch: row gather, the one-launch
+classifier + NLL + backward kernel, clip + SGD) is captured as ONE CUDA graph that reads the epoch's node order
+from a device buffer, so an epoch costs one replay and one small H2D copy (or a device randperm).
+
 Out of scope, as in SURVEY.md §2: `torch.save` of the live modules (utils.py:52) and the console prints.
 """
 from __future__ import annotations
@@ -19,10 +24,10 @@ from typing import Optional, Sequence, Tuple
 import numpy as np
 import torch
 
-from . import native
+from . import native, ops
 from .models import Classification, GraphSage, _as_device_ids
 
-__all__ = ["get_gnn_embeddings", "predict", "micro_f1", "evaluate"]
+__all__ = ["get_gnn_embeddings", "predict", "micro_f1", "evaluate", "train_classification"]
 
 
 def _weights(gnn_model: GraphSage):
@@ -94,3 +99,84 @@ def evaluate(val_nodes, test_nodes, labels, gnn_model: GraphSage, classification
         max_vali_f1 = vali_f1
         test_f1 = score(test_nodes)
     return vali_f1, test_f1, max_vali_f1
+
+
+def train_classification(features: torch.Tensor, train_nodes, labels, classification: Classification, epochs: int = 800,
+                         b_sz: int = 50, lr: float = 0.5, max_norm: float = 5.0, orders=None, on_epoch=None,
+                         use_graph: bool = True, seed: int = 0) -> torch.Tensor:
+    """src/utils.py:80-111 on the device.  `features`: frozen embeddings [N x emb] (what `get_gnn_embeddings`
+    returned, :88); per epoch the train nodes are shuffled (:91), cut into batches of `b_sz` (:85, last one ragged),
+    and every batch does classifier forward, NLL mean (:100-101), backward, clip_grad_norm_(5) (:106) and an SGD
+    step with lr 0.5 (:82,107).  `orders` (optional): one node order per epoch, replacing the shuffle -- replaying
+    the orders the reference's `shuffle` produced reproduces its weights (tests/golden/train_classification.npz).
+    `on_epoch(epoch)` is called after every epoch (the reference evaluates there, :109).  Updates
+    `classification` in place and returns the device loss of the last batch."""
+    lin = classification.layer[0]
+    native.require_cuda(lin.weight, "Classification parameters")
+    dev = lin.weight.device
+    native.require_cuda(features, "features")
+    feats = features.detach()
+    if feats.dtype != torch.float32 or feats.stride(1) != 1 or feats.stride(0) % 4:
+        feats = feats.float().contiguous()
+    dim, classes = int(lin.weight.shape[1]), int(lin.weight.shape[0])
+    if feats.shape[1] != dim:
+        raise ValueError(f"features have {feats.shape[1]} columns, the classifier expects {dim}")
+    train_dev = _as_device_ids(train_nodes, dev)
+    n_train = int(train_dev.shape[0])
+    if n_train == 0 or epochs <= 0:
+        return torch.zeros((1,), dtype=torch.float32, device=dev)
+    labels_dev = labels if isinstance(labels, torch.Tensor) else torch.from_numpy(np.asarray(labels, dtype=np.int64))
+    labels_dev = labels_dev.to(dev)
+    if orders is not None:
+        orders = [np.ascontiguousarray(np.asarray(o), dtype=np.int32) for o in orders]
+        if len(orders) < epochs or any(len(o) != n_train for o in orders[:epochs]):
+            raise ValueError("orders must hold one permutation of the train nodes per epoch")
+    params = [lin.weight.data, lin.bias.data]
+    grads = [torch.zeros_like(p) for p in params]
+    tl = ops.TensorList(params, grads)
+    order = torch.empty((n_train,), dtype=torch.int32, device=dev)      # this epoch's node order, read by the graph
+    loss = torch.zeros((1,), dtype=torch.float32, device=dev)
+
+    def epoch_body():
+        for lo in range(0, n_train, b_sz):
+            ids = order[lo:lo + b_sz]
+            emb = feats.index_select(0, ids)                                           # :97
+            ops.cls_nll_fwd_bwd(emb, dim, params[0], params[1], classes, labels_dev, ids, loss, None, grads[0], grads[1],
+                                mask_relu_input=False)                                 # :99-104
+            ops.clip_sgd(tl, max_norm, lr, 1.0, zero_grads=True)                       # :106-108
+
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+
+    def next_order(epoch):
+        if orders is not None:
+            order.copy_(torch.from_numpy(orders[epoch]), non_blocking=False)
+        else:
+            order.copy_(train_dev[torch.randperm(n_train, device=dev, generator=gen)])
+
+    graph = None
+    for epoch in range(epochs):
+        next_order(epoch)
+        if not use_graph:
+            epoch_body()
+        elif graph is None:
+            side = torch.cuda.Stream(device=dev)                       # warm-up off the capture (allocator, lazy loads)
+            side.wait_stream(torch.cuda.current_stream())
+            saved = [p.clone() for p in params]
+            with torch.cuda.stream(side):
+                epoch_body()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize(dev)
+            for p, q in zip(params, saved):
+                p.copy_(q)
+            for g in grads:
+                g.zero_()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                epoch_body()
+            graph.replay()
+        else:
+            graph.replay()
+        if on_epoch is not None:
+            on_epoch(epoch)
+    return loss

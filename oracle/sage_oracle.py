@@ -331,6 +331,35 @@ def supervised_step(weights, cls_weight, cls_bias, raw_features, adj, nodes_batc
 
 
 # --------------------------------------------------------------------------------------
+# N4  classifier training on frozen embeddings           src/utils.py:80-111
+# --------------------------------------------------------------------------------------
+def train_classification(cls_weight: torch.Tensor, cls_bias: torch.Tensor, features: torch.Tensor, labels,
+                         orders: Sequence[Sequence[int]], b_sz: int = 50, lr: float = 0.5, max_norm: float = 5.0):
+    """The loop body of src/utils.py:90-107 for given per-epoch node orders (`orders[e]` is what
+    `shuffle(train_nodes)` returned in epoch e, :91).  Plain SGD is stateless, so the optimizer of :82 is the
+    in-place update below.  Returns the trained (weight, bias) and the last batch's loss."""
+    w = cls_weight.clone().requires_grad_(True)
+    b = cls_bias.clone().requires_grad_(True)
+    labels = np.asarray(labels)
+    loss = None
+    for order in orders:
+        order = np.asarray(order)
+        for lo in range(0, len(order), b_sz):                             # :92-94
+            nodes_batch = order[lo:lo + b_sz]
+            logists = classification(w, b, features[nodes_batch])         # :97-99
+            loss = -torch.sum(logists[range(logists.size(0)), labels[nodes_batch]], 0)    # :100
+            loss = loss / len(nodes_batch)                                # :101
+            loss.backward()                                               # :104
+            torch.nn.utils.clip_grad_norm_([w, b], max_norm)              # :106
+            with torch.no_grad():                                         # :107-108
+                w -= lr * w.grad
+                b -= lr * b.grad
+                w.grad.zero_()
+                b.grad.zero_()
+    return w.detach(), b.detach(), (loss.detach() if loss is not None else None)
+
+
+# --------------------------------------------------------------------------------------
 # adjacency helpers shared by tests / bench (data plumbing, not reference behaviour)
 # --------------------------------------------------------------------------------------
 class LazySetAdjacency(Mapping):

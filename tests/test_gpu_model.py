@@ -418,3 +418,34 @@ def test_get_gnn_embeddings_and_evaluate_match_the_oracle(M, gcn, agg):
     vali2, tst2, best2 = inference.evaluate(val, test, labels, model, cls, max_vali_f1=2.0)
     assert tst2 is None and best2 == 2.0                         # no improvement: the test split is not scored (utils.py:35)
     assert all(p.requires_grad for p in list(model.parameters()) + list(cls.parameters()))   # utils.py:54-55
+
+
+# ------------------------------------------------------------------------------------------------
+# N4: classifier training on frozen embeddings, src/utils.py:80-111
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('use_graph', [True, False])
+def test_train_classification_matches_the_reference_loop(M, use_graph):
+    """Replaying the node orders the reference's `shuffle` produced, three epochs of the device loop must land on
+    the reference's weights (golden: the reference's own train_classification, 173 train nodes = 3 x 50 + 23)."""
+    import os
+    from graphsage_b200 import inference
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "train_classification.npz"))
+    dev = torch.device('cuda:0')
+    cls = M.Classification(g["w0"].shape[1], g["w0"].shape[0]).to(dev)
+    with torch.no_grad():
+        cls.layer[0].weight.copy_(torch.from_numpy(g["w0"]))
+        cls.layer[0].bias.copy_(torch.from_numpy(g["b0"]))
+    seen = []
+    loss = inference.train_classification(torch.from_numpy(g["feats"]).to(dev), g["train"], g["labels"], cls, epochs=3,
+                                          orders=list(g["orders"]), on_epoch=seen.append, use_graph=use_graph)
+    assert seen == [0, 1, 2]
+    assert rel(cls.layer[0].weight, g["w1"]) <= TOL
+    assert rel(cls.layer[0].bias, g["b1"]) <= TOL
+    assert np.isfinite(float(loss.item()))
+    # native shuffle: a different order, same kind of progress (loss of the last batch far below ln(7))
+    cls2 = M.Classification(g["w0"].shape[1], g["w0"].shape[0]).to(dev)
+    loss2 = inference.train_classification(torch.from_numpy(g["feats"]).to(dev), g["train"], g["labels"], cls2, epochs=40,
+                                           use_graph=use_graph, seed=3)
+    assert float(loss2.item()) < 1.5
+    with pytest.raises(ValueError):
+        inference.train_classification(torch.zeros((10, 8), device=dev), [0, 1], g["labels"], cls, epochs=1)

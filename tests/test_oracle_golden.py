@@ -95,3 +95,19 @@ def test_sampler_semantics():
         got = s - {n}
         assert got <= nb
         assert len(got) == (len(nb) if deg[n] < 10 else 10)               # src/models.py:282
+
+
+def test_train_classification_oracle_matches_the_reference_loop():
+    """N4: oracle restatement of src/utils.py:90-107 against the weights the reference's own loop produced
+    (tests/golden/make_golden_train_classification.py asserts a difference of exactly 0 when it writes them)."""
+    import os
+    import numpy as np
+    import torch
+    from oracle import sage_oracle as so
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "train_classification.npz"))
+    w, b, loss = so.train_classification(torch.from_numpy(g["w0"]), torch.from_numpy(g["b0"]), torch.from_numpy(g["feats"]),
+                                         g["labels"], list(g["orders"]))
+    assert float((w - torch.from_numpy(g["w1"])).abs().max()) <= 1e-7
+    assert float((b - torch.from_numpy(g["b1"])).abs().max()) <= 1e-7
+    assert np.isfinite(float(loss))
+    assert sorted(g["orders"][0].tolist()) == sorted(g["train"].tolist())          # shuffle permutes the train nodes (:91)
