@@ -317,18 +317,22 @@ class GraphSage(nn.Module):
         return self._run_compute(self._run_prep(nodes_dev, injected, offset_dev), weights)
 
     def _run_prep(self, nodes_dev: torch.Tensor, injected=None, offset_dev: Optional[torch.Tensor] = None,
-                  reuse: Optional[List[_Frontier]] = None) -> List[_Frontier]:
+                  reuse: Optional[List[_Frontier]] = None, num_rows: Optional[torch.Tensor] = None) -> List[_Frontier]:
         """The weight-independent half of a forward pass: sampling + unique/remap of every layer
         (src/models.py:249-251) and the layer-1 aggregation of the raw features (:260, index 1).
         `reuse`: the frontiers of an earlier call whose buffers are overwritten in place (static
         addresses: the pipelined trainer prepares step n+1 in a graph branch beside step n)."""
+        if num_rows is not None and injected is not None:
+            raise ValueError("injected samples describe a batch of known size")
         csr, table, dev = self._state()
         L, k = self.num_layers, self.num_sample
         self_mode = native.SELF_ONCE if self.gcn else native.SELF_DROP
         mode = native.AGG_MEAN if self.agg_func == 'MEAN' else native.AGG_MAX
         self._calls += 1
         layers: List[Optional[_Frontier]] = [None] * (L + 1)
-        nodes, num_rows, rows_max = nodes_dev, None, int(nodes_dev.shape[0])
+        # `num_rows` (device int32, optional): only the first num_rows[0] entries of nodes_dev are a batch -- a batch
+        # extended on the device (UnsupervisedTrainer) has a size the host never learns
+        nodes, rows_max = nodes_dev, int(nodes_dev.shape[0])
         # ---- sampling phase, batch outward (src/models.py:249-251) ----
         for l in range(L, 0, -1):
             old = reuse[l - 1] if reuse is not None else None
@@ -583,9 +587,19 @@ class UnsupervisedLoss(object):
 
     # ---- A8: batch extension (src/models.py:135-148) -------------------------------------------
     def extend_nodes(self, nodes, num_neg=6):
+        uniq, num_uniq = self.extend_device(nodes, num_neg)
+        self.target_nodes = nodes
+        batch = uniq[:int(num_uniq.item())]
+        self._pairs['batch'] = batch
+        self.unique_nodes_batch = batch.cpu().tolist()
+        return self.unique_nodes_batch
+
+    def extend_device(self, nodes, num_neg=6):
+        """The device half of extend_nodes: draws the pairs and returns (uniq buffer, device count) without a host
+        round trip -- the first count[0] entries of the buffer are the extended batch, ascending.  The pair stores
+        are installed as in extend_nodes (the python views of them materialise on first access)."""
         csr, train, is_train, dev = self._state()
         self._calls += 1
-        self.target_nodes = nodes
         seeds = _as_device_ids(nodes, dev)
         s = int(seeds.shape[0])
         n_pos = self.N_WALKS * self.WALK_LEN
@@ -596,16 +610,14 @@ class UnsupervisedLoss(object):
         lists = torch.cat([pos, neg], dim=1).contiguous()
         stride = n_pos + int(num_neg)
         uniq, num_uniq, idx, seed_idx = ops.unique_remap(seeds, None, s, lists, stride, csr.id_bits)    # :146
-        n = int(num_uniq.item())
-        batch = uniq[:n]
         self._pairs = dict(seed_idx=seed_idx, pos_idx=idx[:, :n_pos].contiguous().view(-1),
                            neg_idx=idx[:, n_pos:].contiguous().view(-1),
                            pos_ptr=torch.arange(0, (s + 1) * n_pos, n_pos, dtype=torch.int32, device=dev),
                            neg_ptr=torch.arange(0, (s + 1) * int(num_neg), int(num_neg), dtype=torch.int32, device=dev),
-                           seeds=seeds, pos=pos, neg=neg, batch=batch)
+                           seeds=seeds, pos=pos, neg=neg)
         self._host_pairs = None
-        self.unique_nodes_batch = batch.cpu().tolist()
-        return self.unique_nodes_batch
+        self.target_nodes = nodes
+        return uniq, num_uniq
 
     def set_pairs(self, unique_nodes_batch, seeds, node_positive_pairs, node_negtive_pairs):
         """Injected-pair mode: install pair stores recorded from a reference run (same

@@ -58,6 +58,61 @@ def shard_batches(train: np.ndarray, b_sz: int, steps: int, rank: int, world: in
     return np.ascontiguousarray(perm[:need].reshape(steps, world, b_sz)[:, rank, :])
 
 
+class UnsupervisedTrainer:
+    """N1 for `learn_method='unsup'` (src/utils.py:141-191, branch :175-181): one step = extend the batch with
+    random-walk positives and far negatives (device samplers), forward of the union, pair loss
+    (`unsup_loss` = 'normal' -> get_loss_sage with num_neg 100, 'margin' -> get_loss_margin with num_neg 6,
+    utils.py:119-125), backward, clip_grad_norm_(5) and SGD(lr 0.7) on the GraphSage weights (the classifier
+    receives no gradient in this mode, :181-187) -- without a host round trip: the size of the extended batch
+    stays on the device (`UnsupervisedLoss.extend_device`, `GraphSage._run_prep(num_rows=...)`), where the
+    drop-in `extend_nodes` has to hand a python list back to the reference's loop.  Launches are eager; the
+    Philox offsets of the samplers are host counters, so a captured form needs them on the device first."""
+
+    def __init__(self, model: GraphSage, unsupervised_loss, b_sz: int, *, unsup_loss: str = "normal", lr: float = 0.7,
+                 max_norm: float = 5.0):
+        if unsup_loss not in ("normal", "margin"):
+            raise ValueError("unsup_loss can be only 'margin' or 'normal'.")             # utils.py:124-125 (it exits)
+        self.model, self.unsup, self.b_sz = model, unsupervised_loss, int(b_sz)
+        self.mode = 1 if unsup_loss == "margin" else 0
+        self.num_neg = 6 if unsup_loss == "margin" else 100                              # utils.py:119-123
+        self.lr, self.max_norm = lr, max_norm
+        _, _, dev = model._state()
+        self.dev = dev
+        self.weights: List[torch.Tensor] = [getattr(model, f'sage_layer{i}').weight for i in range(1, model.num_layers + 1)]
+        for p in self.weights:
+            native.require_cuda(p, "parameters")
+        self.grads = [torch.zeros_like(w.data) for w in self.weights]
+        self.tl = ops.TensorList([w.data for w in self.weights], self.grads)
+        self.one = torch.ones((1,), dtype=torch.float32, device=dev)
+        self.loss = torch.zeros((1,), dtype=torch.float32, device=dev)
+        self.last_layers = None
+        self.last_count = None
+
+    def step_device(self, seeds) -> torch.Tensor:
+        """One training step on `seeds` (device int32 tensor, numpy array or list of b_sz node ids).  Returns the
+        device loss ([1]); nothing is copied to the host."""
+        m, u = self.model, self.unsup
+        uniq, num_uniq = u.extend_device(seeds, self.num_neg)                            # utils.py:149
+        weights = [w.detach() for w in self.weights]
+        layers = m._run_compute(m._run_prep(uniq, None, num_rows=num_uniq), weights)     # utils.py:157
+        self.last_layers, self.last_count = layers, num_uniq
+        emb = layers[-1].h
+        p = u._pairs
+        loss, coef_pos, coef_neg, num_active = ops.pair_loss_fwd(emb, m.out_size, p['seed_idx'], p['pos_ptr'], p['pos_idx'],
+                                                                 p['neg_ptr'], p['neg_idx'], self.mode, float(u.Q),
+                                                                 float(u.MARGIN))         # utils.py:175-180
+        gemb = torch.zeros_like(emb)
+        ops.pair_loss_bwd(emb, m.out_size, p['seed_idx'], p['pos_ptr'], p['pos_idx'], p['neg_ptr'], p['neg_idx'], coef_pos,
+                          coef_neg, num_active, self.one, gemb)                           # utils.py:184
+        m._run_backward(layers, gemb, weights, [True] * len(weights), grad_bufs=self.grads, own_grad=True)
+        ops.clip_sgd(self.tl, self.max_norm, self.lr, 1.0, zero_grads=True)              # utils.py:185-191
+        self.loss = loss
+        return loss
+
+    def step(self, nodes_batch) -> torch.Tensor:
+        return self.step_device(nodes_batch)
+
+
 def _zero_beside(side: torch.cuda.Stream, loss: torch.Tensor, model: GraphSage, layers):
     """Fork: zero the loss accumulator and the backward's scatter targets on `side` while the forward
     GEMMs run on the current stream.  Returns (scatter_bufs, event to wait on before the loss kernel)."""
