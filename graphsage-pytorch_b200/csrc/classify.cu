@@ -137,8 +137,9 @@ cls_fused_kernel(const float* __restrict__ emb, int64_t ld_emb, int rows, int di
                  const float* __restrict__ bias, int classes, const int64_t* __restrict__ labels,
                  const int32_t* __restrict__ label_index, float* __restrict__ logp, float* __restrict__ loss,
                  float* __restrict__ grad_emb, int64_t ld_ge, float* __restrict__ grad_w, float* __restrict__ grad_b,
-                 int mask_relu) {
+                 int mask_relu, const int32_t* __restrict__ num_rows_dev) {
   pdl_sync();
+  rows = live_rows(num_rows_dev, rows);          // a batch extended on the device: its size is only known here
   extern __shared__ __align__(16) float cls_smem[];
   const int cp = kClsMaxC + 1;                               // W^T row stride: lanes read consecutive classes
   float* w_s = cls_smem;                                     // [classes][dim]
@@ -270,7 +271,7 @@ extern "C" int gs_cls_nll_fwd_bwd(const float* emb, int64_t ld_emb, int32_t rows
                                   const int64_t* labels, const int32_t* label_index,
                                   float* logp, float* loss, float* grad_emb, int64_t ld_ge,
                                   float* grad_w, float* grad_b, float* scratch, int32_t mask_relu_input,
-                                  int32_t zero_loss, int32_t precision, gs_stream_t stream) {
+                                  int32_t zero_loss, const int32_t* num_rows_dev, int32_t precision, gs_stream_t stream) {
   if (!emb || !weight || !labels || !logp || !loss || !scratch || rows < 1 || dim < 1 || num_classes < 1)
     return GS_ERR_BAD_ARG;
   cudaStream_t st = as_stream(stream);
@@ -287,9 +288,10 @@ extern "C" int gs_cls_nll_fwd_bwd(const float* emb, int64_t ld_emb, int32_t rows
     if (ce != cudaSuccess) return static_cast<int>(ce);
     launch(cls_fused_kernel, (rows + kClsRows - 1) / kClsRows, kClsRows * 32, smem, st, 
         emb, ld_emb, rows, dim, weight, bias, num_classes, labels, label_index, logp, loss, grad_emb, ld_ge, grad_w,
-        grad_b, mask_relu_input);
+        grad_b, mask_relu_input, num_rows_dev);
     return finish_launch();
   }
+  if (num_rows_dev) return GS_ERR_UNSUPPORTED;       // device-resident row counts: one-launch heads only
   int e = gs_sage_gemm_fwd(nullptr, 0, nullptr, emb, ld_emb, dim, weight, dim, num_classes, /*gcn=*/1, nullptr, rows,
                            logp, num_classes, /*relu=*/0, precision, stream);
   if (e) return e;

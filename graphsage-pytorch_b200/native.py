@@ -20,7 +20,7 @@ AGG_MEAN, AGG_MAX = 0, 1
 SELF_KEEP, SELF_DROP, SELF_ONCE = 0, 1, 2
 PREC_FP32, PREC_TF32, PREC_TF32X3 = 0, 1, 2
 MAX_FANOUT = 32
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 _P, _I, _L, _F, _U64, _SZ = c_void_p, c_int32, c_int64, c_float, c_uint64, c_size_t
 
@@ -49,7 +49,7 @@ _SIGNATURES = {
     "gs_cls_fwd": (_I, [_P, _L, _I, _I, _P, _P, _I, _P, _I, _P]),
     "gs_cls_bwd": (_I, [_P, _P, _P, _L, _I, _I, _P, _I, _P, _L, _P, _P, _P, _I, _P]),
     "gs_nll_fwd_bwd": (_I, [_P, _P, _P, _I, _I, _P, _P, _P]),
-    "gs_cls_nll_fwd_bwd": (_I, [_P, _L, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _L, _P, _P, _P, _I, _I, _I, _P]),
+    "gs_cls_nll_fwd_bwd": (_I, [_P, _L, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _L, _P, _P, _P, _I, _I, _P, _I, _P]),
     "gs_clip_sgd": (_I, [_P, _P, _P, _I, _L, _F, _F, _F, _I, _P, _P]),
     "gs_agg_fwd_bf16_sharded": (_I, [_P, _I, _L, _L, _I, _P, _I, _P, _P, _P, _I, _P, _L, _P, _L, _P]),
     "gs_dp_state_bytes": (_SZ, []),

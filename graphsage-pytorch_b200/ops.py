@@ -244,9 +244,10 @@ def nll_fwd_bwd(logp, labels, loss=None, grad_logp=None, want_grad=True, label_i
 
 def cls_nll_fwd_bwd(emb, dim: int, weight, bias, num_classes: int, labels, label_index, loss, grad_emb, grad_w, grad_b,
                     logp=None, scratch=None, precision: int = native.PREC_TF32X3, mask_relu_input: bool = False,
-                    zero_loss: bool = True):
+                    zero_loss: bool = True, num_rows=None):
     """Classifier + NLL(mean) forward and backward in one call (src/models.py:25-27, src/utils.py:153,162-163).
-    `zero_loss=False`: the caller zeroed `loss` already (a trainer does it beside the forward GEMMs)."""
+    `zero_loss=False`: the caller zeroed `loss` already (a trainer does it beside the forward GEMMs).
+    `num_rows` (device int32): only the first num_rows[0] rows of `emb` are a batch."""
     rows = emb.shape[0]
     if logp is None:
         logp = torch.empty((rows, num_classes), dtype=F32, device=emb.device)
@@ -255,7 +256,7 @@ def cls_nll_fwd_bwd(emb, dim: int, weight, bias, num_classes: int, labels, label
     check(_lib().gs_cls_nll_fwd_bwd(ptr(emb), emb.stride(0), rows, dim, ptr(weight), ptr(bias), num_classes, ptr(labels),
                                     ptr(label_index), ptr(logp), ptr(loss), ptr(grad_emb),
                                     grad_emb.stride(0) if grad_emb is not None else 0, ptr(grad_w), ptr(grad_b),
-                                    ptr(scratch), int(mask_relu_input), int(zero_loss), precision, stream()),
+                                    ptr(scratch), int(mask_relu_input), int(zero_loss), ptr(num_rows), precision, stream()),
           "gs_cls_nll_fwd_bwd")
     return logp
 

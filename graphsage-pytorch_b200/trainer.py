@@ -59,19 +59,26 @@ def shard_batches(train: np.ndarray, b_sz: int, steps: int, rank: int, world: in
 
 
 class UnsupervisedTrainer:
-    """N1 for `learn_method='unsup'` (src/utils.py:141-191, branch :175-181): one step = extend the batch with
-    random-walk positives and far negatives (device samplers), forward of the union, pair loss
+    """N1 for `learn_method` 'unsup' and 'plus_unsup' (src/utils.py:141-191, branches :165-181): one step = extend
+    the batch with random-walk positives and far negatives (device samplers), forward of the union, pair loss
     (`unsup_loss` = 'normal' -> get_loss_sage with num_neg 100, 'margin' -> get_loss_margin with num_neg 6,
-    utils.py:119-125), backward, clip_grad_norm_(5) and SGD(lr 0.7) on the GraphSage weights (the classifier
-    receives no gradient in this mode, :181-187) -- without a host round trip: the size of the extended batch
-    stays on the device (`UnsupervisedLoss.extend_device`, `GraphSage._run_prep(num_rows=...)`), where the
-    drop-in `extend_nodes` has to hand a python list back to the reference's loop.  Launches are eager; the
-    Philox offsets of the samplers are host counters, so a captured form needs them on the device first."""
+    utils.py:119-125), for 'plus_unsup' also the classifier + NLL over the WHOLE extended batch (:161-164,
+    :169-174), backward, clip_grad_norm_(5) per model and SGD(lr 0.7) (:185-187; in 'unsup' mode the classifier
+    receives no gradient) -- without a host round trip: the size of the extended batch stays on the device
+    (`UnsupervisedLoss.extend_device`, `GraphSage._run_prep(num_rows=...)`, `gs_cls_nll_fwd_bwd(num_rows_dev)`),
+    where the drop-in `extend_nodes` has to hand a python list back to the reference's loop.  Launches are eager;
+    the Philox offsets of the samplers are host counters, so a captured form needs them on the device first."""
 
-    def __init__(self, model: GraphSage, unsupervised_loss, b_sz: int, *, unsup_loss: str = "normal", lr: float = 0.7,
-                 max_norm: float = 5.0):
+    def __init__(self, model: GraphSage, unsupervised_loss, b_sz: int, *, unsup_loss: str = "normal",
+                 learn_method: str = "unsup", classifier: Optional[Classification] = None, labels=None,
+                 lr: float = 0.7, max_norm: float = 5.0):
         if unsup_loss not in ("normal", "margin"):
             raise ValueError("unsup_loss can be only 'margin' or 'normal'.")             # utils.py:124-125 (it exits)
+        if learn_method == "sup":
+            raise ValueError("learn_method 'sup' is SupervisedTrainer / PipelinedTrainer")
+        self.plus = learn_method == "plus_unsup"            # anything else trains on the pair loss alone (:175)
+        if self.plus and (classifier is None or labels is None):
+            raise ValueError("learn_method='plus_unsup' needs the classifier and the labels")
         self.model, self.unsup, self.b_sz = model, unsupervised_loss, int(b_sz)
         self.mode = 1 if unsup_loss == "margin" else 0
         self.num_neg = 6 if unsup_loss == "margin" else 100                              # utils.py:119-123
@@ -83,6 +90,15 @@ class UnsupervisedTrainer:
             native.require_cuda(p, "parameters")
         self.grads = [torch.zeros_like(w.data) for w in self.weights]
         self.tl = ops.TensorList([w.data for w in self.weights], self.grads)
+        if self.plus:
+            lin = classifier.layer[0]
+            native.require_cuda(lin.weight, "parameters")
+            self.cls_w, self.cls_b = lin.weight, lin.bias
+            self.cls_grads = [torch.zeros_like(self.cls_w.data), torch.zeros_like(self.cls_b.data)]
+            self.tl_cls = ops.TensorList([self.cls_w.data, self.cls_b.data], self.cls_grads)
+            self.labels = (labels if isinstance(labels, torch.Tensor) else
+                           torch.from_numpy(np.asarray(labels, dtype=np.int64))).to(dev)
+            self.loss_sup = torch.zeros((1,), dtype=torch.float32, device=dev)
         self.one = torch.ones((1,), dtype=torch.float32, device=dev)
         self.loss = torch.zeros((1,), dtype=torch.float32, device=dev)
         self.last_layers = None
@@ -100,12 +116,20 @@ class UnsupervisedTrainer:
         p = u._pairs
         loss, coef_pos, coef_neg, num_active = ops.pair_loss_fwd(emb, m.out_size, p['seed_idx'], p['pos_ptr'], p['pos_idx'],
                                                                  p['neg_ptr'], p['neg_idx'], self.mode, float(u.Q),
-                                                                 float(u.MARGIN))         # utils.py:175-180
+                                                                 float(u.MARGIN))         # utils.py:169-180
         gemb = torch.zeros_like(emb)
+        if self.plus:
+            # classifier + NLL mean over the extended batch (:161-164); writes its grad_emb rows, the pair loss adds to them
+            ops.cls_nll_fwd_bwd(emb, m.out_size, self.cls_w.detach(), self.cls_b.detach(), self.cls_w.shape[0], self.labels,
+                                uniq, self.loss_sup, gemb, self.cls_grads[0], self.cls_grads[1],
+                                precision=_PRECISIONS[m.precision], mask_relu_input=False, num_rows=num_uniq)
+            loss = loss + self.loss_sup                                                   # :174
         ops.pair_loss_bwd(emb, m.out_size, p['seed_idx'], p['pos_ptr'], p['pos_idx'], p['neg_ptr'], p['neg_idx'], coef_pos,
                           coef_neg, num_active, self.one, gemb)                           # utils.py:184
         m._run_backward(layers, gemb, weights, [True] * len(weights), grad_bufs=self.grads, own_grad=True)
         ops.clip_sgd(self.tl, self.max_norm, self.lr, 1.0, zero_grads=True)              # utils.py:185-191
+        if self.plus:
+            ops.clip_sgd(self.tl_cls, self.max_norm, self.lr, 1.0, zero_grads=True)
         self.loss = loss
         return loss
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 11
+#define GS_ABI_VERSION 12
 
 #define GS_OK 0
 #define GS_ERR_BAD_ARG (-1)
@@ -217,13 +217,15 @@ int gs_nll_fwd_bwd(const float* logp, const int64_t* labels, const int32_t* labe
  * floats.  mask_relu_input != 0: emb is the ReLU output of the last SageLayer
  * (src/models.py:219) and grad_emb is returned already multiplied by (emb > 0).
  * zero_loss == 0: loss[0] was zeroed by the caller (off the critical path of a captured step)
- * and is accumulated into; != 0: it is zeroed here first. */
+ * and is accumulated into; != 0: it is zeroed here first.
+ * num_rows_dev (nullable, device int32): only the first min(*num_rows_dev, rows) rows are a batch -- the mean
+ * of the NLL is taken over them and grad_emb rows beyond them are left untouched (one-launch heads only). */
 int gs_cls_nll_fwd_bwd(const float* emb, int64_t ld_emb, int32_t rows, int32_t dim,
                        const float* weight, const float* bias, int32_t num_classes,
                        const int64_t* labels, const int32_t* label_index,
                        float* logp, float* loss, float* grad_emb, int64_t ld_ge,
                        float* grad_w, float* grad_b, float* scratch, int32_t mask_relu_input, int32_t zero_loss,
-                       int32_t precision, gs_stream_t stream);
+                       const int32_t* num_rows_dev, int32_t precision, gs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Update step of src/utils.py:185-187: per-model clip_grad_norm_(max_norm) then SGD.

@@ -454,29 +454,36 @@ def test_train_classification_matches_the_reference_loop(M, use_graph):
 # ------------------------------------------------------------------------------------------------
 # N1, learn_method='unsup': the device-resident trainer against the drop-in classes driven like apply_model
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize('case,unsup_loss', [('pubmed_max_unsup', 'normal'), ('cora_max_plus', 'margin'),
-                                             ('cora_gcn_margin', 'margin')])
-def test_unsupervised_trainer_matches_the_drop_in_loop(M, case, unsup_loss):
+@pytest.mark.parametrize('case,unsup_loss,learn', [('pubmed_max_unsup', 'normal', 'unsup'), ('cora_max_plus', 'margin', 'unsup'),
+                                                   ('cora_gcn_margin', 'margin', 'plus_unsup'),
+                                                   ('cora_max_plus', 'normal', 'plus_unsup')])
+def test_unsupervised_trainer_matches_the_drop_in_loop(M, case, unsup_loss, learn):
     """Same seeds and Philox offsets on both sides, so both draw the same pairs and neighbours: the trainer
     (extended batch size never leaves the device) must take the same steps as the body of src/utils.py:141-191
     run with the drop-in classes, torch's clip_grad_norm_ and torch's SGD."""
     from graphsage_b200.trainer import UnsupervisedTrainer
     dev = torch.device('cuda:0')
     inp = cases.build_inputs(case)
+    labels = inp['labels']
     num_neg = 100 if unsup_loss == 'normal' else 6
-    model_a, _, adj = build_models(M, inp, dev, seed=31)
-    model_b, _, _ = build_models(M, inp, dev, adj=adj, seed=31)
+    model_a, cls_a, adj = build_models(M, inp, dev, seed=31)
+    model_b, cls_b, _ = build_models(M, inp, dev, adj=adj, seed=31)
     unsup_a = M.UnsupervisedLoss(adj, inp['train'], dev, seed=77)
     unsup_b = M.UnsupervisedLoss(adj, inp['train'], dev, seed=77)
-    opt = torch.optim.SGD(model_a.parameters(), lr=0.7)
-    trainer = UnsupervisedTrainer(model_b, unsup_b, 20, unsup_loss=unsup_loss)
+    opt = torch.optim.SGD(list(model_a.parameters()) + list(cls_a.parameters()), lr=0.7)
+    trainer = UnsupervisedTrainer(model_b, unsup_b, 20, unsup_loss=unsup_loss, learn_method=learn, classifier=cls_b,
+                                  labels=labels)
     for step in range(3):
         seeds = inp['train'][step * 20:(step + 1) * 20]
         batch = np.asarray(list(unsup_a.extend_nodes(seeds, num_neg=num_neg)))              # utils.py:149
         embs = model_a(batch)                                                              # utils.py:157
         loss_a = unsup_a.get_loss_margin(embs, batch) if unsup_loss == 'margin' else unsup_a.get_loss_sage(embs, batch)
+        if learn == 'plus_unsup':                                                          # utils.py:161-174
+            logp = cls_a(embs)
+            loss_a = -torch.sum(logp[range(logp.size(0)), labels[batch]], 0) / len(batch) + loss_a
         loss_a.backward()                                                                  # utils.py:184
-        torch.nn.utils.clip_grad_norm_(model_a.parameters(), 5)                            # utils.py:185-186
+        for mdl in (model_a, cls_a):
+            torch.nn.utils.clip_grad_norm_(mdl.parameters(), 5)                            # utils.py:185-186
         opt.step()
         opt.zero_grad()
         loss_b = trainer.step_device(seeds)
@@ -485,5 +492,9 @@ def test_unsupervised_trainer_matches_the_drop_in_loop(M, case, unsup_loss):
         for i in range(1, inp['spec']['num_layers'] + 1):
             wa, wb = getattr(model_a, f'sage_layer{i}').weight, getattr(model_b, f'sage_layer{i}').weight
             assert rel(wb, wa) <= TOL, f'step {step} layer {i}'
+        assert rel(cls_b.layer[0].weight, cls_a.layer[0].weight) <= TOL       # untouched in 'unsup' mode, trained in plus_unsup
+        assert rel(cls_b.layer[0].bias, cls_a.layer[0].bias) <= TOL
     with pytest.raises(ValueError):
         UnsupervisedTrainer(model_b, unsup_b, 20, unsup_loss='hinge')
+    with pytest.raises(ValueError):
+        UnsupervisedTrainer(model_b, unsup_b, 20, learn_method='plus_unsup')
