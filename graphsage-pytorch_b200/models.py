@@ -571,6 +571,7 @@ class UnsupervisedLoss(object):
         self._dev = None
         self._pairs = None
         self._host_pairs = None
+        self.neg_hops = None             # None: negative_hops() decides (5 on Cora / Pubmed, as the reference)
 
     def _state(self):
         if self._dev is None:
@@ -605,7 +606,7 @@ class UnsupervisedLoss(object):
         n_pos = self.N_WALKS * self.WALK_LEN
         pos = ops.random_walk_pos(csr.rowptr, csr.col, csr.num_nodes, seeds, self.N_WALKS, self.WALK_LEN, is_train,
                                   self.seed, (self._calls << 8) | 1)                            # :169-186
-        neg, _ = ops.negative_sample(csr.rowptr, csr.col, csr.num_nodes, seeds, self.N_WALK_LEN, int(num_neg), train,
+        neg, _ = ops.negative_sample(csr.rowptr, csr.col, csr.num_nodes, seeds, self.negative_hops(), int(num_neg), train,
                                      self.seed, (self._calls << 8) | 2)                         # :153-167
         lists = torch.cat([pos, neg], dim=1).contiguous()
         stride = n_pos + int(num_neg)
@@ -618,6 +619,28 @@ class UnsupervisedLoss(object):
         self._host_pairs = None
         self.target_nodes = nodes
         return uniq, num_uniq
+
+    #: budget of adjacency entries one seed's ball may span before the ball is shrunk (see negative_hops)
+    NEG_BALL_BUDGET = 10_000
+
+    def negative_hops(self) -> int:
+        """Radius of the ball a seed's negatives must lie outside.  The reference excludes the N_WALK_LEN = 5 hop
+        ball (src/models.py:155-162), which is what runs on Cora and Pubmed (mean degree ~4: ~10^3 entries per
+        seed).  On a dense graph that ball is the whole graph -- the reference then dies on an empty `far_nodes`
+        (cfg-3, cfg-4) and a per-seed BFS would walk every edge -- so the radius is the largest
+        h <= N_WALK_LEN whose expected ball, mean_degree^h, stays within NEG_BALL_BUDGET entries, and at least 1
+        (negatives are then train nodes outside the seed's own neighbourhood).  A documented deviation that only
+        takes effect where the reference cannot run; set `neg_hops` to force a radius."""
+        forced = getattr(self, 'neg_hops', None)
+        if forced is not None:
+            return int(forced)
+        csr = self._state()[0]
+        mean_deg = max(float(csr.nnz) / max(csr.num_nodes, 1), 1.0)
+        h, ball = 0, 1.0
+        while h < self.N_WALK_LEN and ball * mean_deg <= self.NEG_BALL_BUDGET:
+            ball *= mean_deg
+            h += 1
+        return max(h, 1)
 
     def set_pairs(self, unique_nodes_batch, seeds, node_positive_pairs, node_negtive_pairs):
         """Injected-pair mode: install pair stores recorded from a reference run (same

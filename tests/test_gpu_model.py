@@ -498,3 +498,38 @@ def test_unsupervised_trainer_matches_the_drop_in_loop(M, case, unsup_loss, lear
         UnsupervisedTrainer(model_b, unsup_b, 20, unsup_loss='hinge')
     with pytest.raises(ValueError):
         UnsupervisedTrainer(model_b, unsup_b, 20, learn_method='plus_unsup')
+
+
+def test_negative_radius_shrinks_on_dense_graphs_only(M):
+    """Cora / Pubmed keep the reference's 5-hop exclusion ball (src/models.py:155-162); on a dense graph, where that
+    ball is the whole graph and the reference dies on an empty far set, negatives are train nodes outside the seed's
+    own neighbourhood (UnsupervisedLoss.negative_hops, a documented deviation)."""
+    from graphsage_b200.graph import AdjCSR
+    dev = torch.device('cuda:0')
+    for case in ('cora_mean_sup', 'pubmed_max_unsup'):
+        inp = cases.build_inputs(case)
+        assert M.UnsupervisedLoss(AdjCSR(inp['rowptr'], inp['col']), inp['train'], dev).negative_hops() == 5
+    rng = np.random.default_rng(9)
+    n, deg = 3000, 300
+    nbrs = [set() for _ in range(n)]
+    for v in range(n):
+        for u in rng.choice(n, size=deg // 2, replace=False):
+            if int(u) != v:
+                nbrs[v].add(int(u))
+                nbrs[int(u)].add(v)
+    adj = {v: s for v, s in enumerate(nbrs)}
+    train = np.sort(rng.permutation(n)[:2000])
+    unsup = M.UnsupervisedLoss(adj, train, dev, seed=4)
+    assert unsup.negative_hops() == 1
+    seeds = train[:32]
+    batch = unsup.extend_nodes(seeds, num_neg=6)
+    assert set(int(s) for s in seeds) <= set(batch)
+    train_set = set(train.tolist())
+    for s in seeds.tolist():
+        negs = [b for _, b in unsup.node_negtive_pairs[s]]
+        assert len(negs) == 6 and len(set(negs)) == 6
+        assert all(b in train_set and b != s and b not in nbrs[s] for b in negs)
+        assert all(b in nbrs[s] and b in train_set for _, b in unsup.node_positive_pairs[s])
+    unsup.neg_hops = 5                                   # forcing the reference's radius: the ball is everything
+    unsup.extend_nodes(seeds, num_neg=6)
+    assert all(len(unsup.node_negtive_pairs[s]) == 0 for s in seeds.tolist())
