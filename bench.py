@@ -572,6 +572,109 @@ def run_infer(args):
     print(json.dumps(line), flush=True)
 
 
+def run_cfg4(args):
+    """`--workload cfg4` (BASELINE configs[3], not the headline): Reddit-shaped synthetic graph (233K nodes, 114M CSR
+    entries, 602 features), gcn=True MEAN, learn_method=plus_unsup with random-walk positives and the margin loss,
+    through trainer.UnsupervisedTrainer (device-resident step, eager launches).  The reference cannot run this
+    configuration (its 5-hop exclusion ball is the whole graph: empty far set, src/models.py:164); negatives here are
+    train nodes outside the seed's own neighbourhood (UnsupervisedLoss.negative_hops -> 1)."""
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the gsage_b200 hot path has no CPU fallback")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    import graphsage_b200  # noqa: F401
+    from graphsage_b200 import models, native, ops
+    from graphsage_b200.graph import AdjCSR
+    from graphsage_b200.trainer import UnsupervisedTrainer
+    import graphsage_b200.synth as synth
+    native.load()
+    cfg = dict(synth.CONFIGS["cfg4_reddit"])
+    n = max(2000, int(round(cfg["n"] * args.scale)))
+    edges = max(4 * n, int(round(cfg["edges"] * args.scale)))
+    t0 = time.time()
+    rowptr, col = synth.powerlaw_graph(n, edges, seed=0, cache_dir=CACHE_DIR)
+    feats = synth.features_normal(n, cfg["feats"], seed=1)
+    labels = synth.labels_uniform(n, cfg["classes"], seed=2)
+    _, _, train = synth.split_nodes(n, seed=3)
+    log(f"[bench] cfg4 n={n} nnz={len(col)} feats={feats.shape} built in {time.time() - t0:.1f}s")
+    b_sz, K, W = args.b_sz, max(4, min(args.steps, 50)), max(3, min(args.warmup, 5))
+    torch.manual_seed(SEED)
+    adj = AdjCSR(rowptr, col)
+    model = models.GraphSage(2, cfg["feats"], cfg["hidden"], torch.from_numpy(feats).to(dev), adj, dev, gcn=True,
+                             agg_func="MEAN", seed=SEED, precision=args.precision).to(dev)
+    cls = models.Classification(cfg["hidden"], cfg["classes"]).to(dev)
+    unsup = models.UnsupervisedLoss(adj, train, dev, seed=SEED)
+    trainer = UnsupervisedTrainer(model, unsup, b_sz, unsup_loss="margin", learn_method="plus_unsup", classifier=cls,
+                                  labels=labels)
+    host_batches = batches_for(train, b_sz, 2 * (K + W) + 1, 0, 1)
+    dev_batches = torch.from_numpy(host_batches.astype(np.int32)).to(dev)
+    for i in range(W):
+        trainer.step_device(dev_batches[i])
+    torch.cuda.synchronize(dev)
+    native.launch_count_reset()
+    sampler = ClockSampler(0)
+    sampler.start()
+    t_begin = time.time()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(K):
+        loss = trainer.step_device(dev_batches[W + i])
+    b.record()
+    torch.cuda.synchronize(dev)
+    launches = int(native.launch_count())
+    ms = a.elapsed_time(b)
+    # e2e: host numpy seeds in, loss value out, every step
+    a.record()
+    last = 0.0
+    for i in range(K):
+        last = float(trainer.step(host_batches[W + K + i]).item())
+    b.record()
+    torch.cuda.synchronize(dev)
+    ms_e2e = a.elapsed_time(b)
+    clk = sampler.stop(t_begin, time.time())
+    # layer-1 aggregation of the last step, relaunched alone: rows of 602 floats (2.4 KB), self row included (gcn)
+    fr = trainer.last_layers[0]
+    rows = int(fr.num_rows.item()) if fr.num_rows is not None else fr.rows_max
+    nnz = int(fr.cnt[:rows].sum().item())
+    d = cfg["feats"]
+    bytes_ = nnz * d * 4 + rows * d * 4 + nnz * 4 + (rows + 1) * 4
+    out = torch.empty_like(fr.agg)
+    table = model._state()[1]
+    for _ in range(2):
+        ops.agg_fwd(table, d, fr.nbr_idx, fr.stride, fr.cnt, fr.num_rows, fr.rows_max, native.AGG_MEAN, out=out)
+    torch.cuda.synchronize(dev)
+    a.record()
+    for _ in range(5):
+        ops.agg_fwd(table, d, fr.nbr_idx, fr.stride, fr.cnt, fr.num_rows, fr.rows_max, native.AGG_MEAN, out=out)
+    b.record()
+    torch.cuda.synchronize(dev)
+    t_agg = a.elapsed_time(b) * 1e-3 / 5
+    peak = 6544.0
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    line = {"metric": "seed_nodes_per_sec_fwd_bwd", "value": b_sz * K / (ms * 1e-3), "unit": "seed nodes/s", "n_gpus": 1,
+            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (tcgen05 3xTF32 split, fp32-faithful)", "data": "synthetic",
+            "config": {"workload": "cfg4_reddit" if args.scale == 1.0 else f"cfg4_reddit@scale{args.scale}", "nodes": n,
+                       "csr_entries": int(len(col)), "feats": d, "hidden": cfg["hidden"], "classes": cfg["classes"],
+                       "layers": 2, "fanout": 10, "agg": "MEAN", "gcn": True, "learn_method": "plus_unsup",
+                       "unsup_loss": "margin", "num_neg": 6, "negative_radius_hops": unsup.negative_hops(),
+                       "b_sz_per_gpu": b_sz, "extended_batch_rows": int(trainer.last_count.item()), "cuda_graph": False,
+                       "l2_policy": "feature table 561 MB >> 126 MB L2; fresh seeds every step"},
+            "e2e": {"value": b_sz * K / (ms_e2e * 1e-3), "unit": "seed nodes/s", "ms_per_step": ms_e2e / K,
+                    "h2d_bytes_per_step": int(b_sz * 4), "d2h_bytes_per_step": 4},
+            "gpu_launches": launches, "launches_per_step": launches // K, "loss": float(loss.item()), "loss_e2e": last,
+            "roofline": {"bound": "hbm", "kernel": "agg_fwd_kernel<MEAN> (layer 1, gcn: self row included)",
+                         "achieved": bytes_ / t_agg / 1e9, "peak": peak, "unit": "GB/s", "frac": bytes_ / t_agg / 1e9 / peak,
+                         "traffic": None, "bytes_per_launch": float(bytes_), "us_per_launch": t_agg * 1e6, "rows": rows,
+                         "note": "last step's layer-1 frontier relaunched alone 5x (gathers >> L2)"},
+            "cpu_baseline": None, "clocks": clk}
+    print(json.dumps(line), flush=True)
+
+
 def dump_timeline(torch, native, PipelinedTrainer, model, cls, labels, b_sz, dev_batches, path):
     """Diagnostics (not a bench number): capture the pipelined step with a %globaltimer marker behind every
     launch, replay it, and write per-branch completion times of the last two-step replay to `path`."""
@@ -760,7 +863,7 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="gradient exchange + update: peer = one fused kernel over NVLink peer memory (default); "
                          "nccl = library all-reduce followed by the separate norm/update kernels (comparison)")
-    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg5", "infer"],
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg5", "infer", "cfg4"],
                     help="cfg3 = ogbn-products-shaped (the headline, BASELINE configs[2]); cfg5 = row-partitioned bf16 "
                          "features with P2P NVLink gather (configs[4]; b_sz 8192 per GPU unless --b_sz is given)")
     ap.add_argument("--cfg5-nodes-per-gpu", type=int, default=12_500_000,
@@ -781,6 +884,8 @@ def main():
         run_cfg5(args)
     elif args.workload == "infer":
         run_infer(args)
+    elif args.workload == "cfg4":
+        run_cfg4(args)
     else:
         run_ours(args)
 
