@@ -575,7 +575,7 @@ def run_infer(args):
 def run_cfg4(args):
     """`--workload cfg4` (BASELINE configs[3], not the headline): Reddit-shaped synthetic graph (233K nodes, 114M CSR
     entries, 602 features), gcn=True MEAN, learn_method=plus_unsup with random-walk positives and the margin loss,
-    through trainer.UnsupervisedTrainer (device-resident step, eager launches).  The reference cannot run this
+    through trainer.UnsupervisedTrainer (device-resident step, one CUDA graph replay per step; --no-graph: eager).  The reference cannot run this
     configuration (its 5-hop exclusion ball is the whole graph: empty far set, src/models.py:164); negatives here are
     train nodes outside the seed's own neighbourhood (UnsupervisedLoss.negative_hops -> 1)."""
     import torch
@@ -606,7 +606,7 @@ def run_cfg4(args):
     cls = models.Classification(cfg["hidden"], cfg["classes"]).to(dev)
     unsup = models.UnsupervisedLoss(adj, train, dev, seed=SEED)
     trainer = UnsupervisedTrainer(model, unsup, b_sz, unsup_loss="margin", learn_method="plus_unsup", classifier=cls,
-                                  labels=labels)
+                                  labels=labels, use_graph=not args.no_graph)
     host_batches = batches_for(train, b_sz, 2 * (K + W) + 1, 0, 1)
     dev_batches = torch.from_numpy(host_batches.astype(np.int32)).to(dev)
     for i in range(W):
@@ -662,11 +662,14 @@ def run_cfg4(args):
                        "csr_entries": int(len(col)), "feats": d, "hidden": cfg["hidden"], "classes": cfg["classes"],
                        "layers": 2, "fanout": 10, "agg": "MEAN", "gcn": True, "learn_method": "plus_unsup",
                        "unsup_loss": "margin", "num_neg": 6, "negative_radius_hops": unsup.negative_hops(),
-                       "b_sz_per_gpu": b_sz, "extended_batch_rows": int(trainer.last_count.item()), "cuda_graph": False,
+                       "b_sz_per_gpu": b_sz, "extended_batch_rows": int(trainer.last_count.item()),
+                       "cuda_graph": bool(trainer.use_graph),
                        "l2_policy": "feature table 561 MB >> 126 MB L2; fresh seeds every step"},
             "e2e": {"value": b_sz * K / (ms_e2e * 1e-3), "unit": "seed nodes/s", "ms_per_step": ms_e2e / K,
                     "h2d_bytes_per_step": int(b_sz * 4), "d2h_bytes_per_step": 4},
-            "gpu_launches": launches, "launches_per_step": launches // K, "loss": float(loss.item()), "loss_e2e": last,
+            "gpu_launches": (trainer.launches_per_step * K if trainer.use_graph else launches),
+            "launches_per_step": (trainer.launches_per_step if trainer.use_graph else launches // K),
+            "loss": float(loss.item()), "loss_e2e": last,
             "roofline": {"bound": "hbm", "kernel": "agg_fwd_kernel<MEAN> (layer 1, gcn: self row included)",
                          "achieved": bytes_ / t_agg / 1e9, "peak": peak, "unit": "GB/s", "frac": bytes_ / t_agg / 1e9 / peak,
                          "traffic": None, "bytes_per_launch": float(bytes_), "us_per_launch": t_agg * 1e6, "rows": rows,

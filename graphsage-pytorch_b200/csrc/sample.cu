@@ -93,8 +93,9 @@ sample_neighbors_kernel(const int64_t* __restrict__ rowptr, const int32_t* __res
 __global__ void random_walk_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                    int64_t num_nodes, const int32_t* __restrict__ seeds, int num_seeds, int n_walks,
                                    int walk_len, const uint8_t* __restrict__ is_train, uint64_t seed, uint64_t offset,
-                                   int32_t* __restrict__ pos) {
+                                   const int64_t* __restrict__ offset_dev, int32_t* __restrict__ pos) {
   pdl_sync();
+  if (offset_dev != nullptr) offset += static_cast<uint64_t>(__ldg(offset_dev)) << 8;     // step counter of a captured loop
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= num_seeds * n_walks) return;
   const int s = t / n_walks;
@@ -134,8 +135,10 @@ __global__ void __launch_bounds__(kNegThreads)
 negative_sample_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t num_nodes,
                        const int32_t* __restrict__ seeds, int hops, int num_neg,
                        const int32_t* __restrict__ train_nodes, int num_train, uint64_t seed, uint64_t offset,
-                       int32_t* __restrict__ neg, int32_t* __restrict__ neg_cnt, uint32_t* __restrict__ workspace) {
+                       const int64_t* __restrict__ offset_dev, int32_t* __restrict__ neg, int32_t* __restrict__ neg_cnt,
+                       uint32_t* __restrict__ workspace) {
   pdl_sync();
+  if (offset_dev != nullptr) offset += static_cast<uint64_t>(__ldg(offset_dev)) << 8;
   const int s = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kNegThreads / 32;
   const int64_t words = (num_nodes + 31) / 32;
@@ -293,14 +296,14 @@ extern "C" int gs_sample_neighbors(const int64_t* rowptr, const int32_t* col, in
 
 extern "C" int gs_random_walk_pos(const int64_t* rowptr, const int32_t* col, int64_t num_nodes,
                                   const int32_t* seeds, int32_t num_seeds, int32_t n_walks, int32_t walk_len,
-                                  const uint8_t* is_train, uint64_t seed, uint64_t offset, int32_t* pos,
-                                  gs_stream_t stream) {
+                                  const uint8_t* is_train, uint64_t seed, uint64_t offset, const int64_t* offset_dev,
+                                  int32_t* pos, gs_stream_t stream) {
   if (!rowptr || !col || !seeds || !is_train || !pos) return GS_ERR_BAD_ARG;
   if (num_seeds < 0 || n_walks < 1 || walk_len < 1) return GS_ERR_BAD_ARG;
   if (num_seeds == 0) return GS_OK;
   const int total = num_seeds * n_walks, threads = 128;
   launch(random_walk_kernel, (total + threads - 1) / threads, threads, 0, as_stream(stream), 
-      rowptr, col, num_nodes, seeds, num_seeds, n_walks, walk_len, is_train, seed, offset, pos);
+      rowptr, col, num_nodes, seeds, num_seeds, n_walks, walk_len, is_train, seed, offset, offset_dev, pos);
   return finish_launch();
 }
 
@@ -312,14 +315,14 @@ extern "C" size_t gs_negative_workspace_bytes(int64_t num_nodes, int32_t num_see
 extern "C" int gs_negative_sample(const int64_t* rowptr, const int32_t* col, int64_t num_nodes,
                                   const int32_t* seeds, int32_t num_seeds, int32_t hops, int32_t num_neg,
                                   const int32_t* train_nodes, int32_t num_train, uint64_t seed, uint64_t offset,
-                                  int32_t* neg, int32_t* neg_cnt, void* workspace, size_t workspace_bytes,
-                                  gs_stream_t stream) {
+                                  const int64_t* offset_dev, int32_t* neg, int32_t* neg_cnt, void* workspace,
+                                  size_t workspace_bytes, gs_stream_t stream) {
   if (!rowptr || !col || !seeds || !train_nodes || !neg || !neg_cnt || !workspace) return GS_ERR_BAD_ARG;
   if (num_neg < 1 || num_neg > GS_MAX_FANOUT * 4 || hops < 0 || num_seeds < 0 || num_train < 0) return GS_ERR_BAD_ARG;
   if (workspace_bytes < gs_negative_workspace_bytes(num_nodes, num_seeds)) return GS_ERR_WORKSPACE;
   if (num_seeds == 0) return GS_OK;
   launch(negative_sample_kernel, num_seeds, kNegThreads, 0, as_stream(stream), 
-      rowptr, col, num_nodes, seeds, hops, num_neg, train_nodes, num_train, seed, offset, neg, neg_cnt,
+      rowptr, col, num_nodes, seeds, hops, num_neg, train_nodes, num_train, seed, offset, offset_dev, neg, neg_cnt,
       static_cast<uint32_t*>(workspace));
   return finish_launch();
 }

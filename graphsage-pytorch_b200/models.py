@@ -595,19 +595,21 @@ class UnsupervisedLoss(object):
         self.unique_nodes_batch = batch.cpu().tolist()
         return self.unique_nodes_batch
 
-    def extend_device(self, nodes, num_neg=6):
+    def extend_device(self, nodes, num_neg=6, offset_dev=None):
         """The device half of extend_nodes: draws the pairs and returns (uniq buffer, device count) without a host
         round trip -- the first count[0] entries of the buffer are the extended batch, ascending.  The pair stores
-        are installed as in extend_nodes (the python views of them materialise on first access)."""
+        are installed as in extend_nodes (the python views of them materialise on first access).  `offset_dev`
+        (device int64 step counter) is added, shifted by 8, to the samplers' Philox offsets: a captured step draws
+        new pairs at every replay."""
         csr, train, is_train, dev = self._state()
         self._calls += 1
         seeds = _as_device_ids(nodes, dev)
         s = int(seeds.shape[0])
         n_pos = self.N_WALKS * self.WALK_LEN
         pos = ops.random_walk_pos(csr.rowptr, csr.col, csr.num_nodes, seeds, self.N_WALKS, self.WALK_LEN, is_train,
-                                  self.seed, (self._calls << 8) | 1)                            # :169-186
+                                  self.seed, (self._calls << 8) | 1, offset_dev=offset_dev)      # :169-186
         neg, _ = ops.negative_sample(csr.rowptr, csr.col, csr.num_nodes, seeds, self.negative_hops(), int(num_neg), train,
-                                     self.seed, (self._calls << 8) | 2)                         # :153-167
+                                     self.seed, (self._calls << 8) | 2, offset_dev=offset_dev)   # :153-167
         lists = torch.cat([pos, neg], dim=1).contiguous()
         stride = n_pos + int(num_neg)
         uniq, num_uniq, idx, seed_idx = ops.unique_remap(seeds, None, s, lists, stride, csr.id_bits)    # :146

@@ -20,7 +20,7 @@ AGG_MEAN, AGG_MAX = 0, 1
 SELF_KEEP, SELF_DROP, SELF_ONCE = 0, 1, 2
 PREC_FP32, PREC_TF32, PREC_TF32X3 = 0, 1, 2
 MAX_FANOUT = 32
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 _P, _I, _L, _F, _U64, _SZ = c_void_p, c_int32, c_int64, c_float, c_uint64, c_size_t
 
@@ -62,9 +62,9 @@ _SIGNATURES = {
     "gs_peer_export": (_I, [_P, _P]),
     "gs_peer_open": (_I, [_P, _P]),
     "gs_peer_close": (_I, [_P]),
-    "gs_random_walk_pos": (_I, [_P, _P, _L, _P, _I, _I, _I, _P, _U64, _U64, _P, _P]),
+    "gs_random_walk_pos": (_I, [_P, _P, _L, _P, _I, _I, _I, _P, _U64, _U64, _P, _P, _P]),
     "gs_negative_workspace_bytes": (_SZ, [_L, _I]),
-    "gs_negative_sample": (_I, [_P, _P, _L, _P, _I, _I, _I, _P, _I, _U64, _U64, _P, _P, _P, _SZ, _P]),
+    "gs_negative_sample": (_I, [_P, _P, _L, _P, _I, _I, _I, _P, _I, _U64, _U64, _P, _P, _P, _P, _SZ, _P]),
     "gs_pair_loss_fwd": (_I, [_P, _L, _I, _P, _I, _P, _P, _P, _P, _I, _F, _F, _P, _P, _P, _P, _P, _P]),
     "gs_pair_loss_bwd": (_I, [_P, _L, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
 }

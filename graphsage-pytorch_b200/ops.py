@@ -283,13 +283,13 @@ def clip_sgd(tl: TensorList, max_norm: float, lr: float, grad_div: float = 1.0, 
 # K5 / K6
 # ----------------------------------------------------------------------------------------------
 def random_walk_pos(rowptr, col, num_nodes: int, seeds, n_walks: int, walk_len: int, is_train, seed: int, offset: int,
-                    out=None):
+                    out=None, offset_dev=None):
     n = seeds.shape[0]
     if out is None:
         out = torch.empty((n, n_walks * walk_len), dtype=I32, device=seeds.device)
     check(_lib().gs_random_walk_pos(ptr(rowptr), ptr(col), num_nodes, ptr(seeds), n, n_walks, walk_len, ptr(is_train),
-                                    seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF, ptr(out), stream()),
-          "gs_random_walk_pos")
+                                    seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF, ptr(offset_dev), ptr(out),
+                                    stream()), "gs_random_walk_pos")
     return out
 
 
@@ -298,7 +298,7 @@ def negative_workspace_bytes(num_nodes: int, num_seeds: int) -> int:
 
 
 def negative_sample(rowptr, col, num_nodes: int, seeds, hops: int, num_neg: int, train_nodes, seed: int, offset: int,
-                    workspace=None, out=None, out_cnt=None):
+                    workspace=None, out=None, out_cnt=None, offset_dev=None):
     n = seeds.shape[0]
     dev = seeds.device
     if workspace is None:
@@ -309,7 +309,7 @@ def negative_sample(rowptr, col, num_nodes: int, seeds, hops: int, num_neg: int,
         out_cnt = torch.empty((n,), dtype=I32, device=dev)
     check(_lib().gs_negative_sample(ptr(rowptr), ptr(col), num_nodes, ptr(seeds), n, hops, num_neg, ptr(train_nodes),
                                     train_nodes.shape[0], seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF,
-                                    ptr(out), ptr(out_cnt), ptr(workspace), workspace.numel(), stream()),
+                                    ptr(offset_dev), ptr(out), ptr(out_cnt), ptr(workspace), workspace.numel(), stream()),
           "gs_negative_sample")
     return out, out_cnt
 

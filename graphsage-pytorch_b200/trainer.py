@@ -66,12 +66,14 @@ class UnsupervisedTrainer:
     :169-174), backward, clip_grad_norm_(5) per model and SGD(lr 0.7) (:185-187; in 'unsup' mode the classifier
     receives no gradient) -- without a host round trip: the size of the extended batch stays on the device
     (`UnsupervisedLoss.extend_device`, `GraphSage._run_prep(num_rows=...)`, `gs_cls_nll_fwd_bwd(num_rows_dev)`),
-    where the drop-in `extend_nodes` has to hand a python list back to the reference's loop.  Launches are eager;
-    the Philox offsets of the samplers are host counters, so a captured form needs them on the device first."""
+    where the drop-in `extend_nodes` has to hand a python list back to the reference's loop.
+    `use_graph=True` captures the whole step (about 27 launches of ours) as one CUDA graph: every buffer is sized by
+    its static bound, the batch is copied into a static seed buffer, and the samplers add a device-resident step
+    counter to their Philox offsets (`offset_dev`), so replay t draws what the eager step t draws."""
 
     def __init__(self, model: GraphSage, unsupervised_loss, b_sz: int, *, unsup_loss: str = "normal",
                  learn_method: str = "unsup", classifier: Optional[Classification] = None, labels=None,
-                 lr: float = 0.7, max_norm: float = 5.0):
+                 lr: float = 0.7, max_norm: float = 5.0, use_graph: bool = False):
         if unsup_loss not in ("normal", "margin"):
             raise ValueError("unsup_loss can be only 'margin' or 'normal'.")             # utils.py:124-125 (it exits)
         if learn_method == "sup":
@@ -103,14 +105,56 @@ class UnsupervisedTrainer:
         self.loss = torch.zeros((1,), dtype=torch.float32, device=dev)
         self.last_layers = None
         self.last_count = None
+        self.use_graph = bool(use_graph)
+        self.seeds = torch.zeros((self.b_sz,), dtype=torch.int32, device=dev)        # static input of the captured step
+        self.step_counter = torch.zeros((1,), dtype=torch.int64, device=dev)          # Philox offset of the captured step
+        self._loss_out = torch.zeros((1,), dtype=torch.float32, device=dev)
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self.launches_per_step = 0
 
     def step_device(self, seeds) -> torch.Tensor:
         """One training step on `seeds` (device int32 tensor, numpy array or list of b_sz node ids).  Returns the
         device loss ([1]); nothing is copied to the host."""
+        if not self.use_graph:
+            return self._body(seeds, None)
+        from .models import _as_device_ids
+        ids = _as_device_ids(seeds, self.dev)
+        if ids.shape[0] != self.b_sz:
+            raise ValueError(f"the captured step takes batches of exactly {self.b_sz} seeds")
+        self.seeds.copy_(ids, non_blocking=True)
+        if self._graph is None:
+            self._capture()
+        self._graph.replay()
+        self.loss = self._loss_out
+        return self._loss_out
+
+    def _capture(self):
         m, u = self.model, self.unsup
-        uniq, num_uniq = u.extend_device(seeds, self.num_neg)                            # utils.py:149
+        params = [w.data for w in self.weights] + ([self.cls_w.data, self.cls_b.data] if self.plus else [])
+        saved = [p.clone() for p in params]
+        calls = (u._calls, m._calls)
+        side = torch.cuda.Stream(device=self.dev)                 # warm-up off the capture: allocator, lazy module loads
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._body(self.seeds, self.step_counter)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        for p, q in zip(params, saved):                            # the warm-up took a real step: undo it
+            p.copy_(q)
+        u._calls, m._calls = calls                                 # the captured launches carry call number calls + 1
+        before = native.launch_count()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            loss = self._body(self.seeds, self.step_counter)
+            self._loss_out.copy_(loss.reshape(1))
+            self.step_counter.add_(1)
+        self.launches_per_step = native.launch_count() - before
+
+    def _body(self, seeds, offset_dev) -> torch.Tensor:
+        m, u = self.model, self.unsup
+        uniq, num_uniq = u.extend_device(seeds, self.num_neg, offset_dev=offset_dev)      # utils.py:149
         weights = [w.detach() for w in self.weights]
-        layers = m._run_compute(m._run_prep(uniq, None, num_rows=num_uniq), weights)     # utils.py:157
+        layers = m._run_compute(m._run_prep(uniq, None, offset_dev=offset_dev, num_rows=num_uniq), weights)   # utils.py:157
         self.last_layers, self.last_count = layers, num_uniq
         emb = layers[-1].h
         p = u._pairs

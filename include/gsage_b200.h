@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 12
+#define GS_ABI_VERSION 13
 
 #define GS_OK 0
 #define GS_ERR_BAD_ARG (-1)
@@ -285,16 +285,19 @@ int gs_peer_close(void* ptr);
  * gs_negative_sample: `num_neg` distinct train nodes outside the `hops`-hop ball of each
  *   seed (:155-164).  The ball is marked in a per-seed bitmap of `num_nodes` bits held in
  *   `workspace`; when fewer than num_neg far train nodes exist all of them are returned.
+ * offset_dev (nullable, device int64), as in gs_sample_neighbors: the Philox offset used is
+ *   offset + (*offset_dev << 8), so a captured loop draws fresh pairs every replay.
  * ------------------------------------------------------------------------------------ */
 int gs_random_walk_pos(const int64_t* rowptr, const int32_t* col, int64_t num_nodes,
                        const int32_t* seeds, int32_t num_seeds, int32_t n_walks, int32_t walk_len,
-                       const uint8_t* is_train, uint64_t seed, uint64_t offset,
+                       const uint8_t* is_train, uint64_t seed, uint64_t offset, const int64_t* offset_dev,
                        int32_t* pos, gs_stream_t stream);
 size_t gs_negative_workspace_bytes(int64_t num_nodes, int32_t num_seeds);
 int gs_negative_sample(const int64_t* rowptr, const int32_t* col, int64_t num_nodes,
                        const int32_t* seeds, int32_t num_seeds, int32_t hops, int32_t num_neg,
                        const int32_t* train_nodes, int32_t num_train, uint64_t seed, uint64_t offset,
-                       int32_t* neg, int32_t* neg_cnt, void* workspace, size_t workspace_bytes, gs_stream_t stream);
+                       const int64_t* offset_dev, int32_t* neg, int32_t* neg_cnt, void* workspace, size_t workspace_bytes,
+                       gs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * K6  pair losses, src/models.py:65-132.  Pairs are grouped per seed: seed s owns

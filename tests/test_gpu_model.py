@@ -457,10 +457,12 @@ def test_train_classification_matches_the_reference_loop(M, use_graph):
 @pytest.mark.parametrize('case,unsup_loss,learn', [('pubmed_max_unsup', 'normal', 'unsup'), ('cora_max_plus', 'margin', 'unsup'),
                                                    ('cora_gcn_margin', 'margin', 'plus_unsup'),
                                                    ('cora_max_plus', 'normal', 'plus_unsup')])
-def test_unsupervised_trainer_matches_the_drop_in_loop(M, case, unsup_loss, learn):
+@pytest.mark.parametrize('use_graph', [False, True])
+def test_unsupervised_trainer_matches_the_drop_in_loop(M, case, unsup_loss, learn, use_graph):
     """Same seeds and Philox offsets on both sides, so both draw the same pairs and neighbours: the trainer
     (extended batch size never leaves the device) must take the same steps as the body of src/utils.py:141-191
-    run with the drop-in classes, torch's clip_grad_norm_ and torch's SGD."""
+    run with the drop-in classes, torch's clip_grad_norm_ and torch's SGD -- launched eagerly or replayed from one
+    CUDA graph whose samplers read their Philox offset from a device step counter."""
     from graphsage_b200.trainer import UnsupervisedTrainer
     dev = torch.device('cuda:0')
     inp = cases.build_inputs(case)
@@ -472,7 +474,7 @@ def test_unsupervised_trainer_matches_the_drop_in_loop(M, case, unsup_loss, lear
     unsup_b = M.UnsupervisedLoss(adj, inp['train'], dev, seed=77)
     opt = torch.optim.SGD(list(model_a.parameters()) + list(cls_a.parameters()), lr=0.7)
     trainer = UnsupervisedTrainer(model_b, unsup_b, 20, unsup_loss=unsup_loss, learn_method=learn, classifier=cls_b,
-                                  labels=labels)
+                                  labels=labels, use_graph=use_graph)       # captured: one graph replay per step
     for step in range(3):
         seeds = inp['train'][step * 20:(step + 1) * 20]
         batch = np.asarray(list(unsup_a.extend_nodes(seeds, num_neg=num_neg)))              # utils.py:149
