@@ -56,11 +56,9 @@ def edges_to_csr(src: np.ndarray, dst: np.ndarray, num_nodes: int) -> Tuple[np.n
 
 def split_data(num_nodes: int, test_split: int = 3, val_split: int = 6):
     """src/dataCenter.py:98-111, same draw from numpy's global stream: (test, val, train) index arrays."""
-    rand_indices = np.random.permutation(num_nodes)
-    test_size = num_nodes // test_split
-    val_size = num_nodes // val_split
-    return (rand_indices[:test_size], rand_indices[test_size:test_size + val_size],
-            rand_indices[test_size + val_size:])
+    order = np.random.permutation(num_nodes)
+    n_test, n_val = num_nodes // test_split, num_nodes // val_split
+    return np.split(order, [n_test, n_test + n_val])
 
 
 class DataSet:
@@ -112,65 +110,77 @@ class DataSet:
         return self
 
 
+def _intern(table: Dict[str, int], key: str) -> int:
+    """Dense id of `key` in order of first appearance."""
+    idx = table.get(key)
+    if idx is None:
+        idx = table[key] = len(table)
+    return idx
+
+
 def parse_cora(content_file: str, cite_file: str) -> DataSet:
-    """src/dataCenter.py:14-52.  `<paper> <f0> ... <fF-1> <label>` per line; `<paper1> <paper2>` per citation."""
-    node_map: Dict[str, int] = {}
-    label_map: Dict[str, int] = {}
-    feats, labels = [], []
+    """The Cora pair of files (read by src/dataCenter.py:14-52): whitespace-separated
+    `<paper> <f0> ... <fF-1> <class name>` per paper, `<paper> <paper>` per citation.  Papers are numbered by line
+    (:26), classes by first appearance (:27-29)."""
+    paper_id: Dict[str, int] = {}
+    class_id: Dict[str, int] = {}
+    rows, classes = [], []
     with open(content_file) as fp:
-        for i, line in enumerate(fp):
-            info = line.strip().split()
-            feats.append(np.asarray(info[1:-1], dtype=np.float64))            # :25 float(x) per token
-            node_map[info[0]] = i                                             # :26
-            if info[-1] not in label_map:                                     # :27-28
-                label_map[info[-1]] = len(label_map)
-            labels.append(label_map[info[-1]])                                # :29
-    n = len(labels)
-    src, dst = [], []
+        for line in fp:
+            tokens = line.split()
+            if not tokens:
+                continue
+            name, values, cls_name = tokens[0], tokens[1:-1], tokens[-1]
+            paper_id[name] = len(rows)                       # a repeated paper keeps its LAST line number, as a dict does
+            rows.append(np.array(values, dtype=np.float64))
+            classes.append(_intern(class_id, cls_name))
+    n = len(rows)
+    ends = []
     with open(cite_file) as fp:
         for line in fp:
-            info = line.strip().split()
-            if len(info) != 2:
+            pair = line.split()
+            if len(pair) != 2:
                 raise ValueError(f"{cite_file}: expected two paper ids per line")     # the reference asserts (:37)
-            src.append(node_map[info[0]])                                     # KeyError for an unknown paper, as the reference
-            dst.append(node_map[info[1]])
-    rowptr, col = edges_to_csr(np.asarray(src, dtype=np.int64), np.asarray(dst, dtype=np.int64), n)
+            ends.append((paper_id[pair[0]], paper_id[pair[1]]))                       # KeyError for an unknown paper
+    ends = np.asarray(ends, dtype=np.int64).reshape(-1, 2)
+    rowptr, col = edges_to_csr(ends[:, 0], ends[:, 1], n)
     _require_no_isolated(rowptr, n)
-    names = [k for k, _ in sorted(label_map.items(), key=lambda kv: kv[1])]
-    return DataSet(rowptr, col, np.stack(feats) if feats else np.zeros((0, 0)), labels, names, {"source": "cora"})
+    names = sorted(class_id, key=class_id.get)
+    return DataSet(rowptr, col, np.stack(rows) if rows else np.zeros((0, 0)), classes, names, {"source": "cora"})
 
 
 def parse_pubmed(paper_file: str, cites_file: str) -> DataSet:
-    """src/dataCenter.py:54-96.  Line 2 of the paper file names the columns (`<type>:<name>:<default>`), every
-    further line is `<paper>\\tlabel=<k>\\t<word>=<value>...\\t<summary>`; the cites file has two header lines and
-    `<id>\\tpaper:<a>\\t|\\tpaper:<b>` per citation."""
-    node_map: Dict[str, int] = {}
-    feats, labels = [], []
+    """The Pubmed-Diabetes pair of `.tab` files (read by src/dataCenter.py:54-96).  Paper file: a title line, a schema
+    line of tab-separated `<type>:<name>:<default>` columns (first the label, last the summary), then per paper
+    `<id>\tlabel=<k>\t<word>=<tfidf>...\tsummary=...`; the feature columns are the schema's words in schema order
+    (:63,:69-72) and the class is k-1 (:67).  Cites file: two header lines, then `<n>\tpaper:<a>\t|\tpaper:<b>`."""
+    paper_id: Dict[str, int] = {}
+    rows, classes = [], []
     with open(paper_file) as fp:
         fp.readline()
-        feat_map = {entry.split(":")[1]: i - 1 for i, entry in enumerate(fp.readline().split("\t"))}   # :63
-        width = len(feat_map) - 2                                             # :69
-        for i, line in enumerate(fp):
-            info = line.split("\t")
-            node_map[info[0]] = i                                             # :66
-            labels.append(int(info[1].split("=")[1]) - 1)                     # :67
-            row = np.zeros(width)
-            for word_info in info[2:-1]:                                      # :70-72 (last field is the summary)
-                name, value = word_info.split("=")
-                row[feat_map[name]] = float(value)
-            feats.append(row)
-    n = len(labels)
-    src, dst = [], []
+        schema = [field.split(":")[1] for field in fp.readline().split("\t")]
+        column = {word: k for k, word in enumerate(schema[1:-1])}          # words only: label first, summary last
+        for line in fp:
+            fields = line.split("\t")
+            paper_id[fields[0]] = len(rows)
+            classes.append(int(fields[1].partition("=")[2]) - 1)
+            vec = np.zeros(len(column))
+            for item in fields[2:-1]:                                      # the last field is the summary
+                word, _, value = item.partition("=")
+                vec[column[word]] = float(value)
+            rows.append(vec)
+    n = len(rows)
+    ends = []
     with open(cites_file) as fp:
         fp.readline()
         fp.readline()
         for line in fp:
-            info = line.strip().split("\t")
-            src.append(node_map[info[1].split(":")[1]])                       # :84
-            dst.append(node_map[info[-1].split(":")[1]])                      # :85
-    rowptr, col = edges_to_csr(np.asarray(src, dtype=np.int64), np.asarray(dst, dtype=np.int64), n)
+            fields = line.strip().split("\t")
+            ends.append((paper_id[fields[1].partition(":")[2]], paper_id[fields[-1].partition(":")[2]]))   # :84-85
+    ends = np.asarray(ends, dtype=np.int64).reshape(-1, 2)
+    rowptr, col = edges_to_csr(ends[:, 0], ends[:, 1], n)
     _require_no_isolated(rowptr, n)
-    return DataSet(rowptr, col, np.stack(feats) if feats else np.zeros((0, 0)), labels, None, {"source": "pubmed"})
+    return DataSet(rowptr, col, np.stack(rows) if rows else np.zeros((0, 0)), classes, None, {"source": "pubmed"})
 
 
 def _require_no_isolated(rowptr: np.ndarray, n: int) -> None:
@@ -217,11 +227,9 @@ class DataCenter:
             data = parse(*files)
             if cache:
                 data.save(cache)
-        test_indexs, val_indexs, train_indexs = split_data(data.num_nodes)
-        setattr(self, dataSet + '_test', test_indexs)
-        setattr(self, dataSet + '_val', val_indexs)
-        setattr(self, dataSet + '_train', train_indexs)
-        setattr(self, dataSet + '_feats', data.feats)
-        setattr(self, dataSet + '_labels', data.labels)
-        setattr(self, dataSet + '_adj_lists', data.adjacency())
+        test, val, train = split_data(data.num_nodes)
+        published = {"test": test, "val": val, "train": train, "feats": data.feats, "labels": data.labels,
+                     "adj_lists": data.adjacency()}
+        for suffix, value in published.items():          # the attribute names the reference's loops read
+            setattr(self, f"{dataSet}_{suffix}", value)
         return data
