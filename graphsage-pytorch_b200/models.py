@@ -550,6 +550,16 @@ class _PairLossFn(torch.autograd.Function):
         return (grad_emb[:, :ctx.dim] if grad_emb.shape[1] != ctx.dim else grad_emb), None, None
 
 
+def negative_radius(nnz: int, num_nodes: int, max_hops: int, budget: int) -> int:
+    """Largest h <= max_hops with mean_degree^h <= budget, at least 1 (UnsupervisedLoss.negative_hops)."""
+    mean_deg = max(float(nnz) / max(num_nodes, 1), 1.0)
+    h, ball = 0, 1.0
+    while h < max_hops and ball * mean_deg <= budget:
+        ball *= mean_deg
+        h += 1
+    return max(h, 1)
+
+
 class UnsupervisedLoss(object):
     """Same surface as src/models.py:45-186.  Sampling (random-walk positives, far negatives,
     batch union) and both losses run on the device; the python pair stores
@@ -637,12 +647,7 @@ class UnsupervisedLoss(object):
         if forced is not None:
             return int(forced)
         csr = self._state()[0]
-        mean_deg = max(float(csr.nnz) / max(csr.num_nodes, 1), 1.0)
-        h, ball = 0, 1.0
-        while h < self.N_WALK_LEN and ball * mean_deg <= self.NEG_BALL_BUDGET:
-            ball *= mean_deg
-            h += 1
-        return max(h, 1)
+        return negative_radius(csr.nnz, csr.num_nodes, self.N_WALK_LEN, self.NEG_BALL_BUDGET)
 
     def set_pairs(self, unique_nodes_batch, seeds, node_positive_pairs, node_negtive_pairs):
         """Injected-pair mode: install pair stores recorded from a reference run (same

@@ -130,3 +130,14 @@ def test_micro_f1_is_sklearn_micro_f1_for_single_label_predictions():
     import pytest
     with pytest.raises(ValueError):
         inference.micro_f1(torch.zeros(3, dtype=torch.int64), torch.zeros(4, dtype=torch.int64))
+
+
+def test_negative_radius_keeps_the_reference_ball_on_sparse_graphs_only():
+    """UnsupervisedLoss.negative_hops: 5 hops (src/models.py:52,155-162) on the reference's data sets, fewer where
+    that ball would be the whole graph (BASELINE configs[2], [3]: the reference's far set is empty there)."""
+    from graphsage_b200.models import negative_radius
+    assert negative_radius(10_556, 2_708, 5, 10_000) == 5              # Cora
+    assert negative_radius(88_651, 19_717, 5, 10_000) == 5             # Pubmed
+    assert negative_radius(123_714_814, 2_449_029, 5, 10_000) == 2     # cfg-3
+    assert negative_radius(114_600_000, 232_965, 5, 10_000) == 1       # cfg-4
+    assert negative_radius(0, 100, 5, 10_000) == 5 and negative_radius(10 ** 9, 10, 5, 10_000) == 1
