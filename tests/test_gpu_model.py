@@ -535,3 +535,18 @@ def test_negative_radius_shrinks_on_dense_graphs_only(M):
     unsup.neg_hops = 5                                   # forcing the reference's radius: the ball is everything
     unsup.extend_nodes(seeds, num_neg=6)
     assert all(len(unsup.node_negtive_pairs[s]) == 0 for s in seeds.tolist())
+
+
+def test_reference_main_flow_end_to_end():
+    """examples/reference_flow.py: text files -> datacache -> GraphSage/Classification -> captured supervised steps ->
+    evaluate -> embeddings -> classifier on frozen embeddings; everything finite and shaped like the reference's."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "reference_flow.py")
+    spec = importlib.util.spec_from_file_location("reference_flow", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = mod.main(log=lambda *_: None)
+    assert len(out["losses"]) >= 4 and all(np.isfinite(out["losses"]))
+    assert 0.0 <= out["max_vali_f1"] <= 1.0 and 0.0 <= out["train_acc"] <= 1.0
+    assert out["embeddings"].shape == (out["num_nodes"], 128) and bool(torch.isfinite(out["embeddings"]).all())
