@@ -141,3 +141,29 @@ def test_negative_radius_keeps_the_reference_ball_on_sparse_graphs_only():
     assert negative_radius(123_714_814, 2_449_029, 5, 10_000) == 2     # cfg-3
     assert negative_radius(114_600_000, 232_965, 5, 10_000) == 1       # cfg-4
     assert negative_radius(0, 100, 5, 10_000) == 5 and negative_radius(10 ** 9, 10, 5, 10_000) == 1
+
+
+def test_reference_arm_prints_the_contract_line(tmp_path):
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the same metric /
+    unit / config keys as our arm, impl == "reference", a cpu_baseline describing the run and an e2e object with
+    zero copy bytes.  Ranks other than 0 print nothing and exit 0."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+           "--scale", "0.003", "--b_sz", "128"]
+    env = dict(os.environ, GSAGE_CACHE=str(tmp_path))
+    out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=240)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "seed_nodes_per_sec_fwd_bwd" and d["unit"] == "seed nodes/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("cfg3_products") and d["config"]["fanout"] == 10
+    other = subprocess.run(cmd, capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2"), timeout=60)
+    assert other.returncode == 0 and not [l for l in other.stdout.splitlines() if l.startswith("{")]
