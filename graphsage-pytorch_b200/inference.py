@@ -160,9 +160,9 @@ def train_classification(features: torch.Tensor, train_nodes, labels, classifica
         if not use_graph:
             epoch_body()
         elif graph is None:
+            saved = [p.clone() for p in params]                        # before the fork: the side stream is ordered behind it
             side = torch.cuda.Stream(device=dev)                       # warm-up off the capture (allocator, lazy loads)
             side.wait_stream(torch.cuda.current_stream())
-            saved = [p.clone() for p in params]
             with torch.cuda.stream(side):
                 epoch_body()
             torch.cuda.current_stream().wait_stream(side)

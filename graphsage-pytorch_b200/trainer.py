@@ -228,6 +228,17 @@ class SupervisedTrainer:
             # clip groups follow src/utils.py:185-186: model 0 = graphSage, model 1 = classification
             self.dp = DpExchange(self.flat_grad, [p.data for p in params], offs, [0] * n_sage + [1, 1],
                                  world=world_size, rank=rank, group=process_group)
+        if world_size > 1:
+            # replicas must start identical (the exchange only averages gradients): rank 0's parameters win
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                for p in params:
+                    dist.broadcast(p.data, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0,
+                                   group=process_group)
+        #: poll the exchange's sticky status word every this many steps (0 = only at flush()/check()); a timed-out
+        #: peer wait would otherwise leave the ranks training different weights silently
+        self.status_every = 256
+        self._steps_since_check = 0
         self.seeds = torch.zeros((self.b_sz,), dtype=torch.int32, device=dev)
         self.seeds_pinned = torch.zeros((self.b_sz,), dtype=torch.int32).pin_memory()
         self.loss = torch.zeros((1,), dtype=torch.float32, device=dev)
@@ -313,7 +324,19 @@ class SupervisedTrainer:
         self.seeds.copy_(self.seeds_pinned, non_blocking=True)
         return self._run()
 
+    def check(self):
+        """Raise if the fused exchange ever timed out waiting for a peer (synchronises the stream)."""
+        self._steps_since_check = 0
+        if self.dp is not None and self.world_size > 1:
+            self.dp.status()
+
+    def _count_steps(self, n: int = 1):
+        self._steps_since_check += n
+        if self.status_every and self.world_size > 1 and self._steps_since_check >= self.status_every:
+            self.check()
+
     def _run(self) -> torch.Tensor:
+        self._count_steps()
         if self.use_graph:
             if self._graph_fb is None:
                 self._capture()
@@ -368,6 +391,8 @@ class PipelinedTrainer(SupervisedTrainer):
         self._ring_pinned = torch.zeros((self.RING, self.b_sz), dtype=torch.int32).pin_memory()
         self._ring_events = [None] * self.RING
         self._fed = 0                          # batches written into the ring so far
+        self._fetched = 0                      # gs_fetch_batch launches enqueued since the ring became the queue
+        self._fetch_events = [None] * self.RING    # _fetch_events[j % RING]: recorded behind the j-th fetch
         self._copy_stream = torch.cuda.Stream(device=dev)
         self._prep_stream = torch.cuda.Stream(device=dev)
         # occupancy cap (CTAs/SM) of the layer-1 aggregation while it runs beside the training chain, 0 = none
@@ -377,6 +402,7 @@ class PipelinedTrainer(SupervisedTrainer):
         self._graphs = [None, None]            # one step from slot 0 / slot 1
         self._graph_pair = None                # two steps (slot 0 then slot 1) in one launch
         self._cur: Optional[int] = None        # slot holding the prepared, not yet trained batch
+        self._prep_call: Optional[int] = None  # the model call number every prep launches with (see _prep)
 
     # ---- batch queue --------------------------------------------------------------------------------
     def set_queue(self, batches_dev: torch.Tensor):
@@ -395,14 +421,13 @@ class PipelinedTrainer(SupervisedTrainer):
         arr = np.asarray(nodes_batch)
         if arr.shape[0] != self.b_sz:
             raise ValueError(f"trainer was built for b_sz={self.b_sz}, got {arr.shape[0]}")
-        if self._queue is not self._ring:
-            torch.cuda.current_stream().synchronize()
-            self.set_queue(self._ring)
-            self._fed = 0
+        self._use_ring()
         r = self._fed % self.RING
+        fetched = self._row_free(r)                       # raises when the ring is over-full
         if self._ring_events[r] is not None:
             self._ring_events[r].synchronize()            # the pinned row is free again
         self._ring_pinned[r].numpy()[:] = arr
+        self._copy_stream.wait_event(fetched)             # ... and the device row has been fetched by its step
         with torch.cuda.stream(self._copy_stream):
             self._ring[r].copy_(self._ring_pinned[r], non_blocking=True)
             ev = torch.cuda.Event()
@@ -411,19 +436,57 @@ class PipelinedTrainer(SupervisedTrainer):
         torch.cuda.current_stream().wait_event(ev)
         self._fed += 1
 
-    def feed_device(self, seeds_dev: torch.Tensor):
+    def _use_ring(self):
         if self._queue is not self._ring:
             torch.cuda.current_stream().synchronize()
             self.set_queue(self._ring)
-            self._fed = 0
-        self._ring[self._fed % self.RING].copy_(seeds_dev, non_blocking=True)
+            self._fed = self._fetched = 0
+            self._fetch_events = [None] * self.RING
+
+    def _row_free(self, r: int) -> torch.cuda.Event:
+        """Event behind the fetch that consumed the batch currently in ring row r (an already-signalled one when
+        the row was never used).  Feeding more than RING batches ahead of the steps that fetch them would overwrite
+        a batch no step has read yet: that is an error, not something to wait for (nothing is enqueued to wait on)."""
+        prev = self._fed - self.RING                       # index of the batch being overwritten
+        if prev < 0:
+            ev = torch.cuda.Event()
+            ev.record()
+            return ev
+        if self._fetched <= prev:
+            raise RuntimeError(f"batch ring is full: {self._fed - self._fetched} batches fed ahead of the steps that "
+                               f"fetch them (capacity {self.RING}); call run()/submit() between feeds")
+        return self._fetch_events[prev % self.RING]
+
+    def _mark_fetched(self, n: int = 1):
+        """n more gs_fetch_batch launches are enqueued on the current stream: one event behind them covers all."""
+        if self._queue is not self._ring:
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        for _ in range(n):
+            self._fetch_events[self._fetched % self.RING] = ev
+            self._fetched += 1
+
+    def feed_device(self, seeds_dev: torch.Tensor):
+        self._use_ring()
+        r = self._fed % self.RING
+        torch.cuda.current_stream().wait_event(self._row_free(r))     # raises when the ring is over-full
+        self._ring[r].copy_(seeds_dev, non_blocking=True)
         self._fed += 1
 
     # ---- the two halves ---------------------------------------------------------------------------
     def _prep(self, slot: int):
         ops.fetch_batch(self.queue_desc, self.b_sz, self.slot_seeds[slot])
-        self.slot_layers[slot] = self.model._run_prep(self.slot_seeds[slot], None, offset_dev=self.sample_counter,
-                                                      reuse=self.slot_layers[slot])
+        # Philox offset of a prep = (model call number << 8 | layer) + (sample_counter << 8).  The call number is
+        # baked into a captured launch, so every prep -- whichever graph or slot it was captured for, or eager --
+        # carries the SAME one and the device counter (+1 per prep) alone tells consecutive batches apart.
+        m = self.model
+        if self._prep_call is None:
+            self._prep_call = m._calls
+        keep, m._calls = m._calls, self._prep_call
+        self.slot_layers[slot] = m._run_prep(self.slot_seeds[slot], None, offset_dev=self.sample_counter,
+                                             reuse=self.slot_layers[slot])
+        m._calls = max(keep, self._prep_call + 1)
         self.sample_counter.add_(1)
 
     def _compute(self, slot: int, update: bool = True):
@@ -503,6 +566,7 @@ class PipelinedTrainer(SupervisedTrainer):
             self._capture_pipeline()
         if self._cur is None:
             self._prep(0)
+            self._mark_fetched()
             self._cur = 0
 
     def run(self, n: int = 1) -> torch.Tensor:
@@ -510,9 +574,11 @@ class PipelinedTrainer(SupervisedTrainer):
         Returns the device loss of the last trained batch."""
         if self._cur is None:
             raise RuntimeError("prime() the pipeline first")
+        self._count_steps(n)
         while n > 0:
             if self.use_graph and self._cur == 0 and n >= 2:
                 self._graph_pair.replay()
+                self._mark_fetched(2)
                 n -= 2
                 continue
             if self.use_graph:
@@ -521,6 +587,7 @@ class PipelinedTrainer(SupervisedTrainer):
                 before = native.launch_count()
                 self._both(self._cur)
                 self.launches_per_step = native.launch_count() - before
+            self._mark_fetched()
             self._cur = 1 - self._cur
             n -= 1
         return self.loss
@@ -531,6 +598,7 @@ class PipelinedTrainer(SupervisedTrainer):
             return None
         self._compute(self._cur)
         self._cur = None
+        self.check()
         return self.loss
 
     # one call per batch, on top of the queue: the batch handed over is the NEXT one

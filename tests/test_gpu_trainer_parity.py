@@ -1,0 +1,240 @@
+"""GPU: the device-resident train loops (trainer.SupervisedTrainer / PipelinedTrainer -- the path bench.py's
+headline number comes from) against the oracle at the HEADLINE shape: a down-scaled `synth.powerlaw_graph`
+(hubs kept: max degree in the thousands), F=100 (K=200, not a multiple of the 32-wide k-stage), H=128, C=47,
+b_sz=1024, fan-out 10, precision 'tf32x3'.  The native sampler draws; the drawn lists are read back from the
+trainer's frontiers and replayed through the oracle's dense-mask algorithm (src/models.py:241-330) followed by
+`clip_grad_norm_(.., 5)` per model and `SGD(lr=0.7)` (src/utils.py:157-163,184-191).  After every step the loss
+and every parameter must agree within 1e-5 norm-relative (max|a-b| / max|ref|)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sage_oracle as so
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+N_NODES, N_EDGES, FEATS, HIDDEN, CLASSES, B_SZ, STEPS = 16000, 16000 * 24, 100, 128, 47, 1024, 3
+
+
+def rel(a, b):
+    a = np.asarray(a.detach().cpu() if isinstance(a, torch.Tensor) else a, dtype=np.float64)
+    b = np.asarray(b.detach().cpu() if isinstance(b, torch.Tensor) else b, dtype=np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+@pytest.fixture(scope='module')
+def world():
+    import graphsage_b200  # noqa: F401
+    from graphsage_b200 import synth
+    rowptr, col = synth.powerlaw_graph(N_NODES, N_EDGES, seed=0)
+    assert int(np.diff(rowptr).max()) >= 2000, "the down-scaled graph must keep its hub rows"
+    feats = synth.features_normal(N_NODES, FEATS, seed=1)
+    labels = synth.labels_uniform(N_NODES, CLASSES, seed=2)
+    _, _, train = synth.split_nodes(N_NODES, seed=3)
+    wrng = np.random.default_rng(7)
+    weights = [synth.xavier_uniform_np(wrng, HIDDEN, 2 * FEATS), synth.xavier_uniform_np(wrng, HIDDEN, 2 * HIDDEN)]
+    cls_w = synth.xavier_uniform_np(wrng, CLASSES, HIDDEN)
+    cls_b = wrng.uniform(-0.05, 0.05, size=(CLASSES,)).astype(np.float32)
+    rng = np.random.default_rng(11)
+    batches = [rng.permutation(train)[:B_SZ].astype(np.int64) for _ in range(STEPS + 1)]
+    return dict(rowptr=rowptr, col=col, feats=feats, labels=labels, weights=weights, cls_w=cls_w, cls_b=cls_b,
+                batches=batches)
+
+
+def _build(world, precision='tf32x3'):
+    from graphsage_b200 import models
+    from graphsage_b200.graph import AdjCSR
+    dev = torch.device('cuda:0')
+    feats = torch.from_numpy(world['feats']).to(dev)
+    model = models.GraphSage(2, FEATS, HIDDEN, feats, AdjCSR(world['rowptr'], world['col']), dev, gcn=False,
+                             agg_func='MEAN', seed=5, precision=precision).to(dev)
+    cls = models.Classification(HIDDEN, CLASSES).to(dev)
+    with torch.no_grad():
+        model.sage_layer1.weight.copy_(torch.from_numpy(world['weights'][0]))
+        model.sage_layer2.weight.copy_(torch.from_numpy(world['weights'][1]))
+        cls.layer[0].weight.copy_(torch.from_numpy(world['cls_w']))
+        cls.layer[0].bias.copy_(torch.from_numpy(world['cls_b']))
+    return model, cls
+
+
+def _drawn_calls(layers):
+    """(samp_neighs incl. self, unique list) per `_get_unique_neighs_list` call, batch-level call first, from the
+    frontiers of the step that has just run.  The unique list of call c is the node list of call c+1 (ascending)."""
+    calls = []
+    for fr in reversed(layers):
+        live = fr.rows_max if fr.num_rows is None else int(fr.num_rows.item())
+        nodes = fr.nodes[:live].cpu().tolist()
+        nbr, cnt = fr.nbr[:live].cpu().numpy(), fr.cnt[:live].cpu().numpy()
+        samp = [set(nbr[i, :cnt[i]].tolist()) | {nodes[i]} for i in range(live)]
+        calls.append((nodes, samp, sorted(set().union(*samp))))
+    return calls
+
+
+class _OracleLoop:
+    """The reference's step on CPU: forward/loss/backward through the oracle, clip per model, SGD(0.7)."""
+
+    def __init__(self, world):
+        self.w = [torch.from_numpy(x.copy()).requires_grad_(True) for x in world['weights']]
+        self.cw = torch.from_numpy(world['cls_w'].copy()).requires_grad_(True)
+        self.cb = torch.from_numpy(world['cls_b'].copy()).requires_grad_(True)
+        self.feats = torch.from_numpy(world['feats'])
+        self.adj = so.LazySetAdjacency(world['rowptr'], world['col'])
+        self.labels = world['labels']
+        self.opt = torch.optim.SGD(self.w + [self.cw, self.cb], lr=0.7)                  # src/utils.py:136
+
+    def step(self, batch, calls):
+        assert calls[0][0] == [int(x) for x in batch]
+        loss, _, _ = so.supervised_step(self.w, self.cw, self.cb, self.feats, self.adj, batch, self.labels,
+                                        injected=[(c[1], c[2]) for c in calls])           # :157-163,184
+        torch.nn.utils.clip_grad_norm_(self.w, 5)                                        # :185-186 (graphSage)
+        torch.nn.utils.clip_grad_norm_([self.cw, self.cb], 5)                            # (classification)
+        self.opt.step()                                                                  # :187
+        self.opt.zero_grad()
+        return float(loss)
+
+
+def _compare(tag, step, loss_dev, model, cls, ref, loss_ref):
+    errs = {'loss': abs(loss_dev - loss_ref) / max(abs(loss_ref), 1e-30),
+            'w1': rel(model.sage_layer1.weight, ref.w[0]), 'w2': rel(model.sage_layer2.weight, ref.w[1]),
+            'cls_w': rel(cls.layer[0].weight, ref.cw), 'cls_b': rel(cls.layer[0].bias, ref.cb)}
+    assert max(errs.values()) <= TOL, (tag, step, errs)
+
+
+@pytest.mark.parametrize('use_graph', [True, False])
+def test_supervised_trainer_matches_the_oracle_at_the_headline_shape(world, use_graph):
+    from graphsage_b200.trainer import SupervisedTrainer
+    model, cls = _build(world)
+    tr = SupervisedTrainer(model, cls, world['labels'], B_SZ, use_graph=use_graph)
+    ref = _OracleLoop(world)
+    for i in range(STEPS):
+        batch = world['batches'][i]
+        loss_dev = float(tr.step(batch).item())
+        torch.cuda.synchronize()
+        calls = _drawn_calls(tr.last_layers)
+        assert len(calls[1][0]) > 5 * B_SZ                      # the layer-1 frontier really is ~10x the batch
+        _compare(f'SupervisedTrainer graph={use_graph}', i, loss_dev, model, cls, ref, ref.step(batch, calls))
+    tr.check()
+
+
+@pytest.mark.parametrize('use_graph', [True, False])
+def test_pipelined_trainer_matches_the_oracle_at_the_headline_shape(world, use_graph):
+    """The two-branch step: batch i is trained while batch i+1 is sampled / aggregated beside it.  The frontiers of
+    the batch being trained live in `slot_layers[slot]` and are not touched again until the step after next."""
+    from graphsage_b200.trainer import PipelinedTrainer
+    model, cls = _build(world)
+    tr = PipelinedTrainer(model, cls, world['labels'], B_SZ, use_graph=use_graph)
+    ref = _OracleLoop(world)
+    queue = torch.from_numpy(np.stack(world['batches']).astype(np.int32)).cuda()
+    tr.set_queue(queue)
+    tr.prime()
+    for i in range(STEPS):
+        slot = tr._cur
+        loss_dev = float(tr.run(1).item())                       # single-step graphs (slot 0, slot 1, slot 0)
+        torch.cuda.synchronize()
+        calls = _drawn_calls(tr.slot_layers[slot])
+        _compare(f'PipelinedTrainer graph={use_graph}', i, loss_dev, model, cls, ref,
+                 ref.step(world['batches'][i], calls))
+    tr.check()
+
+
+def test_pipelined_pair_graph_matches_the_oracle(world):
+    """The form bench.py times: ONE graph launch = two steps (slot 0 then slot 1).  Both steps' frontiers are
+    still intact after the launch except slot 0's, which the second step re-prepared -- so the oracle replays
+    step 2 from slot 1 and step 1 from a single-step twin run with the same seeds, offsets and weights."""
+    from graphsage_b200.trainer import PipelinedTrainer
+    queue = torch.from_numpy(np.stack(world['batches']).astype(np.int32)).cuda()
+    # twin A: two single steps, recording both frontiers
+    model_a, cls_a = _build(world)
+    tr_a = PipelinedTrainer(model_a, cls_a, world['labels'], B_SZ, use_graph=True)
+    tr_a.set_queue(queue)
+    tr_a.prime()
+    ref = _OracleLoop(world)
+    for i in range(2):
+        slot = tr_a._cur
+        loss_a = float(tr_a.run(1).item())
+        torch.cuda.synchronize()
+        _compare('pair twin', i, loss_a, model_a, cls_a, ref, ref.step(world['batches'][i], _drawn_calls(tr_a.slot_layers[slot])))
+    # B: the same two steps as one pair-graph launch must land on the same weights bit for bit or within TOL
+    model_b, cls_b = _build(world)
+    tr_b = PipelinedTrainer(model_b, cls_b, world['labels'], B_SZ, use_graph=True)
+    tr_b.set_queue(queue)
+    tr_b.prime()
+    assert tr_b._cur == 0
+    loss_b = float(tr_b.run(2).item())
+    torch.cuda.synchronize()
+    _compare('pair graph', 1, loss_b, model_b, cls_b, ref, loss_a)
+    for pa, pb in zip(list(model_a.parameters()) + list(cls_a.parameters()), list(model_b.parameters()) + list(cls_b.parameters())):
+        assert rel(pb, pa) <= 1e-6
+
+
+def test_consecutive_preps_draw_with_distinct_philox_offsets(world):
+    """The SAME seed batch queued over and over must be sampled differently at every step, whichever captured
+    graph (slot 0, slot 1, pair) prepares it: the Philox offset is (call << 8 | layer) + (sample_counter << 8),
+    and every prep carries the same call number, so the device counter alone separates the draws."""
+    from graphsage_b200.trainer import PipelinedTrainer
+    model, cls = _build(world)
+    tr = PipelinedTrainer(model, cls, world['labels'], B_SZ, use_graph=True, lr=0.0)
+    same = torch.from_numpy(np.stack([world['batches'][0]] * 4).astype(np.int32)).cuda()
+    tr.set_queue(same)
+    tr.prime()
+    draws = []
+    for n in (1, 1, 2, 2, 1, 2):                                  # single graphs and the pair graph, interleaved
+        tr.run(n)
+        torch.cuda.synchronize()
+        for slot in ((1 - tr._cur, tr._cur) if n == 2 else (tr._cur,)):      # the slot(s) prepared last
+            top = tr.slot_layers[slot][-1]
+            draws.append(top.nbr.cpu().numpy().copy())
+    hub_rows = np.flatnonzero(np.diff(world['rowptr'])[world['batches'][0]] > 20)
+    assert len(hub_rows) > 100
+    for i in range(len(draws)):
+        for j in range(i + 1, len(draws)):
+            same_rows = (draws[i][hub_rows] == draws[j][hub_rows]).all(axis=1).mean()
+            assert same_rows < 0.05, (i, j, same_rows)          # identical offsets would give 1.0
+
+
+def test_submit_without_host_sync_never_loses_a_batch(world):
+    """a loop that calls submit() without reading the loss runs many steps ahead of the GPU; the
+    4-row staging ring must not be rewritten before the step that owns a row has fetched it.  On a graph where
+    the sampler has no choice (every degree <= fan-out) the weights after 40 unsynchronised submits must equal
+    those of the device-queue path over the same batches."""
+    from graphsage_b200 import models
+    from graphsage_b200.graph import AdjCSR
+    from graphsage_b200.trainer import PipelinedTrainer
+    dev = torch.device('cuda:0')
+    n = 3000
+    offs = np.array([1, 2, 5, -1, -2, -5])
+    col = ((np.arange(n)[:, None] + offs[None, :]) % n)
+    col.sort(axis=1)
+    adj = AdjCSR(np.arange(0, 6 * n + 1, 6, dtype=np.int64), col.reshape(-1).astype(np.int32))
+    rng = np.random.default_rng(5)
+    feats = torch.from_numpy(rng.standard_normal((n, 64)).astype(np.float32)).to(dev)
+    labels = rng.integers(0, 5, size=n)
+    batches = [rng.permutation(n)[:128] for _ in range(40)]
+
+    def run(mode):
+        torch.manual_seed(3)
+        model = models.GraphSage(2, 64, 32, feats, adj, dev, gcn=False, agg_func='MEAN', seed=11, precision='fp32').to(dev)
+        cls = models.Classification(32, 5).to(dev)
+        tr = PipelinedTrainer(model, cls, labels, 128, use_graph=True, lr=0.05)
+        if mode == 'queue':
+            tr.set_queue(torch.from_numpy(np.stack(batches).astype(np.int32)).to(dev))
+            tr.prime()
+            tr.run(len(batches) - 1)
+        else:
+            for b in batches:
+                tr.submit(b)                                       # no .item(), no synchronize
+        tr.flush()
+        torch.cuda.synchronize()
+        return [p.detach().clone() for p in list(model.parameters()) + list(cls.parameters())]
+
+    base = run('queue')
+    for a, b in zip(run('submit'), base):
+        assert rel(a, b) <= 1e-6
+    # feeding more than RING batches ahead of the steps that fetch them is refused, not silently dropped
+    model = models.GraphSage(2, 64, 32, feats, adj, dev, gcn=False, agg_func='MEAN', seed=11, precision='fp32').to(dev)
+    tr = PipelinedTrainer(model, models.Classification(32, 5).to(dev), labels, 128, use_graph=False)
+    for b in batches[:PipelinedTrainer.RING]:
+        tr.feed(b)
+    with pytest.raises(RuntimeError, match='ring is full'):
+        tr.feed(batches[0])
