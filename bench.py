@@ -113,9 +113,25 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference algorithm (kind "port")
 # ------------------------------------------------------------------------------------------------
-def cpu_steps(rowptr, col, feats, labels, batches, hidden, classes, warmup, steps, clip_and_sgd=True):
-    """fwd + classifier/NLL + bwd (+ clip + SGD) with oracle/sage_oracle.py, torch CPU, all host
-    threads.  Returns seconds per timed step list."""
+def _ref_modules():
+    """The staged, unmodified reference (baseline/_ref, see baseline/make_ref.py) or None."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    try:
+        import make_ref
+        if make_ref.available() and make_ref.verify():
+            return make_ref.load("models")
+    except Exception as exc:
+        log(f"[bench] staged reference unusable ({exc!r}); falling back to the oracle port")
+    return None
+
+
+def cpu_steps(rowptr, col, feats, labels, batches, hidden, classes, warmup, steps, clip_and_sgd=True, budget_s=None):
+    """One supervised step of the reference per batch, on the host cores, no extension (cfg-3: the reference's
+    extend_nodes cannot run at this scale): the body of src/utils.py:157-163,184-191 --
+    GraphSage.forward -> Classification -> NLL mean -> backward -> clip_grad_norm_(5) per model -> SGD(0.7).
+    kind "reference": the reference's OWN src/models.py classes from baseline/_ref; kind "port" (only when that
+    copy is absent): oracle/sage_oracle.py.  `budget_s` bounds the number of TIMED steps (never the batch size).
+    Returns (seconds per timed step, kind)."""
     import random
     import torch
     from oracle import sage_oracle as so
@@ -124,62 +140,95 @@ def cpu_steps(rowptr, col, feats, labels, batches, hidden, classes, warmup, step
     torch.manual_seed(SEED)
     wrng = np.random.default_rng(7)
     f = feats.shape[1]
-    w = [torch.from_numpy(synth.xavier_uniform_np(wrng, hidden, 2 * f)).requires_grad_(True),
-         torch.from_numpy(synth.xavier_uniform_np(wrng, hidden, 2 * hidden)).requires_grad_(True)]
-    cw = torch.from_numpy(synth.xavier_uniform_np(wrng, classes, hidden)).requires_grad_(True)
-    cb = torch.zeros(classes, requires_grad=True)
-    adj = so.LazySetAdjacency(rowptr, col, cache=True)
+    w_np = [synth.xavier_uniform_np(wrng, hidden, 2 * f), synth.xavier_uniform_np(wrng, hidden, 2 * hidden),
+            synth.xavier_uniform_np(wrng, classes, hidden)]
+    adj = so.LazySetAdjacency(rowptr, col, cache=True)      # dict-of-sets view, rows materialised on first touch
     feats_t = torch.from_numpy(feats)
-    opt = torch.optim.SGD(w + [cw, cb], lr=0.7)                            # src/utils.py:136
+    ref = _ref_modules()
+    if ref is not None:
+        kind = "reference"
+        graphSage = ref.GraphSage(2, f, hidden, feats_t, adj, torch.device("cpu"), gcn=False, agg_func="MEAN")    # main.py:54
+        classification = ref.Classification(hidden, classes)                                                      # main.py:58
+        with torch.no_grad():
+            graphSage.sage_layer1.weight.copy_(torch.from_numpy(w_np[0]))
+            graphSage.sage_layer2.weight.copy_(torch.from_numpy(w_np[1]))
+            classification.layer[0].weight.copy_(torch.from_numpy(w_np[2]))
+            classification.layer[0].bias.zero_()
+        models = [graphSage, classification]
+        opt = torch.optim.SGD([p for m in models for p in m.parameters()], lr=0.7)         # utils.py:136
+
+        def one(batch):
+            embs = graphSage(batch)                                                        # utils.py:157
+            logists = classification(embs)                                                 # :161
+            loss = -torch.sum(logists[range(logists.size(0)), labels[batch]], 0) / len(batch)   # :162-163
+            loss.backward()                                                                # :184
+            if clip_and_sgd:
+                for m in models:
+                    torch.nn.utils.clip_grad_norm_(m.parameters(), 5)                      # :185-186
+                opt.step()                                                                 # :187
+                opt.zero_grad()
+    else:
+        kind = "port"
+        w = [torch.from_numpy(w_np[0]).requires_grad_(True), torch.from_numpy(w_np[1]).requires_grad_(True)]
+        cw = torch.from_numpy(w_np[2]).requires_grad_(True)
+        cb = torch.zeros(classes, requires_grad=True)
+        opt = torch.optim.SGD(w + [cw, cb], lr=0.7)
+
+        def one(batch):
+            so.supervised_step(w, cw, cb, feats_t, adj, batch, labels)
+            if clip_and_sgd:
+                torch.nn.utils.clip_grad_norm_(w, 5)
+                torch.nn.utils.clip_grad_norm_([cw, cb], 5)
+                opt.step()
+                opt.zero_grad()
     times = []
+    t_start = time.perf_counter()
     for i in range(warmup + steps):
         batch = batches[i % len(batches)]
         t0 = time.perf_counter()
-        so.supervised_step(w, cw, cb, feats_t, adj, batch, labels)         # src/utils.py:157-163,184
-        if clip_and_sgd:
-            torch.nn.utils.clip_grad_norm_(w, 5)                           # src/utils.py:185-186 (per model)
-            torch.nn.utils.clip_grad_norm_([cw, cb], 5)
-            opt.step()
-            opt.zero_grad()
+        one(batch)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-        log(f"[bench] cpu step {i} ({'warm' if i < warmup else 'timed'}): {dt:.3f}s, batch {len(batch)}")
-    return times
+        log(f"[bench] cpu step {i} ({'warm' if i < warmup else 'timed'}, {kind}): {dt:.3f}s, batch {len(batch)}")
+        if budget_s is not None and len(times) >= 3 and time.perf_counter() - t_start + dt > budget_s:
+            log(f"[bench] cpu arm: budget of {budget_s:.0f}s reached after {len(times)} timed steps")
+            break
+    return times, kind
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path (oracle port; the Python
-    reference itself cannot travel to the GPU box), all host threads, same config/metric."""
+    """--impl reference: the reference's own CPU implementation of the path (src/models.py from baseline/_ref,
+    device cpu, every host thread), same workload / metric / batch size.  Bounded by time: when K + W full steps
+    would not fit the budget, fewer steps are TIMED (stated in `sample`); the batch is never shrunk."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
+    torch.set_num_threads(os.cpu_count() or 1)        # torchrun exports OMP_NUM_THREADS=1: the CPU arm gets the whole host
     cfg, rowptr, col, feats, labels, train = build_workload(args.scale)
     cores = torch.get_num_threads()
     b_sz = args.b_sz
-    # bound the run: the reference's step cost is dominated by the dense [rows x |U|] mask
-    # (quadratic in the batch), so when K+W full batches would take too long the per-step sample
-    # is a smaller slice of the same batch stream -- this only flatters the reference.
-    probe = batches_for(train, b_sz, 1, 0, 1)
-    t_probe = cpu_steps(rowptr, col, feats, labels, probe, cfg["hidden"], cfg["classes"], 0, 1)[0]
-    budget = args.ref_budget_s
-    total = args.steps + args.warmup
-    sample_b = b_sz
-    while sample_b > 64 and t_probe * (sample_b / b_sz) ** 1.5 * total > budget:
-        sample_b //= 2
-    batches = batches_for(train, sample_b, total, 0, 1)
-    times = cpu_steps(rowptr, col, feats, labels, batches, cfg["hidden"], cfg["classes"], args.warmup, args.steps)
+    warm = min(args.warmup, 3)
+    batches = batches_for(train, b_sz, min(args.steps + warm, 64), 0, 1)
+    t0 = time.time()
+    times, kind = cpu_steps(rowptr, col, feats, labels, batches, cfg["hidden"], cfg["classes"], warm, args.steps,
+                            budget_s=args.ref_budget_s)
     sec = float(np.sum(times))
-    value = sample_b * len(times) / sec
-    sample = (f"{len(times)} timed steps of {sample_b} seeds (b_sz {b_sz} named; probe step {t_probe:.2f}s) on the full "
-              f"{len(rowptr) - 1}-node graph, lazy dict-of-sets view, fwd+NLL+bwd+clip+SGD, torch {torch.__version__} CPU")
+    value = b_sz * len(times) / sec
+    sample = (f"{len(times)} timed steps (of {args.steps} asked; bounded by --ref-budget-s {args.ref_budget_s:.0f}) + {warm} "
+              f"warm-up steps of {b_sz} seeds on the full {len(rowptr) - 1}-node graph; "
+              f"{'the reference src/models.py classes (baseline/_ref)' if kind == 'reference' else 'oracle port of src/models.py'}, "
+              f"device cpu, {cores} threads of {os.cpu_count()} host cores, adjacency = lazy dict-of-sets view over the CSR "
+              f"(rows become Python sets on first touch; measured ~5% of a step), fwd+NLL+bwd+clip+SGD, no batch extension, "
+              f"torch {torch.__version__}, {time.time() - t0:.0f}s wall")
     line = {
         "impl": "reference", "metric": "seed_nodes_per_sec_fwd_bwd", "value": value, "unit": "seed nodes/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / len(times),
+        "n_gpus": args.gpus, "steps": len(times), "steps_requested": args.steps, "warmup": warm,
+        "ms_per_step": 1e3 * sec / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, cfg, rowptr, col, b_sz),
-        "cpu_baseline": {"value": value, "unit": "seed nodes/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "seed nodes/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "seed nodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -202,40 +251,51 @@ def workload_config(args, cfg, rowptr, col, b_sz):
 # ------------------------------------------------------------------------------------------------
 # this repo
 # ------------------------------------------------------------------------------------------------
-def timed_arms(torch, native, trainer, pipelined, dev_batches, host_batches, K, W, rank, local, sync_all, max_over_ranks):
-    """The two timed regions shared by every workload.  Returns (ms_dev, loss_dev, launches, ms_e2e, last_loss, clocks).
-    dev arm ("value"): K steps with every batch already in HBM.  e2e arm: K steps from HOST numpy batches, with the
-    pinned H2D copy of each batch and the D2H read of each loss inside the timed region."""
+def timed_arms(torch, native, trainer, pipelined, dev_batches, host_batches, K, W, rank, local, sync_all, max_over_ranks,
+               windows=25):
+    """The two timed regions shared by every workload.  Returns (ms_dev, loss_dev, launches, ms_e2e, last_loss, clocks,
+    window stats).  dev arm ("value"): K steps with every batch already in HBM.  e2e arm: K steps from HOST numpy
+    batches, with the pinned H2D copy of each batch and the D2H read of each loss inside the timed region.
+    Each arm times `windows` windows of EXACTLY K steps, every window bracketed by barrier + synchronize and by CUDA
+    events on the launching stream, max over ranks per window; the MEDIAN window is the reported one (a 20-step
+    window is 1-2 ms: one hiccup must not move the headline), min / max are reported beside it."""
+    n_rows = int(dev_batches.shape[0])
     if pipelined:
-        trainer.set_queue(dev_batches)                                         # the epoch's batches, resident in HBM
+        trainer.set_queue(dev_batches)                                         # the epoch's batches, resident in HBM (wraps)
         trainer.prime()
         trainer.run(W)
     else:
         for i in range(W):
-            trainer.step_device(dev_batches[i])
+            trainer.step_device(dev_batches[i % n_rows])
     sync_all()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
         time.sleep(0.25)
     native.launch_count_reset()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     t_begin = time.time()
-    e0.record()
-    if pipelined:
-        trainer.run(K)                                                         # K steps: train batch i | prepare batch i+1
-    else:
-        for i in range(K):
-            trainer.step_device(dev_batches[W + i])
-    e1.record()
-    sync_all()
-    t_end = time.time()
-    ms_dev = max_over_ranks(e0.elapsed_time(e1))
+    dev_ms = []
+    for w in range(windows):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if pipelined:
+            trainer.run(K)                                                     # K steps: train batch i | prepare batch i+1
+        else:
+            for i in range(K):
+                trainer.step_device(dev_batches[(W + w * K + i) % n_rows])
+        e1.record()
+        sync_all()
+        dev_ms.append(e0.elapsed_time(e1))
+    dev_ms = [max_over_ranks(x) for x in dev_ms]
+    ms_dev = float(np.median(dev_ms))
     loss_dev = float(trainer.loss.item())
-    launches_timed = trainer.launches_per_step * K if trainer.use_graph else native.launch_count()
+    launches_timed = trainer.launches_per_step * K if trainer.use_graph else native.launch_count() // max(windows, 1)
 
     # ---- end-to-end arm ("e2e"): host numpy batch -> pinned H2D -> step -> loss back on the host, every step ----
+    n_host = len(host_batches)
+    e2e_ms = []
+    last = 0.0
     if pipelined:
         # the loss of step i is copied D2H (pinned) right behind the step and read by the host one step later,
         # while step i+1 runs: one H2D of a batch and one D2H + host read of a loss per step, no bubble
@@ -245,41 +305,60 @@ def timed_arms(torch, native, trainer, pipelined, dev_batches, host_batches, K, 
         trainer.feed(host_batches[0])
         trainer.prime()
         for i in range(min(W, 3)):
-            trainer.feed(host_batches[1 + i])
+            trainer.feed(host_batches[(1 + i) % n_host])
             trainer.run(1)
         sync_all()
-        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e2.record()
-        last = 0.0
-        for i in range(K):
-            trainer.feed(host_batches[W + 1 + i])
-            dev_loss = trainer.run(1)
-            loss_pin[i & 1].copy_(dev_loss, non_blocking=True)
-            loss_ev[i & 1].record()
-            if i > 0:
-                loss_ev[(i - 1) & 1].synchronize()
-                last = float(loss_pin[(i - 1) & 1][0])
-        loss_ev[(K - 1) & 1].synchronize()
-        last = float(loss_pin[(K - 1) & 1][0])
-        e3.record()
-        sync_all()
+        for w in range(windows):
+            e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e2.record()
+            for i in range(K):
+                trainer.feed(host_batches[(W + 1 + w * K + i) % n_host])
+                dev_loss = trainer.run(1)
+                loss_pin[i & 1].copy_(dev_loss, non_blocking=True)
+                loss_ev[i & 1].record()
+                if i > 0:
+                    loss_ev[(i - 1) & 1].synchronize()
+                    last = float(loss_pin[(i - 1) & 1][0])
+            loss_ev[(K - 1) & 1].synchronize()
+            last = float(loss_pin[(K - 1) & 1][0])
+            e3.record()
+            sync_all()
+            e2e_ms.append(e2.elapsed_time(e3))
         trainer.flush()
     else:
         for i in range(min(W, 3)):
-            trainer.step(host_batches[i]).item()
+            trainer.step(host_batches[i % n_host]).item()
         sync_all()
-        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e2.record()
-        last = 0.0
-        for i in range(K):
-            last = trainer.step(host_batches[W + i]).item()                    # D2H of the loss every step
-        e3.record()
-        sync_all()
-    ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+        for w in range(windows):
+            e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e2.record()
+            for i in range(K):
+                last = trainer.step(host_batches[(W + w * K + i) % n_host]).item()   # D2H of the loss every step
+            e3.record()
+            sync_all()
+            e2e_ms.append(e2.elapsed_time(e3))
+    e2e_ms = [max_over_ranks(x) for x in e2e_ms]
+    ms_e2e = float(np.median(e2e_ms))
     if trainer.dp is not None:
         trainer.dp.status()                                                    # raises if a peer wait ever timed out
     clk = clocks.stop(t_begin, time.time()) if rank == 0 else None
-    return ms_dev, loss_dev, launches_timed, ms_e2e, last, clk
+    stats = {"n": windows, "steps_each": K, "reported": "median window",
+             "ms_per_step": {"median": ms_dev / K, "min": min(dev_ms) / K, "max": max(dev_ms) / K},
+             "e2e_ms_per_step": {"median": ms_e2e / K, "min": min(e2e_ms) / K, "max": max(e2e_ms) / K}}
+    return ms_dev, loss_dev, launches_timed, ms_e2e, last, clk, stats
+
+
+def replicas_identical(torch, dist, params, world, dev):
+    """True when every rank holds bit-identical parameters (an integer checksum of the raw fp32 words, all-gathered)."""
+    if world == 1:
+        return None
+    flat = torch.cat([p.detach().reshape(-1) for p in params]).contiguous()
+    words = flat.view(torch.int32).to(torch.int64)
+    idx = torch.arange(1, words.numel() + 1, device=dev, dtype=torch.int64)
+    chk = torch.stack([words.sum(), (words * (idx % 8191)).sum()])
+    out = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(out, chk)
+    return bool(all(torch.equal(o, out[0]) for o in out))
 
 
 def run_ours(args):
@@ -311,6 +390,10 @@ def run_ours(args):
     if rank != 0:
         cfg, rowptr, col, feats, labels, train = build_workload(args.scale)      # from the cache rank 0 wrote
     b_sz, K, W = args.b_sz, args.steps, args.warmup
+    if args.strong:                                  # strong scaling: the GLOBAL batch stays --b_sz, each rank takes 1/N of it
+        if b_sz % world:
+            raise ValueError(f"--strong needs --b_sz ({b_sz}) divisible by the number of GPUs ({world})")
+        b_sz //= world
 
     torch.manual_seed(SEED)
     feats_dev = torch.from_numpy(feats).to(dev)
@@ -346,8 +429,10 @@ def run_ours(args):
         return float(t.item())
 
     # ---- device-resident arm ("value") ----
-    ms_dev, loss_dev, launches_timed, ms_e2e, last, clk = timed_arms(
-        torch, native, trainer, pipelined, dev_batches, host_batches, K, W, rank, local, sync_all, max_over_ranks)
+    ms_dev, loss_dev, launches_timed, ms_e2e, last, clk, wstats = timed_arms(
+        torch, native, trainer, pipelined, dev_batches, host_batches, K, W, rank, local, sync_all, max_over_ranks,
+        windows=args.windows)
+    same = replicas_identical(torch, dist, trainer.weights + [trainer.cls_w, trainer.cls_b], world, dev)
 
     if args.timeline and rank == 0 and pipelined:
         dump_timeline(torch, native, PipelinedTrainer, model, cls, labels, b_sz, dev_batches, args.timeline)
@@ -361,19 +446,22 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         t0 = time.time()
-        cb = batches_for(train, b_sz, 3, 0, 1, seed=SEED + 1)
-        times = cpu_steps(rowptr, col, feats, labels, cb, cfg["hidden"], cfg["classes"], 1, 2)
+        torch.set_num_threads(os.cpu_count() or 1)
+        cb = batches_for(train, b_sz, 6, 0, 1, seed=SEED + 1)
+        times, kind = cpu_steps(rowptr, col, feats, labels, cb, cfg["hidden"], cfg["classes"], 1, 5, budget_s=25.0)
         cpu = {"value": b_sz * len(times) / float(np.sum(times)), "unit": "seed nodes/s",
-               "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"{len(times)} timed + 1 warm-up steps of {b_sz} seeds on the full graph "
-                         f"(oracle port of src/models.py, fwd+NLL+bwd+clip+SGD, {time.time() - t0:.0f}s wall)"}
+               "cores": torch.get_num_threads(), "kind": kind,
+               "sample": f"{len(times)} timed + 1 warm-up steps of {b_sz} seeds on the full graph ("
+                         f"{'the reference src/models.py from baseline/_ref' if kind == 'reference' else 'oracle port of src/models.py'}"
+                         f", device cpu, fwd+NLL+bwd+clip+SGD, {time.time() - t0:.0f}s wall)"}
 
     if rank == 0:
         seeds_total = b_sz * world * K
         line = {
             "metric": "seed_nodes_per_sec_fwd_bwd", "value": seeds_total / (ms_dev * 1e-3), "unit": "seed nodes/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_dev / K, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "f32 (tcgen05 3xTF32 split, fp32-faithful)", "tf32": "tf32"}[args.precision],
+            "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
+            "dtype": {"fp32": "f32", "tf32x3": "f32 (tcgen05 3xTF32 split, fp32-faithful)", "tf32": "tf32"}[args.precision],
             "data": "synthetic", "config": workload_config(args, cfg, rowptr, col, b_sz),
             "e2e": {"value": seeds_total / (ms_e2e * 1e-3), "unit": "seed nodes/s", "ms_per_step": ms_e2e / K,
                     "h2d_bytes_per_step": int(b_sz * 4), "d2h_bytes_per_step": 4},
@@ -381,7 +469,7 @@ def run_ours(args):
             "e2e_loss_read": ("async D2H into pinned memory behind every step, read by the host one step later"
                               if pipelined else "loss.item() after every step"),
             "cuda_graph": bool(trainer.use_graph), "loss": loss_dev, "loss_e2e": last,
-            "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
+            "roofline": roof, "cpu_baseline": cpu, "clocks": clk, "windows": wstats, "replicas_identical": same,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -453,8 +541,10 @@ def run_cfg5(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    ms_dev, loss_dev, _, ms_e2e, last, clk = timed_arms(
-        torch, native, trainer, pipelined, dev_batches, host_batches, K, W, rank, local, sync_all, max_over_ranks)
+    ms_dev, loss_dev, _, ms_e2e, last, clk, wstats = timed_arms(
+        torch, native, trainer, pipelined, dev_batches, host_batches, K, W, rank, local, sync_all, max_over_ranks,
+        windows=args.windows)
+    same = replicas_identical(torch, dist, trainer.weights + [trainer.cls_w, trainer.cls_b], world, dev)
 
     # ---- the sharded gather kernel alone: events around back-to-back launches on distinct frontiers ----
     weights = [w.detach() for w in trainer.weights]
@@ -513,7 +603,7 @@ def run_cfg5(args):
             "gpu_launches": int(trainer.launches_per_step * K), "launches_per_step": int(trainer.launches_per_step),
             "cuda_graph": bool(trainer.use_graph), "loss": loss_dev, "loss_e2e": last, "roofline": roof,
             "cpu_baseline": None, "cpu_baseline_note": "the reference cannot hold this graph (>100 GB of Python sets, SURVEY.md 8d)",
-            "clocks": clk,
+            "clocks": clk, "windows": wstats, "replicas_identical": same,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -877,6 +967,10 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--timeline", default="", help="diagnostics: write a per-launch completion timeline of the step to this file")
     ap.add_argument("--ref-budget-s", type=float, default=150.0)
+    ap.add_argument("--windows", type=int, default=25,
+                    help="timed windows of --steps steps each per arm; the median window is reported (min/max beside it)")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: --b_sz is the GLOBAL batch, split evenly over the GPUs (default: weak, --b_sz per GPU)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         log("[bench] raising --warmup to 3 (timing rule)")

@@ -154,7 +154,7 @@ def test_reference_arm_prints_the_contract_line(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
            "--scale", "0.003", "--b_sz", "128"]
-    env = dict(os.environ, GSAGE_CACHE=str(tmp_path))
+    env = dict(os.environ, GSAGE_CACHE=str(tmp_path), OMP_NUM_THREADS="1")       # what torchrun exports
     out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=240)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
@@ -162,7 +162,10 @@ def test_reference_arm_prints_the_contract_line(tmp_path):
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "seed_nodes_per_sec_fwd_bwd" and d["unit"] == "seed nodes/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 1
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    staged = os.path.isfile(os.path.join(root, "baseline", "_ref", "src", "models.py"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if staged else "port")      # the reference itself when it is staged
+    assert d["cpu_baseline"]["cores"] == (os.cpu_count() or 1)                   # every host thread, also under torchrun's OMP_NUM_THREADS=1
+    assert d["cpu_baseline"]["value"] == d["value"] and d["config"]["b_sz_per_gpu"] == 128      # the batch is never shrunk
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("cfg3_products") and d["config"]["fanout"] == 10
     other = subprocess.run(cmd, capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2"), timeout=60)
