@@ -81,17 +81,27 @@ __device__ __forceinline__ int seg_of(const DpSegs& s, long long elem) {
   return k;
 }
 
+#ifdef GS_TOP_TRACE
+__device__ long long g_dp_trace[16];
+#define GS_DP_MARK(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_dp_trace[(slot)] = clock64(); } while (0)
+#else
+#define GS_DP_MARK(slot) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(kDpThreads)
 dp_update_kernel(float* __restrict__ flat, long long n_total, const DpPeers peers_arg, const DpSegs segs_arg,
                  DpState* __restrict__ st, float max_norm, float lr, unsigned long long timeout_ns,
                  long long* __restrict__ step_counter) {
+  GS_DP_MARK(0);
   pdl_sync();
+  GS_DP_MARK(1);
   // the tables are indexed dynamically: keep them in shared memory, not in a local-memory copy of the parameters
   __shared__ DpPeers peers;
   __shared__ DpSegs segs;
   const int G = gridDim.x, c = blockIdx.x, tid = threadIdx.x;
   if (tid == 0) { peers = peers_arg; segs = segs_arg; }
   __syncthreads();
+  GS_DP_MARK(2);
   const unsigned int e = st->epoch + 1u;
   const int par = static_cast<int>(e & 1u);
   const long long n4 = n_total >> 2;
@@ -128,6 +138,7 @@ dp_update_kernel(float* __restrict__ flat, long long n_total, const DpPeers peer
     __syncthreads();
   }
 
+  GS_DP_MARK(3);
   // ---- reduce in rank order, scale to the mean, per-group sum of squares ----
   const float inv_w = 1.0f / static_cast<float>(W);
   float ss[kDpMaxGroups];
@@ -163,6 +174,7 @@ dp_update_kernel(float* __restrict__ flat, long long n_total, const DpPeers peer
     for (int w = 0; w < kDpThreads / 32; ++w) v += s_red[w][tid];
     st->partial[c][tid] = v;
   }
+  GS_DP_MARK(4);
   // ---- grid barrier (arrive counter grows by G every epoch) ----
   __threadfence();
   __syncthreads();
@@ -179,6 +191,7 @@ dp_update_kernel(float* __restrict__ flat, long long n_total, const DpPeers peer
     }
   }
   __syncthreads();
+  GS_DP_MARK(5);
   if (tid < 32) {
     // all G x groups partials in flight at once (lane = CTA, G <= 64), then a shuffle tree: the order of the
     // additions is fixed by the lane numbers, hence identical on every CTA and every rank
@@ -201,6 +214,7 @@ dp_update_kernel(float* __restrict__ flat, long long n_total, const DpPeers peer
     }
   }
   __syncthreads();
+  GS_DP_MARK(6);
 
   // ---- SGD on my slice, gradient zeroed for the next step ----
   for (long long i = b4 + tid; i < e4; i += kDpThreads) {
@@ -222,6 +236,7 @@ dp_update_kernel(float* __restrict__ flat, long long n_total, const DpPeers peer
     }
     flat4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  GS_DP_MARK(7);
   if (c == 0 && tid == 0) {
     st->epoch = e;
     if (step_counter) *step_counter += 1;          // Philox offset of the next step's sampler (trainer.py)
@@ -345,3 +360,11 @@ extern "C" int gs_peer_close(void* ptr) {
   if (!ptr) return GS_OK;
   return static_cast<int>(cudaIpcCloseMemHandle(ptr));
 }
+
+#ifdef GS_TOP_TRACE
+extern "C" int gs_debug_dp_trace_read(long long* host_out, int n) {
+  if (n > 16) n = 16;
+  cudaDeviceSynchronize();
+  return static_cast<int>(cudaMemcpyFromSymbol(host_out, gs::g_dp_trace, sizeof(long long) * n));
+}
+#endif

@@ -253,19 +253,35 @@ static int check_x(const float* self_table, int64_t ld_self, const float* agg, i
 using namespace gs;
 
 int gs_sage_gemm_fwd_tc(const float*, int64_t, const int32_t*, const float*, int64_t, int32_t, const float*, int64_t,
-                        int32_t, int32_t, const int32_t*, int32_t, float*, int64_t, int32_t, int32_t, gs_stream_t);
+                        int32_t, int32_t, const int32_t*, int32_t, float*, int64_t, int32_t, int32_t, float*, int64_t,
+                        gs_stream_t);
 int gs_sage_gemm_bwd_x_tc(const float*, int64_t, const float*, int64_t, const float*, int64_t, int32_t, int32_t, int32_t,
                           int32_t, const int32_t*, int32_t, float*, int64_t, float*, int64_t, int32_t, gs_stream_t);
 int gs_sage_gemm_bwd_w_tc(const float*, int64_t, const int32_t*, const float*, int64_t, int32_t, const float*, int64_t,
                           const float*, int64_t, int32_t, int32_t, int32_t, const int32_t*, int32_t, float*, int64_t,
                           int32_t, gs_stream_t);
+int gs_sage_gemm_bwd_w_pair_tc(const float* const*, const int64_t*, const int32_t* const*, const float* const*,
+                               const int64_t*, const int32_t*, const float* const*, const int64_t*, const float* const*,
+                               const int64_t*, const int32_t*, int32_t, int32_t, const int32_t* const*, const int32_t*,
+                               float* const*, const int64_t*, int32_t, gs_stream_t);
 
 extern "C" int gs_sage_gemm_fwd(const float* self_table, int64_t ld_self, const int32_t* self_idx,
                                 const float* agg, int64_t ld_agg, int32_t dim,
                                 const float* weight, int64_t ldw, int32_t out_dim, int32_t gcn,
                                 const int32_t* num_rows_dev, int32_t max_rows,
                                 float* out, int64_t ld_out, int32_t relu, int32_t precision, gs_stream_t stream) {
+  return gs_sage_gemm_fwd_ex(self_table, ld_self, self_idx, agg, ld_agg, dim, weight, ldw, out_dim, gcn, num_rows_dev,
+                             max_rows, out, ld_out, relu, precision, nullptr, 0, stream);
+}
+
+extern "C" int gs_sage_gemm_fwd_ex(const float* self_table, int64_t ld_self, const int32_t* self_idx,
+                                   const float* agg, int64_t ld_agg, int32_t dim,
+                                   const float* weight, int64_t ldw, int32_t out_dim, int32_t gcn,
+                                   const int32_t* num_rows_dev, int32_t max_rows,
+                                   float* out, int64_t ld_out, int32_t relu, int32_t precision,
+                                   float* zero_out, int64_t ld_zero, gs_stream_t stream) {
   if (!weight || !out || out_dim < 1 || max_rows < 0) return GS_ERR_BAD_ARG;
+  if (zero_out && ld_zero < out_dim) return GS_ERR_BAD_ARG;
   if (int e = check_x(self_table, ld_self, agg, ld_agg, dim, gcn)) return e;
   if (ldw < (gcn ? dim : 2 * dim) || ld_out < out_dim) return GS_ERR_BAD_ARG;
   if (max_rows == 0) return GS_OK;
@@ -276,7 +292,12 @@ extern "C" int gs_sage_gemm_fwd(const float* self_table, int64_t ld_self, const 
   if (precision == GS_PREC_TF32X3 && k_total > 1024) precision = GS_PREC_FP32;
   if (precision != GS_PREC_FP32)
     return gs_sage_gemm_fwd_tc(self_table, ld_self, self_idx, agg, ld_agg, dim, weight, ldw, out_dim, gcn,
-                               num_rows_dev, max_rows, out, ld_out, relu, precision, stream);
+                               num_rows_dev, max_rows, out, ld_out, relu, precision, zero_out, ld_zero, stream);
+  if (zero_out) {       // FFMA path: a memset node in front (the tensor-core path folds the fill into its epilogue)
+    cudaError_t e = cudaMemset2DAsync(zero_out, static_cast<size_t>(ld_zero) * 4, 0, static_cast<size_t>(out_dim) * 4,
+                                      static_cast<size_t>(max_rows), as_stream(stream));
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
   XOperand x{self_table, ld_self, self_idx, agg, ld_agg, dim, (dim + 3) & ~3, gcn};
   dim3 grid((max_rows + BM - 1) / BM, (out_dim + BN - 1) / BN);
   launch(sage_fwd_kernel, grid, kGemmThreads, 0, as_stream(stream), x, weight, ldw, out_dim, num_rows_dev, max_rows, out,
@@ -334,6 +355,43 @@ extern "C" int gs_sage_gemm_bwd_w(const float* self_table, int64_t ld_self, cons
   launch(sage_bwd_w_kernel, grid, kGemmThreads, 0, as_stream(stream), x, grad_out, ld_go, out, ld_out, out_dim, relu,
                                                                   num_rows_dev, max_rows, rows_per_chunk, grad_w, ldw);
   return finish_launch();
+}
+
+// Two weight-gradient problems (two layers of one step) in one call.  Arrays of 2 (HOST arrays of device pointers /
+// sizes).  Tensor-core precisions run them as ONE grid; otherwise, or when they cannot share a kernel, one after the other.
+extern "C" int gs_sage_gemm_bwd_w_pair(const float* const* self_table_host, const int64_t* ld_self_host,
+                                       const int32_t* const* self_idx_host, const float* const* agg_host,
+                                       const int64_t* ld_agg_host, const int32_t* dim_host,
+                                       const float* const* grad_out_host, const int64_t* ld_go_host,
+                                       const float* const* out_host, const int64_t* ld_out_host,
+                                       const int32_t* out_dim_host, int32_t gcn, int32_t relu,
+                                       const int32_t* const* num_rows_dev_host, const int32_t* max_rows_host,
+                                       float* const* grad_w_host, const int64_t* ldw_host, int32_t precision,
+                                       gs_stream_t stream) {
+  if (!self_table_host || !ld_self_host || !self_idx_host || !agg_host || !ld_agg_host || !dim_host || !grad_out_host ||
+      !ld_go_host || !out_host || !ld_out_host || !out_dim_host || !num_rows_dev_host || !max_rows_host || !grad_w_host ||
+      !ldw_host)
+    return GS_ERR_BAD_ARG;
+  bool fused = precision != GS_PREC_FP32 && max_rows_host[0] > 0 && max_rows_host[1] > 0;
+  for (int i = 0; i < 2 && fused; ++i) {
+    if (!grad_out_host[i] || !grad_w_host[i] || out_dim_host[i] < 1 || (relu && !out_host[i])) return GS_ERR_BAD_ARG;
+    if (int e = check_x(self_table_host[i], ld_self_host[i], agg_host[i], ld_agg_host[i], dim_host[i], gcn)) return e;
+    if (ldw_host[i] < (gcn ? dim_host[i] : 2 * dim_host[i])) return GS_ERR_BAD_ARG;
+  }
+  if (fused) {
+    const int e = gs_sage_gemm_bwd_w_pair_tc(self_table_host, ld_self_host, self_idx_host, agg_host, ld_agg_host, dim_host,
+                                             grad_out_host, ld_go_host, out_host, ld_out_host, out_dim_host, gcn, relu,
+                                             num_rows_dev_host, max_rows_host, grad_w_host, ldw_host, precision, stream);
+    if (e != GS_ERR_UNSUPPORTED) return e;
+  }
+  for (int i = 0; i < 2; ++i) {
+    const int e = gs_sage_gemm_bwd_w(self_table_host[i], ld_self_host[i], self_idx_host[i], agg_host[i], ld_agg_host[i],
+                                     dim_host[i], grad_out_host[i], ld_go_host[i], out_host[i], ld_out_host[i],
+                                     out_dim_host[i], gcn, relu, num_rows_dev_host[i], max_rows_host[i], grad_w_host[i],
+                                     ldw_host[i], precision, stream);
+    if (e) return e;
+  }
+  return GS_OK;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -431,11 +431,16 @@ struct LoadX_MN {          // bwd_w B: X[r = k, kv = n..n+3], MN-major (kv conti
 // consecutive accumulator columns; the lanes of a warp hold consecutive n of ONE row, so global
 // accesses are coalesced
 // ---------------------------------------------------------------------------------------------
-struct StoreOut {          // forward: out[r, h] = relu(acc)
-  float* out; int64_t ld_out; int row0, rows, h0, out_dim, relu;
+struct StoreOut {          // forward: out[r, h] = relu(acc); optionally zero-fills a second buffer of the same shape
+  float* out; int64_t ld_out; int row0, rows, h0, out_dim, relu; float* zero; int64_t ld_zero;
   __device__ __forceinline__ void operator()(int m, int n, float4 v) const {
     const int r = row0 + m, h = h0 + n;
     if (r >= rows || h >= out_dim) return;
+    if (zero) {            // the gradient w.r.t. this output: the backward scatter accumulates into it later in the step
+      float* z = zero + static_cast<int64_t>(r) * ld_zero + h;
+      if (h + 3 < out_dim && ((reinterpret_cast<uintptr_t>(z) & 15u) == 0)) *reinterpret_cast<float4*>(z) = zero4();
+      else for (int j = 0; j < 4; ++j) if (h + j < out_dim) z[j] = 0.f;
+    }
     if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
     float* dst = out + static_cast<int64_t>(r) * ld_out + h;
     if (h + 3 < out_dim && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
@@ -787,7 +792,7 @@ __global__ void __maxnreg__(kMaxRegs)
 sage_fwd_tc_kernel(XView x, const float* __restrict__ weight, int64_t ldw, int out_dim, bool vec_ok,
                    const int32_t* __restrict__ num_rows_dev, int max_rows, float* __restrict__ out, int64_t ld_out,
                    int relu, int n_tile, int k_stages, int num_stages, const __grid_constant__ CUtensorMap tmap_w,
-                   int use_tma_w) {
+                   int use_tma_w, float* __restrict__ zero_out, int64_t ld_zero) {
   pdl_sync();
   extern __shared__ unsigned char smem_dyn[];
   const int rows = live_rows(num_rows_dev, max_rows);
@@ -798,7 +803,7 @@ sage_fwd_tc_kernel(XView x, const float* __restrict__ weight, int64_t ldw, int o
   x.fill_cache(s_rowidx, row0, kTileM, rows);            // made visible by the __syncthreads in gemm_core
   LoadX_K la{x, row0, rows};
   LoadW_K lb{x, weight, ldw, h0, out_dim, vec_ok};
-  StoreOut epi{out, ld_out, row0, rows, h0, out_dim, relu};
+  StoreOut epi{out, ld_out, row0, rows, h0, out_dim, relu, zero_out, ld_zero};
   gemm_core<false, false, SPLIT3, ASYNC>(la, lb, epi, nt, k_stages, num_stages, smem_dyn, weight,
                                          (ASYNC && use_tma_w) ? &tmap_w : nullptr, h0, n_tile);
 }
@@ -822,26 +827,39 @@ sage_bwd_x_tc_kernel(const float* __restrict__ grad_out, int64_t ld_go, const fl
   gemm_core<false, true, SPLIT3, ASYNC>(la, lb, epi, nt, k_stages, num_stages, smem_dyn, weight);
 }
 
+// One weight-gradient problem dW[h,kv] += sum_r dZ[r,h] X[r,kv], cut into `chunks` row chunks.
+struct BwdWProblem {
+  XView x; const float* grad_out; int64_t ld_go; const float* out; int64_t ld_out; int out_dim, relu;
+  const int32_t* num_rows_dev; int max_rows, rows_per_chunk; float* grad_w; int64_t ldw; int n_tile, num_stages;
+  int tiles_x, tiles_y, chunks;
+};
+
+// The grid's z axis runs over the row chunks of problem A, then those of problem B (pb.chunks == 0: one problem).
+// Two layers' weight gradients are independent leaves of a step's dependency graph; launched as one grid they
+// share the machine (CTAs split in proportion to their work) instead of queueing behind each other.
 template <bool SPLIT3, bool ASYNC>
 __global__ void __maxnreg__(kMaxRegs)
-sage_bwd_w_tc_kernel(XView x, const float* __restrict__ grad_out, int64_t ld_go, const float* __restrict__ out,
-                     int64_t ld_out, int out_dim, int relu, const int32_t* __restrict__ num_rows_dev, int max_rows,
-                     int rows_per_chunk, float* __restrict__ grad_w, int64_t ldw, int n_tile, int num_stages) {
+sage_bwd_w_tc_kernel(const BwdWProblem pa, const BwdWProblem pb) {
   pdl_sync();
   extern __shared__ unsigned char smem_dyn[];
-  const int rows = live_rows(num_rows_dev, max_rows);
-  const int kv0 = blockIdx.x * n_tile, h0 = blockIdx.y * kTileM;
-  const int r_begin = blockIdx.z * rows_per_chunk;
-  const int r_end = min(rows, r_begin + rows_per_chunk);
+  const bool first = static_cast<int>(blockIdx.z) < pa.chunks;
+  const BwdWProblem q = first ? pa : pb;
+  const int chunk = first ? blockIdx.z : blockIdx.z - pa.chunks;
+  if (static_cast<int>(blockIdx.x) >= q.tiles_x || static_cast<int>(blockIdx.y) >= q.tiles_y) return;
+  XView x = q.x;
+  const int rows = live_rows(q.num_rows_dev, q.max_rows);
+  const int kv0 = blockIdx.x * q.n_tile, h0 = blockIdx.y * kTileM;
+  const int r_begin = chunk * q.rows_per_chunk;
+  const int r_end = min(rows, r_begin + q.rows_per_chunk);
   if (r_begin >= r_end) return;
-  const int nt = min(n_tile, ((x.kv_total() - kv0) + 15) & ~15);
+  const int nt = min(q.n_tile, ((x.kv_total() - kv0) + 15) & ~15);
   const int k_stages = (r_end - r_begin + kBK - 1) / kBK;
   __shared__ int32_t s_rowidx[kMaxChunkRows];
-  x.fill_cache(s_rowidx, r_begin, min(rows_per_chunk, kMaxChunkRows), rows);
-  LoadDZ_MN la{grad_out, ld_go, out, ld_out, r_begin, r_end, h0, out_dim, relu};
+  x.fill_cache(s_rowidx, r_begin, min(q.rows_per_chunk, kMaxChunkRows), rows);
+  LoadDZ_MN la{q.grad_out, q.ld_go, q.out, q.ld_out, r_begin, r_end, h0, q.out_dim, q.relu};
   LoadX_MN lb{x, r_begin, r_end, kv0};
-  AddDW epi{x, grad_w, ldw, h0, out_dim, kv0};
-  gemm_core<true, true, SPLIT3, ASYNC>(la, lb, epi, nt, k_stages, num_stages, smem_dyn, grad_out);
+  AddDW epi{x, q.grad_w, q.ldw, h0, q.out_dim, kv0};
+  gemm_core<true, true, SPLIT3, ASYNC>(la, lb, epi, nt, k_stages, q.num_stages, smem_dyn, q.grad_out);
 }
 
 struct Plan { int n_tile, num_stages, smem; };
@@ -886,7 +904,7 @@ static EncodeTiledFn encode_tiled_fn() {
   }
   return fn;
 }
-static bool make_tmap_2d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+bool make_tmap_2d(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn || box_rows < 1 || box_rows > 256 || (ld & 3) || !aligned16(base)) return false;
   const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
@@ -927,7 +945,7 @@ using namespace gs::tc;
 int gs_sage_gemm_fwd_tc(const float* self_table, int64_t ld_self, const int32_t* self_idx, const float* agg,
                         int64_t ld_agg, int32_t dim, const float* weight, int64_t ldw, int32_t out_dim, int32_t gcn,
                         const int32_t* num_rows_dev, int32_t max_rows, float* out, int64_t ld_out, int32_t relu,
-                        int32_t precision, gs_stream_t stream) {
+                        int32_t precision, float* zero_out, int64_t ld_zero, gs_stream_t stream) {
   const bool split3 = precision == GS_PREC_TF32X3;
   if (precision != GS_PREC_TF32 && !split3) return GS_ERR_BAD_ARG;
   XView x{self_table, ld_self, self_idx, agg, ld_agg, dim, (dim + 3) & ~3, gcn, nullptr, 0, 0};
@@ -942,7 +960,7 @@ int gs_sage_gemm_fwd_tc(const float* self_table, int64_t ld_self, const int32_t*
   memset(&tmap_w, 0, sizeof(tmap_w));
   const int use_tma_w = (async && out_dim % p.n_tile == 0 && make_tmap_2d(&tmap_w, weight, out_dim, kt, ldw, p.n_tile)) ? 1 : 0;
   GS_TC_LAUNCH(sage_fwd_tc_kernel, grid, p.smem, as_stream(stream), x, weight, ldw, out_dim, vec_ok, num_rows_dev,
-               max_rows, out, ld_out, relu, p.n_tile, k_stages, p.num_stages, tmap_w, use_tma_w);
+               max_rows, out, ld_out, relu, p.n_tile, k_stages, p.num_stages, tmap_w, use_tma_w, zero_out, ld_zero);
   return finish_launch();
 }
 
@@ -964,29 +982,85 @@ int gs_sage_gemm_bwd_x_tc(const float* grad_out, int64_t ld_go, const float* out
   return finish_launch();
 }
 
+// Row chunks of one problem for a budget of `cta_budget` CTAs (about one per SM): at least 4 k-stages per CTA, at
+// most kMaxChunkRows rows (the index cache).  Returns the dynamic shared memory its CTAs need.
+static int plan_bwd_w(BwdWProblem& q, int kt, int out_dim, int max_rows, bool split3, int cta_budget) {
+  const Plan p = make_plan(kt, true, true, split3, kNumSMs);   // row chunks fill the machine
+  q.n_tile = p.n_tile;
+  q.num_stages = p.num_stages;
+  q.tiles_x = (kt + p.n_tile - 1) / p.n_tile;
+  q.tiles_y = (out_dim + kTileM - 1) / kTileM;
+  const int tiles = q.tiles_x * q.tiles_y;
+  int chunks = (cta_budget + tiles - 1) / tiles;
+  const int max_chunks = (max_rows + 4 * kBK - 1) / (4 * kBK);
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  int rows_per_chunk = (max_rows + chunks - 1) / chunks;
+  rows_per_chunk = ((rows_per_chunk + kBK - 1) / kBK) * kBK;
+  if (rows_per_chunk > kMaxChunkRows) rows_per_chunk = kMaxChunkRows;
+  q.rows_per_chunk = rows_per_chunk;
+  q.chunks = (max_rows + rows_per_chunk - 1) / rows_per_chunk;
+  return p.smem;
+}
+
+static bool bwd_w_async_ok(const float* grad_out, int64_t ld_go, int out_dim, int relu) {
+  return !relu && (out_dim % 4 == 0) && (ld_go % 4 == 0) && aligned16(grad_out);
+}
+
+static int launch_bwd_w(const BwdWProblem& pa, const BwdWProblem& pb, int smem, bool split3, bool async, gs_stream_t stream) {
+  const int tx = pa.tiles_x > pb.tiles_x ? pa.tiles_x : pb.tiles_x;
+  const int ty = pa.tiles_y > pb.tiles_y ? pa.tiles_y : pb.tiles_y;
+  dim3 grid(tx, ty, pa.chunks + pb.chunks);
+  GS_TC_LAUNCH(sage_bwd_w_tc_kernel, grid, smem, as_stream(stream), pa, pb);
+  return finish_launch();
+}
+
 int gs_sage_gemm_bwd_w_tc(const float* self_table, int64_t ld_self, const int32_t* self_idx, const float* agg,
                           int64_t ld_agg, int32_t dim, const float* grad_out, int64_t ld_go, const float* out,
                           int64_t ld_out, int32_t out_dim, int32_t gcn, int32_t relu, const int32_t* num_rows_dev,
                           int32_t max_rows, float* grad_w, int64_t ldw, int32_t precision, gs_stream_t stream) {
   const bool split3 = precision == GS_PREC_TF32X3;
   if (precision != GS_PREC_TF32 && !split3) return GS_ERR_BAD_ARG;
-  XView x{self_table, ld_self, self_idx, agg, ld_agg, dim, (dim + 3) & ~3, gcn, nullptr, 0, 0};
-  const int kt = gcn ? x.dim_pad : 2 * x.dim_pad;
-  const Plan p = make_plan(kt, true, true, split3, kNumSMs);   // row chunks fill the machine
-  const int tiles = ((kt + p.n_tile - 1) / p.n_tile) * ((out_dim + kTileM - 1) / kTileM);
-  int chunks = (kNumSMs + tiles - 1) / tiles;                 // about one CTA per SM
-  const int max_chunks = (max_rows + 4 * kBK - 1) / (4 * kBK);   // at least 4 k-stages per CTA
-  if (chunks > max_chunks) chunks = max_chunks;
-  if (chunks < 1) chunks = 1;
-  int rows_per_chunk = (max_rows + chunks - 1) / chunks;
-  rows_per_chunk = ((rows_per_chunk + kBK - 1) / kBK) * kBK;
-  if (rows_per_chunk > kMaxChunkRows) rows_per_chunk = kMaxChunkRows;
-  chunks = (max_rows + rows_per_chunk - 1) / rows_per_chunk;
-  const bool async = !relu && (out_dim % 4 == 0) && (ld_go % 4 == 0) && aligned16(grad_out);
-  dim3 grid((kt + p.n_tile - 1) / p.n_tile, (out_dim + kTileM - 1) / kTileM, chunks);
-  GS_TC_LAUNCH(sage_bwd_w_tc_kernel, grid, p.smem, as_stream(stream), x, grad_out, ld_go, out, ld_out, out_dim, relu,
-               num_rows_dev, max_rows, rows_per_chunk, grad_w, ldw, p.n_tile, p.num_stages);
-  return finish_launch();
+  BwdWProblem pa{};
+  pa.x = XView{self_table, ld_self, self_idx, agg, ld_agg, dim, (dim + 3) & ~3, gcn, nullptr, 0, 0};
+  pa.grad_out = grad_out; pa.ld_go = ld_go; pa.out = out; pa.ld_out = ld_out; pa.out_dim = out_dim; pa.relu = relu;
+  pa.num_rows_dev = num_rows_dev; pa.max_rows = max_rows; pa.grad_w = grad_w; pa.ldw = ldw;
+  const int kt = gcn ? pa.x.dim_pad : 2 * pa.x.dim_pad;
+  const int smem = plan_bwd_w(pa, kt, out_dim, max_rows, split3, kNumSMs);
+  BwdWProblem pb{};                                             // no second problem
+  return launch_bwd_w(pa, pb, smem, split3, bwd_w_async_ok(grad_out, ld_go, out_dim, relu), stream);
+}
+
+// Two problems in one launch (see sage_bwd_w_tc_kernel).  Returns GS_ERR_UNSUPPORTED when they cannot share a
+// kernel instantiation (the caller then launches them one after the other).
+int gs_sage_gemm_bwd_w_pair_tc(const float* const* self_table, const int64_t* ld_self, const int32_t* const* self_idx,
+                               const float* const* agg, const int64_t* ld_agg, const int32_t* dim,
+                               const float* const* grad_out, const int64_t* ld_go, const float* const* out,
+                               const int64_t* ld_out, const int32_t* out_dim, int32_t gcn, int32_t relu,
+                               const int32_t* const* num_rows_dev, const int32_t* max_rows, float* const* grad_w,
+                               const int64_t* ldw, int32_t precision, gs_stream_t stream) {
+  const bool split3 = precision == GS_PREC_TF32X3;
+  if (precision != GS_PREC_TF32 && !split3) return GS_ERR_BAD_ARG;
+  BwdWProblem pr[2] = {};
+  int kt[2];
+  double work[2];
+  for (int i = 0; i < 2; ++i) {
+    pr[i].x = XView{self_table[i], ld_self[i], self_idx[i], agg[i], ld_agg[i], dim[i], (dim[i] + 3) & ~3, gcn, nullptr, 0, 0};
+    pr[i].grad_out = grad_out[i]; pr[i].ld_go = ld_go[i]; pr[i].out = out[i]; pr[i].ld_out = ld_out[i];
+    pr[i].out_dim = out_dim[i]; pr[i].relu = relu; pr[i].num_rows_dev = num_rows_dev[i]; pr[i].max_rows = max_rows[i];
+    pr[i].grad_w = grad_w[i]; pr[i].ldw = ldw[i];
+    kt[i] = gcn ? pr[i].x.dim_pad : 2 * pr[i].x.dim_pad;
+    work[i] = static_cast<double>(max_rows[i]) * kt[i] * out_dim[i];
+  }
+  const bool async0 = bwd_w_async_ok(grad_out[0], ld_go[0], out_dim[0], relu);
+  if (async0 != bwd_w_async_ok(grad_out[1], ld_go[1], out_dim[1], relu)) return GS_ERR_UNSUPPORTED;
+  // CTAs in proportion to the work, every problem at least one CTA per output tile
+  int budget1 = static_cast<int>(kNumSMs * work[1] / (work[0] + work[1]) + 0.5);
+  if (budget1 < 2) budget1 = 2;
+  if (budget1 > kNumSMs - 2) budget1 = kNumSMs - 2;
+  const int smem0 = plan_bwd_w(pr[0], kt[0], out_dim[0], max_rows[0], split3, kNumSMs - budget1);
+  const int smem1 = plan_bwd_w(pr[1], kt[1], out_dim[1], max_rows[1], split3, budget1);
+  return launch_bwd_w(pr[0], pr[1], smem0 > smem1 ? smem0 : smem1, split3, async0, stream);
 }
 
 #ifdef GS_TC_TRACE

@@ -17,74 +17,109 @@ namespace gs {
 // ---------------------------------------------------------------------------------------
 constexpr int kSampleWarps = 8;
 
+// Optional work folded into a sampler launch (each saves a launch of the preparation chain, ~4 us apiece there):
+//   queue / fetch_dst : the rows ARE the next batch of the device-side queue (gs_fetch_batch): row r's node is
+//                       queue[(next % rows) * max_rows + r], copied to fetch_dst[r]; the last CTA advances `next`
+//   mark              : K2's "mark" pass -- every id of the row (its node and the drawn neighbours) sets its bit
+//   clear             : K2's "clear" pass of the PREVIOUS unique -- the rows of this launch are exactly the ids that
+//                       unique emitted, so each row zeroes the bitmap word of its own node
+struct SampleExtras {
+  long long* queue;          // {address, rows, next, ticket}
+  int32_t* fetch_dst;
+  uint32_t* mark;
+  uint32_t* clear;
+};
+
 __global__ void __launch_bounds__(kSampleWarps * 32)
 sample_neighbors_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t num_nodes,
                         const int32_t* __restrict__ nodes, const int32_t* __restrict__ num_rows_dev, int max_rows,
                         int k, int stride, int self_mode, uint64_t seed, uint64_t offset,
                         const int64_t* __restrict__ offset_dev,
-                        int32_t* __restrict__ out_nbr, int32_t* __restrict__ out_cnt) {
+                        int32_t* __restrict__ out_nbr, int32_t* __restrict__ out_cnt, const SampleExtras ex) {
   pdl_sync();
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * kSampleWarps + (threadIdx.x >> 5);
-  if (r >= max_rows) return;
   const int rows = live_rows(num_rows_dev, max_rows);
-  int32_t* dst = out_nbr + static_cast<int64_t>(r) * stride;
-  if (r >= rows) {           // keep the padding region well defined for the consumers
-    for (int j = lane; j < stride; j += 32) dst[j] = -1;
-    if (lane == 0) out_cnt[r] = 0;
-    return;
+  const int32_t* src = nodes;
+  if (ex.queue != nullptr) {                      // fused gs_fetch_batch
+    const int32_t* base = reinterpret_cast<const int32_t*>(ex.queue[0]);
+    const long long q_rows = ex.queue[1], next = ex.queue[2];
+    src = (base != nullptr && q_rows > 0) ? base + (next % q_rows) * max_rows : nullptr;
   }
-  const int32_t me = __ldg(nodes + r);
-  constexpr int32_t kNone = 0x7fffffff;
-  int32_t val = kNone;
-  if (me >= 0 && me < num_nodes) {
-    const int64_t beg = __ldg(rowptr + me);
-    const uint32_t deg = static_cast<uint32_t>(__ldg(rowptr + me + 1) - beg);
-    if (deg < static_cast<uint32_t>(k)) {
-      if (static_cast<uint32_t>(lane) < deg) val = __ldg(col + beg + lane);
+  if (r < max_rows) {
+    int32_t* dst = out_nbr + static_cast<int64_t>(r) * stride;
+    if (r >= rows) {           // keep the padding region well defined for the consumers
+      for (int j = lane; j < stride; j += 32) dst[j] = -1;
+      if (lane == 0) out_cnt[r] = 0;
     } else {
-      if (offset_dev != nullptr) offset += static_cast<uint64_t>(__ldg(offset_dev)) << 8;
-      uint32_t mypos = 0xffffffffu;
-      uint32_t draw[4];
-      for (int i = 0; i < k; ++i) {              // warp-uniform loop: every lane runs the same stream
-        if ((i & 3) == 0)
-          philox4x32_10(static_cast<uint32_t>(r), static_cast<uint32_t>(i >> 2), static_cast<uint32_t>(offset),
-                        static_cast<uint32_t>(offset >> 32), seed, draw);
-        const uint32_t x = (i & 3) == 0 ? draw[0] : (i & 3) == 1 ? draw[1] : (i & 3) == 2 ? draw[2] : draw[3];
-        const uint32_t j = deg - k + i;
-        const uint32_t t = __umulhi(x, j + 1);   // uniform in [0, j]
-        const bool taken = __any_sync(0xffffffffu, mypos == t);
-        if (lane == i) mypos = taken ? j : t;
+      const int32_t me = src != nullptr ? __ldg(src + r) : -1;
+      if (ex.fetch_dst != nullptr && lane == 0) ex.fetch_dst[r] = me;
+      constexpr int32_t kNone = 0x7fffffff;
+      int32_t val = kNone;
+      if (me >= 0 && me < num_nodes) {
+        if (lane == 0) {
+          if (ex.clear != nullptr) ex.clear[me >> 5] = 0u;
+          if (ex.mark != nullptr) atomicOr(ex.mark + (me >> 5), 1u << (me & 31));
+        }
+        const int64_t beg = __ldg(rowptr + me);
+        const uint32_t deg = static_cast<uint32_t>(__ldg(rowptr + me + 1) - beg);
+        if (deg < static_cast<uint32_t>(k)) {
+          if (static_cast<uint32_t>(lane) < deg) val = __ldg(col + beg + lane);
+        } else {
+          if (offset_dev != nullptr) offset += static_cast<uint64_t>(__ldg(offset_dev)) << 8;
+          // Floyd's subset sampling.  Draw i comes from Philox block (row, i): lane i computes its own (the k draws in
+          // parallel instead of every lane running the same serial stream); only the "already taken?" resolution is
+          // sequential, one shuffle + one vote per pick.
+          const uint32_t j_mine = deg - k + lane;                 // pick i ranges over [0, deg - k + i]
+          uint32_t t_mine = 0;
+          if (lane < k) {
+            uint32_t draw[4];
+            philox4x32_10(static_cast<uint32_t>(r), static_cast<uint32_t>(lane), static_cast<uint32_t>(offset),
+                          static_cast<uint32_t>(offset >> 32), seed, draw);
+            t_mine = __umulhi(draw[0], j_mine + 1);               // uniform in [0, j]
+          }
+          uint32_t mypos = 0xffffffffu;
+          for (int i = 0; i < k; ++i) {
+            const uint32_t t = __shfl_sync(0xffffffffu, t_mine, i);
+            const bool taken = __any_sync(0xffffffffu, mypos == t);
+            if (lane == i) mypos = taken ? j_mine : t;
+          }
+          if (lane < k) val = __ldg(col + beg + mypos);
+        }
       }
-      if (lane < k) val = __ldg(col + beg + mypos);
+      bool valid = val != kNone;
+      if (self_mode != GS_SELF_KEEP && val == me) valid = false;
+      if (self_mode == GS_SELF_ONCE && lane == k) { val = me; valid = true; }     // k <= 31 in this mode
+      // The reference's rows are sets (src/dataCenter.py:33).  A CSR row that repeats an id (graphs generated on the
+      // device) must behave the same way: a repeated id keeps only its lowest lane -- otherwise two lanes would share
+      // a rank and leave a slot unwritten.  Invalid lanes get keys of their own, so they match nobody.
+      const uint32_t same = __match_any_sync(0xffffffffu, valid ? static_cast<uint32_t>(val) : (0x80000000u | lane));
+      valid = valid && (same & ((1u << lane) - 1u)) == 0u;
+      const int32_t key = valid ? val : kNone;
+      int rank = 0;
+      const int scan = k + (self_mode == GS_SELF_ONCE ? 1 : 0);
+      for (int o = 0; o < scan; ++o) rank += (__shfl_sync(0xffffffffu, key, o) < key) ? 1 : 0;
+      const int m = __popc(__ballot_sync(0xffffffffu, valid));
+      if (valid) {
+        dst[rank] = val;
+        if (ex.mark != nullptr) atomicOr(ex.mark + (val >> 5), 1u << (val & 31));
+      }
+      for (int j = m + lane; j < stride; j += 32) dst[j] = -1;
+      if (lane == 0) out_cnt[r] = m;
     }
   }
-  bool valid = val != kNone;
-  if (self_mode != GS_SELF_KEEP && val == me) valid = false;
-  if (self_mode == GS_SELF_ONCE && lane == 31) { val = me; valid = true; }     // k <= 31 in this mode
-  const int scan = (self_mode == GS_SELF_ONCE) ? 32 : k;
-  // The reference's rows are sets (src/dataCenter.py:33).  A CSR row that repeats an id (graphs
-  // generated on the device) must behave the same way: the draw is a set, so a repeated id keeps
-  // only its first lane -- otherwise two lanes would share a rank and leave a slot unwritten.
-  {
-    bool dup = false;
-    for (int o = 0; o < scan; ++o) {
-      const int32_t v = __shfl_sync(0xffffffffu, val, o);
-      const bool ok = __shfl_sync(0xffffffffu, static_cast<int>(valid), o) != 0;
-      dup |= ok && o < lane && v == val;
+  if (ex.queue != nullptr) {                      // the last CTA to get here advances the queue cursor
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const long long next = ex.queue[2];
+      __threadfence();
+      const unsigned long long done = atomicAdd(reinterpret_cast<unsigned long long*>(ex.queue + 3), 1ULL);
+      if (done == gridDim.x - 1) {
+        ex.queue[2] = next + 1;
+        ex.queue[3] = 0;
+      }
     }
-    valid = valid && !dup;
   }
-  int rank = 0;
-  for (int o = 0; o < scan; ++o) {
-    const int32_t v = __shfl_sync(0xffffffffu, val, o);
-    const bool ok = __shfl_sync(0xffffffffu, static_cast<int>(valid), o) != 0;
-    rank += (ok && v < val) ? 1 : 0;
-  }
-  const int m = __popc(__ballot_sync(0xffffffffu, valid));
-  if (valid) dst[rank] = val;
-  for (int j = m + lane; j < stride; j += 32) dst[j] = -1;
-  if (lane == 0) out_cnt[r] = m;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -278,20 +313,35 @@ extern "C" int gs_fetch_batch(int64_t* queue_desc, int32_t b_sz, int32_t* dst, g
   return finish_launch();
 }
 
-extern "C" int gs_sample_neighbors(const int64_t* rowptr, const int32_t* col, int64_t num_nodes,
-                                   const int32_t* nodes, const int32_t* num_rows_dev, int32_t max_rows,
-                                   int32_t k, int32_t stride, int32_t self_mode, uint64_t seed, uint64_t offset,
-                                   const int64_t* offset_dev, int32_t* out_nbr, int32_t* out_cnt, gs_stream_t stream) {
-  if (!rowptr || !col || !nodes || !out_nbr || !out_cnt) return GS_ERR_BAD_ARG;
+extern "C" int gs_sample_neighbors_ex(const int64_t* rowptr, const int32_t* col, int64_t num_nodes,
+                                      const int32_t* nodes, const int32_t* num_rows_dev, int32_t max_rows,
+                                      int32_t k, int32_t stride, int32_t self_mode, uint64_t seed, uint64_t offset,
+                                      const int64_t* offset_dev, int32_t* out_nbr, int32_t* out_cnt,
+                                      int64_t* queue_desc, int32_t* fetch_dst, uint32_t* mark_bitmap,
+                                      uint32_t* clear_bitmap, gs_stream_t stream) {
+  if (!rowptr || !col || !out_nbr || !out_cnt) return GS_ERR_BAD_ARG;
+  if (!nodes && !queue_desc) return GS_ERR_BAD_ARG;
+  if (queue_desc && num_rows_dev) return GS_ERR_BAD_ARG;          // a queued batch has exactly max_rows seeds
+  if (mark_bitmap && clear_bitmap) return GS_ERR_BAD_ARG;         // marking and clearing words in one grid would race
   if (k < 1 || k > GS_MAX_FANOUT || max_rows < 0) return GS_ERR_BAD_ARG;
   if (self_mode == GS_SELF_ONCE && k > GS_MAX_FANOUT - 1) return GS_ERR_UNSUPPORTED;
   if (stride < k + (self_mode == GS_SELF_ONCE ? 1 : 0)) return GS_ERR_BAD_ARG;
   if (self_mode < GS_SELF_KEEP || self_mode > GS_SELF_ONCE) return GS_ERR_BAD_ARG;
   if (max_rows == 0) return GS_OK;
-  launch(sample_neighbors_kernel, (max_rows + kSampleWarps - 1) / kSampleWarps, kSampleWarps * 32, 0, as_stream(stream), 
-      rowptr, col, num_nodes, nodes, num_rows_dev, max_rows, k, stride, self_mode, seed, offset, offset_dev, out_nbr,
-      out_cnt);
+  SampleExtras ex{reinterpret_cast<long long*>(queue_desc), fetch_dst, mark_bitmap, clear_bitmap};
+  launch(sample_neighbors_kernel, (max_rows + kSampleWarps - 1) / kSampleWarps, kSampleWarps * 32, 0, as_stream(stream),
+         rowptr, col, num_nodes, nodes, num_rows_dev, max_rows, k, stride, self_mode, seed, offset, offset_dev, out_nbr,
+         out_cnt, ex);
   return finish_launch();
+}
+
+extern "C" int gs_sample_neighbors(const int64_t* rowptr, const int32_t* col, int64_t num_nodes,
+                                   const int32_t* nodes, const int32_t* num_rows_dev, int32_t max_rows,
+                                   int32_t k, int32_t stride, int32_t self_mode, uint64_t seed, uint64_t offset,
+                                   const int64_t* offset_dev, int32_t* out_nbr, int32_t* out_cnt, gs_stream_t stream) {
+  if (!nodes) return GS_ERR_BAD_ARG;
+  return gs_sample_neighbors_ex(rowptr, col, num_nodes, nodes, num_rows_dev, max_rows, k, stride, self_mode, seed, offset,
+                                offset_dev, out_nbr, out_cnt, nullptr, nullptr, nullptr, nullptr, stream);
 }
 
 extern "C" int gs_random_walk_pos(const int64_t* rowptr, const int32_t* col, int64_t num_nodes,

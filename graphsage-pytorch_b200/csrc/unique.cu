@@ -370,10 +370,14 @@ bitmap_mark_kernel(const int32_t* __restrict__ nodes, const int32_t* __restrict_
   }
 }
 
+// per-word exclusive popcount prefix inside 4096-word blocks + the block sums; the LAST block to finish turns the
+// block sums into exclusive prefixes and writes the number of set bits (= |unique|) -- no separate scan launch
 __global__ void __launch_bounds__(1024)
-bitmap_scan_kernel(const uint32_t* __restrict__ bitmap, int32_t* __restrict__ wprefix, uint32_t* __restrict__ block_sum) {
+bitmap_scan_kernel(const uint32_t* __restrict__ bitmap, int32_t* __restrict__ wprefix, uint32_t* __restrict__ block_sum,
+                   int nblk, unsigned int* __restrict__ ticket, int32_t* __restrict__ num_uniq) {
   pdl_sync();
   __shared__ int s_warp[32];
+  __shared__ bool s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t w0 = static_cast<int64_t>(blockIdx.x) * kBmBlockWords + 4 * tid;
   const uint4 b = *reinterpret_cast<const uint4*>(bitmap + w0);
@@ -400,6 +404,32 @@ bitmap_scan_kernel(const uint32_t* __restrict__ bitmap, int32_t* __restrict__ wp
   __syncthreads();
   const int base = s_warp[warp] + incl - mine;
   *reinterpret_cast<int4*>(wprefix + w0) = make_int4(base, base + c0, base + c0 + c1, base + c0 + c1 + c2);
+  // ---- last block: exclusive scan of the block sums (nblk <= 2048), in chunks of 32 by one warp ----
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    s_last = atomicAdd(ticket, 1u) == static_cast<unsigned int>(nblk) - 1u;
+  }
+  __syncthreads();
+  if (!s_last || warp != 0) return;
+  __threadfence();
+  unsigned int carry = 0;
+  for (int b0 = 0; b0 < nblk; b0 += 32) {
+    const int i = b0 + lane;
+    const unsigned int v = i < nblk ? *reinterpret_cast<volatile const uint32_t*>(block_sum + i) : 0u;
+    unsigned int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (i < nblk) block_sum[i] = carry + inc - v;
+    carry += __shfl_sync(0xffffffffu, inc, 31);
+  }
+  if (lane == 0) {
+    *num_uniq = static_cast<int32_t>(carry);
+    *ticket = 0u;
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -457,7 +487,7 @@ bitmap_emit_remap_kernel(const int32_t* __restrict__ nodes, const int32_t* __res
 struct BitmapPlan {
   int64_t words, words_pad;
   int nblk;
-  size_t off_prefix, off_bsum, total;
+  size_t off_prefix, off_bsum, off_ticket, total;
 };
 
 static BitmapPlan make_bitmap_plan(int64_t num_nodes) {
@@ -469,6 +499,8 @@ static BitmapPlan make_bitmap_plan(int64_t num_nodes) {
   size_t off = static_cast<size_t>(p.words_pad) * 4;
   p.off_prefix = off; off += static_cast<size_t>(p.words_pad) * 4;
   p.off_bsum = off;   off += static_cast<size_t>(p.nblk + 1) * 4;
+  off = (off + 15) & ~static_cast<size_t>(15);
+  p.off_ticket = off; off += 16;
   p.total = (off + 15) & ~static_cast<size_t>(15);
   return p;
 }
@@ -575,14 +607,15 @@ extern "C" size_t gs_unique_bitmap_workspace_bytes(int64_t num_nodes) {
   return make_bitmap_plan(num_nodes).total;
 }
 
-extern "C" int gs_unique_remap_bitmap(const int32_t* nodes, const int32_t* num_rows_dev, int32_t max_rows,
-                                      const int32_t* nbr, int32_t stride, int64_t num_nodes,
-                                      int32_t* uniq, int32_t* num_uniq_dev, int32_t* nbr_idx, int32_t* self_idx,
-                                      void* workspace, size_t workspace_bytes, gs_stream_t stream) {
+extern "C" int gs_unique_remap_bitmap_ex(const int32_t* nodes, const int32_t* num_rows_dev, int32_t max_rows,
+                                         const int32_t* nbr, int32_t stride, int64_t num_nodes,
+                                         int32_t* uniq, int32_t* num_uniq_dev, int32_t* nbr_idx, int32_t* self_idx,
+                                         void* workspace, size_t workspace_bytes, int32_t flags, gs_stream_t stream) {
   if (!nodes || !uniq || !num_uniq_dev || max_rows < 0 || stride < 0 || num_nodes < 1) return GS_ERR_BAD_ARG;
   if (stride > 0 && !nbr) return GS_ERR_BAD_ARG;
   if (num_nodes > (1ll << 31)) return GS_ERR_UNSUPPORTED;
   const BitmapPlan p = make_bitmap_plan(num_nodes);
+  if (p.nblk > 2048) return GS_ERR_UNSUPPORTED;
   if (!workspace || workspace_bytes < p.total || !aligned16(workspace)) return GS_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
   if (max_rows == 0) {
@@ -593,17 +626,32 @@ extern "C" int gs_unique_remap_bitmap(const int32_t* nodes, const int32_t* num_r
   uint32_t* bitmap = reinterpret_cast<uint32_t*>(ws);
   int32_t* wprefix = reinterpret_cast<int32_t*>(ws + p.off_prefix);
   uint32_t* bsum = reinterpret_cast<uint32_t*>(ws + p.off_bsum);
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(ws + p.off_ticket);
   const int64_t m = static_cast<int64_t>(max_rows) * (stride + 1);
   const int id_blocks = static_cast<int>(std::min<int64_t>((m + 255) / 256, 148 * 8));
-  launch(bitmap_mark_kernel, id_blocks, 256, 0, st, nodes, num_rows_dev, max_rows, nbr, stride, num_nodes, bitmap, 0);
-  launch(bitmap_scan_kernel, p.nblk, 1024, 0, st, bitmap, wprefix, bsum);
-  launch(exclusive_scan_kernel, 1, 1024, 0, st, bsum, p.nblk, num_uniq_dev);
+  int launches = 2;
+  if (!(flags & GS_UNIQUE_MARKED)) {
+    launch(bitmap_mark_kernel, id_blocks, 256, 0, st, nodes, num_rows_dev, max_rows, nbr, stride, num_nodes, bitmap, 0);
+    ++launches;
+  }
+  launch(bitmap_scan_kernel, p.nblk, 1024, 0, st, bitmap, wprefix, bsum, p.nblk, ticket, num_uniq_dev);
   const int emit_blocks = static_cast<int>((p.words + 255) / 256);
   const int64_t slots = static_cast<int64_t>(max_rows) * (stride > 0 ? stride : 1);
   const int remap_blocks = static_cast<int>(std::min<int64_t>((slots + 255) / 256, 148 * 8));
   launch(bitmap_emit_remap_kernel, emit_blocks + remap_blocks, 256, 0, st, nodes, num_rows_dev, max_rows, nbr, stride,
                                                                       num_nodes, p.words, emit_blocks, bitmap, wprefix,
                                                                       bsum, uniq, nbr_idx, self_idx);
-  launch(bitmap_mark_kernel, id_blocks, 256, 0, st, nodes, num_rows_dev, max_rows, nbr, stride, num_nodes, bitmap, 1);
-  return finish_launch(5);
+  if (!(flags & GS_UNIQUE_LEAVE_MARKS)) {
+    launch(bitmap_mark_kernel, id_blocks, 256, 0, st, nodes, num_rows_dev, max_rows, nbr, stride, num_nodes, bitmap, 1);
+    ++launches;
+  }
+  return finish_launch(launches);
+}
+
+extern "C" int gs_unique_remap_bitmap(const int32_t* nodes, const int32_t* num_rows_dev, int32_t max_rows,
+                                      const int32_t* nbr, int32_t stride, int64_t num_nodes,
+                                      int32_t* uniq, int32_t* num_uniq_dev, int32_t* nbr_idx, int32_t* self_idx,
+                                      void* workspace, size_t workspace_bytes, gs_stream_t stream) {
+  return gs_unique_remap_bitmap_ex(nodes, num_rows_dev, max_rows, nbr, stride, num_nodes, uniq, num_uniq_dev, nbr_idx,
+                                   self_idx, workspace, workspace_bytes, 0, stream);
 }

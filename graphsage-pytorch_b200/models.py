@@ -182,7 +182,20 @@ class SageLayer(nn.Module):
 class _Frontier:
     """Per-layer device state of one forward pass (rows = destination nodes of that layer)."""
     __slots__ = ("nodes", "num_rows", "rows_max", "stride", "nbr", "cnt", "nbr_idx", "self_idx", "agg", "argmax", "h",
-                 "table_in", "dim_in")
+                 "table_in", "dim_in", "dz", "gh")
+    # dz: d(pre-activation) of this layer (A operand of its weight-gradient GEMM), gh: gradient w.r.t. its output h;
+    # both only exist on the fused-top path of the trainers.  Buffers survive from one forward to the next when the
+    # frontiers are reused (`_run_prep(reuse=...)`): static addresses for captured steps.
+
+    def __init__(self):
+        for name in self.__slots__:
+            setattr(self, name, None)
+
+    def inherit(self, old: "_Frontier", first_layer: bool):
+        """Take over the weight-dependent buffers of the frontier this one replaces (same static shapes)."""
+        self.h, self.dz, self.gh = old.h, old.dz, old.gh
+        if not first_layer:
+            self.agg, self.argmax = old.agg, old.argmax
 
 
 class _GraphSageFn(torch.autograd.Function):
@@ -317,13 +330,20 @@ class GraphSage(nn.Module):
         return self._run_compute(self._run_prep(nodes_dev, injected, offset_dev), weights)
 
     def _run_prep(self, nodes_dev: torch.Tensor, injected=None, offset_dev: Optional[torch.Tensor] = None,
-                  reuse: Optional[List[_Frontier]] = None, num_rows: Optional[torch.Tensor] = None) -> List[_Frontier]:
+                  reuse: Optional[List[_Frontier]] = None, num_rows: Optional[torch.Tensor] = None,
+                  queue_desc: Optional[torch.Tensor] = None) -> List[_Frontier]:
         """The weight-independent half of a forward pass: sampling + unique/remap of every layer
         (src/models.py:249-251) and the layer-1 aggregation of the raw features (:260, index 1).
         `reuse`: the frontiers of an earlier call whose buffers are overwritten in place (static
-        addresses: the pipelined trainer prepares step n+1 in a graph branch beside step n)."""
+        addresses: the pipelined trainer prepares step n+1 in a graph branch beside step n).
+        `queue_desc`: the batch is the next row of a device-side queue (ops.fetch_batch's descriptor); the top
+        sampler launch fetches it itself and writes it into `nodes_dev`.
+        With the bitmap unique, its mark / clear passes run inside the sampler launches either side of it, so a
+        2-layer preparation is 5 launches: sample(+fetch, +mark), scan, emit/remap, sample(+clear), aggregate."""
         if num_rows is not None and injected is not None:
             raise ValueError("injected samples describe a batch of known size")
+        if queue_desc is not None and (injected is not None or num_rows is not None):
+            raise ValueError("a queued batch is sampled natively and has a static size")
         csr, table, dev = self._state()
         L, k = self.num_layers, self.num_sample
         self_mode = native.SELF_ONCE if self.gcn else native.SELF_DROP
@@ -337,6 +357,8 @@ class GraphSage(nn.Module):
         for l in range(L, 0, -1):
             old = reuse[l - 1] if reuse is not None else None
             fr = _Frontier()
+            if old is not None:
+                fr.inherit(old, first_layer=(l == 1))
             fr.nodes, fr.num_rows, fr.rows_max = nodes, num_rows, rows_max
             if injected is not None:
                 live = rows_max if num_rows is None else int(num_rows.item())
@@ -350,15 +372,25 @@ class GraphSage(nn.Module):
             else:
                 fr.stride = self._list_stride()
                 offset = (self._calls << 8) | l
+                fuse = self._bitmap_ws is not None
+                marks = fuse and l > 1                      # feeds a bitmap unique: mark while sampling
+                clears = fuse and l == 1 and L > 1          # follows one and marks nothing itself: clear its words
                 fr.nbr, fr.cnt = ops.sample_neighbors(csr.rowptr, csr.col, csr.num_nodes, nodes, num_rows, rows_max, k,
                                                       fr.stride, self_mode, self.seed, offset, offset_dev=offset_dev,
-                                                      out_nbr=old.nbr if old else None, out_cnt=old.cnt if old else None)
+                                                      out_nbr=old.nbr if old else None, out_cnt=old.cnt if old else None,
+                                                      queue_desc=queue_desc if l == L else None,
+                                                      fetch_dst=nodes if (l == L and queue_desc is not None) else None,
+                                                      mark_bitmap=self._bitmap_ws if marks else None,
+                                                      clear_bitmap=self._bitmap_ws if clears else None)
             if l > 1:   # unique + remap (src/models.py:286-288); the next frontier is U, ascending
                 prev = reuse[l - 2] if reuse is not None else None
                 outs = dict(uniq=prev.nodes, num_uniq=prev.num_rows, nbr_idx=old.nbr_idx, self_idx=old.self_idx) if old else {}
                 if self._bitmap_ws is not None:
+                    flags = 0
+                    if injected is None:
+                        flags = native.UNIQUE_MARKED | (native.UNIQUE_LEAVE_MARKS if l - 1 == 1 else 0)
                     uniq, num_uniq, fr.nbr_idx, fr.self_idx = ops.unique_remap_bitmap(
-                        nodes, num_rows, rows_max, fr.nbr, fr.stride, csr.num_nodes, self._bitmap_ws, **outs)
+                        nodes, num_rows, rows_max, fr.nbr, fr.stride, csr.num_nodes, self._bitmap_ws, flags=flags, **outs)
                 else:
                     uniq, num_uniq, fr.nbr_idx, fr.self_idx = ops.unique_remap(nodes, num_rows, rows_max, fr.nbr,
                                                                                fr.stride, csr.id_bits, **outs)
@@ -384,10 +416,14 @@ class GraphSage(nn.Module):
                                             argmax=old.argmax if old else None)
         return layers[1:]
 
-    def _run_compute(self, layers: List[_Frontier], weights: Sequence[torch.Tensor]) -> List[_Frontier]:
+    def _run_compute(self, layers: List[_Frontier], weights: Sequence[torch.Tensor], upto: Optional[int] = None,
+                     zero_grad_of_last: Optional[torch.Tensor] = None) -> List[_Frontier]:
         """The weight-dependent half (src/models.py:255-267): SageLayer GEMM of every layer and the
-        aggregations above layer 1."""
-        L = self.num_layers
+        aggregations above layer 1.  `upto` (default: all layers): stop after that many layers -- a trainer that
+        runs the top layer fused with the loss (ops.sage_top_sup) computes the layers below it here.
+        `zero_grad_of_last`: buffer shaped like the last computed layer's output, zero-filled by that layer's
+        GEMM epilogue (the backward scatter of the layer above accumulates into it)."""
+        L = self.num_layers if upto is None else int(upto)
         mode = native.AGG_MEAN if self.agg_func == 'MEAN' else native.AGG_MAX
         prec = _PRECISIONS[self.precision]
         for l in range(1, L + 1):
@@ -396,9 +432,10 @@ class GraphSage(nn.Module):
                 prev = layers[l - 2]
                 fr.table_in, fr.dim_in = prev.h, self.out_size
                 fr.agg, fr.argmax = ops.agg_fwd(prev.h, self.out_size, fr.nbr_idx, fr.stride, fr.cnt, fr.num_rows,
-                                                fr.rows_max, mode)
+                                                fr.rows_max, mode, out=fr.agg, argmax=fr.argmax)
             fr.h = ops.sage_gemm_fwd(None if self.gcn else fr.table_in, fr.self_idx, fr.agg, fr.dim_in, weights[l - 1],
-                                     self.out_size, self.gcn, fr.num_rows, fr.rows_max, True, prec)
+                                     self.out_size, self.gcn, fr.num_rows, fr.rows_max, True, prec, out=fr.h,
+                                     zero_out=zero_grad_of_last if l == L else None)
         return layers
 
     def _run_backward(self, layers: List[_Frontier], grad_out: torch.Tensor, weights, needs,
@@ -414,7 +451,7 @@ class GraphSage(nn.Module):
         dX -> scatter chain instead of in front of it (a fork/join when captured into a CUDA graph).
         `scatter_bufs[i]` (optional): ZEROED [layers[i].rows_max x pad4(H)] buffer that receives the gradient
         w.r.t. layer i+1's output (see `zeroed_scatter_bufs`); without it the fill runs in line."""
-        L, H = self.num_layers, self.out_size
+        L, H = len(layers), self.out_size          # a trainer that ran the top layer fused passes the layers below it
         mode = native.AGG_MEAN if self.agg_func == 'MEAN' else native.AGG_MAX
         prec = _PRECISIONS[self.precision]
         # tensor-core path: dZ = grad * (h > 0) is formed once, in place, and the GEMMs run with

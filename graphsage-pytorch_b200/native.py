@@ -20,7 +20,8 @@ AGG_MEAN, AGG_MAX = 0, 1
 SELF_KEEP, SELF_DROP, SELF_ONCE = 0, 1, 2
 PREC_FP32, PREC_TF32, PREC_TF32X3 = 0, 1, 2
 MAX_FANOUT = 32
-ABI_VERSION = 13
+UNIQUE_MARKED, UNIQUE_LEAVE_MARKS = 1, 2
+ABI_VERSION = 14
 
 _P, _I, _L, _F, _U64, _SZ = c_void_p, c_int32, c_int64, c_float, c_uint64, c_size_t
 
@@ -32,7 +33,9 @@ _SIGNATURES = {
     "gs_launch_count_reset": (None, []),
     "gs_set_pdl": (None, [_I]),
     "gs_sample_neighbors": (_I, [_P, _P, _L, _P, _P, _I, _I, _I, _I, _U64, _U64, _P, _P, _P, _P]),
+    "gs_sample_neighbors_ex": (_I, [_P, _P, _L, _P, _P, _I, _I, _I, _I, _U64, _U64, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gs_fetch_batch": (_I, [_P, _I, _P, _P]),
+    "gs_unique_remap_bitmap_ex": (_I, [_P, _P, _I, _P, _I, _L, _P, _P, _P, _P, _P, _SZ, _I, _P]),
     "gs_unique_workspace_bytes": (_SZ, [_I, _I]),
     "gs_unique_remap": (_I, [_P, _P, _I, _P, _I, _I, _P, _P, _P, _P, _P, _SZ, _P]),
     "gs_unique_bitmap_workspace_bytes": (_SZ, [_L]),
@@ -43,7 +46,12 @@ _SIGNATURES = {
     "gs_set_background": (None, [_I]),
     "gs_agg_bwd": (_I, [_P, _L, _P, _L, _I, _P, _I, _P, _P, _P, _L, _P, _I, _I, _P, _L, _P, _L, _P]),
     "gs_sage_gemm_fwd": (_I, [_P, _L, _P, _P, _L, _I, _P, _L, _I, _I, _P, _I, _P, _L, _I, _I, _P]),
+    "gs_sage_gemm_fwd_ex": (_I, [_P, _L, _P, _P, _L, _I, _P, _L, _I, _I, _P, _I, _P, _L, _I, _I, _P, _L, _P]),
+    "gs_sage_top_workspace_bytes": (_SZ, []),
+    "gs_sage_top_sup": (_I, [_P, _L, _P, _I, _P, _P, _P, _I, _P, _L, _I, _I, _I, _P, _P, _I, _P, _P, _P, _L, _P, _L, _P, _L,
+                             _P, _P, _P, _P, _P, _L, _P, _SZ, _I, _P]),
     "gs_sage_gemm_bwd_w": (_I, [_P, _L, _P, _P, _L, _I, _P, _L, _P, _L, _I, _I, _I, _P, _I, _P, _L, _I, _P]),
+    "gs_sage_gemm_bwd_w_pair": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _I, _P]),
     "gs_sage_gemm_bwd_x": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _P, _I, _P, _L, _P, _L, _I, _P]),
     "gs_relu_bwd_inplace": (_I, [_P, _L, _P, _L, _I, _P, _I, _P]),
     "gs_cls_fwd": (_I, [_P, _L, _I, _I, _P, _P, _I, _P, _I, _P]),
@@ -82,6 +90,9 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     if _lib is not None:
         return _lib
     path = lib_path()
+    override = os.environ.get("GSAGE_LIB")             # diagnostics: a trace / probe build of the same sources
+    if override:
+        path, build_if_missing = override, False
     if build_if_missing and not _build.is_current():
         try:
             _build.build()

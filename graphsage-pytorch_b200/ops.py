@@ -27,17 +27,24 @@ def _lib():
 # K1
 # ----------------------------------------------------------------------------------------------
 def sample_neighbors(rowptr, col, num_nodes: int, nodes, num_rows, max_rows: int, k: int, stride: int,
-                     self_mode: int, seed: int, offset: int, out_nbr=None, out_cnt=None, offset_dev=None):
-    """src/models.py:279-285 on the device CSR -> (nbr [max_rows, stride] int32, cnt [max_rows] int32)."""
-    native.require_cuda(nodes, "nodes")
-    dev = nodes.device
+                     self_mode: int, seed: int, offset: int, out_nbr=None, out_cnt=None, offset_dev=None, *,
+                     queue_desc=None, fetch_dst=None, mark_bitmap=None, clear_bitmap=None):
+    """src/models.py:279-285 on the device CSR -> (nbr [max_rows, stride] int32, cnt [max_rows] int32).
+    Keyword extras fold neighbouring launches of a preparation chain into this one (gs_sample_neighbors_ex):
+    `queue_desc` + `fetch_dst` = fetch_batch, `mark_bitmap` / `clear_bitmap` = the mark / clear passes of the bitmap
+    unique that follows / preceded."""
+    dev = (nodes if nodes is not None else fetch_dst).device
+    if dev.type != 'cuda':
+        native.require_cuda(nodes if nodes is not None else fetch_dst, "nodes")
     if out_nbr is None:
         out_nbr = torch.empty((max_rows, stride), dtype=I32, device=dev)
     if out_cnt is None:
         out_cnt = torch.empty((max_rows,), dtype=I32, device=dev)
-    check(_lib().gs_sample_neighbors(ptr(rowptr), ptr(col), num_nodes, ptr(nodes), ptr(num_rows), max_rows, k, stride,
-                                     self_mode, seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF,
-                                     ptr(offset_dev), ptr(out_nbr), ptr(out_cnt), stream()), "gs_sample_neighbors")
+    check(_lib().gs_sample_neighbors_ex(ptr(rowptr), ptr(col), num_nodes, ptr(nodes) if queue_desc is None else None,
+                                        ptr(num_rows), max_rows, k, stride, self_mode, seed & 0xFFFFFFFFFFFFFFFF,
+                                        offset & 0xFFFFFFFFFFFFFFFF, ptr(offset_dev), ptr(out_nbr), ptr(out_cnt),
+                                        ptr(queue_desc), ptr(fetch_dst), ptr(mark_bitmap), ptr(clear_bitmap), stream()),
+          "gs_sample_neighbors")
     return out_nbr, out_cnt
 
 
@@ -85,8 +92,9 @@ def unique_bitmap_workspace(num_nodes: int, device) -> torch.Tensor:
 
 
 def unique_remap_bitmap(nodes, num_rows, max_rows: int, nbr, stride: int, num_nodes: int, workspace, *, uniq=None,
-                        num_uniq=None, nbr_idx=None, self_idx=None, want_nbr_idx=True, want_self_idx=True):
-    """Same contract and outputs as unique_remap, via the bitmap/rank path (gs_unique_remap_bitmap)."""
+                        num_uniq=None, nbr_idx=None, self_idx=None, want_nbr_idx=True, want_self_idx=True, flags: int = 0):
+    """Same contract and outputs as unique_remap, via the bitmap/rank path (gs_unique_remap_bitmap_ex).  `flags`:
+    native.UNIQUE_MARKED / UNIQUE_LEAVE_MARKS when the neighbouring sampler launches do the mark / clear passes."""
     native.require_cuda(nodes, "nodes")
     dev = nodes.device
     cap = min(max_rows * (stride + 1), max(num_nodes, 1))
@@ -98,9 +106,9 @@ def unique_remap_bitmap(nodes, num_rows, max_rows: int, nbr, stride: int, num_no
         nbr_idx = torch.empty((max_rows, stride), dtype=I32, device=dev)
     if self_idx is None and want_self_idx:
         self_idx = torch.empty((max_rows,), dtype=I32, device=dev)
-    check(_lib().gs_unique_remap_bitmap(ptr(nodes), ptr(num_rows), max_rows, ptr(nbr), stride, num_nodes, ptr(uniq),
-                                        ptr(num_uniq), ptr(nbr_idx), ptr(self_idx), ptr(workspace), workspace.numel(),
-                                        stream()), "gs_unique_remap_bitmap")
+    check(_lib().gs_unique_remap_bitmap_ex(ptr(nodes), ptr(num_rows), max_rows, ptr(nbr), stride, num_nodes, ptr(uniq),
+                                           ptr(num_uniq), ptr(nbr_idx), ptr(self_idx), ptr(workspace), workspace.numel(),
+                                           int(flags), stream()), "gs_unique_remap_bitmap")
     return uniq, num_uniq, nbr_idx, self_idx
 
 
@@ -160,18 +168,57 @@ def agg_bwd(grad_agg, grad_self, dim: int, nbr, stride: int, cnt, self_idx, argm
 # K4
 # ----------------------------------------------------------------------------------------------
 def sage_gemm_fwd(self_table, self_idx, agg, dim: int, weight, out_dim: int, gcn: bool, num_rows, max_rows: int,
-                  relu: bool = True, precision: int = native.PREC_FP32, out=None):
-    """src/models.py:215-219 -> out [max_rows, pad4(out_dim)]."""
+                  relu: bool = True, precision: int = native.PREC_FP32, out=None, zero_out=None):
+    """src/models.py:215-219 -> out [max_rows, pad4(out_dim)].  `zero_out` (optional, same shape as out) is
+    zero-filled on the way: the buffer the backward of the layer above scatters d(out) into."""
     native.require_cuda(agg, "agg")
     if out is None:
         ld = pad4(out_dim)
         alloc = torch.empty if ld == out_dim else torch.zeros
         out = alloc((max_rows, ld), dtype=F32, device=agg.device)
-    check(_lib().gs_sage_gemm_fwd(ptr(self_table), self_table.stride(0) if self_table is not None else 0, ptr(self_idx),
-                                  ptr(agg), agg.stride(0), dim, ptr(weight), weight.stride(0), out_dim, int(gcn),
-                                  ptr(num_rows), max_rows, ptr(out), out.stride(0), int(relu), precision, stream()),
+    check(_lib().gs_sage_gemm_fwd_ex(ptr(self_table), self_table.stride(0) if self_table is not None else 0, ptr(self_idx),
+                                     ptr(agg), agg.stride(0), dim, ptr(weight), weight.stride(0), out_dim, int(gcn),
+                                     ptr(num_rows), max_rows, ptr(out), out.stride(0), int(relu), precision,
+                                     ptr(zero_out), zero_out.stride(0) if zero_out is not None else 0, stream()),
           "gs_sage_gemm_fwd")
     return out
+
+
+TOP_H, TOP_MAX_CLASSES, TOP_MAX_STRIDE = 128, 64, 16
+
+
+def sage_top_supported(dim: int, out_dim: int, num_classes: int, stride: int, precision: int, mean: bool) -> bool:
+    """Whether gs_sage_top_sup covers this top layer (otherwise it runs as separate kernels)."""
+    return (mean and dim == TOP_H and out_dim == TOP_H and 1 <= num_classes <= TOP_MAX_CLASSES
+            and 1 <= stride <= TOP_MAX_STRIDE and precision in (native.PREC_TF32, native.PREC_TF32X3))
+
+
+def sage_top_workspace(device) -> torch.Tensor:
+    return torch.zeros((int(_lib().gs_sage_top_workspace_bytes()),), dtype=torch.uint8, device=device)
+
+
+def sage_top_sup(table, nbr_idx, stride: int, cnt, self_idx, num_rows, max_rows: int, weight, gcn: bool, cls_w, cls_b,
+                 labels, label_index, loss, grad_cls_w, grad_cls_b, grad_table, workspace, precision: int, *,
+                 out_h=None, out_agg=None, out_dz=None, logp=None):
+    """The top SageLayer + classifier + NLL, forward and backward, in one launch (gs_sage_top_sup).
+    Returns (h, agg, dz): the layer's output, and the B / A operands of its weight-gradient GEMM."""
+    native.require_cuda(table, "table")
+    dev = table.device
+    H = TOP_H
+    if out_h is None:
+        out_h = torch.empty((max_rows, H), dtype=F32, device=dev)
+    if out_agg is None:
+        out_agg = torch.empty((max_rows, H), dtype=F32, device=dev)
+    if out_dz is None:
+        out_dz = torch.empty((max_rows, H), dtype=F32, device=dev)
+    classes = int(cls_w.shape[0])
+    check(_lib().gs_sage_top_sup(ptr(table), table.stride(0), ptr(nbr_idx), stride, ptr(cnt), ptr(self_idx), ptr(num_rows),
+                                 max_rows, ptr(weight), weight.stride(0), H, H, int(gcn), ptr(cls_w), ptr(cls_b), classes,
+                                 ptr(labels), ptr(label_index), ptr(out_h), out_h.stride(0), ptr(out_agg), out_agg.stride(0),
+                                 ptr(out_dz), out_dz.stride(0), ptr(logp), ptr(loss), ptr(grad_cls_w), ptr(grad_cls_b),
+                                 ptr(grad_table), grad_table.stride(0) if grad_table is not None else 0, ptr(workspace),
+                                 workspace.numel(), precision, stream()), "gs_sage_top_sup")
+    return out_h, out_agg, out_dz
 
 
 def sage_gemm_bwd_w(self_table, self_idx, agg, dim: int, grad_out, out, out_dim: int, gcn: bool, relu: bool, num_rows,
@@ -182,6 +229,22 @@ def sage_gemm_bwd_w(self_table, self_idx, agg, dim: int, grad_out, out, out_dim:
                                     ptr(num_rows), max_rows, ptr(grad_w), grad_w.stride(0), precision, stream()),
           "gs_sage_gemm_bwd_w")
     return grad_w
+
+
+def sage_gemm_bwd_w_pair(problems, gcn: bool, relu: bool, precision: int):
+    """Two weight-gradient problems in one launch (gs_sage_gemm_bwd_w_pair).  `problems`: two tuples
+    (self_table, self_idx, agg, dim, grad_out, out, out_dim, num_rows, max_rows, grad_w), as for sage_gemm_bwd_w."""
+    import ctypes
+    assert len(problems) == 2
+    vp, i64, i32 = ctypes.c_void_p * 2, ctypes.c_int64 * 2, ctypes.c_int32 * 2
+    col = list(zip(*problems))
+    st, si, ag, dim, go, out, od, nr, mr, gw = col
+    ld = lambda ts: i64(*[int(t.stride(0)) if t is not None else 0 for t in ts])
+    check(_lib().gs_sage_gemm_bwd_w_pair(vp(*[ptr(t) for t in st]), ld(st), vp(*[ptr(t) for t in si]), vp(*[ptr(t) for t in ag]),
+                                         ld(ag), i32(*[int(d) for d in dim]), vp(*[ptr(t) for t in go]), ld(go),
+                                         vp(*[ptr(t) for t in out]), ld(out), i32(*[int(d) for d in od]), int(gcn), int(relu),
+                                         vp(*[ptr(t) for t in nr]), i32(*[int(m) for m in mr]), vp(*[ptr(t) for t in gw]),
+                                         ld(gw), precision, stream()), "gs_sage_gemm_bwd_w_pair")
 
 
 def sage_gemm_bwd_x(grad_out, out, weight, dim: int, out_dim: int, gcn: bool, relu: bool, num_rows, max_rows: int,

@@ -249,25 +249,82 @@ class SupervisedTrainer:
         self.launches_per_step = 0
         self.last_layers = None
         self._side = torch.cuda.Stream(device=dev)      # dW GEMMs run beside the dX/scatter chain
+        #: run the top layer + classifier + loss, forward and backward, as ONE launch (ops.sage_top_sup) when the
+        #: configuration allows it (MEAN, hidden 128, <= 64 classes, tensor-core precision); GS_FUSED_TOP=0: never
+        self.fused_top = os.environ.get("GS_FUSED_TOP", "1") != "0"
+        self._top_ws = ops.sage_top_workspace(dev)
 
-    # ---- the step, expressed once; runs eagerly or under capture -------------------------------
-    def _forward_backward(self):
-        m, c = self.model, self.classifier
+    # ---- the weight-dependent half of a step on prepared frontiers -------------------------------
+    def _fused_top_ok(self, layers) -> bool:
+        m = self.model
+        return (self.fused_top and m.num_layers >= 2 and
+                ops.sage_top_supported(m.out_size, m.out_size, int(self.cls_w.shape[0]), layers[-1].stride,
+                                       _PRECISIONS[m.precision], m.agg_func == 'MEAN'))
+
+    def _train_on(self, layers, seeds):
+        """forward of the layers -> classifier -> NLL -> backward into self.grads (src/utils.py:157-163,184) for the
+        batch `seeds` whose frontiers `layers` _run_prep has prepared.  Default path: the layers below the top one as
+        tcgen05 GEMMs, then ONE launch for the whole top layer (gather + mean, SageLayer, classifier, log-softmax,
+        NLL, their backward, dX and the scatter into the gradient of the layer below: ops.sage_top_sup), then the
+        weight-gradient GEMMs -- the top layer's on the side stream beside the chain of the layers below."""
+        m = self.model
         weights = [w.detach() for w in self.weights]
-        layers = m._run_prep(self.seeds, None, offset_dev=self.step_counter)
+        n_sage = len(self.weights)
+        if not self._fused_top_ok(layers):
+            return self._train_on_unfused(layers, seeds, weights)
+        L, H = m.num_layers, m.out_size
+        prec = _PRECISIONS[m.precision]
+        below, top = layers[L - 2], layers[L - 1]
+        if below.gh is None:         # gradient w.r.t. the output of the layer below; zero-filled by that layer's GEMM
+            below.gh = torch.empty((below.rows_max, H), dtype=torch.float32, device=self.dev)
+        g_below = below.gh
+        m._run_compute(layers, weights, upto=L - 1, zero_grad_of_last=g_below)
+        top.table_in, top.dim_in = below.h, H
+        top.h, top.agg, top.dz = ops.sage_top_sup(below.h, top.nbr_idx, top.stride, top.cnt, top.self_idx, top.num_rows,
+                                                  top.rows_max, weights[L - 1], m.gcn, self.cls_w.detach(),
+                                                  self.cls_b.detach(), self.labels, seeds, self.loss, self.grads[n_sage],
+                                                  self.grads[n_sage + 1], g_below, self._top_ws, prec, out_h=top.h,
+                                                  out_agg=top.agg, out_dz=top.dz)
+        top.argmax, dz = None, top.dz
+        self.last_layers = layers
+        if L == 2:
+            # both weight gradients are leaves now: ONE grid, CTAs split in proportion to the work (csrc/sage_gemm_tc.cu)
+            ops.sage_gemm_bwd_w_pair([
+                (None if m.gcn else below.table_in, below.self_idx, below.agg, below.dim_in, g_below, below.h, H,
+                 below.num_rows, below.rows_max, self.grads[0]),
+                (None if m.gcn else below.h, top.self_idx, top.agg, H, dz, top.h, H, top.num_rows, top.rows_max,
+                 self.grads[1])], m.gcn, False, prec)
+            return
+        main = torch.cuda.current_stream()
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):                 # dW of the top layer: a leaf, beside the chain below
+            ops.sage_gemm_bwd_w(None if m.gcn else below.h, top.self_idx, top.agg, H, dz, top.h, H, m.gcn, False,
+                                top.num_rows, top.rows_max, self.grads[L - 1], precision=prec)
+        for t in (dz, top.agg, top.h, below.h):
+            t.record_stream(self._side)
+        m._run_backward(layers[:L - 1], g_below, weights[:L - 1], [True] * (L - 1), grad_bufs=self.grads[:L - 1],
+                        own_grad=True, top_masked=True, side_stream=None)
+        main.wait_stream(self._side)
+
+    def _train_on_unfused(self, layers, seeds, weights):
+        m = self.model
+        n_sage = len(self.weights)
         scatter_bufs, zeroed = _zero_beside(self._side, self.loss, m, layers)
         layers = m._run_compute(layers, weights)
         self.last_layers = layers
         emb = layers[-1].h
-        classes = self.cls_w.shape[0]
         gemb = torch.empty_like(emb)
-        n_sage = len(self.weights)
         torch.cuda.current_stream().wait_event(zeroed)
-        ops.cls_nll_fwd_bwd(emb, m.out_size, self.cls_w.detach(), self.cls_b.detach(), classes, self.labels, self.seeds,
-                            self.loss, gemb, self.grads[n_sage], self.grads[n_sage + 1],
+        ops.cls_nll_fwd_bwd(emb, m.out_size, self.cls_w.detach(), self.cls_b.detach(), self.cls_w.shape[0], self.labels,
+                            seeds, self.loss, gemb, self.grads[n_sage], self.grads[n_sage + 1],
                             precision=_PRECISIONS[m.precision], mask_relu_input=True, zero_loss=False)   # utils.py:153,161-163
         m._run_backward(layers, gemb, weights, [True] * n_sage, grad_bufs=self.grads[:n_sage], own_grad=True,
                         top_masked=True, side_stream=self._side, scatter_bufs=scatter_bufs)
+
+    # ---- the step, expressed once; runs eagerly or under capture -------------------------------
+    def _forward_backward(self):
+        layers = self.model._run_prep(self.seeds, None, offset_dev=self.step_counter)
+        self._train_on(layers, self.seeds)
         if self.dp is None:
             self.step_counter.add_(1)        # the fused update kernel bumps it otherwise
 
@@ -385,7 +442,7 @@ class PipelinedTrainer(SupervisedTrainer):
         self.slot_seeds = [torch.zeros((self.b_sz,), dtype=torch.int32, device=dev) for _ in range(2)]
         self.slot_layers = [None, None]
         self.sample_counter = torch.zeros((1,), dtype=torch.int64, device=dev)
-        self.queue_desc = torch.zeros((3,), dtype=torch.int64, device=dev)        # {address, rows, next}
+        self.queue_desc = torch.zeros((4,), dtype=torch.int64, device=dev)        # {address, rows, next, ticket}
         self._queue = None
         self._ring = torch.zeros((self.RING, self.b_sz), dtype=torch.int32, device=dev)
         self._ring_pinned = torch.zeros((self.RING, self.b_sz), dtype=torch.int32).pin_memory()
@@ -412,7 +469,7 @@ class PipelinedTrainer(SupervisedTrainer):
                 or not batches_dev.is_contiguous():
             raise ValueError(f"batch queue must be a contiguous int32 [rows, {self.b_sz}] tensor")
         self._queue = batches_dev
-        desc = torch.tensor([batches_dev.data_ptr(), batches_dev.shape[0], 0], dtype=torch.int64)
+        desc = torch.tensor([batches_dev.data_ptr(), batches_dev.shape[0], 0, 0], dtype=torch.int64)
         self.queue_desc.copy_(desc.to(self.dev), non_blocking=False)
 
     def feed(self, nodes_batch):
@@ -476,7 +533,6 @@ class PipelinedTrainer(SupervisedTrainer):
 
     # ---- the two halves ---------------------------------------------------------------------------
     def _prep(self, slot: int):
-        ops.fetch_batch(self.queue_desc, self.b_sz, self.slot_seeds[slot])
         # Philox offset of a prep = (model call number << 8 | layer) + (sample_counter << 8).  The call number is
         # baked into a captured launch, so every prep -- whichever graph or slot it was captured for, or eager --
         # carries the SAME one and the device counter (+1 per prep) alone tells consecutive batches apart.
@@ -484,26 +540,14 @@ class PipelinedTrainer(SupervisedTrainer):
         if self._prep_call is None:
             self._prep_call = m._calls
         keep, m._calls = m._calls, self._prep_call
+        # the top sampler launch fetches the next queued batch into slot_seeds[slot] itself (gs_sample_neighbors_ex)
         self.slot_layers[slot] = m._run_prep(self.slot_seeds[slot], None, offset_dev=self.sample_counter,
-                                             reuse=self.slot_layers[slot])
+                                             reuse=self.slot_layers[slot], queue_desc=self.queue_desc)
         m._calls = max(keep, self._prep_call + 1)
         self.sample_counter.add_(1)
 
     def _compute(self, slot: int, update: bool = True):
-        m = self.model
-        weights = [w.detach() for w in self.weights]
-        scatter_bufs, zeroed = _zero_beside(self._side, self.loss, m, self.slot_layers[slot])
-        layers = m._run_compute(self.slot_layers[slot], weights)
-        self.last_layers = layers
-        emb = layers[-1].h
-        gemb = torch.empty_like(emb)
-        n_sage = len(self.weights)
-        torch.cuda.current_stream().wait_event(zeroed)
-        ops.cls_nll_fwd_bwd(emb, m.out_size, self.cls_w.detach(), self.cls_b.detach(), self.cls_w.shape[0], self.labels,
-                            self.slot_seeds[slot], self.loss, gemb, self.grads[n_sage], self.grads[n_sage + 1],
-                            precision=_PRECISIONS[m.precision], mask_relu_input=True, zero_loss=False)
-        m._run_backward(layers, gemb, weights, [True] * n_sage, grad_bufs=self.grads[:n_sage], own_grad=True,
-                        top_masked=True, side_stream=self._side, scatter_bufs=scatter_bufs)
+        self._train_on(self.slot_layers[slot], self.slot_seeds[slot])
         if update:
             self.dp.update(self.max_norm, self.lr, None)
 

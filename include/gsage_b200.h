@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 13
+#define GS_ABI_VERSION 14
 
 #define GS_OK 0
 #define GS_ERR_BAD_ARG (-1)
@@ -47,6 +47,9 @@ extern "C" {
 #define GS_PREC_TF32X3 2    /* tcgen05 kind::tf32, 3-term split (fp32-faithful)          */
 
 #define GS_MAX_FANOUT 32
+
+#define GS_UNIQUE_MARKED 1      /* gs_unique_remap_bitmap_ex: the ids are already marked (by gs_sample_neighbors_ex)   */
+#define GS_UNIQUE_LEAVE_MARKS 2 /* ... and the clear pass is left to the next gs_sample_neighbors_ex (clear_bitmap)    */
 
 typedef void* gs_stream_t; /* cudaStream_t */
 
@@ -81,9 +84,26 @@ int gs_sample_neighbors(const int64_t* rowptr, const int32_t* col, int64_t num_n
                         uint64_t seed, uint64_t offset, const int64_t* offset_dev,
                         int32_t* out_nbr, int32_t* out_cnt, gs_stream_t stream);
 
+/* The same with work of the neighbouring kernels of a preparation chain folded in (all four nullable):
+ *   queue_desc / fetch_dst  gs_fetch_batch fused: the rows are the next batch of the queue ({address, rows, next,
+ *                           ticket}: 4 int64, ticket zero), max_rows == b_sz, num_rows_dev and nodes NULL; row r's node is
+ *                           also written to fetch_dst[r] (the batch's id list, e.g. the label index of the loss)
+ *   mark_bitmap             the "mark" pass of the following gs_unique_remap_bitmap_ex (flag GS_UNIQUE_MARKED): every id
+ *                           of a live row (its node and the drawn neighbours) sets its bit
+ *   clear_bitmap            the "clear" pass of the PRECEDING gs_unique_remap_bitmap_ex (flag GS_UNIQUE_LEAVE_MARKS): the
+ *                           rows of this call are exactly the ids it emitted; each zeroes the word of its own node.
+ *                           Not together with mark_bitmap (they would race on a word). */
+int gs_sample_neighbors_ex(const int64_t* rowptr, const int32_t* col, int64_t num_nodes,
+                           const int32_t* nodes, const int32_t* num_rows_dev, int32_t max_rows,
+                           int32_t k, int32_t stride, int32_t self_mode,
+                           uint64_t seed, uint64_t offset, const int64_t* offset_dev,
+                           int32_t* out_nbr, int32_t* out_cnt,
+                           int64_t* queue_desc, int32_t* fetch_dst, uint32_t* mark_bitmap, uint32_t* clear_bitmap,
+                           gs_stream_t stream);
+
 /* Batch queue of the device-resident train loop (src/utils.py:141-145: every batch of an epoch
- * is a slice of one shuffled id array).  queue_desc is 3 DEVICE int64: {address of an int32
- * [rows x b_sz] array, rows, next}; copies row next % rows into dst and increments next -- a
+ * is a slice of one shuffled id array).  queue_desc is 4 DEVICE int64: {address of an int32
+ * [rows x b_sz] array, rows, next, ticket (zero; used by gs_sample_neighbors_ex)}; copies row next % rows into dst and increments next -- a
  * kernel of the step's graph, so back-to-back replays need no host-side copy between them. */
 int gs_fetch_batch(int64_t* queue_desc, int32_t b_sz, int32_t* dst, gs_stream_t stream);
 
@@ -111,6 +131,12 @@ int gs_unique_remap_bitmap(const int32_t* nodes, const int32_t* num_rows_dev, in
                            const int32_t* nbr, int32_t stride, int64_t num_nodes,
                            int32_t* uniq, int32_t* num_uniq_dev, int32_t* nbr_idx, int32_t* self_idx,
                            void* workspace, size_t workspace_bytes, gs_stream_t stream);
+/* flags: GS_UNIQUE_MARKED | GS_UNIQUE_LEAVE_MARKS -- the mark / clear passes run inside the neighbouring sampler
+ * launches (gs_sample_neighbors_ex); with both set the call is two launches (scan, emit + remap). */
+int gs_unique_remap_bitmap_ex(const int32_t* nodes, const int32_t* num_rows_dev, int32_t max_rows,
+                              const int32_t* nbr, int32_t stride, int64_t num_nodes,
+                              int32_t* uniq, int32_t* num_uniq_dev, int32_t* nbr_idx, int32_t* self_idx,
+                              void* workspace, size_t workspace_bytes, int32_t flags, gs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * K3  gather-segment-reduce.  Replaces GraphSage.aggregate, src/models.py:300-326 (the
@@ -170,6 +196,16 @@ int gs_sage_gemm_fwd(const float* self_table, int64_t ld_self, const int32_t* se
                      const int32_t* num_rows_dev, int32_t max_rows,
                      float* out, int64_t ld_out, int32_t relu, int32_t precision, gs_stream_t stream);
 
+/* The same with one more output: zero_out (nullable, [max_rows x ld_zero], same shape as out) is zero-filled for the
+ * live rows and columns.  It is the buffer the backward scatter of the layer above accumulates d(out) into
+ * (gs_agg_bwd / gs_sage_top_sup): the fill rides on the forward epilogue instead of being a launch of its own. */
+int gs_sage_gemm_fwd_ex(const float* self_table, int64_t ld_self, const int32_t* self_idx,
+                        const float* agg, int64_t ld_agg, int32_t dim,
+                        const float* weight, int64_t ldw, int32_t out_dim, int32_t gcn,
+                        const int32_t* num_rows_dev, int32_t max_rows,
+                        float* out, int64_t ld_out, int32_t relu, int32_t precision,
+                        float* zero_out, int64_t ld_zero, gs_stream_t stream);
+
 /* dW[h,k] += sum_r dZ[r,h] X[r,k],  dZ = grad_out * (out > 0) when relu.  grad_w must be
  * zeroed by the caller (partials are accumulated with atomics). */
 int gs_sage_gemm_bwd_w(const float* self_table, int64_t ld_self, const int32_t* self_idx,
@@ -178,6 +214,19 @@ int gs_sage_gemm_bwd_w(const float* self_table, int64_t ld_self, const int32_t* 
                        int32_t out_dim, int32_t gcn, int32_t relu,
                        const int32_t* num_rows_dev, int32_t max_rows,
                        float* grad_w, int64_t ldw, int32_t precision, gs_stream_t stream);
+
+/* Two such problems -- the weight gradients of two layers of one step, independent leaves of its dependency graph --
+ * in one call.  Every argument that differs per problem is a HOST array of 2 (device pointers / sizes of problem 0 and
+ * 1); gcn, relu and precision are common.  With a tensor-core precision both run as ONE grid whose CTAs are split in
+ * proportion to the work (rows x K x out_dim), so neither queues behind the other; otherwise one after the other. */
+int gs_sage_gemm_bwd_w_pair(const float* const* self_table_host, const int64_t* ld_self_host,
+                            const int32_t* const* self_idx_host, const float* const* agg_host,
+                            const int64_t* ld_agg_host, const int32_t* dim_host,
+                            const float* const* grad_out_host, const int64_t* ld_go_host,
+                            const float* const* out_host, const int64_t* ld_out_host,
+                            const int32_t* out_dim_host, int32_t gcn, int32_t relu,
+                            const int32_t* const* num_rows_dev_host, const int32_t* max_rows_host,
+                            float* const* grad_w_host, const int64_t* ldw_host, int32_t precision, gs_stream_t stream);
 
 /* dX[r,k] = sum_h dZ[r,h] W[h,k]  -> grad_self[r,:dim] (non-gcn) and grad_agg[r,:dim]. */
 int gs_sage_gemm_bwd_x(const float* grad_out, int64_t ld_go, const float* out, int64_t ld_out,
@@ -226,6 +275,32 @@ int gs_cls_nll_fwd_bwd(const float* emb, int64_t ld_emb, int32_t rows, int32_t d
                        float* logp, float* loss, float* grad_emb, int64_t ld_ge,
                        float* grad_w, float* grad_b, float* scratch, int32_t mask_relu_input, int32_t zero_loss,
                        const int32_t* num_rows_dev, int32_t precision, gs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * The TOP layer of a supervised step in ONE launch (csrc/sage_top.cu): for the batch rows r < rows
+ *   X[r]  = [ table[self_idx[r]] | mean_j table[nbr_idx[r][j]] ]   (gcn: the mean only)   src/models.py:260-266,300-314
+ *   h[r]  = relu(W . X[r])                                                                src/models.py:215-219
+ *   logp  = log_softmax(Wc . h + bc);  loss[0] = -mean_r logp[r, y_r]                     src/models.py:25-27, src/utils.py:162-163
+ * and the whole backward of it: grad_cls_w / grad_cls_b accumulate (zero them first); out_dz = d(pre-activation) of
+ * the layer; grad_table[t,:] += contributions of dX = dZ . W through the self gather and the mean, multiplied by
+ * (table[t,:] > 0) -- `table` is the ReLU output of the layer below, so grad_table (zeroed by the caller, e.g. by
+ * gs_sage_gemm_fwd_ex) receives that layer's d(pre-activation).  out_agg / out_dz are the B / A operands of this
+ * layer's gs_sage_gemm_bwd_w (relu = 0).  out_h, logp, grad_table, grad_cls_* are nullable.
+ * Supported: dim == out_dim == 128, MEAN, num_classes <= 64, stride <= 16, precision TF32X3 / TF32 (mma.sync
+ * m16n8k8 in the same 3-term split as K4); anything else returns GS_ERR_UNSUPPORTED and the caller runs the layer
+ * as gs_agg_fwd -> gs_sage_gemm_fwd -> gs_cls_nll_fwd_bwd -> gs_sage_gemm_bwd_x -> gs_agg_bwd.
+ * workspace: gs_sage_top_workspace_bytes() of device memory, zeroed ONCE by the caller (loss partials + a ticket
+ * that every launch leaves at zero again); loss[0] is overwritten, nothing needs zeroing per step.
+ * ------------------------------------------------------------------------------------ */
+size_t gs_sage_top_workspace_bytes(void);
+int gs_sage_top_sup(const float* table, int64_t ld_table, const int32_t* nbr_idx, int32_t stride,
+                    const int32_t* cnt, const int32_t* self_idx, const int32_t* num_rows_dev, int32_t max_rows,
+                    const float* weight, int64_t ldw, int32_t dim, int32_t out_dim, int32_t gcn,
+                    const float* cls_w, const float* cls_b, int32_t num_classes, const int64_t* labels,
+                    const int32_t* label_index, float* out_h, int64_t ld_h, float* out_agg, int64_t ld_agg,
+                    float* out_dz, int64_t ld_dz, float* logp, float* loss, float* grad_cls_w,
+                    float* grad_cls_b, float* grad_table, int64_t ld_gt, void* workspace,
+                    size_t workspace_bytes, int32_t precision, gs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Update step of src/utils.py:185-187: per-model clip_grad_norm_(max_norm) then SGD.

@@ -467,3 +467,158 @@ def test_sampler_treats_repeated_ids_in_a_row_as_a_set(g, dev):
                     assert v not in row
                 if self_mode == 2:
                     assert v in row
+
+
+# ------------------------------------------------------------------------------------------------
+# the fused top layer (csrc/sage_top.cu): gather + mean + SageLayer + classifier + NLL + backward + scatter
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('gcn,classes,rows,live,precision,tol', [
+    (False, 47, 1000, 777, 'tf32x3', 1e-5), (False, 47, 1024, None, 'tf32x3', 1e-5), (True, 41, 333, None, 'tf32x3', 1e-5),
+    (False, 3, 16, 5, 'tf32x3', 1e-5), (False, 64, 2500, None, 'tf32x3', 1e-5), (False, 47, 1000, None, 'tf32', 3e-3)])
+def test_sage_top_sup_matches_torch_autograd(g, dev, gcn, classes, rows, live, precision, tol):
+    """One launch against torch fp64 autograd of the same top layer (src/models.py:209-220,25-27,300-314 and
+    src/utils.py:162-163): outputs, loss, classifier gradients, dZ and the ReLU-gated scatter into the gradient of
+    the layer below; `live` < rows exercises the device-side row count, rows % 16 != 0 the ragged last tile,
+    2500 rows the persistent multi-tile loop, repeated / shared neighbours the atomics."""
+    from graphsage_b200 import native, ops
+    H, fan = 128, 10
+    rng = np.random.default_rng(rows + classes)
+    n_prev = max(64, rows * 3)
+    table = np.maximum(rng.standard_normal((n_prev, H)), 0).astype(np.float32)          # a ReLU output: ~half zeros
+    stride = fan + (1 if gcn else 0)
+    nbr = np.full((rows, stride), -1, dtype=np.int32)
+    cnt = rng.integers(1, fan + 1, size=rows).astype(np.int32)
+    self_idx = rng.integers(0, n_prev, size=rows).astype(np.int32)
+    for r in range(rows):
+        ids = rng.choice(n_prev, size=cnt[r], replace=False)
+        if gcn:
+            ids = np.unique(np.concatenate([ids, [self_idx[r]]]))
+            cnt[r] = len(ids)
+        nbr[r, :cnt[r]] = np.sort(ids)
+    k = H if gcn else 2 * H
+    w = (rng.standard_normal((H, k)) * 0.1).astype(np.float32)
+    cw = (rng.standard_normal((classes, H)) * 0.2).astype(np.float32)
+    cb = (rng.standard_normal(classes) * 0.1).astype(np.float32)
+    n_nodes = 5000
+    node_of_row = rng.integers(0, n_nodes, size=rows).astype(np.int32)
+    labels = rng.integers(0, classes, size=n_nodes).astype(np.int64)
+    n_live = rows if live is None else live
+    # ---- torch fp64 reference ----
+    t = torch.tensor(table, dtype=torch.float64, requires_grad=True)
+    W = torch.tensor(w, dtype=torch.float64, requires_grad=True)
+    CW = torch.tensor(cw, dtype=torch.float64, requires_grad=True)
+    CB = torch.tensor(cb, dtype=torch.float64, requires_grad=True)
+    aggs = torch.stack([t[torch.as_tensor(nbr[r, :cnt[r]].astype(np.int64))].mean(0) for r in range(n_live)])
+    X = aggs if gcn else torch.cat([t[torch.as_tensor(self_idx[:n_live].astype(np.int64))], aggs], 1)
+    z = X @ W.t()
+    z.retain_grad()
+    h = torch.relu(z)
+    logp = torch.log_softmax(h @ CW.t() + CB, 1)
+    y = torch.as_tensor(labels[node_of_row[:n_live]])
+    loss = -logp[torch.arange(n_live), y].sum() / n_live
+    loss.backward()
+    want_gt = t.grad * (t.detach() > 0)
+    # ---- device ----
+    d = lambda a: torch.from_numpy(a).to(dev)
+    table_d, g_table = d(table), torch.zeros((n_prev, H), device=dev)
+    gcw, gcb = torch.zeros((classes, H), device=dev), torch.zeros((classes,), device=dev)
+    loss_d = torch.full((1,), 123.0, device=dev)
+    logp_d = torch.zeros((rows, classes), device=dev)
+    num_rows = None if live is None else torch.tensor([live], dtype=torch.int32, device=dev)
+    ws = ops.sage_top_workspace(dev)
+    prec = {'tf32x3': native.PREC_TF32X3, 'tf32': native.PREC_TF32}[precision]
+    for rep in range(2):                                   # twice: the ticket / partials of the workspace reset themselves
+        g_table.zero_(); gcw.zero_(); gcb.zero_()
+        out_h, out_agg, out_dz = ops.sage_top_sup(table_d, d(nbr), stride, d(cnt), d(self_idx), num_rows, rows, d(w), gcn,
+                                                  d(cw), d(cb), d(labels), d(node_of_row), loss_d, gcw, gcb, g_table, ws,
+                                                  prec, logp=logp_d)
+        torch.cuda.synchronize()
+        assert rel(out_agg[:n_live], aggs) <= 1e-6
+        assert rel(out_h[:n_live], h) <= tol
+        assert rel(logp_d[:n_live], logp) <= tol
+        assert rel(loss_d, loss.reshape(1)) <= tol
+        if precision == 'tf32':       # single-pass tf32: pre-activations within 1e-3 of zero gate differently than in fp64,
+            continue                  # which is a property of the reduced-precision mode, not of the kernel
+        assert rel(out_dz[:n_live], z.grad) <= tol * 3
+        assert rel(gcw, CW.grad) <= tol * 3 and rel(gcb, CB.grad) <= tol * 3
+        assert rel(g_table, want_gt) <= tol * 3
+    # the weight gradient of the layer from the saved operands (gs_sage_gemm_bwd_w, relu = 0)
+    if precision == 'tf32':
+        return
+    gw = torch.zeros((H, k), device=dev)
+    ops.sage_gemm_bwd_w(None if gcn else table_d, d(self_idx), out_agg, H, out_dz, out_h, H, gcn, False, num_rows, rows, gw,
+                        precision=prec)
+    assert rel(gw, W.grad) <= tol * 3
+    # unsupported shapes are refused, not mis-computed
+    assert not ops.sage_top_supported(64, 64, 7, 10, native.PREC_TF32X3, True)
+    assert not ops.sage_top_supported(128, 128, 7, 10, native.PREC_FP32, True)
+    assert not ops.sage_top_supported(128, 128, 100, 10, native.PREC_TF32X3, True)
+
+
+@pytest.mark.parametrize('precision', ['tf32x3', 'fp32'])
+def test_sage_gemm_bwd_w_pair_equals_two_launches(g, dev, precision):
+    """gs_sage_gemm_bwd_w_pair: the weight gradients of two layers (cfg-3 shapes: 10.9K x 200 and 1024 x 256 into
+    128 outputs) as ONE grid must equal the two separate launches and the fp64 products."""
+    from graphsage_b200 import native
+    prec = {'tf32x3': native.PREC_TF32X3, 'fp32': native.PREC_FP32}[precision]
+    rng = np.random.default_rng(3)
+    H = 128
+    shapes = [(10900, 11264, 100, 30000), (1000, 1024, 128, 10900)]        # live rows, max rows, dim, table rows
+    probs, want = [], []
+    for live, mx, dim, n_tab in shapes:
+        tab = torch.from_numpy(rng.standard_normal((n_tab, dim)).astype(np.float32)).to(dev)
+        sidx = torch.from_numpy(rng.integers(0, n_tab, size=mx).astype(np.int32)).to(dev)
+        agg = torch.from_numpy(rng.standard_normal((mx, dim)).astype(np.float32)).to(dev)
+        dz = torch.from_numpy((rng.standard_normal((mx, H)) * (rng.random((mx, H)) > 0.5)).astype(np.float32)).to(dev)
+        out = torch.ones((mx, H), device=dev)
+        nr = torch.tensor([live], dtype=torch.int32, device=dev)
+        gw = torch.zeros((H, 2 * dim), device=dev)
+        probs.append((tab, sidx, agg, dim, dz, out, H, nr, mx, gw))
+        X = torch.cat([tab[sidx[:live].long()], agg[:live]], 1).double()
+        want.append(dz[:live].double().t() @ X)
+    g.sage_gemm_bwd_w_pair(probs, False, False, prec)
+    for (tab, sidx, agg, dim, dz, out, _, nr, mx, gw), w in zip(probs, want):
+        single = torch.zeros_like(gw)
+        g.sage_gemm_bwd_w(tab, sidx, agg, dim, dz, out, H, False, False, nr, mx, single, precision=prec)
+        assert rel(gw, w) <= TOL and rel(single, w) <= TOL
+
+
+def test_fused_sampler_unique_chain_equals_numpy(g, dev):
+    """The 5-launch preparation chain: sample(+fetch from the device queue, +mark) -> bitmap scan -> emit/remap ->
+    sample(+clear).  Unique ids / remap indices must equal numpy's on the drawn lists, the bitmap must be all-zero
+    again afterwards, the queue cursor must advance by one per fetch (and wrap), and the draws must equal those of
+    the plain sampler on the same (seed, offset) -- the extras never change what is drawn."""
+    from graphsage_b200 import native, synth
+    n = 20000
+    rowptr_h, col_h = synth.powerlaw_graph(n, n * 12, seed=4)
+    rowptr, col = _csr_dev(rowptr_h, col_h, dev)
+    b_sz, k = 256, 10
+    rng = np.random.default_rng(1)
+    queue = torch.from_numpy(rng.integers(0, n, size=(3, b_sz)).astype(np.int32)).to(dev)
+    desc = torch.tensor([queue.data_ptr(), 3, 0, 0], dtype=torch.int64, device=dev)
+    ws = g.unique_bitmap_workspace(n, dev)
+    words = (n + 31) // 32
+    for step in range(4):                                   # 4 > 3 rows: the cursor wraps
+        seeds = torch.full((b_sz,), -7, dtype=torch.int32, device=dev)
+        nbr, cnt = g.sample_neighbors(rowptr, col, n, None, None, b_sz, k, k, native.SELF_DROP, 99, (step << 8) | 2,
+                                      queue_desc=desc, fetch_dst=seeds, mark_bitmap=ws)
+        want_seeds = queue[step % 3]
+        assert torch.equal(seeds, want_seeds)
+        assert desc.cpu().tolist()[2:] == [step + 1, 0]
+        plain_nbr, plain_cnt = g.sample_neighbors(rowptr, col, n, want_seeds.contiguous(), None, b_sz, k, k, native.SELF_DROP,
+                                                  99, (step << 8) | 2)
+        assert torch.equal(nbr, plain_nbr) and torch.equal(cnt, plain_cnt)
+        uniq, num_uniq, nbr_idx, self_idx = g.unique_remap_bitmap(seeds, None, b_sz, nbr, k, n, ws,
+                                                                  flags=native.UNIQUE_MARKED | native.UNIQUE_LEAVE_MARKS)
+        nbr_h, seeds_h = nbr.cpu().numpy(), seeds.cpu().numpy()
+        want = np.unique(np.concatenate([seeds_h, nbr_h[nbr_h >= 0]]))
+        nu = int(num_uniq.item())
+        assert nu == len(want) and np.array_equal(uniq[:nu].cpu().numpy(), want)
+        idx_h = nbr_idx.cpu().numpy()
+        assert np.array_equal(want[idx_h[nbr_h >= 0]], nbr_h[nbr_h >= 0]) and (idx_h[nbr_h < 0] == -1).all()
+        assert np.array_equal(want[self_idx.cpu().numpy()], seeds_h)
+        # the next sampler (rows = the unique ids) clears the words it owns
+        nbr1, cnt1 = g.sample_neighbors(rowptr, col, n, uniq, num_uniq, uniq.shape[0], k, k, native.SELF_DROP, 99,
+                                        (step << 8) | 1, clear_bitmap=ws)
+        assert int(ws[:words * 4].view(torch.int32).abs().sum().item()) == 0
+        assert int((cnt1[:nu] > 0).sum().item()) == nu

@@ -82,22 +82,53 @@ class _OracleLoop:
         self.adj = so.LazySetAdjacency(world['rowptr'], world['col'])
         self.labels = world['labels']
         self.opt = torch.optim.SGD(self.w + [self.cw, self.cb], lr=0.7)                  # src/utils.py:136
+        self.before = None
 
     def step(self, batch, calls):
         assert calls[0][0] == [int(x) for x in batch]
+        self.before = [p.detach().clone() for p in self.w + [self.cw, self.cb]]
         loss, _, _ = so.supervised_step(self.w, self.cw, self.cb, self.feats, self.adj, batch, self.labels,
                                         injected=[(c[1], c[2]) for c in calls])           # :157-163,184
         torch.nn.utils.clip_grad_norm_(self.w, 5)                                        # :185-186 (graphSage)
         torch.nn.utils.clip_grad_norm_([self.cw, self.cb], 5)                            # (classification)
         self.opt.step()                                                                  # :187
         self.opt.zero_grad()
-        return float(loss)
+        return float(loss.detach())
+
+    def relu_flips(self, calls, layers):
+        """Hidden units of the step just taken whose ReLU gate differs between the device and the oracle: a
+        pre-activation within fp32 rounding of zero can land on either side, and the weight gradient then
+        differs by that unit's whole contribution (both evaluations are correct fp32 evaluations)."""
+        with torch.no_grad():
+            h1 = so.graphsage_forward([self.before[0]], self.feats, self.adj, calls[1][0], False, 'MEAN',
+                                      injected=[(calls[1][1], calls[1][2])])
+            rows = h1.shape[0]
+            flips = int(((layers[0].h[:rows, :HIDDEN].cpu() > 0) != (h1 > 0)).sum())
+            pre = [(calls[1][1], calls[1][2]), (calls[0][1], calls[0][2])]
+            h2 = so.graphsage_forward(self.before[:2], self.feats, self.adj, calls[0][0], False, 'MEAN',
+                                      injected=[pre[1], pre[0]])
+            flips += int(((layers[1].h[:h2.shape[0], :HIDDEN].cpu() > 0) != (h2 > 0)).sum())
+        return flips
+
+    def resync(self, model, cls):
+        with torch.no_grad():
+            for dst, src in zip(self.w + [self.cw, self.cb],
+                                [model.sage_layer1.weight, model.sage_layer2.weight, cls.layer[0].weight, cls.layer[0].bias]):
+                dst.copy_(src.detach().cpu())
 
 
-def _compare(tag, step, loss_dev, model, cls, ref, loss_ref):
+def _compare(tag, step, loss_dev, model, cls, ref, loss_ref, calls=None, layers=None):
     errs = {'loss': abs(loss_dev - loss_ref) / max(abs(loss_ref), 1e-30),
             'w1': rel(model.sage_layer1.weight, ref.w[0]), 'w2': rel(model.sage_layer2.weight, ref.w[1]),
             'cls_w': rel(cls.layer[0].weight, ref.cw), 'cls_b': rel(cls.layer[0].bias, ref.cb)}
+    if max(errs.values()) > TOL and calls is not None and errs['loss'] <= TOL:
+        # the only excuse: a ReLU gate that fell on the other side of zero (see relu_flips).  Then the bound is the
+        # one the golden-fixture tests use for that case (5e-3), and the oracle continues from the device's weights.
+        flips = ref.relu_flips(calls, layers)
+        assert flips > 0, (tag, step, errs, 'no ReLU gate differs: the deviation is a real one')
+        assert max(errs.values()) <= 5e-3, (tag, step, errs, flips)
+        ref.resync(model, cls)
+        return
     assert max(errs.values()) <= TOL, (tag, step, errs)
 
 
@@ -113,7 +144,8 @@ def test_supervised_trainer_matches_the_oracle_at_the_headline_shape(world, use_
         torch.cuda.synchronize()
         calls = _drawn_calls(tr.last_layers)
         assert len(calls[1][0]) > 5 * B_SZ                      # the layer-1 frontier really is ~10x the batch
-        _compare(f'SupervisedTrainer graph={use_graph}', i, loss_dev, model, cls, ref, ref.step(batch, calls))
+        _compare(f'SupervisedTrainer graph={use_graph}', i, loss_dev, model, cls, ref, ref.step(batch, calls), calls,
+                 tr.last_layers)
     tr.check()
 
 
@@ -134,7 +166,7 @@ def test_pipelined_trainer_matches_the_oracle_at_the_headline_shape(world, use_g
         torch.cuda.synchronize()
         calls = _drawn_calls(tr.slot_layers[slot])
         _compare(f'PipelinedTrainer graph={use_graph}', i, loss_dev, model, cls, ref,
-                 ref.step(world['batches'][i], calls))
+                 ref.step(world['batches'][i], calls), calls, tr.slot_layers[slot])
     tr.check()
 
 
@@ -154,7 +186,8 @@ def test_pipelined_pair_graph_matches_the_oracle(world):
         slot = tr_a._cur
         loss_a = float(tr_a.run(1).item())
         torch.cuda.synchronize()
-        _compare('pair twin', i, loss_a, model_a, cls_a, ref, ref.step(world['batches'][i], _drawn_calls(tr_a.slot_layers[slot])))
+        calls = _drawn_calls(tr_a.slot_layers[slot])
+        _compare('pair twin', i, loss_a, model_a, cls_a, ref, ref.step(world['batches'][i], calls), calls, tr_a.slot_layers[slot])
     # B: the same two steps as one pair-graph launch must land on the same weights bit for bit or within TOL
     model_b, cls_b = _build(world)
     tr_b = PipelinedTrainer(model_b, cls_b, world['labels'], B_SZ, use_graph=True)
