@@ -244,7 +244,7 @@ def workload_config(args, cfg, rowptr, col, b_sz):
                                                    else "NCCL all-reduce + separate clip/SGD kernels"),
             "l2_policy": "feature table 980 MB >> 126 MB L2; fresh seeds every step",
             "update": "clip_grad_norm 5 per model + SGD lr 0.7 inside the step",
-            "pipeline": ("2-stage: sampling/unique/layer-1 aggregation of batch n+1 in a graph branch beside the "
+            "pipeline": ("3 slots: layer-1 aggregation of batch n+1 and sampling/unique of batch n+2 in a graph branch beside the "
                          "GEMMs/backward/update of batch n" if (args.pipeline and args.exchange == "peer") else "none")}
 
 
@@ -303,16 +303,17 @@ def timed_arms(torch, native, trainer, pipelined, dev_batches, host_batches, K, 
         loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
         trainer.flush()
         trainer.feed(host_batches[0])
-        trainer.prime()
+        trainer.feed(host_batches[1 % n_host])
+        trainer.prime()                                                        # two batches in flight ahead of the trained one
         for i in range(min(W, 3)):
-            trainer.feed(host_batches[(1 + i) % n_host])
+            trainer.feed(host_batches[(2 + i) % n_host])
             trainer.run(1)
         sync_all()
         for w in range(windows):
             e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e2.record()
             for i in range(K):
-                trainer.feed(host_batches[(W + 1 + w * K + i) % n_host])
+                trainer.feed(host_batches[(W + 2 + w * K + i) % n_host])
                 dev_loss = trainer.run(1)
                 loss_pin[i & 1].copy_(dev_loss, non_blocking=True)
                 loss_ev[i & 1].record()

@@ -88,42 +88,42 @@ __device__ long long g_dp_trace[16];
 #define GS_DP_MARK(slot) do { } while (0)
 #endif
 
+// Elements are float4s; thread t of CTA c owns float4s  c*256 + t + j*G*256  (j < kDpPer): consecutive threads touch
+// consecutive float4s, and everything a thread needs -- its gradient pieces, the segment they fall in, the parameter
+// pieces they update -- is fetched in ONE round of independent loads before the grid barrier, so the kernel is
+// (one memory round trip) + (the barrier) + (stores).  The tables stay in the constant bank (__grid_constant__).
+constexpr int kDpPer = 4;          // float4s per thread held in registers; larger buffers take the looping path
+
 __global__ void __launch_bounds__(kDpThreads)
-dp_update_kernel(float* __restrict__ flat, long long n_total, const DpPeers peers_arg, const DpSegs segs_arg,
-                 DpState* __restrict__ st, float max_norm, float lr, unsigned long long timeout_ns,
-                 long long* __restrict__ step_counter) {
+dp_update_kernel(float* __restrict__ flat, long long n_total, const __grid_constant__ DpPeers peers,
+                 const __grid_constant__ DpSegs segs, DpState* __restrict__ st, float max_norm, float lr,
+                 unsigned long long timeout_ns, long long* __restrict__ step_counter) {
   GS_DP_MARK(0);
   pdl_sync();
   GS_DP_MARK(1);
-  // the tables are indexed dynamically: keep them in shared memory, not in a local-memory copy of the parameters
-  __shared__ DpPeers peers;
-  __shared__ DpSegs segs;
   const int G = gridDim.x, c = blockIdx.x, tid = threadIdx.x;
-  if (tid == 0) { peers = peers_arg; segs = segs_arg; }
-  __syncthreads();
-  GS_DP_MARK(2);
-  const unsigned int e = st->epoch + 1u;
+  const unsigned int e = *reinterpret_cast<volatile unsigned int*>(&st->epoch) + 1u;
   const int par = static_cast<int>(e & 1u);
   const long long n4 = n_total >> 2;
-  const long long per = (n4 + G - 1) / G;
-  const long long b4 = static_cast<long long>(c) * per;
-  const long long e4 = b4 + per < n4 ? b4 + per : n4;
   float4* flat4 = reinterpret_cast<float4*>(flat);
   const int W = peers.world, me = peers.rank;
+  const long long first = static_cast<long long>(c) * kDpThreads + tid;
+  const long long stride = static_cast<long long>(G) * kDpThreads;
+  GS_DP_MARK(2);
 
   if (W > 1) {
-    // ---- push my slice into every peer's slot [par][me] ----
+    // ---- push my pieces into every peer's slot [par][me] ----
     for (int p = 0; p < W; ++p) {
       if (p == me) continue;
       float4* dst = reinterpret_cast<float4*>(peers.recv[p]) + static_cast<long long>(par * W + me) * n4;
-      for (long long i = b4 + tid; i < e4; i += kDpThreads) dst[i] = flat4[i];
+      for (long long i = first; i < n4; i += stride) dst[i] = flat4[i];
     }
     // No per-thread system fence here: the CTA barrier orders every thread's remote stores before the flag
     // writers, and their release at system scope is cumulative -- one fence round trip over NVLink, not two.
     __syncthreads();
     if (tid < W && tid != me) {
       st_release_sys(peers.flags[tid] + me * kDpMaxCtas + c, e);
-      // ---- wait for peer `tid`'s copy of slice c ----
+      // ---- wait for peer `tid`'s copy of the pieces CTA c owns ----
       const uint32_t* f = peers.flags[me] + tid * kDpMaxCtas + c;
       unsigned long long t0 = 0;
       for (unsigned spins = 0; static_cast<int>(ld_acquire_sys(f) - e) < 0; ++spins) {
@@ -137,28 +137,56 @@ dp_update_kernel(float* __restrict__ flat, long long n_total, const DpPeers peer
     }
     __syncthreads();
   }
-
   GS_DP_MARK(3);
-  // ---- reduce in rank order, scale to the mean, per-group sum of squares ----
+
+  // ---- one round of loads: gradient pieces (all ranks' copies), their segments, the parameters they update ----
   const float inv_w = 1.0f / static_cast<float>(W);
+  const float4* mine = reinterpret_cast<const float4*>(peers.recv[me]) + static_cast<long long>(par) * W * n4;
+  const bool in_regs = n4 <= stride * kDpPer;
+  float4 gsum[kDpPer], wv[kDpPer];
+  int segk[kDpPer];
   float ss[kDpMaxGroups];
 #pragma unroll
   for (int g = 0; g < kDpMaxGroups; ++g) ss[g] = 0.f;
-  const float4* mine = reinterpret_cast<const float4*>(peers.recv[me]) + static_cast<long long>(par) * W * n4;
-  for (long long i = b4 + tid; i < e4; i += kDpThreads) {
+  auto reduce_one = [&](long long i) -> float4 {
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < W; ++r) {
+    for (int r = 0; r < W; ++r) {                          // rank order: every rank adds the same numbers in the same order
       const float4 v = (r == me) ? flat4[i] : __ldcg(mine + static_cast<long long>(r) * n4 + i);
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
     s.x *= inv_w; s.y *= inv_w; s.z *= inv_w; s.w *= inv_w;
-    flat4[i] = s;
-    const int k = seg_of(segs, 4 * i);
-    if (k >= 0) {
-      const float q = s.x * s.x + s.y * s.y + s.z * s.z + s.w * s.w;     // padding elements are zero
-      const int g = segs.group[k];
+    return s;
+  };
+  auto add_ss = [&](const float4& s, int k) {
+    if (k < 0) return;
+    const float q = s.x * s.x + s.y * s.y + s.z * s.z + s.w * s.w;     // padding elements are zero
+    const int g = segs.group[k];
 #pragma unroll
-      for (int gg = 0; gg < kDpMaxGroups; ++gg) if (gg == g) ss[gg] += q;
+    for (int gg = 0; gg < kDpMaxGroups; ++gg) if (gg == g) ss[gg] += q;
+  };
+  if (in_regs) {
+#pragma unroll
+    for (int j = 0; j < kDpPer; ++j) {
+      const long long i = first + j * stride;
+      segk[j] = -1;
+      if (i < n4) {
+        gsum[j] = reduce_one(i);
+        const int k = seg_of(segs, 4 * i);
+        segk[j] = k;
+        if (k >= 0) {
+          const long long o = 4 * i - segs.off[k];
+          const float* p = segs.param[k] + o;
+          if (segs.numel[k] - o >= 4 && (reinterpret_cast<uintptr_t>(p) & 15u) == 0) wv[j] = *reinterpret_cast<const float4*>(p);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kDpPer; ++j) add_ss(gsum[j], segk[j]);
+  } else {
+    for (long long i = first; i < n4; i += stride) {
+      const float4 s = reduce_one(i);
+      flat4[i] = s;
+      add_ss(s, seg_of(segs, 4 * i));
     }
   }
   __shared__ float s_red[kDpThreads / 32][kDpMaxGroups];
@@ -216,17 +244,15 @@ dp_update_kernel(float* __restrict__ flat, long long n_total, const DpPeers peer
   __syncthreads();
   GS_DP_MARK(6);
 
-  // ---- SGD on my slice, gradient zeroed for the next step ----
-  for (long long i = b4 + tid; i < e4; i += kDpThreads) {
-    const float4 g = flat4[i];
-    const int k = seg_of(segs, 4 * i);
+  // ---- SGD on my pieces, gradient zeroed for the next step ----
+  auto sgd_one = [&](long long i, const float4& g, int k, const float4* w_have) {
     if (k >= 0) {
       const float step = lr * s_coef[segs.group[k]];
       const long long o = 4 * i - segs.off[k];
       float* p = segs.param[k] + o;
       const long long left = segs.numel[k] - o;
       if (left >= 4 && (reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
-        float4 w = *reinterpret_cast<float4*>(p);
+        float4 w = w_have ? *w_have : *reinterpret_cast<float4*>(p);
         w.x = fmaf(-step, g.x, w.x); w.y = fmaf(-step, g.y, w.y); w.z = fmaf(-step, g.z, w.z); w.w = fmaf(-step, g.w, w.w);
         *reinterpret_cast<float4*>(p) = w;
       } else {
@@ -235,6 +261,15 @@ dp_update_kernel(float* __restrict__ flat, long long n_total, const DpPeers peer
       }
     }
     flat4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  if (in_regs) {
+#pragma unroll
+    for (int j = 0; j < kDpPer; ++j) {
+      const long long i = first + j * stride;
+      if (i < n4) sgd_one(i, gsum[j], segk[j], &wv[j]);
+    }
+  } else {
+    for (long long i = first; i < n4; i += stride) sgd_one(i, flat4[i], seg_of(segs, 4 * i), nullptr);
   }
   GS_DP_MARK(7);
   if (c == 0 && tid == 0) {
@@ -293,7 +328,7 @@ extern "C" int gs_dp_allreduce_clip_sgd(float* flat_grad, int64_t n_total, void*
   segs.groups = groups;
   // the grid size is a pure function of n_total: the barrier counter of `state` relies on it
   const int64_t n4 = n_total >> 2;
-  int grid = static_cast<int>((n4 + 4 * kDpThreads - 1) / (4 * kDpThreads));
+  int grid = static_cast<int>((n4 + kDpThreads - 1) / kDpThreads);      // one float4 per thread while <= 64 CTAs suffice
   if (grid > kDpMaxCtas) grid = kDpMaxCtas;
   if (grid < 1) grid = 1;
   launch(dp_update_kernel, grid, kDpThreads, 0, as_stream(stream), flat_grad, n_total, peers, segs,

@@ -150,7 +150,7 @@ struct Smem {
 };
 
 template <bool GCN, bool SPLIT3>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __maxnreg__(72)
 sage_top_sup_kernel(const Params p, const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_wc) {
   GS_TOP_MARK(0);
   pdl_sync();

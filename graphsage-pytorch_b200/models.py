@@ -194,8 +194,9 @@ class _Frontier:
     def inherit(self, old: "_Frontier", first_layer: bool):
         """Take over the weight-dependent buffers of the frontier this one replaces (same static shapes)."""
         self.h, self.dz, self.gh = old.h, old.dz, old.gh
-        if not first_layer:
-            self.agg, self.argmax = old.agg, old.argmax
+        self.agg, self.argmax = old.agg, old.argmax
+        if first_layer and not isinstance(old.table_in, ShardedTable) and old.self_idx is None:
+            self.table_in = old.table_in                 # the fp32 self rows a sharded gather emits (see _run_agg1)
 
 
 class _GraphSageFn(torch.autograd.Function):
@@ -332,14 +333,20 @@ class GraphSage(nn.Module):
     def _run_prep(self, nodes_dev: torch.Tensor, injected=None, offset_dev: Optional[torch.Tensor] = None,
                   reuse: Optional[List[_Frontier]] = None, num_rows: Optional[torch.Tensor] = None,
                   queue_desc: Optional[torch.Tensor] = None) -> List[_Frontier]:
-        """The weight-independent half of a forward pass: sampling + unique/remap of every layer
-        (src/models.py:249-251) and the layer-1 aggregation of the raw features (:260, index 1).
+        """The weight-independent half of a forward pass: `_run_sample` then `_run_agg1`."""
+        return self._run_agg1(self._run_sample(nodes_dev, injected, offset_dev, reuse, num_rows, queue_desc))
+
+    def _run_sample(self, nodes_dev: torch.Tensor, injected=None, offset_dev: Optional[torch.Tensor] = None,
+                    reuse: Optional[List[_Frontier]] = None, num_rows: Optional[torch.Tensor] = None,
+                    queue_desc: Optional[torch.Tensor] = None) -> List[_Frontier]:
+        """Sampling + unique/remap of every layer (src/models.py:249-251): the integer half of the preparation.
         `reuse`: the frontiers of an earlier call whose buffers are overwritten in place (static
         addresses: the pipelined trainer prepares step n+1 in a graph branch beside step n).
         `queue_desc`: the batch is the next row of a device-side queue (ops.fetch_batch's descriptor); the top
         sampler launch fetches it itself and writes it into `nodes_dev`.
         With the bitmap unique, its mark / clear passes run inside the sampler launches either side of it, so a
-        2-layer preparation is 5 launches: sample(+fetch, +mark), scan, emit/remap, sample(+clear), aggregate."""
+        2-layer preparation is 5 launches: sample(+fetch, +mark), scan, emit/remap, sample(+clear), aggregate
+        (the last one is `_run_agg1`)."""
         if num_rows is not None and injected is not None:
             raise ValueError("injected samples describe a batch of known size")
         if queue_desc is not None and (injected is not None or num_rows is not None):
@@ -399,22 +406,27 @@ class GraphSage(nn.Module):
             else:       # layer 1 gathers straight from the feature table by node id: no U0, no remap
                 fr.nbr_idx, fr.self_idx = fr.nbr, nodes
             layers[l] = fr
-        # ---- layer-1 aggregation: reads only the raw feature table ----
-        fr, old = layers[1], (reuse[0] if reuse is not None else None)
+        return layers[1:]
+
+    def _run_agg1(self, layers: List[_Frontier]) -> List[_Frontier]:
+        """The layer-1 aggregation of the raw features (src/models.py:260, index 1) on sampled frontiers: the
+        HBM-bound half of the preparation.  Output buffers a frontier already owns are overwritten in place."""
+        csr, table, dev = self._state()
+        mode = native.AGG_MEAN if self.agg_func == 'MEAN' else native.AGG_MAX
+        fr = layers[0]
+        self_rows_buf = fr.table_in if (fr.table_in is not None and fr.table_in is not table) else None
         fr.table_in, fr.dim_in = table, self.input_size
         if isinstance(table, ShardedTable):
             # row-partitioned table: K3 also emits the fp32 self rows (:265), which become K4's self
             # operand with the identity index (forward and backward)
             fr.agg, self_rows = ops.agg_fwd_sharded(table, fr.nbr_idx, fr.stride, fr.cnt, fr.nodes, fr.num_rows,
-                                                    fr.rows_max, want_self=not self.gcn,
-                                                    out=old.agg if old else None,
-                                                    out_self=old.table_in if (old and not self.gcn) else None)
+                                                    fr.rows_max, want_self=not self.gcn, out=fr.agg,
+                                                    out_self=self_rows_buf if not self.gcn else None)
             fr.argmax, fr.table_in, fr.self_idx = None, self_rows, None
         else:
             fr.agg, fr.argmax = ops.agg_fwd(table, self.input_size, fr.nbr_idx, fr.stride, fr.cnt, fr.num_rows,
-                                            fr.rows_max, mode, out=old.agg if old else None,
-                                            argmax=old.argmax if old else None)
-        return layers[1:]
+                                            fr.rows_max, mode, out=fr.agg, argmax=fr.argmax)
+        return layers
 
     def _run_compute(self, layers: List[_Frontier], weights: Sequence[torch.Tensor], upto: Optional[int] = None,
                      zero_grad_of_last: Optional[torch.Tensor] = None) -> List[_Frontier]:

@@ -413,34 +413,39 @@ class SupervisedTrainer:
 class PipelinedTrainer(SupervisedTrainer):
     """Software-pipelined, device-resident supervised loop (src/utils.py:141-191).
 
-    Sampling, unique/remap and the layer-1 aggregation of the raw features do not depend on the
-    weights (`GraphSage._run_prep`), so the graph of step n has TWO branches: the GEMMs / loss /
-    backward / exchange+update of batch n, and beside it the preparation of batch n+1 into the
-    other of two static frontier slots.  The HBM-bound gathers overlap the tensor-core and
-    latency-bound half; every batch still gets exactly the same work and arithmetic as in
-    `SupervisedTrainer` (identical results when the sampler has no choice to make, see
-    tests/test_gpu_model.py::test_pipelined_trainer_matches_plain_trainer).
+    Sampling, unique/remap and the layer-1 aggregation of the raw features do not depend on the weights
+    (`GraphSage._run_sample`, `_run_agg1`), so the graph of step n has TWO branches over THREE static frontier slots:
 
-    Batches come from a device-side QUEUE (the reference slices every batch of an epoch from one
-    shuffled array, src/utils.py:127,145): the preparation branch starts with gs_fetch_batch,
-    which copies the next row of the queued [rows x b_sz] array into its slot and advances the
-    cursor, so consecutive replays need no host work in between and two steps share one graph.
+        training chain     layer-1 GEMM -> fused top layer -> weight-gradient GEMMs -> exchange + update   of batch n
+        preparation chain  layer-1 aggregation of batch n+1,  then sampling + unique/remap of batch n+2
+
+    The order inside the preparation chain matters: the aggregation (HBM-bound, fills every SM with resident warps)
+    runs beside the layer-1 GEMM at the start of the step; run later it keeps the CTAs of the top-layer and
+    weight-gradient kernels off the SMs until it has drained (measured: 73.6 us per step with sampling first,
+    63.4 us with the aggregation first; scratch/branch_probe.py).  Every batch still gets exactly the same work and
+    arithmetic as in `SupervisedTrainer` (tests/test_gpu_model.py::test_pipelined_trainer_matches_plain_trainer).
+
+    Batches come from a device-side QUEUE (the reference slices every batch of an epoch from one shuffled array,
+    src/utils.py:127,145): the top sampler launch of a preparation fetches the next row of the queued [rows x b_sz]
+    array and advances the cursor, so consecutive replays need no host work in between and three steps share one
+    graph launch.
 
         tr.set_queue(batches_int32_dev)        # or tr.feed(host_batch) per step (pinned H2D on a copy stream)
-        tr.prime()                             # prepares batch 0
-        loss = tr.run(n)                       # n steps: trains batch i while preparing batch i+1
-        loss = tr.flush()                      # trains on the last prepared batch
+        tr.prime()                             # samples batches 0 and 1, aggregates batch 0
+        loss = tr.run(n)                       # n steps: trains batch i | aggregates batch i+1, samples batch i+2
+        loss = tr.flush()                      # trains on the (up to two) batches still in the pipeline
     `submit` / `submit_device` / `step` keep the one-call-per-batch form on top of the same machinery."""
 
     RING = 4          # rows of the internal staging ring used by feed()/submit()
+    SLOTS = 3         # frontier slots: being trained on / aggregated / sampled
 
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
         if self.dp is None:
             raise ValueError("PipelinedTrainer needs exchange='peer' (the whole step must be one graph)")
         dev = self.dev
-        self.slot_seeds = [torch.zeros((self.b_sz,), dtype=torch.int32, device=dev) for _ in range(2)]
-        self.slot_layers = [None, None]
+        self.slot_seeds = [torch.zeros((self.b_sz,), dtype=torch.int32, device=dev) for _ in range(self.SLOTS)]
+        self.slot_layers = [None] * self.SLOTS
         self.sample_counter = torch.zeros((1,), dtype=torch.int64, device=dev)
         self.queue_desc = torch.zeros((4,), dtype=torch.int64, device=dev)        # {address, rows, next, ticket}
         self._queue = None
@@ -448,18 +453,25 @@ class PipelinedTrainer(SupervisedTrainer):
         self._ring_pinned = torch.zeros((self.RING, self.b_sz), dtype=torch.int32).pin_memory()
         self._ring_events = [None] * self.RING
         self._fed = 0                          # batches written into the ring so far
-        self._fetched = 0                      # gs_fetch_batch launches enqueued since the ring became the queue
+        self._fetched = 0                      # batch fetches enqueued since the ring became the queue
         self._fetch_events = [None] * self.RING    # _fetch_events[j % RING]: recorded behind the j-th fetch
         self._copy_stream = torch.cuda.Stream(device=dev)
         self._prep_stream = torch.cuda.Stream(device=dev)
-        # occupancy cap (CTAs/SM) of the layer-1 aggregation while it runs beside the training chain, 0 = none
-        # (gs_set_agg_ctas).  Measured on B200 with every kernel on the max-shared carveout: 5/SM (no cap)
-        # 10.97M seed nodes/s, 3/SM 10.56M, 2/SM 10.33M, 1/SM 9.5M -- the gathers finish sooner than they hurt.
+        # diagnostics knobs (scratch/sweep.sh): occupancy cap of the background aggregation (CTAs/SM, 0 = none),
+        # programmatic dependent launch inside the preparation chain, max-shared carveout for it, a high-priority
+        # stream for the training chain.  None of them moves the step by more than 1 us once the aggregation runs
+        # first (see the class docstring); the defaults are what bench.py measures.
         self.bg_agg_ctas = int(os.environ.get("GS_BG_AGG_CTAS", "0"))
-        self._graphs = [None, None]            # one step from slot 0 / slot 1
-        self._graph_pair = None                # two steps (slot 0 then slot 1) in one launch
-        self._cur: Optional[int] = None        # slot holding the prepared, not yet trained batch
-        self._prep_call: Optional[int] = None  # the model call number every prep launches with (see _prep)
+        self.prep_pdl = os.environ.get("GS_PREP_PDL", "0") == "1"
+        self.bg_carveout = os.environ.get("GS_BG_CARVE", "1") == "1"
+        self._train_stream = (torch.cuda.Stream(device=dev, priority=-1)
+                              if os.environ.get("GS_TRAIN_PRIO", "0") == "1" else None)
+        self._graphs = [None] * self.SLOTS     # one step training on slot s
+        self._graph_multi = None               # SLOTS steps (slots 0, 1, 2) in one launch
+        self._cur: Optional[int] = None        # slot holding the oldest prepared, not yet trained batch
+        self._pending = 0                      # batches sampled but not yet trained (2 in the steady state)
+        self._agg_done = False                 # the batch in slot _cur has its layer-1 aggregation
+        self._prep_call: Optional[int] = None  # the model call number every sampling launches with (see _sample)
 
     # ---- batch queue --------------------------------------------------------------------------------
     def set_queue(self, batches_dev: torch.Tensor):
@@ -468,6 +480,8 @@ class PipelinedTrainer(SupervisedTrainer):
         if batches_dev.dtype != torch.int32 or batches_dev.dim() != 2 or batches_dev.shape[1] != self.b_sz \
                 or not batches_dev.is_contiguous():
             raise ValueError(f"batch queue must be a contiguous int32 [rows, {self.b_sz}] tensor")
+        if self._pending:
+            raise RuntimeError("flush() the pipeline before changing the batch queue")
         self._queue = batches_dev
         desc = torch.tensor([batches_dev.data_ptr(), batches_dev.shape[0], 0, 0], dtype=torch.int64)
         self.queue_desc.copy_(desc.to(self.dev), non_blocking=False)
@@ -515,7 +529,7 @@ class PipelinedTrainer(SupervisedTrainer):
         return self._fetch_events[prev % self.RING]
 
     def _mark_fetched(self, n: int = 1):
-        """n more gs_fetch_batch launches are enqueued on the current stream: one event behind them covers all."""
+        """n more batch fetches are enqueued on the current stream: one event behind them covers all."""
         if self._queue is not self._ring:
             return
         ev = torch.cuda.Event()
@@ -524,6 +538,10 @@ class PipelinedTrainer(SupervisedTrainer):
             self._fetch_events[self._fetched % self.RING] = ev
             self._fetched += 1
 
+    def _unfetched(self) -> int:
+        """Batches in the queue no sampling has fetched yet (a device queue wraps: never runs dry)."""
+        return (self._fed - self._fetched) if self._queue is self._ring else (1 << 30)
+
     def feed_device(self, seeds_dev: torch.Tensor):
         self._use_ring()
         r = self._fed % self.RING
@@ -531,99 +549,114 @@ class PipelinedTrainer(SupervisedTrainer):
         self._ring[r].copy_(seeds_dev, non_blocking=True)
         self._fed += 1
 
-    # ---- the two halves ---------------------------------------------------------------------------
-    def _prep(self, slot: int):
-        # Philox offset of a prep = (model call number << 8 | layer) + (sample_counter << 8).  The call number is
-        # baked into a captured launch, so every prep -- whichever graph or slot it was captured for, or eager --
-        # carries the SAME one and the device counter (+1 per prep) alone tells consecutive batches apart.
+    # ---- the pieces of a step ---------------------------------------------------------------------
+    def _sample(self, slot: int):
+        # Philox offset of a sampling = (model call number << 8 | layer) + (sample_counter << 8).  The call number is
+        # baked into a captured launch, so every sampling -- whichever graph or slot it was captured for, or eager --
+        # carries the SAME one and the device counter (+1 per batch) alone tells consecutive batches apart.
         m = self.model
         if self._prep_call is None:
             self._prep_call = m._calls
         keep, m._calls = m._calls, self._prep_call
         # the top sampler launch fetches the next queued batch into slot_seeds[slot] itself (gs_sample_neighbors_ex)
-        self.slot_layers[slot] = m._run_prep(self.slot_seeds[slot], None, offset_dev=self.sample_counter,
-                                             reuse=self.slot_layers[slot], queue_desc=self.queue_desc)
+        self.slot_layers[slot] = m._run_sample(self.slot_seeds[slot], None, offset_dev=self.sample_counter,
+                                               reuse=self.slot_layers[slot], queue_desc=self.queue_desc)
         m._calls = max(keep, self._prep_call + 1)
         self.sample_counter.add_(1)
+
+    def _aggregate(self, slot: int):
+        self.model._run_agg1(self.slot_layers[slot])
 
     def _compute(self, slot: int, update: bool = True):
         self._train_on(self.slot_layers[slot], self.slot_seeds[slot])
         if update:
             self.dp.update(self.max_norm, self.lr, None)
 
+    def _background(self, on: bool):
+        native.set_pdl((1 if self.prep_pdl else 0) if on else -1)
+        native.set_agg_ctas(self.bg_agg_ctas if on else 0)
+        native.set_background(self.bg_carveout and on)
+
     def _both(self, slot: int, update: bool = True):
-        """train on `slot` | prepare the other slot -- a fork/join, eagerly or under capture"""
+        """train on `slot` | aggregate slot+1, sample into slot+2 -- a fork/join, eagerly or under capture"""
         main = torch.cuda.current_stream()
         self._prep_stream.wait_stream(main)
         try:
             with torch.cuda.stream(self._prep_stream):
                 # programmatic dependent launch stays on for the (critical) training chain only: early-resident
-                # dependents of the preparation chain would hold SM slots the GEMMs need.  Measured per replay:
-                # both on 127 us, both off 110 us, training chain only 106 us (sequential step: 138 us).
-                native.set_pdl(0)
-                native.set_agg_ctas(self.bg_agg_ctas)
-                native.set_background(True)
-                self._prep(1 - slot)
-            native.set_pdl(-1)
-            native.set_agg_ctas(0)
-            native.set_background(False)
-            self._compute(slot, update)
+                # dependents of the preparation chain would hold SM slots the GEMMs need
+                self._background(True)
+                self._aggregate((slot + 1) % self.SLOTS)
+                self._sample((slot + 2) % self.SLOTS)
+            self._background(False)
+            if self._train_stream is not None:            # the critical chain on a high-priority stream (fork/join)
+                self._train_stream.wait_stream(main)
+                with torch.cuda.stream(self._train_stream):
+                    self._compute(slot, update)
+                main.wait_stream(self._train_stream)
+            else:
+                self._compute(slot, update)
         finally:
-            native.set_pdl(-1)
-            native.set_agg_ctas(0)
-            native.set_background(False)
+            self._background(False)
         main.wait_stream(self._prep_stream)
 
     def _capture_pipeline(self):
         side = torch.cuda.Stream(device=self.dev)
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):            # warm-up: allocates both slots, loads modules; no update, cursors restored
+        with torch.cuda.stream(side):            # warm-up: allocates every slot, loads modules; no update, cursors restored
             saved = (self.sample_counter.clone(), self.queue_desc.clone())
-            self._prep(0)
-            self._prep(1)
-            for slot in (0, 1):
+            for slot in range(self.SLOTS):
+                self._sample(slot)
+                self._aggregate(slot)
+            for slot in range(self.SLOTS):
                 self._both(slot, update=False)
                 self.flat_grad.zero_()
             self.sample_counter.copy_(saved[0])
             self.queue_desc.copy_(saved[1])
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(self.dev)
-        for slot in (0, 1):
+        for slot in range(self.SLOTS):
             before = native.launch_count()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._both(slot)
             self._graphs[slot] = g
             self.launches_per_step = native.launch_count() - before
-        self._graph_pair = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph_pair):
-            self._both(0)
-            self._both(1)
+        self._graph_multi = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph_multi):
+            for slot in range(self.SLOTS):
+                self._both(slot)
         self.flat_grad.zero_()
 
     # ---- public ------------------------------------------------------------------------------------
     def prime(self):
-        """Prepare the first queued batch (nothing to train on yet)."""
+        """Fill the pipeline: sample the first two queued batches, aggregate the first (nothing to train on yet)."""
         if self._queue is None:
             raise RuntimeError("set_queue() or feed() a batch first")
         if self.use_graph and self._graphs[0] is None:
             self._capture_pipeline()
         if self._cur is None:
-            self._prep(0)
-            self._mark_fetched()
-            self._cur = 0
+            if self._unfetched() < 2:
+                raise RuntimeError("prime() needs two queued batches (feed() them first)")
+            self._sample(0)
+            self._aggregate(0)
+            self._sample(1)
+            self._mark_fetched(2)
+            self._cur, self._pending, self._agg_done = 0, 2, True
 
     def run(self, n: int = 1) -> torch.Tensor:
-        """n pipelined steps: step i trains on the prepared batch and prepares the next queued one.
-        Returns the device loss of the last trained batch."""
-        if self._cur is None:
+        """n pipelined steps: step i trains on the oldest prepared batch, aggregates the next one and samples the
+        one after from the queue.  Returns the device loss of the last trained batch."""
+        if self._cur is None or self._pending < 2:
             raise RuntimeError("prime() the pipeline first")
+        if self._unfetched() < n:
+            raise RuntimeError(f"run({n}) needs {n} queued batches to sample, {self._unfetched()} fed")
         self._count_steps(n)
         while n > 0:
-            if self.use_graph and self._cur == 0 and n >= 2:
-                self._graph_pair.replay()
-                self._mark_fetched(2)
-                n -= 2
+            if self.use_graph and self._cur == 0 and n >= self.SLOTS:
+                self._graph_multi.replay()
+                self._mark_fetched(self.SLOTS)
+                n -= self.SLOTS
                 continue
             if self.use_graph:
                 self._graphs[self._cur].replay()
@@ -632,36 +665,52 @@ class PipelinedTrainer(SupervisedTrainer):
                 self._both(self._cur)
                 self.launches_per_step = native.launch_count() - before
             self._mark_fetched()
-            self._cur = 1 - self._cur
+            self._cur = (self._cur + 1) % self.SLOTS
             n -= 1
         return self.loss
 
     def flush(self) -> Optional[torch.Tensor]:
-        """Train on the last prepared batch (nothing left to prepare)."""
+        """Drain: sample what is still queued in the ring (at most what the free slots hold), then train on every
+        prepared batch in order (nothing left to prepare beside them)."""
+        if self._queue is self._ring and self._cur is None and self._unfetched() > 0:
+            self._cur, self._pending, self._agg_done = 0, 0, False
+        if self._queue is self._ring and self._cur is not None:
+            while self._unfetched() > 0 and self._pending < self.SLOTS:
+                self._sample((self._cur + self._pending) % self.SLOTS)
+                self._mark_fetched()
+                self._pending += 1
         if self._cur is None:
             return None
-        self._compute(self._cur)
+        while self._pending > 0:
+            if not self._agg_done:
+                self._aggregate(self._cur)
+            self._compute(self._cur)
+            self._cur = (self._cur + 1) % self.SLOTS
+            self._pending -= 1
+            self._agg_done = False
         self._cur = None
         self.check()
         return self.loss
 
-    # one call per batch, on top of the queue: the batch handed over is the NEXT one
-    def submit_device(self, seeds_dev: torch.Tensor) -> Optional[torch.Tensor]:
-        """Hand over the next batch (int32 [b_sz] in HBM).  Trains on the previously submitted batch
-        (returns its device loss) while this one is prepared; the first call only prepares."""
-        self.feed_device(seeds_dev)
+    # one call per batch, on top of the queue: the batch handed over is trained on two calls later
+    def _submitted(self) -> Optional[torch.Tensor]:
         if self._cur is None:
+            if self._unfetched() < 2:
+                return None
             self.prime()
             return None
         return self.run(1)
 
+    def submit_device(self, seeds_dev: torch.Tensor) -> Optional[torch.Tensor]:
+        """Hand over the next batch (int32 [b_sz] in HBM).  Trains on the batch submitted two calls earlier (returns
+        its device loss) while the later ones are prepared; the first two calls only prepare."""
+        self.feed_device(seeds_dev)
+        return self._submitted()
+
     def submit(self, nodes_batch) -> Optional[torch.Tensor]:
         """`submit_device` from a HOST batch (pinned staging + H2D on the copy stream)."""
         self.feed(nodes_batch)
-        if self._cur is None:
-            self.prime()
-            return None
-        return self.run(1)
+        return self._submitted()
 
     def step_device(self, seeds_dev: torch.Tensor) -> torch.Tensor:
         self.submit_device(seeds_dev)

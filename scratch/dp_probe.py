@@ -34,5 +34,5 @@ if hasattr(lib, 'gs_debug_dp_trace_read'):
     buf = (ctypes.c_longlong * 16)()
     lib.gs_debug_dp_trace_read(buf, 16)
     t = list(buf)[:8]
-    names = ['pdl', 'tables', 'epoch+push', 'reduce', 'barrier', 'coef', 'sgd']
+    names = ['pdl', 'epoch', 'push+wait', 'loads+partials', 'barrier', 'coef', 'sgd']
     print('phase cycles (CTA 0): ' + ', '.join(f"{n} {t[i + 1] - t[i]}" for i, n in enumerate(names)) + f"; total {t[7] - t[0]}")

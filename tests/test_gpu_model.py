@@ -323,7 +323,7 @@ def test_pipelined_trainer_matches_plain_trainer(M):
         if queue:                                # device-resident queue: prime, 2+1+3 steps (pair graph and single graphs), flush
             tr.set_queue(torch.from_numpy(np.stack(batches).astype(np.int32)).to(dev))
             tr.prime()
-            for n_steps in (2, 1, 3):
+            for n_steps in (3, 1, 1):            # the 3-step graph, then two single-step graphs; 2 batches stay in flight
                 tr.run(n_steps)
             tr.flush()
             tr.dp.status()
@@ -346,7 +346,9 @@ def test_pipelined_trainer_matches_plain_trainer(M):
                                    (PipelinedTrainer, False, True)):
         l, p = run(kind, use_graph, queue)
         if l is not None:
-            assert np.allclose(l, base_l, rtol=1e-5, atol=1e-6), (kind.__name__, use_graph, l, base_l)
+            # submit() returns the loss of the batch handed over two calls earlier; flush() the last batch's
+            want = base_l if kind is SupervisedTrainer else base_l[:len(l) - 1] + [base_l[-1]]
+            assert np.allclose(l, want, rtol=1e-5, atol=1e-6), (kind.__name__, use_graph, l, base_l)
         for a, b in zip(p, base_p):
             assert rel(a, b) <= 1e-5, (kind.__name__, use_graph, queue)
 
