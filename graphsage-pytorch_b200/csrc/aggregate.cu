@@ -28,12 +28,23 @@ constexpr int kAggCtasPerSM = 5;      // MEAN: 48 registers -> 5 CTAs = 40 warps
 // at 88K rows; 6 loads/lane at 40 warps/SM = 0.565 and 0.82).  L2 prefetch of looked-ahead rows
 // (prefetch.global.L2) and cp.async rings were measured slower than this.  With a grid that covers
 // every row the same code is the one-row-per-warp kernel (GS_AGG_GRID=rows).
-template <int MODE>
-__global__ void __launch_bounds__(kAggWarps * 32, MODE == GS_AGG_MEAN ? kAggCtasPerSM : 3)
+__device__ __forceinline__ float4 tf32_lo4(const float4& v) {      // x - trunc_tf32(x): the low half of the 3-term split
+  return make_float4(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u), v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u),
+                     v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u), v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
+}
+
+// XOUT: the kernel writes the SageLayer's whole input row  X[r] = [ table[self_nodes[r]] | agg[r] ]  (self part at
+// column 0, aggregate at column agg_off; src/models.py:265 + :260 -- the operands torch.cat joins at :217) and, when
+// out_lo is given, the low halves x - trunc_tf32(x) of both parts in a second buffer of the same layout.  The layer-1
+// GEMMs of a train step then read dense operands by TMA instead of gathering 400-byte rows of the feature table and
+// splitting them on the critical chain; the self row is loaded with the first gather batch.
+template <int MODE, bool XOUT>
+__global__ void __launch_bounds__(kAggWarps * 32, MODE == GS_AGG_MEAN ? (XOUT ? kAggCtasPerSM - 1 : kAggCtasPerSM) : 3)
 agg_fwd_kernel(const float* __restrict__ table, uint32_t ld_bytes, int dim4,
                const int32_t* __restrict__ nbr, int stride, const int32_t* __restrict__ cnt,
                const int32_t* __restrict__ num_rows_dev, int max_rows,
-               float* __restrict__ out, int64_t ld_out, int32_t* __restrict__ argmax, int64_t ld_arg) {
+               float* __restrict__ out, int64_t ld_out, int32_t* __restrict__ argmax, int64_t ld_arg,
+               const int32_t* __restrict__ self_nodes, int agg_off, float* __restrict__ out_lo) {
   pdl_sync();
   const int lane = threadIdx.x & 31;
   const int W = gridDim.x * kAggWarps;
@@ -41,19 +52,22 @@ agg_fwd_kernel(const float* __restrict__ table, uint32_t ld_bytes, int dim4,
   const float qnan = __int_as_float(0x7fc00000);
   const char* tbase = reinterpret_cast<const char*>(table);
 
-  int n_next = 0, v_next = -1;                    // count and this lane's id of the row the warp handles next
+  int n_next = 0, v_next = -1, s_next = -1;       // count, this lane's id and the node id of the row the warp handles next
   if (gw < max_rows) {
     n_next = __ldg(cnt + gw);
     if (lane < stride) v_next = __ldg(nbr + static_cast<int64_t>(gw) * stride + lane);
+    if (XOUT && self_nodes != nullptr) s_next = __ldg(self_nodes + gw);
   }
   const int rows = live_rows(num_rows_dev, max_rows);
   for (int r = gw; r < rows; r += W) {
     const int32_t* row_ids = nbr + static_cast<int64_t>(r) * stride;
     const int n = min(n_next, stride);
     const int mine_raw = v_next;
+    const int self_id = s_next;
     if (r + W < max_rows) {                       // next row's indices fly beside this row's gathers
       n_next = __ldg(cnt + r + W);
       if (lane < stride) v_next = __ldg(row_ids + static_cast<int64_t>(W) * stride + lane);
+      if (XOUT && self_nodes != nullptr) s_next = __ldg(self_nodes + r + W);
     }
     const float inv = 1.0f / static_cast<float>(n);         // n == 0 -> inf; 0 * inf = NaN as in the reference (0/0)
     for (int cbase = 0; cbase < dim4; cbase += 32) {
@@ -63,10 +77,12 @@ agg_fwd_kernel(const float* __restrict__ table, uint32_t ld_bytes, int dim4,
       float4 acc = (MODE == GS_AGG_MEAN) ? make_float4(0.f, 0.f, 0.f, 0.f)
                                          : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
       int4 arg = make_int4(-1, -1, -1, -1);
+      bool self_todo = XOUT && self_id >= 0;
+      const int64_t xoff = static_cast<int64_t>(r) * ld_out + 4 * c4;      // addresses are formed at the stores (registers)
       for (int jc = 0; jc < n; jc += 32) {                  // lists longer than a warp: compatibility callers only
         const int mine = jc == 0 ? (lane < n ? mine_raw : -1) : (jc + lane < n ? __ldg(row_ids + jc + lane) : -1);
         const int here = min(32, n - jc);
-        for (int j0 = 0; j0 < here; j0 += kBatch) {         // two passes for fan-out 10 (+ self)
+        for (int j0 = 0; j0 < here; j0 += kBatch) {         // two passes for fan-out 10
           float4 v[kBatch];
           int id[kBatch];
 #pragma unroll
@@ -76,6 +92,10 @@ agg_fwd_kernel(const float* __restrict__ table, uint32_t ld_bytes, int dim4,
             const char* src = col + static_cast<size_t>(static_cast<uint32_t>(id[u])) * ld_bytes;
             v[u] = ldg_stream_f4_if<(MODE == GS_AGG_MEAN) ? 0u : 0xff800000u>(src, id[u] >= 0);   // 0 / -inf when off
           }
+          float4 sv;
+          const bool self_now = XOUT && self_todo;          // the self row flies with the first batch
+          if (self_now)
+            sv = ldg_stream_f4_if<0u>(col + static_cast<size_t>(static_cast<uint32_t>(self_id)) * ld_bytes, active);
 #pragma unroll
           for (int u = 0; u < kBatch; ++u) {
             if (MODE == GS_AGG_MEAN) {
@@ -87,7 +107,19 @@ agg_fwd_kernel(const float* __restrict__ table, uint32_t ld_bytes, int dim4,
               if (v[u].w > acc.w) { acc.w = v[u].w; arg.w = id[u]; }
             }
           }
+          if (self_now) {
+            if (active) {
+              *reinterpret_cast<float4*>(out + xoff) = sv;
+              if (out_lo != nullptr) *reinterpret_cast<float4*>(out_lo + xoff) = tf32_lo4(sv);
+            }
+            self_todo = false;
+          }
         }
+      }
+      if (XOUT && self_todo && active) {           // a row without neighbours still has its self part
+        const float4 sv = ldg_stream_f4(reinterpret_cast<const float*>(col + static_cast<size_t>(static_cast<uint32_t>(self_id)) * ld_bytes));
+        *reinterpret_cast<float4*>(out + xoff) = sv;
+        if (out_lo != nullptr) *reinterpret_cast<float4*>(out_lo + xoff) = tf32_lo4(sv);
       }
       if (active) {
         if (MODE == GS_AGG_MEAN) {
@@ -95,7 +127,8 @@ agg_fwd_kernel(const float* __restrict__ table, uint32_t ld_bytes, int dim4,
         } else if (n == 0) {
           acc = make_float4(qnan, qnan, qnan, qnan);
         }
-        *reinterpret_cast<float4*>(out + static_cast<int64_t>(r) * ld_out + 4 * c4) = acc;
+        *reinterpret_cast<float4*>(out + xoff + (XOUT ? agg_off : 0)) = acc;
+        if (XOUT && out_lo != nullptr) *reinterpret_cast<float4*>(out_lo + xoff + agg_off) = tf32_lo4(acc);
         if (MODE == GS_AGG_MAX && argmax != nullptr)
           *reinterpret_cast<int4*>(argmax + static_cast<int64_t>(r) * ld_arg + 4 * c4) = arg;
       }
@@ -296,6 +329,37 @@ using namespace gs;
 
 extern "C" void gs_set_agg_ctas(int32_t ctas_per_sm) { g_agg_ctas = ctas_per_sm > 0 ? ctas_per_sm : 0; }
 
+extern "C" int gs_agg_fwd_x(const float* table, int64_t ld, int32_t dim, const int32_t* nbr, int32_t stride,
+                            const int32_t* cnt, const int32_t* self_nodes, const int32_t* num_rows_dev, int32_t max_rows,
+                            int32_t mode, float* out_x, int64_t ld_x, int32_t agg_off, float* out_x_lo,
+                            gs_stream_t stream) {
+  if (!table || !nbr || !cnt || !out_x || dim < 1 || stride < 1 || max_rows < 0 || agg_off < 0) return GS_ERR_BAD_ARG;
+  if (mode != GS_AGG_MEAN && mode != GS_AGG_MAX) return GS_ERR_BAD_ARG;
+  const int dim4 = (dim + 3) / 4;
+  if (self_nodes && agg_off < 4 * dim4) return GS_ERR_BAD_ARG;            // the self part occupies columns [0, 4*dim4)
+  if ((ld & 3) || (ld_x & 3) || (agg_off & 3) || ld < 4 * dim4 || ld_x < agg_off + 4 * dim4) return GS_ERR_ALIGNMENT;
+  if (!aligned16(table) || !aligned16(out_x) || (out_x_lo && !aligned16(out_x_lo))) return GS_ERR_ALIGNMENT;
+  if (max_rows == 0) return GS_OK;
+  if (ld * 4 > 0xffffffffLL) return GS_ERR_UNSUPPORTED;
+  int blocks = (max_rows + kAggWarps - 1) / kAggWarps;
+  int per_sm = mode == GS_AGG_MEAN ? kAggCtasPerSM - 1 : 3;       // the X variant: 64 registers, 4 CTAs = 32 warps per SM
+  if (g_agg_ctas > 0 && g_agg_ctas < per_sm) per_sm = g_agg_ctas;
+  const int persistent = kNumSMs * per_sm;
+  if (agg_grid_persistent() && blocks > persistent) blocks = persistent;
+  const uint32_t ld_bytes = static_cast<uint32_t>(ld * 4);
+  cudaStream_t st = as_stream(stream);
+  if (mode == GS_AGG_MEAN) {
+    set_kernel_carveout(reinterpret_cast<const void*>(agg_fwd_kernel<GS_AGG_MEAN, true>), background_launches());
+    launch(agg_fwd_kernel<GS_AGG_MEAN, true>, blocks, kAggWarps * 32, 0, st, table, ld_bytes, dim4, nbr, stride, cnt,
+           num_rows_dev, max_rows, out_x, ld_x, nullptr, 0, self_nodes, agg_off, out_x_lo);
+  } else {
+    set_kernel_carveout(reinterpret_cast<const void*>(agg_fwd_kernel<GS_AGG_MAX, true>), background_launches());
+    launch(agg_fwd_kernel<GS_AGG_MAX, true>, blocks, kAggWarps * 32, 0, st, table, ld_bytes, dim4, nbr, stride, cnt,
+           num_rows_dev, max_rows, out_x, ld_x, nullptr, 0, self_nodes, agg_off, out_x_lo);
+  }
+  return finish_launch();
+}
+
 extern "C" int gs_agg_fwd(const float* table, int64_t ld, int32_t dim, const int32_t* nbr, int32_t stride,
                           const int32_t* cnt, const int32_t* num_rows_dev, int32_t max_rows, int32_t mode,
                           float* out, int64_t ld_out, int32_t* argmax, int64_t ld_arg, gs_stream_t stream) {
@@ -314,15 +378,15 @@ extern "C" int gs_agg_fwd(const float* table, int64_t ld, int32_t dim, const int
   const int persistent = kNumSMs * per_sm;
   if (agg_grid_persistent() && blocks > persistent) blocks = persistent;
   const uint32_t ld_bytes = static_cast<uint32_t>(ld * 4);
-  set_kernel_carveout(mode == GS_AGG_MEAN ? reinterpret_cast<const void*>(agg_fwd_kernel<GS_AGG_MEAN>)
-                                          : reinterpret_cast<const void*>(agg_fwd_kernel<GS_AGG_MAX>),
+  set_kernel_carveout(mode == GS_AGG_MEAN ? reinterpret_cast<const void*>(agg_fwd_kernel<GS_AGG_MEAN, false>)
+                                          : reinterpret_cast<const void*>(agg_fwd_kernel<GS_AGG_MAX, false>),
                       background_launches());
   if (mode == GS_AGG_MEAN)
-    launch(agg_fwd_kernel<GS_AGG_MEAN>, blocks, kAggWarps * 32, 0, st, 
-        table, ld_bytes, dim4, nbr, stride, cnt, num_rows_dev, max_rows, out, ld_out, nullptr, 0);
+    launch(agg_fwd_kernel<GS_AGG_MEAN, false>, blocks, kAggWarps * 32, 0, st,
+        table, ld_bytes, dim4, nbr, stride, cnt, num_rows_dev, max_rows, out, ld_out, nullptr, 0, nullptr, 0, nullptr);
   else
-    launch(agg_fwd_kernel<GS_AGG_MAX>, blocks, kAggWarps * 32, 0, st, 
-        table, ld_bytes, dim4, nbr, stride, cnt, num_rows_dev, max_rows, out, ld_out, argmax, ld_arg);
+    launch(agg_fwd_kernel<GS_AGG_MAX, false>, blocks, kAggWarps * 32, 0, st,
+        table, ld_bytes, dim4, nbr, stride, cnt, num_rows_dev, max_rows, out, ld_out, argmax, ld_arg, nullptr, 0, nullptr);
   return finish_launch();
 }
 

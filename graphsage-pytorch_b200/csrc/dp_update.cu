@@ -41,6 +41,7 @@ struct DpPeers {
 };
 struct DpSegs {
   float* param[kDpMaxSegs];
+  float* param_lo[kDpMaxSegs];     // nullable: receives p - trunc_tf32(p) of the updated parameter (K4's split operand)
   long long off[kDpMaxSegs];       // offset of the tensor's gradient inside the flat buffer (multiple of 4)
   long long numel[kDpMaxSegs];
   int group[kDpMaxSegs];           // clip group (model) of the tensor
@@ -71,6 +72,14 @@ __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
+}
+
+__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+__global__ void split_lo_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n) {
+  pdl_sync();
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x)
+    dst[i] = tf32_lo(src[i]);
 }
 
 __device__ __forceinline__ int seg_of(const DpSegs& s, long long elem) {
@@ -255,9 +264,14 @@ dp_update_kernel(float* __restrict__ flat, long long n_total, const __grid_const
         float4 w = w_have ? *w_have : *reinterpret_cast<float4*>(p);
         w.x = fmaf(-step, g.x, w.x); w.y = fmaf(-step, g.y, w.y); w.z = fmaf(-step, g.z, w.z); w.w = fmaf(-step, g.w, w.w);
         *reinterpret_cast<float4*>(p) = w;
+        if (segs.param_lo[k] != nullptr)
+          *reinterpret_cast<float4*>(segs.param_lo[k] + o) = make_float4(tf32_lo(w.x), tf32_lo(w.y), tf32_lo(w.z), tf32_lo(w.w));
       } else {
         const float gv[4] = {g.x, g.y, g.z, g.w};
-        for (int j = 0; j < 4 && j < left; ++j) p[j] = fmaf(-step, gv[j], p[j]);
+        for (int j = 0; j < 4 && j < left; ++j) {
+          p[j] = fmaf(-step, gv[j], p[j]);
+          if (segs.param_lo[k] != nullptr) segs.param_lo[k][o + j] = tf32_lo(p[j]);
+        }
       }
     }
     flat4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -298,7 +312,7 @@ extern "C" int gs_dp_allreduce_clip_sgd(float* flat_grad, int64_t n_total, void*
                                         int32_t world, float* const* seg_params_host, const int64_t* seg_offsets_host,
                                         const int64_t* seg_numels_host, const int32_t* seg_groups_host, int32_t num_segs,
                                         float max_norm, float lr, void* state, uint64_t timeout_ns,
-                                        int64_t* step_counter, gs_stream_t stream) {
+                                        int64_t* step_counter, float* const* seg_params_lo_host, gs_stream_t stream) {
   if (!flat_grad || !state || n_total < 4 || (n_total & 3) || !aligned16(flat_grad)) return GS_ERR_BAD_ARG;
   if (world < 1 || world > kDpMaxWorld || rank < 0 || rank >= world) return GS_ERR_BAD_ARG;
   if (num_segs < 1 || num_segs > kDpMaxSegs || !seg_params_host || !seg_offsets_host || !seg_numels_host) return GS_ERR_BAD_ARG;
@@ -317,6 +331,8 @@ extern "C" int gs_dp_allreduce_clip_sgd(float* flat_grad, int64_t n_total, void*
   int groups = 1;
   for (int i = 0; i < num_segs; ++i) {
     segs.param[i] = seg_params_host[i];
+    segs.param_lo[i] = seg_params_lo_host ? seg_params_lo_host[i] : nullptr;
+    if (segs.param_lo[i] && !aligned16(segs.param_lo[i])) return GS_ERR_ALIGNMENT;
     segs.off[i] = seg_offsets_host[i];
     segs.numel[i] = seg_numels_host[i];
     segs.group[i] = seg_groups_host ? seg_groups_host[i] : 0;
@@ -335,6 +351,16 @@ extern "C" int gs_dp_allreduce_clip_sgd(float* flat_grad, int64_t n_total, void*
                                                               static_cast<DpState*>(state), max_norm, lr,
                                                               timeout_ns ? timeout_ns : 2000000000ULL,
                                                               reinterpret_cast<long long*>(step_counter));
+  return finish_launch();
+}
+
+// dst[i] = src[i] - trunc_tf32(src[i]): the low half of the 3-term tf32 split of a weight (kept current by the update
+// kernel afterwards, see seg_params_lo_host)
+extern "C" int gs_split_lo(const float* src, float* dst, int64_t n, gs_stream_t stream) {
+  if (!src || !dst || n < 0) return GS_ERR_BAD_ARG;
+  if (n == 0) return GS_OK;
+  const int blocks = static_cast<int>(n / 256 + 1 < 1184 ? n / 256 + 1 : 1184);
+  launch(split_lo_kernel, blocks, 256, 0, as_stream(stream), src, dst, static_cast<long long>(n));
   return finish_launch();
 }
 

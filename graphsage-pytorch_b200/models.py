@@ -182,7 +182,8 @@ class SageLayer(nn.Module):
 class _Frontier:
     """Per-layer device state of one forward pass (rows = destination nodes of that layer)."""
     __slots__ = ("nodes", "num_rows", "rows_max", "stride", "nbr", "cnt", "nbr_idx", "self_idx", "agg", "argmax", "h",
-                 "table_in", "dim_in", "dz", "gh")
+                 "table_in", "dim_in", "dz", "gh", "x", "x_lo")
+    # x / x_lo: layer 1's dense input rows [self | agg] and their low tf32 halves (GraphSage._run_agg1(dense_x=True)).
     # dz: d(pre-activation) of this layer (A operand of its weight-gradient GEMM), gh: gradient w.r.t. its output h;
     # both only exist on the fused-top path of the trainers.  Buffers survive from one forward to the next when the
     # frontiers are reused (`_run_prep(reuse=...)`): static addresses for captured steps.
@@ -195,6 +196,7 @@ class _Frontier:
         """Take over the weight-dependent buffers of the frontier this one replaces (same static shapes)."""
         self.h, self.dz, self.gh = old.h, old.dz, old.gh
         self.agg, self.argmax = old.agg, old.argmax
+        self.x, self.x_lo = old.x, old.x_lo
         if first_layer and not isinstance(old.table_in, ShardedTable) and old.self_idx is None:
             self.table_in = old.table_in                 # the fp32 self rows a sharded gather emits (see _run_agg1)
 
@@ -332,9 +334,9 @@ class GraphSage(nn.Module):
 
     def _run_prep(self, nodes_dev: torch.Tensor, injected=None, offset_dev: Optional[torch.Tensor] = None,
                   reuse: Optional[List[_Frontier]] = None, num_rows: Optional[torch.Tensor] = None,
-                  queue_desc: Optional[torch.Tensor] = None) -> List[_Frontier]:
+                  queue_desc: Optional[torch.Tensor] = None, dense_x: bool = False) -> List[_Frontier]:
         """The weight-independent half of a forward pass: `_run_sample` then `_run_agg1`."""
-        return self._run_agg1(self._run_sample(nodes_dev, injected, offset_dev, reuse, num_rows, queue_desc))
+        return self._run_agg1(self._run_sample(nodes_dev, injected, offset_dev, reuse, num_rows, queue_desc), dense_x)
 
     def _run_sample(self, nodes_dev: torch.Tensor, injected=None, offset_dev: Optional[torch.Tensor] = None,
                     reuse: Optional[List[_Frontier]] = None, num_rows: Optional[torch.Tensor] = None,
@@ -405,15 +407,43 @@ class GraphSage(nn.Module):
                 rows_max = min(rows_max * (fr.stride + 1), max(csr.num_nodes, 1))
             else:       # layer 1 gathers straight from the feature table by node id: no U0, no remap
                 fr.nbr_idx, fr.self_idx = fr.nbr, nodes
+                # what _run_agg1 will leave behind, set here as well: under CUDA-graph replay the python objects of
+                # the last captured sampling stand for every later batch of the slot
+                fr.dim_in = self.input_size
+                if isinstance(table, ShardedTable):
+                    fr.self_idx = None                      # K4 reads the fp32 self rows the gather emits, in row order
+                elif fr.x is not None:
+                    self._bind_dense(fr)                    # dense input rows from an earlier _run_agg1(dense_x=True)
+                else:
+                    fr.table_in = table
             layers[l] = fr
         return layers[1:]
 
-    def _run_agg1(self, layers: List[_Frontier]) -> List[_Frontier]:
+    def _bind_dense(self, fr: _Frontier):
+        """Layer 1 reads its operands from the dense rows fr.x = [self | agg] (views, identity row index)."""
+        f = self.input_size
+        fr.table_in, fr.self_idx = (None, None) if self.gcn else (fr.x[:, :f], None)
+        fr.agg, fr.argmax = (fr.x if self.gcn else fr.x[:, f:]), None
+
+    def dense_x_ok(self) -> bool:
+        """Whether layer 1 can take dense input rows (gs_agg_fwd_x): a plain fp32 table whose width is a multiple of 4."""
+        _, table, _ = self._state()
+        return not isinstance(table, ShardedTable) and self.input_size % 4 == 0
+
+    def _run_agg1(self, layers: List[_Frontier], dense_x: bool = False) -> List[_Frontier]:
         """The layer-1 aggregation of the raw features (src/models.py:260, index 1) on sampled frontiers: the
-        HBM-bound half of the preparation.  Output buffers a frontier already owns are overwritten in place."""
+        HBM-bound half of the preparation.  Output buffers a frontier already owns are overwritten in place.
+        `dense_x`: write the layer's whole input row [self | agg] and its low tf32 halves (ops.agg_fwd_x) -- a train
+        step's layer-1 GEMMs then read dense operands by TMA instead of gathering feature rows on the critical chain."""
         csr, table, dev = self._state()
         mode = native.AGG_MEAN if self.agg_func == 'MEAN' else native.AGG_MAX
         fr = layers[0]
+        if dense_x and self.dense_x_ok():
+            fr.dim_in = self.input_size
+            fr.x, fr.x_lo = ops.agg_fwd_x(table, self.input_size, fr.nbr, fr.stride, fr.cnt, None if self.gcn else fr.nodes,
+                                          fr.num_rows, fr.rows_max, mode, x=fr.x, x_lo=fr.x_lo)
+            self._bind_dense(fr)
+            return layers
         self_rows_buf = fr.table_in if (fr.table_in is not None and fr.table_in is not table) else None
         fr.table_in, fr.dim_in = table, self.input_size
         if isinstance(table, ShardedTable):
@@ -429,7 +459,8 @@ class GraphSage(nn.Module):
         return layers
 
     def _run_compute(self, layers: List[_Frontier], weights: Sequence[torch.Tensor], upto: Optional[int] = None,
-                     zero_grad_of_last: Optional[torch.Tensor] = None) -> List[_Frontier]:
+                     zero_grad_of_last: Optional[torch.Tensor] = None,
+                     weights_lo: Optional[Sequence[Optional[torch.Tensor]]] = None) -> List[_Frontier]:
         """The weight-dependent half (src/models.py:255-267): SageLayer GEMM of every layer and the
         aggregations above layer 1.  `upto` (default: all layers): stop after that many layers -- a trainer that
         runs the top layer fused with the loss (ops.sage_top_sup) computes the layers below it here.
@@ -447,7 +478,9 @@ class GraphSage(nn.Module):
                                                 fr.rows_max, mode, out=fr.agg, argmax=fr.argmax)
             fr.h = ops.sage_gemm_fwd(None if self.gcn else fr.table_in, fr.self_idx, fr.agg, fr.dim_in, weights[l - 1],
                                      self.out_size, self.gcn, fr.num_rows, fr.rows_max, True, prec, out=fr.h,
-                                     zero_out=zero_grad_of_last if l == L else None)
+                                     zero_out=zero_grad_of_last if l == L else None,
+                                     x_lo=fr.x_lo if l == 1 else None,
+                                     weight_lo=weights_lo[l - 1] if weights_lo is not None else None)
         return layers
 
     def _run_backward(self, layers: List[_Frontier], grad_out: torch.Tensor, weights, needs,

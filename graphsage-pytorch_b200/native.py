@@ -46,7 +46,9 @@ _SIGNATURES = {
     "gs_set_background": (None, [_I]),
     "gs_agg_bwd": (_I, [_P, _L, _P, _L, _I, _P, _I, _P, _P, _P, _L, _P, _I, _I, _P, _L, _P, _L, _P]),
     "gs_sage_gemm_fwd": (_I, [_P, _L, _P, _P, _L, _I, _P, _L, _I, _I, _P, _I, _P, _L, _I, _I, _P]),
-    "gs_sage_gemm_fwd_ex": (_I, [_P, _L, _P, _P, _L, _I, _P, _L, _I, _I, _P, _I, _P, _L, _I, _I, _P, _L, _P]),
+    "gs_sage_gemm_fwd_ex": (_I, [_P, _L, _P, _P, _L, _I, _P, _L, _I, _I, _P, _I, _P, _L, _I, _I, _P, _L, _P, _P, _P]),
+    "gs_agg_fwd_x": (_I, [_P, _L, _I, _P, _I, _P, _P, _P, _I, _I, _P, _L, _I, _P, _P]),
+    "gs_split_lo": (_I, [_P, _P, _L, _P]),
     "gs_sage_top_workspace_bytes": (_SZ, []),
     "gs_sage_top_sup": (_I, [_P, _L, _P, _I, _P, _P, _P, _I, _P, _L, _I, _I, _I, _P, _P, _I, _P, _P, _P, _L, _P, _L, _P, _L,
                              _P, _P, _P, _P, _P, _L, _P, _SZ, _I, _P]),
@@ -63,7 +65,7 @@ _SIGNATURES = {
     "gs_dp_state_bytes": (_SZ, []),
     "gs_dp_region_bytes": (_SZ, [_L, _I]),
     "gs_dp_region_recv_offset": (_SZ, []),
-    "gs_dp_allreduce_clip_sgd": (_I, [_P, _L, _P, _I, _I, _P, _P, _P, _P, _I, _F, _F, _P, _U64, _P, _P]),
+    "gs_dp_allreduce_clip_sgd": (_I, [_P, _L, _P, _I, _I, _P, _P, _P, _P, _I, _F, _F, _P, _U64, _P, _P, _P]),
     "gs_dp_status": (_I, [_P, _P, _P, _P, _P]),
     "gs_peer_alloc": (_I, [_SZ, _P]),
     "gs_peer_free": (_I, [_P]),

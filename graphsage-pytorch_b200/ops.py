@@ -167,8 +167,34 @@ def agg_bwd(grad_agg, grad_self, dim: int, nbr, stride: int, cnt, self_idx, argm
 # ----------------------------------------------------------------------------------------------
 # K4
 # ----------------------------------------------------------------------------------------------
+def agg_fwd_x(table, dim: int, nbr, stride: int, cnt, self_nodes, num_rows, max_rows: int, mode: int, x=None, x_lo=None,
+              want_lo: bool = True):
+    """K3 writing the layer's dense input row X = [table[self] | agg] (gs_agg_fwd_x) and its low halves.
+    self_nodes None (gcn): X = agg only.  Returns (x [max_rows, K], x_lo or None) with K = pad4(dim) * (1 or 2)."""
+    native.require_cuda(table, "table")
+    d4 = pad4(dim)
+    k = d4 if self_nodes is None else 2 * d4
+    kp = (k + 31) & ~31          # row pitch: a multiple of 128 bytes, so the 128-byte pieces a TMA box reads are whole lines
+    if x is None:
+        x = torch.empty((max_rows, kp), dtype=F32, device=table.device)[:, :k]
+    if x_lo is None and want_lo:
+        x_lo = torch.empty((max_rows, kp), dtype=F32, device=table.device)[:, :k]
+    check(_lib().gs_agg_fwd_x(ptr(table), table.stride(0), dim, ptr(nbr), stride, ptr(cnt), ptr(self_nodes), ptr(num_rows),
+                              max_rows, mode, ptr(x), x.stride(0), 0 if self_nodes is None else d4, ptr(x_lo), stream()),
+          "gs_agg_fwd_x")
+    return x, x_lo
+
+
+def split_lo(src, dst=None):
+    """dst = src - trunc_tf32(src) (the low half of K4's 3-term split); the fused update kernel keeps it current."""
+    if dst is None:
+        dst = torch.empty_like(src)
+    check(_lib().gs_split_lo(ptr(src), ptr(dst), src.numel(), stream()), "gs_split_lo")
+    return dst
+
+
 def sage_gemm_fwd(self_table, self_idx, agg, dim: int, weight, out_dim: int, gcn: bool, num_rows, max_rows: int,
-                  relu: bool = True, precision: int = native.PREC_FP32, out=None, zero_out=None):
+                  relu: bool = True, precision: int = native.PREC_FP32, out=None, zero_out=None, x_lo=None, weight_lo=None):
     """src/models.py:215-219 -> out [max_rows, pad4(out_dim)].  `zero_out` (optional, same shape as out) is
     zero-filled on the way: the buffer the backward of the layer above scatters d(out) into."""
     native.require_cuda(agg, "agg")
@@ -179,7 +205,8 @@ def sage_gemm_fwd(self_table, self_idx, agg, dim: int, weight, out_dim: int, gcn
     check(_lib().gs_sage_gemm_fwd_ex(ptr(self_table), self_table.stride(0) if self_table is not None else 0, ptr(self_idx),
                                      ptr(agg), agg.stride(0), dim, ptr(weight), weight.stride(0), out_dim, int(gcn),
                                      ptr(num_rows), max_rows, ptr(out), out.stride(0), int(relu), precision,
-                                     ptr(zero_out), zero_out.stride(0) if zero_out is not None else 0, stream()),
+                                     ptr(zero_out), zero_out.stride(0) if zero_out is not None else 0, ptr(x_lo),
+                                     ptr(weight_lo), stream()),
           "gs_sage_gemm_fwd")
     return out
 

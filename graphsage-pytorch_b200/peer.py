@@ -149,7 +149,7 @@ class DpExchange:
 
     def __init__(self, flat_grad: torch.Tensor, params: Sequence[torch.Tensor], offsets: Sequence[int],
                  groups: Sequence[int], *, world: int = 1, rank: int = 0, group=None, timeout_s: float = 10.0,
-                 region_ptrs: Optional[Sequence[int]] = None):
+                 region_ptrs: Optional[Sequence[int]] = None, params_lo: Optional[Sequence[Optional[torch.Tensor]]] = None):
         lib = native.load()
         self.lib, self.flat, self.world, self.rank = lib, flat_grad, int(world), int(rank)
         native.require_cuda(flat_grad, "flat gradient")
@@ -160,6 +160,11 @@ class DpExchange:
         self._o = (ctypes.c_int64 * n)(*[int(o) for o in offsets])
         self._n = (ctypes.c_int64 * n)(*[int(p.numel()) for p in params])
         self._g = (ctypes.c_int32 * n)(*[int(g) for g in groups])
+        # low halves p - trunc_tf32(p) of selected parameters, rewritten by the update (K4's pre-split weight operand)
+        self._params_lo = list(params_lo) if params_lo is not None else None
+        self._plo = None
+        if self._params_lo is not None:
+            self._plo = (ctypes.c_void_p * n)(*[(t.data_ptr() if t is not None else None) for t in self._params_lo])
         self.num_segs = n
         self.state = torch.zeros((int(lib.gs_dp_state_bytes()),), dtype=torch.uint8, device=flat_grad.device)
         self.timeout_ns = int(timeout_s * 1e9)
@@ -179,7 +184,7 @@ class DpExchange:
                                                 self._p, self._o, self._n, self._g, self.num_segs, float(max_norm),
                                                 float(lr), self.state.data_ptr(), self.timeout_ns,
                                                 step_counter.data_ptr() if step_counter is not None else None,
-                                                native.stream()),
+                                                self._plo, native.stream()),
               "gs_dp_allreduce_clip_sgd")
 
     def status(self):

@@ -213,6 +213,13 @@ class SupervisedTrainer:
             native.require_cuda(p, "parameters")
         # one flat gradient buffer (single allreduce), views per tensor
         params = self.weights + [self.cls_w, self.cls_b]
+        if world_size > 1:
+            # replicas must start identical (the exchange only averages gradients): rank 0's parameters win
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                for p in params:
+                    dist.broadcast(p.data, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0,
+                                   group=process_group)
         offs, total = flat_layout([tuple(p.shape) for p in params])
         self.flat_grad = torch.zeros((total,), dtype=torch.float32, device=dev)
         self.grads = [self.flat_grad[o:o + p.numel()].view_as(p) for o, p in zip(offs, params)]
@@ -224,17 +231,22 @@ class SupervisedTrainer:
             raise ValueError("exchange must be 'peer' (fused NVLink kernel) or 'nccl'")
         self.exchange = exchange
         self.dp: Optional[DpExchange] = None
+        # Layer 1 on DENSE operands (GS_DENSE_X1=1, off by default): the aggregation writes the layer's input rows
+        # [self | agg] and their low tf32 halves (ops.agg_fwd_x), the fused update keeps W1's low half current, and the
+        # forward GEMM is fed by TMA alone (csrc/sage_gemm_tma.cu).  Measured at the headline configuration: the GEMM
+        # drops from 13.8 to 10.1 us, but the aggregation moves 66 MB instead of 50 (18.5 us instead of 11.5), outlasts
+        # the GEMM it hides behind and keeps the top-layer kernel's CTAs off the SMs: 73.9 us per step against 66.5 with
+        # the self rows gathered inside the GEMMs (profiles/r2_dense_x1_sweep.txt).
+        self.dense_x1 = (os.environ.get("GS_DENSE_X1", "0") == "1" and exchange == "peer" and model.dense_x_ok()
+                         and _PRECISIONS[model.precision] != native.PREC_FP32)
+        self.weights_lo: List[Optional[torch.Tensor]] = [None] * n_sage
+        if self.dense_x1:
+            self.weights_lo[0] = ops.split_lo(self.weights[0].data)
         if exchange == "peer":
             # clip groups follow src/utils.py:185-186: model 0 = graphSage, model 1 = classification
             self.dp = DpExchange(self.flat_grad, [p.data for p in params], offs, [0] * n_sage + [1, 1],
-                                 world=world_size, rank=rank, group=process_group)
-        if world_size > 1:
-            # replicas must start identical (the exchange only averages gradients): rank 0's parameters win
-            import torch.distributed as dist
-            if dist.is_available() and dist.is_initialized():
-                for p in params:
-                    dist.broadcast(p.data, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0,
-                                   group=process_group)
+                                 world=world_size, rank=rank, group=process_group,
+                                 params_lo=self.weights_lo + [None, None])
         #: poll the exchange's sticky status word every this many steps (0 = only at flush()/check()); a timed-out
         #: peer wait would otherwise leave the ranks training different weights silently
         self.status_every = 256
@@ -278,7 +290,7 @@ class SupervisedTrainer:
         if below.gh is None:         # gradient w.r.t. the output of the layer below; zero-filled by that layer's GEMM
             below.gh = torch.empty((below.rows_max, H), dtype=torch.float32, device=self.dev)
         g_below = below.gh
-        m._run_compute(layers, weights, upto=L - 1, zero_grad_of_last=g_below)
+        m._run_compute(layers, weights, upto=L - 1, zero_grad_of_last=g_below, weights_lo=self.weights_lo)
         top.table_in, top.dim_in = below.h, H
         top.h, top.agg, top.dz = ops.sage_top_sup(below.h, top.nbr_idx, top.stride, top.cnt, top.self_idx, top.num_rows,
                                                   top.rows_max, weights[L - 1], m.gcn, self.cls_w.detach(),
@@ -310,7 +322,7 @@ class SupervisedTrainer:
         m = self.model
         n_sage = len(self.weights)
         scatter_bufs, zeroed = _zero_beside(self._side, self.loss, m, layers)
-        layers = m._run_compute(layers, weights)
+        layers = m._run_compute(layers, weights, weights_lo=self.weights_lo)
         self.last_layers = layers
         emb = layers[-1].h
         gemb = torch.empty_like(emb)
@@ -323,7 +335,7 @@ class SupervisedTrainer:
 
     # ---- the step, expressed once; runs eagerly or under capture -------------------------------
     def _forward_backward(self):
-        layers = self.model._run_prep(self.seeds, None, offset_dev=self.step_counter)
+        layers = self.model._run_prep(self.seeds, None, offset_dev=self.step_counter, dense_x=self.dense_x1)
         self._train_on(layers, self.seeds)
         if self.dp is None:
             self.step_counter.add_(1)        # the fused update kernel bumps it otherwise
@@ -463,7 +475,7 @@ class PipelinedTrainer(SupervisedTrainer):
         # first (see the class docstring); the defaults are what bench.py measures.
         self.bg_agg_ctas = int(os.environ.get("GS_BG_AGG_CTAS", "0"))
         self.prep_pdl = os.environ.get("GS_PREP_PDL", "0") == "1"
-        self.bg_carveout = os.environ.get("GS_BG_CARVE", "1") == "1"
+        self.bg_carveout = os.environ.get("GS_BG_CARVE", "0") == "1"
         self._train_stream = (torch.cuda.Stream(device=dev, priority=-1)
                               if os.environ.get("GS_TRAIN_PRIO", "0") == "1" else None)
         self._graphs = [None] * self.SLOTS     # one step training on slot s
@@ -565,7 +577,7 @@ class PipelinedTrainer(SupervisedTrainer):
         self.sample_counter.add_(1)
 
     def _aggregate(self, slot: int):
-        self.model._run_agg1(self.slot_layers[slot])
+        self.model._run_agg1(self.slot_layers[slot], dense_x=self.dense_x1)
 
     def _compute(self, slot: int, update: bool = True):
         self._train_on(self.slot_layers[slot], self.slot_seeds[slot])

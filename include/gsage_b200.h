@@ -196,15 +196,28 @@ int gs_sage_gemm_fwd(const float* self_table, int64_t ld_self, const int32_t* se
                      const int32_t* num_rows_dev, int32_t max_rows,
                      float* out, int64_t ld_out, int32_t relu, int32_t precision, gs_stream_t stream);
 
+/* K3 writing the SageLayer's whole input row (the operands torch.cat joins at src/models.py:217), for layers whose
+ * table is the raw feature table:  out_x[r, 0:dim] = table[self_nodes[r], :]  (src/models.py:265; skipped when self_nodes
+ * is NULL),  out_x[r, agg_off : agg_off+dim] = mean / max over the row's list (:300-326); out_x_lo (nullable, same layout)
+ * receives x - trunc_tf32(x) of every element written: the low half of K4's 3-term tf32 split.  The layer's GEMMs then
+ * read dense operands (gs_sage_gemm_fwd_ex with self_idx NULL takes its all-TMA kernel). */
+int gs_agg_fwd_x(const float* table, int64_t ld, int32_t dim, const int32_t* nbr, int32_t stride, const int32_t* cnt,
+                 const int32_t* self_nodes, const int32_t* num_rows_dev, int32_t max_rows, int32_t mode,
+                 float* out_x, int64_t ld_x, int32_t agg_off, float* out_x_lo, gs_stream_t stream);
+
 /* The same with one more output: zero_out (nullable, [max_rows x ld_zero], same shape as out) is zero-filled for the
  * live rows and columns.  It is the buffer the backward scatter of the layer above accumulates d(out) into
  * (gs_agg_bwd / gs_sage_top_sup): the fill rides on the forward epilogue instead of being a launch of its own. */
+/* x_lo / weight_lo (nullable): the low halves x - trunc_tf32(x) of the input rows (laid out like self_table .. agg,
+ * which must then be one dense [max_rows x 2*dim] matrix: self_idx NULL, agg == self_table + dim, ld_self == ld_agg) and
+ * of the weight.  With both given (or precision GS_PREC_TF32) the call runs the all-TMA kernel: no gather, no in-kernel
+ * split. */
 int gs_sage_gemm_fwd_ex(const float* self_table, int64_t ld_self, const int32_t* self_idx,
                         const float* agg, int64_t ld_agg, int32_t dim,
                         const float* weight, int64_t ldw, int32_t out_dim, int32_t gcn,
                         const int32_t* num_rows_dev, int32_t max_rows,
                         float* out, int64_t ld_out, int32_t relu, int32_t precision,
-                        float* zero_out, int64_t ld_zero, gs_stream_t stream);
+                        float* zero_out, int64_t ld_zero, const float* x_lo, const float* weight_lo, gs_stream_t stream);
 
 /* dW[h,k] += sum_r dZ[r,h] X[r,k],  dZ = grad_out * (out > 0) when relu.  grad_w must be
  * zeroed by the caller (partials are accumulated with atomics). */
@@ -339,7 +352,10 @@ int gs_dp_allreduce_clip_sgd(float* flat_grad, int64_t n_total, void* const* pee
                              int32_t world, float* const* seg_params_host, const int64_t* seg_offsets_host,
                              const int64_t* seg_numels_host, const int32_t* seg_groups_host, int32_t num_segs,
                              float max_norm, float lr, void* state, uint64_t timeout_ns, int64_t* step_counter,
-                             gs_stream_t stream);
+                             float* const* seg_params_lo_host, gs_stream_t stream);
+/* seg_params_lo_host (nullable HOST array of num_segs nullable device pointers): buffers shaped like the parameters that
+ * receive p - trunc_tf32(p) of every updated element (gs_sage_gemm_fwd_ex's weight_lo); gs_split_lo initialises one. */
+int gs_split_lo(const float* src, float* dst, int64_t n, gs_stream_t stream);
 /* synchronises `stream`, then reports the epoch counter, the status word (0 ok, 1 peer
  * wait timed out, 2 grid barrier timed out) and the last step's 4 per-group gradient norms */
 int gs_dp_status(const void* state, uint32_t* epoch_host, uint32_t* status_host, float* norms_host, gs_stream_t stream);

@@ -622,3 +622,59 @@ def test_fused_sampler_unique_chain_equals_numpy(g, dev):
                                         (step << 8) | 1, clear_bitmap=ws)
         assert int(ws[:words * 4].view(torch.int32).abs().sum().item()) == 0
         assert int((cnt1[:nu] > 0).sum().item()) == nu
+
+
+@pytest.mark.parametrize('mode,gcn,dim', [(0, False, 100), (0, True, 100), (1, False, 64), (0, False, 500)])
+def test_agg_fwd_x_writes_the_dense_input_rows(g, dev, mode, gcn, dim):
+    """gs_agg_fwd_x: X[r] = [table[self] | mean/max of the row's list] and the low tf32 halves x - trunc(x);
+    hi (= the raw word with its low 13 mantissa bits cleared) + lo must reproduce x exactly."""
+    rng = np.random.default_rng(dim + mode)
+    n, rows, stride = 5000, 700, 11 if gcn else 10
+    table = torch.from_numpy(rng.standard_normal((n, dim)).astype(np.float32)).to(dev)
+    cnt = rng.integers(0 if mode == 0 else 1, stride + 1, size=rows).astype(np.int32)
+    nbr = np.full((rows, stride), -1, dtype=np.int32)
+    for r in range(rows):
+        nbr[r, :cnt[r]] = np.sort(rng.choice(n, size=cnt[r], replace=False))
+    nodes = rng.integers(0, n, size=rows).astype(np.int32)
+    live = torch.tensor([rows - 13], dtype=torch.int32, device=dev)
+    x, x_lo = g.agg_fwd_x(table, dim, torch.from_numpy(nbr).to(dev), stride, torch.from_numpy(cnt).to(dev),
+                          None if gcn else torch.from_numpy(nodes).to(dev), live, rows, mode)
+    want_agg = _agg_ref(table.cpu(), nbr[:rows - 13].astype(np.int64), cnt[:rows - 13], mode).numpy()
+    got = x[:rows - 13].cpu().numpy()
+    if gcn:
+        assert got.shape[1] == dim and np.allclose(got, want_agg, rtol=1e-6, atol=1e-6, equal_nan=True)
+    else:
+        assert got.shape[1] == 2 * dim
+        assert np.array_equal(got[:, :dim], table.cpu().numpy()[nodes[:rows - 13]])
+        assert np.allclose(got[:, dim:], want_agg, rtol=1e-6, atol=1e-6, equal_nan=True)
+    hi = (x[:rows - 13].view(torch.int32) & -8192).view(torch.float32)
+    ok = torch.isfinite(x[:rows - 13])
+    assert torch.equal((hi + x_lo[:rows - 13])[ok], x[:rows - 13][ok])
+
+
+@pytest.mark.parametrize('precision,tol', [('tf32x3', 1e-5), ('tf32', 2e-3)])
+@pytest.mark.parametrize('rows,live,dim,gcn', [(10900, 10000, 100, False), (300, None, 64, False), (1000, None, 128, True)])
+def test_sage_gemm_dense_tma_path(g, dev, precision, tol, rows, live, dim, gcn):
+    """The all-TMA forward kernel (dense [self | agg] rows + pre-split low halves) against fp64, with the zero fill
+    of the gradient buffer, and against the gathered-operand kernel on the same numbers."""
+    from graphsage_b200 import native
+    prec = {'tf32x3': native.PREC_TF32X3, 'tf32': native.PREC_TF32}[precision]
+    rng = np.random.default_rng(rows + dim)
+    H, k = 128, dim if gcn else 2 * dim
+    x = torch.from_numpy(rng.standard_normal((rows, k)).astype(np.float32)).to(dev)
+    w = torch.from_numpy((rng.standard_normal((H, k)) * 0.1).astype(np.float32)).to(dev)
+    x_lo, w_lo = g.split_lo(x), g.split_lo(w)
+    nr = None if live is None else torch.tensor([live], dtype=torch.int32, device=dev)
+    n_live = rows if live is None else live
+    zero = torch.full((rows, H), 7.0, device=dev)
+    self_t, agg = (None, x) if gcn else (x[:, :dim], x[:, dim:])
+    native.launch_count_reset()
+    out = g.sage_gemm_fwd(self_t, None, agg, dim, w, H, gcn, nr, rows, True, prec, zero_out=zero, x_lo=x_lo, weight_lo=w_lo)
+    want = torch.relu(x[:n_live].double() @ w.double().t())
+    assert rel(out[:n_live], want) <= tol
+    assert float(zero[:n_live].abs().max()) == 0.0 and (live is None or float(zero[n_live:].min()) == 7.0)
+    # the gathered-operand kernel on a copy whose halves are NOT adjacent (so it cannot take the dense path)
+    agg2 = agg.clone()
+    out2 = g.sage_gemm_fwd(self_t, None if gcn else torch.arange(rows, dtype=torch.int32, device=dev), agg2, dim, w, H, gcn, nr,
+                           rows, True, prec)
+    assert rel(out2[:n_live], want) <= tol
