@@ -297,31 +297,47 @@ def timed_arms(torch, native, trainer, pipelined, dev_batches, host_batches, K, 
     e2e_ms = []
     last = 0.0
     if pipelined:
-        # the loss of step i is copied D2H (pinned) right behind the step and read by the host one step later,
-        # while step i+1 runs: one H2D of a batch and one D2H + host read of a loss per step, no bubble
-        loss_pin = [torch.zeros((1,), dtype=torch.float32).pin_memory() for _ in range(2)]
-        loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+        # Host batches go in through the pinned staging ring (H2D on the copy stream), losses come back by an async D2H
+        # copy into pinned memory behind every launch and are read by the host two launches later, while the GPU runs
+        # on: every step has its batch copied H2D and its loss read by the host, and nothing in the loop waits for the
+        # step just launched.  Where the slot rotation allows, three steps go out as one graph launch (their three
+        # losses land in trainer.slot_loss and come back in one 12-byte copy).
+        DEPTH = 4
+        loss_pin = [torch.zeros((3,), dtype=torch.float32).pin_memory() for _ in range(DEPTH)]
+        loss_ev = [torch.cuda.Event() for _ in range(DEPTH)]
+        group_len = [0] * DEPTH
         trainer.flush()
         trainer.feed(host_batches[0])
         trainer.feed(host_batches[1 % n_host])
         trainer.prime()                                                        # two batches in flight ahead of the trained one
+        fed = 2
         for i in range(min(W, 3)):
-            trainer.feed(host_batches[(2 + i) % n_host])
+            trainer.feed(host_batches[fed % n_host]); fed += 1
             trainer.run(1)
         sync_all()
         for w in range(windows):
             e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e2.record()
-            for i in range(K):
-                trainer.feed(host_batches[(W + 2 + w * K + i) % n_host])
-                dev_loss = trainer.run(1)
-                loss_pin[i & 1].copy_(dev_loss, non_blocking=True)
-                loss_ev[i & 1].record()
-                if i > 0:
-                    loss_ev[(i - 1) & 1].synchronize()
-                    last = float(loss_pin[(i - 1) & 1][0])
-            loss_ev[(K - 1) & 1].synchronize()
-            last = float(loss_pin[(K - 1) & 1][0])
+            i, launches = 0, 0
+            while i < K:
+                g = trainer.SLOTS if (trainer._cur == 0 and K - i >= trainer.SLOTS and trainer.use_graph) else 1
+                for _ in range(g):
+                    trainer.feed(host_batches[fed % n_host]); fed += 1
+                dev_loss = trainer.run(g)
+                d = launches % DEPTH
+                if launches >= DEPTH - 1:                                      # read the losses of the launch DEPTH-1 back
+                    o = (launches + 1) % DEPTH
+                    loss_ev[o].synchronize()
+                    last = float(loss_pin[o][group_len[o] - 1])
+                loss_pin[d][:g].copy_(trainer.slot_loss if g == trainer.SLOTS else dev_loss, non_blocking=True)
+                loss_ev[d].record()
+                group_len[d] = g
+                launches += 1
+                i += g
+            for back in range(min(launches, DEPTH - 1), 0, -1):                 # drain: every loss is read inside the timed region
+                o = (launches - back) % DEPTH
+                loss_ev[o].synchronize()
+                last = float(loss_pin[o][group_len[o] - 1])
             e3.record()
             sync_all()
             e2e_ms.append(e2.elapsed_time(e3))
@@ -439,9 +455,13 @@ def run_ours(args):
         dump_timeline(torch, native, PipelinedTrainer, model, cls, labels, b_sz, dev_batches, args.timeline)
 
     # ---- roofline of the dominant kernel: layer-1 aggregation, events around its launch ----
-    roof = None
+    roof = roof_gemm = None
     if rank == 0:
         roof = measure_agg_roofline(torch, ops, native, model, trainer, dev_batches, W, K, dev)
+        try:
+            roof_gemm = measure_gemm_roofline(torch, ops, native, model, trainer, dev_batches, W, K, dev)
+        except Exception as exc:
+            roof_gemm = {"error": repr(exc)[:300]}
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ----
     cpu = None
@@ -467,10 +487,11 @@ def run_ours(args):
             "e2e": {"value": seeds_total / (ms_e2e * 1e-3), "unit": "seed nodes/s", "ms_per_step": ms_e2e / K,
                     "h2d_bytes_per_step": int(b_sz * 4), "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches_timed), "launches_per_step": int(trainer.launches_per_step),
-            "e2e_loss_read": ("async D2H into pinned memory behind every step, read by the host one step later"
+            "e2e_loss_read": ("async D2H into pinned memory behind every graph launch (1 or 3 steps), read by the host three launches later"
                               if pipelined else "loss.item() after every step"),
             "cuda_graph": bool(trainer.use_graph), "loss": loss_dev, "loss_e2e": last,
-            "roofline": roof, "cpu_baseline": cpu, "clocks": clk, "windows": wstats, "replicas_identical": same,
+            "roofline": roof, "roofline_gemm": roof_gemm, "cpu_baseline": cpu, "clocks": clk, "windows": wstats,
+            "replicas_identical": same,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -800,146 +821,193 @@ def dump_timeline(torch, native, PipelinedTrainer, model, cls, labels, b_sz, dev
     log(f"[bench] timeline written to {path}")
 
 
+def _peak(key, fallback):
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))[key]), f"MEASURED_PEAKS.json {key}"
+    except Exception:
+        return fallback, f"fallback {fallback} (B200_PROFILING.md)"
+
+
+def _chain_us(torch, dev, fn_list, reps=5):
+    """CUDA-event time per element of fn_list, the whole list captured as ONE CUDA graph and replayed (how the
+    product launches its kernels: programmatic dependent launch between neighbours, no host in between)."""
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for fn in fn_list:
+            fn()
+    g.replay()
+    torch.cuda.synchronize(dev)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        g.replay()
+    b.record()
+    torch.cuda.synchronize(dev)
+    return a.elapsed_time(b) * 1e3 / (reps * len(fn_list))
+
+
 def measure_agg_roofline(torch, ops, native, model, trainer, dev_batches, W, K, dev):
-    """Instrumented pass: run the step's sampling phase for fresh batches, then time ONLY the
-    layer-1 gs_agg_fwd launch with CUDA events on its stream.  Algorithmic bytes per launch =
-    nnz*D*4 + R*D*4 + nnz*4 + (R+1)*4 from the batch's actual nnz / R."""
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-    if os.path.exists(peaks_path):
-        try:
-            peak = float(json.load(open(peaks_path))["hbm_gbs"])
-            peak_src = "MEASURED_PEAKS.json hbm_gbs"
-        except Exception:
-            pass
+    """Roofline of the dominant kernel, the layer-1 aggregation (gs_agg_fwd), as the step launches it: behind the
+    layer-1 sampler, which requests the rows it drew into L2 (gs_sample_neighbors_ex prefetch_table), on the default
+    L1/shared split.  Algorithmic bytes per launch = nnz*D*4 + R*D*4 + nnz*4 + (R+1)*4 from the batch's actual
+    nnz / R.  Timed with CUDA events around graph-replayed chains over n distinct frontiers (fresh
+    seeds each: the 44 MB a launch gathers are a different random subset of the 980 MB table every time, and n x 44 MB
+    cycles through the 126 MB L2 between replays):
+        t_pair = chain of [sampler L1 (+prefetch), aggregation]        t_samp = chain of [sampler L1 (+prefetch)]
+        in-step kernel time = t_pair - t_samp
+    beside it the aggregation chain alone (no prefetch: every row comes from DRAM inside the kernel) and the same
+    kernel at a saturating size."""
+    peak, peak_src = _peak("hbm_gbs", 6650.0)
     csr, table, _ = model._state()
-    weights = [w.detach() for w in trainer.weights]
     mode = native.AGG_MEAN
-    d = model.input_size
+    d, k = model.input_size, model.num_sample
     n_iter = max(4, min(K, 16))
-    # distinct frontiers (fresh seeds each): the 44 MB a launch gathers is a different random subset
-    # of the 980 MB table every time, so nothing useful survives in the 126 MB L2 between launches
     fronts, bytes_ = [], []
     for i in range(n_iter):
-        seeds = dev_batches[(W + i) % dev_batches.shape[0]]
-        fr = model._run_forward(seeds, weights, None)[0]
+        seeds = dev_batches[(W + i) % dev_batches.shape[0]].contiguous()
+        fr = model._run_agg1(model._run_sample(seeds, None))[0]
         rows = int(fr.num_rows.item())
         nnz = int(fr.cnt[:rows].sum().item())
         bytes_.append(nnz * d * 4 + rows * d * 4 + nnz * 4 + (rows + 1) * 4)
         fronts.append((fr, torch.empty_like(fr.agg)))
+    self_mode = native.SELF_ONCE if model.gcn else native.SELF_DROP
 
-    def launch(fr, out):
-        ops.agg_fwd(table, d, fr.nbr_idx, fr.stride, fr.cnt, fr.num_rows, fr.rows_max, mode, out=out)
+    def agg(fr, out):
+        ops.agg_fwd(table, d, fr.nbr, fr.stride, fr.cnt, fr.num_rows, fr.rows_max, mode, out=out)
 
+    def samp(fr, prefetch):      # re-draws the same lists (same Philox offset) into the frontier's own buffers
+        ops.sample_neighbors(csr.rowptr, csr.col, csr.num_nodes, fr.nodes, fr.num_rows, fr.rows_max, k, fr.stride, self_mode,
+                             model.seed, (model._calls << 8) | 1, out_nbr=fr.nbr, out_cnt=fr.cnt,
+                             prefetch_table=table if prefetch else None, prefetch_cols=d)
+
+    nnz0 = [int(fr.cnt.sum().item()) for fr, _ in fronts]
     for fr, out in fronts[:2]:
-        launch(fr, out)
+        samp(fr, True)
+        agg(fr, out)
     torch.cuda.synchronize(dev)
-    # (1) back-to-back launches between one pair of events: per-launch time without the event overhead
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for fr, out in fronts:
-        launch(fr, out)
-    b.record()
-    torch.cuda.synchronize(dev)
-    t_batch = a.elapsed_time(b) * 1e-3 / n_iter
-    # (2) one pair of events per launch (includes ~5 us of event/launch latency on a ~10-20 us kernel)
-    singles = []
-    for fr, out in fronts:
-        a.record()
-        launch(fr, out)
-        b.record()
-        torch.cuda.synchronize(dev)
-        singles.append(a.elapsed_time(b) * 1e-3)
-    # (1b) the same chain replayed from a CUDA graph -- how the product launches it (the step is one graph)
-    t_graph = None
-    if trainer.use_graph:
-        try:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                for fr, out in fronts:
-                    launch(fr, out)
-            g.replay()
-            torch.cuda.synchronize(dev)
-            reps = 5
-            a.record()
-            for _ in range(reps):
-                g.replay()
-            b.record()
-            torch.cuda.synchronize(dev)
-            t_graph = a.elapsed_time(b) * 1e-3 / (reps * n_iter)
-        except Exception as exc:
-            log(f"[bench] graph-replayed roofline chain failed: {exc!r}")
-    # (1c) the same chain with the kernel on the max-shared carveout, as it runs in the background branch of
-    # the pipelined step (less L1 for loads in flight; see gs_set_background)
-    t_bg = None
-    if trainer.use_graph:
-        try:
-            native.set_background(True)
-            g2 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g2):
-                for fr, out in fronts:
-                    launch(fr, out)
-            native.set_background(False)
-            g2.replay()
-            torch.cuda.synchronize(dev)
-            a.record()
-            for _ in range(5):
-                g2.replay()
-            b.record()
-            torch.cuda.synchronize(dev)
-            t_bg = a.elapsed_time(b) * 1e-3 / (5 * n_iter)
-        except Exception as exc:
-            log(f"[bench] background-mode roofline chain failed: {exc!r}")
-        finally:
-            native.set_background(False)
-    times = [t_graph if t_graph is not None else t_batch]
-    # (3) the same kernel at a saturating size: frontier of 8 x b_sz seeds (~85K rows, ~390 MB gathered)
+    pf = bool(model.l2_prefetch)
+    t_agg = _chain_us(torch, dev, [(lambda f=f, o=o: agg(f, o)) for f, o in fronts])
+    t_samp = _chain_us(torch, dev, [(lambda f=f: samp(f, pf)) for f, _ in fronts])
+    t_pair = _chain_us(torch, dev, [fn for f, o in fronts for fn in ((lambda f=f: samp(f, pf)), (lambda f=f, o=o: agg(f, o)))]) * 2
+    t_samp_np = _chain_us(torch, dev, [(lambda f=f: samp(f, False)) for f, _ in fronts])
+    assert nnz0 == [int(fr.cnt.sum().item()) for fr, _ in fronts], "the re-drawn lists must be the ones the bytes were counted on"
+    t_in_step = t_pair - t_samp
+    # the same kernel at a saturating size: frontier of 8 x b_sz seeds (~85K rows, ~390 MB gathered)
     big = None
     try:
         b8 = dev_batches[:8].reshape(-1) if dev_batches.shape[0] >= 8 else dev_batches.reshape(-1)
-        frb = model._run_forward(b8.contiguous(), weights, None)[0]
+        frb = model._run_agg1(model._run_sample(b8.contiguous(), None))[0]
         rows_b = int(frb.num_rows.item())
         nnz_b = int(frb.cnt[:rows_b].sum().item())
         bytes_b = nnz_b * d * 4 + rows_b * d * 4 + nnz_b * 4 + (rows_b + 1) * 4
         outb = torch.empty_like(frb.agg)
-        for _ in range(2):
-            launch(frb, outb)
-        torch.cuda.synchronize(dev)
-        a.record()
-        for _ in range(5):
-            launch(frb, outb)
-        b.record()
-        torch.cuda.synchronize(dev)
-        tb = a.elapsed_time(b) * 1e-3 / 5
-        big = {"rows": rows_b, "bytes_per_launch": float(bytes_b), "us_per_launch": tb * 1e6,
-               "achieved": bytes_b / tb / 1e9, "frac": bytes_b / tb / 1e9 / peak,
-               "note": "same frontier relaunched; 390 MB gathered >> 126 MB L2"}
+        tb = _chain_us(torch, dev, [lambda: agg(frb, outb)] * 4)
+        big = {"rows": rows_b, "bytes_per_launch": float(bytes_b), "us_per_launch": tb, "achieved": bytes_b / tb / 1e3,
+               "frac": bytes_b / tb / 1e3 / peak, "note": "same frontier relaunched; 390 MB gathered >> 126 MB L2"}
     except Exception as exc:      # the headline roofline above does not depend on this extra point
         big = {"error": repr(exc)[:200]}
-    achieved = float(np.mean(bytes_) / np.mean(times) / 1e9)
-    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full` capture
+    mean_bytes = float(np.mean(bytes_))
+    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full` capture; only
+    # quoted while the kernel's source is the one that was captured
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "agg_traffic.json")
-    if os.path.exists(tpath):
-        try:
-            t = json.load(open(tpath))
+    try:
+        import hashlib
+        t = json.load(open(tpath))
+        src = os.path.join(ROOT, "graphsage-pytorch_b200", "csrc", "aggregate.cu")
+        if t.get("source_sha256") == hashlib.sha256(open(src, "rb").read()).hexdigest():
             traffic, traffic_src = float(t["dram_bytes_per_launch"]), t.get("source")
-        except Exception:
-            pass
-    kname = "agg_fwd_kernel<MEAN>"
-    return {"bound": "hbm", "kernel": f"{kname} (layer 1, gs_agg_fwd)", "achieved": achieved, "peak": peak,
-            "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-            "peak_source": peak_src,
-            "bytes_per_launch": float(np.mean(bytes_)), "us_per_launch": float(np.mean(times) * 1e6),
-            "saturating_size": big, "launches_timed": n_iter, "us_per_launch_single_event_pair": float(np.mean(singles) * 1e6),
-            "us_per_launch_eager_chain": float(t_batch * 1e6),
-            "us_per_launch_graph_chain": None if t_graph is None else float(t_graph * 1e6),
-            "background_mode": None if t_bg is None else {
-                "us_per_launch": float(t_bg * 1e6), "achieved": float(np.mean(bytes_) / t_bg / 1e9),
-                "frac": float(np.mean(bytes_) / t_bg / 1e9 / peak),
-                "note": "same kernel on the max-shared carveout (how the pipelined step launches it beside the GEMMs)"},
-            "note": "achieved = algorithmic bytes / (CUDA-event time of a chain of n back-to-back launches on distinct "
-                    "frontiers / n); the chain is replayed from a CUDA graph like the product's step (eager chain beside it)"}
+        else:
+            traffic_src = "aggregate.cu changed since the ncu capture in profiles/agg_traffic.json: not quoted"
+    except Exception:
+        pass
+    ach = mean_bytes / t_in_step / 1e3
+    return {"bound": "hbm", "kernel": "agg_fwd_kernel<MEAN> (layer 1, gs_agg_fwd)", "achieved": ach, "peak": peak,
+            "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+            "bytes_per_launch": mean_bytes, "us_per_launch": t_in_step, "launches_timed": n_iter,
+            "how": ("in-step configuration: graph-replayed chain of [layer-1 sampler with L2 prefetch of the drawn rows, "
+                    "aggregation] minus the chain of the sampler alone" if pf else
+                    "graph-replayed chain of [layer-1 sampler, aggregation] minus the chain of the sampler alone (prefetch off)"),
+            "us_sampler_with_prefetch": t_samp, "us_sampler_without_prefetch": t_samp_np, "us_pair": t_pair,
+            "without_prefetch": {"us_per_launch": t_agg, "achieved": mean_bytes / t_agg / 1e3, "frac": mean_bytes / t_agg / 1e3 / peak,
+                                 "note": "chain of the aggregation kernel alone: every gathered row comes from DRAM inside the kernel"},
+            "saturating_size": big,
+            "note": "achieved = algorithmic bytes / kernel time; with the sampler's prefetch part of the DRAM fetch of those "
+                    "bytes is issued before the kernel starts (it overlaps the launch gap and the ramp), so DRAM traffic "
+                    "INSIDE the kernel is below the algorithmic bytes -- `without_prefetch` is the kernel on its own"}
+
+
+def measure_gemm_roofline(torch, ops, native, model, trainer, dev_batches, W, K, dev):
+    """The tensor-core kernels of the training chain, each as a graph-replayed chain on distinct frontiers: the layer-1
+    forward GEMM (tcgen05 kind::tf32, 3-term split) against the TF32 tensor peak (= half the measured bf16 peak) and
+    against HBM, plus the times of the fused top-layer kernel and of the grouped weight-gradient launch."""
+    from graphsage_b200.models import _PRECISIONS
+    bf16, src = _peak("bf16_tflops", 1636.0)
+    hbm, _ = _peak("hbm_gbs", 6650.0)
+    tf32_peak = bf16 / 2.0
+    prec = _PRECISIONS[model.precision]
+    n_iter = max(4, min(K, 8))
+    weights = [w.detach() for w in trainer.weights]
+    d, H = model.input_size, model.out_size
+    kx = d if model.gcn else 2 * d
+    fronts, flops, bytes_ = [], [], []
+    for i in range(n_iter):
+        seeds = dev_batches[(W + i) % dev_batches.shape[0]].contiguous()
+        layers = model._run_agg1(model._run_sample(seeds, None), dense_x=getattr(trainer, "dense_x1", False))
+        fr = layers[0]
+        rows = int(fr.num_rows.item())
+        flops.append(2.0 * rows * kx * H)
+        bytes_.append(rows * kx * 4 + H * kx * 4 + 2 * rows * H * 4)
+        gh = torch.empty((fr.rows_max, H), dtype=torch.float32, device=dev)
+        fronts.append((layers, gh))
+
+    def fwd(layers, gh):
+        model._run_compute(layers, weights, upto=1, zero_grad_of_last=gh, weights_lo=getattr(trainer, "weights_lo", None))
+
+    for f in fronts[:2]:
+        fwd(*f)
+    torch.cuda.synchronize(dev)
+    t_fwd = _chain_us(torch, dev, [(lambda l=l, g=g: fwd(l, g)) for l, g in fronts])
+    products = 3 if prec == native.PREC_TF32X3 else 1
+    useful = float(np.mean(flops)) / t_fwd / 1e6          # TFLOP/s
+    out = {"bound": "tensor", "kernel": ("sage_fwd_tma_kernel" if getattr(trainer, "dense_x1", False) else "sage_fwd_tc_kernel") +
+           " (layer 1 forward, gs_sage_gemm_fwd_ex)", "unit": "TFLOP/s", "achieved": useful, "achieved_issued": useful * products,
+           "peak": tf32_peak, "peak_source": f"{src} / 2 (kind::tf32 runs at half the bf16 rate)", "frac": useful / tf32_peak,
+           "frac_issued": useful * products / tf32_peak, "products_per_mac": products, "flop_per_launch": float(np.mean(flops)),
+           "us_per_launch": t_fwd, "hbm_bytes_per_launch": float(np.mean(bytes_)),
+           "hbm_frac": float(np.mean(bytes_)) / t_fwd / 1e3 / hbm, "launches_timed": n_iter,
+           "note": "useful = 2*R*K*H per launch; issued = x3 (the fp32-faithful split computes three tf32 products per MAC)"}
+    # the other two launches of the training chain, on the prepared frontiers of the trainer's slot 0
+    try:
+        layers = trainer.slot_layers[0] if hasattr(trainer, "slot_layers") else trainer.last_layers
+        below, top = layers[-2], layers[-1]
+        if top.dz is not None:
+            seeds0 = trainer.slot_seeds[0] if hasattr(trainer, "slot_seeds") else trainer.seeds
+            scratch = torch.zeros_like(trainer.flat_grad)
+            views = [scratch[:w.numel()].view_as(w) for w in trainer.weights[:2]]
+
+            def top_k():
+                ops.sage_top_sup(below.h, top.nbr_idx, top.stride, top.cnt, top.self_idx, top.num_rows, top.rows_max, weights[-1],
+                                 model.gcn, trainer.cls_w.detach(), trainer.cls_b.detach(), trainer.labels, seeds0,
+                                 torch.zeros((1,), device=dev), scratch[-8192:-2048], scratch[-64:], below.gh, trainer._top_ws, prec,
+                                 out_h=top.h, out_agg=top.agg, out_dz=top.dz)
+            if scratch.numel() >= 8192 + int(trainer.cls_w.numel()):
+                out["us_top_layer_kernel"] = _chain_us(torch, dev, [top_k] * 8)
+            if model.num_layers == 2:
+                def dw():
+                    ops.sage_gemm_bwd_w_pair([
+                        (None if model.gcn else below.table_in, below.self_idx, below.agg, below.dim_in, below.gh, below.h, H,
+                         below.num_rows, below.rows_max, views[0]),
+                        (None if model.gcn else below.h, top.self_idx, top.agg, H, top.dz, top.h, H, top.num_rows, top.rows_max,
+                         views[0][:, :2 * H] if views[0].shape[1] >= 2 * H else views[1])], model.gcn, False, prec)
+                out["us_weight_gradient_pair"] = _chain_us(torch, dev, [dw] * 8)
+                rows1 = int(below.num_rows.item())
+                fl = 2.0 * rows1 * kx * H + 2.0 * top.rows_max * (H if model.gcn else 2 * H) * H
+                out["weight_gradient_pair_tflops_useful"] = fl / out["us_weight_gradient_pair"] / 1e6
+    except Exception as exc:
+        out["chain_kernels_error"] = repr(exc)[:200]
+    return out
 
 
 def main():

@@ -15,8 +15,14 @@
 namespace gs {
 
 constexpr int kAggWarps = 8;          // warps per CTA
-constexpr int kBatch = 6;             // 16-byte loads in flight per lane: fan-out 10 (+ self) goes in two batches
-constexpr int kAggCtasPerSM = 5;      // MEAN: 48 registers -> 5 CTAs = 40 warps per SM
+#ifndef GS_AGG_BATCH
+#define GS_AGG_BATCH 6
+#endif
+#ifndef GS_AGG_CTAS
+#define GS_AGG_CTAS 5
+#endif
+constexpr int kBatch = GS_AGG_BATCH;  // 16-byte loads in flight per lane: fan-out 10 (+ self) goes in two batches
+constexpr int kAggCtasPerSM = GS_AGG_CTAS;   // MEAN: 48 registers -> 5 CTAs = 40 warps per SM
 
 // Register-staged forward, persistent warps.  A warp owns destination rows gw, gw+W, ... (W = warps
 // in the grid); lane = float4 column.  The count and id list of a row are loaded one row AHEAD, and

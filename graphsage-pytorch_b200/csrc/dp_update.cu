@@ -42,10 +42,13 @@ struct DpPeers {
 struct DpSegs {
   float* param[kDpMaxSegs];
   float* param_lo[kDpMaxSegs];     // nullable: receives p - trunc_tf32(p) of the updated parameter (K4's split operand)
+  float* extra[kDpMaxSegs];        // nullable: extra_n[k] more partial gradients of the tensor, extra_stride[k] floats apart
+  int extra_n[kDpMaxSegs];         //   (replicas a producer spread its atomics over); folded into the sum and cleared
+  long long extra_stride[kDpMaxSegs];
   long long off[kDpMaxSegs];       // offset of the tensor's gradient inside the flat buffer (multiple of 4)
   long long numel[kDpMaxSegs];
   int group[kDpMaxSegs];           // clip group (model) of the tensor
-  int n, groups;
+  int n, groups, any_extra;
 };
 struct DpState {                   // device memory, zeroed once by the caller
   unsigned int epoch;
@@ -120,6 +123,31 @@ dp_update_kernel(float* __restrict__ flat, long long n_total, const __grid_const
   const long long stride = static_cast<long long>(G) * kDpThreads;
   GS_DP_MARK(2);
 
+  // partial-gradient replicas of a segment are folded into the flat buffer (and cleared) before anything reads it
+  auto fold = [&](long long i, int k, float4 g) -> float4 {
+    if (k >= 0 && segs.extra[k] != nullptr) {
+      const long long o = 4 * i - segs.off[k];
+      const int n = segs.extra_n[k];
+      for (int x0 = 0; x0 < n; x0 += 8) {                  // 8 independent loads in flight, then the adds in replica order
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          v[u] = x0 + u < n ? __ldcg(reinterpret_cast<const float4*>(segs.extra[k] + (x0 + u) * segs.extra_stride[k] + o))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          g.x += v[u].x; g.y += v[u].y; g.z += v[u].z; g.w += v[u].w;
+          if (x0 + u < n) *reinterpret_cast<float4*>(segs.extra[k] + (x0 + u) * segs.extra_stride[k] + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    }
+    return g;
+  };
+  if (segs.any_extra)                                      // (uniform branch; off in the default configuration)
+    for (long long i = first; i < n4; i += stride) {
+      const int k = seg_of(segs, 4 * i);
+      if (k >= 0 && segs.extra[k] != nullptr) flat4[i] = fold(i, k, flat4[i]);
+    }
   if (W > 1) {
     // ---- push my pieces into every peer's slot [par][me] ----
     for (int p = 0; p < W; ++p) {
@@ -157,7 +185,7 @@ dp_update_kernel(float* __restrict__ flat, long long n_total, const __grid_const
   float ss[kDpMaxGroups];
 #pragma unroll
   for (int g = 0; g < kDpMaxGroups; ++g) ss[g] = 0.f;
-  auto reduce_one = [&](long long i) -> float4 {
+  auto reduce_one = [&](long long i, int k) -> float4 {
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int r = 0; r < W; ++r) {                          // rank order: every rank adds the same numbers in the same order
       const float4 v = (r == me) ? flat4[i] : __ldcg(mine + static_cast<long long>(r) * n4 + i);
@@ -179,8 +207,8 @@ dp_update_kernel(float* __restrict__ flat, long long n_total, const __grid_const
       const long long i = first + j * stride;
       segk[j] = -1;
       if (i < n4) {
-        gsum[j] = reduce_one(i);
         const int k = seg_of(segs, 4 * i);
+        gsum[j] = reduce_one(i, k);
         segk[j] = k;
         if (k >= 0) {
           const long long o = 4 * i - segs.off[k];
@@ -193,9 +221,10 @@ dp_update_kernel(float* __restrict__ flat, long long n_total, const __grid_const
     for (int j = 0; j < kDpPer; ++j) add_ss(gsum[j], segk[j]);
   } else {
     for (long long i = first; i < n4; i += stride) {
-      const float4 s = reduce_one(i);
+      const int k = seg_of(segs, 4 * i);
+      const float4 s = reduce_one(i, k);
       flat4[i] = s;
-      add_ss(s, seg_of(segs, 4 * i));
+      add_ss(s, k);
     }
   }
   __shared__ float s_red[kDpThreads / 32][kDpMaxGroups];
@@ -312,7 +341,9 @@ extern "C" int gs_dp_allreduce_clip_sgd(float* flat_grad, int64_t n_total, void*
                                         int32_t world, float* const* seg_params_host, const int64_t* seg_offsets_host,
                                         const int64_t* seg_numels_host, const int32_t* seg_groups_host, int32_t num_segs,
                                         float max_norm, float lr, void* state, uint64_t timeout_ns,
-                                        int64_t* step_counter, float* const* seg_params_lo_host, gs_stream_t stream) {
+                                        int64_t* step_counter, float* const* seg_params_lo_host,
+                                        float* const* seg_extra_host, const int32_t* seg_extra_n_host,
+                                        const int64_t* seg_extra_stride_host, gs_stream_t stream) {
   if (!flat_grad || !state || n_total < 4 || (n_total & 3) || !aligned16(flat_grad)) return GS_ERR_BAD_ARG;
   if (world < 1 || world > kDpMaxWorld || rank < 0 || rank >= world) return GS_ERR_BAD_ARG;
   if (num_segs < 1 || num_segs > kDpMaxSegs || !seg_params_host || !seg_offsets_host || !seg_numels_host) return GS_ERR_BAD_ARG;
@@ -333,6 +364,17 @@ extern "C" int gs_dp_allreduce_clip_sgd(float* flat_grad, int64_t n_total, void*
     segs.param[i] = seg_params_host[i];
     segs.param_lo[i] = seg_params_lo_host ? seg_params_lo_host[i] : nullptr;
     if (segs.param_lo[i] && !aligned16(segs.param_lo[i])) return GS_ERR_ALIGNMENT;
+    segs.extra[i] = seg_extra_host ? seg_extra_host[i] : nullptr;
+    segs.extra_n[i] = (segs.extra[i] && seg_extra_n_host) ? seg_extra_n_host[i] : 0;
+    segs.extra_stride[i] = (segs.extra[i] && seg_extra_stride_host) ? seg_extra_stride_host[i] : 0;
+    if (segs.extra[i]) {
+      if (!aligned16(segs.extra[i]) || (segs.extra_stride[i] & 3) || segs.extra_stride[i] < ((segs.numel[i] + 3) & ~3LL) ||
+          segs.extra_n[i] < 1 || segs.extra_n[i] > 16)
+        return GS_ERR_BAD_ARG;
+      segs.any_extra = 1;
+    } else {
+      segs.extra_n[i] = 0;
+    }
     segs.off[i] = seg_offsets_host[i];
     segs.numel[i] = seg_numels_host[i];
     segs.group[i] = seg_groups_host ? seg_groups_host[i] : 0;

@@ -59,6 +59,7 @@ struct Params {
   float* out_dz; int64_t ld_dz;
   float* logp;
   float* loss; float* grad_cls_w; float* grad_cls_b;
+  float* cls_w_rep; float* cls_b_rep; int cls_reps;       // replicas 1..cls_reps-1 of the classifier gradients (see P4c)
   float* grad_table; int64_t ld_gt;
   float* partials; unsigned int* ticket;
 };
@@ -96,6 +97,13 @@ __device__ __forceinline__ int swz(int row, int col, int box_bytes) {
 }
 __device__ __forceinline__ float lds_swz(const unsigned char* base, int row, int col, int box_bytes) {
   return *reinterpret_cast<const float*>(base + swz(row, col, box_bytes));
+}
+// The 8 piece offsets of one swizzled row: piece j (columns 4j..4j+3 of a 32-column box) of row `row` sits at
+// xor8[j]; with them a fragment address is  box * box_bytes + row * 128 + xor8[piece] + (col & 3) * 4  -- all but the
+// (compile-time) box term are per-lane constants, so the unrolled MMA loops issue bare loads.
+__device__ __forceinline__ void swz_pieces(int row, int (&xor8)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) xor8[j] = (j ^ (row & 7)) << 4;
 }
 
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
@@ -142,6 +150,7 @@ struct Smem {
   float logit[kTM * kCs];
   float dlog[kTM * kCs];                                  // d(logits), columns >= num_classes zero
   float red[kWarps];
+  float bias[kMaxClasses];
   int32_t nbr[kTM * kMaxStride];
   int32_t cnt[kTM];
   int32_t self_row[kTM];
@@ -170,6 +179,7 @@ sage_top_sup_kernel(const Params p, const __grid_constant__ CUtensorMap tmap_w, 
   float loss_part = 0.f;                                  // this thread's share of -sum logp[y] / rows
   bool weights_pending = static_cast<int>(blockIdx.x) < tiles;
 
+  if (tid < kMaxClasses) s.bias[tid] = (tid < C && p.cls_b) ? __ldg(p.cls_b + tid) : 0.f;   // visible after the first barrier
   if (weights_pending && tid == 0) {
     // W and Wc -> shared memory: K/32 + 4 tiled bulk copies, landing while the first tile is gathered
     const uint32_t bar = smem_u32(&s.bar);
@@ -256,11 +266,19 @@ sage_top_sup_kernel(const Params p, const __grid_constant__ CUtensorMap tmap_w, 
       const float* xa = &s.x[g * XS + t];
       const float* xb = &s.x[(g + 8) * XS + t];
       const int n = 8 * warp + g;
-#pragma unroll 8
-      for (int k0 = 0; k0 < K; k0 += 8) {
-        const float a[4] = {xa[k0], xb[k0], xa[k0 + 4], xb[k0 + 4]};
-        const float b[2] = {lds_swz(s.w, n, k0 + t, kWBox), lds_swz(s.w, n, k0 + t + 4, kWBox)};
-        mma_split<SPLIT3>(acc, cor, a, b);
+      int pc[8];
+      swz_pieces(n, pc);
+      const unsigned char* wrow = s.w + n * 128 + t * 4;
+#pragma unroll
+      for (int b = 0; b < K / 32; ++b) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k0 = 32 * b + 8 * j;
+          const float a[4] = {xa[k0], xb[k0], xa[k0 + 4], xb[k0 + 4]};
+          const float bv[2] = {*reinterpret_cast<const float*>(wrow + b * kWBox + pc[2 * j]),
+                               *reinterpret_cast<const float*>(wrow + b * kWBox + pc[2 * j + 1])};
+          mma_split<SPLIT3>(acc, cor, a, bv);
+        }
       }
       const int col = 8 * warp + 2 * t;
       const float2 top = make_float2(fmaxf(acc[0] + cor[0], 0.f), fmaxf(acc[1] + cor[1], 0.f));      // src/models.py:219
@@ -275,23 +293,36 @@ sage_top_sup_kernel(const Params p, const __grid_constant__ CUtensorMap tmap_w, 
     __syncthreads();
     GS_TOP_MARK(5);
 
-    // ---- P4a: logits = h . Wc^T + bc on the tensor cores: warp w < c_pad/8 owns classes 8w .. 8w+7 ----
-    if (8 * warp < c_pad) {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f}, cor[4] = {0.f, 0.f, 0.f, 0.f};
-      const float* ha = &s.h[g * kHs + t];
-      const float* hb = &s.h[(g + 8) * kHs + t];
-      const int n = 8 * warp + g;
-#pragma unroll 8
-      for (int k0 = 0; k0 < kH; k0 += 8) {
-        const float a[4] = {ha[k0], hb[k0], ha[k0 + 4], hb[k0 + 4]};
-        const float b[2] = {lds_swz(s.wc, n, k0 + t, kWcBox), lds_swz(s.wc, n, k0 + t + 4, kWcBox)};
-        mma_split<SPLIT3>(acc, cor, a, b);
+    // ---- P4a: logits = h . Wc^T + bc on the tensor cores.  Warps 0..7 own the classes 8w .. 8w+7 over the first half
+    //      of the contraction, warps 8..15 the same classes over the second half (two short dependency chains instead
+    //      of one long one; the halves meet in shared memory). ----
+    {
+      const int cw = warp & 7, half = warp >> 3;
+      if (8 * cw < c_pad) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f}, cor[4] = {0.f, 0.f, 0.f, 0.f};
+        const float* ha = &s.h[g * kHs + t];
+        const float* hb = &s.h[(g + 8) * kHs + t];
+        const int n = 8 * cw + g;
+        int pc[8];
+        swz_pieces(n, pc);
+        const unsigned char* wrow = s.wc + n * 128 + t * 4;
+#pragma unroll
+        for (int bb = 0; bb < kH / 64; ++bb) {
+          const int b = half * (kH / 64) + bb;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k0 = 32 * b + 8 * j;
+            const float a[4] = {ha[k0], hb[k0], ha[k0 + 4], hb[k0 + 4]};
+            const float bv[2] = {*reinterpret_cast<const float*>(wrow + b * kWcBox + pc[2 * j]),
+                                 *reinterpret_cast<const float*>(wrow + b * kWcBox + pc[2 * j + 1])};
+            mma_split<SPLIT3>(acc, cor, a, bv);
+          }
+        }
+        const int c = 8 * cw + 2 * t;
+        float* dst = half == 0 ? s.logit : s.dlog;          // dlog is free until the softmax writes it
+        *reinterpret_cast<float2*>(&dst[g * kCs + c]) = make_float2(acc[0] + cor[0], acc[1] + cor[1]);
+        *reinterpret_cast<float2*>(&dst[(g + 8) * kCs + c]) = make_float2(acc[2] + cor[2], acc[3] + cor[3]);
       }
-      const int c = 8 * warp + 2 * t;
-      const float b0 = (c < C && p.cls_b) ? __ldg(p.cls_b + c) : 0.f;
-      const float b1 = (c + 1 < C && p.cls_b) ? __ldg(p.cls_b + c + 1) : 0.f;
-      *reinterpret_cast<float2*>(&s.logit[g * kCs + c]) = make_float2(acc[0] + cor[0] + b0, acc[1] + cor[1] + b1);
-      *reinterpret_cast<float2*>(&s.logit[(g + 8) * kCs + c]) = make_float2(acc[2] + cor[2] + b0, acc[3] + cor[3] + b1);
     }
     __syncthreads();
     GS_TOP_MARK(10);
@@ -302,7 +333,10 @@ sage_top_sup_kernel(const Params p, const __grid_constant__ CUtensorMap tmap_w, 
       const int row = row0 + r;
       float z[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) z[q] = (j + 16 * q < C) ? s.logit[r * kCs + j + 16 * q] : -INFINITY;
+      for (int q = 0; q < 4; ++q) {
+        const int c = j + 16 * q;
+        z[q] = (c < C) ? s.logit[r * kCs + c] + s.dlog[r * kCs + c] + s.bias[c] : -INFINITY;
+      }
       float m = fmaxf(fmaxf(z[0], z[1]), fmaxf(z[2], z[3]));
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -335,10 +369,15 @@ sage_top_sup_kernel(const Params p, const __grid_constant__ CUtensorMap tmap_w, 
       const int n0 = 8 * warp;                            // this warp's 8 columns of h (both products)
       {
         float acc[4] = {0.f, 0.f, 0.f, 0.f}, cor[4] = {0.f, 0.f, 0.f, 0.f};   // dh[r][h] = sum_c dlog[r][c] Wc[c][h]
+        // B[k = class][n = column]: rows c0 + t and c0 + t + 4 of the swizzled Wc tile, column n0 + g
+        const int colw = n0 + g;
+        const unsigned char* wb0 = s.wc + (colw >> 5) * kWcBox + t * 128 + (((((colw & 31) >> 2)) ^ t) << 4) + (colw & 3) * 4;
+        const unsigned char* wb1 = s.wc + (colw >> 5) * kWcBox + (t + 4) * 128 + (((((colw & 31) >> 2)) ^ (t + 4)) << 4) + (colw & 3) * 4;
+#pragma unroll 2
         for (int c0 = 0; c0 < c_pad; c0 += 8) {
           const float a[4] = {s.dlog[g * kCs + c0 + t], s.dlog[(g + 8) * kCs + c0 + t], s.dlog[g * kCs + c0 + t + 4],
                               s.dlog[(g + 8) * kCs + c0 + t + 4]};
-          const float b[2] = {lds_swz(s.wc, c0 + t, n0 + g, kWcBox), lds_swz(s.wc, c0 + t + 4, n0 + g, kWcBox)};
+          const float b[2] = {*reinterpret_cast<const float*>(wb0 + c0 * 128), *reinterpret_cast<const float*>(wb1 + c0 * 128)};
           mma_split<SPLIT3>(acc, cor, a, b);
         }
         const int col = n0 + 2 * t;
@@ -354,6 +393,12 @@ sage_top_sup_kernel(const Params p, const __grid_constant__ CUtensorMap tmap_w, 
         }
       }
       GS_TOP_MARK(11);
+      // 64 CTAs adding into the same [C x 128] block serialise in the L2 atomic units (~60 cycles per add and address:
+      // 4K cycles of tail).  CTA b therefore adds into replica b % cls_reps (replica 0 = the gradient buffer itself,
+      // the others a side buffer the update kernel folds in and clears): 8 adds per address instead of 64.
+      const int rep = p.cls_reps > 1 ? static_cast<int>(blockIdx.x) % p.cls_reps : 0;
+      float* gcw = rep == 0 ? p.grad_cls_w : p.cls_w_rep + static_cast<int64_t>(rep - 1) * C * kH;
+      float* gcb = rep == 0 ? p.grad_cls_b : p.cls_b_rep + static_cast<int64_t>(rep - 1) * kMaxClasses;
       if (p.grad_cls_w) {
         for (int m0 = 0; m0 < c_pad; m0 += 16) {          // D[c][h] = sum_r dlog[r][c] h[r][h]
           float acc[4] = {0.f, 0.f, 0.f, 0.f}, cor[4] = {0.f, 0.f, 0.f, 0.f};
@@ -365,9 +410,9 @@ sage_top_sup_kernel(const Params p, const __grid_constant__ CUtensorMap tmap_w, 
             mma_split<SPLIT3>(acc, cor, a, b);
           }
           const int c = m0 + g, hcol = n0 + 2 * t;
-          if (c < C) atomicAdd(reinterpret_cast<float2*>(p.grad_cls_w + static_cast<int64_t>(c) * kH + hcol),
+          if (c < C) atomicAdd(reinterpret_cast<float2*>(gcw + static_cast<int64_t>(c) * kH + hcol),
                                make_float2(acc[0] + cor[0], acc[1] + cor[1]));
-          if (c + 8 < C) atomicAdd(reinterpret_cast<float2*>(p.grad_cls_w + static_cast<int64_t>(c + 8) * kH + hcol),
+          if (c + 8 < C) atomicAdd(reinterpret_cast<float2*>(gcw + static_cast<int64_t>(c + 8) * kH + hcol),
                                    make_float2(acc[2] + cor[2], acc[3] + cor[3]));
         }
       }
@@ -375,7 +420,7 @@ sage_top_sup_kernel(const Params p, const __grid_constant__ CUtensorMap tmap_w, 
         float sb = 0.f;
 #pragma unroll
         for (int r = 0; r < kTM; ++r) sb += s.dlog[r * kCs + tid];
-        atomicAdd(p.grad_cls_b + tid, sb);
+        atomicAdd(gcb + tid, sb);
       }
     }
     __syncthreads();
@@ -387,13 +432,25 @@ sage_top_sup_kernel(const Params p, const __grid_constant__ CUtensorMap tmap_w, 
       constexpr int NT = K / (8 * kWarps);                // n8 tiles per warp: 2 (K = 256) or 1 (gcn)
       float acc[NT][4] = {}, cor[NT][4] = {};
       const int c_base = warp * (K / kWarps);
-#pragma unroll 4
+      // B[k = output h][n = input column]: rows h0 + t and h0 + t + 4 of the swizzled W tile; (h & 7) = t or t + 4 for
+      // every h0, so a lane's two addresses per n-tile only advance by h0 * 128
+      const unsigned char* wb0[NT];
+      const unsigned char* wb1[NT];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int colw = c_base + 8 * nt + g;
+        const unsigned char* base = s.w + (colw >> 5) * kWBox + (colw & 3) * 4;
+        wb0[nt] = base + t * 128 + ((((colw & 31) >> 2) ^ t) << 4);
+        wb1[nt] = base + (t + 4) * 128 + ((((colw & 31) >> 2) ^ (t + 4)) << 4);
+      }
+      const float* da = &s.dz[g * kHs + t];
+      const float* db = &s.dz[(g + 8) * kHs + t];
+#pragma unroll
       for (int h0 = 0; h0 < kH; h0 += 8) {
-        const float a[4] = {s.dz[g * kHs + h0 + t], s.dz[(g + 8) * kHs + h0 + t], s.dz[g * kHs + h0 + t + 4],
-                            s.dz[(g + 8) * kHs + h0 + t + 4]};
+        const float a[4] = {da[h0], db[h0], da[h0 + 4], db[h0 + 4]};
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
-          const float b[2] = {lds_swz(s.w, h0 + t, c_base + 8 * nt + g, kWBox), lds_swz(s.w, h0 + t + 4, c_base + 8 * nt + g, kWBox)};
+          const float b[2] = {*reinterpret_cast<const float*>(wb0[nt] + h0 * 128), *reinterpret_cast<const float*>(wb1[nt] + h0 * 128)};
           mma_split<SPLIT3>(acc[nt], cor[nt], a, b);
         }
       }
@@ -469,7 +526,8 @@ extern "C" int gs_sage_top_sup(const float* table, int64_t ld_table, const int32
                                const int32_t* label_index, float* out_h, int64_t ld_h, float* out_agg, int64_t ld_agg,
                                float* out_dz, int64_t ld_dz, float* logp, float* loss, float* grad_cls_w,
                                float* grad_cls_b, float* grad_table, int64_t ld_gt, void* workspace,
-                               size_t workspace_bytes, int32_t precision, gs_stream_t stream) {
+                               size_t workspace_bytes, int32_t precision, float* cls_w_replicas, float* cls_b_replicas,
+                               int32_t cls_reps, gs_stream_t stream) {
   if (!table || !nbr_idx || !cnt || !weight || !cls_w || !labels || !loss || max_rows < 0) return GS_ERR_BAD_ARG;
   if (dim != top::kH || out_dim != top::kH || num_classes < 1 || num_classes > top::kMaxClasses || stride < 1 ||
       stride > top::kMaxStride)
@@ -483,10 +541,13 @@ extern "C" int gs_sage_top_sup(const float* table, int64_t ld_table, const int32
       (grad_cls_w && !aligned16(grad_cls_w)))
     return GS_ERR_ALIGNMENT;
   if (!workspace || workspace_bytes < gs_sage_top_workspace_bytes()) return GS_ERR_WORKSPACE;
+  if (cls_reps < 1 || cls_reps > 16 || (cls_reps > 1 && (!cls_w_replicas || !cls_b_replicas || !aligned16(cls_w_replicas))))
+    return GS_ERR_BAD_ARG;
+  if (cls_reps > 1 && ((num_classes * top::kH) & 3)) return GS_ERR_BAD_ARG;
   if (max_rows == 0) return GS_OK;
   top::Params p{table, ld_table, nbr_idx, stride, cnt, self_idx, num_rows_dev, max_rows, weight, ldw, cls_w, cls_b,
                 num_classes, labels, label_index, out_h, ld_h, out_agg, ld_agg, out_dz, ld_dz, logp, loss, grad_cls_w,
-                grad_cls_b, grad_table, ld_gt, reinterpret_cast<float*>(workspace) + 4,
+                grad_cls_b, cls_w_replicas, cls_b_replicas, cls_reps, grad_table, ld_gt, reinterpret_cast<float*>(workspace) + 4,
                 reinterpret_cast<unsigned int*>(workspace)};
   int tiles = (max_rows + top::kTM - 1) / top::kTM;
   // one tile per CTA while the tiles fit one wave; beyond that a persistent grid (W stays in shared memory)

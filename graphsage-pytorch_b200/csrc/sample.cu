@@ -23,12 +23,32 @@ constexpr int kSampleWarps = 8;
 //   mark              : K2's "mark" pass -- every id of the row (its node and the drawn neighbours) sets its bit
 //   clear             : K2's "clear" pass of the PREVIOUS unique -- the rows of this launch are exactly the ids that
 //                       unique emitted, so each row zeroes the bitmap word of its own node
+//   prefetch          the rows the NEXT kernel of the chain will gather (layer 1: the drawn neighbours' and the node's
+//                       own row of the feature table) are requested into L2 with one bulk prefetch each, so their DRAM
+//                       fetch runs under the launch gap and the ramp of the aggregation kernel instead of inside it
 struct SampleExtras {
   long long* queue;          // {address, rows, next, ticket}
   int32_t* fetch_dst;
   uint32_t* mark;
   uint32_t* clear;
+  const char* prefetch_table;
+  long long prefetch_ld_bytes;
+  int prefetch_row_bytes;    // multiple of 16
 };
+
+// One prefetch.global.L2 per 128-byte line a row touches (LSU path: a few cycles each).  The bulk form
+// (cp.async.bulk.prefetch.L2, one instruction per row) goes through the TMA unit at ~45 cycles per request and made the
+// sampler 4 us slower at 120K rows (measured, profiles/r2_l2_prefetch.txt).
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, int bytes) {
+#ifdef GS_PREFETCH_BULK
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+#else
+  const char* c = static_cast<const char*>(p);
+  const char* last = c + bytes - 1;
+  for (const char* q = c; q < last; q += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(last));
+#endif
+}
 
 __global__ void __launch_bounds__(kSampleWarps * 32)
 sample_neighbors_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t num_nodes,
@@ -103,7 +123,10 @@ sample_neighbors_kernel(const int64_t* __restrict__ rowptr, const int32_t* __res
       if (valid) {
         dst[rank] = val;
         if (ex.mark != nullptr) atomicOr(ex.mark + (val >> 5), 1u << (val & 31));
+        if (ex.prefetch_table != nullptr) prefetch_l2_bulk(ex.prefetch_table + val * ex.prefetch_ld_bytes, ex.prefetch_row_bytes);
       }
+      if (ex.prefetch_table != nullptr && lane == 31 && me >= 0 && me < num_nodes)
+        prefetch_l2_bulk(ex.prefetch_table + me * ex.prefetch_ld_bytes, ex.prefetch_row_bytes);
       for (int j = m + lane; j < stride; j += 32) dst[j] = -1;
       if (lane == 0) out_cnt[r] = m;
     }
@@ -318,7 +341,8 @@ extern "C" int gs_sample_neighbors_ex(const int64_t* rowptr, const int32_t* col,
                                       int32_t k, int32_t stride, int32_t self_mode, uint64_t seed, uint64_t offset,
                                       const int64_t* offset_dev, int32_t* out_nbr, int32_t* out_cnt,
                                       int64_t* queue_desc, int32_t* fetch_dst, uint32_t* mark_bitmap,
-                                      uint32_t* clear_bitmap, gs_stream_t stream) {
+                                      uint32_t* clear_bitmap, const void* prefetch_table, int64_t prefetch_ld_bytes,
+                                      int32_t prefetch_row_bytes, gs_stream_t stream) {
   if (!rowptr || !col || !out_nbr || !out_cnt) return GS_ERR_BAD_ARG;
   if (!nodes && !queue_desc) return GS_ERR_BAD_ARG;
   if (queue_desc && num_rows_dev) return GS_ERR_BAD_ARG;          // a queued batch has exactly max_rows seeds
@@ -328,7 +352,11 @@ extern "C" int gs_sample_neighbors_ex(const int64_t* rowptr, const int32_t* col,
   if (stride < k + (self_mode == GS_SELF_ONCE ? 1 : 0)) return GS_ERR_BAD_ARG;
   if (self_mode < GS_SELF_KEEP || self_mode > GS_SELF_ONCE) return GS_ERR_BAD_ARG;
   if (max_rows == 0) return GS_OK;
-  SampleExtras ex{reinterpret_cast<long long*>(queue_desc), fetch_dst, mark_bitmap, clear_bitmap};
+  if (prefetch_table && ((prefetch_row_bytes & 15) || prefetch_row_bytes < 16 || (prefetch_ld_bytes & 15) ||
+                         (reinterpret_cast<uintptr_t>(prefetch_table) & 15)))
+    return GS_ERR_ALIGNMENT;
+  SampleExtras ex{reinterpret_cast<long long*>(queue_desc), fetch_dst, mark_bitmap, clear_bitmap,
+                  static_cast<const char*>(prefetch_table), prefetch_ld_bytes, prefetch_row_bytes};
   launch(sample_neighbors_kernel, (max_rows + kSampleWarps - 1) / kSampleWarps, kSampleWarps * 32, 0, as_stream(stream),
          rowptr, col, num_nodes, nodes, num_rows_dev, max_rows, k, stride, self_mode, seed, offset, offset_dev, out_nbr,
          out_cnt, ex);
@@ -341,7 +369,7 @@ extern "C" int gs_sample_neighbors(const int64_t* rowptr, const int32_t* col, in
                                    const int64_t* offset_dev, int32_t* out_nbr, int32_t* out_cnt, gs_stream_t stream) {
   if (!nodes) return GS_ERR_BAD_ARG;
   return gs_sample_neighbors_ex(rowptr, col, num_nodes, nodes, num_rows_dev, max_rows, k, stride, self_mode, seed, offset,
-                                offset_dev, out_nbr, out_cnt, nullptr, nullptr, nullptr, nullptr, stream);
+                                offset_dev, out_nbr, out_cnt, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, stream);
 }
 
 extern "C" int gs_random_walk_pos(const int64_t* rowptr, const int32_t* col, int64_t num_nodes,

@@ -9,6 +9,7 @@ tensors are not on a CUDA device raises.  Reference lines are cited per method.
 """
 from __future__ import annotations
 
+import os
 import weakref
 from typing import Dict, List, Optional, Sequence
 
@@ -247,6 +248,10 @@ class GraphSage(nn.Module):
         self.adj_lists = adj_lists            # :235
         self.seed = int(torch.initial_seed() if seed is None else seed) & 0x7FFFFFFFFFFFFFFF
         self._calls = 0
+        #: GS_L2_PREFETCH=1 (off by default): the layer-1 sampler requests the feature rows it drew (and the nodes' own
+        #: rows) into L2 for the aggregation kernel that follows.  Measured: the aggregation drops from 13.1 to 10.6 us,
+        #: the sampler grows from 8.1 to 12.6 us (it becomes the DRAM-bound kernel), the step from 64.7 to 69.7 us
+        self.l2_prefetch = os.environ.get("GS_L2_PREFETCH", "0") == "1"
         self._native_state = None
         self._bitmap_ws = None
         self._injected = None
@@ -390,7 +395,10 @@ class GraphSage(nn.Module):
                                                       queue_desc=queue_desc if l == L else None,
                                                       fetch_dst=nodes if (l == L and queue_desc is not None) else None,
                                                       mark_bitmap=self._bitmap_ws if marks else None,
-                                                      clear_bitmap=self._bitmap_ws if clears else None)
+                                                      clear_bitmap=self._bitmap_ws if clears else None,
+                                                      prefetch_table=table if (l == 1 and self.l2_prefetch and
+                                                                               not isinstance(table, ShardedTable)) else None,
+                                                      prefetch_cols=self.input_size)
             if l > 1:   # unique + remap (src/models.py:286-288); the next frontier is U, ascending
                 prev = reuse[l - 2] if reuse is not None else None
                 outs = dict(uniq=prev.nodes, num_uniq=prev.num_rows, nbr_idx=old.nbr_idx, self_idx=old.self_idx) if old else {}

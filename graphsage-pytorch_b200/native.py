@@ -33,7 +33,7 @@ _SIGNATURES = {
     "gs_launch_count_reset": (None, []),
     "gs_set_pdl": (None, [_I]),
     "gs_sample_neighbors": (_I, [_P, _P, _L, _P, _P, _I, _I, _I, _I, _U64, _U64, _P, _P, _P, _P]),
-    "gs_sample_neighbors_ex": (_I, [_P, _P, _L, _P, _P, _I, _I, _I, _I, _U64, _U64, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gs_sample_neighbors_ex": (_I, [_P, _P, _L, _P, _P, _I, _I, _I, _I, _U64, _U64, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P]),
     "gs_fetch_batch": (_I, [_P, _I, _P, _P]),
     "gs_unique_remap_bitmap_ex": (_I, [_P, _P, _I, _P, _I, _L, _P, _P, _P, _P, _P, _SZ, _I, _P]),
     "gs_unique_workspace_bytes": (_SZ, [_I, _I]),
@@ -51,7 +51,7 @@ _SIGNATURES = {
     "gs_split_lo": (_I, [_P, _P, _L, _P]),
     "gs_sage_top_workspace_bytes": (_SZ, []),
     "gs_sage_top_sup": (_I, [_P, _L, _P, _I, _P, _P, _P, _I, _P, _L, _I, _I, _I, _P, _P, _I, _P, _P, _P, _L, _P, _L, _P, _L,
-                             _P, _P, _P, _P, _P, _L, _P, _SZ, _I, _P]),
+                             _P, _P, _P, _P, _P, _L, _P, _SZ, _I, _P, _P, _I, _P]),
     "gs_sage_gemm_bwd_w": (_I, [_P, _L, _P, _P, _L, _I, _P, _L, _P, _L, _I, _I, _I, _P, _I, _P, _L, _I, _P]),
     "gs_sage_gemm_bwd_w_pair": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _I, _P]),
     "gs_sage_gemm_bwd_x": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _P, _I, _P, _L, _P, _L, _I, _P]),
@@ -65,7 +65,7 @@ _SIGNATURES = {
     "gs_dp_state_bytes": (_SZ, []),
     "gs_dp_region_bytes": (_SZ, [_L, _I]),
     "gs_dp_region_recv_offset": (_SZ, []),
-    "gs_dp_allreduce_clip_sgd": (_I, [_P, _L, _P, _I, _I, _P, _P, _P, _P, _I, _F, _F, _P, _U64, _P, _P, _P]),
+    "gs_dp_allreduce_clip_sgd": (_I, [_P, _L, _P, _I, _I, _P, _P, _P, _P, _I, _F, _F, _P, _U64, _P, _P, _P, _P, _P, _P]),
     "gs_dp_status": (_I, [_P, _P, _P, _P, _P]),
     "gs_peer_alloc": (_I, [_SZ, _P]),
     "gs_peer_free": (_I, [_P]),

@@ -28,11 +28,13 @@ def _lib():
 # ----------------------------------------------------------------------------------------------
 def sample_neighbors(rowptr, col, num_nodes: int, nodes, num_rows, max_rows: int, k: int, stride: int,
                      self_mode: int, seed: int, offset: int, out_nbr=None, out_cnt=None, offset_dev=None, *,
-                     queue_desc=None, fetch_dst=None, mark_bitmap=None, clear_bitmap=None):
+                     queue_desc=None, fetch_dst=None, mark_bitmap=None, clear_bitmap=None, prefetch_table=None,
+                     prefetch_cols: int = 0):
     """src/models.py:279-285 on the device CSR -> (nbr [max_rows, stride] int32, cnt [max_rows] int32).
     Keyword extras fold neighbouring launches of a preparation chain into this one (gs_sample_neighbors_ex):
     `queue_desc` + `fetch_dst` = fetch_batch, `mark_bitmap` / `clear_bitmap` = the mark / clear passes of the bitmap
-    unique that follows / preceded."""
+    unique that follows / preceded, `prefetch_table` (+ `prefetch_cols` floats per row) = an L2 prefetch of the
+    table rows of every drawn id and of the node itself, for the gather kernel that follows."""
     dev = (nodes if nodes is not None else fetch_dst).device
     if dev.type != 'cuda':
         native.require_cuda(nodes if nodes is not None else fetch_dst, "nodes")
@@ -43,7 +45,10 @@ def sample_neighbors(rowptr, col, num_nodes: int, nodes, num_rows, max_rows: int
     check(_lib().gs_sample_neighbors_ex(ptr(rowptr), ptr(col), num_nodes, ptr(nodes) if queue_desc is None else None,
                                         ptr(num_rows), max_rows, k, stride, self_mode, seed & 0xFFFFFFFFFFFFFFFF,
                                         offset & 0xFFFFFFFFFFFFFFFF, ptr(offset_dev), ptr(out_nbr), ptr(out_cnt),
-                                        ptr(queue_desc), ptr(fetch_dst), ptr(mark_bitmap), ptr(clear_bitmap), stream()),
+                                        ptr(queue_desc), ptr(fetch_dst), ptr(mark_bitmap), ptr(clear_bitmap),
+                                        ptr(prefetch_table),
+                                        prefetch_table.stride(0) * prefetch_table.element_size() if prefetch_table is not None else 0,
+                                        pad4(prefetch_cols) * 4 if prefetch_table is not None else 0, stream()),
           "gs_sample_neighbors")
     return out_nbr, out_cnt
 
@@ -226,9 +231,11 @@ def sage_top_workspace(device) -> torch.Tensor:
 
 def sage_top_sup(table, nbr_idx, stride: int, cnt, self_idx, num_rows, max_rows: int, weight, gcn: bool, cls_w, cls_b,
                  labels, label_index, loss, grad_cls_w, grad_cls_b, grad_table, workspace, precision: int, *,
-                 out_h=None, out_agg=None, out_dz=None, logp=None):
+                 out_h=None, out_agg=None, out_dz=None, logp=None, cls_w_rep=None, cls_b_rep=None):
     """The top SageLayer + classifier + NLL, forward and backward, in one launch (gs_sage_top_sup).
-    Returns (h, agg, dz): the layer's output, and the B / A operands of its weight-gradient GEMM."""
+    Returns (h, agg, dz): the layer's output, and the B / A operands of its weight-gradient GEMM.
+    `cls_w_rep` [R-1, C*128] / `cls_b_rep` [R-1, 64] (zeroed): more replicas of the classifier gradients the CTAs spread
+    their atomic adds over; the fused update folds them in (peer.DpExchange(extras=...))."""
     native.require_cuda(table, "table")
     dev = table.device
     H = TOP_H
@@ -244,7 +251,8 @@ def sage_top_sup(table, nbr_idx, stride: int, cnt, self_idx, num_rows, max_rows:
                                  ptr(labels), ptr(label_index), ptr(out_h), out_h.stride(0), ptr(out_agg), out_agg.stride(0),
                                  ptr(out_dz), out_dz.stride(0), ptr(logp), ptr(loss), ptr(grad_cls_w), ptr(grad_cls_b),
                                  ptr(grad_table), grad_table.stride(0) if grad_table is not None else 0, ptr(workspace),
-                                 workspace.numel(), precision, stream()), "gs_sage_top_sup")
+                                 workspace.numel(), precision, ptr(cls_w_rep), ptr(cls_b_rep),
+                                 1 + (int(cls_w_rep.shape[0]) if cls_w_rep is not None else 0), stream()), "gs_sage_top_sup")
     return out_h, out_agg, out_dz
 
 

@@ -149,7 +149,8 @@ class DpExchange:
 
     def __init__(self, flat_grad: torch.Tensor, params: Sequence[torch.Tensor], offsets: Sequence[int],
                  groups: Sequence[int], *, world: int = 1, rank: int = 0, group=None, timeout_s: float = 10.0,
-                 region_ptrs: Optional[Sequence[int]] = None, params_lo: Optional[Sequence[Optional[torch.Tensor]]] = None):
+                 region_ptrs: Optional[Sequence[int]] = None, params_lo: Optional[Sequence[Optional[torch.Tensor]]] = None,
+                 extras: Optional[Sequence[Optional[torch.Tensor]]] = None):
         lib = native.load()
         self.lib, self.flat, self.world, self.rank = lib, flat_grad, int(world), int(rank)
         native.require_cuda(flat_grad, "flat gradient")
@@ -165,6 +166,13 @@ class DpExchange:
         self._plo = None
         if self._params_lo is not None:
             self._plo = (ctypes.c_void_p * n)(*[(t.data_ptr() if t is not None else None) for t in self._params_lo])
+        # extras[k]: [replicas, stride] more partial gradients of tensor k (zeroed; folded in and cleared by every update)
+        self._extras = list(extras) if extras is not None else None
+        self._ex = self._exn = self._exs = None
+        if self._extras is not None:
+            self._ex = (ctypes.c_void_p * n)(*[(t.data_ptr() if t is not None else None) for t in self._extras])
+            self._exn = (ctypes.c_int32 * n)(*[(int(t.shape[0]) if t is not None else 0) for t in self._extras])
+            self._exs = (ctypes.c_int64 * n)(*[(int(t.stride(0)) if t is not None else 0) for t in self._extras])
         self.num_segs = n
         self.state = torch.zeros((int(lib.gs_dp_state_bytes()),), dtype=torch.uint8, device=flat_grad.device)
         self.timeout_ns = int(timeout_s * 1e9)
@@ -184,7 +192,7 @@ class DpExchange:
                                                 self._p, self._o, self._n, self._g, self.num_segs, float(max_norm),
                                                 float(lr), self.state.data_ptr(), self.timeout_ns,
                                                 step_counter.data_ptr() if step_counter is not None else None,
-                                                self._plo, native.stream()),
+                                                self._plo, self._ex, self._exn, self._exs, native.stream()),
               "gs_dp_allreduce_clip_sgd")
 
     def status(self):

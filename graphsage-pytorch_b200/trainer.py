@@ -242,11 +242,20 @@ class SupervisedTrainer:
         self.weights_lo: List[Optional[torch.Tensor]] = [None] * n_sage
         if self.dense_x1:
             self.weights_lo[0] = ops.split_lo(self.weights[0].data)
+        # replicas of the classifier gradients (GS_CLS_REPS=8, off by default): the top-layer kernel's 64+ CTAs spread
+        # their atomic adds over them and the fused update folds them back in.  Measured: 0.8K of the kernel's 30K
+        # cycles saved, the same again spent in the update kernel -- the adds are issue-bound, not contention-bound.
+        self._cls_rep = None
+        reps = int(os.environ.get("GS_CLS_REPS", "1"))
+        if reps > 1 and exchange == "peer" and self.cls_w.numel() % 4 == 0 and self.cls_w.shape[1] == ops.TOP_H:
+            self._cls_rep = (torch.zeros((reps - 1, self.cls_w.numel()), dtype=torch.float32, device=dev),
+                             torch.zeros((reps - 1, ops.TOP_MAX_CLASSES), dtype=torch.float32, device=dev))
         if exchange == "peer":
             # clip groups follow src/utils.py:185-186: model 0 = graphSage, model 1 = classification
             self.dp = DpExchange(self.flat_grad, [p.data for p in params], offs, [0] * n_sage + [1, 1],
                                  world=world_size, rank=rank, group=process_group,
-                                 params_lo=self.weights_lo + [None, None])
+                                 params_lo=self.weights_lo + [None, None],
+                                 extras=([None] * n_sage + list(self._cls_rep)) if self._cls_rep is not None else None)
         #: poll the exchange's sticky status word every this many steps (0 = only at flush()/check()); a timed-out
         #: peer wait would otherwise leave the ranks training different weights silently
         self.status_every = 256
@@ -273,7 +282,7 @@ class SupervisedTrainer:
                 ops.sage_top_supported(m.out_size, m.out_size, int(self.cls_w.shape[0]), layers[-1].stride,
                                        _PRECISIONS[m.precision], m.agg_func == 'MEAN'))
 
-    def _train_on(self, layers, seeds):
+    def _train_on(self, layers, seeds, loss_out: Optional[torch.Tensor] = None):
         """forward of the layers -> classifier -> NLL -> backward into self.grads (src/utils.py:157-163,184) for the
         batch `seeds` whose frontiers `layers` _run_prep has prepared.  Default path: the layers below the top one as
         tcgen05 GEMMs, then ONE launch for the whole top layer (gather + mean, SageLayer, classifier, log-softmax,
@@ -282,8 +291,9 @@ class SupervisedTrainer:
         m = self.model
         weights = [w.detach() for w in self.weights]
         n_sage = len(self.weights)
+        loss_out = self.loss if loss_out is None else loss_out
         if not self._fused_top_ok(layers):
-            return self._train_on_unfused(layers, seeds, weights)
+            return self._train_on_unfused(layers, seeds, weights, loss_out)
         L, H = m.num_layers, m.out_size
         prec = _PRECISIONS[m.precision]
         below, top = layers[L - 2], layers[L - 1]
@@ -294,9 +304,11 @@ class SupervisedTrainer:
         top.table_in, top.dim_in = below.h, H
         top.h, top.agg, top.dz = ops.sage_top_sup(below.h, top.nbr_idx, top.stride, top.cnt, top.self_idx, top.num_rows,
                                                   top.rows_max, weights[L - 1], m.gcn, self.cls_w.detach(),
-                                                  self.cls_b.detach(), self.labels, seeds, self.loss, self.grads[n_sage],
+                                                  self.cls_b.detach(), self.labels, seeds, loss_out, self.grads[n_sage],
                                                   self.grads[n_sage + 1], g_below, self._top_ws, prec, out_h=top.h,
-                                                  out_agg=top.agg, out_dz=top.dz)
+                                                  out_agg=top.agg, out_dz=top.dz,
+                                                  cls_w_rep=self._cls_rep[0] if self._cls_rep else None,
+                                                  cls_b_rep=self._cls_rep[1] if self._cls_rep else None)
         top.argmax, dz = None, top.dz
         self.last_layers = layers
         if L == 2:
@@ -318,17 +330,17 @@ class SupervisedTrainer:
                         own_grad=True, top_masked=True, side_stream=None)
         main.wait_stream(self._side)
 
-    def _train_on_unfused(self, layers, seeds, weights):
+    def _train_on_unfused(self, layers, seeds, weights, loss_out):
         m = self.model
         n_sage = len(self.weights)
-        scatter_bufs, zeroed = _zero_beside(self._side, self.loss, m, layers)
+        scatter_bufs, zeroed = _zero_beside(self._side, loss_out, m, layers)
         layers = m._run_compute(layers, weights, weights_lo=self.weights_lo)
         self.last_layers = layers
         emb = layers[-1].h
         gemb = torch.empty_like(emb)
         torch.cuda.current_stream().wait_event(zeroed)
         ops.cls_nll_fwd_bwd(emb, m.out_size, self.cls_w.detach(), self.cls_b.detach(), self.cls_w.shape[0], self.labels,
-                            seeds, self.loss, gemb, self.grads[n_sage], self.grads[n_sage + 1],
+                            seeds, loss_out, gemb, self.grads[n_sage], self.grads[n_sage + 1],
                             precision=_PRECISIONS[m.precision], mask_relu_input=True, zero_loss=False)   # utils.py:153,161-163
         m._run_backward(layers, gemb, weights, [True] * n_sage, grad_bufs=self.grads[:n_sage], own_grad=True,
                         top_masked=True, side_stream=self._side, scatter_bufs=scatter_bufs)
@@ -359,7 +371,7 @@ class SupervisedTrainer:
         with torch.cuda.stream(side):
             for _ in range(2):
                 self._forward_backward()
-                self.flat_grad.zero_()
+                self._zero_grads()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(self.dev)
         before = native.launch_count()
@@ -375,7 +387,7 @@ class SupervisedTrainer:
                 self._update()
         self.launches_per_step = native.launch_count() - before
         self._fb_launches, self._up_launches = mid - before, native.launch_count() - mid
-        self.flat_grad.zero_()
+        self._zero_grads()
 
     def step_device(self, seeds_dev: torch.Tensor) -> torch.Tensor:
         """One step with the batch already in HBM (int32 [b_sz]).  Returns the device loss."""
@@ -392,6 +404,13 @@ class SupervisedTrainer:
         self.seeds_pinned.numpy()[:] = arr
         self.seeds.copy_(self.seeds_pinned, non_blocking=True)
         return self._run()
+
+    def _zero_grads(self):
+        """Clear the flat gradient and the replicas beside it (after a warm-up pass that did not update)."""
+        self.flat_grad.zero_()
+        if self._cls_rep is not None:
+            for t in self._cls_rep:
+                t.zero_()
 
     def check(self):
         """Raise if the fused exchange ever timed out waiting for a peer (synchronises the stream)."""
@@ -448,7 +467,7 @@ class PipelinedTrainer(SupervisedTrainer):
         loss = tr.flush()                      # trains on the (up to two) batches still in the pipeline
     `submit` / `submit_device` / `step` keep the one-call-per-batch form on top of the same machinery."""
 
-    RING = 4          # rows of the internal staging ring used by feed()/submit()
+    RING = 8          # rows of the internal staging ring used by feed()/submit(): two 3-step launches and the 2 in flight
     SLOTS = 3         # frontier slots: being trained on / aggregated / sampled
 
     def __init__(self, *args, **kwargs):
@@ -458,6 +477,7 @@ class PipelinedTrainer(SupervisedTrainer):
         dev = self.dev
         self.slot_seeds = [torch.zeros((self.b_sz,), dtype=torch.int32, device=dev) for _ in range(self.SLOTS)]
         self.slot_layers = [None] * self.SLOTS
+        self.slot_loss = torch.zeros((self.SLOTS,), dtype=torch.float32, device=dev)
         self.sample_counter = torch.zeros((1,), dtype=torch.int64, device=dev)
         self.queue_desc = torch.zeros((4,), dtype=torch.int64, device=dev)        # {address, rows, next, ticket}
         self._queue = None
@@ -580,7 +600,9 @@ class PipelinedTrainer(SupervisedTrainer):
         self.model._run_agg1(self.slot_layers[slot], dense_x=self.dense_x1)
 
     def _compute(self, slot: int, update: bool = True):
-        self._train_on(self.slot_layers[slot], self.slot_seeds[slot])
+        # the loss of the batch trained from slot s lands in slot_loss[s]: the three steps of a multi-step graph
+        # launch leave three losses behind (run() points self.loss at the last one)
+        self._train_on(self.slot_layers[slot], self.slot_seeds[slot], loss_out=self.slot_loss[slot:slot + 1])
         if update:
             self.dp.update(self.max_norm, self.lr, None)
 
@@ -622,7 +644,7 @@ class PipelinedTrainer(SupervisedTrainer):
                 self._aggregate(slot)
             for slot in range(self.SLOTS):
                 self._both(slot, update=False)
-                self.flat_grad.zero_()
+                self._zero_grads()
             self.sample_counter.copy_(saved[0])
             self.queue_desc.copy_(saved[1])
         torch.cuda.current_stream().wait_stream(side)
@@ -638,7 +660,7 @@ class PipelinedTrainer(SupervisedTrainer):
         with torch.cuda.graph(self._graph_multi):
             for slot in range(self.SLOTS):
                 self._both(slot)
-        self.flat_grad.zero_()
+        self._zero_grads()
 
     # ---- public ------------------------------------------------------------------------------------
     def prime(self):
@@ -679,6 +701,8 @@ class PipelinedTrainer(SupervisedTrainer):
             self._mark_fetched()
             self._cur = (self._cur + 1) % self.SLOTS
             n -= 1
+        last = (self._cur + self.SLOTS - 1) % self.SLOTS
+        self.loss = self.slot_loss[last:last + 1]
         return self.loss
 
     def flush(self) -> Optional[torch.Tensor]:
@@ -697,6 +721,7 @@ class PipelinedTrainer(SupervisedTrainer):
             if not self._agg_done:
                 self._aggregate(self._cur)
             self._compute(self._cur)
+            self.loss = self.slot_loss[self._cur:self._cur + 1]
             self._cur = (self._cur + 1) % self.SLOTS
             self._pending -= 1
             self._agg_done = False

@@ -92,13 +92,18 @@ int gs_sample_neighbors(const int64_t* rowptr, const int32_t* col, int64_t num_n
  *                           of a live row (its node and the drawn neighbours) sets its bit
  *   clear_bitmap            the "clear" pass of the PRECEDING gs_unique_remap_bitmap_ex (flag GS_UNIQUE_LEAVE_MARKS): the
  *                           rows of this call are exactly the ids it emitted; each zeroes the word of its own node.
- *                           Not together with mark_bitmap (they would race on a word). */
+ *                           Not together with mark_bitmap (they would race on a word).
+ *   prefetch_table          (layer 1) the table the next kernel gathers from: row id of every drawn neighbour and of the
+ *                           node itself is requested into L2 (cp.async.bulk.prefetch.L2, prefetch_row_bytes bytes at
+ *                           prefetch_table + id * prefetch_ld_bytes; both multiples of 16), so the DRAM fetch of the
+ *                           gathered rows starts here and overlaps the launch gap / ramp of gs_agg_fwd. */
 int gs_sample_neighbors_ex(const int64_t* rowptr, const int32_t* col, int64_t num_nodes,
                            const int32_t* nodes, const int32_t* num_rows_dev, int32_t max_rows,
                            int32_t k, int32_t stride, int32_t self_mode,
                            uint64_t seed, uint64_t offset, const int64_t* offset_dev,
                            int32_t* out_nbr, int32_t* out_cnt,
                            int64_t* queue_desc, int32_t* fetch_dst, uint32_t* mark_bitmap, uint32_t* clear_bitmap,
+                           const void* prefetch_table, int64_t prefetch_ld_bytes, int32_t prefetch_row_bytes,
                            gs_stream_t stream);
 
 /* Batch queue of the device-resident train loop (src/utils.py:141-145: every batch of an epoch
@@ -302,6 +307,10 @@ int gs_cls_nll_fwd_bwd(const float* emb, int64_t ld_emb, int32_t rows, int32_t d
  * Supported: dim == out_dim == 128, MEAN, num_classes <= 64, stride <= 16, precision TF32X3 / TF32 (mma.sync
  * m16n8k8 in the same 3-term split as K4); anything else returns GS_ERR_UNSUPPORTED and the caller runs the layer
  * as gs_agg_fwd -> gs_sage_gemm_fwd -> gs_cls_nll_fwd_bwd -> gs_sage_gemm_bwd_x -> gs_agg_bwd.
+ * cls_reps (1..16) > 1: CTA b adds its classifier-gradient contribution into replica b % cls_reps -- replica 0 is
+ * grad_cls_w / grad_cls_b, replica r > 0 is cls_w_replicas + (r-1)*num_classes*128 and cls_b_replicas + (r-1)*64 (both
+ * zeroed by the caller; gs_dp_allreduce_clip_sgd folds them in and clears them, see seg_extra_host): 64 CTAs adding into
+ * one block serialise in the L2 atomic units otherwise.
  * workspace: gs_sage_top_workspace_bytes() of device memory, zeroed ONCE by the caller (loss partials + a ticket
  * that every launch leaves at zero again); loss[0] is overwritten, nothing needs zeroing per step.
  * ------------------------------------------------------------------------------------ */
@@ -313,7 +322,8 @@ int gs_sage_top_sup(const float* table, int64_t ld_table, const int32_t* nbr_idx
                     const int32_t* label_index, float* out_h, int64_t ld_h, float* out_agg, int64_t ld_agg,
                     float* out_dz, int64_t ld_dz, float* logp, float* loss, float* grad_cls_w,
                     float* grad_cls_b, float* grad_table, int64_t ld_gt, void* workspace,
-                    size_t workspace_bytes, int32_t precision, gs_stream_t stream);
+                    size_t workspace_bytes, int32_t precision, float* cls_w_replicas, float* cls_b_replicas,
+                    int32_t cls_reps, gs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Update step of src/utils.py:185-187: per-model clip_grad_norm_(max_norm) then SGD.
@@ -352,7 +362,12 @@ int gs_dp_allreduce_clip_sgd(float* flat_grad, int64_t n_total, void* const* pee
                              int32_t world, float* const* seg_params_host, const int64_t* seg_offsets_host,
                              const int64_t* seg_numels_host, const int32_t* seg_groups_host, int32_t num_segs,
                              float max_norm, float lr, void* state, uint64_t timeout_ns, int64_t* step_counter,
-                             float* const* seg_params_lo_host, gs_stream_t stream);
+                             float* const* seg_params_lo_host, float* const* seg_extra_host,
+                             const int32_t* seg_extra_n_host, const int64_t* seg_extra_stride_host, gs_stream_t stream);
+/* seg_extra_host (nullable HOST array of num_segs nullable device pointers): tensor k has seg_extra_n_host[k] (1..16) more
+ * partial gradients, seg_extra_stride_host[k] floats apart (multiple of 4, >= numel rounded up to 4), which a producer
+ * spread its atomic adds over (gs_sage_top_sup's cls_reps); they are added to the flat gradient before the exchange and
+ * cleared. */
 /* seg_params_lo_host (nullable HOST array of num_segs nullable device pointers): buffers shaped like the parameters that
  * receive p - trunc_tf32(p) of every updated element (gs_sage_gemm_fwd_ex's weight_lo); gs_split_lo initialises one. */
 int gs_split_lo(const float* src, float* dst, int64_t n, gs_stream_t stream);

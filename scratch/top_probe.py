@@ -24,9 +24,13 @@ ws = ops.sage_top_workspace(dev)
 oh, oa, od = (torch.empty((rows, H), device=dev) for _ in range(3))
 prec = native.PREC_TF32X3 if os.environ.get('PREC', 'x3') == 'x3' else native.PREC_TF32
 
+reps = int(os.environ.get('REPS', 8))
+rw = torch.zeros((reps - 1, C * H), device=dev) if reps > 1 else None
+rb = torch.zeros((reps - 1, 64), device=dev) if reps > 1 else None
+
 def launch():
     ops.sage_top_sup(table, nbr, fan, cnt, self_idx, None, rows, w, False, cw, cb, labels, None, loss, gcw, gcb, gt, ws, prec,
-                     out_h=oh, out_agg=oa, out_dz=od)
+                     out_h=oh, out_agg=oa, out_dz=od, cls_w_rep=rw, cls_b_rep=rb)
 
 for _ in range(3):
     launch()

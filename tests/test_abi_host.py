@@ -170,3 +170,23 @@ def test_reference_arm_prints_the_contract_line(tmp_path):
     assert d["config"]["workload"].startswith("cfg3_products") and d["config"]["fanout"] == 10
     other = subprocess.run(cmd, capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2"), timeout=60)
     assert other.returncode == 0 and not [l for l in other.stdout.splitlines() if l.startswith("{")]
+
+
+def test_ctypes_signatures_have_the_arity_the_header_declares():
+    """Every entry of native._SIGNATURES must list exactly as many arguments as the declaration in include/gsage_b200.h
+    (a missing entry shifts every later argument: ctypes would pass a pointer where the library reads a size)."""
+    import os
+    import re
+    import graphsage_b200  # noqa: F401
+    from graphsage_b200 import native
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = re.sub(r'/\*.*?\*/', '', open(os.path.join(root, 'include', 'gsage_b200.h')).read(), flags=re.S)
+    bad = []
+    for name, (_, args) in native._SIGNATURES.items():
+        m = re.search(r'\b' + name + r'\s*\(([^;]*?)\)\s*;', hdr, flags=re.S)
+        assert m, f'{name} is bound but not declared in the header'
+        params = m.group(1).strip()
+        n = 0 if params in ('', 'void') else len(params.split(','))
+        if n != len(args):
+            bad.append((name, n, len(args)))
+    assert not bad, bad

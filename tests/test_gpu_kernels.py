@@ -527,12 +527,19 @@ def test_sage_top_sup_matches_torch_autograd(g, dev, gcn, classes, rows, live, p
     num_rows = None if live is None else torch.tensor([live], dtype=torch.int32, device=dev)
     ws = ops.sage_top_workspace(dev)
     prec = {'tf32x3': native.PREC_TF32X3, 'tf32': native.PREC_TF32}[precision]
+    # rows == 1024: the classifier gradients spread over 8 replicas, as the trainers launch the kernel
+    rep_w = torch.zeros((7, classes * H), device=dev) if rows == 1024 else None
+    rep_b = torch.zeros((7, 64), device=dev) if rows == 1024 else None
     for rep in range(2):                                   # twice: the ticket / partials of the workspace reset themselves
         g_table.zero_(); gcw.zero_(); gcb.zero_()
         out_h, out_agg, out_dz = ops.sage_top_sup(table_d, d(nbr), stride, d(cnt), d(self_idx), num_rows, rows, d(w), gcn,
                                                   d(cw), d(cb), d(labels), d(node_of_row), loss_d, gcw, gcb, g_table, ws,
-                                                  prec, logp=logp_d)
+                                                  prec, logp=logp_d, cls_w_rep=rep_w, cls_b_rep=rep_b)
         torch.cuda.synchronize()
+        if rep_w is not None:
+            assert float(rep_w.abs().max()) > 0                      # the replicas really took part of the adds
+            gcw += rep_w.sum(0).view(classes, H); gcb += rep_b[:, :classes].sum(0)
+            rep_w.zero_(); rep_b.zero_()
         assert rel(out_agg[:n_live], aggs) <= 1e-6
         assert rel(out_h[:n_live], h) <= tol
         assert rel(logp_d[:n_live], logp) <= tol

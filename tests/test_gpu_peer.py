@@ -89,6 +89,45 @@ def test_dp_update_world1_matches_torch_clip_sgd(P, dev, scale):
         assert rel(p, w) <= 1e-6
 
 
+@pytest.mark.parametrize('world', [1, 2])
+def test_dp_update_folds_gradient_replicas_and_keeps_weight_low_halves(P, dev, world):
+    """seg_extra (replicas a producer spread its atomics over) are summed into the gradient before the norm / the
+    exchange and cleared; seg_params_lo receives p - trunc_tf32(p) of the updated parameter."""
+    from graphsage_b200 import native, ops
+    lib = native.load()
+    shapes = [(128, 200), (47, 128), (47,)]
+    groups = [0, 1, 1]
+    params, offs, flat, grads = _flat_problem(dev, shapes, 21, 1.0)
+    gen = torch.Generator(device='cpu').manual_seed(4)
+    ex_w = torch.randn((7, 47 * 128), generator=gen).to(dev)
+    ex_b = torch.zeros((7, 64), device=dev)
+    ex_b[:, :47] = torch.randn((7, 47), generator=gen).to(dev)
+    w_lo = ops.split_lo(params[0])
+    total = [grads[0].clone(), grads[1] + ex_w.sum(0).view(47, 128), grads[2] + ex_b[:, :47].sum(0)]
+    kw = {}
+    if world == 2:      # the emulated peer contributes zeros: the mean halves the local sum
+        nbytes, recv_off = int(lib.gs_dp_region_bytes(flat.numel(), 2)), int(lib.gs_dp_region_recv_offset())
+        mine = torch.zeros((nbytes,), dtype=torch.uint8, device=dev)
+        theirs = torch.zeros((nbytes,), dtype=torch.uint8, device=dev)
+        mine[:recv_off].view(torch.int32).view(8, -1)[1].fill_(1)
+        kw = dict(region_ptrs=[mine.data_ptr(), theirs.data_ptr()])
+        total = [t * 0.5 for t in total]
+    want, _ = _torch_update(params, total, groups, 5.0, 0.7)
+    dp = P.DpExchange(flat, params, offs, groups, world=world, rank=0, params_lo=[w_lo, None, None],
+                      extras=[None, ex_w, ex_b], **kw)
+    dp.update(5.0, 0.7)
+    assert dp.status()[:2] == (1, 0)
+    for p, w in zip(params, want):
+        assert rel(p, w) <= 1e-6
+    assert float(ex_w.abs().max()) == 0.0 and float(ex_b.abs().max()) == 0.0 and float(flat.abs().max()) == 0.0
+    hi = (params[0].view(torch.int32) & -8192).view(torch.float32)
+    assert torch.equal(hi + w_lo, params[0])
+    if world == 2:      # what went over the wire already contained the replicas
+        their_recv = theirs[recv_off:].view(torch.float32).view(2, 2, flat.numel())
+        o = offs[1]
+        assert rel(their_recv[1, 0, o:o + 47 * 128], (total[1] * 2).reshape(-1)) <= 1e-6
+
+
 def test_dp_update_rank0_of_2_with_emulated_peer(P, dev):
     from graphsage_b200 import native
     lib = native.load()
