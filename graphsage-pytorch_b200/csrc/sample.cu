@@ -194,7 +194,7 @@ negative_sample_kernel(const int64_t* __restrict__ rowptr, const int32_t* __rest
                        const int32_t* __restrict__ seeds, int hops, int num_neg,
                        const int32_t* __restrict__ train_nodes, int num_train, uint64_t seed, uint64_t offset,
                        const int64_t* __restrict__ offset_dev, int32_t* __restrict__ neg, int32_t* __restrict__ neg_cnt,
-                       uint32_t* __restrict__ workspace) {
+                       uint32_t* __restrict__ workspace, const uint8_t* __restrict__ is_train) {
   pdl_sync();
   if (offset_dev != nullptr) offset += static_cast<uint64_t>(__ldg(offset_dev)) << 8;
   const int s = blockIdx.x;
@@ -204,18 +204,19 @@ negative_sample_kernel(const int64_t* __restrict__ rowptr, const int32_t* __rest
   uint32_t* bitmap = workspace + s * per_seed;
   int32_t* queue_a = reinterpret_cast<int32_t*>(bitmap + words);
   int32_t* queue_b = queue_a + num_nodes;
-  __shared__ int s_cur, s_next, s_far;
+  __shared__ int s_cur, s_next, s_far, s_ball_train;
   __shared__ uint32_t s_rank[GS_MAX_FANOUT * 4];
   __shared__ int s_scan[kNegThreads];
 
   for (int64_t w = tid; w < words; w += kNegThreads) bitmap[w] = 0u;
   const int32_t me = seeds[s];
-  if (tid == 0) { s_cur = 0; s_next = 0; }
+  if (tid == 0) { s_cur = 0; s_next = 0; s_ball_train = 0; }
   __syncthreads();
   if (tid == 0 && me >= 0 && me < num_nodes) {
     bitmap[me >> 5] |= 1u << (me & 31);
     queue_a[0] = me;
     s_cur = 1;
+    if (is_train != nullptr && is_train[me]) s_ball_train = 1;
   }
   __syncthreads();
   int32_t* cur_q = queue_a;
@@ -230,7 +231,10 @@ negative_sample_kernel(const int64_t* __restrict__ rowptr, const int32_t* __rest
         const int32_t u = col[e];
         const uint32_t bit = 1u << (u & 31);
         const uint32_t old = atomicOr(&bitmap[u >> 5], bit);
-        if (!(old & bit)) next_q[atomicAdd(&s_next, 1)] = u;
+        if (!(old & bit)) {
+          next_q[atomicAdd(&s_next, 1)] = u;
+          if (is_train != nullptr && is_train[u]) atomicAdd(&s_ball_train, 1);     // train nodes inside the ball
+        }
       }
     }
     __syncthreads();
@@ -239,6 +243,36 @@ negative_sample_kernel(const int64_t* __restrict__ rowptr, const int32_t* __rest
     __syncthreads();
   }
   __threadfence_block();
+  // ---- fast path (is_train given, plenty of far nodes): rejection sampling.  |far| = |train| - |train in ball| is known
+  //      from the marking pass; 32 candidates per round are drawn uniformly from the train list (one Philox block per
+  //      lane), those inside the ball or already taken are rejected, the rest are accepted in lane order -- the accepted
+  //      sequence is that of sequential rejection sampling, i.e. a uniform num_neg-subset of the far set (:164), without
+  //      walking the train list (twice) per seed as the exact path below does. ----
+  if (is_train != nullptr && num_train - s_ball_train >= 4 * num_neg) {
+    int32_t* dst = neg + static_cast<int64_t>(s) * num_neg;
+    if (warp == 0) {
+      int32_t* acc = reinterpret_cast<int32_t*>(s_rank);
+      int have = 0;
+      for (uint32_t round = 0; have < num_neg && round < 4096u; ++round) {
+        uint32_t draw[4];
+        philox4x32_10(static_cast<uint32_t>(s), round * 32u + lane, static_cast<uint32_t>(offset),
+                      static_cast<uint32_t>(offset >> 32), seed, draw);
+        const int32_t v = train_nodes[__umulhi(draw[0], static_cast<uint32_t>(num_train))];
+        bool ok = !((bitmap[v >> 5] >> (v & 31)) & 1u);
+        for (int j = 0; j < have; ++j) ok = ok && acc[j] != v;
+        const uint32_t same = __match_any_sync(0xffffffffu, ok ? static_cast<uint32_t>(v) : (0x80000000u | lane));
+        ok = ok && (same & ((1u << lane) - 1u)) == 0u;
+        const uint32_t m = __ballot_sync(0xffffffffu, ok);
+        const int pos = have + __popc(m & ((1u << lane) - 1u));
+        if (ok && pos < num_neg) { acc[pos] = v; dst[pos] = v; }
+        have = min(num_neg, have + __popc(m));
+        __syncwarp();
+      }
+      for (int j = have + lane; j < num_neg; j += 32) dst[j] = -1;           // (only if the round cap was hit)
+      if (lane == 0) neg_cnt[s] = have;
+    }
+    return;
+  }
   // count far train nodes
   int mine = 0;
   for (int i = tid; i < num_train; i += kNegThreads) {
@@ -390,17 +424,26 @@ extern "C" size_t gs_negative_workspace_bytes(int64_t num_nodes, int32_t num_see
   return static_cast<size_t>(num_seeds) * static_cast<size_t>(words + 2 * num_nodes) * sizeof(uint32_t);
 }
 
+extern "C" int gs_negative_sample_ex(const int64_t* rowptr, const int32_t* col, int64_t num_nodes,
+                                     const int32_t* seeds, int32_t num_seeds, int32_t hops, int32_t num_neg,
+                                     const int32_t* train_nodes, int32_t num_train, const uint8_t* is_train,
+                                     uint64_t seed, uint64_t offset, const int64_t* offset_dev, int32_t* neg,
+                                     int32_t* neg_cnt, void* workspace, size_t workspace_bytes, gs_stream_t stream) {
+  if (!rowptr || !col || !seeds || !train_nodes || !neg || !neg_cnt || !workspace) return GS_ERR_BAD_ARG;
+  if (num_neg < 1 || num_neg > GS_MAX_FANOUT * 4 || hops < 0 || num_seeds < 0 || num_train < 0) return GS_ERR_BAD_ARG;
+  if (workspace_bytes < gs_negative_workspace_bytes(num_nodes, num_seeds)) return GS_ERR_WORKSPACE;
+  if (num_seeds == 0) return GS_OK;
+  launch(negative_sample_kernel, num_seeds, kNegThreads, 0, as_stream(stream),
+      rowptr, col, num_nodes, seeds, hops, num_neg, train_nodes, num_train, seed, offset, offset_dev, neg, neg_cnt,
+      static_cast<uint32_t*>(workspace), is_train);
+  return finish_launch();
+}
+
 extern "C" int gs_negative_sample(const int64_t* rowptr, const int32_t* col, int64_t num_nodes,
                                   const int32_t* seeds, int32_t num_seeds, int32_t hops, int32_t num_neg,
                                   const int32_t* train_nodes, int32_t num_train, uint64_t seed, uint64_t offset,
                                   const int64_t* offset_dev, int32_t* neg, int32_t* neg_cnt, void* workspace,
                                   size_t workspace_bytes, gs_stream_t stream) {
-  if (!rowptr || !col || !seeds || !train_nodes || !neg || !neg_cnt || !workspace) return GS_ERR_BAD_ARG;
-  if (num_neg < 1 || num_neg > GS_MAX_FANOUT * 4 || hops < 0 || num_seeds < 0 || num_train < 0) return GS_ERR_BAD_ARG;
-  if (workspace_bytes < gs_negative_workspace_bytes(num_nodes, num_seeds)) return GS_ERR_WORKSPACE;
-  if (num_seeds == 0) return GS_OK;
-  launch(negative_sample_kernel, num_seeds, kNegThreads, 0, as_stream(stream), 
-      rowptr, col, num_nodes, seeds, hops, num_neg, train_nodes, num_train, seed, offset, offset_dev, neg, neg_cnt,
-      static_cast<uint32_t*>(workspace));
-  return finish_launch();
+  return gs_negative_sample_ex(rowptr, col, num_nodes, seeds, num_seeds, hops, num_neg, train_nodes, num_train, nullptr,
+                               seed, offset, offset_dev, neg, neg_cnt, workspace, workspace_bytes, stream);
 }

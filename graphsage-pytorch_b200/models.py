@@ -669,6 +669,7 @@ class UnsupervisedLoss(object):
         self.seed = int(torch.initial_seed() if seed is None else seed) & 0x7FFFFFFFFFFFFFFF
         self._calls = 0
         self._dev = None
+        self._train_distinct = False
         self._pairs = None
         self._host_pairs = None
         self.neg_hops = None             # None: negative_hops() decides (5 on Cora / Pubmed, as the reference)
@@ -683,6 +684,8 @@ class UnsupervisedLoss(object):
             train = torch.from_numpy(np.ascontiguousarray(np.asarray(self.train_nodes), dtype=np.int32)).to(dev)
             is_train = torch.zeros((csr.num_nodes,), dtype=torch.uint8, device=dev)
             is_train[train.long()] = 1
+            # the rejection sampler of gs_negative_sample_ex counts far nodes as |train| - |train in ball|: ids must be distinct
+            self._train_distinct = int(is_train.sum().item()) == int(train.numel())
             self._dev = (csr, train, is_train, dev)
         return self._dev
 
@@ -709,7 +712,8 @@ class UnsupervisedLoss(object):
         pos = ops.random_walk_pos(csr.rowptr, csr.col, csr.num_nodes, seeds, self.N_WALKS, self.WALK_LEN, is_train,
                                   self.seed, (self._calls << 8) | 1, offset_dev=offset_dev)      # :169-186
         neg, _ = ops.negative_sample(csr.rowptr, csr.col, csr.num_nodes, seeds, self.negative_hops(), int(num_neg), train,
-                                     self.seed, (self._calls << 8) | 2, offset_dev=offset_dev)   # :153-167
+                                     self.seed, (self._calls << 8) | 2, offset_dev=offset_dev,
+                                     is_train=is_train if self._train_distinct else None)      # :153-167
         lists = torch.cat([pos, neg], dim=1).contiguous()
         stride = n_pos + int(num_neg)
         uniq, num_uniq, idx, seed_idx = ops.unique_remap(seeds, None, s, lists, stride, csr.id_bits)    # :146

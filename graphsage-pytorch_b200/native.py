@@ -75,6 +75,7 @@ _SIGNATURES = {
     "gs_random_walk_pos": (_I, [_P, _P, _L, _P, _I, _I, _I, _P, _U64, _U64, _P, _P, _P]),
     "gs_negative_workspace_bytes": (_SZ, [_L, _I]),
     "gs_negative_sample": (_I, [_P, _P, _L, _P, _I, _I, _I, _P, _I, _U64, _U64, _P, _P, _P, _P, _SZ, _P]),
+    "gs_negative_sample_ex": (_I, [_P, _P, _L, _P, _I, _I, _I, _P, _I, _P, _U64, _U64, _P, _P, _P, _P, _SZ, _P]),
     "gs_pair_loss_fwd": (_I, [_P, _L, _I, _P, _I, _P, _P, _P, _P, _I, _F, _F, _P, _P, _P, _P, _P, _P]),
     "gs_pair_loss_bwd": (_I, [_P, _L, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P]),
 }

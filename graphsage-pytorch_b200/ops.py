@@ -396,7 +396,7 @@ def negative_workspace_bytes(num_nodes: int, num_seeds: int) -> int:
 
 
 def negative_sample(rowptr, col, num_nodes: int, seeds, hops: int, num_neg: int, train_nodes, seed: int, offset: int,
-                    workspace=None, out=None, out_cnt=None, offset_dev=None):
+                    workspace=None, out=None, out_cnt=None, offset_dev=None, is_train=None):
     n = seeds.shape[0]
     dev = seeds.device
     if workspace is None:
@@ -405,10 +405,10 @@ def negative_sample(rowptr, col, num_nodes: int, seeds, hops: int, num_neg: int,
         out = torch.empty((n, num_neg), dtype=I32, device=dev)
     if out_cnt is None:
         out_cnt = torch.empty((n,), dtype=I32, device=dev)
-    check(_lib().gs_negative_sample(ptr(rowptr), ptr(col), num_nodes, ptr(seeds), n, hops, num_neg, ptr(train_nodes),
-                                    train_nodes.shape[0], seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF,
-                                    ptr(offset_dev), ptr(out), ptr(out_cnt), ptr(workspace), workspace.numel(), stream()),
-          "gs_negative_sample")
+    check(_lib().gs_negative_sample_ex(ptr(rowptr), ptr(col), num_nodes, ptr(seeds), n, hops, num_neg, ptr(train_nodes),
+                                       train_nodes.shape[0], ptr(is_train), seed & 0xFFFFFFFFFFFFFFFF,
+                                       offset & 0xFFFFFFFFFFFFFFFF, ptr(offset_dev), ptr(out), ptr(out_cnt), ptr(workspace),
+                                       workspace.numel(), stream()), "gs_negative_sample")
     return out, out_cnt
 
 

@@ -59,48 +59,73 @@ def shard_batches(train: np.ndarray, b_sz: int, steps: int, rank: int, world: in
 
 
 class UnsupervisedTrainer:
-    """N1 for `learn_method` 'unsup' and 'plus_unsup' (src/utils.py:141-191, branches :165-181): one step = extend
-    the batch with random-walk positives and far negatives (device samplers), forward of the union, pair loss
-    (`unsup_loss` = 'normal' -> get_loss_sage with num_neg 100, 'margin' -> get_loss_margin with num_neg 6,
-    utils.py:119-125), for 'plus_unsup' also the classifier + NLL over the WHOLE extended batch (:161-164,
-    :169-174), backward, clip_grad_norm_(5) per model and SGD(lr 0.7) (:185-187; in 'unsup' mode the classifier
-    receives no gradient) -- without a host round trip: the size of the extended batch stays on the device
-    (`UnsupervisedLoss.extend_device`, `GraphSage._run_prep(num_rows=...)`, `gs_cls_nll_fwd_bwd(num_rows_dev)`),
-    where the drop-in `extend_nodes` has to hand a python list back to the reference's loop.
-    `use_graph=True` captures the whole step (about 27 launches of ours) as one CUDA graph: every buffer is sized by
-    its static bound, the batch is copied into a static seed buffer, and the samplers add a device-resident step
-    counter to their Philox offsets (`offset_dev`), so replay t draws what the eager step t draws."""
+    """N1 for every `learn_method` that needs the batch EXTENSION of src/utils.py:149 -- 'unsup', 'plus_unsup' and, with
+    `learn_method='sup'`, the reference's own supervised step, whose NLL is averaged over the extended batch
+    (src/utils.py:141-191, branches :159-181).  One step = extend the batch with random-walk positives and far
+    negatives (device samplers), forward of the union, pair loss (`unsup_loss` = 'normal' -> get_loss_sage with num_neg
+    100, 'margin' -> get_loss_margin with num_neg 6, utils.py:119-125; not for 'sup'), for 'plus_unsup' / 'sup' the
+    classifier + NLL over the WHOLE extended batch (:161-164, :169-174), backward, exchange, clip_grad_norm_(5) per
+    model and SGD(lr 0.7) (:185-187; in 'unsup' mode the classifier receives no gradient) -- without a host round trip:
+    the size of the extended batch stays on the device (`UnsupervisedLoss.extend_device`,
+    `GraphSage._run_prep(num_rows=...)`, `gs_cls_nll_fwd_bwd(num_rows_dev)`), where the drop-in `extend_nodes` has to
+    hand a python list back to the reference's loop.
+    Data parallel like SupervisedTrainer: the gradients live in one flat buffer and the fused exchange + clip + SGD
+    kernel (peer.DpExchange) ends the step at any `world_size`; every rank trains on its own seed slice.
+    `use_graph=True` captures the whole step as one CUDA graph: every buffer is sized by its static bound, the batch is
+    copied into a static seed buffer, and the samplers add a device-resident step counter to their Philox offsets
+    (`offset_dev`), so replay t draws what the eager step t draws.
+    A layer-1 width that is not a multiple of 4 (Reddit's 602) runs on zero-padded copies of W1 / dW1 so the GEMMs keep
+    their asynchronous tensor-core path (two tiny copies per step instead of register-staged operand loads)."""
 
     def __init__(self, model: GraphSage, unsupervised_loss, b_sz: int, *, unsup_loss: str = "normal",
                  learn_method: str = "unsup", classifier: Optional[Classification] = None, labels=None,
-                 lr: float = 0.7, max_norm: float = 5.0, use_graph: bool = False):
+                 lr: float = 0.7, max_norm: float = 5.0, use_graph: bool = False, process_group=None, world_size: int = 1,
+                 rank: int = 0):
         if unsup_loss not in ("normal", "margin"):
             raise ValueError("unsup_loss can be only 'margin' or 'normal'.")             # utils.py:124-125 (it exits)
-        if learn_method == "sup":
-            raise ValueError("learn_method 'sup' is SupervisedTrainer / PipelinedTrainer")
-        self.plus = learn_method == "plus_unsup"            # anything else trains on the pair loss alone (:175)
+        self.plus = learn_method in ("plus_unsup", "sup")   # a classifier head trained with the NLL of the extended batch
+        self.pairs = learn_method != "sup"                  # anything but 'sup' trains on the pair loss (:165-181)
         if self.plus and (classifier is None or labels is None):
-            raise ValueError("learn_method='plus_unsup' needs the classifier and the labels")
+            raise ValueError(f"learn_method='{learn_method}' needs the classifier and the labels")
         self.model, self.unsup, self.b_sz = model, unsupervised_loss, int(b_sz)
         self.mode = 1 if unsup_loss == "margin" else 0
         self.num_neg = 6 if unsup_loss == "margin" else 100                              # utils.py:119-123
-        self.lr, self.max_norm = lr, max_norm
+        self.lr, self.max_norm, self.world_size = lr, max_norm, int(world_size)
         _, _, dev = model._state()
         self.dev = dev
         self.weights: List[torch.Tensor] = [getattr(model, f'sage_layer{i}').weight for i in range(1, model.num_layers + 1)]
-        for p in self.weights:
-            native.require_cuda(p, "parameters")
-        self.grads = [torch.zeros_like(w.data) for w in self.weights]
-        self.tl = ops.TensorList([w.data for w in self.weights], self.grads)
+        params = list(self.weights)
         if self.plus:
             lin = classifier.layer[0]
-            native.require_cuda(lin.weight, "parameters")
             self.cls_w, self.cls_b = lin.weight, lin.bias
-            self.cls_grads = [torch.zeros_like(self.cls_w.data), torch.zeros_like(self.cls_b.data)]
-            self.tl_cls = ops.TensorList([self.cls_w.data, self.cls_b.data], self.cls_grads)
+            params += [self.cls_w, self.cls_b]
             self.labels = (labels if isinstance(labels, torch.Tensor) else
                            torch.from_numpy(np.asarray(labels, dtype=np.int64))).to(dev)
             self.loss_sup = torch.zeros((1,), dtype=torch.float32, device=dev)
+        for p in params:
+            native.require_cuda(p, "parameters")
+        if self.world_size > 1:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():          # replicas start identical: rank 0's parameters win
+                for p in params:
+                    dist.broadcast(p.data, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0,
+                                   group=process_group)
+        n_sage = len(self.weights)
+        offs, total = flat_layout([tuple(p.shape) for p in params])
+        self.flat_grad = torch.zeros((total,), dtype=torch.float32, device=dev)
+        self.grads = [self.flat_grad[o:o + p.numel()].view_as(p) for o, p in zip(offs, params)]
+        self.cls_grads = self.grads[n_sage:]
+        # clip groups follow src/utils.py:185-186: model 0 = graphSage, model 1 = classification
+        self.dp = DpExchange(self.flat_grad, [p.data for p in params], offs, [0] * n_sage + [1] * (len(params) - n_sage),
+                             world=self.world_size, rank=rank, group=process_group)
+        # zero-padded W1 / dW1 when the layer-1 width is not a multiple of 4 (see the class docstring)
+        f = model.input_size
+        self._pad = None
+        if f % 4 and _PRECISIONS[model.precision] != native.PREC_FP32:
+            f4 = ops.pad4(f)
+            cols = f4 if model.gcn else 2 * f4
+            self._pad = dict(f=f, f4=f4, w=torch.zeros((self.weights[0].shape[0], cols), dtype=torch.float32, device=dev),
+                             g=torch.zeros((self.weights[0].shape[0], cols), dtype=torch.float32, device=dev))
         self.one = torch.ones((1,), dtype=torch.float32, device=dev)
         self.loss = torch.zeros((1,), dtype=torch.float32, device=dev)
         self.last_layers = None
@@ -116,7 +141,10 @@ class UnsupervisedTrainer:
         """One training step on `seeds` (device int32 tensor, numpy array or list of b_sz node ids).  Returns the
         device loss ([1]); nothing is copied to the host."""
         if not self.use_graph:
-            return self._body(seeds, None)
+            before = native.launch_count()
+            out = self._body(seeds, None)
+            self.launches_per_step = native.launch_count() - before
+            return out
         from .models import _as_device_ids
         ids = _as_device_ids(seeds, self.dev)
         if ids.shape[0] != self.b_sz:
@@ -150,35 +178,65 @@ class UnsupervisedTrainer:
             self.step_counter.add_(1)
         self.launches_per_step = native.launch_count() - before
 
+    def _effective_weights(self):
+        """The weights the GEMMs read: W1 re-laid into its zero-padded copy when the input width needs it."""
+        weights = [w.detach() for w in self.weights]
+        if self._pad is not None:
+            f, f4, wp = self._pad['f'], self._pad['f4'], self._pad['w']
+            wp[:, :f].copy_(weights[0][:, :f])
+            if not self.model.gcn:
+                wp[:, f4:f4 + f].copy_(weights[0][:, f:])
+            weights[0] = wp
+        return weights
+
     def _body(self, seeds, offset_dev) -> torch.Tensor:
         m, u = self.model, self.unsup
         uniq, num_uniq = u.extend_device(seeds, self.num_neg, offset_dev=offset_dev)      # utils.py:149
-        weights = [w.detach() for w in self.weights]
-        layers = m._run_compute(m._run_prep(uniq, None, offset_dev=offset_dev, num_rows=num_uniq), weights)   # utils.py:157
+        weights = self._effective_weights()
+        layers = m._run_prep(uniq, None, offset_dev=offset_dev, num_rows=num_uniq)
+        if self._pad is not None:
+            layers[0].dim_in = self._pad['f4']                   # layer 1 contracts over the padded width (pad columns are zero)
+        layers = m._run_compute(layers, weights)                 # utils.py:157
         self.last_layers, self.last_count = layers, num_uniq
         emb = layers[-1].h
         p = u._pairs
-        loss, coef_pos, coef_neg, num_active = ops.pair_loss_fwd(emb, m.out_size, p['seed_idx'], p['pos_ptr'], p['pos_idx'],
-                                                                 p['neg_ptr'], p['neg_idx'], self.mode, float(u.Q),
-                                                                 float(u.MARGIN))         # utils.py:169-180
         gemb = torch.zeros_like(emb)
+        loss = None
+        if self.pairs:
+            loss, coef_pos, coef_neg, num_active = ops.pair_loss_fwd(emb, m.out_size, p['seed_idx'], p['pos_ptr'], p['pos_idx'],
+                                                                     p['neg_ptr'], p['neg_idx'], self.mode, float(u.Q),
+                                                                     float(u.MARGIN))     # utils.py:169-180
         if self.plus:
             # classifier + NLL mean over the extended batch (:161-164); writes its grad_emb rows, the pair loss adds to them
             ops.cls_nll_fwd_bwd(emb, m.out_size, self.cls_w.detach(), self.cls_b.detach(), self.cls_w.shape[0], self.labels,
                                 uniq, self.loss_sup, gemb, self.cls_grads[0], self.cls_grads[1],
                                 precision=_PRECISIONS[m.precision], mask_relu_input=False, num_rows=num_uniq)
-            loss = loss + self.loss_sup                                                   # :174
-        ops.pair_loss_bwd(emb, m.out_size, p['seed_idx'], p['pos_ptr'], p['pos_idx'], p['neg_ptr'], p['neg_idx'], coef_pos,
-                          coef_neg, num_active, self.one, gemb)                           # utils.py:184
-        m._run_backward(layers, gemb, weights, [True] * len(weights), grad_bufs=self.grads, own_grad=True)
-        ops.clip_sgd(self.tl, self.max_norm, self.lr, 1.0, zero_grads=True)              # utils.py:185-191
-        if self.plus:
-            ops.clip_sgd(self.tl_cls, self.max_norm, self.lr, 1.0, zero_grads=True)
+            loss = self.loss_sup if loss is None else loss + self.loss_sup                # :164 / :174
+        if self.pairs:
+            ops.pair_loss_bwd(emb, m.out_size, p['seed_idx'], p['pos_ptr'], p['pos_idx'], p['neg_ptr'], p['neg_idx'], coef_pos,
+                              coef_neg, num_active, self.one, gemb)                       # utils.py:184
+        n_sage = len(self.weights)
+        grad_bufs = list(self.grads[:n_sage])
+        if self._pad is not None:
+            self._pad['g'].zero_()
+            grad_bufs[0] = self._pad['g']
+        m._run_backward(layers, gemb, weights, [True] * n_sage, grad_bufs=grad_bufs, own_grad=True)
+        if self._pad is not None:                                # dW1 back into its place in the flat gradient
+            f, f4, gp = self._pad['f'], self._pad['f4'], self._pad['g']
+            self.grads[0][:, :f].copy_(gp[:, :f])
+            if not m.gcn:
+                self.grads[0][:, f:].copy_(gp[:, f4:f4 + f])
+        self.dp.update(self.max_norm, self.lr, None)             # exchange + clip per model + SGD + zero (utils.py:185-191)
         self.loss = loss
         return loss
 
     def step(self, nodes_batch) -> torch.Tensor:
         return self.step_device(nodes_batch)
+
+    def check(self):
+        """Raise if the fused exchange ever timed out waiting for a peer (synchronises the stream)."""
+        if self.world_size > 1:
+            self.dp.status()
 
 
 def _zero_beside(side: torch.cuda.Stream, loss: torch.Tensor, model: GraphSage, layers):

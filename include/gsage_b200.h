@@ -405,6 +405,16 @@ int gs_negative_sample(const int64_t* rowptr, const int32_t* col, int64_t num_no
                        const int64_t* offset_dev, int32_t* neg, int32_t* neg_cnt, void* workspace, size_t workspace_bytes,
                        gs_stream_t stream);
 
+/* is_train (nullable, num_nodes bytes, 1 for the ids in train_nodes, which must be distinct): with it the number of far
+ * train nodes is known from the marking pass (|train| - |train nodes in the ball|), and when at least 4 * num_neg of them
+ * exist the negatives are drawn by rejection sampling (uniform train node, rejected when inside the ball or already
+ * taken) instead of two walks over the whole train list per seed; same distribution, order of acceptance. */
+int gs_negative_sample_ex(const int64_t* rowptr, const int32_t* col, int64_t num_nodes,
+                          const int32_t* seeds, int32_t num_seeds, int32_t hops, int32_t num_neg,
+                          const int32_t* train_nodes, int32_t num_train, const uint8_t* is_train,
+                          uint64_t seed, uint64_t offset, const int64_t* offset_dev, int32_t* neg, int32_t* neg_cnt,
+                          void* workspace, size_t workspace_bytes, gs_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * K6  pair losses, src/models.py:65-132.  Pairs are grouped per seed: seed s owns
  * pos_idx[pos_ptr[s]..pos_ptr[s+1]) and neg_idx[neg_ptr[s]..), all row indices into `emb`

@@ -685,3 +685,92 @@ def test_sage_gemm_dense_tma_path(g, dev, precision, tol, rows, live, dim, gcn):
     out2 = g.sage_gemm_fwd(self_t, None if gcn else torch.arange(rows, dtype=torch.int32, device=dev), agg2, dim, w, H, gcn, nr,
                            rows, True, prec)
     assert rel(out2[:n_live], want) <= tol
+
+
+# ------------------------------------------------------------------------------------------------
+# distributional tests of the native samplers (they cannot match random's stream)
+# ------------------------------------------------------------------------------------------------
+def test_sampler_distribution_on_a_hub_row(g, dev):
+    """K1 on a hub (degree 5000, the cfg-3 case: Floyd's subset sampling over thousands of positions).  Every
+    neighbour must be included with probability k/deg (chi-square over 5000 cells), no draw may repeat inside a row,
+    and the draws of two rows / two offsets must be independent."""
+    deg, k, trials = 5000, 10, 200_000
+    rowptr = np.array([0, deg], dtype=np.int64)
+    col = np.arange(1, deg + 1, dtype=np.int32)
+    rp, cl = _csr_dev(rowptr, col, dev)
+    nodes = torch.zeros((trials,), dtype=torch.int32, device=dev)
+    nbr, cnt = g.sample_neighbors(rp, cl, deg + 1, nodes, None, trials, k, k, 0, 4242, 7)
+    nbr = nbr.cpu().numpy()
+    assert np.all(cnt.cpu().numpy() == k) and np.all(np.diff(nbr, axis=1) > 0)      # k distinct ids, ascending
+    counts = np.bincount(nbr.ravel(), minlength=deg + 1)[1:]
+    expect = trials * k / deg                                                        # 400 per cell
+    chi2 = ((counts - expect) ** 2 / (expect * (1 - k / deg))).sum()
+    dof = deg - 1
+    assert abs(chi2 - dof) < 6 * np.sqrt(2 * dof), chi2                              # +-6 sigma of chi2(4999)
+    # the first and the last position of the row are drawn as often as any other (Floyd's "take j" branch)
+    assert abs(counts[0] - expect) < 6 * np.sqrt(expect) and abs(counts[-1] - expect) < 6 * np.sqrt(expect)
+    # positions are not correlated with the pick order: mean of the j-th smallest id follows the order statistics
+    want_mean = (np.arange(1, k + 1) * (deg + 1)) / (k + 1)
+    assert np.allclose(nbr.mean(axis=0), want_mean, rtol=0.01)
+    # another offset gives another, equally uniform, draw; rows are independent of each other
+    nbr2, _ = g.sample_neighbors(rp, cl, deg + 1, nodes, None, trials, k, k, 0, 4242, 8)
+    nbr2 = nbr2.cpu().numpy()
+    same = (nbr[:20000, None, :] == nbr2[:20000, :, None]).any(axis=1).sum(axis=1).mean()
+    assert abs(same - k * k / deg) < 0.01, same                                      # E|A n B| = k^2/deg = 0.02
+
+
+def test_random_walk_positives_are_uniform_over_the_neighbour_row(g, dev):
+    """K5a, src/models.py:178: `random.choice(neighs)` -- each of the 6 one-step walks of a seed picks a neighbour
+    uniformly; picks outside the train set or equal to the seed yield no pair (-1) but still consume a draw."""
+    deg, walks, trials = 23, 6, 60_000
+    n = deg + 1
+    rowptr = np.zeros(n + 1, dtype=np.int64)
+    rowptr[1:] = deg                                       # node 0 has neighbours 1..deg, the others none
+    col = np.arange(1, deg + 1, dtype=np.int32)
+    rp, cl = _csr_dev(rowptr, col, dev)
+    is_train = np.ones(n, dtype=np.uint8)
+    is_train[[3, 7]] = 0                                   # two neighbours outside the train set: never a pair
+    seeds = torch.zeros((trials,), dtype=torch.int32, device=dev)
+    pos = g.random_walk_pos(rp, cl, n, seeds, walks, 1, torch.from_numpy(is_train).to(dev), 99, 3).cpu().numpy()
+    assert pos.shape == (trials, walks)
+    got = pos[pos >= 0]
+    assert not np.isin(got, [0, 3, 7]).any()
+    frac_pairs = (pos >= 0).mean()
+    assert abs(frac_pairs - (deg - 2) / deg) < 0.005                                 # 2 of 23 choices are rejected
+    counts = np.bincount(got, minlength=n)[1:]
+    live = np.delete(counts, [2, 6])                                                 # neighbours 3 and 7
+    expect = trials * walks / deg
+    chi2 = ((live - expect) ** 2 / expect).sum()
+    assert chi2 < 60, chi2                                                           # dof 20: p(>60) ~ 1e-6
+    # the 6 walks of a seed are independent draws: P(two given walks agree) = 1/deg
+    agree = (pos[:, 0] == pos[:, 1])[(pos[:, 0] >= 0) & (pos[:, 1] >= 0)].mean()
+    assert abs(agree - 1 / (deg - 2)) < 0.01
+
+
+def test_negative_sampler_is_uniform_over_the_far_train_nodes(g, dev):
+    """K5b, src/models.py:163-164: `random.sample(far_nodes, num_neg)` -- a uniform num_neg-subset of the train nodes
+    outside the seed's ball.  A path graph makes the ball known: with `hops` = 2 the ball of node 50 is 48..52."""
+    n, hops, num_neg, trials = 101, 2, 6, 30_000
+    src = np.arange(n - 1)
+    from graphsage_b200 import synth
+    rowptr, col = synth.edges_to_csr(n, src, src + 1)
+    rp, cl = _csr_dev(rowptr, col, dev)
+    train = np.arange(0, n, 2, dtype=np.int32)                                       # even nodes: 51 of them
+    far = np.setdiff1d(train, np.arange(48, 53))                                     # minus 48, 50, 52 -> 48 far nodes
+    seeds = torch.full((trials,), 50, dtype=torch.int32, device=dev)
+    is_train = np.zeros(n, dtype=np.uint8)
+    is_train[train] = 1
+    for flags in (None, torch.from_numpy(is_train).to(dev)):      # the exact walk over the train list / rejection sampling
+        neg, cnt = g.negative_sample(rp, cl, n, seeds, hops, num_neg, torch.from_numpy(train).to(dev), 7, 11, is_train=flags)
+        neg = neg.cpu().numpy()
+        assert np.all(cnt.cpu().numpy() == num_neg) and np.isin(neg, far).all()
+        assert all(len(set(r)) == num_neg for r in neg[:2000])                       # without replacement
+        counts = np.bincount(neg.ravel(), minlength=n)[far]
+        expect = trials * num_neg / len(far)
+        chi2 = ((counts - expect) ** 2 / (expect * (1 - num_neg / len(far)))).sum()
+        assert chi2 < 110, (chi2, flags is None)                                     # dof 47: p(>110) ~ 1e-6
+        pair = (neg[:, :1] < neg[:, 1:2]).mean() if flags is not None else 0.5       # acceptance order carries no bias
+        assert abs(pair - 0.5) < 0.02
+    # fewer far nodes than asked for: all of them, once each (:164)
+    few, few_cnt = g.negative_sample(rp, cl, n, seeds[:4], 60, num_neg, torch.from_numpy(train).to(dev), 7, 12)
+    assert np.all(few_cnt.cpu().numpy() == 0) and np.all(few.cpu().numpy() == -1)    # ball of 60 hops = the whole path

@@ -458,7 +458,9 @@ def test_train_classification_matches_the_reference_loop(M, use_graph):
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize('case,unsup_loss,learn', [('pubmed_max_unsup', 'normal', 'unsup'), ('cora_max_plus', 'margin', 'unsup'),
                                                    ('cora_gcn_margin', 'margin', 'plus_unsup'),
-                                                   ('cora_max_plus', 'normal', 'plus_unsup')])
+                                                   ('cora_max_plus', 'normal', 'plus_unsup'),
+                                                   ('cora_mean_sup', 'normal', 'sup'),          # BASELINE configs[0]
+                                                   ('odd_width_gcn', 'margin', 'plus_unsup')])  # 602-like width: padded W1
 @pytest.mark.parametrize('use_graph', [False, True])
 def test_unsupervised_trainer_matches_the_drop_in_loop(M, case, unsup_loss, learn, use_graph):
     """Same seeds and Philox offsets on both sides, so both draw the same pairs and neighbours: the trainer
@@ -467,7 +469,14 @@ def test_unsupervised_trainer_matches_the_drop_in_loop(M, case, unsup_loss, lear
     CUDA graph whose samplers read their Philox offset from a device step counter."""
     from graphsage_b200.trainer import UnsupervisedTrainer
     dev = torch.device('cuda:0')
-    inp = cases.build_inputs(case)
+    if case == 'odd_width_gcn':          # a feature width that is not a multiple of 4 (Reddit's 602): 50 columns, gcn
+        inp = cases.build_inputs('cora_gcn_margin')
+        from graphsage_b200 import synth
+        inp['feats'] = synth.features_normal(inp['feats'].shape[0], 50, seed=3)
+        wrng = np.random.default_rng(9)
+        inp['weights'] = [synth.xavier_uniform_np(wrng, inp['spec']['hidden'], 50), inp['weights'][1]]
+    else:
+        inp = cases.build_inputs(case)
     labels = inp['labels']
     num_neg = 100 if unsup_loss == 'normal' else 6
     model_a, cls_a, adj = build_models(M, inp, dev, seed=31)
@@ -481,8 +490,12 @@ def test_unsupervised_trainer_matches_the_drop_in_loop(M, case, unsup_loss, lear
         seeds = inp['train'][step * 20:(step + 1) * 20]
         batch = np.asarray(list(unsup_a.extend_nodes(seeds, num_neg=num_neg)))              # utils.py:149
         embs = model_a(batch)                                                              # utils.py:157
-        loss_a = unsup_a.get_loss_margin(embs, batch) if unsup_loss == 'margin' else unsup_a.get_loss_sage(embs, batch)
-        if learn == 'plus_unsup':                                                          # utils.py:161-174
+        if learn == 'sup':                                                                 # utils.py:159-164
+            logp = cls_a(embs)
+            loss_a = -torch.sum(logp[range(logp.size(0)), labels[batch]], 0) / len(batch)
+        else:
+            loss_a = unsup_a.get_loss_margin(embs, batch) if unsup_loss == 'margin' else unsup_a.get_loss_sage(embs, batch)
+        if learn == 'plus_unsup':                                                          # utils.py:165-174
             logp = cls_a(embs)
             loss_a = -torch.sum(logp[range(logp.size(0)), labels[batch]], 0) / len(batch) + loss_a
         loss_a.backward()                                                                  # utils.py:184
