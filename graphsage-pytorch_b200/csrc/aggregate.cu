@@ -242,8 +242,16 @@ __device__ __forceinline__ void bf16x8_add(float (&acc)[8], const uint4& v) {
   acc[6] += __uint_as_float(v.w << 16); acc[7] += __uint_as_float(v.w & 0xffff0000u);
 }
 
-// LPR = lanes per gathered row (16: two rows per warp instruction, dim <= 128; 32: one row, column loop)
-template <int LPR>
+__device__ __forceinline__ void bf16x8_max(float (&acc)[8], const uint4& v) {
+  acc[0] = fmaxf(acc[0], __uint_as_float(v.x << 16)); acc[1] = fmaxf(acc[1], __uint_as_float(v.x & 0xffff0000u));
+  acc[2] = fmaxf(acc[2], __uint_as_float(v.y << 16)); acc[3] = fmaxf(acc[3], __uint_as_float(v.y & 0xffff0000u));
+  acc[4] = fmaxf(acc[4], __uint_as_float(v.z << 16)); acc[5] = fmaxf(acc[5], __uint_as_float(v.z & 0xffff0000u));
+  acc[6] = fmaxf(acc[6], __uint_as_float(v.w << 16)); acc[7] = fmaxf(acc[7], __uint_as_float(v.w & 0xffff0000u));
+}
+
+// LPR = lanes per gathered row (16: two rows per warp instruction, dim <= 128; 32: one row, column loop).
+// MODE: GS_AGG_MEAN (src/models.py:311-314) or GS_AGG_MAX (:316-326; no argmax: the raw features take no gradient).
+template <int LPR, int MODE>
 __global__ void __launch_bounds__(kAggWarps * 32, 4)
 agg_fwd_bf16_sharded_kernel(const ShardTable tab_arg, int64_t ld, int dim8, const int32_t* __restrict__ nbr, int stride,
                             const int32_t* __restrict__ cnt, const int32_t* __restrict__ self_nodes,
@@ -271,7 +279,7 @@ agg_fwd_bf16_sharded_kernel(const ShardTable tab_arg, int64_t ld, int dim8, cons
     const bool active = c8 < dim8;
     float acc[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int k = 0; k < 8; ++k) acc[k] = MODE == GS_AGG_MEAN ? 0.f : -INFINITY;
     uint4 sv = make_uint4(0u, 0u, 0u, 0u);
     const bool self_here = active && me >= 0 && sub == 0;
     if (self_here) sv = ldg_stream_u4(row_ptr(me) + 8 * c8);
@@ -287,17 +295,21 @@ agg_fwd_bf16_sharded_kernel(const ShardTable tab_arg, int64_t ld, int dim8, cons
       }
 #pragma unroll
       for (int u = 0; u < kShardBatch; ++u)
-        if (ok[u]) bf16x8_add(acc, v[u]);
+        if (ok[u]) { if (MODE == GS_AGG_MEAN) bf16x8_add(acc, v[u]); else bf16x8_max(acc, v[u]); }
     }
     if (SUB == 2) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 16);
+      for (int k = 0; k < 8; ++k) {
+        const float o = __shfl_xor_sync(0xffffffffu, acc[k], 16);
+        acc[k] = MODE == GS_AGG_MEAN ? acc[k] + o : fmaxf(acc[k], o);
+      }
     }
     if (active) {
       // 8 fp32 outputs per column piece: with two half-warps each writes one float4 of them
       float* dst = out_agg + static_cast<int64_t>(r) * ld_agg + 8 * c8;
-      const float4 lo = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
-      const float4 hi = make_float4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);
+      const float sc = MODE == GS_AGG_MEAN ? inv : (n == 0 ? __int_as_float(0x7fc00000) : 1.0f);   // MAX of nothing: NaN
+      const float4 lo = make_float4(acc[0] * sc, acc[1] * sc, acc[2] * sc, acc[3] * sc);
+      const float4 hi = make_float4(acc[4] * sc, acc[5] * sc, acc[6] * sc, acc[7] * sc);
       if (SUB == 1 || sub == 0) *reinterpret_cast<float4*>(dst) = lo;
       if (SUB == 1 || sub == 1) *reinterpret_cast<float4*>(dst + 4) = hi;
       if (self_here) {
@@ -430,7 +442,8 @@ extern "C" int gs_agg_fwd_bf16_sharded(const void* const* shard_bases_host, int3
                                        int64_t ld, int32_t dim, const int32_t* nbr, int32_t stride, const int32_t* cnt,
                                        const int32_t* self_nodes, const int32_t* num_rows_dev, int32_t max_rows,
                                        float* out_agg, int64_t ld_agg, float* out_self, int64_t ld_self,
-                                       gs_stream_t stream) {
+                                       int32_t mode, gs_stream_t stream) {
+  if (mode != GS_AGG_MEAN && mode != GS_AGG_MAX) return GS_ERR_BAD_ARG;
   if (!shard_bases_host || num_shards < 1 || num_shards > kMaxShards || rows_per_shard < 1 || rows_per_shard > 0x7fffffffLL)
     return GS_ERR_BAD_ARG;
   if (!nbr || !cnt || !out_agg || dim < 1 || stride < 1 || stride > 32 || max_rows < 0) return GS_ERR_BAD_ARG;
@@ -448,14 +461,14 @@ extern "C" int gs_agg_fwd_bf16_sharded(const void* const* shard_bases_host, int3
   }
   if (max_rows == 0) return GS_OK;
   const int blocks = (max_rows + kAggWarps - 1) / kAggWarps;
-  set_kernel_carveout(dim8 <= 16 ? reinterpret_cast<const void*>(agg_fwd_bf16_sharded_kernel<16>)
-                                 : reinterpret_cast<const void*>(agg_fwd_bf16_sharded_kernel<32>),
-                      background_launches());
-  if (dim8 <= 16)
-    launch(agg_fwd_bf16_sharded_kernel<16>, blocks, kAggWarps * 32, 0, as_stream(stream), 
-        tab, ld, dim8, nbr, stride, cnt, self_nodes, num_rows_dev, max_rows, out_agg, ld_agg, out_self, ld_self);
-  else
-    launch(agg_fwd_bf16_sharded_kernel<32>, blocks, kAggWarps * 32, 0, as_stream(stream), 
-        tab, ld, dim8, nbr, stride, cnt, self_nodes, num_rows_dev, max_rows, out_agg, ld_agg, out_self, ld_self);
+#define GS_SHARD_LAUNCH(LPR, MODE)                                                                                   \
+  do {                                                                                                               \
+    set_kernel_carveout(reinterpret_cast<const void*>(agg_fwd_bf16_sharded_kernel<LPR, MODE>), background_launches()); \
+    launch(agg_fwd_bf16_sharded_kernel<LPR, MODE>, blocks, kAggWarps * 32, 0, as_stream(stream), tab, ld, dim8, nbr,   \
+           stride, cnt, self_nodes, num_rows_dev, max_rows, out_agg, ld_agg, out_self, ld_self);                     \
+  } while (0)
+  if (dim8 <= 16) { if (mode == GS_AGG_MEAN) GS_SHARD_LAUNCH(16, GS_AGG_MEAN); else GS_SHARD_LAUNCH(16, GS_AGG_MAX); }
+  else { if (mode == GS_AGG_MEAN) GS_SHARD_LAUNCH(32, GS_AGG_MEAN); else GS_SHARD_LAUNCH(32, GS_AGG_MAX); }
+#undef GS_SHARD_LAUNCH
   return finish_launch();
 }

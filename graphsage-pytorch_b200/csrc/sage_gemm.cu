@@ -254,7 +254,7 @@ using namespace gs;
 
 int gs_sage_gemm_fwd_tc(const float*, int64_t, const int32_t*, const float*, int64_t, int32_t, const float*, int64_t,
                         int32_t, int32_t, const int32_t*, int32_t, float*, int64_t, int32_t, int32_t, float*, int64_t,
-                        gs_stream_t);
+                        int32_t, gs_stream_t);
 int gs_sage_gemm_fwd_tma(const float*, const float*, int64_t, int32_t, const float*, const float*, int64_t, int32_t,
                          const int32_t*, int32_t, float*, int64_t, int32_t, int32_t, float*, int64_t, gs_stream_t);
 int gs_sage_gemm_bwd_x_tc(const float*, int64_t, const float*, int64_t, const float*, int64_t, int32_t, int32_t, int32_t,
@@ -273,7 +273,7 @@ extern "C" int gs_sage_gemm_fwd(const float* self_table, int64_t ld_self, const 
                                 const int32_t* num_rows_dev, int32_t max_rows,
                                 float* out, int64_t ld_out, int32_t relu, int32_t precision, gs_stream_t stream) {
   return gs_sage_gemm_fwd_ex(self_table, ld_self, self_idx, agg, ld_agg, dim, weight, ldw, out_dim, gcn, num_rows_dev,
-                             max_rows, out, ld_out, relu, precision, nullptr, 0, nullptr, nullptr, stream);
+                             max_rows, out, ld_out, relu, precision, nullptr, 0, nullptr, nullptr, 0, stream);
 }
 
 extern "C" int gs_sage_gemm_fwd_ex(const float* self_table, int64_t ld_self, const int32_t* self_idx,
@@ -282,8 +282,9 @@ extern "C" int gs_sage_gemm_fwd_ex(const float* self_table, int64_t ld_self, con
                                    const int32_t* num_rows_dev, int32_t max_rows,
                                    float* out, int64_t ld_out, int32_t relu, int32_t precision,
                                    float* zero_out, int64_t ld_zero, const float* x_lo, const float* weight_lo,
-                                   gs_stream_t stream) {
+                                   int32_t l2_normalize, gs_stream_t stream) {
   if (!weight || !out || out_dim < 1 || max_rows < 0) return GS_ERR_BAD_ARG;
+  if (l2_normalize && precision == GS_PREC_FP32) return GS_ERR_UNSUPPORTED;    // an epilogue of the tensor-core kernel
   if (zero_out && ld_zero < out_dim) return GS_ERR_BAD_ARG;
   if (int e = check_x(self_table, ld_self, agg, ld_agg, dim, gcn)) return e;
   if (ldw < (gcn ? dim : 2 * dim) || ld_out < out_dim) return GS_ERR_BAD_ARG;
@@ -298,14 +299,14 @@ extern "C" int gs_sage_gemm_fwd_ex(const float* self_table, int64_t ld_self, con
     // both operands supplied: the all-TMA kernel (sage_gemm_tma.cu).  Anything else: the gathered-operand kernel.
     const bool dense = self_idx == nullptr && (dim & 3) == 0 &&
                        (gcn ? true : (self_table != nullptr && agg == self_table + dim && ld_self == ld_agg));
-    if (dense && max_rows > 0 && (precision == GS_PREC_TF32 || (x_lo != nullptr && weight_lo != nullptr))) {
+    if (dense && !l2_normalize && max_rows > 0 && (precision == GS_PREC_TF32 || (x_lo != nullptr && weight_lo != nullptr))) {
       const int e = gs_sage_gemm_fwd_tma(gcn ? agg : self_table, x_lo, ld_agg, gcn ? dim : 2 * dim, weight, weight_lo, ldw,
                                          out_dim, num_rows_dev, max_rows, out, ld_out, relu, precision, zero_out, ld_zero,
                                          stream);
       if (e != GS_ERR_UNSUPPORTED) return e;
     }
     return gs_sage_gemm_fwd_tc(self_table, ld_self, self_idx, agg, ld_agg, dim, weight, ldw, out_dim, gcn,
-                               num_rows_dev, max_rows, out, ld_out, relu, precision, zero_out, ld_zero, stream);
+                               num_rows_dev, max_rows, out, ld_out, relu, precision, zero_out, ld_zero, l2_normalize, stream);
   }
   if (zero_out) {       // FFMA path: a memset node in front (the tensor-core path folds the fill into its epilogue)
     cudaError_t e = cudaMemset2DAsync(zero_out, static_cast<size_t>(ld_zero) * 4, 0, static_cast<size_t>(out_dim) * 4,

@@ -514,7 +514,9 @@ __device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 1, %0;
 template <bool A_MN, bool B_MN, bool SPLIT3, bool ASYNC, class LoadA, class LoadB, class Epi>
 __device__ __forceinline__ void gemm_core(const LoadA& load_a, const LoadB& load_b, const Epi& epi, int n_tile,
                                           int k_stages, int num_stages, unsigned char* smem, const void* gdummy,
-                                          const CUtensorMap* tmap_b = nullptr, int tma_b_row = 0, int tma_b_box_rows = 0) {
+                                          const CUtensorMap* tmap_b = nullptr, int tma_b_row = 0, int tma_b_box_rows = 0,
+                                          int l2norm = 0) {
+  // l2norm (forward only, n_tile == 128 == the whole output row): rows leave as relu(acc) / max(||relu(acc)||_2, 1e-12)
   // tmap_b != nullptr (K-major B only): the B tile of k-stage ks is the TMA box {32 k from 32*ks, tma_b_box_rows
   // rows from tma_b_row}; the producers only split it (hi/lo) once it has landed
   // ---- carve shared memory: [stages][A_hi, (A_lo), B_hi, (B_lo)], 1024-byte aligned ----
@@ -739,6 +741,15 @@ __device__ __forceinline__ void gemm_core(const LoadA& load_a, const LoadB& load
           const uint32_t a = stg_s + static_cast<uint32_t>(((m0 + u * kProducerWarps) * ldst + 4 * q) * 4);
           asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "r"(a));
         }
+        if (l2norm) {             // n4 == 32: the 32 lanes of the warp hold one whole row per u
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            v[u].x = fmaxf(v[u].x, 0.f); v[u].y = fmaxf(v[u].y, 0.f); v[u].z = fmaxf(v[u].z, 0.f); v[u].w = fmaxf(v[u].w, 0.f);
+            const float ss = warp_sum(v[u].x * v[u].x + v[u].y * v[u].y + v[u].z * v[u].z + v[u].w * v[u].w);
+            const float sc = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+            v[u].x *= sc; v[u].y *= sc; v[u].z *= sc; v[u].w *= sc;
+          }
+        }
 #pragma unroll
         for (int u = 0; u < 4; ++u) epi(m0 + u * kProducerWarps, 4 * q, v[u]);
       }
@@ -792,7 +803,7 @@ __global__ void __maxnreg__(kMaxRegs)
 sage_fwd_tc_kernel(XView x, const float* __restrict__ weight, int64_t ldw, int out_dim, bool vec_ok,
                    const int32_t* __restrict__ num_rows_dev, int max_rows, float* __restrict__ out, int64_t ld_out,
                    int relu, int n_tile, int k_stages, int num_stages, const __grid_constant__ CUtensorMap tmap_w,
-                   int use_tma_w, float* __restrict__ zero_out, int64_t ld_zero) {
+                   int use_tma_w, float* __restrict__ zero_out, int64_t ld_zero, int l2norm) {
   pdl_sync();
   extern __shared__ unsigned char smem_dyn[];
   const int rows = live_rows(num_rows_dev, max_rows);
@@ -805,7 +816,7 @@ sage_fwd_tc_kernel(XView x, const float* __restrict__ weight, int64_t ldw, int o
   LoadW_K lb{x, weight, ldw, h0, out_dim, vec_ok};
   StoreOut epi{out, ld_out, row0, rows, h0, out_dim, relu, zero_out, ld_zero};
   gemm_core<false, false, SPLIT3, ASYNC>(la, lb, epi, nt, k_stages, num_stages, smem_dyn, weight,
-                                         (ASYNC && use_tma_w) ? &tmap_w : nullptr, h0, n_tile);
+                                         (ASYNC && use_tma_w) ? &tmap_w : nullptr, h0, n_tile, l2norm);
 }
 
 template <bool SPLIT3, bool ASYNC>
@@ -945,12 +956,17 @@ using namespace gs::tc;
 int gs_sage_gemm_fwd_tc(const float* self_table, int64_t ld_self, const int32_t* self_idx, const float* agg,
                         int64_t ld_agg, int32_t dim, const float* weight, int64_t ldw, int32_t out_dim, int32_t gcn,
                         const int32_t* num_rows_dev, int32_t max_rows, float* out, int64_t ld_out, int32_t relu,
-                        int32_t precision, float* zero_out, int64_t ld_zero, gs_stream_t stream) {
+                        int32_t precision, float* zero_out, int64_t ld_zero, int32_t l2norm, gs_stream_t stream) {
   const bool split3 = precision == GS_PREC_TF32X3;
   if (precision != GS_PREC_TF32 && !split3) return GS_ERR_BAD_ARG;
   XView x{self_table, ld_self, self_idx, agg, ld_agg, dim, (dim + 3) & ~3, gcn, nullptr, 0, 0};
   const int kt = gcn ? x.dim_pad : 2 * x.dim_pad;
-  const Plan p = make_plan(out_dim, false, false, split3, (max_rows + kTileM - 1) / kTileM);
+  Plan p = make_plan(out_dim, false, false, split3, (max_rows + kTileM - 1) / kTileM);
+  if (l2norm) {                                    // the normalising epilogue needs the whole row in one CTA
+    if (out_dim != 128 || !relu) return GS_ERR_UNSUPPORTED;
+    p = make_plan(out_dim, false, false, split3, kNumSMs);
+    if (p.n_tile != 128) return GS_ERR_UNSUPPORTED;
+  }
   const int k_stages = (kt + kBK - 1) / kBK;
   const bool vec_ok = (dim % 4 == 0) && (ldw % 4 == 0) && aligned16(weight);
   const bool async = vec_ok;                       // X rows are always 16-byte aligned (padded tables)
@@ -960,7 +976,7 @@ int gs_sage_gemm_fwd_tc(const float* self_table, int64_t ld_self, const int32_t*
   memset(&tmap_w, 0, sizeof(tmap_w));
   const int use_tma_w = (async && out_dim % p.n_tile == 0 && make_tmap_2d(&tmap_w, weight, out_dim, kt, ldw, p.n_tile)) ? 1 : 0;
   GS_TC_LAUNCH(sage_fwd_tc_kernel, grid, p.smem, as_stream(stream), x, weight, ldw, out_dim, vec_ok, num_rows_dev,
-               max_rows, out, ld_out, relu, p.n_tile, k_stages, p.num_stages, tmap_w, use_tma_w, zero_out, ld_zero);
+               max_rows, out, ld_out, relu, p.n_tile, k_stages, p.num_stages, tmap_w, use_tma_w, zero_out, ld_zero, l2norm);
   return finish_launch();
 }
 

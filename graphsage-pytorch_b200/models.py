@@ -225,7 +225,7 @@ class GraphSage(nn.Module):
 
     def __init__(self, num_layers, input_size, out_size, raw_features, adj_lists, device, gcn=False, agg_func='MEAN',
                  *, num_sample: int = 10, precision: str = "tf32x3", seed: Optional[int] = None,
-                 unique_algo: str = "auto"):
+                 unique_algo: str = "auto", normalize: bool = False):
         super().__init__()
         if agg_func not in ('MEAN', 'MAX'):
             raise ValueError("agg_func must be 'MEAN' or 'MAX' (src/models.py:311,316)")
@@ -244,6 +244,9 @@ class GraphSage(nn.Module):
             raise ValueError("unique_algo must be 'auto', 'bitmap' or 'radix'")
         self.unique_algo = unique_algo        # K2 path: bitmap/rank (default when N <= 2^28) or radix sort
         self.precision = precision
+        #: row-L2-normalise every layer's output in the GEMM epilogue (the original GraphSAGE's step; this reference stops
+        #: at the ReLU, src/models.py:219, so the default is off).  Forward only: embeddings / inference.
+        self.normalize = bool(normalize)
         self.raw_features = raw_features      # :234
         self.adj_lists = adj_lists            # :235
         self.seed = int(torch.initial_seed() if seed is None else seed) & 0x7FFFFFFFFFFFFFFF
@@ -281,8 +284,6 @@ class GraphSage(nn.Module):
             native.load()
             feats = self.raw_features
             if isinstance(feats, ShardedTable):        # row-partitioned bf16 table, peer shards read over NVLink
-                if self.agg_func != 'MEAN':
-                    raise NotImplementedError("a ShardedTable supports agg_func='MEAN' (BASELINE configs[4])")
                 table = feats
             else:
                 if not isinstance(feats, torch.Tensor):
@@ -459,7 +460,7 @@ class GraphSage(nn.Module):
             # operand with the identity index (forward and backward)
             fr.agg, self_rows = ops.agg_fwd_sharded(table, fr.nbr_idx, fr.stride, fr.cnt, fr.nodes, fr.num_rows,
                                                     fr.rows_max, want_self=not self.gcn, out=fr.agg,
-                                                    out_self=self_rows_buf if not self.gcn else None)
+                                                    out_self=self_rows_buf if not self.gcn else None, mode=mode)
             fr.argmax, fr.table_in, fr.self_idx = None, self_rows, None
         else:
             fr.agg, fr.argmax = ops.agg_fwd(table, self.input_size, fr.nbr_idx, fr.stride, fr.cnt, fr.num_rows,
@@ -486,12 +487,19 @@ class GraphSage(nn.Module):
                                                 fr.rows_max, mode, out=fr.agg, argmax=fr.argmax)
             fr.h = ops.sage_gemm_fwd(None if self.gcn else fr.table_in, fr.self_idx, fr.agg, fr.dim_in, weights[l - 1],
                                      self.out_size, self.gcn, fr.num_rows, fr.rows_max, True, prec, out=fr.h,
-                                     zero_out=zero_grad_of_last if l == L else None,
+                                     zero_out=zero_grad_of_last if l == L else None, l2_normalize=self.normalize,
                                      x_lo=fr.x_lo if l == 1 else None,
                                      weight_lo=weights_lo[l - 1] if weights_lo is not None else None)
         return layers
 
     def _run_backward(self, layers: List[_Frontier], grad_out: torch.Tensor, weights, needs,
+                      *args, **kwargs):
+        if self.normalize:
+            raise NotImplementedError("normalize=True is a forward-only epilogue (embeddings / inference); "
+                                      "the reference's training path has no normalisation (src/models.py:219)")
+        return self._run_backward_impl(layers, grad_out, weights, needs, *args, **kwargs)
+
+    def _run_backward_impl(self, layers: List[_Frontier], grad_out: torch.Tensor, weights, needs,
                       grad_bufs=None, own_grad: bool = False, top_masked: bool = False,
                       side_stream: Optional[torch.cuda.Stream] = None,
                       scatter_bufs: Optional[Sequence[Optional[torch.Tensor]]] = None) -> List[Optional[torch.Tensor]]:

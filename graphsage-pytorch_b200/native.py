@@ -46,7 +46,7 @@ _SIGNATURES = {
     "gs_set_background": (None, [_I]),
     "gs_agg_bwd": (_I, [_P, _L, _P, _L, _I, _P, _I, _P, _P, _P, _L, _P, _I, _I, _P, _L, _P, _L, _P]),
     "gs_sage_gemm_fwd": (_I, [_P, _L, _P, _P, _L, _I, _P, _L, _I, _I, _P, _I, _P, _L, _I, _I, _P]),
-    "gs_sage_gemm_fwd_ex": (_I, [_P, _L, _P, _P, _L, _I, _P, _L, _I, _I, _P, _I, _P, _L, _I, _I, _P, _L, _P, _P, _P]),
+    "gs_sage_gemm_fwd_ex": (_I, [_P, _L, _P, _P, _L, _I, _P, _L, _I, _I, _P, _I, _P, _L, _I, _I, _P, _L, _P, _P, _I, _P]),
     "gs_agg_fwd_x": (_I, [_P, _L, _I, _P, _I, _P, _P, _P, _I, _I, _P, _L, _I, _P, _P]),
     "gs_split_lo": (_I, [_P, _P, _L, _P]),
     "gs_sage_top_workspace_bytes": (_SZ, []),
@@ -61,7 +61,7 @@ _SIGNATURES = {
     "gs_nll_fwd_bwd": (_I, [_P, _P, _P, _I, _I, _P, _P, _P]),
     "gs_cls_nll_fwd_bwd": (_I, [_P, _L, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _L, _P, _P, _P, _I, _I, _P, _I, _P]),
     "gs_clip_sgd": (_I, [_P, _P, _P, _I, _L, _F, _F, _F, _I, _P, _P]),
-    "gs_agg_fwd_bf16_sharded": (_I, [_P, _I, _L, _L, _I, _P, _I, _P, _P, _P, _I, _P, _L, _P, _L, _P]),
+    "gs_agg_fwd_bf16_sharded": (_I, [_P, _I, _L, _L, _I, _P, _I, _P, _P, _P, _I, _P, _L, _P, _L, _I, _P]),
     "gs_dp_state_bytes": (_SZ, []),
     "gs_dp_region_bytes": (_SZ, [_L, _I]),
     "gs_dp_region_recv_offset": (_SZ, []),

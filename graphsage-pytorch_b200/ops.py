@@ -139,8 +139,8 @@ def pad8(n: int) -> int:
 
 
 def agg_fwd_sharded(table, nbr, stride: int, cnt, self_nodes, num_rows, max_rows: int, want_self: bool = True,
-                    out=None, out_self=None):
-    """MEAN over a row-partitioned bf16 table (peer.ShardedTable), global node ids in `nbr`
+                    out=None, out_self=None, mode: int = native.AGG_MEAN):
+    """MEAN or MAX over a row-partitioned bf16 table (peer.ShardedTable), global node ids in `nbr`
     -> (agg fp32 [max_rows, pad8(dim)], self rows fp32 or None).  Remote shards are read over NVLink."""
     native.require_cuda(nbr, "nbr")
     ld = pad8(table.dim)
@@ -152,7 +152,7 @@ def agg_fwd_sharded(table, nbr, stride: int, cnt, self_nodes, num_rows, max_rows
                                          ptr(nbr), stride, ptr(cnt), ptr(self_nodes) if want_self else None,
                                          ptr(num_rows), max_rows, ptr(out), out.stride(0),
                                          ptr(out_self) if want_self else None,
-                                         out_self.stride(0) if want_self else 0, stream()), "gs_agg_fwd_bf16_sharded")
+                                         out_self.stride(0) if want_self else 0, mode, stream()), "gs_agg_fwd_bf16_sharded")
     return out, (out_self if want_self else None)
 
 
@@ -199,7 +199,8 @@ def split_lo(src, dst=None):
 
 
 def sage_gemm_fwd(self_table, self_idx, agg, dim: int, weight, out_dim: int, gcn: bool, num_rows, max_rows: int,
-                  relu: bool = True, precision: int = native.PREC_FP32, out=None, zero_out=None, x_lo=None, weight_lo=None):
+                  relu: bool = True, precision: int = native.PREC_FP32, out=None, zero_out=None, x_lo=None, weight_lo=None,
+                  l2_normalize: bool = False):
     """src/models.py:215-219 -> out [max_rows, pad4(out_dim)].  `zero_out` (optional, same shape as out) is
     zero-filled on the way: the buffer the backward of the layer above scatters d(out) into."""
     native.require_cuda(agg, "agg")
@@ -211,7 +212,7 @@ def sage_gemm_fwd(self_table, self_idx, agg, dim: int, weight, out_dim: int, gcn
                                      ptr(agg), agg.stride(0), dim, ptr(weight), weight.stride(0), out_dim, int(gcn),
                                      ptr(num_rows), max_rows, ptr(out), out.stride(0), int(relu), precision,
                                      ptr(zero_out), zero_out.stride(0) if zero_out is not None else 0, ptr(x_lo),
-                                     ptr(weight_lo), stream()),
+                                     ptr(weight_lo), int(l2_normalize), stream()),
           "gs_sage_gemm_fwd")
     return out
 

@@ -182,13 +182,14 @@ int gs_agg_bwd(const float* grad_agg, int64_t ld_ga, const float* grad_self, int
  * array of `num_shards` (<= 8) device pointers: shard s holds rows [s*rows_per_shard,
  * (s+1)*rows_per_shard) as bf16, `ld` elements apart (ld % 8 == 0); a base may be local HBM or
  * a peer mapping obtained with gs_peer_open -- gathered rows are then read straight over
- * NVLink, no collective.  nbr holds GLOBAL node ids (MEAN of src/models.py:311-314, fp32
- * accumulate).  out_self (nullable) receives the fp32 copy of row self_nodes[r]: the
+ * NVLink, no collective.  nbr holds GLOBAL node ids; mode GS_AGG_MEAN (src/models.py:311-314, fp32
+ * accumulate) or GS_AGG_MAX (:316-326; no argmax, the raw features take no gradient).  out_self (nullable) receives the fp32 copy of row self_nodes[r]: the
  * self_feats gather of src/models.py:265 for layer 1, which K4 then reads with self_idx = NULL. */
 int gs_agg_fwd_bf16_sharded(const void* const* shard_bases_host, int32_t num_shards, int64_t rows_per_shard,
                             int64_t ld, int32_t dim, const int32_t* nbr, int32_t stride, const int32_t* cnt,
                             const int32_t* self_nodes, const int32_t* num_rows_dev, int32_t max_rows,
-                            float* out_agg, int64_t ld_agg, float* out_self, int64_t ld_self, gs_stream_t stream);
+                            float* out_agg, int64_t ld_agg, float* out_self, int64_t ld_self, int32_t mode,
+                            gs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * K4  SageLayer.  Replaces src/models.py:215-219: out = relu(W . [self | agg]^T)^T with the
@@ -216,13 +217,17 @@ int gs_agg_fwd_x(const float* table, int64_t ld, int32_t dim, const int32_t* nbr
 /* x_lo / weight_lo (nullable): the low halves x - trunc_tf32(x) of the input rows (laid out like self_table .. agg,
  * which must then be one dense [max_rows x 2*dim] matrix: self_idx NULL, agg == self_table + dim, ld_self == ld_agg) and
  * of the weight.  With both given (or precision GS_PREC_TF32) the call runs the all-TMA kernel: no gather, no in-kernel
- * split. */
+ * split.
+ * l2_normalize != 0 (forward only; relu != 0, out_dim == 128, tensor-core precisions): the optional epilogue the original
+ * GraphSAGE applies and this reference does not (src/models.py:219 ends at the ReLU): every output row is divided by
+ * max(||row||_2, 1e-12).  Off everywhere the reference's numbers are reproduced. */
 int gs_sage_gemm_fwd_ex(const float* self_table, int64_t ld_self, const int32_t* self_idx,
                         const float* agg, int64_t ld_agg, int32_t dim,
                         const float* weight, int64_t ldw, int32_t out_dim, int32_t gcn,
                         const int32_t* num_rows_dev, int32_t max_rows,
                         float* out, int64_t ld_out, int32_t relu, int32_t precision,
-                        float* zero_out, int64_t ld_zero, const float* x_lo, const float* weight_lo, gs_stream_t stream);
+                        float* zero_out, int64_t ld_zero, const float* x_lo, const float* weight_lo,
+                        int32_t l2_normalize, gs_stream_t stream);
 
 /* dW[h,k] += sum_r dZ[r,h] X[r,k],  dZ = grad_out * (out > 0) when relu.  grad_w must be
  * zeroed by the caller (partials are accumulated with atomics). */

@@ -774,3 +774,23 @@ def test_negative_sampler_is_uniform_over_the_far_train_nodes(g, dev):
     # fewer far nodes than asked for: all of them, once each (:164)
     few, few_cnt = g.negative_sample(rp, cl, n, seeds[:4], 60, num_neg, torch.from_numpy(train).to(dev), 7, 12)
     assert np.all(few_cnt.cpu().numpy() == 0) and np.all(few.cpu().numpy() == -1)    # ball of 60 hops = the whole path
+
+
+def test_sage_gemm_l2_normalize_epilogue(g, dev):
+    """X1 (north_star item 3): the optional row-L2-normalise epilogue of K4, relu(X W^T) / max(||.||_2, 1e-12)
+    (torch.nn.functional.normalize), forward only, off by default."""
+    from graphsage_b200 import native
+    rng = np.random.default_rng(12)
+    rows, dim, H = 1000, 100, 128
+    tab = torch.from_numpy(rng.standard_normal((3000, dim)).astype(np.float32)).to(dev)
+    idx = torch.from_numpy(rng.integers(0, 3000, size=rows).astype(np.int32)).to(dev)
+    agg = torch.from_numpy(rng.standard_normal((rows, dim)).astype(np.float32)).to(dev)
+    w = torch.from_numpy((rng.standard_normal((H, 2 * dim)) * 0.1).astype(np.float32)).to(dev)
+    w[:, :] = torch.where(torch.arange(H, device=dev)[:, None] == 5, torch.zeros_like(w), w)      # some dead columns
+    out = g.sage_gemm_fwd(tab, idx, agg, dim, w, H, False, None, rows, True, native.PREC_TF32X3, l2_normalize=True)
+    x = torch.cat([tab[idx.long()], agg], 1).double()
+    want = torch.nn.functional.normalize(torch.relu(x @ w.double().t()), p=2, dim=1)
+    assert rel(out, want) <= 1e-5
+    assert torch.allclose(out.double().norm(dim=1), torch.ones(rows, dtype=torch.float64, device=dev), atol=1e-5)
+    with pytest.raises(RuntimeError):
+        g.sage_gemm_fwd(tab, idx, agg, dim, w, H, False, None, rows, True, native.PREC_FP32, l2_normalize=True)

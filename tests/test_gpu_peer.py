@@ -247,3 +247,66 @@ def test_two_ranks_over_cuda_ipc():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert 'MP_PEER_CHECK_OK' in out.stdout
+
+
+@pytest.mark.parametrize('agg_func', ['MEAN', 'MAX'])
+def test_sharded_gather_matches_the_oracle_on_a_device_generated_powerlaw_graph(P, dev, agg_func):
+    """The cfg-5 path against the ORACLE (oracle.aggregate, the reference's dense-mask algorithm, src/models.py:
+    291-326) -- not against another kernel of this repo: a down-scaled `synth.device_powerlaw_csr` graph (the
+    generator bench.py --workload cfg5 uses: rows repeat ids), bf16 table in 4 shards, native sampler draws, the
+    drawn lists replayed through the oracle on the bf16-rounded table.  MEAN within 1e-6 (fp32 accumulation of the
+    same bf16 values), MAX exactly."""
+    from graphsage_b200 import native, ops, synth
+    from oracle import sage_oracle as so
+    n, dim, rows, k = 60000, 128, 1500, 10
+    rowptr, col = synth.device_powerlaw_csr(n, 16.0, dev, seed=3)
+    rng = np.random.default_rng(8)
+    feats = torch.from_numpy(rng.standard_normal((n, dim)).astype(np.float32)).to(dev)
+    table = P.ShardedTable.from_full(feats, 4)
+    rounded = table.to_dense_fp32().cpu()                       # what the kernel really reads
+    nodes = torch.from_numpy(rng.choice(n, size=rows, replace=False).astype(np.int32)).to(dev)
+    nbr, cnt = ops.sample_neighbors(rowptr, col, n, nodes, None, rows, k, k, native.SELF_DROP, 5, 9)
+    mode = native.AGG_MEAN if agg_func == 'MEAN' else native.AGG_MAX
+    agg, selfr = ops.agg_fwd_sharded(table, nbr, k, cnt, nodes, None, rows, mode=mode)
+    torch.cuda.synchronize()
+    nbr_h, cnt_h, nodes_h = nbr.cpu().numpy(), cnt.cpu().numpy(), nodes.cpu().tolist()
+    keep = [i for i in range(rows) if cnt_h[i] > 0]              # the reference raises on an empty MAX row, NaN for MEAN
+    assert len(keep) > rows * 0.9
+    samp = [set(nbr_h[i, :cnt_h[i]].tolist()) | {nodes_h[i]} for i in keep]
+    uniq = sorted(set().union(*samp))
+    index_of = {v: j for j, v in enumerate(uniq)}
+    want = so.aggregate([nodes_h[i] for i in keep], rounded, (uniq, samp, index_of), False, agg_func)
+    got = agg[torch.as_tensor(keep, device=dev), :dim].cpu()
+    if agg_func == 'MAX':
+        assert torch.equal(got, want)
+    else:
+        assert rel(got, want) <= 1e-6
+    assert torch.equal(selfr[:, :dim].cpu(), rounded[torch.as_tensor(nodes_h)])
+    # repeated ids inside CSR rows (the generator draws targets with replacement) really occurred and were drawn as sets
+    rp, cl = rowptr.cpu().numpy(), col.cpu().numpy()
+    assert any(len(set(cl[rp[v]:rp[v + 1]].tolist())) < rp[v + 1] - rp[v] for v in nodes_h[:400])
+    assert all(len(set(nbr_h[i, :cnt_h[i]].tolist())) == cnt_h[i] for i in range(rows))
+
+
+def test_graphsage_max_over_a_sharded_table(P, dev):
+    """agg_func='MAX' over a ShardedTable (src/models.py:316-326): forward and weight gradients equal the same model
+    over the dense copy of the bf16 table."""
+    from graphsage_b200 import models
+    from graphsage_b200.graph import AdjCSR
+    rowptr, col = cases.load_topology('cora')
+    n = len(rowptr) - 1
+    rng = np.random.default_rng(4)
+    feats = torch.from_numpy(rng.standard_normal((n, 128)).astype(np.float32)).to(dev)
+    table = P.ShardedTable.from_full(feats, 4)
+    adj = AdjCSR(rowptr, col)
+    torch.manual_seed(0)
+    a = models.GraphSage(2, 128, 64, table, adj, dev, gcn=False, agg_func='MAX', seed=9, precision='fp32').to(dev)
+    b = models.GraphSage(2, 128, 64, table.to_dense_fp32(), adj, dev, gcn=False, agg_func='MAX', seed=9, precision='fp32').to(dev)
+    b.load_state_dict(a.state_dict())
+    batch = np.arange(0, n, 9)
+    ea, eb = a(batch), b(batch)
+    assert rel(ea, eb) <= 1e-5
+    ea.square().sum().backward()
+    eb.square().sum().backward()
+    for l in (1, 2):
+        assert rel(getattr(a, f'sage_layer{l}').weight.grad, getattr(b, f'sage_layer{l}').weight.grad) <= 1e-5
