@@ -691,10 +691,17 @@ def run_cfg4(args):
     configuration (its 5-hop exclusion ball is the whole graph: empty far set, src/models.py:164); negatives here are
     train nodes outside the seed's own neighbourhood (UnsupervisedLoss.negative_hops -> 1)."""
     import torch
+    import torch.distributed as dist
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the gsage_b200 hot path has no CPU fallback")
-    dev = torch.device("cuda", 0)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    args.gpus = world
+    dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
     import graphsage_b200  # noqa: F401
     from graphsage_b200 import models, native, ops
     from graphsage_b200.graph import AdjCSR
@@ -705,7 +712,11 @@ def run_cfg4(args):
     n = max(2000, int(round(cfg["n"] * args.scale)))
     edges = max(4 * n, int(round(cfg["edges"] * args.scale)))
     t0 = time.time()
+    if rank != 0 and world > 1:
+        dist.barrier()                                      # rank 0 builds (and caches) the graph first
     rowptr, col = synth.powerlaw_graph(n, edges, seed=0, cache_dir=CACHE_DIR)
+    if rank == 0 and world > 1:
+        dist.barrier()
     feats = synth.features_normal(n, cfg["feats"], seed=1)
     labels = synth.labels_uniform(n, cfg["classes"], seed=2)
     _, _, train = synth.split_nodes(n, seed=3)
@@ -714,37 +725,52 @@ def run_cfg4(args):
     torch.manual_seed(SEED)
     adj = AdjCSR(rowptr, col)
     model = models.GraphSage(2, cfg["feats"], cfg["hidden"], torch.from_numpy(feats).to(dev), adj, dev, gcn=True,
-                             agg_func="MEAN", seed=SEED, precision=args.precision).to(dev)
+                             agg_func="MEAN", seed=SEED + rank, precision=args.precision).to(dev)
     cls = models.Classification(cfg["hidden"], cfg["classes"]).to(dev)
-    unsup = models.UnsupervisedLoss(adj, train, dev, seed=SEED)
+    unsup = models.UnsupervisedLoss(adj, train, dev, seed=SEED + rank)
     trainer = UnsupervisedTrainer(model, unsup, b_sz, unsup_loss="margin", learn_method="plus_unsup", classifier=cls,
-                                  labels=labels, use_graph=not args.no_graph)
-    host_batches = batches_for(train, b_sz, 2 * (K + W) + 1, 0, 1)
+                                  labels=labels, use_graph=not args.no_graph, world_size=world, rank=rank)
+    host_batches = batches_for(train, b_sz, 2 * (K + W) + 1, rank, world)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
     dev_batches = torch.from_numpy(host_batches.astype(np.int32)).to(dev)
     for i in range(W):
         trainer.step_device(dev_batches[i])
-    torch.cuda.synchronize(dev)
+    sync_all()
     native.launch_count_reset()
-    sampler = ClockSampler(0)
-    sampler.start()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     t_begin = time.time()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for i in range(K):
         loss = trainer.step_device(dev_batches[W + i])
     b.record()
-    torch.cuda.synchronize(dev)
+    sync_all()
     launches = int(native.launch_count())
-    ms = a.elapsed_time(b)
+    ms = max_over_ranks(a.elapsed_time(b))
     # e2e: host numpy seeds in, loss value out, every step
     a.record()
     last = 0.0
     for i in range(K):
         last = float(trainer.step(host_batches[W + K + i]).item())
     b.record()
-    torch.cuda.synchronize(dev)
-    ms_e2e = a.elapsed_time(b)
-    clk = sampler.stop(t_begin, time.time())
+    sync_all()
+    ms_e2e = max_over_ranks(a.elapsed_time(b))
+    trainer.check()
+    clk = sampler.stop(t_begin, time.time()) if rank == 0 else None
+    same = replicas_identical(torch, dist, trainer.weights + [trainer.cls_w, trainer.cls_b], world, dev)
     # layer-1 aggregation of the last step, relaunched alone: rows of 602 floats (2.4 KB), self row included (gcn)
     fr = trainer.last_layers[0]
     rows = int(fr.num_rows.item()) if fr.num_rows is not None else fr.rows_max
@@ -767,17 +793,18 @@ def run_cfg4(args):
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
     except Exception:
         pass
-    line = {"metric": "seed_nodes_per_sec_fwd_bwd", "value": b_sz * K / (ms * 1e-3), "unit": "seed nodes/s", "n_gpus": 1,
+    line = {"metric": "seed_nodes_per_sec_fwd_bwd", "value": b_sz * world * K / (ms * 1e-3), "unit": "seed nodes/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (tcgen05 3xTF32 split, fp32-faithful)", "data": "synthetic",
             "config": {"workload": "cfg4_reddit" if args.scale == 1.0 else f"cfg4_reddit@scale{args.scale}", "nodes": n,
                        "csr_entries": int(len(col)), "feats": d, "hidden": cfg["hidden"], "classes": cfg["classes"],
                        "layers": 2, "fanout": 10, "agg": "MEAN", "gcn": True, "learn_method": "plus_unsup",
                        "unsup_loss": "margin", "num_neg": 6, "negative_radius_hops": unsup.negative_hops(),
-                       "b_sz_per_gpu": b_sz, "extended_batch_rows": int(trainer.last_count.item()),
+                       "b_sz_per_gpu": b_sz, "global_batch": b_sz * world, "parallelism": f"dp{world}", "extended_batch_rows": int(trainer.last_count.item()),
                        "cuda_graph": bool(trainer.use_graph),
                        "l2_policy": "feature table 561 MB >> 126 MB L2; fresh seeds every step"},
-            "e2e": {"value": b_sz * K / (ms_e2e * 1e-3), "unit": "seed nodes/s", "ms_per_step": ms_e2e / K,
+            "replicas_identical": same,
+            "e2e": {"value": b_sz * world * K / (ms_e2e * 1e-3), "unit": "seed nodes/s", "ms_per_step": ms_e2e / K,
                     "h2d_bytes_per_step": int(b_sz * 4), "d2h_bytes_per_step": 4},
             "gpu_launches": (trainer.launches_per_step * K if trainer.use_graph else launches),
             "launches_per_step": (trainer.launches_per_step if trainer.use_graph else launches // K),
@@ -787,7 +814,246 @@ def run_cfg4(args):
                          "traffic": None, "bytes_per_launch": float(bytes_), "us_per_launch": t_agg * 1e6, "rows": rows,
                          "note": "last step's layer-1 frontier relaunched alone 5x (gathers >> L2)"},
             "cpu_baseline": None, "clocks": clk}
-    print(json.dumps(line), flush=True)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs[0] / configs[1]: the reference's own CPU-runnable cases (--workload cfg1 | cfg2)
+#   cfg1  Cora topology (2708 nodes, 1433 binary features), 2-layer MEAN, learn_method sup, b_sz 20
+#   cfg2  Pubmed topology (19717 nodes, 500 features), 2-layer MAX, learn_method unsup, normal loss, b_sz 20
+# One step = one full `apply_model` iteration (src/utils.py:141-191): batch extension (random-walk positives, far
+# negatives, union), forward of the extended batch, loss, backward, clip per model, SGD.  A "seed node" is one of the
+# b_sz ids sliced at :145, before the extension.  Topologies ship under tests/golden/ (the .content feature files are
+# not part of the reference checkout: synthetic features of the documented shape).
+# ------------------------------------------------------------------------------------------------
+SMALL = {"cfg1": ("cora_mean_sup", "cfg1_cora"), "cfg2": ("pubmed_max_unsup", "cfg2_pubmed")}
+
+
+def _small_inputs(which):
+    for pth in (os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")):
+        if pth not in sys.path:
+            sys.path.insert(0, pth)
+    import cases
+    inp = cases.build_inputs(SMALL[which][0])
+    return inp, inp["spec"]
+
+
+def _small_batches(train, b_sz, n, seed=SEED):
+    rng = np.random.default_rng(seed)
+    perm = rng.permutation(train)
+    need = b_sz * n
+    if need > len(perm):
+        perm = np.concatenate([perm] * (need // len(perm) + 1))
+    return np.ascontiguousarray(perm[:need].reshape(n, b_sz)).astype(np.int64)
+
+
+def _apply_model_step(M, graphSage, classification, unsup, opt, labels, seeds, learn, unsup_loss, torch):
+    """The body of the reference's loop, src/utils.py:145-191 (without its print), for the classes of module M."""
+    num_neg = 6 if unsup_loss == "margin" else 100                                           # :119-122
+    nodes_batch = np.asarray(list(unsup.extend_nodes(seeds, num_neg=num_neg)))               # :149
+    labels_batch = labels[nodes_batch]                                                       # :153
+    embs = graphSage(nodes_batch)                                                            # :157
+    if learn in ("sup", "plus_unsup"):
+        logists = classification(embs)                                                       # :161
+        loss = -torch.sum(logists[range(logists.size(0)), labels_batch], 0) / len(nodes_batch)   # :162-163
+    if learn != "sup":
+        net = unsup.get_loss_margin(embs, nodes_batch) if unsup_loss == "margin" else unsup.get_loss_sage(embs, nodes_batch)
+        loss = loss + net if learn == "plus_unsup" else net                                  # :169-180
+    loss.backward()                                                                          # :184
+    for model in (graphSage, classification):
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 5)                                # :185-186
+    opt.step()                                                                               # :187
+    opt.zero_grad()
+    return float(loss.detach()), len(nodes_batch)
+
+
+def cpu_steps_small(which, warmup, steps, budget_s):
+    """The reference itself (baseline/_ref) on the host cores: full apply_model iterations.  Returns (seconds per timed
+    step, kind, mean extended batch)."""
+    import random
+    import torch
+    from oracle import sage_oracle as so
+    inp, spec = _small_inputs(which)
+    ref = _ref_modules()
+    if ref is None:
+        raise RuntimeError("baseline/_ref is not staged (python baseline/make_ref.py): the small configurations are "
+                           "timed on the reference's own classes")
+    random.seed(SEED); np.random.seed(SEED); torch.manual_seed(SEED)
+    adj = so.csr_to_adj_dict(inp["rowptr"], inp["col"])                                      # src/dataCenter.py:33
+    dev = torch.device("cpu")
+    feats = torch.from_numpy(inp["feats"])
+    graphSage = ref.GraphSage(2, feats.shape[1], spec["hidden"], feats, adj, dev, gcn=spec["gcn"], agg_func=spec["agg"])
+    classification = ref.Classification(spec["hidden"], spec["classes"])
+    unsup = ref.UnsupervisedLoss(adj, inp["train"], dev)
+    opt = torch.optim.SGD(list(graphSage.parameters()) + list(classification.parameters()), lr=0.7)
+    batches = _small_batches(inp["train"], spec["b_sz"], warmup + steps)
+    times, ext = [], []
+    t_start = time.perf_counter()
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        _, n_ext = _apply_model_step(ref, graphSage, classification, unsup, opt, inp["labels"], batches[i], spec["learn"],
+                                     spec["unsup_loss"], torch)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt); ext.append(n_ext)
+        if len(times) >= 3 and time.perf_counter() - t_start + dt > budget_s:
+            break
+    return times, "reference", float(np.mean(ext))
+
+
+def small_config(which, spec, inp, extended):
+    return {"workload": SMALL[which][1], "nodes": int(len(inp["rowptr"]) - 1), "csr_entries": int(len(inp["col"])),
+            "feats": int(inp["feats"].shape[1]), "hidden": spec["hidden"], "classes": spec["classes"], "layers": 2,
+            "fanout": 10, "agg": spec["agg"], "gcn": spec["gcn"], "learn_method": spec["learn"],
+            "unsup_loss": spec["unsup_loss"], "b_sz_per_gpu": spec["b_sz"], "global_batch": spec["b_sz"],
+            "parallelism": "dp1", "batch_extension": True, "extended_batch_rows": extended,
+            "step": "one apply_model iteration: extend -> forward -> loss -> backward -> clip per model -> SGD",
+            "l2_policy": "whole graph fits in L2 (the reference's own small cases); fresh seeds every step"}
+
+
+def run_small_reference(args, which):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    inp, spec = _small_inputs(which)
+    warm = min(args.warmup, 3)
+    t0 = time.time()
+    times, kind, ext = cpu_steps_small(which, warm, args.steps, args.ref_budget_s)
+    sec = float(np.sum(times))
+    value = spec["b_sz"] * len(times) / sec
+    cores = torch.get_num_threads()
+    sample = (f"{len(times)} timed apply_model iterations (of {args.steps} asked) + {warm} warm-up, b_sz {spec['b_sz']}, "
+              f"extended batch ~{ext:.0f} nodes; the reference's own classes (baseline/_ref), device cpu, {cores} threads, "
+              f"{time.time() - t0:.0f}s wall")
+    print(json.dumps({"impl": "reference", "metric": "seed_nodes_per_sec_fwd_bwd", "value": value, "unit": "seed nodes/s",
+                      "n_gpus": args.gpus, "steps": len(times), "steps_requested": args.steps, "warmup": warm,
+                      "ms_per_step": 1e3 * sec / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "f32", "data": "synthetic features on the shipped topology",
+                      "config": small_config(which, spec, inp, ext),
+                      "cpu_baseline": {"value": value, "unit": "seed nodes/s", "cores": cores, "kind": kind, "sample": sample},
+                      "e2e": {"value": value, "unit": "seed nodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                      "gpu_launches": 0}), flush=True)
+
+
+def run_small(args, which):
+    """cfg1 / cfg2 on one B200: the device-resident trainer (`value`: one CUDA-graph replay per apply_model iteration;
+    `e2e`: the same from host numpy batches with the loss read back every step) and, beside it, the reference's loop
+    body run UNCHANGED against the drop-in classes (`dropin_loop`: eager autograd, python lists from extend_nodes)."""
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the gsage_b200 hot path has no CPU fallback")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    import graphsage_b200  # noqa: F401
+    from graphsage_b200 import models, native, ops
+    from graphsage_b200.graph import AdjCSR
+    from graphsage_b200.trainer import UnsupervisedTrainer
+    native.load()
+    inp, spec = _small_inputs(which)
+    b_sz, K, W = spec["b_sz"], max(10, min(args.steps, 200)), max(3, min(args.warmup, 10))
+    windows = max(1, min(args.windows, 9))
+    feats = torch.from_numpy(inp["feats"]).to(dev)
+    adj = AdjCSR(inp["rowptr"], inp["col"])
+
+    def build():
+        torch.manual_seed(SEED)
+        m = models.GraphSage(2, feats.shape[1], spec["hidden"], feats, adj, dev, gcn=spec["gcn"], agg_func=spec["agg"],
+                             seed=SEED, precision=args.precision).to(dev)
+        c = models.Classification(spec["hidden"], spec["classes"]).to(dev)
+        u = models.UnsupervisedLoss(adj, inp["train"], dev, seed=SEED)
+        return m, c, u
+
+    model, cls, unsup = build()
+    trainer = UnsupervisedTrainer(model, unsup, b_sz, unsup_loss=spec["unsup_loss"], learn_method=spec["learn"], classifier=cls,
+                                  labels=inp["labels"], use_graph=not args.no_graph)
+    host = _small_batches(inp["train"], b_sz, W + K * windows + 1)
+    devb = torch.from_numpy(host.astype(np.int32)).to(dev)
+    for i in range(W):
+        trainer.step_device(devb[i])
+    torch.cuda.synchronize(dev)
+    clocks = ClockSampler(0)
+    clocks.start()
+    time.sleep(0.25)
+    t_begin = time.time()
+    dev_ms, e2e_ms = [], []
+    for w in range(windows):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(K):
+            loss = trainer.step_device(devb[W + w * K + i])
+        b.record()
+        torch.cuda.synchronize(dev)
+        dev_ms.append(a.elapsed_time(b))
+    last = 0.0
+    for w in range(windows):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(K):
+            last = float(trainer.step(host[W + w * K + i]).item())           # H2D of the seeds, D2H of the loss, every step
+        b.record()
+        torch.cuda.synchronize(dev)
+        e2e_ms.append(a.elapsed_time(b))
+    clk = clocks.stop(t_begin, time.time())
+    ms, ms_e2e = float(np.median(dev_ms)), float(np.median(e2e_ms))
+    extended = int(trainer.last_count.item())
+    # the reference's loop body, unchanged, against the drop-in classes (eager autograd path)
+    m2, c2, u2 = build()
+    opt = torch.optim.SGD(list(m2.parameters()) + list(c2.parameters()), lr=0.7)
+    n_loop = max(5, min(K, 30))
+    for i in range(3):
+        _apply_model_step(models, m2, c2, u2, opt, inp["labels"], host[i], spec["learn"], spec["unsup_loss"], torch)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for i in range(n_loop):
+        _apply_model_step(models, m2, c2, u2, opt, inp["labels"], host[3 + i], spec["learn"], spec["unsup_loss"], torch)
+    torch.cuda.synchronize(dev)
+    t_loop = (time.perf_counter() - t0) / n_loop
+    # layer-1 aggregation of the last step, relaunched alone (tiny: ~10K rows of 1433 / 500 floats, L2-resident)
+    fr = trainer.last_layers[0]
+    rows = int(fr.num_rows.item()) if fr.num_rows is not None else fr.rows_max
+    nnz = int(fr.cnt[:rows].sum().item())
+    d = int(feats.shape[1])
+    bytes_ = nnz * d * 4 + rows * d * 4 + nnz * 4 + (rows + 1) * 4
+    table = model._state()[1]
+    mode = native.AGG_MEAN if spec["agg"] == "MEAN" else native.AGG_MAX
+    out = torch.empty_like(fr.agg)
+    t_agg = _chain_us(torch, dev, [lambda: ops.agg_fwd(table, d, fr.nbr_idx, fr.stride, fr.cnt, fr.num_rows, fr.rows_max, mode, out=out)] * 8)
+    peak, peak_src = _peak("hbm_gbs", 6650.0)
+    cpu = None
+    if not args.skip_cpu:
+        torch.set_num_threads(os.cpu_count() or 1)
+        t0 = time.time()
+        times, kind, ext = cpu_steps_small(which, 2, 20, 25.0)
+        cpu = {"value": b_sz * len(times) / float(np.sum(times)), "unit": "seed nodes/s", "cores": torch.get_num_threads(),
+               "kind": kind, "sample": f"{len(times)} timed + 2 warm-up apply_model iterations of the reference's own classes "
+                                        f"(baseline/_ref), device cpu, extended batch ~{ext:.0f} nodes, {time.time() - t0:.0f}s wall"}
+    print(json.dumps({
+        "metric": "seed_nodes_per_sec_fwd_bwd", "value": b_sz * K / (ms * 1e-3), "unit": "seed nodes/s", "n_gpus": 1,
+        "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"fp32": "f32", "tf32x3": "f32 (tcgen05 3xTF32 split, fp32-faithful; K > 1024 contractions on FFMA)", "tf32": "tf32"}[args.precision],
+        "data": "synthetic features on the shipped topology", "config": small_config(which, spec, inp, extended),
+        "e2e": {"value": b_sz * K / (ms_e2e * 1e-3), "unit": "seed nodes/s", "ms_per_step": ms_e2e / K,
+                "h2d_bytes_per_step": int(b_sz * 4), "d2h_bytes_per_step": 4},
+        "dropin_loop": {"value": b_sz / t_loop, "unit": "seed nodes/s", "ms_per_step": t_loop * 1e3,
+                        "what": "the loop body of src/utils.py:145-191 run unchanged against graphsage_b200.models (eager autograd, "
+                                "python lists from extend_nodes, torch clip_grad_norm_ and SGD)"},
+        "gpu_launches": int(trainer.launches_per_step * K), "launches_per_step": int(trainer.launches_per_step),
+        "cuda_graph": bool(trainer.use_graph), "loss": float(loss.item()), "loss_e2e": last,
+        "roofline": {"bound": "hbm", "kernel": f"agg_fwd_kernel<{spec['agg']}> (layer 1)", "achieved": bytes_ / t_agg / 1e3,
+                     "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": bytes_ / t_agg / 1e3 / peak, "traffic": None,
+                     "bytes_per_launch": float(bytes_), "us_per_launch": t_agg, "rows": rows,
+                     "note": "a few MB per launch that stay in L2: launch-latency bound, not an HBM measurement"},
+        "cpu_baseline": cpu, "clocks": clk,
+        "windows": {"n": windows, "steps_each": K, "reported": "median window",
+                    "ms_per_step": {"median": ms / K, "min": min(dev_ms) / K, "max": max(dev_ms) / K},
+                    "e2e_ms_per_step": {"median": ms_e2e / K, "min": min(e2e_ms) / K, "max": max(e2e_ms) / K}},
+    }), flush=True)
 
 
 def dump_timeline(torch, native, PipelinedTrainer, model, cls, labels, b_sz, dev_batches, path):
@@ -1025,7 +1291,7 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="gradient exchange + update: peer = one fused kernel over NVLink peer memory (default); "
                          "nccl = library all-reduce followed by the separate norm/update kernels (comparison)")
-    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg5", "infer", "cfg4"],
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg5", "infer", "cfg4", "cfg1", "cfg2"],
                     help="cfg3 = ogbn-products-shaped (the headline, BASELINE configs[2]); cfg5 = row-partitioned bf16 "
                          "features with P2P NVLink gather (configs[4]; b_sz 8192 per GPU unless --b_sz is given)")
     ap.add_argument("--cfg5-nodes-per-gpu", type=int, default=12_500_000,
@@ -1044,7 +1310,11 @@ def main():
     if args.warmup < 3 and args.impl == "ours":
         log("[bench] raising --warmup to 3 (timing rule)")
         args.warmup = 3
-    if args.impl == "reference":
+    if args.impl == "reference" and args.workload in SMALL:
+        run_small_reference(args, args.workload)
+    elif args.workload in SMALL:
+        run_small(args, args.workload)
+    elif args.impl == "reference":
         run_reference(args)
     elif args.workload == "cfg5":
         run_cfg5(args)
