@@ -7,23 +7,28 @@
 // write this step is ncclAllReduce followed by 2 x (norm kernel + update kernel) = 5 launches
 // and two latency-bound round trips for a 258 KB buffer.  Here:
 //
-//   push    every CTA copies its slice of the local flat gradient into a receive slot inside
-//           every peer's memory (plain 16-byte stores over NVLink; fire and forget), then
-//           publishes flag[rank][cta] = epoch with a system-scope release store;
-//   wait    the CTA spins on the W-1 flags of ITS OWN slice only (no grid-wide dependency on
-//           the network), acquire at system scope;
-//   reduce  sums the W copies in rank order 0..W-1 -- every rank adds the same numbers in the
-//           same order, so replicas stay bit-identical -- scales by 1/W, accumulates the
-//           per-model sum of squares;
-//   clip    one grid barrier (all CTAs are co-resident: <= 64 CTAs of 256 threads); the
-//           per-CTA partial sums are combined in CTA order by every CTA (deterministic);
+//   push    every thread copies its float4s of the local flat gradient into a receive slot inside every peer's
+//           memory (plain 16-byte stores over NVLink; fire and forget).  There is NO flag and NO fence: an empty
+//           receive word holds the bit pattern 0xffffffff (a NaN payload arithmetic never produces; the sender
+//           rewrites a gradient word that happens to carry it to the canonical NaN), so the data are their own
+//           arrival signal, word by word -- no assumption about the atomicity of a 16-byte store either;
+//   wait    the thread polls ITS OWN float4s of the W-1 peer slots until none of the words is empty (no CTA- or
+//           grid-wide dependency on the network) and puts the empty pattern back for the epoch after next;
+//   reduce  sums the W copies in rank order 0..W-1 -- every rank adds the same numbers in the same order, so
+//           replicas stay bit-identical -- scales by 1/W, accumulates the per-model sum of squares;
+//   clip    the per-CTA partial sums of squares meet through tagged 8-byte records every CTA polls (all CTAs are
+//           co-resident: <= 64 CTAs of 256 threads) and are combined in CTA order by every CTA (deterministic);
 //   update  p -= lr * min(1, max_norm / (norm + 1e-6)) * g, gradient slice zeroed for the
 //           next step.
 //
-// Receive slots are double-buffered by epoch parity: a rank can only start epoch e+2 (and
-// overwrite parity e&1 in a peer) after that peer published epoch e+1, i.e. after the peer's
-// epoch-e kernel has completed.  A wait that exceeds `timeout_ns` records status = 1 and
-// proceeds (the host checks gs_dp_status) instead of hanging the GPU.
+// Compared with the first version (data, CTA barrier, release flag at system scope, acquire poll of the flag) the
+// critical path loses the fence's round trip over NVLink and the flag's flight: measured in lockstep chains on
+// 2 x B200 (scratch/dp_probe_mp.py), push + wait was 9.4-11.8K cycles per launch.
+//
+// Receive slots are double-buffered by epoch parity: a rank can only start epoch e+2 (and overwrite parity e&1 in a
+// peer) after it has seen that peer's epoch-e+1 data, i.e. after the peer's epoch-e kernel -- which emptied the slot --
+// has completed.  The regions start out filled with 0xff bytes (peer.py).  A wait that exceeds `timeout_ns` records
+// status = 1 and proceeds (the host checks gs_dp_status) instead of hanging the GPU.
 #include "common.cuh"
 
 namespace gs {
@@ -35,8 +40,8 @@ constexpr int kDpMaxSegs = 16;
 constexpr int kDpMaxGroups = 4;
 
 struct DpPeers {
-  float* recv[kDpMaxWorld];        // rank r's receive region: [2 parities][world][n_total] floats
-  uint32_t* flags[kDpMaxWorld];    // rank r's flag region:    [world][kDpMaxCtas] epochs
+  float* recv[kDpMaxWorld];        // rank r's receive region: [2 parities][world][n_total] floats, empty words = 0xffffffff
+  uint32_t* flags[kDpMaxWorld];    // rank r's 2 KB header (the first protocol's flags; reserved)
   int rank, world;
 };
 struct DpSegs {
@@ -53,23 +58,30 @@ struct DpSegs {
 struct DpState {                   // device memory, zeroed once by the caller
   unsigned int epoch;
   unsigned int status;
-  unsigned long long arrive;
-  float partial[kDpMaxCtas][kDpMaxGroups];
+  unsigned long long rec[kDpMaxCtas][kDpMaxGroups];   // {epoch << 32 | partial sum of squares} of CTA c, clip group g
   float norm[kDpMaxGroups];        // last step's total gradient norms (diagnostics / tests)
 };
 
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+constexpr uint32_t kDpEmpty = 0xffffffffu;   // a receive word nobody has written yet this epoch
+
+__device__ __forceinline__ uint4 ld_relaxed_sys_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+__device__ __forceinline__ void st_relaxed_sys_v4(void* p, uint4 v) {
+  asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ bool dp_landed(const uint4& v) {
+  return v.x != kDpEmpty && v.y != kDpEmpty && v.z != kDpEmpty && v.w != kDpEmpty;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p) {
   unsigned long long v;
-  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
@@ -85,7 +97,23 @@ __global__ void split_lo_kernel(const float* __restrict__ src, float* __restrict
     dst[i] = tf32_lo(src[i]);
 }
 
-__device__ __forceinline__ int seg_of(const DpSegs& s, long long elem) {
+// slow path of the wait: poll one float4 of a receive slot until every word has landed (or the timeout strikes)
+__device__ __noinline__ uint4 dp_poll(const float4* slot, unsigned long long timeout_ns, unsigned int* status) {
+  unsigned long long t0 = 0;
+  uint4 v = ld_relaxed_sys_v4(slot);
+  for (unsigned spins = 0; !dp_landed(v); ++spins) {
+    if ((spins & 63u) == 63u) {                            // the timer is only consulted once the wait is long
+      const unsigned long long now = global_ns();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > timeout_ns) { atomicExch(status, 1u); break; }
+      __nanosleep(64);
+    }
+    v = ld_relaxed_sys_v4(slot);
+  }
+  return v;
+}
+
+__device__ __noinline__ int seg_of(const DpSegs& s, long long elem) {
   int k = -1;
 #pragma unroll 4
   for (int i = 0; i < s.n; ++i)
@@ -100,13 +128,14 @@ __device__ long long g_dp_trace[16];
 #define GS_DP_MARK(slot) do { } while (0)
 #endif
 
-// Elements are float4s; thread t of CTA c owns float4s  c*256 + t + j*G*256  (j < kDpPer): consecutive threads touch
-// consecutive float4s, and everything a thread needs -- its gradient pieces, the segment they fall in, the parameter
-// pieces they update -- is fetched in ONE round of independent loads before the grid barrier, so the kernel is
-// (one memory round trip) + (the barrier) + (stores).  The tables stay in the constant bank (__grid_constant__).
-constexpr int kDpPer = 4;          // float4s per thread held in registers; larger buffers take the looping path
-
-__global__ void __launch_bounds__(kDpThreads)
+// Elements are float4s; thread t of CTA c owns float4s  c*256 + t + j*G*256: consecutive threads touch consecutive
+// float4s.  While the buffer fits one float4 per thread (G <= kDpMaxCtas CTAs; 64432 floats at the headline
+// configuration = 63 CTAs) everything a thread needs -- its gradient piece (all ranks' copies), the segment it falls in,
+// the parameter piece it updates -- is fetched in ONE round of independent loads before the grid barrier and stays in
+// registers, so the kernel is (one memory round trip) + (the barrier) + (stores); larger buffers loop and park the reduced
+// gradient in the flat buffer across the barrier.  One copy of the code serves both (the kernel is launch-latency
+// bound: its instruction footprint is part of its cost).  The tables stay in the constant bank (__grid_constant__).
+__global__ void __launch_bounds__(kDpThreads, 4)     // <= 64 registers: the CTAs slot in beside the previous kernel's (PDL)
 dp_update_kernel(float* __restrict__ flat, long long n_total, const __grid_constant__ DpPeers peers,
                  const __grid_constant__ DpSegs segs, DpState* __restrict__ st, float max_norm, float lr,
                  unsigned long long timeout_ns, long long* __restrict__ step_counter) {
@@ -116,17 +145,17 @@ dp_update_kernel(float* __restrict__ flat, long long n_total, const __grid_const
   const int G = gridDim.x, c = blockIdx.x, tid = threadIdx.x;
   const unsigned int e = *reinterpret_cast<volatile unsigned int*>(&st->epoch) + 1u;
   const int par = static_cast<int>(e & 1u);
-  const long long n4 = n_total >> 2;
+  const int n4 = static_cast<int>(n_total >> 2);          // (the host refuses buffers of 2^31 floats or more)
   float4* flat4 = reinterpret_cast<float4*>(flat);
   const int W = peers.world, me = peers.rank;
-  const long long first = static_cast<long long>(c) * kDpThreads + tid;
-  const long long stride = static_cast<long long>(G) * kDpThreads;
+  const int first = c * kDpThreads + tid;
+  const int stride = G * kDpThreads;
   GS_DP_MARK(2);
 
   // partial-gradient replicas of a segment are folded into the flat buffer (and cleared) before anything reads it
-  auto fold = [&](long long i, int k, float4 g) -> float4 {
+  auto fold = [&](int i, int k, float4 g) -> float4 {
     if (k >= 0 && segs.extra[k] != nullptr) {
-      const long long o = 4 * i - segs.off[k];
+      const long long o = 4LL * i - segs.off[k];
       const int n = segs.extra_n[k];
       for (int x0 = 0; x0 < n; x0 += 8) {                  // 8 independent loads in flight, then the adds in replica order
         float4 v[8];
@@ -144,52 +173,57 @@ dp_update_kernel(float* __restrict__ flat, long long n_total, const __grid_const
     return g;
   };
   if (segs.any_extra)                                      // (uniform branch; off in the default configuration)
-    for (long long i = first; i < n4; i += stride) {
-      const int k = seg_of(segs, 4 * i);
+    for (int i = first; i < n4; i += stride) {
+      const int k = seg_of(segs, 4LL * i);
       if (k >= 0 && segs.extra[k] != nullptr) flat4[i] = fold(i, k, flat4[i]);
     }
   if (W > 1) {
-    // ---- push my pieces into every peer's slot [par][me] ----
-    for (int p = 0; p < W; ++p) {
-      if (p == me) continue;
-      float4* dst = reinterpret_cast<float4*>(peers.recv[p]) + static_cast<long long>(par * W + me) * n4;
-      for (long long i = first; i < n4; i += stride) dst[i] = flat4[i];
+    // ---- push my pieces into every peer's slot [par][me]; a word that carries the empty pattern goes out as the
+    //      canonical NaN (it is a NaN either way) ----
+    for (int i = first; i < n4; i += stride) {
+      uint4 v = *reinterpret_cast<const uint4*>(flat4 + i);
+      v.x = v.x == kDpEmpty ? 0x7fffffffu : v.x; v.y = v.y == kDpEmpty ? 0x7fffffffu : v.y;
+      v.z = v.z == kDpEmpty ? 0x7fffffffu : v.z; v.w = v.w == kDpEmpty ? 0x7fffffffu : v.w;
+      for (int p = 0; p < W; ++p)
+        if (p != me) st_relaxed_sys_v4(reinterpret_cast<float4*>(peers.recv[p]) + static_cast<long long>(par * W + me) * n4 + i, v);
     }
-    // No per-thread system fence here: the CTA barrier orders every thread's remote stores before the flag
-    // writers, and their release at system scope is cumulative -- one fence round trip over NVLink, not two.
-    __syncthreads();
-    if (tid < W && tid != me) {
-      st_release_sys(peers.flags[tid] + me * kDpMaxCtas + c, e);
-      // ---- wait for peer `tid`'s copy of the pieces CTA c owns ----
-      const uint32_t* f = peers.flags[me] + tid * kDpMaxCtas + c;
-      unsigned long long t0 = 0;
-      for (unsigned spins = 0; static_cast<int>(ld_acquire_sys(f) - e) < 0; ++spins) {
-        if ((spins & 63u) == 63u) {                        // the timer is only consulted once the wait is long
-          const unsigned long long now = global_ns();
-          if (t0 == 0) t0 = now;
-          if (now - t0 > timeout_ns) { atomicExch(&st->status, 1u); break; }
-          __nanosleep(64);
-        }
-      }
-    }
-    __syncthreads();
   }
   GS_DP_MARK(3);
 
   // ---- one round of loads: gradient pieces (all ranks' copies), their segments, the parameters they update ----
   const float inv_w = 1.0f / static_cast<float>(W);
-  const float4* mine = reinterpret_cast<const float4*>(peers.recv[me]) + static_cast<long long>(par) * W * n4;
-  const bool in_regs = n4 <= stride * kDpPer;
-  float4 gsum[kDpPer], wv[kDpPer];
-  int segk[kDpPer];
+  const bool in_regs = n4 <= stride;                       // one float4 per thread: nothing goes through memory
+  float4 g_keep = make_float4(0.f, 0.f, 0.f, 0.f), w_keep = make_float4(0.f, 0.f, 0.f, 0.f);
+  int k_keep = -1;
   float ss[kDpMaxGroups];
 #pragma unroll
   for (int g = 0; g < kDpMaxGroups; ++g) ss[g] = 0.f;
-  auto reduce_one = [&](long long i, int k) -> float4 {
+  float4* mine_w = reinterpret_cast<float4*>(peers.recv[me]) + static_cast<long long>(par) * W * n4;
+  auto reduce_one = [&](int i, int k) -> float4 {
+    // the W-1 peer copies of this float4, four ranks at a time: their loads in flight together, stragglers polled one
+    // by one; summed in rank order 0..W-1 -- every rank adds the same numbers in the same order
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < W; ++r) {                          // rank order: every rank adds the same numbers in the same order
-      const float4 v = (r == me) ? flat4[i] : __ldcg(mine + static_cast<long long>(r) * n4 + i);
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    const float4 own = flat4[i];
+#pragma unroll 1
+    for (int r0 = 0; r0 < W; r0 += 4) {
+      uint4 got[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (r0 + u < W && r0 + u != me) got[u] = ld_relaxed_sys_v4(mine_w + static_cast<long long>(r0 + u) * n4 + i);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = r0 + u;
+        if (r >= W) break;
+        float4 v = own;
+        if (r != me) {
+          float4* slot = mine_w + static_cast<long long>(r) * n4 + i;
+          if (!dp_landed(got[u])) got[u] = dp_poll(slot, timeout_ns, &st->status);
+          // the slot is empty again for the epoch after next (nobody writes it before this kernel has completed)
+          *reinterpret_cast<uint4*>(slot) = make_uint4(kDpEmpty, kDpEmpty, kDpEmpty, kDpEmpty);
+          v = make_float4(__uint_as_float(got[u].x), __uint_as_float(got[u].y), __uint_as_float(got[u].z), __uint_as_float(got[u].w));
+        }
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
     }
     s.x *= inv_w; s.y *= inv_w; s.z *= inv_w; s.w *= inv_w;
     return s;
@@ -201,33 +235,25 @@ dp_update_kernel(float* __restrict__ flat, long long n_total, const __grid_const
 #pragma unroll
     for (int gg = 0; gg < kDpMaxGroups; ++gg) if (gg == g) ss[gg] += q;
   };
-  if (in_regs) {
-#pragma unroll
-    for (int j = 0; j < kDpPer; ++j) {
-      const long long i = first + j * stride;
-      segk[j] = -1;
-      if (i < n4) {
-        const int k = seg_of(segs, 4 * i);
-        gsum[j] = reduce_one(i, k);
-        segk[j] = k;
-        if (k >= 0) {
-          const long long o = 4 * i - segs.off[k];
-          const float* p = segs.param[k] + o;
-          if (segs.numel[k] - o >= 4 && (reinterpret_cast<uintptr_t>(p) & 15u) == 0) wv[j] = *reinterpret_cast<const float4*>(p);
-        }
-      }
+#pragma unroll 1
+  for (int i = first; i < n4; i += stride) {
+    const int k = seg_of(segs, 4LL * i);
+    if (in_regs && k >= 0) {                               // the parameter piece: in flight while the peers' copies arrive
+      const long long o = 4LL * i - segs.off[k];
+      const float* p = segs.param[k] + o;
+      if (segs.numel[k] - o >= 4 && (reinterpret_cast<uintptr_t>(p) & 15u) == 0) w_keep = *reinterpret_cast<const float4*>(p);
     }
-#pragma unroll
-    for (int j = 0; j < kDpPer; ++j) add_ss(gsum[j], segk[j]);
-  } else {
-    for (long long i = first; i < n4; i += stride) {
-      const int k = seg_of(segs, 4 * i);
-      const float4 s = reduce_one(i, k);
+    const float4 s = reduce_one(i, k);
+    add_ss(s, k);
+    if (in_regs) {
+      g_keep = s;
+      k_keep = k;
+    } else {
       flat4[i] = s;
-      add_ss(s, k);
     }
   }
   __shared__ float s_red[kDpThreads / 32][kDpMaxGroups];
+  __shared__ float s_part[kDpMaxCtas][kDpMaxGroups];
   __shared__ float s_coef[kDpMaxGroups];
 #pragma unroll
   for (int g = 0; g < kDpMaxGroups; ++g) {
@@ -235,38 +261,44 @@ dp_update_kernel(float* __restrict__ flat, long long n_total, const __grid_const
     if ((tid & 31) == 0) s_red[tid >> 5][g] = v;
   }
   __syncthreads();
+  // ---- the per-CTA partial sums meet without a barrier of their own: CTA c publishes {partial, epoch} as ONE 8-byte
+  //      word per group (naturally atomic: no fence, no counter), and every CTA polls the G x groups words -- thread t
+  //      the word of CTA t / 4, group t % 4 -- until they carry this epoch.  One store and one load round trip instead of
+  //      store + fence + atomic, poll, load. ----
+  static_assert(kDpThreads == kDpMaxCtas * kDpMaxGroups, "one polling thread per (CTA, group) record");
   if (tid < kDpMaxGroups) {
     float v = 0.f;
     for (int w = 0; w < kDpThreads / 32; ++w) v += s_red[w][tid];
-    st->partial[c][tid] = v;
+    st_relaxed_gpu_u64(&st->rec[c][tid], (static_cast<unsigned long long>(e) << 32) | __float_as_uint(v));
   }
   GS_DP_MARK(4);
-  // ---- grid barrier (arrive counter grows by G every epoch) ----
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    atomicAdd(&st->arrive, 1ULL);
-    const unsigned long long target = static_cast<unsigned long long>(e) * static_cast<unsigned long long>(G);
-    unsigned long long t0 = 0;
-    for (unsigned spins = 0; ld_acquire_gpu_u64(&st->arrive) < target; ++spins) {
-      if ((spins & 255u) == 255u) {
-        const unsigned long long now = global_ns();
-        if (t0 == 0) t0 = now;
-        if (now - t0 > timeout_ns) { atomicExch(&st->status, 2u); break; }
+  {
+    const int cc = tid / kDpMaxGroups, g = tid % kDpMaxGroups;
+    float v = 0.f;
+    if (cc < G) {
+      unsigned long long rec = ld_relaxed_gpu_u64(&st->rec[cc][g]);
+      unsigned long long t0 = 0;
+      for (unsigned spins = 0; static_cast<unsigned int>(rec >> 32) != e; ++spins) {
+        if ((spins & 255u) == 255u) {
+          const unsigned long long now = global_ns();
+          if (t0 == 0) t0 = now;
+          if (now - t0 > timeout_ns) { atomicExch(&st->status, 2u); break; }
+        }
+        rec = ld_relaxed_gpu_u64(&st->rec[cc][g]);
       }
+      v = __uint_as_float(static_cast<unsigned int>(rec));
     }
+    s_part[cc][g] = v;
   }
   __syncthreads();
   GS_DP_MARK(5);
   if (tid < 32) {
-    // all G x groups partials in flight at once (lane = CTA, G <= 64), then a shuffle tree: the order of the
-    // additions is fixed by the lane numbers, hence identical on every CTA and every rank
+    // lane = CTA (G <= 64), then a shuffle tree: the order of the additions is fixed by the lane numbers, hence
+    // identical on every CTA and every rank
     float v[kDpMaxGroups];
 #pragma unroll
     for (int g = 0; g < kDpMaxGroups; ++g) {
-      const float a = tid < G ? __ldcg(&st->partial[tid][g]) : 0.f;
-      const float b = tid + 32 < G ? __ldcg(&st->partial[tid + 32][g]) : 0.f;
-      v[g] = a + b;
+      v[g] = s_part[tid][g] + s_part[tid + 32][g];          // (CTAs beyond G hold zeros)
     }
 #pragma unroll
     for (int g = 0; g < kDpMaxGroups; ++g) {
@@ -283,10 +315,10 @@ dp_update_kernel(float* __restrict__ flat, long long n_total, const __grid_const
   GS_DP_MARK(6);
 
   // ---- SGD on my pieces, gradient zeroed for the next step ----
-  auto sgd_one = [&](long long i, const float4& g, int k, const float4* w_have) {
+  auto sgd_one = [&](int i, const float4& g, int k, const float4* w_have) {
     if (k >= 0) {
       const float step = lr * s_coef[segs.group[k]];
-      const long long o = 4 * i - segs.off[k];
+      const long long o = 4LL * i - segs.off[k];
       float* p = segs.param[k] + o;
       const long long left = segs.numel[k] - o;
       if (left >= 4 && (reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
@@ -305,14 +337,11 @@ dp_update_kernel(float* __restrict__ flat, long long n_total, const __grid_const
     }
     flat4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   };
-  if (in_regs) {
-#pragma unroll
-    for (int j = 0; j < kDpPer; ++j) {
-      const long long i = first + j * stride;
-      if (i < n4) sgd_one(i, gsum[j], segk[j], &wv[j]);
-    }
-  } else {
-    for (long long i = first; i < n4; i += stride) sgd_one(i, flat4[i], seg_of(segs, 4 * i), nullptr);
+#pragma unroll 1
+  for (int i = first; i < n4; i += stride) {
+    const float4 g = in_regs ? g_keep : flat4[i];
+    const int k = in_regs ? k_keep : seg_of(segs, 4LL * i);
+    sgd_one(i, g, k, in_regs ? &w_keep : nullptr);
   }
   GS_DP_MARK(7);
   if (c == 0 && tid == 0) {
@@ -344,7 +373,7 @@ extern "C" int gs_dp_allreduce_clip_sgd(float* flat_grad, int64_t n_total, void*
                                         int64_t* step_counter, float* const* seg_params_lo_host,
                                         float* const* seg_extra_host, const int32_t* seg_extra_n_host,
                                         const int64_t* seg_extra_stride_host, gs_stream_t stream) {
-  if (!flat_grad || !state || n_total < 4 || (n_total & 3) || !aligned16(flat_grad)) return GS_ERR_BAD_ARG;
+  if (!flat_grad || !state || n_total < 4 || (n_total & 3) || n_total >= (1LL << 31) || !aligned16(flat_grad)) return GS_ERR_BAD_ARG;
   if (world < 1 || world > kDpMaxWorld || rank < 0 || rank >= world) return GS_ERR_BAD_ARG;
   if (num_segs < 1 || num_segs > kDpMaxSegs || !seg_params_host || !seg_offsets_host || !seg_numels_host) return GS_ERR_BAD_ARG;
   if (world > 1 && !peer_regions_host) return GS_ERR_BAD_ARG;
@@ -384,7 +413,7 @@ extern "C" int gs_dp_allreduce_clip_sgd(float* flat_grad, int64_t n_total, void*
     if (segs.group[i] + 1 > groups) groups = segs.group[i] + 1;
   }
   segs.groups = groups;
-  // the grid size is a pure function of n_total: the barrier counter of `state` relies on it
+  // the grid size is a pure function of n_total (every CTA polls the records of all of them)
   const int64_t n4 = n_total >> 2;
   int grid = static_cast<int>((n4 + kDpThreads - 1) / kDpThreads);      // one float4 per thread while <= 64 CTAs suffice
   if (grid > kDpMaxCtas) grid = kDpMaxCtas;

@@ -262,10 +262,10 @@ int gs_sage_gemm_bwd_x_tc(const float*, int64_t, const float*, int64_t, const fl
 int gs_sage_gemm_bwd_w_tc(const float*, int64_t, const int32_t*, const float*, int64_t, int32_t, const float*, int64_t,
                           const float*, int64_t, int32_t, int32_t, int32_t, const int32_t*, int32_t, float*, int64_t,
                           int32_t, gs_stream_t);
-int gs_sage_gemm_bwd_w_pair_tc(const float* const*, const int64_t*, const int32_t* const*, const float* const*,
-                               const int64_t*, const int32_t*, const float* const*, const int64_t*, const float* const*,
-                               const int64_t*, const int32_t*, int32_t, int32_t, const int32_t* const*, const int32_t*,
-                               float* const*, const int64_t*, int32_t, gs_stream_t);
+int gs_sage_gemm_bwd_w_group_tc(int32_t, const float* const*, const int64_t*, const int32_t* const*, const float* const*,
+                                const int64_t*, const int32_t*, const float* const*, const int64_t*, const float* const*,
+                                const int64_t*, const int32_t*, const int32_t*, const int32_t*, const int32_t*,
+                                const int32_t* const*, const int32_t*, float* const*, const int64_t*, int32_t, gs_stream_t);
 
 extern "C" int gs_sage_gemm_fwd(const float* self_table, int64_t ld_self, const int32_t* self_idx,
                                 const float* agg, int64_t ld_agg, int32_t dim,
@@ -372,8 +372,51 @@ extern "C" int gs_sage_gemm_bwd_w(const float* self_table, int64_t ld_self, cons
   return finish_launch();
 }
 
-// Two weight-gradient problems (two layers of one step) in one call.  Arrays of 2 (HOST arrays of device pointers /
-// sizes).  Tensor-core precisions run them as ONE grid; otherwise, or when they cannot share a kernel, one after the other.
+// Up to three weight-gradient problems (the layers of one step and its classifier) in one call.  Arrays of n (HOST
+// arrays of device pointers / sizes).  Tensor-core precisions run them as ONE grid; otherwise, or when they cannot share
+// a kernel, one after the other.
+extern "C" int gs_sage_gemm_bwd_w_group(int32_t n, const float* const* self_table_host, const int64_t* ld_self_host,
+                                        const int32_t* const* self_idx_host, const float* const* agg_host,
+                                        const int64_t* ld_agg_host, const int32_t* dim_host,
+                                        const float* const* grad_out_host, const int64_t* ld_go_host,
+                                        const float* const* out_host, const int64_t* ld_out_host,
+                                        const int32_t* out_dim_host, const int32_t* grad_out_cols_host,
+                                        const int32_t* gcn_host, const int32_t* relu_host,
+                                        const int32_t* const* num_rows_dev_host, const int32_t* max_rows_host,
+                                        float* const* grad_w_host, const int64_t* ldw_host, int32_t precision,
+                                        gs_stream_t stream) {
+  if (n < 1 || n > 3 || !self_table_host || !ld_self_host || !self_idx_host || !agg_host || !ld_agg_host || !dim_host ||
+      !grad_out_host || !ld_go_host || !out_host || !ld_out_host || !out_dim_host || !gcn_host || !relu_host ||
+      !num_rows_dev_host || !max_rows_host || !grad_w_host || !ldw_host)
+    return GS_ERR_BAD_ARG;
+  bool fused = precision != GS_PREC_FP32;
+  for (int i = 0; i < n; ++i) {
+    if (max_rows_host[i] <= 0) { fused = false; continue; }
+    if (!grad_out_host[i] || !grad_w_host[i] || out_dim_host[i] < 1 || (relu_host[i] && !out_host[i])) return GS_ERR_BAD_ARG;
+    if (int e = check_x(self_table_host[i], ld_self_host[i], agg_host[i], ld_agg_host[i], dim_host[i], gcn_host[i])) return e;
+    if (ldw_host[i] < (gcn_host[i] ? dim_host[i] : 2 * dim_host[i])) return GS_ERR_BAD_ARG;
+    if (grad_out_cols_host && grad_out_cols_host[i] > 0 &&
+        (grad_out_cols_host[i] < out_dim_host[i] || grad_out_cols_host[i] > ld_go_host[i]))
+      return GS_ERR_BAD_ARG;
+  }
+  if (fused) {
+    const int e = gs_sage_gemm_bwd_w_group_tc(n, self_table_host, ld_self_host, self_idx_host, agg_host, ld_agg_host,
+                                              dim_host, grad_out_host, ld_go_host, out_host, ld_out_host, out_dim_host,
+                                              grad_out_cols_host, gcn_host, relu_host, num_rows_dev_host, max_rows_host,
+                                              grad_w_host, ldw_host, precision, stream);
+    if (e != GS_ERR_UNSUPPORTED) return e;
+  }
+  for (int i = 0; i < n; ++i) {
+    const int e = gs_sage_gemm_bwd_w(self_table_host[i], ld_self_host[i], self_idx_host[i], agg_host[i], ld_agg_host[i],
+                                     dim_host[i], grad_out_host[i], ld_go_host[i], out_host[i], ld_out_host[i],
+                                     out_dim_host[i], gcn_host[i], relu_host[i], num_rows_dev_host[i], max_rows_host[i],
+                                     grad_w_host[i], ldw_host[i], precision, stream);
+    if (e) return e;
+  }
+  return GS_OK;
+}
+
+// The two-problem form with common gcn / relu (the layers of a two-layer step).
 extern "C" int gs_sage_gemm_bwd_w_pair(const float* const* self_table_host, const int64_t* ld_self_host,
                                        const int32_t* const* self_idx_host, const float* const* agg_host,
                                        const int64_t* ld_agg_host, const int32_t* dim_host,
@@ -383,30 +426,10 @@ extern "C" int gs_sage_gemm_bwd_w_pair(const float* const* self_table_host, cons
                                        const int32_t* const* num_rows_dev_host, const int32_t* max_rows_host,
                                        float* const* grad_w_host, const int64_t* ldw_host, int32_t precision,
                                        gs_stream_t stream) {
-  if (!self_table_host || !ld_self_host || !self_idx_host || !agg_host || !ld_agg_host || !dim_host || !grad_out_host ||
-      !ld_go_host || !out_host || !ld_out_host || !out_dim_host || !num_rows_dev_host || !max_rows_host || !grad_w_host ||
-      !ldw_host)
-    return GS_ERR_BAD_ARG;
-  bool fused = precision != GS_PREC_FP32 && max_rows_host[0] > 0 && max_rows_host[1] > 0;
-  for (int i = 0; i < 2 && fused; ++i) {
-    if (!grad_out_host[i] || !grad_w_host[i] || out_dim_host[i] < 1 || (relu && !out_host[i])) return GS_ERR_BAD_ARG;
-    if (int e = check_x(self_table_host[i], ld_self_host[i], agg_host[i], ld_agg_host[i], dim_host[i], gcn)) return e;
-    if (ldw_host[i] < (gcn ? dim_host[i] : 2 * dim_host[i])) return GS_ERR_BAD_ARG;
-  }
-  if (fused) {
-    const int e = gs_sage_gemm_bwd_w_pair_tc(self_table_host, ld_self_host, self_idx_host, agg_host, ld_agg_host, dim_host,
-                                             grad_out_host, ld_go_host, out_host, ld_out_host, out_dim_host, gcn, relu,
-                                             num_rows_dev_host, max_rows_host, grad_w_host, ldw_host, precision, stream);
-    if (e != GS_ERR_UNSUPPORTED) return e;
-  }
-  for (int i = 0; i < 2; ++i) {
-    const int e = gs_sage_gemm_bwd_w(self_table_host[i], ld_self_host[i], self_idx_host[i], agg_host[i], ld_agg_host[i],
-                                     dim_host[i], grad_out_host[i], ld_go_host[i], out_host[i], ld_out_host[i],
-                                     out_dim_host[i], gcn, relu, num_rows_dev_host[i], max_rows_host[i], grad_w_host[i],
-                                     ldw_host[i], precision, stream);
-    if (e) return e;
-  }
-  return GS_OK;
+  const int32_t g[2] = {gcn, gcn}, r[2] = {relu, relu};
+  return gs_sage_gemm_bwd_w_group(2, self_table_host, ld_self_host, self_idx_host, agg_host, ld_agg_host, dim_host,
+                                  grad_out_host, ld_go_host, out_host, ld_out_host, out_dim_host, nullptr, g, r,
+                                  num_rows_dev_host, max_rows_host, grad_w_host, ldw_host, precision, stream);
 }
 
 // ---------------------------------------------------------------------------------------

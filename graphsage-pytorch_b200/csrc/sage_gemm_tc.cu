@@ -839,23 +839,28 @@ sage_bwd_x_tc_kernel(const float* __restrict__ grad_out, int64_t ld_go, const fl
 }
 
 // One weight-gradient problem dW[h,kv] += sum_r dZ[r,h] X[r,kv], cut into `chunks` row chunks.
+// out_dim bounds the columns of dZ that are READ (a multiple of 4 on the cp.async path; a caller whose dZ rows are
+// zero-padded passes the padded width), out_rows <= out_dim the rows of dW that exist.
 struct BwdWProblem {
-  XView x; const float* grad_out; int64_t ld_go; const float* out; int64_t ld_out; int out_dim, relu;
+  XView x; const float* grad_out; int64_t ld_go; const float* out; int64_t ld_out; int out_dim, out_rows, relu;
   const int32_t* num_rows_dev; int max_rows, rows_per_chunk; float* grad_w; int64_t ldw; int n_tile, num_stages;
   int tiles_x, tiles_y, chunks;
 };
 
-// The grid's z axis runs over the row chunks of problem A, then those of problem B (pb.chunks == 0: one problem).
-// Two layers' weight gradients are independent leaves of a step's dependency graph; launched as one grid they
-// share the machine (CTAs split in proportion to their work) instead of queueing behind each other.
+// The grid's z axis runs over the row chunks of problem A, then those of problem B, then those of problem C (chunks == 0:
+// problem absent).  The weight gradients of a step -- the layers' and the classifier's -- are independent leaves of its
+// dependency graph; launched as one grid they share the machine (CTAs split in proportion to their work) instead of
+// queueing behind each other.
 template <bool SPLIT3, bool ASYNC>
 __global__ void __maxnreg__(kMaxRegs)
-sage_bwd_w_tc_kernel(const BwdWProblem pa, const BwdWProblem pb) {
+sage_bwd_w_tc_kernel(const __grid_constant__ BwdWProblem pa, const __grid_constant__ BwdWProblem pb,
+                     const __grid_constant__ BwdWProblem pc) {
   pdl_sync();
   extern __shared__ unsigned char smem_dyn[];
-  const bool first = static_cast<int>(blockIdx.z) < pa.chunks;
-  const BwdWProblem q = first ? pa : pb;
-  const int chunk = first ? blockIdx.z : blockIdx.z - pa.chunks;
+  const int z = blockIdx.z;
+  const int which = z < pa.chunks ? 0 : (z < pa.chunks + pb.chunks ? 1 : 2);
+  const BwdWProblem& q = *(which == 0 ? &pa : (which == 1 ? &pb : &pc));     // stays in the constant bank
+  const int chunk = which == 0 ? z : (which == 1 ? z - pa.chunks : z - pa.chunks - pb.chunks);
   if (static_cast<int>(blockIdx.x) >= q.tiles_x || static_cast<int>(blockIdx.y) >= q.tiles_y) return;
   XView x = q.x;
   const int rows = live_rows(q.num_rows_dev, q.max_rows);
@@ -869,7 +874,7 @@ sage_bwd_w_tc_kernel(const BwdWProblem pa, const BwdWProblem pb) {
   x.fill_cache(s_rowidx, r_begin, min(q.rows_per_chunk, kMaxChunkRows), rows);
   LoadDZ_MN la{q.grad_out, q.ld_go, q.out, q.ld_out, r_begin, r_end, h0, q.out_dim, q.relu};
   LoadX_MN lb{x, r_begin, r_end, kv0};
-  AddDW epi{x, q.grad_w, q.ldw, h0, q.out_dim, kv0};
+  AddDW epi{x, q.grad_w, q.ldw, h0, q.out_rows, kv0};
   gemm_core<true, true, SPLIT3, ASYNC>(la, lb, epi, nt, k_stages, q.num_stages, smem_dyn, q.grad_out);
 }
 
@@ -999,20 +1004,24 @@ int gs_sage_gemm_bwd_x_tc(const float* grad_out, int64_t ld_go, const float* out
 }
 
 // Row chunks of one problem for a budget of `cta_budget` CTAs (about one per SM): at least 4 k-stages per CTA, at
-// most kMaxChunkRows rows (the index cache).  Returns the dynamic shared memory its CTAs need.
-static int plan_bwd_w(BwdWProblem& q, int kt, int out_dim, int max_rows, bool split3, int cta_budget) {
+// most kMaxChunkRows rows (the index cache); fixed_rows > 0 prescribes the chunk length instead.  Returns the dynamic
+// shared memory its CTAs need.
+static int plan_bwd_w(BwdWProblem& q, int kt, int out_dim, int max_rows, bool split3, int cta_budget, int fixed_rows = 0) {
   const Plan p = make_plan(kt, true, true, split3, kNumSMs);   // row chunks fill the machine
   q.n_tile = p.n_tile;
   q.num_stages = p.num_stages;
   q.tiles_x = (kt + p.n_tile - 1) / p.n_tile;
   q.tiles_y = (out_dim + kTileM - 1) / kTileM;
   const int tiles = q.tiles_x * q.tiles_y;
-  int chunks = (cta_budget + tiles - 1) / tiles;
-  const int max_chunks = (max_rows + 4 * kBK - 1) / (4 * kBK);
-  if (chunks > max_chunks) chunks = max_chunks;
-  if (chunks < 1) chunks = 1;
-  int rows_per_chunk = (max_rows + chunks - 1) / chunks;
-  rows_per_chunk = ((rows_per_chunk + kBK - 1) / kBK) * kBK;
+  int rows_per_chunk = fixed_rows;
+  if (rows_per_chunk <= 0) {
+    int chunks = (cta_budget + tiles - 1) / tiles;
+    const int max_chunks = (max_rows + 4 * kBK - 1) / (4 * kBK);
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    rows_per_chunk = (max_rows + chunks - 1) / chunks;
+    rows_per_chunk = ((rows_per_chunk + kBK - 1) / kBK) * kBK;
+  }
   if (rows_per_chunk > kMaxChunkRows) rows_per_chunk = kMaxChunkRows;
   q.rows_per_chunk = rows_per_chunk;
   q.chunks = (max_rows + rows_per_chunk - 1) / rows_per_chunk;
@@ -1023,11 +1032,17 @@ static bool bwd_w_async_ok(const float* grad_out, int64_t ld_go, int out_dim, in
   return !relu && (out_dim % 4 == 0) && (ld_go % 4 == 0) && aligned16(grad_out);
 }
 
-static int launch_bwd_w(const BwdWProblem& pa, const BwdWProblem& pb, int smem, bool split3, bool async, gs_stream_t stream) {
-  const int tx = pa.tiles_x > pb.tiles_x ? pa.tiles_x : pb.tiles_x;
-  const int ty = pa.tiles_y > pb.tiles_y ? pa.tiles_y : pb.tiles_y;
-  dim3 grid(tx, ty, pa.chunks + pb.chunks);
-  GS_TC_LAUNCH(sage_bwd_w_tc_kernel, grid, smem, as_stream(stream), pa, pb);
+static int launch_bwd_w(const BwdWProblem* pr, int n, int smem, bool split3, bool async, gs_stream_t stream) {
+  BwdWProblem q[3] = {};
+  int tx = 1, ty = 1, chunks = 0;
+  for (int i = 0; i < n; ++i) {
+    q[i] = pr[i];
+    tx = q[i].tiles_x > tx ? q[i].tiles_x : tx;
+    ty = q[i].tiles_y > ty ? q[i].tiles_y : ty;
+    chunks += q[i].chunks;
+  }
+  dim3 grid(tx, ty, chunks);
+  GS_TC_LAUNCH(sage_bwd_w_tc_kernel, grid, smem, as_stream(stream), q[0], q[1], q[2]);
   return finish_launch();
 }
 
@@ -1039,44 +1054,61 @@ int gs_sage_gemm_bwd_w_tc(const float* self_table, int64_t ld_self, const int32_
   if (precision != GS_PREC_TF32 && !split3) return GS_ERR_BAD_ARG;
   BwdWProblem pa{};
   pa.x = XView{self_table, ld_self, self_idx, agg, ld_agg, dim, (dim + 3) & ~3, gcn, nullptr, 0, 0};
-  pa.grad_out = grad_out; pa.ld_go = ld_go; pa.out = out; pa.ld_out = ld_out; pa.out_dim = out_dim; pa.relu = relu;
+  pa.grad_out = grad_out; pa.ld_go = ld_go; pa.out = out; pa.ld_out = ld_out; pa.out_dim = out_dim; pa.out_rows = out_dim;
+  pa.relu = relu;
   pa.num_rows_dev = num_rows_dev; pa.max_rows = max_rows; pa.grad_w = grad_w; pa.ldw = ldw;
   const int kt = gcn ? pa.x.dim_pad : 2 * pa.x.dim_pad;
   const int smem = plan_bwd_w(pa, kt, out_dim, max_rows, split3, kNumSMs);
-  BwdWProblem pb{};                                             // no second problem
-  return launch_bwd_w(pa, pb, smem, split3, bwd_w_async_ok(grad_out, ld_go, out_dim, relu), stream);
+  return launch_bwd_w(&pa, 1, smem, split3, bwd_w_async_ok(grad_out, ld_go, out_dim, relu), stream);
 }
 
-// Two problems in one launch (see sage_bwd_w_tc_kernel).  Returns GS_ERR_UNSUPPORTED when they cannot share a
-// kernel instantiation (the caller then launches them one after the other).
-int gs_sage_gemm_bwd_w_pair_tc(const float* const* self_table, const int64_t* ld_self, const int32_t* const* self_idx,
-                               const float* const* agg, const int64_t* ld_agg, const int32_t* dim,
-                               const float* const* grad_out, const int64_t* ld_go, const float* const* out,
-                               const int64_t* ld_out, const int32_t* out_dim, int32_t gcn, int32_t relu,
-                               const int32_t* const* num_rows_dev, const int32_t* max_rows, float* const* grad_w,
-                               const int64_t* ldw, int32_t precision, gs_stream_t stream) {
+// Up to three problems in one launch (see sage_bwd_w_tc_kernel).  gcn / relu are per problem; go_cols[i] (nullable
+// array; 0 = out_dim[i]) is the zero-padded width of problem i's dZ rows.  Returns GS_ERR_UNSUPPORTED when the problems
+// cannot share a kernel instantiation (the caller then launches them one after the other).
+int gs_sage_gemm_bwd_w_group_tc(int32_t n, const float* const* self_table, const int64_t* ld_self,
+                                const int32_t* const* self_idx, const float* const* agg, const int64_t* ld_agg,
+                                const int32_t* dim, const float* const* grad_out, const int64_t* ld_go,
+                                const float* const* out, const int64_t* ld_out, const int32_t* out_dim,
+                                const int32_t* go_cols, const int32_t* gcn, const int32_t* relu,
+                                const int32_t* const* num_rows_dev, const int32_t* max_rows, float* const* grad_w,
+                                const int64_t* ldw, int32_t precision, gs_stream_t stream) {
   const bool split3 = precision == GS_PREC_TF32X3;
   if (precision != GS_PREC_TF32 && !split3) return GS_ERR_BAD_ARG;
-  BwdWProblem pr[2] = {};
-  int kt[2];
-  double work[2];
-  for (int i = 0; i < 2; ++i) {
-    pr[i].x = XView{self_table[i], ld_self[i], self_idx[i], agg[i], ld_agg[i], dim[i], (dim[i] + 3) & ~3, gcn, nullptr, 0, 0};
+  if (n < 1 || n > 3) return GS_ERR_BAD_ARG;
+  BwdWProblem pr[3] = {};
+  int kt[3];
+  bool async0 = false;
+  for (int i = 0; i < n; ++i) {
+    pr[i].x = XView{self_table[i], ld_self[i], self_idx[i], agg[i], ld_agg[i], dim[i], (dim[i] + 3) & ~3, gcn[i], nullptr, 0, 0};
+    const int cols = (go_cols && go_cols[i] > 0) ? go_cols[i] : out_dim[i];
+    if (cols < out_dim[i] || cols > ld_go[i]) return GS_ERR_BAD_ARG;
     pr[i].grad_out = grad_out[i]; pr[i].ld_go = ld_go[i]; pr[i].out = out[i]; pr[i].ld_out = ld_out[i];
-    pr[i].out_dim = out_dim[i]; pr[i].relu = relu; pr[i].num_rows_dev = num_rows_dev[i]; pr[i].max_rows = max_rows[i];
+    pr[i].out_dim = cols; pr[i].out_rows = out_dim[i]; pr[i].relu = relu[i];
+    pr[i].num_rows_dev = num_rows_dev[i]; pr[i].max_rows = max_rows[i];
     pr[i].grad_w = grad_w[i]; pr[i].ldw = ldw[i];
-    kt[i] = gcn ? pr[i].x.dim_pad : 2 * pr[i].x.dim_pad;
-    work[i] = static_cast<double>(max_rows[i]) * kt[i] * out_dim[i];
+    kt[i] = gcn[i] ? pr[i].x.dim_pad : 2 * pr[i].x.dim_pad;
+    const bool a = bwd_w_async_ok(grad_out[i], ld_go[i], cols, relu[i]);
+    if (i == 0) async0 = a;
+    else if (a != async0) return GS_ERR_UNSUPPORTED;
   }
-  const bool async0 = bwd_w_async_ok(grad_out[0], ld_go[0], out_dim[0], relu);
-  if (async0 != bwd_w_async_ok(grad_out[1], ld_go[1], out_dim[1], relu)) return GS_ERR_UNSUPPORTED;
-  // CTAs in proportion to the work, every problem at least one CTA per output tile
-  int budget1 = static_cast<int>(kNumSMs * work[1] / (work[0] + work[1]) + 0.5);
-  if (budget1 < 2) budget1 = 2;
-  if (budget1 > kNumSMs - 2) budget1 = kNumSMs - 2;
-  const int smem0 = plan_bwd_w(pr[0], kt[0], out_dim[0], max_rows[0], split3, kNumSMs - budget1);
-  const int smem1 = plan_bwd_w(pr[1], kt[1], out_dim[1], max_rows[1], split3, budget1);
-  return launch_bwd_w(pr[0], pr[1], smem0 > smem1 ? smem0 : smem1, split3, async0, stream);
+  // CTAs of EQUAL length: every problem is cut into chunks of the same R rows, R the smallest multiple of the k-stage
+  // (>= 4 stages) with which all the CTAs fit one wave -- the grid ends when its longest CTA does, and a small problem
+  // given CTAs in proportion to its flops would have had the longest ones
+  int smem = 0, rows_fixed = kMaxChunkRows;
+  for (int r = 4 * kBK; r <= kMaxChunkRows; r += kBK) {
+    int ctas = 0;
+    for (int i = 0; i < n; ++i) {
+      const Plan p = make_plan(kt[i], true, true, split3, kNumSMs);
+      const int tiles = ((kt[i] + p.n_tile - 1) / p.n_tile) * ((pr[i].out_dim + kTileM - 1) / kTileM);
+      ctas += tiles * ((max_rows[i] + r - 1) / r);
+    }
+    if (ctas <= kNumSMs) { rows_fixed = r; break; }
+  }
+  for (int i = 0; i < n; ++i) {
+    const int sm = plan_bwd_w(pr[i], kt[i], pr[i].out_dim, max_rows[i], split3, 0, rows_fixed);
+    smem = sm > smem ? sm : smem;
+  }
+  return launch_bwd_w(pr, n, smem, split3, async0, stream);
 }
 
 #ifdef GS_TC_TRACE

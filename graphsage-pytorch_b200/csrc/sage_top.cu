@@ -57,6 +57,7 @@ struct Params {
   float* out_h; int64_t ld_h;
   float* out_agg; int64_t ld_agg;
   float* out_dz; int64_t ld_dz;
+  float* out_dlog; int64_t ld_dlog;                       // d(logits), kMaxClasses columns per row (zeros beyond num_classes)
   float* logp;
   float* loss; float* grad_cls_w; float* grad_cls_b;
   float* cls_w_rep; float* cls_b_rep; int cls_reps;       // replicas 1..cls_reps-1 of the classifier gradients (see P4c)
@@ -362,6 +363,12 @@ sage_top_sup_kernel(const Params p, const __grid_constant__ CUtensorMap tmap_w, 
       }
     }
     __syncthreads();
+    if (p.out_dlog && tid < kTM * (kMaxClasses / 4)) {    // d(logits) for a classifier weight gradient computed elsewhere
+      const int r = tid / (kMaxClasses / 4), c4 = (tid % (kMaxClasses / 4)) * 4;
+      if (row0 + r < rows)
+        *reinterpret_cast<float4*>(p.out_dlog + static_cast<int64_t>(row0 + r) * p.ld_dlog + c4) =
+            *reinterpret_cast<const float4*>(&s.dlog[r * kCs + c4]);
+    }
     GS_TOP_MARK(6);
 
     // ---- P4c: dh = dlog . Wc on the tensor cores, dZ = dh * (h > 0); then grad Wc = dlog^T . h and grad bc ----
@@ -524,7 +531,8 @@ extern "C" int gs_sage_top_sup(const float* table, int64_t ld_table, const int32
                                const float* weight, int64_t ldw, int32_t dim, int32_t out_dim, int32_t gcn,
                                const float* cls_w, const float* cls_b, int32_t num_classes, const int64_t* labels,
                                const int32_t* label_index, float* out_h, int64_t ld_h, float* out_agg, int64_t ld_agg,
-                               float* out_dz, int64_t ld_dz, float* logp, float* loss, float* grad_cls_w,
+                               float* out_dz, int64_t ld_dz, float* out_dlog, int64_t ld_dlog, float* logp,
+                               float* loss, float* grad_cls_w,
                                float* grad_cls_b, float* grad_table, int64_t ld_gt, void* workspace,
                                size_t workspace_bytes, int32_t precision, float* cls_w_replicas, float* cls_b_replicas,
                                int32_t cls_reps, gs_stream_t stream) {
@@ -538,15 +546,16 @@ extern "C" int gs_sage_top_sup(const float* table, int64_t ld_table, const int32
   if ((ld_table & 3) || (ldw & 3) || !aligned16(table) || !aligned16(weight) || !aligned16(cls_w)) return GS_ERR_ALIGNMENT;
   if ((out_h && ((ld_h & 1) || (reinterpret_cast<uintptr_t>(out_h) & 7u))) || (out_agg && ((ld_agg & 3) || !aligned16(out_agg))) ||
       (out_dz && ((ld_dz & 3) || !aligned16(out_dz))) || (grad_table && ((ld_gt & 3) || !aligned16(grad_table))) ||
-      (grad_cls_w && !aligned16(grad_cls_w)))
+      (grad_cls_w && !aligned16(grad_cls_w)) || (out_dlog && ((ld_dlog & 3) || !aligned16(out_dlog))))
     return GS_ERR_ALIGNMENT;
+  if (out_dlog && ld_dlog < top::kMaxClasses) return GS_ERR_BAD_ARG;
   if (!workspace || workspace_bytes < gs_sage_top_workspace_bytes()) return GS_ERR_WORKSPACE;
   if (cls_reps < 1 || cls_reps > 16 || (cls_reps > 1 && (!cls_w_replicas || !cls_b_replicas || !aligned16(cls_w_replicas))))
     return GS_ERR_BAD_ARG;
   if (cls_reps > 1 && ((num_classes * top::kH) & 3)) return GS_ERR_BAD_ARG;
   if (max_rows == 0) return GS_OK;
   top::Params p{table, ld_table, nbr_idx, stride, cnt, self_idx, num_rows_dev, max_rows, weight, ldw, cls_w, cls_b,
-                num_classes, labels, label_index, out_h, ld_h, out_agg, ld_agg, out_dz, ld_dz, logp, loss, grad_cls_w,
+                num_classes, labels, label_index, out_h, ld_h, out_agg, ld_agg, out_dz, ld_dz, out_dlog, ld_dlog, logp, loss, grad_cls_w,
                 grad_cls_b, cls_w_replicas, cls_b_replicas, cls_reps, grad_table, ld_gt, reinterpret_cast<float*>(workspace) + 4,
                 reinterpret_cast<unsigned int*>(workspace)};
   int tiles = (max_rows + top::kTM - 1) / top::kTM;

@@ -21,7 +21,7 @@ SELF_KEEP, SELF_DROP, SELF_ONCE = 0, 1, 2
 PREC_FP32, PREC_TF32, PREC_TF32X3 = 0, 1, 2
 MAX_FANOUT = 32
 UNIQUE_MARKED, UNIQUE_LEAVE_MARKS = 1, 2
-ABI_VERSION = 14
+ABI_VERSION = 15
 
 _P, _I, _L, _F, _U64, _SZ = c_void_p, c_int32, c_int64, c_float, c_uint64, c_size_t
 
@@ -51,8 +51,9 @@ _SIGNATURES = {
     "gs_split_lo": (_I, [_P, _P, _L, _P]),
     "gs_sage_top_workspace_bytes": (_SZ, []),
     "gs_sage_top_sup": (_I, [_P, _L, _P, _I, _P, _P, _P, _I, _P, _L, _I, _I, _I, _P, _P, _I, _P, _P, _P, _L, _P, _L, _P, _L,
-                             _P, _P, _P, _P, _P, _L, _P, _SZ, _I, _P, _P, _I, _P]),
+                             _P, _L, _P, _P, _P, _P, _P, _L, _P, _SZ, _I, _P, _P, _I, _P]),
     "gs_sage_gemm_bwd_w": (_I, [_P, _L, _P, _P, _L, _I, _P, _L, _P, _L, _I, _I, _I, _P, _I, _P, _L, _I, _P]),
+    "gs_sage_gemm_bwd_w_group": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
     "gs_sage_gemm_bwd_w_pair": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _I, _P]),
     "gs_sage_gemm_bwd_x": (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _P, _I, _P, _L, _P, _L, _I, _P]),
     "gs_relu_bwd_inplace": (_I, [_P, _L, _P, _L, _I, _P, _I, _P]),

@@ -232,11 +232,13 @@ def sage_top_workspace(device) -> torch.Tensor:
 
 def sage_top_sup(table, nbr_idx, stride: int, cnt, self_idx, num_rows, max_rows: int, weight, gcn: bool, cls_w, cls_b,
                  labels, label_index, loss, grad_cls_w, grad_cls_b, grad_table, workspace, precision: int, *,
-                 out_h=None, out_agg=None, out_dz=None, logp=None, cls_w_rep=None, cls_b_rep=None):
+                 out_h=None, out_agg=None, out_dz=None, logp=None, cls_w_rep=None, cls_b_rep=None, out_dlog=None):
     """The top SageLayer + classifier + NLL, forward and backward, in one launch (gs_sage_top_sup).
     Returns (h, agg, dz): the layer's output, and the B / A operands of its weight-gradient GEMM.
     `cls_w_rep` [R-1, C*128] / `cls_b_rep` [R-1, 64] (zeroed): more replicas of the classifier gradients the CTAs spread
-    their atomic adds over; the fused update folds them in (peer.DpExchange(extras=...))."""
+    their atomic adds over; the fused update folds them in (peer.DpExchange(extras=...)).
+    `out_dlog` [max_rows, 64] with grad_cls_w None: d(logits) is saved instead and the classifier's weight gradient is a
+    problem of sage_gemm_bwd_w_group."""
     native.require_cuda(table, "table")
     dev = table.device
     H = TOP_H
@@ -250,7 +252,8 @@ def sage_top_sup(table, nbr_idx, stride: int, cnt, self_idx, num_rows, max_rows:
     check(_lib().gs_sage_top_sup(ptr(table), table.stride(0), ptr(nbr_idx), stride, ptr(cnt), ptr(self_idx), ptr(num_rows),
                                  max_rows, ptr(weight), weight.stride(0), H, H, int(gcn), ptr(cls_w), ptr(cls_b), classes,
                                  ptr(labels), ptr(label_index), ptr(out_h), out_h.stride(0), ptr(out_agg), out_agg.stride(0),
-                                 ptr(out_dz), out_dz.stride(0), ptr(logp), ptr(loss), ptr(grad_cls_w), ptr(grad_cls_b),
+                                 ptr(out_dz), out_dz.stride(0), ptr(out_dlog), out_dlog.stride(0) if out_dlog is not None else 0,
+                                 ptr(logp), ptr(loss), ptr(grad_cls_w), ptr(grad_cls_b),
                                  ptr(grad_table), grad_table.stride(0) if grad_table is not None else 0, ptr(workspace),
                                  workspace.numel(), precision, ptr(cls_w_rep), ptr(cls_b_rep),
                                  1 + (int(cls_w_rep.shape[0]) if cls_w_rep is not None else 0), stream()), "gs_sage_top_sup")
@@ -267,20 +270,29 @@ def sage_gemm_bwd_w(self_table, self_idx, agg, dim: int, grad_out, out, out_dim:
     return grad_w
 
 
-def sage_gemm_bwd_w_pair(problems, gcn: bool, relu: bool, precision: int):
-    """Two weight-gradient problems in one launch (gs_sage_gemm_bwd_w_pair).  `problems`: two tuples
-    (self_table, self_idx, agg, dim, grad_out, out, out_dim, num_rows, max_rows, grad_w), as for sage_gemm_bwd_w."""
+def sage_gemm_bwd_w_group(problems, precision: int):
+    """Up to three weight-gradient problems in one launch (gs_sage_gemm_bwd_w_group).  `problems`: tuples
+    (self_table, self_idx, agg, dim, grad_out, out, out_dim, num_rows, max_rows, grad_w, gcn, relu, grad_out_cols);
+    the first ten as for sage_gemm_bwd_w, grad_out_cols = 0 or the zero-padded readable width of grad_out's rows."""
     import ctypes
-    assert len(problems) == 2
-    vp, i64, i32 = ctypes.c_void_p * 2, ctypes.c_int64 * 2, ctypes.c_int32 * 2
-    col = list(zip(*problems))
-    st, si, ag, dim, go, out, od, nr, mr, gw = col
+    n = len(problems)
+    assert 1 <= n <= 3
+    vp, i64, i32 = ctypes.c_void_p * n, ctypes.c_int64 * n, ctypes.c_int32 * n
+    st, si, ag, dim, go, out, od, nr, mr, gw, gcn, relu, cols = list(zip(*problems))
     ld = lambda ts: i64(*[int(t.stride(0)) if t is not None else 0 for t in ts])
-    check(_lib().gs_sage_gemm_bwd_w_pair(vp(*[ptr(t) for t in st]), ld(st), vp(*[ptr(t) for t in si]), vp(*[ptr(t) for t in ag]),
-                                         ld(ag), i32(*[int(d) for d in dim]), vp(*[ptr(t) for t in go]), ld(go),
-                                         vp(*[ptr(t) for t in out]), ld(out), i32(*[int(d) for d in od]), int(gcn), int(relu),
-                                         vp(*[ptr(t) for t in nr]), i32(*[int(m) for m in mr]), vp(*[ptr(t) for t in gw]),
-                                         ld(gw), precision, stream()), "gs_sage_gemm_bwd_w_pair")
+    ints = lambda xs: i32(*[int(x) for x in xs])
+    check(_lib().gs_sage_gemm_bwd_w_group(n, vp(*[ptr(t) for t in st]), ld(st), vp(*[ptr(t) for t in si]),
+                                          vp(*[ptr(t) for t in ag]), ld(ag), ints(dim), vp(*[ptr(t) for t in go]), ld(go),
+                                          vp(*[ptr(t) for t in out]), ld(out), ints(od), ints(cols), ints(gcn), ints(relu),
+                                          vp(*[ptr(t) for t in nr]), ints(mr), vp(*[ptr(t) for t in gw]), ld(gw),
+                                          precision, stream()), "gs_sage_gemm_bwd_w_group")
+
+
+def sage_gemm_bwd_w_pair(problems, gcn: bool, relu: bool, precision: int):
+    """Two weight-gradient problems with common gcn / relu in one launch.  `problems`: two tuples
+    (self_table, self_idx, agg, dim, grad_out, out, out_dim, num_rows, max_rows, grad_w), as for sage_gemm_bwd_w."""
+    assert len(problems) == 2
+    sage_gemm_bwd_w_group([tuple(q) + (int(gcn), int(relu), 0) for q in problems], precision)
 
 
 def sage_gemm_bwd_x(grad_out, out, weight, dim: int, out_dim: int, gcn: bool, relu: bool, num_rows, max_rows: int,

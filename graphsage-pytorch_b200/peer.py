@@ -184,6 +184,13 @@ class DpExchange:
             nbytes = int(lib.gs_dp_region_bytes(self.n_total, self.world))
             self.region = PeerRegion(nbytes, flat_grad.device, group=group, world=self.world, rank=self.rank)
             self._regions = (ctypes.c_void_p * self.world)(*self.region.ptrs)
+            # the receive slots start out EMPTY (every word 0xffffffff): the exchange has no flags, data words are their
+            # own arrival signal (csrc/dp_update.cu); no rank may push before every rank has filled its region
+            recv_off = int(lib.gs_dp_region_recv_offset())
+            self.region.tensor(self.rank, recv_off, (nbytes - recv_off,), torch.uint8).fill_(0xFF)
+            torch.cuda.synchronize(flat_grad.device)
+            import torch.distributed as dist
+            dist.barrier(group=group)
 
     def update(self, max_norm: float, lr: float, step_counter: Optional[torch.Tensor] = None):
         """all-reduce(mean) -> clip per group -> SGD -> zero gradients (-> step_counter += 1); one launch

@@ -332,6 +332,11 @@ class SupervisedTrainer:
         #: configuration allows it (MEAN, hidden 128, <= 64 classes, tensor-core precision); GS_FUSED_TOP=0: never
         self.fused_top = os.environ.get("GS_FUSED_TOP", "1") != "0"
         self._top_ws = ops.sage_top_workspace(dev)
+        #: two-layer steps: the classifier's weight gradient dlog^T . h runs as a third problem of the weight-gradient
+        #: launch (a few row chunks) instead of one atomic add per CTA and element inside the top-layer kernel, which
+        #: then only saves d(logits); GS_CLS_DW_GROUP=0: inside the top-layer kernel
+        self.cls_dw_in_group = os.environ.get("GS_CLS_DW_GROUP", "1") != "0" and self._cls_rep is None
+        self._dlog: Optional[torch.Tensor] = None
 
     # ---- the weight-dependent half of a step on prepared frontiers -------------------------------
     def _fused_top_ok(self, layers) -> bool:
@@ -360,22 +365,33 @@ class SupervisedTrainer:
         g_below = below.gh
         m._run_compute(layers, weights, upto=L - 1, zero_grad_of_last=g_below, weights_lo=self.weights_lo)
         top.table_in, top.dim_in = below.h, H
+        cls_in_group = self.cls_dw_in_group and L == 2
+        if cls_in_group and (self._dlog is None or self._dlog.shape[0] < top.rows_max):
+            self._dlog = torch.zeros((top.rows_max, ops.TOP_MAX_CLASSES), dtype=torch.float32, device=self.dev)
         top.h, top.agg, top.dz = ops.sage_top_sup(below.h, top.nbr_idx, top.stride, top.cnt, top.self_idx, top.num_rows,
                                                   top.rows_max, weights[L - 1], m.gcn, self.cls_w.detach(),
-                                                  self.cls_b.detach(), self.labels, seeds, loss_out, self.grads[n_sage],
+                                                  self.cls_b.detach(), self.labels, seeds, loss_out,
+                                                  None if cls_in_group else self.grads[n_sage],
                                                   self.grads[n_sage + 1], g_below, self._top_ws, prec, out_h=top.h,
                                                   out_agg=top.agg, out_dz=top.dz,
                                                   cls_w_rep=self._cls_rep[0] if self._cls_rep else None,
-                                                  cls_b_rep=self._cls_rep[1] if self._cls_rep else None)
+                                                  cls_b_rep=self._cls_rep[1] if self._cls_rep else None,
+                                                  out_dlog=self._dlog if cls_in_group else None)
         top.argmax, dz = None, top.dz
         self.last_layers = layers
         if L == 2:
-            # both weight gradients are leaves now: ONE grid, CTAs split in proportion to the work (csrc/sage_gemm_tc.cu)
-            ops.sage_gemm_bwd_w_pair([
+            # the weight gradients are leaves now: ONE grid, CTAs split in proportion to the work (csrc/sage_gemm_tc.cu)
+            g = int(m.gcn)
+            problems = [
                 (None if m.gcn else below.table_in, below.self_idx, below.agg, below.dim_in, g_below, below.h, H,
-                 below.num_rows, below.rows_max, self.grads[0]),
+                 below.num_rows, below.rows_max, self.grads[0], g, 0, 0),
                 (None if m.gcn else below.h, top.self_idx, top.agg, H, dz, top.h, H, top.num_rows, top.rows_max,
-                 self.grads[1])], m.gcn, False, prec)
+                 self.grads[1], g, 0, 0)]
+            if cls_in_group:         # grad Wc[c, :] = sum_r dlog[r, c] h[r, :]: a 'gcn' problem whose rows are h
+                classes = int(self.cls_w.shape[0])
+                problems.append((None, None, top.h, H, self._dlog, None, classes, top.num_rows, top.rows_max,
+                                 self.grads[n_sage], 1, 0, (classes + 3) & ~3))
+            ops.sage_gemm_bwd_w_group(problems, prec)
             return
         main = torch.cuda.current_stream()
         self._side.wait_stream(main)

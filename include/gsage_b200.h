@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 14
+#define GS_ABI_VERSION 15
 
 #define GS_OK 0
 #define GS_ERR_BAD_ARG (-1)
@@ -238,10 +238,23 @@ int gs_sage_gemm_bwd_w(const float* self_table, int64_t ld_self, const int32_t* 
                        const int32_t* num_rows_dev, int32_t max_rows,
                        float* grad_w, int64_t ldw, int32_t precision, gs_stream_t stream);
 
-/* Two such problems -- the weight gradients of two layers of one step, independent leaves of its dependency graph --
- * in one call.  Every argument that differs per problem is a HOST array of 2 (device pointers / sizes of problem 0 and
- * 1); gcn, relu and precision are common.  With a tensor-core precision both run as ONE grid whose CTAs are split in
- * proportion to the work (rows x K x out_dim), so neither queues behind the other; otherwise one after the other. */
+/* Up to three such problems -- the weight gradients of the layers of one step and of its classifier (gcn = 1, agg = the
+ * classifier's input rows, grad_out = d(logits)), independent leaves of the step's dependency graph -- in one call.  Every
+ * argument is a HOST array of n (device pointers / sizes per problem).  grad_out_cols_host (nullable; entries 0 =
+ * out_dim): the zero-padded width of a problem's grad_out rows that may be read, so that a width that is not a multiple
+ * of 4 (47 classes) still takes the 16-byte copy path.  With a tensor-core precision all run as ONE grid whose CTAs
+ * are split in proportion to the work (rows x K x out_dim), so none queues behind another; otherwise one after the other. */
+int gs_sage_gemm_bwd_w_group(int32_t n, const float* const* self_table_host, const int64_t* ld_self_host,
+                             const int32_t* const* self_idx_host, const float* const* agg_host,
+                             const int64_t* ld_agg_host, const int32_t* dim_host,
+                             const float* const* grad_out_host, const int64_t* ld_go_host,
+                             const float* const* out_host, const int64_t* ld_out_host,
+                             const int32_t* out_dim_host, const int32_t* grad_out_cols_host,
+                             const int32_t* gcn_host, const int32_t* relu_host,
+                             const int32_t* const* num_rows_dev_host, const int32_t* max_rows_host,
+                             float* const* grad_w_host, const int64_t* ldw_host, int32_t precision, gs_stream_t stream);
+
+/* The two-problem form with common gcn / relu. */
 int gs_sage_gemm_bwd_w_pair(const float* const* self_table_host, const int64_t* ld_self_host,
                             const int32_t* const* self_idx_host, const float* const* agg_host,
                             const int64_t* ld_agg_host, const int32_t* dim_host,
@@ -309,6 +322,10 @@ int gs_cls_nll_fwd_bwd(const float* emb, int64_t ld_emb, int32_t rows, int32_t d
  * (table[t,:] > 0) -- `table` is the ReLU output of the layer below, so grad_table (zeroed by the caller, e.g. by
  * gs_sage_gemm_fwd_ex) receives that layer's d(pre-activation).  out_agg / out_dz are the B / A operands of this
  * layer's gs_sage_gemm_bwd_w (relu = 0).  out_h, logp, grad_table, grad_cls_* are nullable.
+ * out_dlog (nullable, [rows x ld_dlog], ld_dlog >= 64): d(logits) of the batch rows, columns num_classes..63 zero.  With
+ * it and grad_cls_w NULL the classifier's weight gradient dlog^T . h is left to gs_sage_gemm_bwd_w_group (problem with
+ * gcn = 1, agg = out_h, grad_out = out_dlog, grad_out_cols = 64 or num_classes rounded up to 4): a handful of row chunks
+ * there instead of one atomic add per CTA and element here.
  * Supported: dim == out_dim == 128, MEAN, num_classes <= 64, stride <= 16, precision TF32X3 / TF32 (mma.sync
  * m16n8k8 in the same 3-term split as K4); anything else returns GS_ERR_UNSUPPORTED and the caller runs the layer
  * as gs_agg_fwd -> gs_sage_gemm_fwd -> gs_cls_nll_fwd_bwd -> gs_sage_gemm_bwd_x -> gs_agg_bwd.
@@ -325,8 +342,8 @@ int gs_sage_top_sup(const float* table, int64_t ld_table, const int32_t* nbr_idx
                     const float* weight, int64_t ldw, int32_t dim, int32_t out_dim, int32_t gcn,
                     const float* cls_w, const float* cls_b, int32_t num_classes, const int64_t* labels,
                     const int32_t* label_index, float* out_h, int64_t ld_h, float* out_agg, int64_t ld_agg,
-                    float* out_dz, int64_t ld_dz, float* logp, float* loss, float* grad_cls_w,
-                    float* grad_cls_b, float* grad_table, int64_t ld_gt, void* workspace,
+                    float* out_dz, int64_t ld_dz, float* out_dlog, int64_t ld_dlog, float* logp, float* loss,
+                    float* grad_cls_w, float* grad_cls_b, float* grad_table, int64_t ld_gt, void* workspace,
                     size_t workspace_bytes, int32_t precision, float* cls_w_replicas, float* cls_b_replicas,
                     int32_t cls_reps, gs_stream_t stream);
 

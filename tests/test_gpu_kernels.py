@@ -590,6 +590,72 @@ def test_sage_gemm_bwd_w_pair_equals_two_launches(g, dev, precision):
         assert rel(gw, w) <= TOL and rel(single, w) <= TOL
 
 
+@pytest.mark.parametrize('classes,live', [(47, 1000), (64, None), (3, 130)])
+def test_classifier_weight_gradient_as_third_problem_of_the_group(g, dev, classes, live):
+    """The step's three weight gradients as ONE grid (gs_sage_gemm_bwd_w_group): the two layers' and the classifier's,
+    the latter from d(logits) saved by the top-layer kernel (out_dlog, 64 zero-padded columns, grad_cls_w = NULL) and the
+    layer output h -- against the fp64 products; the rows of grad Wc beyond num_classes do not exist and what follows
+    the buffer must stay untouched."""
+    from graphsage_b200 import native, ops
+    prec = native.PREC_TF32X3
+    rng = np.random.default_rng(classes)
+    H, fan, rows = 128, 10, 1024
+    n_live = rows if live is None else live
+    n_prev = 10900
+    d = lambda a: torch.from_numpy(a).to(dev)
+    table = np.maximum(rng.standard_normal((n_prev, H)), 0).astype(np.float32)
+    nbr = np.full((rows, fan), -1, dtype=np.int32)
+    cnt = rng.integers(1, fan + 1, size=rows).astype(np.int32)
+    self_idx = rng.integers(0, n_prev, size=rows).astype(np.int32)
+    for r in range(rows):
+        nbr[r, :cnt[r]] = np.sort(rng.choice(n_prev, size=cnt[r], replace=False))
+    w = (rng.standard_normal((H, 2 * H)) * 0.1).astype(np.float32)
+    cw = (rng.standard_normal((classes, H)) * 0.2).astype(np.float32)
+    cb = (rng.standard_normal(classes) * 0.1).astype(np.float32)
+    labels = rng.integers(0, classes, size=5000).astype(np.int64)
+    node_of_row = rng.integers(0, 5000, size=rows).astype(np.int32)
+    num_rows = None if live is None else torch.tensor([live], dtype=torch.int32, device=dev)
+    table_d, g_table = d(table), torch.zeros((n_prev, H), device=dev)
+    guard = torch.full((classes * H + 64,), 7.0, device=dev)          # grad Wc followed by a guard zone
+    gcw = guard[:classes * H].view(classes, H)
+    gcw.zero_()
+    gcb, loss_d = torch.zeros((classes,), device=dev), torch.zeros((1,), device=dev)
+    dlog = torch.full((rows, 64), 9.0, device=dev)
+    ws = ops.sage_top_workspace(dev)
+    out_h, out_agg, out_dz = ops.sage_top_sup(table_d, d(nbr), fan, d(cnt), d(self_idx), num_rows, rows, d(w), False, d(cw),
+                                              d(cb), d(labels), d(node_of_row), loss_d, None, gcb, g_table, ws, prec,
+                                              out_dlog=dlog)
+    torch.cuda.synchronize()
+    assert float(gcw.abs().max()) == 0.0                                # the kernel left the weight gradient alone
+    # d(logits) against torch: (softmax - onehot) / rows, zero beyond the classes
+    hh = out_h[:n_live].double()
+    logp = torch.log_softmax(hh @ d(cw).double().t() + d(cb).double(), 1)
+    y = d(labels)[d(node_of_row)[:n_live].long()]
+    want_dlog = logp.exp()
+    want_dlog[torch.arange(n_live, device=dev), y] -= 1.0
+    want_dlog /= n_live
+    assert rel(dlog[:n_live, :classes], want_dlog) <= 1e-5
+    assert float(dlog[:n_live, classes:].abs().max() if classes < 64 else 0.0) == 0.0
+    # the three problems in one launch
+    tab1 = d(rng.standard_normal((30000, 100)).astype(np.float32))
+    sidx1 = d(rng.integers(0, 30000, size=11264).astype(np.int32))
+    agg1 = d(rng.standard_normal((11264, 100)).astype(np.float32))
+    dz1 = d((rng.standard_normal((11264, H)) * (rng.random((11264, H)) > 0.5)).astype(np.float32))
+    nr1 = torch.tensor([10900], dtype=torch.int32, device=dev)
+    gw1, gw2 = torch.zeros((H, 200), device=dev), torch.zeros((H, 2 * H), device=dev)
+    ops.sage_gemm_bwd_w_group([
+        (tab1, sidx1, agg1, 100, dz1, None, H, nr1, 11264, gw1, 0, 0, 0),
+        (table_d, d(self_idx), out_agg, H, out_dz, None, H, num_rows, rows, gw2, 0, 0, 0),
+        (None, None, out_h, H, dlog, None, classes, num_rows, rows, gcw, 1, 0, (classes + 3) & ~3)], prec)
+    torch.cuda.synchronize()
+    X1 = torch.cat([tab1[sidx1[:10900].long()], agg1[:10900]], 1).double()
+    assert rel(gw1, dz1[:10900].double().t() @ X1) <= TOL
+    X2 = torch.cat([table_d[d(self_idx)[:n_live].long()], out_agg[:n_live]], 1).double()
+    assert rel(gw2, out_dz[:n_live].double().t() @ X2) <= TOL
+    assert rel(gcw, dlog[:n_live, :classes].double().t() @ hh) <= TOL
+    assert torch.all(guard[classes * H:] == 7.0)
+
+
 def test_fused_sampler_unique_chain_equals_numpy(g, dev):
     """The 5-launch preparation chain: sample(+fetch from the device queue, +mark) -> bitmap scan -> emit/remap ->
     sample(+clear).  Unique ids / remap indices must equal numpy's on the drawn lists, the bitmap must be all-zero

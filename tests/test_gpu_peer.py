@@ -3,8 +3,8 @@
 
   * gs_dp_allreduce_clip_sgd at world 1 against torch's clip_grad_norm_ + SGD (src/utils.py:185-187);
   * the same kernel as rank 0 of a world of 2, with the peer emulated by pre-filling this rank's
-    receive slot and flags (so nothing waits), checking the sum order, the pushed copy and the
-    published flags;
+    receive slot (so nothing waits), checking the sum order, the pushed copy, the slot being left
+    empty again and the rewrite of a gradient word that carries the empty pattern;
   * gs_agg_fwd_bf16_sharded against the dense fp32 kernel on the bf16-rounded table;
   * GraphSage over a ShardedTable against GraphSage over the equivalent dense table.
 """
@@ -26,6 +26,14 @@ def rel(a, b):
     a = np.asarray(a.detach().cpu() if isinstance(a, torch.Tensor) else a, dtype=np.float64)
     b = np.asarray(b.detach().cpu() if isinstance(b, torch.Tensor) else b, dtype=np.float64)
     return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def _empty_region(lib, n_total, world, dev):
+    """An exchange region as peer.DpExchange prepares it: zeroed header, receive slots filled with the EMPTY word."""
+    nbytes, recv_off = int(lib.gs_dp_region_bytes(n_total, world)), int(lib.gs_dp_region_recv_offset())
+    reg = torch.zeros((nbytes,), dtype=torch.uint8, device=dev)
+    reg[recv_off:].fill_(0xFF)
+    return reg, recv_off
 
 
 @pytest.fixture(scope='module')
@@ -106,10 +114,9 @@ def test_dp_update_folds_gradient_replicas_and_keeps_weight_low_halves(P, dev, w
     total = [grads[0].clone(), grads[1] + ex_w.sum(0).view(47, 128), grads[2] + ex_b[:, :47].sum(0)]
     kw = {}
     if world == 2:      # the emulated peer contributes zeros: the mean halves the local sum
-        nbytes, recv_off = int(lib.gs_dp_region_bytes(flat.numel(), 2)), int(lib.gs_dp_region_recv_offset())
-        mine = torch.zeros((nbytes,), dtype=torch.uint8, device=dev)
-        theirs = torch.zeros((nbytes,), dtype=torch.uint8, device=dev)
-        mine[:recv_off].view(torch.int32).view(8, -1)[1].fill_(1)
+        mine, recv_off = _empty_region(lib, flat.numel(), 2, dev)
+        theirs, _ = _empty_region(lib, flat.numel(), 2, dev)
+        mine[recv_off:].view(torch.float32).view(2, 2, flat.numel())[1, 1].zero_()      # epoch 1 -> parity 1, source rank 1
         kw = dict(region_ptrs=[mine.data_ptr(), theirs.data_ptr()])
         total = [t * 0.5 for t in total]
     want, _ = _torch_update(params, total, groups, 5.0, 0.7)
@@ -135,18 +142,13 @@ def test_dp_update_rank0_of_2_with_emulated_peer(P, dev):
     groups = [0, 1, 1]
     params, offs, flat, grads = _flat_problem(dev, shapes, 11, 2.0)
     n_total = flat.numel()
-    nbytes = int(lib.gs_dp_region_bytes(n_total, 2))
-    recv_off = int(lib.gs_dp_region_recv_offset())
-    mine = torch.zeros((nbytes,), dtype=torch.uint8, device=dev)
-    theirs = torch.zeros((nbytes,), dtype=torch.uint8, device=dev)
+    mine, recv_off = _empty_region(lib, n_total, 2, dev)
+    theirs, _ = _empty_region(lib, n_total, 2, dev)
     dp = P.DpExchange(flat, params, offs, groups, world=2, rank=0, region_ptrs=[mine.data_ptr(), theirs.data_ptr()])
-    max_ctas = recv_off // 4 // 8
-    my_flags = mine[:recv_off].view(torch.int32).view(8, max_ctas)
-    their_flags = theirs[:recv_off].view(torch.int32).view(8, max_ctas)
     my_recv = mine[recv_off:].view(torch.float32).view(2, 2, n_total)          # [parity][source rank][n]
     their_recv = theirs[recv_off:].view(torch.float32).view(2, 2, n_total)
     gen = torch.Generator(device='cpu').manual_seed(3)
-    for epoch in (1, 2, 3):
+    for epoch in (1, 2, 3, 4):
         par = epoch & 1
         local = (torch.randn((n_total,), generator=gen) * 2.0).to(dev)
         for gr, o in zip(grads, offs):
@@ -155,8 +157,8 @@ def test_dp_update_rank0_of_2_with_emulated_peer(P, dev):
         remote = torch.zeros_like(flat)
         for gr, o in zip(grads, offs):
             remote[o:o + gr.numel()] = (torch.randn((gr.numel(),), generator=gen) * 2.0).to(dev)
-        my_recv[par, 1].copy_(remote)              # what rank 1 would have pushed ...
-        my_flags[1].fill_(epoch)                   # ... and published
+        assert torch.all(my_recv[par, 1].view(torch.int32) == -1)               # empty before the peer pushes
+        my_recv[par, 1].copy_(remote)              # what rank 1 would have pushed
         mean = [((local[o:o + p.numel()] + remote[o:o + p.numel()]) * 0.5).view_as(p) for o, p in zip(offs, params)]
         want, _ = _torch_update(params, mean, groups, 5.0, 0.7)
         torch.cuda.synchronize()
@@ -165,9 +167,28 @@ def test_dp_update_rank0_of_2_with_emulated_peer(P, dev):
         for p, w in zip(params, want):
             assert rel(p, w) <= 1e-6
         assert torch.equal(their_recv[par, 0], local)                           # my gradient landed in the peer's slot
-        grid = int(their_flags[0].ne(0).sum().item())
-        assert grid >= 1 and torch.all(their_flags[0, :grid] == epoch) and torch.all(their_flags[0, grid:] == 0)
+        assert torch.all(my_recv[par, 1].view(torch.int32) == -1)               # what I consumed is empty again
+        assert torch.all(my_recv[par ^ 1].view(torch.int32) == -1) and torch.all(my_recv[par, 0].view(torch.int32) == -1)
         assert float(flat.abs().max()) == 0.0
+        their_recv[par, 0].view(torch.int32).fill_(-1)                          # the peer's own kernel would have done this
+
+
+def test_dp_update_never_pushes_the_empty_pattern(P, dev):
+    """A gradient word with the bits 0xffffffff (a NaN) must not look like 'nothing arrived' to the peer: it goes out
+    as the canonical NaN."""
+    from graphsage_b200 import native
+    lib = native.load()
+    shapes = [(16, 16)]
+    params, offs, flat, grads = _flat_problem(dev, shapes, 5)
+    mine, recv_off = _empty_region(lib, flat.numel(), 2, dev)
+    theirs, _ = _empty_region(lib, flat.numel(), 2, dev)
+    mine[recv_off:].view(torch.float32).view(2, 2, flat.numel())[1, 1].zero_()
+    flat.view(torch.int32)[7] = -1
+    dp = P.DpExchange(flat, params, offs, [0], world=2, rank=0, region_ptrs=[mine.data_ptr(), theirs.data_ptr()])
+    dp.update(5.0, 0.7)
+    assert dp.status()[:2] == (1, 0)
+    sent = theirs[recv_off:].view(torch.int32).view(2, 2, flat.numel())[1, 0]
+    assert int(sent[7]) == 0x7fffffff and not bool((sent == -1).any())
 
 
 def test_dp_update_times_out_instead_of_hanging(P, dev):
@@ -175,9 +196,8 @@ def test_dp_update_times_out_instead_of_hanging(P, dev):
     params, offs, flat, grads = _flat_problem(dev, shapes, 1)
     from graphsage_b200 import native
     lib = native.load()
-    nbytes = int(lib.gs_dp_region_bytes(flat.numel(), 2))
-    mine = torch.zeros((nbytes,), dtype=torch.uint8, device=dev)
-    theirs = torch.zeros((nbytes,), dtype=torch.uint8, device=dev)
+    mine, _ = _empty_region(lib, flat.numel(), 2, dev)
+    theirs, _ = _empty_region(lib, flat.numel(), 2, dev)
     dp = P.DpExchange(flat, params, offs, [0], world=2, rank=0, timeout_s=0.05,
                       region_ptrs=[mine.data_ptr(), theirs.data_ptr()])
     dp.update(5.0, 0.7)                                # the peer never publishes
