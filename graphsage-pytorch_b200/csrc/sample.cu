@@ -5,7 +5,8 @@
 namespace gs {
 
 // ---------------------------------------------------------------------------------------
-// K1: one WARP per destination row, everything in registers.  Replaces src/models.py:279-285.
+// K1: one warp -- or half-warp, see the kernel -- per destination row, everything in registers.  Replaces
+// src/models.py:279-285.
 //   deg <  k : every neighbour (lane j reads col[beg+j])             (:282 else-branch)
 //   deg >= k : k distinct uniform positions by Floyd's subset sampling: for i in 0..k-1,
 //              j = deg-k+i, draw t in [0,j]; take t unless some earlier pick equals t, else
@@ -50,6 +51,13 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, int bytes) {
 #endif
 }
 
+// LANES = 32: one warp per row.  LANES = 16 (fan-out + self <= 16, the usual case): one HALF-warp per row, two rows per
+// warp -- the kernel is a chain of three dependent memory round trips per row (node id -> rowptr -> col) with a few
+// hundred cycles of warp votes in between, so what matters is that every row of a launch is resident at once: 11K rows
+// are 1.2 waves of whole warps but 0.6 of a wave of half-warps.  A lane's pick index is its lane number inside the
+// group, so the draws (Philox block (row, pick)) and the outputs are the same for both layouts.  All warp-level
+// operations are executed by the whole warp (full mask); votes are cut down to the lane's group afterwards.
+template <int LANES>
 __global__ void __launch_bounds__(kSampleWarps * 32)
 sample_neighbors_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t num_nodes,
                         const int32_t* __restrict__ nodes, const int32_t* __restrict__ num_rows_dev, int max_rows,
@@ -57,8 +65,12 @@ sample_neighbors_kernel(const int64_t* __restrict__ rowptr, const int32_t* __res
                         const int64_t* __restrict__ offset_dev,
                         int32_t* __restrict__ out_nbr, int32_t* __restrict__ out_cnt, const SampleExtras ex) {
   pdl_sync();
+  constexpr int kRowsPerWarp = 32 / LANES;
+  constexpr uint32_t kFull = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  const int r = blockIdx.x * kSampleWarps + (threadIdx.x >> 5);
+  const int sl = lane % LANES;                                                  // lane inside the row's group = pick index
+  const uint32_t gm = LANES == 32 ? kFull : (0xffffu << (lane & 16));           // the lanes of my group
+  const int r = (blockIdx.x * kSampleWarps + (threadIdx.x >> 5)) * kRowsPerWarp + lane / LANES;
   const int rows = live_rows(num_rows_dev, max_rows);
   const int32_t* src = nodes;
   if (ex.queue != nullptr) {                      // fused gs_fetch_batch
@@ -66,69 +78,73 @@ sample_neighbors_kernel(const int64_t* __restrict__ rowptr, const int32_t* __res
     const long long q_rows = ex.queue[1], next = ex.queue[2];
     src = (base != nullptr && q_rows > 0) ? base + (next % q_rows) * max_rows : nullptr;
   }
+  constexpr int32_t kNone = 0x7fffffff;
+  const bool live = r < rows && r < max_rows;
+  const int32_t me = (live && src != nullptr) ? __ldg(src + r) : -1;
+  const bool ok = live && me >= 0 && me < num_nodes;
+  if (live && ex.fetch_dst != nullptr && sl == 0) ex.fetch_dst[r] = me;
+  int64_t beg = 0;
+  uint32_t deg = 0;
+  if (ok) {
+    if (sl == 0) {
+      if (ex.clear != nullptr) ex.clear[me >> 5] = 0u;
+      if (ex.mark != nullptr) atomicOr(ex.mark + (me >> 5), 1u << (me & 31));
+    }
+    beg = __ldg(rowptr + me);
+    deg = static_cast<uint32_t>(__ldg(rowptr + me + 1) - beg);
+  }
+  const bool floyd = ok && deg >= static_cast<uint32_t>(k);
+  int32_t val = kNone;
+  if (ok && !floyd && static_cast<uint32_t>(sl) < deg) val = __ldg(col + beg + sl);
+  if (__any_sync(kFull, floyd)) {
+    if (offset_dev != nullptr) offset += static_cast<uint64_t>(__ldg(offset_dev)) << 8;
+    // Floyd's subset sampling.  Draw i comes from Philox block (row, i): lane i of the group computes its own (the k
+    // draws in parallel instead of every lane running the same serial stream); only the "already taken?" resolution is
+    // sequential, one shuffle + one vote per pick.  (Groups whose row takes every neighbour run along idly.)
+    const uint32_t j_mine = deg - k + sl;                     // pick i ranges over [0, deg - k + i]
+    uint32_t t_mine = 0;
+    if (floyd && sl < k) {
+      uint32_t draw[4];
+      philox4x32_10(static_cast<uint32_t>(r), static_cast<uint32_t>(sl), static_cast<uint32_t>(offset),
+                    static_cast<uint32_t>(offset >> 32), seed, draw);
+      t_mine = __umulhi(draw[0], j_mine + 1);                 // uniform in [0, j]
+    }
+    uint32_t mypos = 0xffffffffu;
+    for (int i = 0; i < k; ++i) {
+      const uint32_t t = __shfl_sync(kFull, t_mine, i, LANES);
+      const bool taken = (__ballot_sync(kFull, mypos == t) & gm) != 0u;
+      if (sl == i) mypos = taken ? j_mine : t;
+    }
+    if (floyd && sl < k) val = __ldg(col + beg + mypos);
+  }
+  bool valid = val != kNone;
+  if (self_mode != GS_SELF_KEEP && val == me) valid = false;
+  if (self_mode == GS_SELF_ONCE && sl == k && ok) { val = me; valid = true; }   // k < LANES in this mode
+  // The reference's rows are sets (src/dataCenter.py:33).  A CSR row that repeats an id (graphs generated on the
+  // device) must behave the same way: a repeated id keeps only its lowest lane -- otherwise two lanes would share
+  // a rank and leave a slot unwritten.  Invalid lanes get keys of their own, so they match nobody.
+  const uint32_t same = __match_any_sync(kFull, valid ? static_cast<uint32_t>(val) : (0x80000000u | lane)) & gm;
+  valid = valid && (same & ((1u << lane) - 1u)) == 0u;
+  const int32_t key = valid ? val : kNone;
+  int rank = 0;
+  const int scan = k + (self_mode == GS_SELF_ONCE ? 1 : 0);
+  for (int o = 0; o < scan; ++o) rank += (__shfl_sync(kFull, key, o, LANES) < key) ? 1 : 0;
+  const int m = __popc(__ballot_sync(kFull, valid) & gm);
   if (r < max_rows) {
     int32_t* dst = out_nbr + static_cast<int64_t>(r) * stride;
-    if (r >= rows) {           // keep the padding region well defined for the consumers
-      for (int j = lane; j < stride; j += 32) dst[j] = -1;
-      if (lane == 0) out_cnt[r] = 0;
+    if (!live) {               // keep the padding region well defined for the consumers
+      for (int j = sl; j < stride; j += LANES) dst[j] = -1;
+      if (sl == 0) out_cnt[r] = 0;
     } else {
-      const int32_t me = src != nullptr ? __ldg(src + r) : -1;
-      if (ex.fetch_dst != nullptr && lane == 0) ex.fetch_dst[r] = me;
-      constexpr int32_t kNone = 0x7fffffff;
-      int32_t val = kNone;
-      if (me >= 0 && me < num_nodes) {
-        if (lane == 0) {
-          if (ex.clear != nullptr) ex.clear[me >> 5] = 0u;
-          if (ex.mark != nullptr) atomicOr(ex.mark + (me >> 5), 1u << (me & 31));
-        }
-        const int64_t beg = __ldg(rowptr + me);
-        const uint32_t deg = static_cast<uint32_t>(__ldg(rowptr + me + 1) - beg);
-        if (deg < static_cast<uint32_t>(k)) {
-          if (static_cast<uint32_t>(lane) < deg) val = __ldg(col + beg + lane);
-        } else {
-          if (offset_dev != nullptr) offset += static_cast<uint64_t>(__ldg(offset_dev)) << 8;
-          // Floyd's subset sampling.  Draw i comes from Philox block (row, i): lane i computes its own (the k draws in
-          // parallel instead of every lane running the same serial stream); only the "already taken?" resolution is
-          // sequential, one shuffle + one vote per pick.
-          const uint32_t j_mine = deg - k + lane;                 // pick i ranges over [0, deg - k + i]
-          uint32_t t_mine = 0;
-          if (lane < k) {
-            uint32_t draw[4];
-            philox4x32_10(static_cast<uint32_t>(r), static_cast<uint32_t>(lane), static_cast<uint32_t>(offset),
-                          static_cast<uint32_t>(offset >> 32), seed, draw);
-            t_mine = __umulhi(draw[0], j_mine + 1);               // uniform in [0, j]
-          }
-          uint32_t mypos = 0xffffffffu;
-          for (int i = 0; i < k; ++i) {
-            const uint32_t t = __shfl_sync(0xffffffffu, t_mine, i);
-            const bool taken = __any_sync(0xffffffffu, mypos == t);
-            if (lane == i) mypos = taken ? j_mine : t;
-          }
-          if (lane < k) val = __ldg(col + beg + mypos);
-        }
-      }
-      bool valid = val != kNone;
-      if (self_mode != GS_SELF_KEEP && val == me) valid = false;
-      if (self_mode == GS_SELF_ONCE && lane == k) { val = me; valid = true; }     // k <= 31 in this mode
-      // The reference's rows are sets (src/dataCenter.py:33).  A CSR row that repeats an id (graphs generated on the
-      // device) must behave the same way: a repeated id keeps only its lowest lane -- otherwise two lanes would share
-      // a rank and leave a slot unwritten.  Invalid lanes get keys of their own, so they match nobody.
-      const uint32_t same = __match_any_sync(0xffffffffu, valid ? static_cast<uint32_t>(val) : (0x80000000u | lane));
-      valid = valid && (same & ((1u << lane) - 1u)) == 0u;
-      const int32_t key = valid ? val : kNone;
-      int rank = 0;
-      const int scan = k + (self_mode == GS_SELF_ONCE ? 1 : 0);
-      for (int o = 0; o < scan; ++o) rank += (__shfl_sync(0xffffffffu, key, o) < key) ? 1 : 0;
-      const int m = __popc(__ballot_sync(0xffffffffu, valid));
       if (valid) {
         dst[rank] = val;
         if (ex.mark != nullptr) atomicOr(ex.mark + (val >> 5), 1u << (val & 31));
         if (ex.prefetch_table != nullptr) prefetch_l2_bulk(ex.prefetch_table + val * ex.prefetch_ld_bytes, ex.prefetch_row_bytes);
       }
-      if (ex.prefetch_table != nullptr && lane == 31 && me >= 0 && me < num_nodes)
+      if (ex.prefetch_table != nullptr && sl == LANES - 1 && ok)
         prefetch_l2_bulk(ex.prefetch_table + me * ex.prefetch_ld_bytes, ex.prefetch_row_bytes);
-      for (int j = m + lane; j < stride; j += 32) dst[j] = -1;
-      if (lane == 0) out_cnt[r] = m;
+      for (int j = m + sl; j < stride; j += LANES) dst[j] = -1;
+      if (sl == 0) out_cnt[r] = m;
     }
   }
   if (ex.queue != nullptr) {                      // the last CTA to get here advances the queue cursor
@@ -391,9 +407,16 @@ extern "C" int gs_sample_neighbors_ex(const int64_t* rowptr, const int32_t* col,
     return GS_ERR_ALIGNMENT;
   SampleExtras ex{reinterpret_cast<long long*>(queue_desc), fetch_dst, mark_bitmap, clear_bitmap,
                   static_cast<const char*>(prefetch_table), prefetch_ld_bytes, prefetch_row_bytes};
-  launch(sample_neighbors_kernel, (max_rows + kSampleWarps - 1) / kSampleWarps, kSampleWarps * 32, 0, as_stream(stream),
-         rowptr, col, num_nodes, nodes, num_rows_dev, max_rows, k, stride, self_mode, seed, offset, offset_dev, out_nbr,
-         out_cnt, ex);
+  if (k + (self_mode == GS_SELF_ONCE ? 1 : 0) <= 16) {            // two rows per warp
+    const int per_cta = kSampleWarps * 2;
+    launch(sample_neighbors_kernel<16>, (max_rows + per_cta - 1) / per_cta, kSampleWarps * 32, 0, as_stream(stream),
+           rowptr, col, num_nodes, nodes, num_rows_dev, max_rows, k, stride, self_mode, seed, offset, offset_dev, out_nbr,
+           out_cnt, ex);
+  } else {
+    launch(sample_neighbors_kernel<32>, (max_rows + kSampleWarps - 1) / kSampleWarps, kSampleWarps * 32, 0,
+           as_stream(stream), rowptr, col, num_nodes, nodes, num_rows_dev, max_rows, k, stride, self_mode, seed, offset,
+           offset_dev, out_nbr, out_cnt, ex);
+  }
   return finish_launch();
 }
 
