@@ -113,7 +113,7 @@ __device__ __noinline__ uint4 dp_poll(const float4* slot, unsigned long long tim
   return v;
 }
 
-__device__ __noinline__ int seg_of(const DpSegs& s, long long elem) {
+__device__ __forceinline__ int seg_of(const DpSegs& s, long long elem) {
   int k = -1;
 #pragma unroll 4
   for (int i = 0; i < s.n; ++i)

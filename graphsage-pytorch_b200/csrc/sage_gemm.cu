@@ -13,6 +13,8 @@
 // row chunks, accumulated with fp32 atomics).  dZ = grad_out * (out > 0) is applied while
 // the tile is loaded, so the ReLU backward never touches HBM on its own.
 // The tcgen05 tensor-core path lives in sage_gemm_tc.cu.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gs {
@@ -257,6 +259,9 @@ int gs_sage_gemm_fwd_tc(const float*, int64_t, const int32_t*, const float*, int
                         int32_t, gs_stream_t);
 int gs_sage_gemm_fwd_tma(const float*, const float*, int64_t, int32_t, const float*, const float*, int64_t, int32_t,
                          const int32_t*, int32_t, float*, int64_t, int32_t, int32_t, float*, int64_t, gs_stream_t);
+int gs_sage_gemm_fwd_tma_gather(const float*, int64_t, const int32_t*, const float*, int64_t, int32_t, const float*,
+                                const float*, int64_t, int32_t, int32_t, const int32_t*, int32_t, float*, int64_t, int32_t,
+                                int32_t, float*, int64_t, gs_stream_t);
 int gs_sage_gemm_bwd_x_tc(const float*, int64_t, const float*, int64_t, const float*, int64_t, int32_t, int32_t, int32_t,
                           int32_t, const int32_t*, int32_t, float*, int64_t, float*, int64_t, int32_t, gs_stream_t);
 int gs_sage_gemm_bwd_w_tc(const float*, int64_t, const int32_t*, const float*, int64_t, int32_t, const float*, int64_t,
@@ -304,6 +309,16 @@ extern "C" int gs_sage_gemm_fwd_ex(const float* self_table, int64_t ld_self, con
                                          out_dim, num_rows_dev, max_rows, out, ld_out, relu, precision, zero_out, ld_zero,
                                          stream);
       if (e != GS_ERR_UNSUPPORTED) return e;
+    }
+    // GATHERED input rows of a width the 32-column boxes handle (dim % 4 == 0): the self half by TMA gather4, the
+    // aggregate half and W by tiled copies (sage_gemm_tma.cu); GS_TMA_GATHER=0 keeps the thread-staged kernel (A/B runs)
+    // (GS_TMA_GATHER=2: no fallback -- a refused shape is reported, for tests that must know which kernel ran)
+    static const int tma_gather = [] { const char* e = getenv("GS_TMA_GATHER"); return e ? atoi(e) : 1; }();
+    if (tma_gather && !l2_normalize && (dim & 3) == 0 && agg != nullptr) {
+      const int e = gs_sage_gemm_fwd_tma_gather(self_table, ld_self, self_idx, agg, ld_agg, dim, weight, weight_lo, ldw,
+                                                out_dim, gcn, num_rows_dev, max_rows, out, ld_out, relu, precision,
+                                                zero_out, ld_zero, stream);
+      if (e != GS_ERR_UNSUPPORTED || tma_gather == 2) return e;
     }
     return gs_sage_gemm_fwd_tc(self_table, ld_self, self_idx, agg, ld_agg, dim, weight, ldw, out_dim, gcn,
                                num_rows_dev, max_rows, out, ld_out, relu, precision, zero_out, ld_zero, l2_normalize, stream);

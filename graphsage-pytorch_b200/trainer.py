@@ -297,9 +297,12 @@ class SupervisedTrainer:
         # the self rows gathered inside the GEMMs (profiles/r2_dense_x1_sweep.txt).
         self.dense_x1 = (os.environ.get("GS_DENSE_X1", "0") == "1" and exchange == "peer" and model.dense_x_ok()
                          and _PRECISIONS[model.precision] != native.PREC_FP32)
+        # W1's low tf32 half w - trunc_tf32(w), kept current by the fused update: the layer-1 forward GEMM takes it as a
+        # TMA operand next to W1 itself (csrc/sage_gemm_tma.cu) instead of splitting the tile in shared memory
         self.weights_lo: List[Optional[torch.Tensor]] = [None] * n_sage
-        if self.dense_x1:
+        if exchange == "peer" and _PRECISIONS[model.precision] == native.PREC_TF32X3 and self.weights[0].shape[1] % 4 == 0:
             self.weights_lo[0] = ops.split_lo(self.weights[0].data)
+        self._lo_version = [w._version for w in self.weights]
         # replicas of the classifier gradients (GS_CLS_REPS=8, off by default): the top-layer kernel's 64+ CTAs spread
         # their atomic adds over them and the fused update folds them back in.  Measured: 0.8K of the kernel's 30K
         # cycles saved, the same again spent in the update kernel -- the adds are issue-bound, not contention-bound.
@@ -492,7 +495,18 @@ class SupervisedTrainer:
         if self.dp is not None and self.world_size > 1:
             self.dp.status()
 
+    def weights_changed(self):
+        """Call after writing the SageLayer weights from OUTSIDE the trainer (a checkpoint load): the low halves the
+        layer-1 GEMM reads beside them are recomputed.  In-place torch writes to the parameters themselves are noticed
+        through their version counters at the next step; writes through `.data` or raw pointers are not."""
+        for i, lo in enumerate(self.weights_lo):
+            if lo is not None:
+                ops.split_lo(self.weights[i].data, lo)
+            self._lo_version[i] = self.weights[i]._version
+
     def _count_steps(self, n: int = 1):
+        if any(lo is not None and w._version != v for lo, w, v in zip(self.weights_lo, self.weights, self._lo_version)):
+            self.weights_changed()
         self._steps_since_check += n
         if self.status_every and self.world_size > 1 and self._steps_since_check >= self.status_every:
             self.check()
@@ -791,6 +805,7 @@ class PipelinedTrainer(SupervisedTrainer):
                 self._pending += 1
         if self._cur is None:
             return None
+        self._count_steps(0)
         while self._pending > 0:
             if not self._agg_done:
                 self._aggregate(self._cur)

@@ -10,6 +10,8 @@ from graphsage_b200.peer import DpExchange
 from graphsage_b200.trainer import flat_layout
 dev = torch.device('cuda:0')
 shapes = [(128, 200), (128, 256), (47, 128), (47,)]
+if os.environ.get('DP_SHAPES') == 'cfg1':
+    shapes = [(128, 2866), (128, 256), (7, 128), (7,)]
 params = [torch.randn(s, device=dev) for s in shapes]
 offs, total = flat_layout(shapes)
 flat = torch.randn((total,), device=dev)

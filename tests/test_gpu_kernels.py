@@ -1,6 +1,8 @@
 """GPU: each kernel through the C ABI (ops.py -> libgsage_b200.so) against an independent CPU
 statement of the same operation.  Integer outputs are compared bit-exactly; fp32 outputs with
 the norm-relative 1e-5 bound of SURVEY.md §8(c)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -654,6 +656,49 @@ def test_classifier_weight_gradient_as_third_problem_of_the_group(g, dev, classe
     assert rel(gw2, out_dz[:n_live].double().t() @ X2) <= TOL
     assert rel(gcw, dlog[:n_live, :classes].double().t() @ hh) <= TOL
     assert torch.all(guard[classes * H:] == 7.0)
+
+
+_TMA_GEMM_CHECK = r"""
+import numpy as np, torch, sys
+sys.path.insert(0, %r)
+import graphsage_b200
+from graphsage_b200 import native, ops
+dev = torch.device('cuda:0')
+rng = np.random.default_rng(0)
+for (n_tab, rows, mx, dim, H, gcn, prec) in [(50000, 10500, 11264, 100, 128, False, native.PREC_TF32X3),
+                                              (3000, 300, 384, 128, 64, False, native.PREC_TF32X3),
+                                              (3000, 1000, 1000, 36, 128, True, native.PREC_TF32X3),
+                                              (3000, 700, 1024, 100, 128, False, native.PREC_TF32)]:
+    tab = torch.from_numpy(rng.standard_normal((n_tab, dim)).astype(np.float32)).to(dev)
+    sidx = torch.from_numpy(rng.integers(0, n_tab, size=mx).astype(np.int32)).to(dev)
+    agg = torch.from_numpy(rng.standard_normal((mx, dim)).astype(np.float32)).to(dev)
+    k = dim if gcn else 2 * dim
+    w = torch.from_numpy((rng.standard_normal((H, k)) * 0.1).astype(np.float32)).to(dev)
+    nr = torch.tensor([rows], dtype=torch.int32, device=dev)
+    X = (agg[:rows] if gcn else torch.cat([tab[sidx[:rows].long()], agg[:rows]], 1)).double()
+    want = torch.relu(X @ w.double().t())
+    for wl in (None, ops.split_lo(w)):
+        out = torch.zeros((mx, H), device=dev)
+        ops.sage_gemm_fwd(None if gcn else tab, sidx, agg, dim, w, H, gcn, nr, mx, relu=True, precision=prec, out=out, weight_lo=wl)
+        torch.cuda.synchronize()
+        err = float((out[:rows].double() - want).abs().max() / want.abs().max())
+        assert err <= (1e-5 if prec == native.PREC_TF32X3 else 3e-3), (dim, H, gcn, err)
+        assert rows == mx or float(out[rows:].abs().max()) == 0.0
+print('TMA_GEMM_OK')
+"""
+
+
+@pytest.mark.parametrize('self_mode', ['threads', 'gather4'])
+def test_forward_gemm_takes_the_tma_kernel_and_both_self_row_paths_agree_with_fp64(dev, self_mode):
+    """The gathered-operand forward GEMM of csrc/sage_gemm_tma.cu must be the kernel that runs for 16-byte-aligned
+    widths (GS_TMA_GATHER=2: a refusal is an error instead of a silent fall-back to the thread-staged kernel), with the
+    self rows fetched by the epilogue warps (default) or by TMA gather4, W_lo supplied or split in the kernel, gcn,
+    ragged tiles and a device-side row count.  The switches are read once per process, hence the subprocess."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, GS_TMA_GATHER='2', GS_TMA_SELF=self_mode)
+    r = subprocess.run([sys.executable, '-c', _TMA_GEMM_CHECK % root], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and 'TMA_GEMM_OK' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 def test_fused_sampler_unique_chain_equals_numpy(g, dev):
