@@ -1188,20 +1188,27 @@ def measure_agg_roofline(torch, ops, native, model, trainer, dev_batches, W, K, 
             traffic_src = "aggregate.cu changed since the ncu capture in profiles/agg_traffic.json: not quoted"
     except Exception:
         pass
-    ach = mean_bytes / t_in_step / 1e3
+    # With the prefetch off (the product default) nothing of the kernel's work happens outside it, and the kernel's average
+    # launch duration is the chain of the kernel alone, in the step's launch configuration (persistent grid, default
+    # L1/shared split), on distinct frontiers.  The difference of the [sampler, aggregation] and [sampler] chains is
+    # kept beside it: it also contains the launch gap between two DIFFERENT kernels, which a chain of one kernel hides
+    # (it grew from 13.1 to 14.8 us when the sampler alone got 1 us faster, with the aggregation kernel unchanged).
+    t_head = t_in_step if pf else t_agg
+    ach = mean_bytes / t_head / 1e3
     return {"bound": "hbm", "kernel": "agg_fwd_kernel<MEAN> (layer 1, gs_agg_fwd)", "achieved": ach, "peak": peak,
             "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-            "bytes_per_launch": mean_bytes, "us_per_launch": t_in_step, "launches_timed": n_iter,
+            "bytes_per_launch": mean_bytes, "us_per_launch": t_head, "launches_timed": n_iter,
             "how": ("in-step configuration: graph-replayed chain of [layer-1 sampler with L2 prefetch of the drawn rows, "
                     "aggregation] minus the chain of the sampler alone" if pf else
-                    "graph-replayed chain of [layer-1 sampler, aggregation] minus the chain of the sampler alone (prefetch off)"),
-            "us_sampler_with_prefetch": t_samp, "us_sampler_without_prefetch": t_samp_np, "us_pair": t_pair,
-            "without_prefetch": {"us_per_launch": t_agg, "achieved": mean_bytes / t_agg / 1e3, "frac": mean_bytes / t_agg / 1e3 / peak,
-                                 "note": "chain of the aggregation kernel alone: every gathered row comes from DRAM inside the kernel"},
+                    "in-step configuration (persistent grid, default carveout, sampler prefetch off): CUDA events around a "
+                    "graph-replayed chain of the kernel on distinct frontiers, every gathered row fetched from DRAM inside it"),
+            "behind_sampler": {"us_pair": t_pair, "us_sampler": t_samp, "us_sampler_without_prefetch": t_samp_np,
+                               "us_per_launch": t_in_step, "frac": mean_bytes / t_in_step / 1e3 / peak,
+                               "note": "chain of [layer-1 sampler, aggregation] minus the chain of the sampler alone: includes "
+                                       "the launch gap between two different kernels"},
+            "kernel_alone": {"us_per_launch": t_agg, "achieved": mean_bytes / t_agg / 1e3, "frac": mean_bytes / t_agg / 1e3 / peak},
             "saturating_size": big,
-            "note": "achieved = algorithmic bytes / kernel time; with the sampler's prefetch part of the DRAM fetch of those "
-                    "bytes is issued before the kernel starts (it overlaps the launch gap and the ramp), so DRAM traffic "
-                    "INSIDE the kernel is below the algorithmic bytes -- `without_prefetch` is the kernel on its own"}
+            "note": "achieved = algorithmic bytes (SURVEY.md 8d: nnz*D*4 + R*D*4 + nnz*4 + (R+1)*4 of the batch) / kernel time"}
 
 
 def measure_gemm_roofline(torch, ops, native, model, trainer, dev_batches, W, K, dev):
@@ -1237,7 +1244,9 @@ def measure_gemm_roofline(torch, ops, native, model, trainer, dev_batches, W, K,
     t_fwd = _chain_us(torch, dev, [(lambda l=l, g=g: fwd(l, g)) for l, g in fronts])
     products = 3 if prec == native.PREC_TF32X3 else 1
     useful = float(np.mean(flops)) / t_fwd / 1e6          # TFLOP/s
-    out = {"bound": "tensor", "kernel": ("sage_fwd_tma_kernel" if getattr(trainer, "dense_x1", False) else "sage_fwd_tc_kernel") +
+    tma_gather = os.environ.get("GS_TMA_GATHER", "1") != "0" and d % 4 == 0 and H % 16 == 0 and H <= 128
+    out = {"bound": "tensor", "kernel": ("sage_fwd_tma_kernel" if getattr(trainer, "dense_x1", False) else
+                                         "sage_fwd_tma_gather_kernel" if tma_gather else "sage_fwd_tc_kernel") +
            " (layer 1 forward, gs_sage_gemm_fwd_ex)", "unit": "TFLOP/s", "achieved": useful, "achieved_issued": useful * products,
            "peak": tf32_peak, "peak_source": f"{src} / 2 (kind::tf32 runs at half the bf16 rate)", "frac": useful / tf32_peak,
            "frac_issued": useful * products / tf32_peak, "products_per_mac": products, "flop_per_launch": float(np.mean(flops)),
