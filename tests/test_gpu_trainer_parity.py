@@ -194,9 +194,26 @@ def test_pipelined_multi_step_graph_matches_the_oracle(world):
     assert tr_b._cur == 0
     loss_b = float(tr_b.run(3).item())
     torch.cuda.synchronize()
-    assert abs(loss_b - loss_a) <= 1e-5 * abs(loss_a)
-    for pa, pb in zip(list(model_a.parameters()) + list(cls_a.parameters()), list(model_b.parameters()) + list(cls_b.parameters())):
-        assert rel(pb, pa) <= 2e-6
+    err = max(rel(pb, pa) for pa, pb in zip(list(model_a.parameters()) + list(cls_a.parameters()),
+                                             list(model_b.parameters()) + list(cls_b.parameters())))
+    err_loss = abs(loss_b - loss_a) / abs(loss_a)
+    if err > 2e-6 or err_loss > 1e-5:
+        # Two runs of the same steps are not bit-identical (the weight gradients and the scatter accumulate with fp32
+        # atomics), and a hidden unit whose pre-activation lies within those last bits of zero can fall on either side
+        # of the ReLU in one of them -- the excuse the oracle comparison has too (_OracleLoop.relu_flips).  It has to be
+        # PROVEN: some gate of the three steps differs between the runs, every differing gate sits at rounding distance
+        # from zero, and the deviation stays within the bound the golden tests use for that case.
+        flips = 0
+        for s in range(3):                                   # slot s = step s in both runs
+            for la, lb in zip(tr_a.slot_layers[s], tr_b.slot_layers[s]):
+                rows = la.rows_max if la.num_rows is None else int(la.num_rows.item())
+                ha, hb = la.h[:rows, :HIDDEN], lb.h[:rows, :HIDDEN]
+                differ = (ha > 0) != (hb > 0)
+                flips += int(differ.sum())
+                if bool(differ.any()):
+                    assert float(torch.maximum(ha.abs(), hb.abs())[differ].max()) <= 1e-5
+        assert flips > 0, (err, err_loss, 'no ReLU gate differs between the runs: the deviation is a real one')
+        assert err <= 5e-3 and err_loss <= 5e-3, (err, err_loss, flips)
 
 
 def test_consecutive_preps_draw_with_distinct_philox_offsets(world):
