@@ -23,6 +23,7 @@ static std::mutex g_carve_mu;
 static const void* g_carve_seen[256];
 static int g_carve_n = 0;
 static int g_background = 0;            // gs_set_background
+static int g_early_reads = 0;           // gs_set_early_reads
 
 static bool carveout_enabled() {
   static int enabled = -1;
@@ -51,9 +52,12 @@ void set_kernel_carveout(const void* kernel, bool max_shared) {
                        max_shared ? cudaSharedmemCarveoutMaxShared : cudaSharedmemCarveoutDefault);
 }
 bool background_launches() { return g_background != 0; }
+bool early_reads() { return g_early_reads != 0; }
 }
 
 extern "C" void gs_set_background(int32_t on) { gs::g_background = on ? 1 : 0; }
+
+extern "C" void gs_set_early_reads(int32_t on) { gs::g_early_reads = on ? 1 : 0; }
 
 extern "C" void gs_set_pdl(int32_t mode) { gs::g_pdl_override = mode < 0 ? -1 : (mode ? 1 : 0); }
 

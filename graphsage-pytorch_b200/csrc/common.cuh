@@ -31,6 +31,12 @@ __device__ __forceinline__ void pdl_sync() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
+// The two halves on their own, for a kernel that reads some inputs BEFORE it waits.  Every kernel of the library lets
+// its successor in at its own start, so a whole chain of launches can be resident and waiting: an early read is only
+// safe for data whose producer is ordered before the chain by a FULL dependency (another stream's event, a host
+// synchronisation) -- never for anything a kernel of the same stream wrote with programmatic launches in between.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // Every kernel of the library asks for the maximum shared-memory carveout, whether it uses shared memory
 // or not.  An SM can only hold CTAs that agree on its L1/shared split: a CTA that needs a different split
@@ -44,6 +50,7 @@ void prefer_max_smem(const void* kernel);      // api.cu; once per kernel functi
 // they ask for it only when launched as background work of a two-branch step (gs_set_background).
 void set_kernel_carveout(const void* kernel, bool max_shared);
 bool background_launches();
+bool early_reads();          // gs_set_early_reads: index lists / row counts may be read before the PDL wait
 
 template <typename... KArgs, typename... Args>
 inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

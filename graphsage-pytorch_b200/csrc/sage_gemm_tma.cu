@@ -286,6 +286,7 @@ __device__ __forceinline__ float4 tf32_lo4(float4 v) {
 struct GatherArgs {
   const int32_t* self_idx; int dim, ks_self, ks_agg, has_wlo;
   const float* self_table; int64_t ld_self; int self_by_threads;     // see the kernel: who fetches the self half
+  int early_idx;                                                     // gs_set_early_reads at launch time
 };
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes));
@@ -323,8 +324,7 @@ sage_fwd_tma_gather_kernel(const __grid_constant__ CUtensorMap tm_self, const __
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(&s_tmem), tmem_cols);
-  pdl_sync();
-  if (threadIdx.x == 0) GS_TMA_MARK(1);
+  if (!ga.early_idx) pdl_sync();    // gs_set_early_reads: the row count and the index list may be read before the wait
   const int rows = live_rows(a.num_rows_dev, a.max_rows);
   if (warp == 0 && row0 < rows) {   // the tile's table rows (rows past the live ones read row 0: their results are dropped)
 #pragma unroll
@@ -333,6 +333,8 @@ sage_fwd_tma_gather_kernel(const __grid_constant__ CUtensorMap tm_self, const __
       s_idx[lane + 32 * i] = r < rows ? (ga.self_idx ? __ldg(ga.self_idx + r) : r) : 0;
     }
   }
+  if (ga.early_idx) pdl_sync();
+  if (threadIdx.x == 0) GS_TMA_MARK(1);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -600,7 +602,8 @@ int gs_sage_gemm_fwd_tma_gather(const float* self_table, int64_t ld_self, const 
   const int smem = (stages * stage > staging ? stages * stage : staging) + 1024;
   const int ks_half = (dim + tma::kBK - 1) / tma::kBK;
   static const int by_threads = [] { const char* e = getenv("GS_TMA_SELF"); return (e && e[0] == 'g') ? 0 : 1; }();   // GS_TMA_SELF=gather4: A/B runs
-  tma::GatherArgs ga{self_idx, dim, gcn ? 0 : ks_half, ks_half, (split3 && w_lo) ? 1 : 0, self_table, ld_self, by_threads};
+  tma::GatherArgs ga{self_idx, dim, gcn ? 0 : ks_half, ks_half, (split3 && w_lo) ? 1 : 0, self_table, ld_self, by_threads,
+                     early_reads() ? 1 : 0};
   tma::Args a{num_rows_dev, max_rows, out, ld_out, out_dim, relu, zero_out, ld_zero, n_tile, ga.ks_self + ga.ks_agg, stages};
   const dim3 grid((max_rows + tma::kTileM - 1) / tma::kTileM);
   cudaError_t e;

@@ -63,6 +63,7 @@ struct Params {
   float* cls_w_rep; float* cls_b_rep; int cls_reps;       // replicas 1..cls_reps-1 of the classifier gradients (see P4c)
   float* grad_table; int64_t ld_gt;
   float* partials; unsigned int* ticket;
+  int early_lists;                                        // gs_set_early_reads at launch time
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -163,8 +164,11 @@ template <bool GCN, bool SPLIT3>
 __global__ void __maxnreg__(72)
 sage_top_sup_kernel(const Params p, const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_wc) {
   GS_TOP_MARK(0);
-  pdl_sync();
-  GS_TOP_MARK(1);
+  // With gs_set_early_reads the wait for the previous kernels of the stream comes LATE: the index lists and labels of
+  // the first tile are read before it (in a pipelined train step they come from the preparation branch, which the
+  // step's first kernel waits for with a full dependency -- common.cuh: pdl_wait).  Weights, bias and the rows of the
+  // layer below are always read after it.
+  if (!p.early_lists) pdl_sync();
   extern __shared__ unsigned char smem_raw[];
   using S = Smem<GCN>;
   // the TMA boxes (first members) need 1024-byte alignment; the launch asks for 1 KB of slack
@@ -179,19 +183,6 @@ sage_top_sup_kernel(const Params p, const __grid_constant__ CUtensorMap tmap_w, 
   const float inv_rows = 1.0f / static_cast<float>(rows > 0 ? rows : 1);
   float loss_part = 0.f;                                  // this thread's share of -sum logp[y] / rows
   bool weights_pending = static_cast<int>(blockIdx.x) < tiles;
-
-  if (tid < kMaxClasses) s.bias[tid] = (tid < C && p.cls_b) ? __ldg(p.cls_b + tid) : 0.f;   // visible after the first barrier
-  if (weights_pending && tid == 0) {
-    // W and Wc -> shared memory: K/32 + 4 tiled bulk copies, landing while the first tile is gathered
-    const uint32_t bar = smem_u32(&s.bar);
-    mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    mbar_expect_tx(bar, static_cast<uint32_t>((K / 32) * kWBox + (kH / 32) * kWcBox));
-#pragma unroll
-    for (int b = 0; b < K / 32; ++b) tma_load_2d(smem_u32(s.w + b * kWBox), &tmap_w, 32 * b, 0, bar);
-#pragma unroll
-    for (int b = 0; b < kH / 32; ++b) tma_load_2d(smem_u32(s.wc + b * kWcBox), &tmap_wc, 32 * b, 0, bar);
-  }
 
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int row0 = tile * kTM;
@@ -208,6 +199,22 @@ sage_top_sup_kernel(const Params p, const __grid_constant__ CUtensorMap tmap_w, 
     } else if (tid < kTM * kMaxStride + 2 * kTM) {
       const int r = tid - kTM * kMaxStride - kTM, row = row0 + r;
       s.label[r] = row < rows ? static_cast<int>(__ldg(p.labels + (p.label_index ? __ldg(p.label_index + row) : row))) : -1;
+    }
+    if (tile == static_cast<int>(blockIdx.x)) {           // first tile: from here on, data the previous kernels wrote
+      if (p.early_lists) { pdl_wait(); pdl_trigger(); }
+      GS_TOP_MARK(1);
+      if (tid < kMaxClasses) s.bias[tid] = (tid < C && p.cls_b) ? __ldg(p.cls_b + tid) : 0.f;   // visible after the first barrier
+      if (weights_pending && tid == 0) {
+        // W and Wc -> shared memory: K/32 + 4 tiled bulk copies, landing while the first tile is gathered
+        const uint32_t bar = smem_u32(&s.bar);
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(bar, static_cast<uint32_t>((K / 32) * kWBox + (kH / 32) * kWcBox));
+    #pragma unroll
+        for (int b = 0; b < K / 32; ++b) tma_load_2d(smem_u32(s.w + b * kWBox), &tmap_w, 32 * b, 0, bar);
+    #pragma unroll
+        for (int b = 0; b < kH / 32; ++b) tma_load_2d(smem_u32(s.wc + b * kWcBox), &tmap_wc, 32 * b, 0, bar);
+      }
     }
     __syncthreads();
     GS_TOP_MARK(2);
@@ -496,6 +503,7 @@ sage_top_sup_kernel(const Params p, const __grid_constant__ CUtensorMap tmap_w, 
     GS_TOP_MARK(9);
   }
 
+  if (p.early_lists) pdl_wait();                          // (a CTA without a tile has not waited yet; the workspace is shared with the previous launch)
   // ---- loss: per-CTA partial, the last CTA to finish adds them up in CTA order (deterministic, nothing to zero) ----
   loss_part = warp_sum(loss_part);
   if (lane == 0) s.red[warp] = loss_part;
@@ -557,7 +565,7 @@ extern "C" int gs_sage_top_sup(const float* table, int64_t ld_table, const int32
   top::Params p{table, ld_table, nbr_idx, stride, cnt, self_idx, num_rows_dev, max_rows, weight, ldw, cls_w, cls_b,
                 num_classes, labels, label_index, out_h, ld_h, out_agg, ld_agg, out_dz, ld_dz, out_dlog, ld_dlog, logp, loss, grad_cls_w,
                 grad_cls_b, cls_w_replicas, cls_b_replicas, cls_reps, grad_table, ld_gt, reinterpret_cast<float*>(workspace) + 4,
-                reinterpret_cast<unsigned int*>(workspace)};
+                reinterpret_cast<unsigned int*>(workspace), early_reads() ? 1 : 0};
   int tiles = (max_rows + top::kTM - 1) / top::kTM;
   // one tile per CTA while the tiles fit one wave; beyond that a persistent grid (W stays in shared memory)
   int grid = tiles <= kNumSMs ? tiles : kNumSMs;

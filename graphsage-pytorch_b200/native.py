@@ -21,7 +21,7 @@ SELF_KEEP, SELF_DROP, SELF_ONCE = 0, 1, 2
 PREC_FP32, PREC_TF32, PREC_TF32X3 = 0, 1, 2
 MAX_FANOUT = 32
 UNIQUE_MARKED, UNIQUE_LEAVE_MARKS = 1, 2
-ABI_VERSION = 15
+ABI_VERSION = 16
 
 _P, _I, _L, _F, _U64, _SZ = c_void_p, c_int32, c_int64, c_float, c_uint64, c_size_t
 
@@ -44,6 +44,7 @@ _SIGNATURES = {
     "gs_debug_stamp": (_I, [_P, _P]),
     "gs_set_agg_ctas": (None, [_I]),
     "gs_set_background": (None, [_I]),
+    "gs_set_early_reads": (None, [_I]),
     "gs_agg_bwd": (_I, [_P, _L, _P, _L, _I, _P, _I, _P, _P, _P, _L, _P, _I, _I, _P, _L, _P, _L, _P]),
     "gs_sage_gemm_fwd": (_I, [_P, _L, _P, _P, _L, _I, _P, _L, _I, _I, _P, _I, _P, _L, _I, _I, _P]),
     "gs_sage_gemm_fwd_ex": (_I, [_P, _L, _P, _P, _L, _I, _P, _L, _I, _I, _P, _I, _P, _L, _I, _I, _P, _L, _P, _P, _I, _P]),
@@ -162,6 +163,12 @@ def set_agg_ctas(ctas_per_sm: int) -> None:
 def set_background(on: bool) -> None:
     """Mark subsequent launches as background work of a two-branch step (see gs_set_background)."""
     load().gs_set_background(int(bool(on)))
+
+
+def set_early_reads(on: bool) -> None:
+    """Let subsequent launches read their index inputs before the PDL wait (see gs_set_early_reads for when that is
+    correct: the inputs must come from another stream joined by an event, not from the launch chain itself)."""
+    load().gs_set_early_reads(int(bool(on)))
 
 
 def check(code: int, what: str) -> None:

@@ -566,6 +566,8 @@ class PipelinedTrainer(SupervisedTrainer):
         self.slot_seeds = [torch.zeros((self.b_sz,), dtype=torch.int32, device=dev) for _ in range(self.SLOTS)]
         self.slot_layers = [None] * self.SLOTS
         self.slot_loss = torch.zeros((self.SLOTS,), dtype=torch.float32, device=dev)
+        self._chain_fence = torch.zeros((1,), dtype=torch.float32, device=dev)      # see _both
+        self.early_reads = os.environ.get("GS_EARLY_READS", "1") != "0"                   # A/B switch, see _compute
         self.sample_counter = torch.zeros((1,), dtype=torch.int64, device=dev)
         self.queue_desc = torch.zeros((4,), dtype=torch.int64, device=dev)        # {address, rows, next, ticket}
         self._queue = None
@@ -687,10 +689,17 @@ class PipelinedTrainer(SupervisedTrainer):
     def _aggregate(self, slot: int):
         self.model._run_agg1(self.slot_layers[slot], dense_x=self.dense_x1)
 
-    def _compute(self, slot: int, update: bool = True):
+    def _compute(self, slot: int, update: bool = True, early: bool = False):
         # the loss of the batch trained from slot s lands in slot_loss[s]: the three steps of a multi-step graph
         # launch leave three losses behind (run() points self.loss at the last one)
-        self._train_on(self.slot_layers[slot], self.slot_seeds[slot], loss_out=self.slot_loss[slot:slot + 1])
+        # early (from _both only): the frontiers' index lists and row counts come from the preparation branch --
+        # another stream, joined by an event -- so the kernels of the training chain may read them before their PDL
+        # wait (gs_set_early_reads); never when the lists were written by launches of THIS stream just before
+        native.set_early_reads(early and self.early_reads)
+        try:
+            self._train_on(self.slot_layers[slot], self.slot_seeds[slot], loss_out=self.slot_loss[slot:slot + 1])
+        finally:
+            native.set_early_reads(False)
         if update:
             self.dp.update(self.max_norm, self.lr, None)
 
@@ -702,6 +711,11 @@ class PipelinedTrainer(SupervisedTrainer):
     def _both(self, slot: int, update: bool = True):
         """train on `slot` | aggregate slot+1, sample into slot+2 -- a fork/join, eagerly or under capture"""
         main = torch.cuda.current_stream()
+        if not torch.cuda.is_current_stream_capturing():
+            # Eager calls may follow launches of this stream that wrote the frontiers (prime(), the warm-up).  A launch
+            # WITHOUT the programmatic attribute is a full barrier in the chain: everything before it has completed
+            # before anything after it is scheduled.  (Captured: the graph launch / the join edges are that barrier.)
+            self._chain_fence.add_(0)
         self._prep_stream.wait_stream(main)
         try:
             with torch.cuda.stream(self._prep_stream):
@@ -714,10 +728,10 @@ class PipelinedTrainer(SupervisedTrainer):
             if self._train_stream is not None:            # the critical chain on a high-priority stream (fork/join)
                 self._train_stream.wait_stream(main)
                 with torch.cuda.stream(self._train_stream):
-                    self._compute(slot, update)
+                    self._compute(slot, update, early=True)
                 main.wait_stream(self._train_stream)
             else:
-                self._compute(slot, update)
+                self._compute(slot, update, early=True)
         finally:
             self._background(False)
         main.wait_stream(self._prep_stream)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GS_ABI_VERSION 15
+#define GS_ABI_VERSION 16
 
 #define GS_OK 0
 #define GS_ERR_BAD_ARG (-1)
@@ -160,6 +160,14 @@ void gs_set_agg_ctas(int32_t ctas_per_sm);
  * shared-memory carveout so that CTAs of both branches can share an SM; the K3 forward kernel, whose HBM
  * throughput needs the L1 that carveout removes, does so only while this switch is on. */
 void gs_set_background(int32_t on);
+/* Process-wide switch like gs_set_pdl: launches issued while it is on may read their INDEX inputs (neighbour / self
+ * index lists, labels and label_index, num_rows_dev) before they wait for the previous kernels of the stream, so that
+ * those loads run under the tail of the predecessor (programmatic dependent launch lets a whole chain of launches be
+ * resident and waiting).  Only correct when those inputs were produced before the chain began: by another stream joined
+ * with an event (trainer.PipelinedTrainer's preparation branch), by a host-synchronised copy, or by a launch without
+ * the attribute.  Off by default: every kernel waits first.  Honoured by gs_sage_top_sup and by the TMA-fed
+ * gs_sage_gemm_fwd_ex. */
+void gs_set_early_reads(int32_t on);
 int gs_agg_fwd(const float* table, int64_t ld, int32_t dim,
                const int32_t* nbr, int32_t stride, const int32_t* cnt,
                const int32_t* num_rows_dev, int32_t max_rows, int32_t mode,
@@ -333,6 +341,8 @@ int gs_cls_nll_fwd_bwd(const float* emb, int64_t ld_emb, int32_t rows, int32_t d
  * grad_cls_w / grad_cls_b, replica r > 0 is cls_w_replicas + (r-1)*num_classes*128 and cls_b_replicas + (r-1)*64 (both
  * zeroed by the caller; gs_dp_allreduce_clip_sgd folds them in and clears them, see seg_extra_host): 64 CTAs adding into
  * one block serialise in the L2 atomic units otherwise.
+ * With gs_set_early_reads(1) the index lists, labels and row count are read before the wait for the previous kernels
+ * of the stream (see there for when that is allowed).
  * workspace: gs_sage_top_workspace_bytes() of device memory, zeroed ONCE by the caller (loss partials + a ticket
  * that every launch leaves at zero again); loss[0] is overwritten, nothing needs zeroing per step.
  * ------------------------------------------------------------------------------------ */
