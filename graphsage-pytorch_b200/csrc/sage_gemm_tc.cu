@@ -515,7 +515,7 @@ template <bool A_MN, bool B_MN, bool SPLIT3, bool ASYNC, class LoadA, class Load
 __device__ __forceinline__ void gemm_core(const LoadA& load_a, const LoadB& load_b, const Epi& epi, int n_tile,
                                           int k_stages, int num_stages, unsigned char* smem, const void* gdummy,
                                           const CUtensorMap* tmap_b = nullptr, int tma_b_row = 0, int tma_b_box_rows = 0,
-                                          int l2norm = 0) {
+                                          int l2norm = 0, bool late_pdl = false) {
   // l2norm (forward only, n_tile == 128 == the whole output row): rows leave as relu(acc) / max(||relu(acc)||_2, 1e-12)
   // tmap_b != nullptr (K-major B only): the B tile of k-stage ks is the TMA box {32 k from 32*ks, tma_b_box_rows
   // rows from tma_b_row}; the producers only split it (hi/lo) once it has landed
@@ -549,6 +549,7 @@ __device__ __forceinline__ void gemm_core(const LoadA& load_a, const LoadB& load
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = s_tmem;
+  if (late_pdl) pdl_sync();                        // the caller has read nothing the previous kernels wrote so far
   GS_TRACE(1);
 
   if (warp < kProducerWarps) {
@@ -845,6 +846,7 @@ struct BwdWProblem {
   XView x; const float* grad_out; int64_t ld_go; const float* out; int64_t ld_out; int out_dim, out_rows, relu;
   const int32_t* num_rows_dev; int max_rows, rows_per_chunk; float* grad_w; int64_t ldw; int n_tile, num_stages;
   int tiles_x, tiles_y, chunks;
+  int early;                 // gs_set_early_reads at launch time: row count and index list are read before the PDL wait
 };
 
 // The grid's z axis runs over the row chunks of problem A, then those of problem B, then those of problem C (chunks == 0:
@@ -855,7 +857,7 @@ template <bool SPLIT3, bool ASYNC>
 __global__ void __maxnreg__(kMaxRegs)
 sage_bwd_w_tc_kernel(const __grid_constant__ BwdWProblem pa, const __grid_constant__ BwdWProblem pb,
                      const __grid_constant__ BwdWProblem pc) {
-  pdl_sync();
+  if (!pa.early) pdl_sync();   // else: after the setup inside gemm_core (row count and index cache are read early)
   extern __shared__ unsigned char smem_dyn[];
   const int z = blockIdx.z;
   const int which = z < pa.chunks ? 0 : (z < pa.chunks + pb.chunks ? 1 : 2);
@@ -875,7 +877,8 @@ sage_bwd_w_tc_kernel(const __grid_constant__ BwdWProblem pa, const __grid_consta
   LoadDZ_MN la{q.grad_out, q.ld_go, q.out, q.ld_out, r_begin, r_end, h0, q.out_dim, q.relu};
   LoadX_MN lb{x, r_begin, r_end, kv0};
   AddDW epi{x, q.grad_w, q.ldw, h0, q.out_rows, kv0};
-  gemm_core<true, true, SPLIT3, ASYNC>(la, lb, epi, nt, k_stages, q.num_stages, smem_dyn, q.grad_out);
+  gemm_core<true, true, SPLIT3, ASYNC>(la, lb, epi, nt, k_stages, q.num_stages, smem_dyn, q.grad_out, nullptr, 0, 0, 0,
+                                       pa.early != 0);
 }
 
 struct Plan { int n_tile, num_stages, smem; };
@@ -1055,7 +1058,7 @@ int gs_sage_gemm_bwd_w_tc(const float* self_table, int64_t ld_self, const int32_
   BwdWProblem pa{};
   pa.x = XView{self_table, ld_self, self_idx, agg, ld_agg, dim, (dim + 3) & ~3, gcn, nullptr, 0, 0};
   pa.grad_out = grad_out; pa.ld_go = ld_go; pa.out = out; pa.ld_out = ld_out; pa.out_dim = out_dim; pa.out_rows = out_dim;
-  pa.relu = relu;
+  pa.relu = relu; pa.early = early_reads() ? 1 : 0;
   pa.num_rows_dev = num_rows_dev; pa.max_rows = max_rows; pa.grad_w = grad_w; pa.ldw = ldw;
   const int kt = gcn ? pa.x.dim_pad : 2 * pa.x.dim_pad;
   const int smem = plan_bwd_w(pa, kt, out_dim, max_rows, split3, kNumSMs);
@@ -1085,7 +1088,7 @@ int gs_sage_gemm_bwd_w_group_tc(int32_t n, const float* const* self_table, const
     pr[i].grad_out = grad_out[i]; pr[i].ld_go = ld_go[i]; pr[i].out = out[i]; pr[i].ld_out = ld_out[i];
     pr[i].out_dim = cols; pr[i].out_rows = out_dim[i]; pr[i].relu = relu[i];
     pr[i].num_rows_dev = num_rows_dev[i]; pr[i].max_rows = max_rows[i];
-    pr[i].grad_w = grad_w[i]; pr[i].ldw = ldw[i];
+    pr[i].grad_w = grad_w[i]; pr[i].ldw = ldw[i]; pr[i].early = early_reads() ? 1 : 0;
     kt[i] = gcn[i] ? pr[i].x.dim_pad : 2 * pr[i].x.dim_pad;
     const bool a = bwd_w_async_ok(grad_out[i], ld_go[i], cols, relu[i]);
     if (i == 0) async0 = a;
