@@ -19,6 +19,9 @@
 // smallest tcgen05 tile; W (128 KB) sits in shared memory for both contractions.  Everything else is fp32 FFMA.
 // The ReLU gates of the gathered rows are kept as bits in registers from the gather to the scatter, so the table is
 // read once.  The loss is reduced without atomics on floats (per-CTA partials, last CTA sums them in a fixed order).
+// Two options the trainers use: out_dlog -- d(logits) is saved and grad Wc = dlog^T . h is left to the grouped
+// weight-gradient launch (64 CTAs adding into one [C x 128] block cost each of them 3.5-4.4K cycles here); and
+// gs_set_early_reads -- the tile's index lists and labels are loaded before the wait for the previous kernel.
 #include <cuda.h>
 #include <string.h>
 
